@@ -1,0 +1,156 @@
+/*
+ * ungar_b200 — C ABI of the B200-native batched derivative-evaluation engine for Ungar NMPC problems.
+ *
+ * This is the drop-in boundary.  In the reference (fdevinc/ungar @ db9cc70) the derivative path sits
+ * behind `CppAD::cg::GenericModel<double>` over a JIT-compiled, dlopen'ed C library
+ * (include/ungar/autodiff/function.hpp:364-365, :433-438, :505-514).  Each entry point below names the
+ * reference call it replaces.  The reference evaluates ONE flat vector xp = [x; p] per call on one CPU
+ * core; every entry point here takes `batch` such vectors (stride `ld_xp` scalars) and evaluates all of
+ * them on the GPU.  `batch = 1` with `UNGAR_B200_MEM_HOST` reproduces the reference call exactly.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; no C++ or torch types cross this boundary;
+ *   - every function returns a status code (0 = success) and never throws; the message of the last
+ *     failure on the calling thread is available from ungar_b200_last_error()
+ *     (the reference aborts via UNGAR_ASSERT, include/ungar/assert.hpp:97-108, or throws
+ *     std::runtime_error, function.hpp:531-534);
+ *   - buffers are in the model's dtype (float for F32, double for F64), owned by the caller;
+ *   - with UNGAR_B200_MEM_DEVICE the pointers are device pointers and the call is asynchronous on
+ *     `stream` (a cudaStream_t passed as void*; NULL = legacy default stream);
+ *     with UNGAR_B200_MEM_HOST the pointers are host pointers, the library stages them through its own
+ *     device buffers (H2D, kernels, D2H on `stream`) and returns after the results have landed;
+ *   - a model handle is immutable after creation except for its internal workspaces: calls on one handle
+ *     must be issued from one thread at a time (the reference's Function is not re-entrant either:
+ *     function.hpp:380-383).
+ *   - there is NO CPU fallback: every compute entry point fails with UNGAR_B200_ECUDA when no CUDA
+ *     device is usable.
+ */
+#ifndef UNGAR_B200_H_
+#define UNGAR_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define UNGAR_B200_ABI_VERSION 1
+
+typedef struct ungar_b200_model ungar_b200_model;
+
+enum ungar_b200_status {
+    UNGAR_B200_OK           = 0,
+    UNGAR_B200_EINVAL       = 1, /* bad argument (sizes, null pointers, unknown enum) */
+    UNGAR_B200_ECUDA        = 2, /* CUDA runtime error or no device */
+    UNGAR_B200_ENOMEM       = 3,
+    UNGAR_B200_EUNSUPPORTED = 4  /* e.g. Hessian of a vector-valued function (function.hpp:136-137) */
+};
+
+/* The three NMPC problems of example/mpc/{quadrotor,rc_car,quadruped}.example.cpp. */
+enum ungar_b200_model_kind { UNGAR_B200_QUADROTOR = 0, UNGAR_B200_RC_CAR = 1, UNGAR_B200_QUADRUPED = 2 };
+
+/* The reference computes in double only (include/ungar/data_types.hpp:89); F32 is an addition. */
+enum ungar_b200_dtype { UNGAR_B200_F32 = 0, UNGAR_B200_F64 = 1 };
+
+/* The functions an Ungar NLP problem is made of (include/ungar/optimization/concepts.hpp:153-161) plus
+ * the barrier function SoftSQPOptimizer JIT-compiles for itself (optimization/soft_sqp.hpp:114-138):
+ * Zsoft(z) = sum_i b(-z_i), independent size m_ineq, no parameters. */
+enum ungar_b200_function {
+    UNGAR_B200_OBJECTIVE         = 0,
+    UNGAR_B200_EQUALITIES        = 1,
+    UNGAR_B200_INEQUALITIES      = 2,
+    UNGAR_B200_SOFT_INEQUALITIES = 3
+};
+
+enum ungar_b200_mem { UNGAR_B200_MEM_DEVICE = 0, UNGAR_B200_MEM_HOST = 1 };
+
+typedef struct ungar_b200_model_desc {
+    int32_t kind;    /* ungar_b200_model_kind */
+    int32_t horizon; /* N; the reference hard-codes 30 (quadrotor.example.cpp:52) */
+    int32_t dtype;   /* ungar_b200_dtype */
+    int32_t device;  /* CUDA device ordinal */
+    /* RelaxedPolyBarrierFunction{0, stiffness, epsilon} (optimization/soft_inequality_constraint.hpp:133-145);
+     * per example: quadrotor (100, 2e-5), rc_car (100, 1e-2), quadruped (1, 1). */
+    double barrier_stiffness;
+    double barrier_epsilon;
+} ungar_b200_model_desc;
+
+/* Replaces FunctionFactory::Make / MakeFunction (function.hpp:589-613): where the reference tapes,
+ * generates C, runs gcc and dlopens, this selects the hand-written sm_100a kernels of the model,
+ * derives the structural sparsity of its three functions and allocates device-side index tables. */
+int ungar_b200_model_create(const ungar_b200_model_desc* desc, ungar_b200_model** out);
+int ungar_b200_model_destroy(ungar_b200_model* model);
+
+/* Function::IndependentVariableSize / ParameterSize / DependentVariableSize (function.hpp:351-361) and
+ * the nnz counts the Function constructor derives (function.hpp:98-101, :138-140). */
+int ungar_b200_function_info(const ungar_b200_model* model, int32_t function, int64_t* independent_size,
+                             int64_t* parameter_size, int64_t* dependent_size, int64_t* nnz_jacobian,
+                             int64_t* nnz_hessian);
+
+/* GenericModel::JacobianSparsity(rows, cols) (function.hpp:103-105): row-major, rows ascending, columns
+ * ascending within a row, parameter columns trimmed (function.hpp:529-550).  The arrays belong to the
+ * handle. */
+int ungar_b200_jacobian_sparsity(const ungar_b200_model* model, int32_t function, const int64_t** rows,
+                                 const int64_t** cols, int64_t* nnz);
+
+/* GenericModel::HessianSparsity(0, rows, cols) (function.hpp:142-144): upper triangle of the x-x block
+ * (function.hpp:552-574); scalar functions only. */
+int ungar_b200_hessian_sparsity(const ungar_b200_model* model, int32_t function, const int64_t** rows,
+                                const int64_t** cols, int64_t* nnz);
+
+/* GenericModel::ForwardZero (function.hpp:186-189): y[b, :] = f(xp[b, :]). */
+int ungar_b200_forward_zero(ungar_b200_model* model, int32_t function, const void* xp, int64_t batch,
+                            int64_t ld_xp, void* y, int64_t ld_y, int32_t mem, void* stream);
+
+/* GenericModel::SparseJacobian (function.hpp:224-228): vals[b, :] = nonzeros of df/dx at xp[b, :] in the
+ * order of ungar_b200_jacobian_sparsity. */
+int ungar_b200_sparse_jacobian(ungar_b200_model* model, int32_t function, const void* xp, int64_t batch,
+                               int64_t ld_xp, void* vals, int64_t ld_vals, int32_t mem, void* stream);
+
+/* GenericModel::SparseHessian with a unit weight on dependent 0 (function.hpp:249-257): vals[b, :] =
+ * nonzeros of the upper-triangular Hessian in the order of ungar_b200_hessian_sparsity. */
+int ungar_b200_sparse_hessian(ungar_b200_model* model, int32_t function, const void* xp, int64_t batch,
+                              int64_t ld_xp, void* vals, int64_t ld_vals, int32_t mem, void* stream);
+
+/* Element offsets of the per-trajectory KKT block record written by ungar_b200_kkt_blocks
+ * (every array starts on a multiple of 4 elements; `size` is the record length = minimum ld_rec).
+ *   g    [m_eq]                 equality residuals, reference row order
+ *   A    [N][nx][nz]            A_k = d g_{dyn,k} / d [x_k; u_k]  (= -df/dz; d/dx_{k+1} = I is implicit)
+ *   C    [N][legs][4][20]       quadruped contact rows wrt [p_k q_k r_{k,i} | p_{k-1} q_{k-1} r_{k-1,i}]
+ *   h    [m_ineq]               inequality values
+ *   cost [2]                    objective f, barrier Zsoft(h)
+ *   grad [n_dec]                QP vector  q = grad f + J_h^T dZsoft        (soft_sqp.hpp:151-153)
+ *   H    [N][nz(nz+1)/2]        upper triangle (row-major packed) of the z_k-z_k block of
+ *                               P = grad^2 f + J_h^T d2Zsoft J_h + 1e-6 I   (soft_sqp.hpp:145-150)
+ *   HN   [nx(nx+1)/2]           the same for the terminal state x_N
+ *   Hc   [N-1][nu]              diagonal of the u_{k}-u_{k+1} coupling block (quadrotor, rc_car) */
+typedef struct ungar_b200_kkt_layout {
+    int64_t g, A, C, h, cost, grad, H, HN, Hc, size;
+    int64_t nx, nu, nz, horizon, n_dec, n_par, m_eq, m_ineq, tri, tri_terminal, legs, hc_per_node;
+} ungar_b200_kkt_layout;
+
+int ungar_b200_kkt_layout_get(const ungar_b200_model* model, ungar_b200_kkt_layout* out);
+
+/* Replaces one pass of SoftSQPOptimizer::AssembleOSQPInstance (soft_sqp.hpp:141-158, :236-264): every
+ * value, Jacobian block and Gauss-Newton Hessian block of every shooting node of every trajectory, in one
+ * sweep: records[b, :] laid out as ungar_b200_kkt_layout. */
+int ungar_b200_kkt_blocks(ungar_b200_model* model, const void* xp, int64_t batch, int64_t ld_xp,
+                          void* records, int64_t ld_rec, int32_t mem, void* stream);
+
+/* Per-trajectory summary (32 scalars: u_0 [nu<=24], cost f, barrier, |g|_inf, max h, pad) read back from
+ * the records — the payload of the one all-gather per outer iteration. */
+#define UNGAR_B200_SUMMARY_SIZE 32
+int ungar_b200_summaries(ungar_b200_model* model, const void* xp, int64_t batch, int64_t ld_xp,
+                         const void* records, int64_t ld_rec, void* summaries, void* stream);
+
+/* Number of kernel launches this library has issued in the calling process (bench accounting). */
+int64_t ungar_b200_launch_count(void);
+
+const char* ungar_b200_last_error(void);
+int32_t ungar_b200_abi_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+
+#endif /* UNGAR_B200_H_ */

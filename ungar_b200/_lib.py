@@ -1,0 +1,83 @@
+"""ctypes binding of the C ABI declared in include/ungar_b200.h (the only way Python reaches the kernels)."""
+from __future__ import annotations
+
+import ctypes
+import os
+
+from . import build as _build
+
+c_i32, c_i64, c_f64, c_vp = ctypes.c_int32, ctypes.c_int64, ctypes.c_double, ctypes.c_void_p
+c_i64_p = ctypes.POINTER(c_i64)
+
+OK, EINVAL, ECUDA, ENOMEM, EUNSUPPORTED = 0, 1, 2, 3, 4
+F32, F64 = 0, 1
+OBJECTIVE, EQUALITIES, INEQUALITIES, SOFT_INEQUALITIES = 0, 1, 2, 3
+MEM_DEVICE, MEM_HOST = 0, 1
+SUMMARY_SIZE = 32
+
+# every symbol include/ungar_b200.h declares (checked by tests/test_abi.py)
+SYMBOLS = [
+    "ungar_b200_model_create", "ungar_b200_model_destroy", "ungar_b200_function_info",
+    "ungar_b200_jacobian_sparsity", "ungar_b200_hessian_sparsity", "ungar_b200_forward_zero",
+    "ungar_b200_sparse_jacobian", "ungar_b200_sparse_hessian", "ungar_b200_kkt_layout_get",
+    "ungar_b200_kkt_blocks", "ungar_b200_summaries", "ungar_b200_launch_count", "ungar_b200_last_error",
+    "ungar_b200_abi_version",
+]
+
+
+class ModelDesc(ctypes.Structure):
+    _fields_ = [("kind", c_i32), ("horizon", c_i32), ("dtype", c_i32), ("device", c_i32),
+                ("barrier_stiffness", c_f64), ("barrier_epsilon", c_f64)]
+
+
+class KktLayout(ctypes.Structure):
+    _names = ["g", "A", "C", "h", "cost", "grad", "H", "HN", "Hc", "size", "nx", "nu", "nz", "horizon", "n_dec",
+              "n_par", "m_eq", "m_ineq", "tri", "tri_terminal", "legs", "hc_per_node"]
+    _fields_ = [(n, c_i64) for n in _names]
+
+    def as_dict(self) -> dict:
+        return {n: int(getattr(self, n)) for n in self._names}
+
+
+class UngarB200Error(RuntimeError):
+    def __init__(self, code: int, message: str):
+        super().__init__(f"ungar_b200 error {code}: {message}")
+        self.code = code
+
+
+_lib = None
+
+
+def load() -> ctypes.CDLL:
+    """Load (building if the sources are newer) the in-tree CUDA library.  Fails loudly if it is missing."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    path = _build.LIB
+    if not os.path.exists(path) or not _build.up_to_date():
+        try:
+            _build.build()
+        except Exception as exc:  # no nvcc on the box: use the prebuilt library if there is one
+            if not os.path.exists(path):
+                raise RuntimeError(f"ungar_b200: CUDA library missing and cannot be built: {exc}") from exc
+    L = ctypes.CDLL(path)
+    L.ungar_b200_model_create.argtypes = [ctypes.POINTER(ModelDesc), ctypes.POINTER(c_vp)]
+    L.ungar_b200_model_destroy.argtypes = [c_vp]
+    L.ungar_b200_function_info.argtypes = [c_vp, c_i32, c_i64_p, c_i64_p, c_i64_p, c_i64_p, c_i64_p]
+    for name in ("ungar_b200_jacobian_sparsity", "ungar_b200_hessian_sparsity"):
+        getattr(L, name).argtypes = [c_vp, c_i32, ctypes.POINTER(c_i64_p), ctypes.POINTER(c_i64_p), c_i64_p]
+    for name in ("ungar_b200_forward_zero", "ungar_b200_sparse_jacobian", "ungar_b200_sparse_hessian"):
+        getattr(L, name).argtypes = [c_vp, c_i32, c_vp, c_i64, c_i64, c_vp, c_i64, c_i32, c_vp]
+    L.ungar_b200_kkt_layout_get.argtypes = [c_vp, ctypes.POINTER(KktLayout)]
+    L.ungar_b200_kkt_blocks.argtypes = [c_vp, c_vp, c_i64, c_i64, c_vp, c_i64, c_i32, c_vp]
+    L.ungar_b200_summaries.argtypes = [c_vp, c_vp, c_i64, c_i64, c_vp, c_i64, c_vp, c_vp]
+    L.ungar_b200_launch_count.restype = c_i64
+    L.ungar_b200_last_error.restype = ctypes.c_char_p
+    L.ungar_b200_abi_version.restype = c_i32
+    _lib = L
+    return L
+
+
+def check(code: int) -> None:
+    if code != OK:
+        raise UngarB200Error(code, load().ungar_b200_last_error().decode())

@@ -1,0 +1,569 @@
+// C ABI of ungar_b200 (include/ungar_b200.h): model handles, structural sparsity, kernel launches.
+// No CPU fallback lives here: the only host-side arithmetic is the one-time structural analysis
+// (dependency masks -> CSR index arrays) at model_create.
+#include <atomic>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "../../include/ungar_b200.h"
+#include "sweep.cuh"
+
+namespace {
+
+thread_local std::string g_last_error;
+std::atomic<long long> g_launches{0};
+
+int fail(int code, const char* fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    g_last_error = buf;
+    return code;
+}
+
+#define UB_CUDA(call)                                                                              \
+    do {                                                                                           \
+        cudaError_t e_ = (call);                                                                   \
+        if (e_ != cudaSuccess)                                                                     \
+            return fail(UNGAR_B200_ECUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), \
+                        __FILE__, __LINE__);                                                       \
+    } while (0)
+
+struct DeviceBuffer {
+    void* ptr  = nullptr;
+    size_t cap = 0;
+    int reserve(size_t bytes) {
+        if (bytes <= cap) return UNGAR_B200_OK;
+        if (ptr) cudaFree(ptr);
+        ptr = nullptr;
+        cap = 0;
+        cudaError_t e = cudaMalloc(&ptr, bytes);
+        if (e != cudaSuccess) return fail(UNGAR_B200_ENOMEM, "cudaMalloc(%zu) failed: %s", bytes, cudaGetErrorString(e));
+        cap = bytes;
+        return UNGAR_B200_OK;
+    }
+    ~DeviceBuffer() {
+        if (ptr) cudaFree(ptr);
+    }
+};
+
+struct FunctionTables {
+    int64_t nx = 0, np = 0, ny = 0;
+    std::vector<int64_t> jac_rows, jac_cols, hes_rows, hes_cols;
+    std::vector<int32_t> y_src, jac_src, hes_src;  // record offsets (>= 0) or constants (-1: 1, -2: 0)
+    int32_t *d_y_src = nullptr, *d_jac_src = nullptr, *d_hes_src = nullptr;
+    bool has_hessian = false;
+};
+
+}  // namespace
+
+struct ungar_b200_model {
+    ungar_b200_model_desc desc{};
+    int N = 0;
+    ungar_b200_kkt_layout layout{};
+    ub::RecLayout rl{};
+    ub::BarrierCoef<double> bar{};
+    FunctionTables fn[4];
+    DeviceBuffer stage_cost, ws_records, ws_xp, ws_out;
+    size_t elem = 8;
+};
+
+namespace {
+
+using ub::Dep;
+
+// ---------------------------------------------------------------------------------------------
+// Layout
+// ---------------------------------------------------------------------------------------------
+int64_t round4(int64_t x) { return (x + 3) & ~int64_t(3); }
+
+template <class Mdl>
+void make_layout(int N, ungar_b200_kkt_layout& L) {
+    L.nx = Mdl::NX; L.nu = Mdl::NU; L.nz = Mdl::NZ; L.horizon = N;
+    L.n_dec = Mdl::n_dec(N); L.n_par = Mdl::n_par(N); L.m_eq = Mdl::m_eq(N); L.m_ineq = int64_t(Mdl::NH) * N;
+    L.tri = int64_t(Mdl::NZ) * (Mdl::NZ + 1) / 2; L.tri_terminal = int64_t(Mdl::NX) * (Mdl::NX + 1) / 2;
+    L.legs = Mdl::LEGS; L.hc_per_node = Mdl::HC ? Mdl::NU : 0;
+    int64_t off = 0;
+    L.g = off;    off = round4(off + L.m_eq);
+    L.A = off;    off = round4(off + N * L.nx * L.nz);
+    L.C = off;    off = round4(off + N * L.legs * 80);
+    L.h = off;    off = round4(off + L.m_ineq);
+    L.cost = off; off = round4(off + 2);
+    L.grad = off; off = round4(off + L.n_dec);
+    L.H = off;    off = round4(off + N * L.tri);
+    L.HN = off;   off = round4(off + L.tri_terminal);
+    L.Hc = off;   off = round4(off + (N - 1) * L.hc_per_node);
+    L.size = off;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Structural sparsity from dependency masks (what CppAD's pattern propagation gives the reference,
+// function.hpp:98-105 / :529-574), and the map from each CSR nonzero to its slot in the block record.
+// ---------------------------------------------------------------------------------------------
+template <class Mdl>
+void seed_locals(const std::vector<double>& xp, int N, int k, Dep* z, int count) {
+    for (int i = 0; i < count; ++i) {
+        const int off = i < Mdl::NX ? Mdl::x_off(N, k) + i : Mdl::u_off(N, k) + i - Mdl::NX;
+        z[i] = Dep(xp[off], uint64_t(1) << i);
+    }
+}
+
+template <class Mdl>
+void build_tables(ungar_b200_model& M) {
+    const int N = M.N;
+    const ungar_b200_kkt_layout& L = M.layout;
+    constexpr int NX = Mdl::NX, NU = Mdl::NU, NZ = Mdl::NZ, NH = Mdl::NH;
+    std::vector<double> xp(L.n_dec + L.n_par);
+    for (size_t i = 0; i < xp.size(); ++i) xp[i] = 0.37 + 0.001 * double(i % 97);  // any generic point
+    auto local_col = [&](int k, int i) { return int64_t(i < NX ? Mdl::x_off(N, k) + i : Mdl::u_off(N, k) + i - NX); };
+
+    // ---------------- equalities
+    FunctionTables& E = M.fn[UNGAR_B200_EQUALITIES];
+    E.nx = L.n_dec; E.np = L.n_par; E.ny = L.m_eq;
+    for (int i = 0; i < NX; ++i) {  // x_0 - x_measured
+        E.jac_rows.push_back(i); E.jac_cols.push_back(i); E.jac_src.push_back(-1);
+    }
+    for (int k = 0; k < N; ++k) {
+        Dep z[NZ], xn[NX];
+        seed_locals<Mdl>(xp, N, k, z, NZ);
+        Mdl::dynamics(xp.data(), N, k, z, xn);
+        for (int r = 0; r < NX; ++r) {
+            const int64_t row = NX + int64_t(NX) * k + r;
+            auto emit = [&](int i) {
+                if (xn[r].m >> i & 1) {
+                    E.jac_rows.push_back(row); E.jac_cols.push_back(local_col(k, i));
+                    E.jac_src.push_back(int32_t(L.A + (int64_t(k) * NX + r) * NZ + i));
+                }
+            };
+            for (int i = 0; i < NX; ++i) emit(i);  // x_k columns
+            E.jac_rows.push_back(row); E.jac_cols.push_back(Mdl::x_off(N, k + 1) + r); E.jac_src.push_back(-1);
+            for (int i = NX; i < NZ; ++i) emit(i);  // u_k columns
+        }
+    }
+    if constexpr (Mdl::LEGS > 0) {
+        for (int k = 0; k < N; ++k)
+            for (int leg = 0; leg < Mdl::LEGS; ++leg) {
+                Dep zl[20], rows[4];
+                for (int i = 0; i < 20; ++i) zl[i] = Dep(0.3 + 0.01 * i, uint64_t(1) << i);
+                Mdl::contact_rows(xp.data(), N, k, leg, zl, rows);
+                for (int rr = 0; rr < 4; ++rr) {
+                    const int64_t row = NX + int64_t(NX) * N + 16 * k + 4 * leg + rr;
+                    const int64_t src = L.C + ((int64_t(k) * 4 + leg) * 4 + rr) * 20;
+                    auto emit = [&](int i, int64_t col) {
+                        if (rows[rr].m >> i & 1) {
+                            E.jac_rows.push_back(row); E.jac_cols.push_back(col); E.jac_src.push_back(int32_t(src + i));
+                        }
+                    };
+                    // ascending global column: pose_{k-1}, pose_k, r_{k-1,leg}, r_{k,leg}
+                    if (k) for (int i = 0; i < 7; ++i) emit(10 + i, Mdl::x_off(N, k - 1) + i);
+                    for (int i = 0; i < 7; ++i) emit(i, Mdl::x_off(N, k) + i);
+                    if (k) for (int i = 0; i < 3; ++i) emit(17 + i, Mdl::u_off(N, k - 1) + 6 * leg + 3 + i);
+                    for (int i = 0; i < 3; ++i) emit(7 + i, Mdl::u_off(N, k) + 6 * leg + 3 + i);
+                }
+            }
+    }
+    for (int64_t i = 0; i < L.m_eq; ++i) E.y_src.push_back(int32_t(L.g + i));
+
+    // ---------------- inequalities (their Jacobian is consumed inside the sweep; for the reference-format
+    // call the values come from the Gauss-Newton-free pass: J_h entries are recovered per node below)
+    FunctionTables& I = M.fn[UNGAR_B200_INEQUALITIES];
+    I.nx = L.n_dec; I.np = L.n_par; I.ny = L.m_ineq;
+    for (int64_t i = 0; i < L.m_ineq; ++i) I.y_src.push_back(int32_t(L.h + i));
+    for (int k = 0; k < N; ++k) {
+        Dep z[NZ], h[NH];
+        seed_locals<Mdl>(xp, N, k, z, NZ);
+        Mdl::inequalities(xp.data(), N, k, z, h);
+        for (int r = 0; r < NH; ++r)
+            for (int i = 0; i < NZ; ++i)
+                if (h[r].m >> i & 1) {
+                    I.jac_rows.push_back(int64_t(NH) * k + r); I.jac_cols.push_back(local_col(k, i));
+                    // J_h is written by the sweep into the (otherwise unused in this mode) A area:
+                    // slot (k, r, i) of an [N][NH][NZ] array placed at L.A — see launch_sweep(JH_MODE).
+                    I.jac_src.push_back(int32_t(L.A + (int64_t(k) * NH + r) * NZ + i));
+                }
+    }
+
+    // ---------------- objective
+    FunctionTables& O = M.fn[UNGAR_B200_OBJECTIVE];
+    O.nx = L.n_dec; O.np = L.n_par; O.ny = 1; O.has_hessian = true;
+    O.y_src.push_back(int32_t(L.cost));
+    std::vector<uint8_t> used(L.n_dec, 0), coupled(L.n_dec, 0);
+    for (int k = 0; k <= N; ++k) {
+        Dep z[NZ];
+        const int nz = k == N ? NX : NZ;
+        seed_locals<Mdl>(xp, N, k, z, nz);
+        Mdl::cost_terms(xp.data(), N, k, z, [&](double, const Dep& r, bool counts) {
+            for (int i = 0; i < nz; ++i)
+                if (r.m >> i & 1) {
+                    used[local_col(k, i)] = 1;
+                    if (!counts) coupled[local_col(k, i)] = 1;
+                }
+        });
+    }
+    // Jacobian 1 x n_dec (ascending columns) and upper-triangular Hessian (diagonal + u_k/u_{k+1} coupling)
+    auto grad_src = [&](int64_t col) { return int32_t(L.grad + col); };
+    auto locate = [&](int64_t col, int& k, int& i) {
+        const int64_t nX = int64_t(NX) * (N + 1);
+        if (col < nX) { k = int(col / NX); i = int(col % NX); }
+        else { k = int((col - nX) / NU); i = NX + int((col - nX) % NU); }
+    };
+    for (int64_t col = 0; col < L.n_dec; ++col) {
+        if (!used[col]) continue;
+        O.jac_rows.push_back(0); O.jac_cols.push_back(col); O.jac_src.push_back(grad_src(col));
+        int k, i;
+        locate(col, k, i);
+        O.hes_rows.push_back(col); O.hes_cols.push_back(col);
+        O.hes_src.push_back(k == N ? int32_t(L.HN + ub::tri_index(NX, i, i)) : int32_t(L.H + k * L.tri + ub::tri_index(NZ, i, i)));
+        if (coupled[col]) {  // (u_k[i], u_{k+1}[i])
+            O.hes_rows.push_back(col); O.hes_cols.push_back(col + NU);
+            O.hes_src.push_back(int32_t(L.Hc + int64_t(k) * NU + (i - NX)));
+        }
+    }
+
+    // ---------------- barrier function Zsoft (soft_sqp.hpp:114-138): dense row / diagonal Hessian
+    FunctionTables& S = M.fn[UNGAR_B200_SOFT_INEQUALITIES];
+    S.nx = L.m_ineq; S.np = 0; S.ny = 1; S.has_hessian = true;
+    for (int64_t i = 0; i < L.m_ineq; ++i) {
+        S.jac_rows.push_back(0); S.jac_cols.push_back(i);
+        S.hes_rows.push_back(i); S.hes_cols.push_back(i);
+    }
+}
+
+int upload(const std::vector<int32_t>& host, int32_t** dev) {
+    *dev = nullptr;
+    if (host.empty()) return UNGAR_B200_OK;
+    UB_CUDA(cudaMalloc(reinterpret_cast<void**>(dev), host.size() * sizeof(int32_t)));
+    UB_CUDA(cudaMemcpy(*dev, host.data(), host.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
+    return UNGAR_B200_OK;
+}
+
+template <class T>
+ub::BarrierCoef<T> cast_barrier(const ub::BarrierCoef<double>& b) {
+    return {T(b.eps), T(b.a1), T(b.b1), T(b.c1), T(b.a2), T(b.b2), T(b.c2), T(b.d2)};
+}
+
+// ---------------------------------------------------------------------------------------------
+// Launches
+// ---------------------------------------------------------------------------------------------
+enum SweepMode { MODE_KKT = 0, MODE_PLAIN = 1, MODE_JH = 2 };
+
+template <class Mdl, class T, int M, bool BARRIER>
+int launch_generic(ungar_b200_model& mdl, const T* xp, int64_t batch, int64_t ld_xp, T* rec, int64_t ld_rec,
+                   cudaStream_t stream) {
+    using Sh = ub::SweepShape<Mdl, M>;
+    auto kernel = ub::kkt_sweep_kernel<Mdl, T, M, BARRIER>;
+    const int smem = Sh::total * int(sizeof(T));
+    static bool configured = false;  // per instantiation
+    if (!configured) {
+        UB_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        configured = true;
+    }
+    const int tiles = (mdl.N + M - 1) / M;
+    const long long grid = (long long)batch * tiles;
+    if (grid > 2147483647LL) return fail(UNGAR_B200_EINVAL, "batch too large for one launch (%lld CTAs)", grid);
+    kernel<<<(unsigned)grid, Sh::THREADS, smem, stream>>>(xp, ld_xp, rec, ld_rec, static_cast<T*>(mdl.stage_cost.ptr),
+                                                          mdl.N, tiles, mdl.rl, cast_barrier<T>(mdl.bar));
+    ++g_launches;
+    UB_CUDA(cudaGetLastError());
+    return UNGAR_B200_OK;
+}
+
+template <class Mdl, class T, int M>
+int launch_sweep_t(ungar_b200_model& mdl, const void* xp, int64_t batch, int64_t ld_xp, void* rec, int64_t ld_rec,
+                   int mode, cudaStream_t stream) {
+    if (int rc = mdl.stage_cost.reserve(size_t(batch) * (mdl.N + 1) * 2 * sizeof(T))) return rc;
+    const T* x = static_cast<const T*>(xp);
+    T* r       = static_cast<T*>(rec);
+    int rc;
+    if (mode == MODE_JH) {
+        rc = ub::launch_jh<Mdl, T>(x, batch, ld_xp, r, ld_rec, mdl.N, mdl.rl, stream);
+        if (rc == 0) ++g_launches;
+        else return fail(UNGAR_B200_ECUDA, "J_h kernel launch failed: %s", cudaGetErrorString(cudaError_t(rc)));
+        return UNGAR_B200_OK;
+    }
+    if (mode == MODE_KKT) rc = launch_generic<Mdl, T, M, true>(mdl, x, batch, ld_xp, r, ld_rec, stream);
+    else rc = launch_generic<Mdl, T, M, false>(mdl, x, batch, ld_xp, r, ld_rec, stream);
+    if (rc) return rc;
+    const int threads = 128;
+    ub::reduce_cost_kernel<T><<<unsigned((batch + threads - 1) / threads), threads, 0, stream>>>(
+        static_cast<const T*>(mdl.stage_cost.ptr), r, ld_rec, mdl.rl.cost, mdl.N, batch);
+    ++g_launches;
+    UB_CUDA(cudaGetLastError());
+    return UNGAR_B200_OK;
+}
+
+int launch_sweep(ungar_b200_model& mdl, const void* xp, int64_t batch, int64_t ld_xp, void* rec, int64_t ld_rec,
+                 int mode, cudaStream_t stream) {
+    const bool f64 = mdl.desc.dtype == UNGAR_B200_F64;
+    switch (mdl.desc.kind) {
+        case UNGAR_B200_QUADROTOR:
+            return f64 ? launch_sweep_t<ub::Quadrotor, double, 15>(mdl, xp, batch, ld_xp, rec, ld_rec, mode, stream)
+                       : launch_sweep_t<ub::Quadrotor, float, 15>(mdl, xp, batch, ld_xp, rec, ld_rec, mode, stream);
+        case UNGAR_B200_RC_CAR:
+            return f64 ? launch_sweep_t<ub::RcCar, double, 30>(mdl, xp, batch, ld_xp, rec, ld_rec, mode, stream)
+                       : launch_sweep_t<ub::RcCar, float, 30>(mdl, xp, batch, ld_xp, rec, ld_rec, mode, stream);
+        case UNGAR_B200_QUADRUPED:
+            return f64 ? launch_sweep_t<ub::Quadruped, double, 4>(mdl, xp, batch, ld_xp, rec, ld_rec, mode, stream)
+                       : launch_sweep_t<ub::Quadruped, float, 4>(mdl, xp, batch, ld_xp, rec, ld_rec, mode, stream);
+    }
+    return fail(UNGAR_B200_EINVAL, "unknown model kind %d", mdl.desc.kind);
+}
+
+template <class T>
+int launch_gather_t(const void* rec, int64_t ld_rec, const int32_t* src, int64_t count, void* out, int64_t ld_out,
+                    int64_t batch, cudaStream_t stream) {
+    if (count == 0 || batch == 0) return UNGAR_B200_OK;
+    const int threads = 256;
+    dim3 grid(unsigned(std::min<int64_t>((count + threads - 1) / threads, 64)), unsigned(batch));
+    if (batch > 65535) return fail(UNGAR_B200_EINVAL, "reference-format calls support batch <= 65535 (got %lld)", (long long)batch);
+    ub::gather_kernel<T><<<grid, threads, 0, stream>>>(static_cast<const T*>(rec), ld_rec, src, int(count),
+                                                      static_cast<T*>(out), ld_out, batch);
+    ++g_launches;
+    UB_CUDA(cudaGetLastError());
+    return UNGAR_B200_OK;
+}
+
+int launch_gather(ungar_b200_model& mdl, const void* rec, int64_t ld_rec, const int32_t* src, int64_t count, void* out,
+                  int64_t ld_out, int64_t batch, cudaStream_t stream) {
+    return mdl.desc.dtype == UNGAR_B200_F64
+               ? launch_gather_t<double>(rec, ld_rec, src, count, out, ld_out, batch, stream)
+               : launch_gather_t<float>(rec, ld_rec, src, count, out, ld_out, batch, stream);
+}
+
+template <class T>
+int launch_barrier_t(ungar_b200_model& mdl, const void* z, int64_t ld_z, void* out, int64_t ld_out, int64_t batch,
+                     int mode, cudaStream_t stream) {
+    ub::barrier_kernel<T><<<unsigned(batch), 256, 0, stream>>>(static_cast<const T*>(z), ld_z, int(mdl.layout.m_ineq),
+                                                              static_cast<T*>(out), ld_out, cast_barrier<T>(mdl.bar), mode);
+    ++g_launches;
+    UB_CUDA(cudaGetLastError());
+    return UNGAR_B200_OK;
+}
+
+bool valid_fn(int32_t f) { return f >= 0 && f <= 3; }
+
+// What a reference-format call needs: which sweep mode fills the slots its gather map points at.
+enum Want { WANT_Y = 0, WANT_JAC = 1, WANT_HES = 2 };
+
+int reference_call(ungar_b200_model* mdl, int32_t function, int want, const void* xp, int64_t batch, int64_t ld_xp,
+                   void* out, int64_t ld_out, int32_t mem, void* stream_) {
+    if (!mdl) return fail(UNGAR_B200_EINVAL, "null model");
+    if (!valid_fn(function)) return fail(UNGAR_B200_EINVAL, "unknown function %d", function);
+    if (batch < 0 || (batch > 0 && (!xp || !out))) return fail(UNGAR_B200_EINVAL, "null buffer");
+    if (mem != UNGAR_B200_MEM_DEVICE && mem != UNGAR_B200_MEM_HOST) return fail(UNGAR_B200_EINVAL, "unknown mem %d", mem);
+    FunctionTables& F = mdl->fn[function];
+    if (want == WANT_HES && !F.has_hessian)
+        return fail(UNGAR_B200_EUNSUPPORTED, "the Hessian is implemented only for scalar functions (function.hpp:136-137)");
+    const int64_t n_in  = F.nx + F.np;
+    const int64_t n_out = want == WANT_Y ? F.ny : want == WANT_JAC ? int64_t(F.jac_rows.size()) : int64_t(F.hes_rows.size());
+    if (ld_xp < n_in) return fail(UNGAR_B200_EINVAL, "ld_xp %lld < %lld", (long long)ld_xp, (long long)n_in);
+    if (ld_out < n_out) return fail(UNGAR_B200_EINVAL, "output stride %lld < %lld", (long long)ld_out, (long long)n_out);
+    if (batch == 0) return UNGAR_B200_OK;
+    UB_CUDA(cudaSetDevice(mdl->desc.device));
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    const size_t es = mdl->elem;
+
+    const void* d_xp = xp;
+    void* d_out      = out;
+    int64_t d_ld_xp = ld_xp, d_ld_out = ld_out;
+    if (mem == UNGAR_B200_MEM_HOST) {
+        if (int rc = mdl->ws_xp.reserve(size_t(batch) * n_in * es)) return rc;
+        if (int rc = mdl->ws_out.reserve(size_t(batch) * std::max<int64_t>(n_out, 1) * es)) return rc;
+        UB_CUDA(cudaMemcpy2DAsync(mdl->ws_xp.ptr, n_in * es, xp, ld_xp * es, n_in * es, batch, cudaMemcpyHostToDevice, stream));
+        d_xp = mdl->ws_xp.ptr; d_ld_xp = n_in;
+        d_out = mdl->ws_out.ptr; d_ld_out = std::max<int64_t>(n_out, 1);
+    }
+
+    int rc = UNGAR_B200_OK;
+    if (function == UNGAR_B200_SOFT_INEQUALITIES) {
+        rc = mdl->desc.dtype == UNGAR_B200_F64 ? launch_barrier_t<double>(*mdl, d_xp, d_ld_xp, d_out, d_ld_out, batch, want, stream)
+                                               : launch_barrier_t<float>(*mdl, d_xp, d_ld_xp, d_out, d_ld_out, batch, want, stream);
+    } else {
+        if ((rc = mdl->ws_records.reserve(size_t(batch) * mdl->layout.size * es))) return rc;
+        const int mode = (function == UNGAR_B200_INEQUALITIES && want == WANT_JAC) ? MODE_JH : MODE_PLAIN;
+        rc = launch_sweep(*mdl, d_xp, batch, d_ld_xp, mdl->ws_records.ptr, mdl->layout.size, mode, stream);
+        if (rc) return rc;
+        const int32_t* src = want == WANT_Y ? F.d_y_src : want == WANT_JAC ? F.d_jac_src : F.d_hes_src;
+        rc = launch_gather(*mdl, mdl->ws_records.ptr, mdl->layout.size, src, n_out, d_out, d_ld_out, batch, stream);
+    }
+    if (rc) return rc;
+    if (mem == UNGAR_B200_MEM_HOST) {
+        if (n_out)
+            UB_CUDA(cudaMemcpy2DAsync(out, ld_out * es, d_out, d_ld_out * es, n_out * es, batch, cudaMemcpyDeviceToHost, stream));
+        UB_CUDA(cudaStreamSynchronize(stream));
+    }
+    return UNGAR_B200_OK;
+}
+
+}  // namespace
+
+// =============================================================================================
+extern "C" {
+
+int32_t ungar_b200_abi_version(void) { return UNGAR_B200_ABI_VERSION; }
+const char* ungar_b200_last_error(void) { return g_last_error.c_str(); }
+int64_t ungar_b200_launch_count(void) { return g_launches.load(); }
+
+int ungar_b200_model_create(const ungar_b200_model_desc* desc, ungar_b200_model** out) {
+    if (!desc || !out) return fail(UNGAR_B200_EINVAL, "null argument");
+    *out = nullptr;
+    if (desc->kind < 0 || desc->kind > 2) return fail(UNGAR_B200_EINVAL, "unknown model kind %d", desc->kind);
+    if (desc->dtype != UNGAR_B200_F32 && desc->dtype != UNGAR_B200_F64) return fail(UNGAR_B200_EINVAL, "unknown dtype %d", desc->dtype);
+    if (desc->horizon < 2 || desc->horizon > 4096) return fail(UNGAR_B200_EINVAL, "horizon %d out of range [2, 4096]", desc->horizon);
+    if (!(desc->barrier_stiffness > 0.0) || !(desc->barrier_epsilon > 0.0))
+        return fail(UNGAR_B200_EINVAL, "barrier stiffness and epsilon must be positive");
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0)
+        return fail(UNGAR_B200_ECUDA, "no usable CUDA device (%s); ungar_b200 has no CPU fallback", cudaGetErrorString(e));
+    if (desc->device < 0 || desc->device >= ndev) return fail(UNGAR_B200_EINVAL, "device %d out of range (%d devices)", desc->device, ndev);
+    UB_CUDA(cudaSetDevice(desc->device));
+
+    ungar_b200_model* M = new (std::nothrow) ungar_b200_model;
+    if (!M) return fail(UNGAR_B200_ENOMEM, "out of host memory");
+    M->desc = *desc;
+    M->N    = desc->horizon;
+    M->elem = desc->dtype == UNGAR_B200_F64 ? 8 : 4;
+    switch (desc->kind) {
+        case UNGAR_B200_QUADROTOR: make_layout<ub::Quadrotor>(M->N, M->layout); build_tables<ub::Quadrotor>(*M); break;
+        case UNGAR_B200_RC_CAR: make_layout<ub::RcCar>(M->N, M->layout); build_tables<ub::RcCar>(*M); break;
+        default: make_layout<ub::Quadruped>(M->N, M->layout); build_tables<ub::Quadruped>(*M); break;
+    }
+    const ungar_b200_kkt_layout& L = M->layout;
+    if (L.size > 2147483647LL) { delete M; return fail(UNGAR_B200_EINVAL, "record too large"); }
+    M->rl = {int(L.g), int(L.A), int(L.C), int(L.h), int(L.cost), int(L.grad), int(L.H), int(L.HN), int(L.Hc), int(L.size)};
+    {  // soft_inequality_constraint.hpp:133-145
+        const double a1 = desc->barrier_stiffness, eps = desc->barrier_epsilon;
+        const double b1 = -0.5 * a1 * eps;
+        const double c1 = -1.0 / 3.0 * (-b1 - a1 * eps) * eps - 0.5 * a1 * eps * eps - b1 * eps;
+        M->bar = {eps, a1, b1, c1, (-b1 - a1 * eps) / (eps * eps), a1, b1, c1};
+    }
+    for (int f = 0; f < 3; ++f) {
+        int rc = upload(M->fn[f].y_src, &M->fn[f].d_y_src);
+        if (!rc) rc = upload(M->fn[f].jac_src, &M->fn[f].d_jac_src);
+        if (!rc) rc = upload(M->fn[f].hes_src, &M->fn[f].d_hes_src);
+        if (rc) { ungar_b200_model_destroy(M); return rc; }
+    }
+    *out = M;
+    return UNGAR_B200_OK;
+}
+
+int ungar_b200_model_destroy(ungar_b200_model* model) {
+    if (!model) return UNGAR_B200_OK;
+    cudaSetDevice(model->desc.device);
+    for (auto& f : model->fn) {
+        if (f.d_y_src) cudaFree(f.d_y_src);
+        if (f.d_jac_src) cudaFree(f.d_jac_src);
+        if (f.d_hes_src) cudaFree(f.d_hes_src);
+    }
+    delete model;
+    return UNGAR_B200_OK;
+}
+
+int ungar_b200_function_info(const ungar_b200_model* model, int32_t function, int64_t* independent_size,
+                             int64_t* parameter_size, int64_t* dependent_size, int64_t* nnz_jacobian,
+                             int64_t* nnz_hessian) {
+    if (!model) return fail(UNGAR_B200_EINVAL, "null model");
+    if (!valid_fn(function)) return fail(UNGAR_B200_EINVAL, "unknown function %d", function);
+    const FunctionTables& F = model->fn[function];
+    if (independent_size) *independent_size = F.nx;
+    if (parameter_size) *parameter_size = F.np;
+    if (dependent_size) *dependent_size = F.ny;
+    if (nnz_jacobian) *nnz_jacobian = int64_t(F.jac_rows.size());
+    if (nnz_hessian) *nnz_hessian = int64_t(F.hes_rows.size());
+    return UNGAR_B200_OK;
+}
+
+int ungar_b200_jacobian_sparsity(const ungar_b200_model* model, int32_t function, const int64_t** rows,
+                                 const int64_t** cols, int64_t* nnz) {
+    if (!model || !rows || !cols || !nnz) return fail(UNGAR_B200_EINVAL, "null argument");
+    if (!valid_fn(function)) return fail(UNGAR_B200_EINVAL, "unknown function %d", function);
+    const FunctionTables& F = model->fn[function];
+    *rows = F.jac_rows.data(); *cols = F.jac_cols.data(); *nnz = int64_t(F.jac_rows.size());
+    return UNGAR_B200_OK;
+}
+
+int ungar_b200_hessian_sparsity(const ungar_b200_model* model, int32_t function, const int64_t** rows,
+                                const int64_t** cols, int64_t* nnz) {
+    if (!model || !rows || !cols || !nnz) return fail(UNGAR_B200_EINVAL, "null argument");
+    if (!valid_fn(function)) return fail(UNGAR_B200_EINVAL, "unknown function %d", function);
+    const FunctionTables& F = model->fn[function];
+    if (!F.has_hessian)
+        return fail(UNGAR_B200_EUNSUPPORTED, "the Hessian is implemented only for scalar functions (function.hpp:136-137)");
+    *rows = F.hes_rows.data(); *cols = F.hes_cols.data(); *nnz = int64_t(F.hes_rows.size());
+    return UNGAR_B200_OK;
+}
+
+int ungar_b200_forward_zero(ungar_b200_model* model, int32_t function, const void* xp, int64_t batch, int64_t ld_xp,
+                            void* y, int64_t ld_y, int32_t mem, void* stream) {
+    return reference_call(model, function, WANT_Y, xp, batch, ld_xp, y, ld_y, mem, stream);
+}
+
+int ungar_b200_sparse_jacobian(ungar_b200_model* model, int32_t function, const void* xp, int64_t batch,
+                               int64_t ld_xp, void* vals, int64_t ld_vals, int32_t mem, void* stream) {
+    return reference_call(model, function, WANT_JAC, xp, batch, ld_xp, vals, ld_vals, mem, stream);
+}
+
+int ungar_b200_sparse_hessian(ungar_b200_model* model, int32_t function, const void* xp, int64_t batch, int64_t ld_xp,
+                              void* vals, int64_t ld_vals, int32_t mem, void* stream) {
+    return reference_call(model, function, WANT_HES, xp, batch, ld_xp, vals, ld_vals, mem, stream);
+}
+
+int ungar_b200_kkt_layout_get(const ungar_b200_model* model, ungar_b200_kkt_layout* out) {
+    if (!model || !out) return fail(UNGAR_B200_EINVAL, "null argument");
+    *out = model->layout;
+    return UNGAR_B200_OK;
+}
+
+int ungar_b200_kkt_blocks(ungar_b200_model* model, const void* xp, int64_t batch, int64_t ld_xp, void* records,
+                          int64_t ld_rec, int32_t mem, void* stream_) {
+    if (!model) return fail(UNGAR_B200_EINVAL, "null model");
+    if (batch < 0 || (batch > 0 && (!xp || !records))) return fail(UNGAR_B200_EINVAL, "null buffer");
+    const ungar_b200_kkt_layout& L = model->layout;
+    const int64_t n_in = L.n_dec + L.n_par;
+    if (ld_xp < n_in) return fail(UNGAR_B200_EINVAL, "ld_xp %lld < %lld", (long long)ld_xp, (long long)n_in);
+    if (ld_rec < L.size) return fail(UNGAR_B200_EINVAL, "ld_rec %lld < record size %lld", (long long)ld_rec, (long long)L.size);
+    if (mem != UNGAR_B200_MEM_DEVICE && mem != UNGAR_B200_MEM_HOST) return fail(UNGAR_B200_EINVAL, "unknown mem %d", mem);
+    if (batch == 0) return UNGAR_B200_OK;
+    UB_CUDA(cudaSetDevice(model->desc.device));
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    const size_t es = model->elem;
+    if (mem == UNGAR_B200_MEM_DEVICE) return launch_sweep(*model, xp, batch, ld_xp, records, ld_rec, MODE_KKT, stream);
+
+    if (int rc = model->ws_xp.reserve(size_t(batch) * n_in * es)) return rc;
+    if (int rc = model->ws_records.reserve(size_t(batch) * L.size * es)) return rc;
+    UB_CUDA(cudaMemcpy2DAsync(model->ws_xp.ptr, n_in * es, xp, ld_xp * es, n_in * es, batch, cudaMemcpyHostToDevice, stream));
+    if (int rc = launch_sweep(*model, model->ws_xp.ptr, batch, n_in, model->ws_records.ptr, L.size, MODE_KKT, stream)) return rc;
+    UB_CUDA(cudaMemcpy2DAsync(records, ld_rec * es, model->ws_records.ptr, L.size * es, L.size * es, batch,
+                              cudaMemcpyDeviceToHost, stream));
+    UB_CUDA(cudaStreamSynchronize(stream));
+    return UNGAR_B200_OK;
+}
+
+int ungar_b200_summaries(ungar_b200_model* model, const void* xp, int64_t batch, int64_t ld_xp, const void* records,
+                         int64_t ld_rec, void* summaries, void* stream_) {
+    if (!model || (batch > 0 && (!xp || !records || !summaries))) return fail(UNGAR_B200_EINVAL, "null argument");
+    if (batch <= 0) return batch == 0 ? UNGAR_B200_OK : fail(UNGAR_B200_EINVAL, "negative batch");
+    UB_CUDA(cudaSetDevice(model->desc.device));
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    const ungar_b200_kkt_layout& L = model->layout;
+    const int u0 = int(L.nx * (L.horizon + 1));
+    if (model->desc.dtype == UNGAR_B200_F64)
+        ub::summary_kernel<double><<<unsigned(batch), 32, 0, stream>>>(static_cast<const double*>(xp), ld_xp,
+            static_cast<const double*>(records), ld_rec, static_cast<double*>(summaries), model->rl, u0, int(L.nu), int(L.m_eq), int(L.m_ineq));
+    else
+        ub::summary_kernel<float><<<unsigned(batch), 32, 0, stream>>>(static_cast<const float*>(xp), ld_xp,
+            static_cast<const float*>(records), ld_rec, static_cast<float*>(summaries), model->rl, u0, int(L.nu), int(L.m_eq), int(L.m_ineq));
+    ++g_launches;
+    UB_CUDA(cudaGetLastError());
+    return UNGAR_B200_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,231 @@
+"""Python mirror of the reference's evaluator interface, over the C ABI.
+
+``Function`` keeps the public surface of ``Ungar::Autodiff::Function``
+(include/ungar/autodiff/function.hpp:180-361: ``Evaluate``, ``operator()``, ``Jacobian``, ``Hessian``,
+``Implements*``, ``*Size``) so parity tests read like test/autodiff/function.test.cpp; every method also accepts
+a batch ``xp[B, nx + np]``.  ``Model`` stands where ``MakeFunction`` / ``MakeNLPProblem`` stand in the examples
+(quadruped.example.cpp:343-363) and adds the batched KKT sweep replacing
+``SoftSQPOptimizer::AssembleOSQPInstance`` (optimization/soft_sqp.hpp:141-158).
+
+numpy arrays are host buffers (the library stages them: H2D, kernels, D2H); torch CUDA tensors are device
+buffers and the call is asynchronous on torch's current stream.  There is no CPU evaluation path here.
+"""
+from __future__ import annotations
+
+import ctypes
+
+import numpy as np
+
+from . import _lib
+from ._lib import (EQUALITIES, F32, F64, INEQUALITIES, MEM_DEVICE, MEM_HOST, OBJECTIVE, SOFT_INEQUALITIES, KktLayout,
+                   ModelDesc, check)
+from .workloads import MODEL_IDS
+
+_NP_DTYPE = {F32: np.float32, F64: np.float64}
+
+
+def _is_torch(x) -> bool:
+    return type(x).__module__.startswith("torch")
+
+
+def _torch_stream() -> int:
+    import torch
+
+    return torch.cuda.current_stream().cuda_stream
+
+
+class Model:
+    """One of the three reference NMPC problems at horizon N, backed by the sm_100a kernels."""
+
+    def __init__(self, kind, horizon: int, dtype: str = "f64", device: int = 0, barrier=(100.0, 2e-5)):
+        self.kind = MODEL_IDS[kind] if isinstance(kind, str) else int(kind)
+        self.horizon = int(horizon)
+        self.dtype = {"f32": F32, "f64": F64}[dtype]
+        self.np_dtype = _NP_DTYPE[self.dtype]
+        self.device = int(device)
+        self._lib = _lib.load()
+        desc = ModelDesc(self.kind, self.horizon, self.dtype, self.device, float(barrier[0]), float(barrier[1]))
+        handle = ctypes.c_void_p()
+        check(self._lib.ungar_b200_model_create(ctypes.byref(desc), ctypes.byref(handle)))
+        self._handle = handle
+        lay = KktLayout()
+        check(self._lib.ungar_b200_kkt_layout_get(self._handle, ctypes.byref(lay)))
+        self.layout = lay.as_dict()
+        self.n_xp = self.layout["n_dec"] + self.layout["n_par"]
+        self.objective = Function(self, OBJECTIVE)
+        self.equalityConstraints = Function(self, EQUALITIES)
+        self.inequalityConstraints = Function(self, INEQUALITIES)
+        self.softInequalityConstraints = Function(self, SOFT_INEQUALITIES)
+
+    def close(self) -> None:
+        if getattr(self, "_handle", None):
+            self._lib.ungar_b200_model_destroy(self._handle)
+            self._handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # -------------------------------------------------------------------------------------------
+    def _buffers(self, xp, out, out_cols: int):
+        """Normalise (xp, out) to pointers / strides / memory kind.  Returns (xp, out, batch, mem, stream, squeeze)."""
+        if _is_torch(xp):
+            import torch
+
+            if not xp.is_cuda:
+                raise ValueError("torch inputs must be CUDA tensors (use numpy for host buffers)")
+            want = torch.float32 if self.dtype == F32 else torch.float64
+            if xp.dtype != want:
+                raise ValueError(f"xp dtype {xp.dtype} does not match the model dtype")
+            squeeze = xp.dim() == 1
+            xp2 = xp.unsqueeze(0) if squeeze else xp
+            if xp2.stride(-1) != 1:
+                raise ValueError("xp rows must be contiguous")
+            if out is None:
+                out = torch.empty((xp2.shape[0], out_cols), dtype=want, device=xp.device)
+            out2 = out.unsqueeze(0) if out.dim() == 1 else out
+            return xp2, out2, MEM_DEVICE, _torch_stream(), squeeze
+        xp2 = np.ascontiguousarray(xp, dtype=self.np_dtype)
+        squeeze = xp2.ndim == 1
+        if squeeze:
+            xp2 = xp2[None]
+        if out is None:
+            out = np.empty((xp2.shape[0], out_cols), dtype=self.np_dtype)
+        out2 = out[None] if out.ndim == 1 else out
+        if out2.dtype != self.np_dtype or not out2.flags.c_contiguous:
+            raise ValueError("output buffer must be a C-contiguous array of the model dtype")
+        return xp2, out2, MEM_HOST, None, squeeze
+
+    @staticmethod
+    def _ptr(a):
+        return a.data_ptr() if _is_torch(a) else a.ctypes.data
+
+    @staticmethod
+    def _ld(a):
+        return a.stride(0) if _is_torch(a) else a.strides[0] // a.itemsize
+
+    def kkt_blocks(self, xp, out=None):
+        """All values, Jacobian blocks and Gauss-Newton Hessian blocks of every node: ``records[B, layout.size]``."""
+        xp2, out2, mem, stream, squeeze = self._buffers(xp, out, self.layout["size"])
+        check(self._lib.ungar_b200_kkt_blocks(self._handle, self._ptr(xp2), xp2.shape[0], self._ld(xp2), self._ptr(out2),
+                                              self._ld(out2), mem, stream))
+        return out2[0] if squeeze else out2
+
+    def summaries(self, xp, records, out=None):
+        """``[B, 32]`` per-trajectory summaries (device tensors only): the all-gather payload."""
+        import torch
+
+        if out is None:
+            out = torch.empty((xp.shape[0], _lib.SUMMARY_SIZE), dtype=xp.dtype, device=xp.device)
+        check(self._lib.ungar_b200_summaries(self._handle, xp.data_ptr(), xp.shape[0], xp.stride(0), records.data_ptr(),
+                                             records.stride(0), out.data_ptr(), _torch_stream()))
+        return out
+
+    def launch_count(self) -> int:
+        return int(self._lib.ungar_b200_launch_count())
+
+    def split_record(self, rec) -> dict:
+        """Views of one record (or a batch of records) by block name, reshaped per ungar_b200_kkt_layout."""
+        L = self.layout
+        N, nx, nu, nz = L["horizon"], L["nx"], L["nu"], L["nz"]
+        lead = rec.shape[:-1]
+
+        def cut(off, count, *shape):
+            return rec[..., off:off + count].reshape(*lead, *shape)
+
+        out = {"g": cut(L["g"], L["m_eq"], L["m_eq"]), "A": cut(L["A"], N * nx * nz, N, nx, nz),
+               "h": cut(L["h"], L["m_ineq"], L["m_ineq"]), "cost": cut(L["cost"], 2, 2),
+               "grad": cut(L["grad"], L["n_dec"], L["n_dec"]), "H": cut(L["H"], N * L["tri"], N, L["tri"]),
+               "HN": cut(L["HN"], L["tri_terminal"], L["tri_terminal"])}
+        if L["legs"]:
+            out["C"] = cut(L["C"], N * L["legs"] * 80, N, L["legs"], 4, 20)
+        if L["hc_per_node"]:
+            out["Hc"] = cut(L["Hc"], (N - 1) * nu, N - 1, nu)
+        return out
+
+
+class Function:
+    """Mirror of ``Ungar::Autodiff::Function`` for one function of a ``Model``."""
+
+    def __init__(self, model: Model, which: int):
+        self._m = model
+        self._which = which
+        v = [ctypes.c_int64() for _ in range(5)]
+        check(model._lib.ungar_b200_function_info(model._handle, which, *[ctypes.byref(x) for x in v]))
+        self._nx, self._np, self._ny, self._nnz_jac, self._nnz_hes = (int(x.value) for x in v)
+
+    # sizes (function.hpp:351-361)
+    def IndependentVariableSize(self) -> int:
+        return self._nx
+
+    def ParameterSize(self) -> int:
+        return self._np
+
+    def DependentVariableSize(self) -> int:
+        return self._ny
+
+    def ImplementsFunction(self) -> bool:
+        return True
+
+    def ImplementsJacobian(self) -> bool:
+        return True
+
+    def ImplementsHessian(self) -> bool:
+        return self._which in (OBJECTIVE, SOFT_INEQUALITIES)
+
+    def _sparsity(self, fn_name):
+        rows, cols, nnz = _lib.c_i64_p(), _lib.c_i64_p(), ctypes.c_int64()
+        check(getattr(self._m._lib, fn_name)(self._m._handle, self._which, ctypes.byref(rows), ctypes.byref(cols),
+                                             ctypes.byref(nnz)))
+        n = int(nnz.value)
+        return (np.ctypeslib.as_array(rows, (n,)).copy() if n else np.zeros(0, np.int64),
+                np.ctypeslib.as_array(cols, (n,)).copy() if n else np.zeros(0, np.int64))
+
+    def JacobianSparsity(self):
+        """(rows, cols): row-major, columns ascending within a row (GenericModel::JacobianSparsity)."""
+        return self._sparsity("ungar_b200_jacobian_sparsity")
+
+    def HessianSparsity(self):
+        """(rows, cols) of the upper triangle (GenericModel::HessianSparsity(0, ...))."""
+        return self._sparsity("ungar_b200_hessian_sparsity")
+
+    def _call(self, entry, xp, out, cols):
+        m = self._m
+        xp2, out2, mem, stream, squeeze = m._buffers(xp, out, max(cols, 1))
+        if xp2.shape[-1] != self._nx + self._np:
+            raise ValueError(f"xp has {xp2.shape[-1]} entries, expected {self._nx + self._np}")
+        check(getattr(m._lib, entry)(m._handle, self._which, m._ptr(xp2), xp2.shape[0], m._ld(xp2), m._ptr(out2),
+                                     m._ld(out2), mem, stream))
+        out2 = out2[..., :cols]
+        return out2[0] if squeeze else out2
+
+    # Evaluate / operator() (function.hpp:180-214)
+    def Evaluate(self, xp, y=None):
+        return self._call("ungar_b200_forward_zero", xp, y, self._ny)
+
+    __call__ = Evaluate
+
+    def JacobianValues(self, xp, out=None):
+        """Nonzeros of dy/dx in JacobianSparsity() order; ``[B, nnz]`` for a batch."""
+        return self._call("ungar_b200_sparse_jacobian", xp, out, self._nnz_jac)
+
+    def HessianValues(self, xp, out=None):
+        return self._call("ungar_b200_sparse_hessian", xp, out, self._nnz_hes)
+
+    # Jacobian / Hessian as sparse matrices for ONE xp (function.hpp:216-274)
+    def Jacobian(self, xp):
+        import scipy.sparse as sp
+
+        vals = np.asarray(self.JacobianValues(np.asarray(xp)), dtype=np.float64)
+        rows, cols = self.JacobianSparsity()
+        return sp.csr_matrix((vals, (rows, cols)), shape=(self._ny, self._nx))
+
+    def Hessian(self, xp):
+        """Upper-triangular view, like the reference (function.hpp:232-235)."""
+        import scipy.sparse as sp
+
+        vals = np.asarray(self.HessianValues(np.asarray(xp)), dtype=np.float64)
+        rows, cols = self.HessianSparsity()
+        return sp.csr_matrix((vals, (rows, cols)), shape=(self._nx, self._nx))
