@@ -84,8 +84,9 @@ def test_kkt_blocks_match_oracle(torch_cuda, oracle, name, N, dtype):
     assert np.isnan(d_rec[:, model.layout["size"]:].cpu().numpy()).all()  # nothing written past the record
     compare_records(model, got, ref, xp, RTOL[dtype])
     # host buffers through the same entry point (H2D + kernels + D2H inside the call)
-    got_host = model.kkt_blocks(xp)
-    assert np.array_equal(got_host, got)
+    got_host = model.split_record(model.kkt_blocks(xp))
+    for key, blk in model.split_record(got).items():  # (padding between blocks is never written)
+        assert np.array_equal(got_host[key], blk), key
     # summaries
     summ = model.summaries(d_xp[:, :model.n_xp], out).cpu().numpy()
     nu, nX = model.layout["nu"], model.layout["nx"] * (N + 1)
@@ -182,7 +183,8 @@ def test_full_size_properties(torch_cuda, oracle, name, N, dtype, B):
     k, eps = EXAMPLE_BARRIER[mid]
     xp = W.synthetic_batch(mid, N, B, seed=101).astype(model.np_dtype)
     d_xp = torch.from_numpy(xp).cuda()
-    rec = model.kkt_blocks(d_xp)
+    zeros = lambda: torch.zeros((B, model.layout["size"]), dtype=d_xp.dtype, device="cuda")  # noqa: E731
+    rec = model.kkt_blocks(d_xp, zeros())  # (the padding between blocks is never written: pre-zero it)
     torch.cuda.synchronize()
     got = rec.cpu().numpy()
     assert np.isfinite(got).all()
@@ -191,11 +193,11 @@ def test_full_size_properties(torch_cuda, oracle, name, N, dtype, B):
     compare_records(model, got[sample], ref, xp[sample], RTOL[dtype])
     # permutation equivariance: trajectories are independent work items
     perm = np.random.default_rng(0).permutation(B)
-    rec2 = model.kkt_blocks(d_xp[torch.from_numpy(perm).cuda()])
+    rec2 = model.kkt_blocks(d_xp[torch.from_numpy(perm).cuda()], zeros())
     torch.cuda.synchronize()
     assert torch.equal(rec2, rec[torch.from_numpy(perm).cuda()])
     # idempotence / determinism
-    assert torch.equal(model.kkt_blocks(d_xp), rec)
+    assert torch.equal(model.kkt_blocks(d_xp, zeros()), rec)
     # checksum of checksums: cost = sum of what the per-function call reports
     f = model.objective(d_xp[:64])
     torch.cuda.synchronize()

@@ -104,7 +104,8 @@ class Model:
 
     @staticmethod
     def _ld(a):
-        return a.stride(0) if _is_torch(a) else a.strides[0] // a.itemsize
+        ld = a.stride(0) if _is_torch(a) else a.strides[0] // a.itemsize
+        return max(int(ld), int(a.shape[-1]))  # a size-1 leading dimension may report any stride
 
     def kkt_blocks(self, xp, out=None):
         """All values, Jacobian blocks and Gauss-Newton Hessian blocks of every node: ``records[B, layout.size]``."""
