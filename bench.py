@@ -1,0 +1,404 @@
+#!/usr/bin/env python
+"""Headline benchmark: shooting-nodes/sec (forward + Jacobian/Hessian blocks) of the quadruped NMPC sweep.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W]            this repo's CUDA path
+  python bench.py --impl reference [--gpus N] [--steps K] ...     the CPU implementation of the same path
+
+One "step" = one pass of the hot path over one batch of synthetic trajectories: the KKT sweep
+(every value / Jacobian block / Gauss-Newton Hessian block of every shooting node), the per-trajectory
+summary kernel and, for N > 1 ranks, one all-gather of the summaries.  Workload at N = 1:
+BASELINE.json configs[3] — quadruped SRBD, horizon 100, 1024 trajectories, fp64.  For N > 1 every rank keeps
+1024 trajectories (weak scaling; 8 ranks = the 8192 trajectories of configs[4]).
+
+Prints ONE JSON line (rank 0).  See DESIGN.md §6 for how every field is measured.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+from ungar_b200 import workloads as W  # noqa: E402
+
+METRIC = "shooting_nodes_per_sec_fwd_jac_quadruped_nmpc_N100"
+UNIT = "nodes/s"
+FALLBACK_HBM_GBS = 6650.0  # /opt/skills/guides/B200_PROFILING.md, used only if MEASURED_PEAKS.json is absent
+BARRIER = {W.QUADROTOR: (100.0, 2e-5), W.RC_CAR: (100.0, 1e-2), W.QUADRUPED: (1.0, 1.0)}
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=400)
+    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
+    ap.add_argument("--model", default="quadruped", choices=list(W.MODEL_IDS))
+    ap.add_argument("--horizon", type=int, default=100)
+    ap.add_argument("--batch", type=int, default=1024, help="trajectories per GPU")
+    ap.add_argument("--dtype", default="f64", choices=["f32", "f64"])
+    ap.add_argument("--cpu-seconds", type=float, default=15.0, help="CPU work budget of the cpu_baseline leg")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+# ------------------------------------------------------------------------------------------------------
+# Workload description shared by both arms
+# ------------------------------------------------------------------------------------------------------
+def workload_config(args, world: int) -> dict:
+    return {
+        "workload": f"{args.model} NMPC KKT sweep, N={args.horizon}, {args.batch} trajectories/GPU, {args.dtype} "
+                    f"(BASELINE.json configs[3]; {world} GPU(s) -> {args.batch * world} trajectories)",
+        "model_problem": args.model, "horizon": args.horizon, "batch_per_gpu": args.batch,
+        "global_batch": args.batch * world, "parallelism": f"independent trajectories sharded over {world} rank(s)",
+        "l2_policy": "no flush: each step streams 1.35 GB of records (> 126 MB L2) and the inputs rotate over 4 buffers "
+                     "(220 MB > L2)",
+    }
+
+
+def algorithmic_bytes_per_trajectory(layout: dict, elem: int) -> int:
+    """every input scalar read once + every output scalar written once (padding excluded;
+    quadruped contact rows in their compact 4x20 form, 4x10 for k = 0)."""
+    L = layout
+    N = L["horizon"]
+    contact = N * L["legs"] * 80 - L["legs"] * 40 if L["legs"] else 0
+    scalars = (L["n_dec"] + L["n_par"] + L["m_eq"] + N * L["nx"] * L["nz"] + contact + L["m_ineq"] + 2 + L["n_dec"] +
+               N * L["tri"] + L["tri_terminal"] + (N - 1) * L["hc_per_node"])
+    return scalars * elem
+
+
+def measured_peak_gbs():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        with open(path) as f:
+            return float(json.load(f)["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs (of measured)"
+    except Exception:
+        return FALLBACK_HBM_GBS, "B200_PROFILING.md fallback (of fallback)"
+
+
+def recorded_traffic(key: str):
+    try:
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+            return json.load(f).get(key)
+    except Exception:
+        return None
+
+
+# ------------------------------------------------------------------------------------------------------
+# Clock sampling during the timed region (B200_PROFILING.md "clocks line")
+# ------------------------------------------------------------------------------------------------------
+class ClockSampler:
+    FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+              "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.samples = []
+        self.windows = []
+        self._proc = None
+        self._thread = None
+        self.index = index
+
+    def start(self):
+        try:
+            self._proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits",
+                 "-lms", "50"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except Exception:
+            self._proc = None
+            return
+        self._thread = threading.Thread(target=self._pump, daemon=True)
+        self._thread.start()
+
+    def _pump(self):
+        for line in self._proc.stdout:
+            parts = [p.strip() for p in line.split(",")]
+            if len(parts) >= 7:
+                try:
+                    self.samples.append((time.time(), float(parts[0]), float(parts[1]), parts[3:7]))
+                except ValueError:
+                    pass
+
+    def window(self, t0, t1):
+        self.windows.append((t0, t1))
+
+    def stop(self) -> dict:
+        if self._proc is not None:
+            self._proc.terminate()  # the exact PID we started
+            try:
+                self._proc.wait(timeout=5)
+            except Exception:
+                self._proc.kill()
+        inside = [s for s in self.samples if any(a - 0.05 <= s[0] <= b + 0.05 for a, b in self.windows)]
+        use = inside or self.samples
+        if not use:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({n for s in use for n, v in zip(names, s[3]) if v.lower().startswith("active")})
+        return {"sm_mhz": statistics.median(s[1] for s in use), "sm_max_mhz": max(s[2] for s in use),
+                "reasons": reasons, "samples": len(use), "samples_in_timed_region": len(inside)}
+
+
+# ------------------------------------------------------------------------------------------------------
+# CPU arm: the oracle's stage-wise port (kind "port"; the reference itself cannot be built: DESIGN.md §4)
+# ------------------------------------------------------------------------------------------------------
+def cpu_sweep_runner(args):
+    """Returns (run(sample_xp) -> (seconds, records), threads).  ORACLE USE: timed CPU baseline only."""
+    import oracle
+
+    oracle.build()
+    orc = oracle.Oracle(fast=True)
+    threads = os.cpu_count() or 1
+    mid = W.MODEL_IDS[args.model]
+    k, eps = BARRIER[mid]
+    size = orc.record_layout(mid, args.horizon)["size"]
+
+    def run(xp):
+        out = np.empty((xp.shape[0], size))
+        t0 = time.perf_counter()
+        orc.stage_sweep(mid, args.horizon, xp, k, eps, threads=threads, out=out)
+        return time.perf_counter() - t0, out
+
+    return run, threads
+
+
+def cpu_sample_size(run, threads, xp_pool, seconds):
+    probe = xp_pool[:min(len(xp_pool), 2 * threads)]
+    run(probe)  # warm caches / page in
+    t, _ = run(probe)
+    per_traj = t / len(probe)
+    n = int(max(threads, min(len(xp_pool), seconds / max(per_traj, 1e-9))))
+    return max(threads, (n // threads) * threads)
+
+
+def reference_arm(args, rank: int, world: int):
+    if rank != 0:
+        return  # the CPU arm has no multi-process path: rank 0 alone runs and prints it
+    mid = W.MODEL_IDS[args.model]
+    run, threads = cpu_sweep_runner(args)
+    pool = W.synthetic_batch(mid, args.horizon, min(args.batch, 1024), seed=20240807)
+    total_steps = args.steps + args.warmup
+    per_step = min(60.0 / max(total_steps, 1), 10.0)  # whole run within ~1-2 minutes
+    n = cpu_sample_size(run, threads, pool, per_step)
+    sample = pool[:n]
+    for _ in range(args.warmup):
+        run(sample)
+    t_total = 0.0
+    for _ in range(args.steps):
+        t, _ = run(sample)
+        t_total += t
+    value = n * args.horizon * args.steps / t_total
+    desc = (f"{n} of the workload's {args.batch} trajectories per step, {args.steps} steps, fp64, "
+            f"oracle/stage_port.cpp built -O3 -ffast-math -march=x86-64-v3")
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": 1e3 * t_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic", "impl": "reference", "config": workload_config(args, 1),
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": desc},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+        "note": "CPU arm: the reference's CppAD/CppADCodeGen path cannot be built offline; this is the oracle's "
+                "stage-wise port of the same assembly on all host threads (rank 0 only).",
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------------
+# Our arm
+# ------------------------------------------------------------------------------------------------------
+def ours(args, rank: int, local_rank: int, world: int):
+    import torch
+    import torch.distributed as dist
+
+    import ungar_b200
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the product path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    mid = W.MODEL_IDS[args.model]
+    B, N = args.batch, args.horizon
+    model = ungar_b200.Model(args.model, N, dtype=args.dtype, device=local_rank, barrier=BARRIER[mid])
+    tdt = torch.float64 if args.dtype == "f64" else torch.float32
+    elem = 8 if args.dtype == "f64" else 4
+    L = model.layout
+
+    # synthetic inputs: host copy in pinned memory (e2e leg), 4 rotating device copies (device-resident leg)
+    xp_np = W.synthetic_batch(mid, N, B, seed=20240807 + rank).astype(model.np_dtype)
+    xp_host = torch.empty((B, model.n_xp), dtype=tdt, pin_memory=True)
+    xp_host.copy_(torch.from_numpy(xp_np))
+    d_xps = [xp_host.to(dev, non_blocking=True).clone() for _ in range(4)]
+    d_rec = torch.empty((B, L["size"]), dtype=tdt, device=dev)
+    d_sum = torch.empty((B, 32), dtype=tdt, device=dev)
+    gathered = torch.empty((world * B, 32), dtype=tdt, device=dev) if world > 1 else None
+    sum_host = torch.empty((B, 32), dtype=tdt, pin_memory=True)
+
+    def step(i):
+        model.step(d_xps[i % 4], records=d_rec, summaries=d_sum)
+        if world > 1:
+            dist.all_gather_into_tensor(gathered, d_sum)
+
+    def fence():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    if sampler:
+        sampler.start()
+
+    # ---- device-resident leg -----------------------------------------------------------------------
+    for i in range(max(args.warmup, 3)):
+        step(i)
+    fence()
+    model.set_profiling(True)
+    launches0 = model.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0 = time.time()
+    e0.record()
+    for i in range(args.steps):
+        step(i)
+    e1.record()
+    fence()
+    t1 = time.time()
+    launches = model.launch_count() - launches0
+    sweep_ms = model.sweep_times_ms()
+    model.set_profiling(False)
+    if sampler:
+        sampler.window(t0, t1)
+    elapsed_ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(elapsed_ms, op=dist.ReduceOp.MAX)
+    elapsed_ms = float(elapsed_ms.item())
+    value = world * B * N * args.steps / (elapsed_ms * 1e-3)
+
+    # ---- end-to-end leg: host buffers through the C ABI, H2D of the inputs + D2H of the summaries per step ----
+    e2e_steps = max(10, min(args.steps, 100))
+    xp_host_np, sum_host_np = xp_host.numpy(), sum_host.numpy()
+    for _ in range(3):
+        model.step(xp_host_np, records=d_rec, summaries=sum_host_np)
+    fence()
+    t0 = time.time()
+    e0.record()
+    for _ in range(e2e_steps):
+        model.step(xp_host_np, records=d_rec, summaries=sum_host_np)
+        if world > 1:
+            dist.all_gather_into_tensor(gathered, d_sum)
+    e1.record()
+    fence()
+    t1 = time.time()
+    if sampler:
+        sampler.window(t0, t1)
+    e2e_ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(e2e_ms, op=dist.ReduceOp.MAX)
+    e2e_value = world * B * N * e2e_steps / (float(e2e_ms.item()) * 1e-3)
+
+    # full drop-in variant: the whole record goes back to the host every step (what a host-side QP solver needs)
+    full_value = None
+    if world == 1:
+        try:
+            rec_host = torch.empty((B, L["size"]), dtype=tdt, pin_memory=True).numpy()
+            model.kkt_blocks(xp_host_np, rec_host)
+            t0 = time.perf_counter()
+            reps = 3
+            for _ in range(reps):
+                model.kkt_blocks(xp_host_np, rec_host)
+            full_value = B * N * reps / (time.perf_counter() - t0)
+        except Exception:
+            full_value = None
+    clocks = sampler.stop() if sampler else None
+
+    if rank != 0:
+        if world > 1:
+            dist.barrier()
+            dist.destroy_process_group()
+        return
+
+    # ---- roofline of the dominant kernel (the sweep), from device events around each launch ---------------
+    bytes_per_launch = algorithmic_bytes_per_trajectory(L, elem) * B
+    peak, peak_src = measured_peak_gbs()
+    mean_sweep_ms = statistics.fmean(sweep_ms) if sweep_ms else elapsed_ms / args.steps
+    achieved = bytes_per_launch / (mean_sweep_ms * 1e-3) / 1e9
+    key = f"{args.model}_{args.dtype}_N{N}_B{B}"
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": recorded_traffic(key), "kernel": "kkt_sweep", "kernel_ms": mean_sweep_ms,
+                "algorithmic_bytes_per_launch": bytes_per_launch, "peak_source": peak_src,
+                "kernel_share_of_step": mean_sweep_ms / (elapsed_ms / args.steps)}
+
+    # ---- CPU baseline on this box's host cores (bounded sample of the same workload) + parity gate -----------
+    cpu = None
+    parity = None
+    if world == 1 and not args.no_cpu_baseline:
+        run, threads = cpu_sweep_runner(args)
+        pool = xp_np.astype(np.float64)
+        n = cpu_sample_size(run, threads, pool, args.cpu_seconds)
+        t, ref = run(pool[:n])
+        cpu = {"value": n * N / t, "unit": UNIT, "cores": threads, "kind": "port",
+               "sample": f"first {n} of the {B} trajectories, one pass, fp64, oracle/stage_port.cpp on {threads} threads "
+                         f"({t:.2f} s)"}
+        got = d_rec_sample(model, d_xps[0], n, tdt, dev)
+        tol = 1e-6 if args.dtype == "f64" else 1e-3
+        err = float(np.max(np.abs(got - ref) / (np.abs(ref) + 1e-3 * np.max(np.abs(ref)))))
+        parity = {"checked_trajectories": n, "max_rel_err": err, "tolerance": tol, "ok": bool(err <= tol)}
+        if not parity["ok"]:
+            print(json.dumps({"error": "parity gate failed", "parity": parity}), flush=True)
+            raise SystemExit(2)
+
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+        "ms_per_step": elapsed_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": args.dtype, "data": "synthetic", "config": workload_config(args, world), "clocks": clocks,
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": B * model.n_xp * elem,
+                "d2h_bytes_per_step": B * 32 * elem, "steps": e2e_steps,
+                "path": "ungar_b200_kkt_step(MEM_HOST): pinned host xp -> H2D -> sweep (records stay in HBM) -> summaries -> D2H"},
+        "e2e_full_record_d2h": ({"value": full_value, "unit": UNIT, "d2h_bytes_per_step": B * L["size"] * elem,
+                                 "path": "ungar_b200_kkt_blocks(MEM_HOST): whole record back to the host every step"}
+                                if full_value else None),
+        "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu, "parity": parity,
+    }
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def d_rec_sample(model, d_xp, n, tdt, dev):
+    import torch
+
+    out = torch.zeros((n, model.layout["size"]), dtype=tdt, device=dev)
+    model.kkt_blocks(d_xp[:n], out)
+    torch.cuda.synchronize()
+    return out.cpu().numpy().astype(np.float64)
+
+
+def main():
+    args = parse_args()
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        reference_arm(args, rank, world)
+        return
+    if args.gpus > 1 and world == 1:  # convenience: relaunch under torchrun
+        cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={args.gpus}",
+               "--master-addr", "127.0.0.1", "--master-port", os.environ.get("MASTER_PORT", "29511"), __file__] + sys.argv[1:]
+        raise SystemExit(subprocess.call(cmd))
+    ours(args, rank, local_rank, world)
+
+
+if __name__ == "__main__":
+    main()

@@ -143,6 +143,19 @@ int ungar_b200_kkt_blocks(ungar_b200_model* model, const void* xp, int64_t batch
 int ungar_b200_summaries(ungar_b200_model* model, const void* xp, int64_t batch, int64_t ld_xp,
                          const void* records, int64_t ld_rec, void* summaries, void* stream);
 
+/* One outer-iteration step of the B200-native data flow: inputs `xp` (host or device per `mem`), the KKT
+ * records stay resident in HBM (`records_device`, a DEVICE pointer, or NULL to use the handle's workspace)
+ * for the on-device consumers, and only the per-trajectory summaries go back (`summaries`, host or device per
+ * `mem`).  With UNGAR_B200_MEM_HOST the call returns after the summaries have landed. */
+int ungar_b200_kkt_step(ungar_b200_model* model, const void* xp, int64_t batch, int64_t ld_xp, void* records_device,
+                        int64_t ld_rec, void* summaries, int32_t mem, void* stream);
+
+/* Device-side timing of the dominant kernel (the KKT sweep): when enabled, every sweep launch is bracketed by
+ * CUDA events on the launching stream; ungar_b200_sweep_times synchronises and returns up to `cap` most recent
+ * durations in milliseconds (oldest first) and clears the ring. */
+int ungar_b200_set_profiling(int32_t enabled);
+int ungar_b200_sweep_times(float* ms, int32_t cap, int32_t* count);
+
 /* Number of kernel launches this library has issued in the calling process (bench accounting). */
 int64_t ungar_b200_launch_count(void);
 

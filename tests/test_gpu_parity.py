@@ -206,11 +206,12 @@ def test_full_size_properties(torch_cuda, oracle, name, N, dtype, B):
     # first-order consistency of A with g (linearity): g(x + dz) - g(x) ~ J dz for a tiny step in x_k, u_k
     blocks = model.split_record(got[:2])
     L = model.layout
-    step = 1e-6 if dtype == "f64" else 1e-2
+    step = 1e-6 if dtype == "f64" else 1e-3
     dz = np.random.default_rng(1).standard_normal(L["n_dec"]) * step
     xq = xp[:2].astype(np.float64).copy()
     xq[:, :L["n_dec"]] += dz
     g1 = model.equalityConstraints(xq.astype(model.np_dtype)).astype(np.float64)
     J = model.equalityConstraints.Jacobian(xp[0])
-    lin = blocks["g"][0] + J @ dz
-    assert np.max(np.abs(g1[0] - lin)) < (1e-9 if dtype == "f64" else 2e-3)
+    lin = J @ dz
+    # second-order remainder (and fp32 rounding of g) relative to the size of the linear term
+    assert np.max(np.abs(g1[0] - blocks["g"][0] - lin)) < (1e-4 if dtype == "f64" else 5e-2) * np.max(np.abs(lin))

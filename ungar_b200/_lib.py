@@ -20,7 +20,8 @@ SYMBOLS = [
     "ungar_b200_model_create", "ungar_b200_model_destroy", "ungar_b200_function_info",
     "ungar_b200_jacobian_sparsity", "ungar_b200_hessian_sparsity", "ungar_b200_forward_zero",
     "ungar_b200_sparse_jacobian", "ungar_b200_sparse_hessian", "ungar_b200_kkt_layout_get",
-    "ungar_b200_kkt_blocks", "ungar_b200_summaries", "ungar_b200_launch_count", "ungar_b200_last_error",
+    "ungar_b200_kkt_blocks", "ungar_b200_summaries", "ungar_b200_kkt_step", "ungar_b200_set_profiling",
+    "ungar_b200_sweep_times", "ungar_b200_launch_count", "ungar_b200_last_error",
     "ungar_b200_abi_version",
 ]
 
@@ -71,6 +72,9 @@ def load() -> ctypes.CDLL:
     L.ungar_b200_kkt_layout_get.argtypes = [c_vp, ctypes.POINTER(KktLayout)]
     L.ungar_b200_kkt_blocks.argtypes = [c_vp, c_vp, c_i64, c_i64, c_vp, c_i64, c_i32, c_vp]
     L.ungar_b200_summaries.argtypes = [c_vp, c_vp, c_i64, c_i64, c_vp, c_i64, c_vp, c_vp]
+    L.ungar_b200_kkt_step.argtypes = [c_vp, c_vp, c_i64, c_i64, c_vp, c_i64, c_vp, c_i32, c_vp]
+    L.ungar_b200_set_profiling.argtypes = [c_i32]
+    L.ungar_b200_sweep_times.argtypes = [ctypes.POINTER(ctypes.c_float), c_i32, ctypes.POINTER(c_i32)]
     L.ungar_b200_launch_count.restype = c_i64
     L.ungar_b200_last_error.restype = ctypes.c_char_p
     L.ungar_b200_abi_version.restype = c_i32

@@ -5,18 +5,30 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
+#include <type_traits>
 #include <new>
 #include <string>
 #include <vector>
 
 #include "../../include/ungar_b200.h"
 #include "sweep.cuh"
+#include "sweep_structured.cuh"
 
 namespace {
 
 thread_local std::string g_last_error;
 std::atomic<long long> g_launches{0};
+
+// Event ring for device-side timing of the sweep kernel (ungar_b200_set_profiling).
+constexpr int kRing = 512;
+struct EventRing {
+    bool enabled = false;
+    cudaEvent_t start[kRing] = {}, stop[kRing] = {};
+    bool created[kRing] = {};
+    int head = 0, count = 0;
+} g_ring;
 
 int fail(int code, const char* fmt, ...) {
     char buf[512];
@@ -268,8 +280,73 @@ int launch_generic(ungar_b200_model& mdl, const T* xp, int64_t batch, int64_t ld
     const int tiles = (mdl.N + M - 1) / M;
     const long long grid = (long long)batch * tiles;
     if (grid > 2147483647LL) return fail(UNGAR_B200_EINVAL, "batch too large for one launch (%lld CTAs)", grid);
+    int slot = -1;
+    if (g_ring.enabled) {
+        slot = g_ring.head;
+        if (!g_ring.created[slot]) {
+            UB_CUDA(cudaEventCreate(&g_ring.start[slot]));
+            UB_CUDA(cudaEventCreate(&g_ring.stop[slot]));
+            g_ring.created[slot] = true;
+        }
+        UB_CUDA(cudaEventRecord(g_ring.start[slot], stream));
+    }
     kernel<<<(unsigned)grid, Sh::THREADS, smem, stream>>>(xp, ld_xp, rec, ld_rec, static_cast<T*>(mdl.stage_cost.ptr),
                                                           mdl.N, tiles, mdl.rl, cast_barrier<T>(mdl.bar));
+    if (slot >= 0) {
+        UB_CUDA(cudaEventRecord(g_ring.stop[slot], stream));
+        g_ring.head  = (g_ring.head + 1) % kRing;
+        g_ring.count = g_ring.count < kRing ? g_ring.count + 1 : kRing;
+    }
+    ++g_launches;
+    UB_CUDA(cudaGetLastError());
+    return UNGAR_B200_OK;
+}
+
+// Structured quadruped fp64 sweep (sweep_structured.cuh).  Needs paired nodes (even horizon) and 16-byte aligned
+// block slices for the TMA bulk stores; anything else takes the generic kernel.
+bool structured_applicable(const ungar_b200_model& mdl, const void* rec, int64_t ld_rec) {
+    static const bool forced_generic = [] {
+        const char* e = getenv("UNGAR_B200_FORCE_GENERIC");
+        return e && e[0] == '1';
+    }();
+    return !forced_generic && mdl.desc.kind == UNGAR_B200_QUADRUPED && mdl.desc.dtype == UNGAR_B200_F64 &&
+           mdl.N % 2 == 0 && ld_rec % 2 == 0 && (reinterpret_cast<uintptr_t>(rec) & 15) == 0;
+}
+
+template <bool BARRIER>
+int launch_structured(ungar_b200_model& mdl, const double* xp, int64_t batch, int64_t ld_xp, double* rec, int64_t ld_rec,
+                      cudaStream_t stream) {
+    using Q = ub::QuadrupedStructured;
+    auto kernel = ub::quadruped_structured_kernel<BARRIER>;
+    static bool configured = false;
+    static int sm_count = 148;
+    if (!configured) {
+        UB_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, Q::SMEM_BYTES));
+        UB_CUDA(cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, mdl.desc.device));
+        configured = true;
+    }
+    const int runs_per_traj = (mdl.N + 9) / 10;
+    const int run_len       = 2 * ((mdl.N + 2 * runs_per_traj - 1) / (2 * runs_per_traj));
+    const long long total_runs = (long long)batch * runs_per_traj;
+    const long long want = (total_runs + Q::WARPS - 1) / Q::WARPS;
+    const unsigned grid  = unsigned(std::min<long long>(want, (long long)sm_count * 3));  // persistent: 3 CTAs / SM
+    int slot = -1;
+    if (g_ring.enabled) {
+        slot = g_ring.head;
+        if (!g_ring.created[slot]) {
+            UB_CUDA(cudaEventCreate(&g_ring.start[slot]));
+            UB_CUDA(cudaEventCreate(&g_ring.stop[slot]));
+            g_ring.created[slot] = true;
+        }
+        UB_CUDA(cudaEventRecord(g_ring.start[slot], stream));
+    }
+    kernel<<<grid, Q::WARPS * 32, Q::SMEM_BYTES, stream>>>(xp, ld_xp, rec, ld_rec, static_cast<double*>(mdl.stage_cost.ptr),
+                                                           mdl.N, run_len, runs_per_traj, total_runs, mdl.rl, mdl.bar);
+    if (slot >= 0) {
+        UB_CUDA(cudaEventRecord(g_ring.stop[slot], stream));
+        g_ring.head  = (g_ring.head + 1) % kRing;
+        g_ring.count = g_ring.count < kRing ? g_ring.count + 1 : kRing;
+    }
     ++g_launches;
     UB_CUDA(cudaGetLastError());
     return UNGAR_B200_OK;
@@ -288,7 +365,14 @@ int launch_sweep_t(ungar_b200_model& mdl, const void* xp, int64_t batch, int64_t
         else return fail(UNGAR_B200_ECUDA, "J_h kernel launch failed: %s", cudaGetErrorString(cudaError_t(rc)));
         return UNGAR_B200_OK;
     }
-    if (mode == MODE_KKT) rc = launch_generic<Mdl, T, M, true>(mdl, x, batch, ld_xp, r, ld_rec, stream);
+    if constexpr (std::is_same<Mdl, ub::Quadruped>::value && std::is_same<T, double>::value) {
+        if (structured_applicable(mdl, rec, ld_rec))
+            rc = mode == MODE_KKT ? launch_structured<true>(mdl, x, batch, ld_xp, r, ld_rec, stream)
+                                  : launch_structured<false>(mdl, x, batch, ld_xp, r, ld_rec, stream);
+        else
+            rc = mode == MODE_KKT ? launch_generic<Mdl, T, M, true>(mdl, x, batch, ld_xp, r, ld_rec, stream)
+                                  : launch_generic<Mdl, T, M, false>(mdl, x, batch, ld_xp, r, ld_rec, stream);
+    } else if (mode == MODE_KKT) rc = launch_generic<Mdl, T, M, true>(mdl, x, batch, ld_xp, r, ld_rec, stream);
     else rc = launch_generic<Mdl, T, M, false>(mdl, x, batch, ld_xp, r, ld_rec, stream);
     if (rc) return rc;
     const int threads = 128;
@@ -544,6 +628,63 @@ int ungar_b200_kkt_blocks(ungar_b200_model* model, const void* xp, int64_t batch
     UB_CUDA(cudaMemcpy2DAsync(records, ld_rec * es, model->ws_records.ptr, L.size * es, L.size * es, batch,
                               cudaMemcpyDeviceToHost, stream));
     UB_CUDA(cudaStreamSynchronize(stream));
+    return UNGAR_B200_OK;
+}
+
+int ungar_b200_set_profiling(int32_t enabled) {
+    g_ring.enabled = enabled != 0;
+    g_ring.head = g_ring.count = 0;
+    return UNGAR_B200_OK;
+}
+
+int ungar_b200_sweep_times(float* ms, int32_t cap, int32_t* count) {
+    if (!ms || !count || cap < 0) return fail(UNGAR_B200_EINVAL, "null argument");
+    const int n = g_ring.count < cap ? g_ring.count : cap;
+    for (int i = 0; i < n; ++i) {
+        const int slot = ((g_ring.head - n + i) % kRing + kRing) % kRing;
+        UB_CUDA(cudaEventSynchronize(g_ring.stop[slot]));
+        UB_CUDA(cudaEventElapsedTime(&ms[i], g_ring.start[slot], g_ring.stop[slot]));
+    }
+    *count = n;
+    g_ring.head = g_ring.count = 0;
+    return UNGAR_B200_OK;
+}
+
+int ungar_b200_kkt_step(ungar_b200_model* model, const void* xp, int64_t batch, int64_t ld_xp, void* records_device,
+                        int64_t ld_rec, void* summaries, int32_t mem, void* stream_) {
+    if (!model) return fail(UNGAR_B200_EINVAL, "null model");
+    if (batch < 0 || (batch > 0 && (!xp || !summaries))) return fail(UNGAR_B200_EINVAL, "null buffer");
+    const ungar_b200_kkt_layout& L = model->layout;
+    const int64_t n_in = L.n_dec + L.n_par;
+    if (ld_xp < n_in) return fail(UNGAR_B200_EINVAL, "ld_xp %lld < %lld", (long long)ld_xp, (long long)n_in);
+    if (mem != UNGAR_B200_MEM_DEVICE && mem != UNGAR_B200_MEM_HOST) return fail(UNGAR_B200_EINVAL, "unknown mem %d", mem);
+    if (batch == 0) return UNGAR_B200_OK;
+    UB_CUDA(cudaSetDevice(model->desc.device));
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    const size_t es = model->elem;
+    if (!records_device) {
+        if (int rc = model->ws_records.reserve(size_t(batch) * L.size * es)) return rc;
+        records_device = model->ws_records.ptr;
+        ld_rec = L.size;
+    } else if (ld_rec < L.size) {
+        return fail(UNGAR_B200_EINVAL, "ld_rec %lld < record size %lld", (long long)ld_rec, (long long)L.size);
+    }
+    const void* d_xp = xp;
+    int64_t d_ld_xp  = ld_xp;
+    void* d_summ     = summaries;
+    if (mem == UNGAR_B200_MEM_HOST) {
+        if (int rc = model->ws_xp.reserve(size_t(batch) * n_in * es)) return rc;
+        if (int rc = model->ws_out.reserve(size_t(batch) * UNGAR_B200_SUMMARY_SIZE * es)) return rc;
+        if (ld_xp == n_in) UB_CUDA(cudaMemcpyAsync(model->ws_xp.ptr, xp, size_t(batch) * n_in * es, cudaMemcpyHostToDevice, stream));
+        else UB_CUDA(cudaMemcpy2DAsync(model->ws_xp.ptr, n_in * es, xp, ld_xp * es, n_in * es, batch, cudaMemcpyHostToDevice, stream));
+        d_xp = model->ws_xp.ptr; d_ld_xp = n_in; d_summ = model->ws_out.ptr;
+    }
+    if (int rc = launch_sweep(*model, d_xp, batch, d_ld_xp, records_device, ld_rec, MODE_KKT, stream)) return rc;
+    if (int rc = ungar_b200_summaries(model, d_xp, batch, d_ld_xp, records_device, ld_rec, d_summ, stream)) return rc;
+    if (mem == UNGAR_B200_MEM_HOST) {
+        UB_CUDA(cudaMemcpyAsync(summaries, d_summ, size_t(batch) * UNGAR_B200_SUMMARY_SIZE * es, cudaMemcpyDeviceToHost, stream));
+        UB_CUDA(cudaStreamSynchronize(stream));
+    }
     return UNGAR_B200_OK;
 }
 

@@ -124,6 +124,25 @@ class Model:
                                              records.stride(0), out.data_ptr(), _torch_stream()))
         return out
 
+    def step(self, xp, records=None, summaries=None):
+        """One outer-iteration step: KKT records stay in HBM (``records``: CUDA tensor or None for the handle's
+        workspace), per-trajectory summaries ``[B, 32]`` come back where ``xp`` lives (numpy -> host)."""
+        xp2, out2, mem, stream, _ = self._buffers(xp, summaries, _lib.SUMMARY_SIZE)
+        rec_ptr, rec_ld = (records.data_ptr(), records.stride(0)) if records is not None else (None, 0)
+        check(self._lib.ungar_b200_kkt_step(self._handle, self._ptr(xp2), xp2.shape[0], self._ld(xp2), rec_ptr, rec_ld,
+                                            self._ptr(out2), mem, stream))
+        return out2
+
+    def set_profiling(self, enabled: bool) -> None:
+        check(self._lib.ungar_b200_set_profiling(int(enabled)))
+
+    def sweep_times_ms(self) -> list:
+        """Device durations (ms) of the sweep-kernel launches since profiling was enabled (synchronises)."""
+        buf = (ctypes.c_float * 512)()
+        n = ctypes.c_int32()
+        check(self._lib.ungar_b200_sweep_times(buf, 512, ctypes.byref(n)))
+        return [float(buf[i]) for i in range(n.value)]
+
     def launch_count(self) -> int:
         return int(self._lib.ungar_b200_launch_count())
 
