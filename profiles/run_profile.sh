@@ -10,6 +10,6 @@ python bench.py --steps 200 --warmup 10 > gpurun_out/bench_${TAG}.json 2> gpurun
 tail -c 3000 gpurun_out/bench_${TAG}.json
 ncu --metrics gpu__time_duration.sum --clock-control none -c 200 --csv --log-file gpurun_out/launches_${TAG}.csv \
     python bench.py --steps 20 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_launches_${TAG}.log 2>&1
-ncu --set full --clock-control none --import-source on -k regex:kkt_sweep -s 4 -c 2 -f -o gpurun_out/sweep_${TAG} \
+ncu --set full --clock-control none --import-source on -k regex:"sweep|structured" -s 4 -c 2 -f -o gpurun_out/sweep_${TAG} \
     python bench.py --steps 5 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_full_${TAG}.log 2>&1
 ls -la gpurun_out

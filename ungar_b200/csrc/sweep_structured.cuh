@@ -1,23 +1,26 @@
-// KKT stage sweep of the quadruped single-rigid-body NMPC, structured version: ONE WARP OWNS ONE SHOOTING
-// NODE at a time and walks a run of consecutive nodes of one trajectory.
+// KKT stage sweep of the quadruped single-rigid-body NMPC, structured version: a warp walks a run of up to 10
+// consecutive shooting nodes of one trajectory and OWNS ONE NODE AT A TIME when it fills the blocks.
 //
-// Why a second kernel: the generic sweep (sweep.cuh) pushes one dense tangent per thread through the whole
-// stage and needs ~250 registers in fp64.  Here the chain rule is applied by hand through the model's
-// bottlenecks — everything downstream of (q, w, f_i, r_i) goes through the 3-vector w+ = w + dt I^-1 tau and
-// the 4x3 matrix Qw = d q+ / d w+ — so a node costs ~700 fp64 instructions per lane instead of ~50 000 per
-// node, and the kernel becomes what the roofline says it should be: a stream of stores.
+// Why a second kernel: the generic sweep (sweep.cuh) pushes one dense tangent per thread through the whole stage
+// (~50 000 fp64 instructions per node, ~250 registers).  Here the chain rule is applied by hand through the model's
+// bottlenecks — everything downstream of (q, w, f_i, r_i) goes through the 3-vector w+ = w + dt I^-1 tau and the 4x3
+// matrix Qw = d q+ / d w+ — and the work is split in two phases so nothing is computed 32 times:
 //
-// Data flow per warp (persistent, grid = #SMs x resident CTAs):
-//   inputs   flat Ungar vector [X | U | P | Rho] of the trajectory, read through L1 (4 % of the traffic)
-//   staging  per-warp shared-memory image of the A, H and C blocks of TWO consecutive nodes (24 064 B).  It is
-//            zeroed once; every node rewrites exactly the structurally non-zero slots, so the ~65 % zeros of the
-//            dense blocks never cost an instruction again
-//   stores   one elected lane issues three TMA bulk copies (cp.async.bulk.global.shared::cta, SASS UBLKCP) per
-//            node pair: 7 696 + 11 248 + 5 120 B, 16-byte aligned because nodes are paired; the small vectors
-//            (g, h, grad: 5 % of the bytes) go out as plain coalesced stores from registers
+//   phase 0  the run's slice of the flat Ungar vector (x_{k0-1..k0+10}, u_{k0-1..k0+9}, p_{k0-1..k0+9}; 5.9 KB) is
+//            copied into shared memory with cp.async (LDGSTS, 8-byte granules: the Ungar layout is not 16-byte aligned),
+//            so the only exposed HBM latency is once per run and every later read is an LDS
+//   phase A  thread-per-node: lane j computes the node-global primal "core" of node k0 + j - 1 (rotation matrix, Lie-Euler
+//            step, exponential map and Qw; one sincos / sqrt / divide per node) and parks 39 doubles in shared memory
+//   phase B  warp-per-node: for each node the 32 lanes take one column of d w+/d z each (24 input columns, 4 + 3 state
+//            columns), the rows of the Gauss-Newton block and of the contact Jacobians of "their" leg, and write ONLY the
+//            structurally non-zero slots into a per-warp shared-memory image of the A, H and C blocks of a node PAIR.
+//            The image is zeroed once per kernel; the ~65 % zeros of the dense blocks never cost an instruction again
+//   stores   one elected lane hands the image to the TMA engine: three cp.async.bulk.global.shared::cta copies per pair
+//            (7 696 + 11 248 + 5 120 B; 16-byte aligned because nodes are paired; SASS UBLKCP).  The small vectors
+//            (g, h, grad: 5 % of the bytes) leave as plain coalesced stores from registers.
 //
-// Reference lines restated: quadruped.example.cpp:148-203 (dynamics), :209-251 (objective), :279-303 (contact
-// rows), :312-338 (inequalities); soft_sqp.hpp:141-158, :245-264 (assembly); soft_inequality_constraint.hpp:133-190.
+// Reference lines restated: quadruped.example.cpp:148-203 (dynamics), :209-251 (objective), :279-303 (contact rows),
+// :312-338 (inequalities); soft_sqp.hpp:141-158, :245-264 (assembly); soft_inequality_constraint.hpp:133-190.
 #pragma once
 
 #include "sweep.cuh"
@@ -25,11 +28,18 @@
 namespace ub {
 
 struct QuadrupedStructured {
-    static constexpr int NX = 13, NU = 24, NZ = 37, TRI = 703, NA = NX * NZ, NC = 320;
+    static constexpr int NX = 13, NU = 24, NZ = 37, NP = 29, TRI = 703, NA = NX * NZ, NC = 320;
     static constexpr int PAIR_A = 2 * NA, PAIR_H = 2 * TRI, PAIR_C = 2 * NC;
-    static constexpr int STAGE = PAIR_A + PAIR_H + PAIR_C;  // doubles per warp = 3008 (24 064 B)
-    static constexpr int WARPS = 3;                          // per CTA; 3 CTAs / SM -> 9 warps, 216.6 KB smem
-    static constexpr int SMEM_BYTES = WARPS * STAGE * 8;
+    static constexpr int STAGE = PAIR_A + PAIR_H + PAIR_C;  // 3008 doubles
+    static constexpr int RUN = 10;                          // nodes per run (even)
+    static constexpr int CORE = 41;                         // doubles per node core (odd stride: conflict-free)
+    static constexpr int oCORE = STAGE, oXS = oCORE + 452, oUS = oXS + (RUN + 2) * NX, oPS = oUS + (RUN + 1) * NU,
+                         PER_WARP = 4200;                   // doubles per warp (33 600 B, multiple of 16)
+    static_assert(oPS + (RUN + 1) * NP <= PER_WARP, "per-warp shared memory layout");
+    static constexpr int WARPS = 2;                         // per CTA; 3 CTAs / SM -> 6 warps, 201.6 KB smem
+    static constexpr int SMEM_BYTES = WARPS * PER_WARP * 8;
+    // core slot layout
+    static constexpr int cR = 0, cQ = 9, cE = 21, cXN = 25, cSGN = 38;
 };
 
 __device__ __forceinline__ double pick3(int c, double a0, double a1, double a2) { return c == 0 ? a0 : (c == 1 ? a1 : a2); }
@@ -44,22 +54,17 @@ __device__ __forceinline__ void drot_dq(int c, double qx, double qy, double qz, 
     const double a0 = 2.0 * (e0 * qv_v + qx * vc - 2.0 * v0 * qc) + 2.0 * qw * (e1 * v2 - e2 * v1);
     const double a1 = 2.0 * (e1 * qv_v + qy * vc - 2.0 * v1 * qc) + 2.0 * qw * (e2 * v0 - e0 * v2);
     const double a2 = 2.0 * (e2 * qv_v + qz * vc - 2.0 * v2 * qc) + 2.0 * qw * (e0 * v1 - e1 * v0);
-    // c == 3: 2 (qv x v)
-    const bool isw = c == 3;
+    const bool isw = c == 3;  // 2 (qv x v)
     o0 = isw ? 2.0 * (qy * v2 - qz * v1) : a0;
     o1 = isw ? 2.0 * (qz * v0 - qx * v2) : a1;
     o2 = isw ? 2.0 * (qx * v1 - qy * v0) : a2;
 }
 
-struct Rot3 {
-    double m00, m01, m02, m10, m11, m12, m20, m21, m22;
-};
-__device__ __forceinline__ Rot3 rot_matrix(double x, double y, double z, double w) {
-    Rot3 R;
-    R.m00 = 1.0 - 2.0 * (y * y + z * z); R.m01 = 2.0 * (x * y - w * z);       R.m02 = 2.0 * (x * z + w * y);
-    R.m10 = 2.0 * (x * y + w * z);       R.m11 = 1.0 - 2.0 * (x * x + z * z); R.m12 = 2.0 * (y * z - w * x);
-    R.m20 = 2.0 * (x * z - w * y);       R.m21 = 2.0 * (y * z + w * x);       R.m22 = 1.0 - 2.0 * (x * x + y * y);
-    return R;
+// R with R v = v + 2 w (qv x v) + 2 qv x (qv x v)  (Eigen/src/Geometry/Quaternion.h:531-541), row-major into out[9].
+__device__ __forceinline__ void rot_matrix(double x, double y, double z, double w, double* out) {
+    out[0] = 1.0 - 2.0 * (y * y + z * z); out[1] = 2.0 * (x * y - w * z);       out[2] = 2.0 * (x * z + w * y);
+    out[3] = 2.0 * (x * y + w * z);       out[4] = 1.0 - 2.0 * (x * x + z * z); out[5] = 2.0 * (y * z - w * x);
+    out[6] = 2.0 * (x * z - w * y);       out[7] = 2.0 * (y * z + w * x);       out[8] = 1.0 - 2.0 * (x * x + y * y);
 }
 
 __device__ __forceinline__ double warp_sum(double v) {
@@ -73,8 +78,71 @@ __device__ __forceinline__ void bulk_store(void* gmem, const void* smem, unsigne
                  "r"((unsigned)__cvta_generic_to_shared(smem)), "r"(bytes)
                  : "memory");
 }
+__device__ __forceinline__ void async_copy8(double* smem, const double* gmem) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((unsigned)__cvta_generic_to_shared(smem)), "l"(gmem) : "memory");
+}
 
-// One warp = one run of `run_len` consecutive nodes (even start, even length) of one trajectory.
+// Phase A: node-global primal core of one node (thread-per-node), written to `core`.
+__device__ __forceinline__ void node_core(const double* __restrict__ xk, const double* __restrict__ uk,
+                                          const double* __restrict__ pk, double dt, double inv_m, double g0, double I0,
+                                          double I1, double I2, double iI0, double iI1, double iI2, double* __restrict__ core) {
+    using Q = QuadrupedStructured;
+    const double qx = xk[3], qy = xk[4], qz = xk[5], qw = xk[6];
+    const double w0 = xk[10], w1 = xk[11], w2 = xk[12];
+    double R[9];
+    rot_matrix(qx, qy, qz, qw, R);
+    double a0 = 0.0, a1 = 0.0, a2 = -g0;  // p'' = -g e_z + sum s_i f_i / m                   (quadruped.example.cpp:168,176)
+    const double Iw0 = I0 * w0, Iw1 = I1 * w1, Iw2 = I2 * w2;
+    double t0 = -(w1 * Iw2 - w2 * Iw1), t1 = -(w2 * Iw0 - w0 * Iw2), t2 = -(w0 * Iw1 - w1 * Iw0);  // -w x I w   (:169)
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const double f0 = uk[6 * i], f1 = uk[6 * i + 1], f2 = uk[6 * i + 2];
+        const double r0 = uk[6 * i + 3], r1 = uk[6 * i + 4], r2 = uk[6 * i + 5];
+        const double s = pk[13 + 4 * i];
+        const double Rf0 = R[0] * f0 + R[1] * f1 + R[2] * f2, Rf1 = R[3] * f0 + R[4] * f1 + R[5] * f2,
+                     Rf2 = R[6] * f0 + R[7] * f1 + R[8] * f2;
+        a0 += s * f0 * inv_m; a1 += s * f1 * inv_m; a2 += s * f2 * inv_m;
+        t0 += s * (r1 * Rf2 - r2 * Rf1); t1 += s * (r2 * Rf0 - r0 * Rf2); t2 += s * (r0 * Rf1 - r1 * Rf0);  // (:177)
+    }
+    // Lie-group semi-implicit Euler (:197-200)
+    const double vn0 = xk[7] + dt * a0, vn1 = xk[8] + dt * a1, vn2 = xk[9] + dt * a2;
+    const double wn0 = w0 + dt * (t0 * iI0), wn1 = w1 + dt * (t1 * iI1), wn2 = w2 + dt * (t2 * iI2);
+    const double y0 = dt * wn0, y1 = dt * wn1, y2 = dt * wn2;
+    const double nn = sqrt(y0 * y0 + y1 * y1 + y2 * y2 + UB_EPS);  // Utils::ApproximateNorm
+    double sh, ch;
+    sincos(0.5 * nn, &sh, &ch);
+    const double inv_n = 1.0 / nn, kap = sh * inv_n;
+    const double e0 = y0 * kap, e1 = y1 * kap, e2 = y2 * kap, e3 = ch;  // Utils::ApproximateExponentialMap
+#pragma unroll
+    for (int i = 0; i < 9; ++i) core[Q::cR + i] = R[i];
+    core[Q::cE] = e0; core[Q::cE + 1] = e1; core[Q::cE + 2] = e2; core[Q::cE + 3] = e3;
+    core[Q::cXN + 0] = xk[0] + dt * vn0; core[Q::cXN + 1] = xk[1] + dt * vn1; core[Q::cXN + 2] = xk[2] + dt * vn2;
+    core[Q::cXN + 3] = qw * e0 + qx * e3 + qy * e2 - qz * e1;  // q (x) e, Eigen product (Quaternion.h:487-498)
+    core[Q::cXN + 4] = qw * e1 + qy * e3 + qz * e0 - qx * e2;
+    core[Q::cXN + 5] = qw * e2 + qz * e3 + qx * e1 - qy * e0;
+    core[Q::cXN + 6] = qw * e3 - qx * e0 - qy * e1 - qz * e2;
+    core[Q::cXN + 7] = vn0; core[Q::cXN + 8] = vn1; core[Q::cXN + 9] = vn2;
+    core[Q::cXN + 10] = wn0; core[Q::cXN + 11] = wn1; core[Q::cXN + 12] = wn2;
+    // Qw = d q+ / d w+ = dt Lmat(q) E,  E = d e / d y:  E[a][b] = kap d_ab + beta y_a y_b (a < 3),  E[3][b] = -kap/2 y_b
+    const double beta = (0.5 * ch - kap) * inv_n * inv_n;
+    const double Ly0 = qw * y0 - qz * y1 + qy * y2, Ly1 = qz * y0 + qw * y1 - qx * y2, Ly2 = -qy * y0 + qx * y1 + qw * y2,
+                 Ly3 = -qx * y0 - qy * y1 - qz * y2;
+    const double m0 = beta * Ly0 - 0.5 * kap * qx, m1 = beta * Ly1 - 0.5 * kap * qy, m2 = beta * Ly2 - 0.5 * kap * qz,
+                 m3 = beta * Ly3 - 0.5 * kap * qw;
+    core[Q::cQ + 0] = dt * (kap * qw + y0 * m0);  core[Q::cQ + 1] = dt * (-kap * qz + y1 * m0); core[Q::cQ + 2] = dt * (kap * qy + y2 * m0);
+    core[Q::cQ + 3] = dt * (kap * qz + y0 * m1);  core[Q::cQ + 4] = dt * (kap * qw + y1 * m1);  core[Q::cQ + 5] = dt * (-kap * qx + y2 * m1);
+    core[Q::cQ + 6] = dt * (-kap * qy + y0 * m2); core[Q::cQ + 7] = dt * (kap * qx + y1 * m2);  core[Q::cQ + 8] = dt * (kap * qw + y2 * m2);
+    core[Q::cQ + 9] = dt * (-kap * qx + y0 * m3); core[Q::cQ + 10] = dt * (-kap * qy + y1 * m3); core[Q::cQ + 11] = dt * (-kap * qz + y2 * m3);
+    // Min(|q - qRef|^2, |q + qRef|^2) = CondExpGt(dm, dp, dp, dm): '+' branch only when dm > dp (utils.hpp:976)
+    double dm = 0.0, dp = 0.0;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const double a = xk[3 + i] - pk[3 + i], bq = xk[3 + i] + pk[3 + i];
+        dm += a * a; dp += bq * bq;
+    }
+    core[Q::cSGN] = dm > dp ? 1.0 : -1.0;
+}
+
 template <bool BARRIER>
 __global__ void __launch_bounds__(QuadrupedStructured::WARPS * 32, 3)
 quadruped_structured_kernel(const double* __restrict__ xp_all, long long ld_xp, double* __restrict__ rec_all, long long ld_rec,
@@ -84,242 +152,226 @@ quadruped_structured_kernel(const double* __restrict__ xp_all, long long ld_xp, 
     using Mdl = Quadruped;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-    double* const stage = reinterpret_cast<double*>(smem_raw) + wib * Q::STAGE;
-    double* const stA = stage;
-    double* const stH = stage + Q::PAIR_A;
-    double* const stC = stage + Q::PAIR_A + Q::PAIR_H;
-    for (int e = lane; e < Q::STAGE; e += 32) stage[e] = 0.0;
+    double* const wsm   = reinterpret_cast<double*>(smem_raw) + wib * Q::PER_WARP;
+    double* const stA   = wsm;
+    double* const stH   = wsm + Q::PAIR_A;
+    double* const stC   = wsm + Q::PAIR_A + Q::PAIR_H;
+    double* const cores = wsm + Q::oCORE;
+    double* const xs    = wsm + Q::oXS;
+    double* const us    = wsm + Q::oUS;
+    double* const ps    = wsm + Q::oPS;
+    for (int e = lane; e < Q::STAGE; e += 32) wsm[e] = 0.0;
     __syncwarp();
 
     const int leg = lane >> 3, c = lane & 7;  // column lanes: c < 6 -> (f0 f1 f2 r0 r1 r2) of `leg`
     const bool col_lane = c < 6;
     const int c3 = c < 3 ? c : c - 3;
+    const int cq = c & 3;
     const long long warp_id = (long long)blockIdx.x * Q::WARPS + wib;
     const long long n_warps = (long long)gridDim.x * Q::WARPS;
+    bool pending = false;  // a bulk store may still be reading the staging image
 
     for (long long run = warp_id; run < total_runs; run += n_warps) {
         const long long b = run / runs_per_traj;
-        const int k_begin = int(run - b * runs_per_traj) * run_len;
-        const int k_end   = min(N, k_begin + run_len);
+        const int k0    = int(run - b * runs_per_traj) * run_len;
+        const int nodes = min(N, k0 + run_len) - k0;
         const double* __restrict__ x = xp_all + b * ld_xp;
         double* __restrict__ r       = rec_all + b * ld_rec;
         const double* __restrict__ Rho = x + Mdl::rho_off(N);
+
+        // ---- phase 0: the run's inputs -> shared memory (slot j of xs/us/ps = node k0 - 1 + j) ------------------------
+        {
+            const int halo = k0 > 0 ? 0 : 1;  // no node -1
+            const double* gx = x + Mdl::x_off(N, k0 - 1 + halo);
+            for (int e = lane + halo * Q::NX; e < (nodes + 2) * Q::NX; e += 32) async_copy8(xs + e, gx + (e - halo * Q::NX));
+            const double* gu = x + Mdl::u_off(N, k0 - 1 + halo);
+            for (int e = lane + halo * Q::NU; e < (nodes + 1) * Q::NU; e += 32) async_copy8(us + e, gu + (e - halo * Q::NU));
+            const double* gp = x + Mdl::p_off(N, k0 - 1 + halo);
+            for (int e = lane + halo * Q::NP; e < (nodes + 1) * Q::NP; e += 32) async_copy8(ps + e, gp + (e - halo * Q::NP));
+            asm volatile("cp.async.commit_group;" ::: "memory");
+        }
         const double dt = Rho[0], mass = Rho[1], I0 = Rho[2], I1 = Rho[3], I2 = Rho[4], Llen = Rho[17], g0 = Rho[18],
                      mu = Rho[19];
         const double iI0 = 1.0 / I0, iI1 = 1.0 / I1, iI2 = 1.0 / I2, inv_m = 1.0 / mass;
         const double hip0 = Rho[5 + 3 * leg], hip1 = Rho[6 + 3 * leg], hip2 = Rho[7 + 3 * leg];
+        if (k0 == 0 && lane < 13) r[L.g + lane] = x[lane] - x[Mdl::xm_off(N) + lane];  // x_0 - x_measured (:266-268)
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+        __syncwarp();
 
-        if (k_begin == 0 && lane < 13) r[L.g + lane] = x[lane] - x[Mdl::xm_off(N) + lane];  // x_0 - x_measured
+        // ---- phase A: thread-per-node primal cores (lane 0 = halo node k0 - 1: only its rotation matrix) --------------
+        if (lane >= 1 && lane <= nodes) {
+            node_core(xs + lane * Q::NX, us + lane * Q::NU, ps + lane * Q::NP, dt, inv_m, g0, I0, I1, I2, iI0, iI1, iI2,
+                      cores + lane * Q::CORE);
+        } else if (lane == 0 && k0 > 0) {
+            rot_matrix(xs[3], xs[4], xs[5], xs[6], cores + Q::cR);
+        }
+        __syncwarp();
 
-        // ---- carried "previous node" foot kinematics of this lane's leg (contact rows) ---------------------
-        double Rp0 = 0, Rp1 = 0, Rp2 = 0;      // column c3 of R(q_{k-1})
-        double Dp0 = 0, Dp1 = 0, Dp2 = 0;      // d(R r_{k-1,leg}) / d q_c   (c < 4)
-        double fp0, fp1, fp2;                  // previous foot position
-        double s_prev;
-        if (k_begin > 0) {
-            const double* xq = x + Mdl::x_off(N, k_begin - 1);
-            const double* ur = x + Mdl::u_off(N, k_begin - 1) + 6 * leg + 3;
-            const double qx = xq[3], qy = xq[4], qz = xq[5], qw = xq[6], r0 = ur[0], r1 = ur[1], r2 = ur[2];
-            const Rot3 R = rot_matrix(qx, qy, qz, qw);
-            Rp0 = pick3(c3, R.m00, R.m01, R.m02); Rp1 = pick3(c3, R.m10, R.m11, R.m12); Rp2 = pick3(c3, R.m20, R.m21, R.m22);
-            drot_dq(c & 3, qx, qy, qz, qw, r0, r1, r2, Dp0, Dp1, Dp2);
-            fp0 = xq[0] + R.m00 * r0 + R.m01 * r1 + R.m02 * r2;
-            fp1 = xq[1] + R.m10 * r0 + R.m11 * r1 + R.m12 * r2;
-            fp2 = xq[2] + R.m20 * r0 + R.m21 * r1 + R.m22 * r2;
-            s_prev = x[Mdl::p_off(N, k_begin - 1) + 13 + 4 * leg];
+        // ---- previous-node foot kinematics of this lane's leg (contact rows), carried from node to node ----------------
+        double Rp0 = 0, Rp1 = 0, Rp2 = 0;  // column c3 of R(q_{k-1})
+        double Dp0 = 0, Dp1 = 0, Dp2 = 0;  // d(R r_{k-1,leg}) / d q_cq
+        double fp0, fp1, fp2, s_prev;      // previous foot position and contact flag
+        if (k0 > 0) {
+            const double* Rh = cores + Q::cR;
+            const double r0 = us[6 * leg + 3], r1 = us[6 * leg + 4], r2 = us[6 * leg + 5];
+            Rp0 = Rh[c3]; Rp1 = Rh[3 + c3]; Rp2 = Rh[6 + c3];
+            drot_dq(cq, xs[3], xs[4], xs[5], xs[6], r0, r1, r2, Dp0, Dp1, Dp2);
+            fp0 = xs[0] + Rh[0] * r0 + Rh[1] * r1 + Rh[2] * r2;
+            fp1 = xs[1] + Rh[3] * r0 + Rh[4] * r1 + Rh[5] * r2;
+            fp2 = xs[2] + Rh[6] * r0 + Rh[7] * r1 + Rh[8] * r2;
+            s_prev = ps[13 + 4 * leg];
         } else {
-            fp0 = Rho[34 + 4 * leg]; fp1 = Rho[35 + 4 * leg]; fp2 = Rho[36 + 4 * leg];  // measured foot
+            fp0 = Rho[34 + 4 * leg]; fp1 = Rho[35 + 4 * leg]; fp2 = Rho[36 + 4 * leg];  // measured foot (:296)
             s_prev = Rho[33 + 4 * leg];
         }
 
-        for (int k = k_begin; k < k_end; ++k) {
-            const int slot = (k - k_begin) & 1;
+        // ---- phase B: warp-per-node block fill ------------------------------------------------------------------------
+        for (int n = 0; n < nodes; ++n) {
+            const int k = k0 + n, slot = n & 1;
             double* const sA = stA + slot * Q::NA;
             double* const sH = stH + slot * Q::TRI;
             double* const sC = stC + slot * Q::NC;
-            const double* __restrict__ xk = x + Mdl::x_off(N, k);
-            const double* __restrict__ uk = x + Mdl::u_off(N, k);
-            const double* __restrict__ pk = x + Mdl::p_off(N, k);
+            const double* __restrict__ xk = xs + (n + 1) * Q::NX;
+            const double* __restrict__ uk = us + (n + 1) * Q::NU;
+            const double* __restrict__ pk = ps + (n + 1) * Q::NP;
+            const double* __restrict__ co = cores + (n + 1) * Q::CORE;
+            const double* __restrict__ R  = co + Q::cR;
+            const double* __restrict__ Qw = co + Q::cQ;
 
-            // ---- node-global primal pass (identical in every lane) ------------------------------------------
             const double qx = xk[3], qy = xk[4], qz = xk[5], qw = xk[6];
-            const double w0 = xk[10], w1 = xk[11], w2 = xk[12];
-            const Rot3 R = rot_matrix(qx, qy, qz, qw);
-            double a0 = 0.0, a1 = 0.0, a2 = -g0;                                  // linear acceleration
-            const double Iw0 = I0 * w0, Iw1 = I1 * w1, Iw2 = I2 * w2;
-            double t0 = -(w1 * Iw2 - w2 * Iw1), t1 = -(w2 * Iw0 - w0 * Iw2), t2 = -(w0 * Iw1 - w1 * Iw0);  // torque
-            double my_f0 = 0, my_f1 = 0, my_f2 = 0, my_r0 = 0, my_r1 = 0, my_r2 = 0, my_s = 0;
-            double my_Rf0 = 0, my_Rf1 = 0, my_Rf2 = 0;
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                const double f0 = uk[6 * i], f1 = uk[6 * i + 1], f2 = uk[6 * i + 2];
-                const double r0 = uk[6 * i + 3], r1 = uk[6 * i + 4], r2 = uk[6 * i + 5];
-                const double s = pk[13 + 4 * i];
-                const double Rf0 = R.m00 * f0 + R.m01 * f1 + R.m02 * f2;
-                const double Rf1 = R.m10 * f0 + R.m11 * f1 + R.m12 * f2;
-                const double Rf2 = R.m20 * f0 + R.m21 * f1 + R.m22 * f2;
-                a0 += s * f0 * inv_m; a1 += s * f1 * inv_m; a2 += s * f2 * inv_m;
-                t0 += s * (r1 * Rf2 - r2 * Rf1); t1 += s * (r2 * Rf0 - r0 * Rf2); t2 += s * (r0 * Rf1 - r1 * Rf0);
-                if (i == leg) {
-                    my_f0 = f0; my_f1 = f1; my_f2 = f2; my_r0 = r0; my_r1 = r1; my_r2 = r2; my_s = s;
-                    my_Rf0 = Rf0; my_Rf1 = Rf1; my_Rf2 = Rf2;
-                }
-            }
-            const double vn0 = xk[7] + dt * a0, vn1 = xk[8] + dt * a1, vn2 = xk[9] + dt * a2;
-            const double wn0 = w0 + dt * (t0 * iI0), wn1 = w1 + dt * (t1 * iI1), wn2 = w2 + dt * (t2 * iI2);
-            const double pn0 = xk[0] + dt * vn0, pn1 = xk[1] + dt * vn1, pn2 = xk[2] + dt * vn2;
-            const double y0 = dt * wn0, y1 = dt * wn1, y2 = dt * wn2;           // argument of the exponential map
-            const double nn = sqrt(y0 * y0 + y1 * y1 + y2 * y2 + UB_EPS);
-            double sh, ch;
-            sincos(0.5 * nn, &sh, &ch);
-            const double inv_n = 1.0 / nn;
-            const double kap = sh * inv_n;
-            const double e0 = y0 * kap, e1 = y1 * kap, e2 = y2 * kap, e3 = ch;   // e = aexp(dt w+)
-            const double qn0 = qw * e0 + qx * e3 + qy * e2 - qz * e1;
-            const double qn1 = qw * e1 + qy * e3 + qz * e0 - qx * e2;
-            const double qn2 = qw * e2 + qz * e3 + qx * e1 - qy * e0;
-            const double qn3 = qw * e3 - qx * e0 - qy * e1 - qz * e2;
-            // Qw = d q+ / d w+ = dt * Lmat(q) * E,  E = d e / d y:  E[a][b] = kap d_ab + beta y_a y_b, E[3][b] = -kap/2 y_b
-            const double beta = (0.5 * ch - kap) * inv_n * inv_n;
-            // Lmat(q) columns (x y z w):  [qw qz -qy -qx], [-qz qw qx -qy], [qy -qx qw -qz], [qx qy qz qw]
-            const double Ly0 = qw * y0 - qz * y1 + qy * y2, Ly1 = qz * y0 + qw * y1 - qx * y2,
-                         Ly2 = -qy * y0 + qx * y1 + qw * y2, Ly3 = -qx * y0 - qy * y1 - qz * y2;
-            const double m0 = beta * Ly0 - 0.5 * kap * qx, m1 = beta * Ly1 - 0.5 * kap * qy,
-                         m2 = beta * Ly2 - 0.5 * kap * qz, m3 = beta * Ly3 - 0.5 * kap * qw;
-            // Qw[a][b] = dt (kap Lmat[a][b] + y_b m_a)
-            const double Q00 = dt * (kap * qw + y0 * m0), Q01 = dt * (-kap * qz + y1 * m0), Q02 = dt * (kap * qy + y2 * m0);
-            const double Q10 = dt * (kap * qz + y0 * m1), Q11 = dt * (kap * qw + y1 * m1), Q12 = dt * (-kap * qx + y2 * m1);
-            const double Q20 = dt * (-kap * qy + y0 * m2), Q21 = dt * (kap * qx + y1 * m2), Q22 = dt * (kap * qw + y2 * m2);
-            const double Q30 = dt * (-kap * qx + y0 * m3), Q31 = dt * (-kap * qy + y1 * m3), Q32 = dt * (-kap * qz + y2 * m3);
+            const double f0 = uk[6 * leg], f1 = uk[6 * leg + 1], f2 = uk[6 * leg + 2];
+            const double r0 = uk[6 * leg + 3], r1 = uk[6 * leg + 4], r2 = uk[6 * leg + 5];
+            const double s = pk[13 + 4 * leg];
+            const double Rc0 = R[c3], Rc1 = R[3 + c3], Rc2 = R[6 + c3];  // column c3 of R
 
-            // ---- this lane's column of W = d w+ / d z ------------------------------------------------------------
-            // leg lanes: f column c:  dt I^-1 s (r x R[:, c]);  r column c':  dt I^-1 s (e_c' x R f)
-            double W0 = 0, W1 = 0, W2 = 0;
+            // this lane's column of W = d w+ / d z:  f column: dt I^-1 s (r x R[:, c]);  r column: dt I^-1 s (e_c x R f)
+            double W0, W1, W2;
             {
-                const double Rc0 = pick3(c3, R.m00, R.m01, R.m02), Rc1 = pick3(c3, R.m10, R.m11, R.m12),
-                             Rc2 = pick3(c3, R.m20, R.m21, R.m22);
-                const double ec0 = c3 == 0 ? 1.0 : 0.0, ec1 = c3 == 1 ? 1.0 : 0.0, ec2 = c3 == 2 ? 1.0 : 0.0;
                 const bool fcol = c < 3;
-                const double u0 = fcol ? my_r0 : ec0, u1 = fcol ? my_r1 : ec1, u2 = fcol ? my_r2 : ec2;
-                const double v0 = fcol ? Rc0 : my_Rf0, v1 = fcol ? Rc1 : my_Rf1, v2 = fcol ? Rc2 : my_Rf2;
-                const double sc = dt * my_s;
+                const double Rf0 = R[0] * f0 + R[1] * f1 + R[2] * f2, Rf1 = R[3] * f0 + R[4] * f1 + R[5] * f2,
+                             Rf2 = R[6] * f0 + R[7] * f1 + R[8] * f2;
+                const double u0 = fcol ? r0 : (c3 == 0 ? 1.0 : 0.0), u1 = fcol ? r1 : (c3 == 1 ? 1.0 : 0.0),
+                             u2 = fcol ? r2 : (c3 == 2 ? 1.0 : 0.0);
+                const double v0 = fcol ? Rc0 : Rf0, v1 = fcol ? Rc1 : Rf1, v2 = fcol ? Rc2 : Rf2;
+                const double sc = dt * s;
                 W0 = sc * iI0 * (u1 * v2 - u2 * v1); W1 = sc * iI1 * (u2 * v0 - u0 * v2); W2 = sc * iI2 * (u0 * v1 - u1 * v0);
             }
-            if (col_lane) {
-                const int col = 13 + 6 * leg + c;
-                sA[10 * 37 + col] = -W0; sA[11 * 37 + col] = -W1; sA[12 * 37 + col] = -W2;
-                sA[3 * 37 + col] = -(Q00 * W0 + Q01 * W1 + Q02 * W2);
-                sA[4 * 37 + col] = -(Q10 * W0 + Q11 * W1 + Q12 * W2);
-                sA[5 * 37 + col] = -(Q20 * W0 + Q21 * W1 + Q22 * W2);
-                sA[6 * 37 + col] = -(Q30 * W0 + Q31 * W1 + Q32 * W2);
-                if (c < 3) {
-                    sA[c * 37 + col]       = -(dt * dt) * (my_s * inv_m);
-                    sA[(7 + c) * 37 + col] = -dt * (my_s * inv_m);
-                }
-            }
-            // q columns: dt I^-1 sum_i s_i r_i x d(R f_i)/dq_c  — every leg's lanes c < 4 add their leg, then xor-reduce
+            // q columns: dt I^-1 sum_i s_i r_i x d(R f_i)/dq_c — every leg adds its part, xor-reduced over the 4 legs
+            double z0, z1, z2;
             {
                 double d0, d1, d2;
-                drot_dq(c & 3, qx, qy, qz, qw, my_f0, my_f1, my_f2, d0, d1, d2);
-                double z0 = my_s * (my_r1 * d2 - my_r2 * d1), z1 = my_s * (my_r2 * d0 - my_r0 * d2),
-                       z2 = my_s * (my_r0 * d1 - my_r1 * d0);
-                z0 += __shfl_xor_sync(0xffffffffu, z0, 8); z1 += __shfl_xor_sync(0xffffffffu, z1, 8); z2 += __shfl_xor_sync(0xffffffffu, z2, 8);
+                drot_dq(cq, qx, qy, qz, qw, f0, f1, f2, d0, d1, d2);
+                z0 = s * (r1 * d2 - r2 * d1); z1 = s * (r2 * d0 - r0 * d2); z2 = s * (r0 * d1 - r1 * d0);
+                z0 += __shfl_xor_sync(0xffffffffu, z0, 8);  z1 += __shfl_xor_sync(0xffffffffu, z1, 8);  z2 += __shfl_xor_sync(0xffffffffu, z2, 8);
                 z0 += __shfl_xor_sync(0xffffffffu, z0, 16); z1 += __shfl_xor_sync(0xffffffffu, z1, 16); z2 += __shfl_xor_sync(0xffffffffu, z2, 16);
-                if (leg == 0 && c < 4) {  // lanes 0..3 own the q columns
-                    const double G0 = dt * iI0 * z0, G1 = dt * iI1 * z1, G2 = dt * iI2 * z2;
-                    const int col = 3 + c;
-                    // Rmat(e) column c: d(q (x) e)/dq_c
-                    const double r0c = c == 0 ? e3 : c == 1 ? e2 : c == 2 ? -e1 : e0;
-                    const double r1c = c == 0 ? -e2 : c == 1 ? e3 : c == 2 ? e0 : e1;
-                    const double r2c = c == 0 ? e1 : c == 1 ? -e0 : c == 2 ? e3 : e2;
-                    const double r3c = c == 0 ? -e0 : c == 1 ? -e1 : c == 2 ? -e2 : e3;
+            }
+            if (slot == 0 && pending) {  // the previous pair's bulk stores must have finished reading the image
+                if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+                __syncwarp();
+                pending = false;
+            }
+            // ---- A = d(x_{k+1} - f)/dz: rows w+ (10-12) = -W, rows q+ (3-6) = -(Qw W [+ Rmat(e)]), rows p+/v+ constants --
+            {
+                double G0 = W0, G1 = W1, G2 = W2, add0 = 0, add1 = 0, add2 = 0, add3 = 0;
+                int col = 13 + 6 * leg + c;
+                bool write = col_lane;
+                if (write) {
                     sA[10 * 37 + col] = -G0; sA[11 * 37 + col] = -G1; sA[12 * 37 + col] = -G2;
-                    sA[3 * 37 + col] = -(r0c + Q00 * G0 + Q01 * G1 + Q02 * G2);
-                    sA[4 * 37 + col] = -(r1c + Q10 * G0 + Q11 * G1 + Q12 * G2);
-                    sA[5 * 37 + col] = -(r2c + Q20 * G0 + Q21 * G1 + Q22 * G2);
-                    sA[6 * 37 + col] = -(r3c + Q30 * G0 + Q31 * G1 + Q32 * G2);
+                    sA[3 * 37 + col] = -(add0 + Qw[0] * G0 + Qw[1] * G1 + Qw[2] * G2);
+                    sA[4 * 37 + col] = -(add1 + Qw[3] * G0 + Qw[4] * G1 + Qw[5] * G2);
+                    sA[5 * 37 + col] = -(add2 + Qw[6] * G0 + Qw[7] * G1 + Qw[8] * G2);
+                    sA[6 * 37 + col] = -(add3 + Qw[9] * G0 + Qw[10] * G1 + Qw[11] * G2);
+                    if (c < 3) {
+                        sA[c * 37 + col]       = -(dt * dt) * (s * inv_m);
+                        sA[(7 + c) * 37 + col] = -dt * (s * inv_m);
+                    }
                 }
-                if (leg == 1 && c < 3) {  // lanes 8..10 own the w columns: e_c + dt I^-1 (Iw x e_c - I_c (w x e_c))
-                    const double ec0 = c == 0 ? 1.0 : 0.0, ec1 = c == 1 ? 1.0 : 0.0, ec2 = c == 2 ? 1.0 : 0.0;
-                    const double Ic = pick3(c, I0, I1, I2);
-                    const double G0 = ec0 + dt * iI0 * ((Iw1 * ec2 - Iw2 * ec1) - Ic * (w1 * ec2 - w2 * ec1));
-                    const double G1 = ec1 + dt * iI1 * ((Iw2 * ec0 - Iw0 * ec2) - Ic * (w2 * ec0 - w0 * ec2));
-                    const double G2 = ec2 + dt * iI2 * ((Iw0 * ec1 - Iw1 * ec0) - Ic * (w0 * ec1 - w1 * ec0));
-                    const int col = 10 + c;
+                // state columns: lanes 0..3 -> q_c, lanes 8..10 -> w_c (second, short pass with the same store code)
+                const bool qcol = lane < 4, wcol = lane >= 8 && lane < 11;
+                if (qcol || wcol) {
+                    const double e0 = co[Q::cE], e1 = co[Q::cE + 1], e2 = co[Q::cE + 2], e3 = co[Q::cE + 3];
+                    if (qcol) {
+                        G0 = dt * iI0 * z0; G1 = dt * iI1 * z1; G2 = dt * iI2 * z2;
+                        // Rmat(e) column c: d(q (x) e)/dq_c
+                        add0 = c == 0 ? e3 : c == 1 ? e2 : c == 2 ? -e1 : e0;
+                        add1 = c == 0 ? -e2 : c == 1 ? e3 : c == 2 ? e0 : e1;
+                        add2 = c == 0 ? e1 : c == 1 ? -e0 : c == 2 ? e3 : e2;
+                        add3 = c == 0 ? -e0 : c == 1 ? -e1 : c == 2 ? -e2 : e3;
+                        col = 3 + c;
+                    } else {  // e_c + dt I^-1 (Iw x e_c - I_c (w x e_c))
+                        const double w0 = xk[10], w1 = xk[11], w2 = xk[12];
+                        const double Iw0 = I0 * w0, Iw1 = I1 * w1, Iw2 = I2 * w2;
+                        const double ec0 = c == 0 ? 1.0 : 0.0, ec1 = c == 1 ? 1.0 : 0.0, ec2 = c == 2 ? 1.0 : 0.0;
+                        const double Ic = pick3(c, I0, I1, I2);
+                        G0 = ec0 + dt * iI0 * ((Iw1 * ec2 - Iw2 * ec1) - Ic * (w1 * ec2 - w2 * ec1));
+                        G1 = ec1 + dt * iI1 * ((Iw2 * ec0 - Iw0 * ec2) - Ic * (w2 * ec0 - w0 * ec2));
+                        G2 = ec2 + dt * iI2 * ((Iw0 * ec1 - Iw1 * ec0) - Ic * (w0 * ec1 - w1 * ec0));
+                        col = 10 + c;
+                    }
                     sA[10 * 37 + col] = -G0; sA[11 * 37 + col] = -G1; sA[12 * 37 + col] = -G2;
-                    sA[3 * 37 + col] = -(Q00 * G0 + Q01 * G1 + Q02 * G2);
-                    sA[4 * 37 + col] = -(Q10 * G0 + Q11 * G1 + Q12 * G2);
-                    sA[5 * 37 + col] = -(Q20 * G0 + Q21 * G1 + Q22 * G2);
-                    sA[6 * 37 + col] = -(Q30 * G0 + Q31 * G1 + Q32 * G2);
+                    sA[3 * 37 + col] = -(add0 + Qw[0] * G0 + Qw[1] * G1 + Qw[2] * G2);
+                    sA[4 * 37 + col] = -(add1 + Qw[3] * G0 + Qw[4] * G1 + Qw[5] * G2);
+                    sA[5 * 37 + col] = -(add2 + Qw[6] * G0 + Qw[7] * G1 + Qw[8] * G2);
+                    sA[6 * 37 + col] = -(add3 + Qw[9] * G0 + Qw[10] * G1 + Qw[11] * G2);
                 }
                 if (leg == 2 && c < 3) {  // lanes 16..18: the constant p / v entries
                     sA[c * 37 + c] = -1.0; sA[c * 37 + 7 + c] = -dt; sA[(7 + c) * 37 + 7 + c] = -1.0;
                 }
             }
 
-            // ---- state part of the objective, defects: lanes 0..12 own state entry `lane` -----------------------
+            // ---- state part of the objective and the defects: lanes 0..12 own state entry `lane` -----------------------------
             double cost_part = 0.0, bar_part = 0.0;
-            {
-                double dm = 0.0, dp = 0.0;  // Min(|q - qRef|^2, |q + qRef|^2) = CondExpGt(dm, dp, dp, dm)
-#pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                    const double a = xk[3 + i] - pk[3 + i], bq = xk[3 + i] + pk[3 + i];
-                    dm += a * a; dp += bq * bq;
-                }
-                const double sgn = dm > dp ? 1.0 : -1.0;
-                if (lane < 13) {
-                    const double wgt = lane < 2 ? 0.1 : (lane == 2 ? 10.0 : 1.0);
-                    const bool isq = lane >= 3 && lane < 7;
-                    const double res = wgt * (isq ? xk[lane] + sgn * pk[lane] : xk[lane] - pk[lane]);
-                    cost_part = res * res;
-                    r[L.grad + Mdl::x_off(N, k) + lane] = 2.0 * wgt * res;
-                    sH[lane * 37 - (lane * (lane - 1)) / 2] = 2.0 * wgt * wgt + (BARRIER ? 1e-6 : 0.0);
-                    const double xn = lane == 0 ? pn0 : lane == 1 ? pn1 : lane == 2 ? pn2 : lane == 3 ? qn0 : lane == 4 ? qn1
-                                    : lane == 5 ? qn2 : lane == 6 ? qn3 : lane == 7 ? vn0 : lane == 8 ? vn1 : lane == 9 ? vn2
-                                    : lane == 10 ? wn0 : lane == 11 ? wn1 : wn2;
-                    r[L.g + 13 + 13 * k + lane] = x[Mdl::x_off(N, k + 1) + lane] - xn;
-                }
+            if (lane < 13) {
+                const double sgn = co[Q::cSGN];
+                const double wgt = lane < 2 ? 0.1 : (lane == 2 ? 10.0 : 1.0);  // Vector3r{0.1, 0.1, 10} (:228)
+                const bool isq   = lane >= 3 && lane < 7;
+                const double res = wgt * (isq ? xk[lane] + sgn * pk[lane] : xk[lane] - pk[lane]);
+                cost_part = res * res;
+                r[L.grad + Mdl::x_off(N, k) + lane] = 2.0 * wgt * res;
+                sH[lane * 37 - (lane * (lane - 1)) / 2] = 2.0 * wgt * wgt + (BARRIER ? 1e-6 : 0.0);
+                r[L.g + 13 + 13 * k + lane] = xk[13 + lane] - co[Q::cXN + lane];  // x_{k+1} - f(x_k, u_k)   (:276)
             }
 
-            // ---- this lane's input entry: objective, inequalities of its leg, barrier, Gauss-Newton rows -----------
-            const double fxy = sqrt(my_f0 * my_f0 + my_f1 * my_f1 + UB_EPS);
-            const double dr0 = my_r0 - hip0, dr1 = my_r1 - hip1, dr2 = my_r2 - hip2;
-            const double nr = sqrt(dr0 * dr0 + dr1 * dr1 + dr2 * dr2 + UB_EPS);
-            const double hA = -my_s * my_f2, hB = my_s * fxy - mu * my_f2, hC = my_s * nr - Llen;
-            double bA = 0, dA = 0, ddA = 0, bB = 0, dB = 0, ddB = 0, bC = 0, dC = 0, ddC = 0;
-            if (BARRIER) {
-                barrier_eval(bar, hA, &bA, &dA, &ddA);
-                barrier_eval(bar, hB, &bB, &dB, &ddB);
-                barrier_eval(bar, hC, &bC, &dC, &ddC);
-            }
+            // ---- this lane's input entry: objective, inequalities of its leg, barrier, Gauss-Newton rows -----------------------
             if (col_lane) {
-                const int zi = 13 + 6 * leg + c;
+                const int zi   = 13 + 6 * leg + c;
                 const int diag = zi * 37 - (zi * (zi - 1)) / 2;
-                if (c < 3) {
+                if (c < 3) {  // f_c:  h_A = -s f_z,  h_B = s |f_xy|_eps - mu f_z   (:330-331)
+                    const double fxy = sqrt(f0 * f0 + f1 * f1 + UB_EPS);
+                    const double hA = -s * f2, hB = s * fxy - mu * f2;
+                    double bA = 0, dA = 0, ddA = 0, bB = 0, dB = 0, ddB = 0;
+                    if (BARRIER) {
+                        barrier_eval(bar, hA, &bA, &dA, &ddA);
+                        barrier_eval(bar, hB, &bB, &dB, &ddB);
+                    }
                     const double inv_fxy = 1.0 / fxy;
-                    const double gB0 = my_s * my_f0 * inv_fxy, gB1 = my_s * my_f1 * inv_fxy, gB2 = -mu;  // grad h_B wrt f
-                    const double gA_c = c == 2 ? -my_s : 0.0;
-                    const double gB_c = pick3(c, gB0, gB1, gB2);
-                    const double fc = pick3(c, my_f0, my_f1, my_f2);
+                    const double gB0 = s * f0 * inv_fxy, gB1 = s * f1 * inv_fxy, gB2 = -mu;  // grad h_B wrt f
+                    const double gA_c = c == 2 ? -s : 0.0, gB_c = pick3(c, gB0, gB1, gB2), fc = pick3(c, f0, f1, f2);
                     cost_part += 1e-8 * fc * fc;
                     r[L.grad + Mdl::u_off(N, k) + 6 * leg + c] = 2e-8 * fc + dA * gA_c + dB * gB_c;
-                    r[L.h + 12 * k + 3 * leg + c] = pick3(c, hA, hB, hC);
-                    bar_part = pick3(c, bA, bB, bC);
-                    // row c of the f-f block: entries (c, c .. 2)
-                    sH[diag] = ddA * gA_c * gA_c + ddB * gB_c * gB_c + 2e-8 + (BARRIER ? 1e-6 : 0.0);
                     if (c < 2) {
-                        const double gA_1 = (c + 1 == 2) ? -my_s : 0.0;
-                        const double gB_1 = c == 0 ? gB1 : gB2;
-                        sH[diag + 1] = ddA * gA_c * gA_1 + ddB * gB_c * gB_1;
+                        r[L.h + 12 * k + 3 * leg + c] = c == 0 ? hA : hB;
+                        bar_part = c == 0 ? bA : bB;
                     }
-                    if (c < 1) sH[diag + 2] = ddA * gA_c * (-my_s) + ddB * gB_c * gB2;
-                } else {
+                    sH[diag] = ddA * gA_c * gA_c + ddB * gB_c * gB_c + 2e-8 + (BARRIER ? 1e-6 : 0.0);
+                    if (c < 2) sH[diag + 1] = ddA * gA_c * (c == 1 ? -s : 0.0) + ddB * gB_c * (c == 0 ? gB1 : gB2);
+                    if (c < 1) sH[diag + 2] = ddA * gA_c * (-s) + ddB * gB_c * gB2;
+                } else {  // r_c':  h_C = s |r - hip|_eps - L   (:332-333)
+                    const double dr0 = r0 - hip0, dr1 = r1 - hip1, dr2 = r2 - hip2;
+                    const double nr = sqrt(dr0 * dr0 + dr1 * dr1 + dr2 * dr2 + UB_EPS);
+                    const double hC = s * nr - Llen;
+                    double bC = 0, dC = 0, ddC = 0;
+                    if (BARRIER) barrier_eval(bar, hC, &bC, &dC, &ddC);
                     const double inv_nr = 1.0 / nr;
-                    const double gC0 = my_s * dr0 * inv_nr, gC1 = my_s * dr1 * inv_nr, gC2 = my_s * dr2 * inv_nr;
+                    const double gC0 = s * dr0 * inv_nr, gC1 = s * dr1 * inv_nr, gC2 = s * dr2 * inv_nr;
                     const double gC_c = pick3(c3, gC0, gC1, gC2);
-                    const double rc = pick3(c3, my_r0, my_r1, my_r2) - pk[14 + 4 * leg + c3];
+                    const double rc = pick3(c3, r0, r1, r2) - pk[14 + 4 * leg + c3];
                     cost_part += rc * rc;
                     r[L.grad + Mdl::u_off(N, k) + 6 * leg + c] = 2.0 * rc + dC * gC_c;
+                    if (c == 3) {
+                        r[L.h + 12 * k + 3 * leg + 2] = hC;
+                        bar_part = bC;
+                    }
                     sH[diag] = ddC * gC_c * gC_c + 2.0 + (BARRIER ? 1e-6 : 0.0);
                     if (c3 < 2) sH[diag + 1] = ddC * gC_c * (c3 == 0 ? gC1 : gC2);
                     if (c3 < 1) sH[diag + 2] = ddC * gC_c * gC2;
@@ -333,16 +385,14 @@ quadruped_structured_kernel(const double* __restrict__ xp_all, long long ld_xp, 
                 stage_cost[((long long)b * (N + 1) + k) * 2 + 1] = bar_part;
             }
 
-            // ---- contact rows of this lane's leg ----------------------------------------------------------------------
+            // ---- contact rows of this lane's leg (:279-303) ----------------------------------------------------------------------
             {
-                const double ft0 = xk[0] + R.m00 * my_r0 + R.m01 * my_r1 + R.m02 * my_r2;
-                const double ft1 = xk[1] + R.m10 * my_r0 + R.m11 * my_r1 + R.m12 * my_r2;
-                const double ft2 = xk[2] + R.m20 * my_r0 + R.m21 * my_r1 + R.m22 * my_r2;
-                const double c0 = (1.0 - s_prev) * my_s, ss = s_prev * my_s;
-                const double Rc0 = pick3(c3, R.m00, R.m01, R.m02), Rc1 = pick3(c3, R.m10, R.m11, R.m12),
-                             Rc2 = pick3(c3, R.m20, R.m21, R.m22);
+                const double ft0 = xk[0] + R[0] * r0 + R[1] * r1 + R[2] * r2;
+                const double ft1 = xk[1] + R[3] * r0 + R[4] * r1 + R[5] * r2;
+                const double ft2 = xk[2] + R[6] * r0 + R[7] * r1 + R[8] * r2;
+                const double c0 = (1.0 - s_prev) * s, ss = s_prev * s;
                 double D0, D1, D2;
-                drot_dq(c & 3, qx, qy, qz, qw, my_r0, my_r1, my_r2, D0, D1, D2);
+                drot_dq(cq, qx, qy, qz, qw, r0, r1, r2, D0, D1, D2);
                 double* const cl = sC + leg * 80;
                 if (c < 4) {  // d foot / d q_c, and the contact values (row c)
                     cl[3 + c] = c0 * D2;
@@ -352,45 +402,42 @@ quadruped_structured_kernel(const double* __restrict__ xp_all, long long ld_xp, 
                     r[L.g + 13 + 13 * N + 16 * k + 4 * leg + c] = val;
                 }
                 if (c < 3) {  // d foot / d r_c = R[:, c];  d foot / d p = I
-                    const double pfac = k > 0 ? -ss : 0.0;
                     cl[7 + c] = c0 * Rc2;
                     cl[20 + 7 + c] = ss * Rc0; cl[40 + 7 + c] = ss * Rc1; cl[60 + 7 + c] = ss * Rc2;
                     cl[20 + 17 + c] = -ss * Rp0; cl[40 + 17 + c] = -ss * Rp1; cl[60 + 17 + c] = -ss * Rp2;
                     cl[(c + 1) * 20 + c]      = ss;
-                    cl[(c + 1) * 20 + 10 + c] = pfac;
+                    cl[(c + 1) * 20 + 10 + c] = k > 0 ? -ss : 0.0;
                     if (c == 2) cl[2] = c0;
                 }
-                // carry to the next node
-                Rp0 = Rc0; Rp1 = Rc1; Rp2 = Rc2; Dp0 = D0; Dp1 = D1; Dp2 = D2;
-                fp0 = ft0; fp1 = ft1; fp2 = ft2; s_prev = my_s;
+                Rp0 = Rc0; Rp1 = Rc1; Rp2 = Rc2; Dp0 = D0; Dp1 = D1; Dp2 = D2;  // carry to the next node
+                fp0 = ft0; fp1 = ft1; fp2 = ft2; s_prev = s;
             }
 
-            // ---- node pair complete: hand the staged blocks to the TMA engine ------------------------------------------
-            if (slot == 1 || k + 1 == k_end) {
+            // ---- node pair complete: hand the staged blocks to the TMA engine ------------------------------------------------------
+            if (slot == 1 || n + 1 == nodes) {
                 const int k_pair = k - slot;
-                const int cnt    = slot + 1;
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                 __syncwarp();
-                if (cnt == 2) {
+                if (slot == 1) {
                     if (lane == 0) {
                         bulk_store(r + L.A + (long long)k_pair * Q::NA, stA, Q::PAIR_A * 8);
                         bulk_store(r + L.H + (long long)k_pair * Q::TRI, stH, Q::PAIR_H * 8);
                         bulk_store(r + L.C + (long long)k_pair * Q::NC, stC, Q::PAIR_C * 8);
                         asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-                        asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
                     }
+                    pending = true;
                 } else {  // odd tail (never taken when the run length is even): plain coalesced stores
                     for (int e = lane; e < Q::NA; e += 32) r[L.A + (long long)k_pair * Q::NA + e] = stA[e];
                     for (int e = lane; e < Q::TRI; e += 32) r[L.H + (long long)k_pair * Q::TRI + e] = stH[e];
                     for (int e = lane; e < Q::NC; e += 32) r[L.C + (long long)k_pair * Q::NC + e] = stC[e];
+                    __syncwarp();
                 }
-                __syncwarp();
             }
         }
 
-        // ---- terminal state x_N: objective gradient and diagonal block (last run of the trajectory) -----------------
-        if (k_end == N) {
-            const double* __restrict__ xN = x + Mdl::x_off(N, N);
+        // ---- terminal state x_N: objective gradient and diagonal block (last run of the trajectory) -----------------------------
+        if (k0 + nodes == N) {
+            const double* __restrict__ xN = xs + (nodes + 1) * Q::NX;
             const double* __restrict__ pN = x + Mdl::p_off(N, N);
             double dm = 0.0, dp = 0.0;
 #pragma unroll
@@ -402,7 +449,7 @@ quadruped_structured_kernel(const double* __restrict__ xp_all, long long ld_xp, 
             double cpart = 0.0, hdiag = 0.0;
             if (lane < 13) {
                 const double wgt = lane < 2 ? 0.1 : (lane == 2 ? 10.0 : 1.0);
-                const bool isq = lane >= 3 && lane < 7;
+                const bool isq   = lane >= 3 && lane < 7;
                 const double res = wgt * (isq ? xN[lane] + sgn * pN[lane] : xN[lane] - pN[lane]);
                 cpart = res * res;
                 hdiag = 2.0 * wgt * wgt + (BARRIER ? 1e-6 : 0.0);
@@ -419,6 +466,7 @@ quadruped_structured_kernel(const double* __restrict__ xp_all, long long ld_xp, 
                 if (lane < 13 - row) r[L.HN + base + lane] = lane == 0 ? dv : 0.0;
             }
         }
+        __syncwarp();  // all lanes are done with xs/us/ps/cores before the next run overwrites them
     }
     if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
 }
