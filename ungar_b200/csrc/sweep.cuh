@@ -89,7 +89,7 @@ kkt_sweep_kernel(const T* __restrict__ xp_all, long long ld_xp, T* __restrict__ 
     const int k = k0 + m;
 
     T w[NH > 0 ? NH : 1];  // d2Z_i * dh_i/dz_j, kept for the Gauss-Newton column
-    T hjj = T(0);
+    T hjj = T(0), cval = T(0), bsum = T(0);
     if (active) {
         D z[NZ];
 #pragma unroll
@@ -108,7 +108,7 @@ kkt_sweep_kernel(const T* __restrict__ xp_all, long long ld_xp, T* __restrict__ 
             }
         }
         // --- inequalities, barrier gradient, staging of J_h ------------------------------------------
-        T gq = T(0), bsum = T(0);
+        T gq = T(0);
         {
             D h[NH];
             Mdl::inequalities(x, N, k, z, h);
@@ -124,7 +124,7 @@ kkt_sweep_kernel(const T* __restrict__ xp_all, long long ld_xp, T* __restrict__ 
             }
         }
         // --- separable objective terms -------------------------------------------------------------------
-        T cval = T(0), hc = T(0);
+        T hc = T(0);
         Mdl::cost_terms(x, N, k, z, [&](T c, const D& res, bool counts) {
             if (counts) cval += c * res.v * res.v;
             else hc -= T(2) * c * res.d * res.d;  // d2/du_k du_{k+1} of c (u_{k+1} - u_k)^2
@@ -133,10 +133,6 @@ kkt_sweep_kernel(const T* __restrict__ xp_all, long long ld_xp, T* __restrict__ 
         });
         sQ[m * NZ + j] = gq;
         if (Mdl::HC && j >= NX) sHc[m * NU + j - NX] = hc;
-        if (j == 0) {
-            stage_cost[((long long)b * (N + 1) + k) * 2]     = cval;
-            stage_cost[((long long)b * (N + 1) + k) * 2 + 1] = bsum;
-        }
         // --- contact rows (quadruped), 20 local tangents per leg -----------------------------------------
         if constexpr (LEGS > 0) {
             if (j < 20) {
@@ -164,6 +160,15 @@ kkt_sweep_kernel(const T* __restrict__ xp_all, long long ld_xp, T* __restrict__ 
         }
     }
     __syncthreads();
+    // --- per-node partials: objective, barrier, |g|_inf, max h (reduced over nodes by finalize_kernel) -----------
+    if (active && j == 0) {
+        T gmax = T(0), hmax = -INFINITY;
+        for (int i = 0; i < NX; ++i) gmax = fmax(gmax, m_abs(sG[m * NX + i]));
+        for (int i = 0; i < LEGS * 4; ++i) gmax = fmax(gmax, m_abs(sGc[m * LEGS * 4 + i]));
+        for (int i = 0; i < NH; ++i) hmax = fmax(hmax, sHv[m * NH + i]);
+        T* pt = stage_cost + ((long long)b * (N + 1) + k) * 4;
+        pt[0] = cval; pt[1] = bsum; pt[2] = gmax; pt[3] = hmax;
+    }
     // --- column j of the block  H_k = diag(objective) + J_h^T D J_h + 1e-6 I  (upper triangle) ---------------
     if (active) {
         for (int a = 0; a <= j; ++a) {
@@ -180,9 +185,9 @@ kkt_sweep_kernel(const T* __restrict__ xp_all, long long ld_xp, T* __restrict__ 
         D zN[NZ];
 #pragma unroll
         for (int i = 0; i < NX; ++i) zN[i] = D(x[Mdl::x_off(N, N) + i], i == t ? T(1) : T(0));
-        T gq = T(0), hnn = T(0), cval = T(0);
+        T gq = T(0), hnn = T(0), cvalN = T(0);
         Mdl::cost_terms(x, N, N, zN, [&](T c, const D& res, bool) {
-            cval += c * res.v * res.v;
+            cvalN += c * res.v * res.v;
             gq += T(2) * c * res.v * res.d;
             hnn += T(2) * c * res.d * res.d;
         });
@@ -190,8 +195,8 @@ kkt_sweep_kernel(const T* __restrict__ xp_all, long long ld_xp, T* __restrict__ 
         for (int a = 0; a <= t; ++a)
             r[L.HN + tri_index(NX, a, t)] = a == t ? hnn + (BARRIER ? T(1e-6) : T(0)) : T(0);
         if (t == 0) {
-            stage_cost[((long long)b * (N + 1) + N) * 2]     = cval;
-            stage_cost[((long long)b * (N + 1) + N) * 2 + 1] = T(0);
+            T* pt = stage_cost + ((long long)b * (N + 1) + N) * 4;
+            pt[0] = cvalN; pt[1] = T(0); pt[2] = T(0); pt[3] = -INFINITY;
         }
     }
     __syncthreads();
@@ -212,20 +217,45 @@ kkt_sweep_kernel(const T* __restrict__ xp_all, long long ld_xp, T* __restrict__ 
     }
 }
 
-// cost[0] = sum_k stage objective, cost[1] = sum_k stage barrier, in node order (deterministic).
+// One warp per trajectory: reduces the sweep's partials [entries][4] = (objective, barrier, |g|_inf, max h) in a fixed
+// order (lane-strided, then xor-tree: deterministic), writes cost[0..1] into the record and, when `summaries` is not
+// null, the 32-scalar summary: u_0 (nu <= 24), f, Zsoft, |g|_inf, max h, zero padding.
 template <class T>
-__global__ void reduce_cost_kernel(const T* __restrict__ stage_cost, T* __restrict__ rec_all, long long ld_rec,
-                                   int cost_off, int N, long long batch) {
-    const long long b = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+__global__ void finalize_kernel(const T* __restrict__ partials, int entries, const T* __restrict__ xp_all, long long ld_xp,
+                                T* __restrict__ rec_all, long long ld_rec, T* __restrict__ summaries, int cost_off, int u0_off,
+                                int nu, int nx, int xm_off, long long batch) {
+    const long long b = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
     if (b >= batch) return;
-    const T* s = stage_cost + b * (N + 1) * 2;
-    T f = T(0), z = T(0);
-    for (int k = 0; k <= N; ++k) {
-        f += s[2 * k];
-        z += s[2 * k + 1];
+    const int lane = threadIdx.x & 31;
+    const T* p = partials + b * entries * 4;
+    const T* x = xp_all + b * ld_xp;
+    T f = T(0), z = T(0), gmax = T(0), hmax = -INFINITY;
+    for (int e = lane; e < entries; e += 32) {
+        f += p[4 * e];
+        z += p[4 * e + 1];
+        gmax = fmax(gmax, p[4 * e + 2]);
+        hmax = fmax(hmax, p[4 * e + 3]);
     }
-    rec_all[b * ld_rec + cost_off]     = f;
-    rec_all[b * ld_rec + cost_off + 1] = z;
+    if (lane < nx) gmax = fmax(gmax, m_abs(x[lane] - x[xm_off + lane]));  // rows x_0 - x_measured
+    for (int o = 16; o; o >>= 1) {
+        f += __shfl_xor_sync(0xffffffffu, f, o);
+        z += __shfl_xor_sync(0xffffffffu, z, o);
+        gmax = fmax(gmax, __shfl_xor_sync(0xffffffffu, gmax, o));
+        hmax = fmax(hmax, __shfl_xor_sync(0xffffffffu, hmax, o));
+    }
+    if (lane == 0) {
+        rec_all[b * ld_rec + cost_off]     = f;
+        rec_all[b * ld_rec + cost_off + 1] = z;
+    }
+    if (summaries) {
+        T v = T(0);
+        if (lane < nu) v = x[u0_off + lane];
+        else if (lane == 24) v = f;
+        else if (lane == 25) v = z;
+        else if (lane == 26) v = gmax;
+        else if (lane == 27) v = hmax;
+        summaries[b * 32 + lane] = v;
+    }
 }
 
 // out[b, e] = src[e] >= 0 ? rec[b, src[e]] : constant(-src[e]).  Serves the reference-format outputs

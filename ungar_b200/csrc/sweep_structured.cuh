@@ -34,10 +34,10 @@ struct QuadrupedStructured {
     static constexpr int RUN = 10;                          // nodes per run (even)
     static constexpr int CORE = 41;                         // doubles per node core (odd stride: conflict-free)
     static constexpr int oCORE = STAGE, oXS = oCORE + 452, oUS = oXS + (RUN + 2) * NX, oPS = oUS + (RUN + 1) * NU,
-                         PER_WARP = 4200;                   // doubles per warp (33 600 B, multiple of 16)
+                         PER_WARP = 4200;                   // doubles per team (33 600 B, multiple of 16)
     static_assert(oPS + (RUN + 1) * NP <= PER_WARP, "per-warp shared memory layout");
-    static constexpr int WARPS = 2;                         // per CTA; 3 CTAs / SM -> 6 warps, 201.6 KB smem
-    static constexpr int SMEM_BYTES = WARPS * PER_WARP * 8;
+    static constexpr int WARPS = 2;                         // one team of two warps per CTA; 6 CTAs / SM -> 12 warps
+    static constexpr int SMEM_BYTES = PER_WARP * 8;         // the team shares one staging image + inputs (33 600 B)
     // core slot layout
     static constexpr int cR = 0, cQ = 9, cE = 21, cXN = 25, cSGN = 38;
 };
@@ -143,16 +143,29 @@ __device__ __forceinline__ void node_core(const double* __restrict__ xk, const d
     core[Q::cSGN] = dm > dp ? 1.0 : -1.0;
 }
 
+// Branch-free RelaxedPolyBarrierFunction pieces (same polynomials as barrier_eval, selected instead of branched).
+__device__ __forceinline__ void barrier_eval_sel(const BarrierCoef<double>& B, double h, double& b0, double& dz, double& d2z) {
+    const double x = -h;
+    const double q0 = (0.5 * B.a1 * x + B.b1) * x + B.c1, q1 = B.a1 * x + B.b1;
+    const double c0 = ((1.0 / 3.0 * B.a2 * x + 0.5 * B.b2) * x + B.c2) * x + B.d2, c1 = (B.a2 * x + B.b2) * x + B.c2,
+                 c2 = 2.0 * B.a2 * x + B.b2;
+    const bool neg = x < 0.0, mid = x < B.eps;
+    b0  = neg ? q0 : (mid ? c0 : 0.0);
+    dz  = -(neg ? q1 : (mid ? c1 : 0.0));
+    d2z = neg ? B.a1 : (mid ? c2 : 0.0);
+}
+
+// One CTA = one TEAM of two warps sharing one staging image: warp w fills slot w of every node pair of the run.
 template <bool BARRIER>
-__global__ void __launch_bounds__(QuadrupedStructured::WARPS * 32, 3)
+__global__ void __launch_bounds__(64, 6)
 quadruped_structured_kernel(const double* __restrict__ xp_all, long long ld_xp, double* __restrict__ rec_all, long long ld_rec,
-                            double* __restrict__ stage_cost, int N, int run_len, int runs_per_traj, long long total_runs,
+                            double* __restrict__ partials, int N, int run_len, int runs_per_traj, long long total_runs,
                             RecLayout L, BarrierCoef<double> bar) {
     using Q = QuadrupedStructured;
     using Mdl = Quadruped;
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-    double* const wsm   = reinterpret_cast<double*>(smem_raw) + wib * Q::PER_WARP;
+    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+    double* const wsm   = reinterpret_cast<double*>(smem_raw);
     double* const stA   = wsm;
     double* const stH   = wsm + Q::PAIR_A;
     double* const stC   = wsm + Q::PAIR_A + Q::PAIR_H;
@@ -160,20 +173,30 @@ quadruped_structured_kernel(const double* __restrict__ xp_all, long long ld_xp, 
     double* const xs    = wsm + Q::oXS;
     double* const us    = wsm + Q::oUS;
     double* const ps    = wsm + Q::oPS;
-    for (int e = lane; e < Q::STAGE; e += 32) wsm[e] = 0.0;
-    __syncwarp();
+    for (int e = tid; e < Q::STAGE; e += 64) wsm[e] = 0.0;
+    __syncthreads();
 
+    // ---- per-lane roles and staging addresses (the slot is fixed per warp, so all of these are loop constants) ----------
     const int leg = lane >> 3, c = lane & 7;  // column lanes: c < 6 -> (f0 f1 f2 r0 r1 r2) of `leg`
-    const bool col_lane = c < 6;
-    const int c3 = c < 3 ? c : c - 3;
+    const bool col_lane = c < 6, fcol = c < 3;
+    const int c3 = fcol ? c : (c < 6 ? c - 3 : 0);
     const int cq = c & 3;
-    const long long warp_id = (long long)blockIdx.x * Q::WARPS + wib;
-    const long long n_warps = (long long)gridDim.x * Q::WARPS;
-    bool pending = false;  // a bulk store may still be reading the staging image
+    const bool qcol = lane < 4, wcol = lane >= 8 && lane < 11, pvlane = lane >= 16 && lane < 19;
+    double* const sA  = stA + w * Q::NA;
+    double* const sH  = stH + w * Q::TRI;
+    double* const cl  = stC + w * Q::NC + leg * 80;
+    double* const aCol = sA + 13 + 6 * leg + c;           // input column of this lane (valid if col_lane)
+    double* const aSt  = sA + (qcol ? 3 + c : 10 + c);    // state column of this lane (valid if qcol || wcol)
+    const int zi       = 13 + 6 * leg + c;
+    double* const hIn  = sH + zi * 37 - (zi * (zi - 1)) / 2;
+    double* const hSt  = sH + lane * 37 - (lane * (lane - 1)) / 2;  // valid if lane < 13
+    const double ec0 = c3 == 0 ? 1.0 : 0.0, ec1 = c3 == 1 ? 1.0 : 0.0, ec2 = c3 == 2 ? 1.0 : 0.0;
+    bool pending = false;  // a bulk store may still be reading the staging image (CTA-uniform)
 
-    for (long long run = warp_id; run < total_runs; run += n_warps) {
+    for (long long run = blockIdx.x; run < total_runs; run += gridDim.x) {
         const long long b = run / runs_per_traj;
-        const int k0    = int(run - b * runs_per_traj) * run_len;
+        const int run_in_traj = int(run - b * runs_per_traj);
+        const int k0    = run_in_traj * run_len;
         const int nodes = min(N, k0 + run_len) - k0;
         const double* __restrict__ x = xp_all + b * ld_xp;
         double* __restrict__ r       = rec_all + b * ld_rec;
@@ -183,260 +206,242 @@ quadruped_structured_kernel(const double* __restrict__ xp_all, long long ld_xp, 
         {
             const int halo = k0 > 0 ? 0 : 1;  // no node -1
             const double* gx = x + Mdl::x_off(N, k0 - 1 + halo);
-            for (int e = lane + halo * Q::NX; e < (nodes + 2) * Q::NX; e += 32) async_copy8(xs + e, gx + (e - halo * Q::NX));
+            for (int e = tid + halo * Q::NX; e < (nodes + 2) * Q::NX; e += 64) async_copy8(xs + e, gx + (e - halo * Q::NX));
             const double* gu = x + Mdl::u_off(N, k0 - 1 + halo);
-            for (int e = lane + halo * Q::NU; e < (nodes + 1) * Q::NU; e += 32) async_copy8(us + e, gu + (e - halo * Q::NU));
+            for (int e = tid + halo * Q::NU; e < (nodes + 1) * Q::NU; e += 64) async_copy8(us + e, gu + (e - halo * Q::NU));
             const double* gp = x + Mdl::p_off(N, k0 - 1 + halo);
-            for (int e = lane + halo * Q::NP; e < (nodes + 1) * Q::NP; e += 32) async_copy8(ps + e, gp + (e - halo * Q::NP));
+            for (int e = tid + halo * Q::NP; e < (nodes + 1) * Q::NP; e += 64) async_copy8(ps + e, gp + (e - halo * Q::NP));
             asm volatile("cp.async.commit_group;" ::: "memory");
         }
         const double dt = Rho[0], mass = Rho[1], I0 = Rho[2], I1 = Rho[3], I2 = Rho[4], Llen = Rho[17], g0 = Rho[18],
                      mu = Rho[19];
         const double iI0 = 1.0 / I0, iI1 = 1.0 / I1, iI2 = 1.0 / I2, inv_m = 1.0 / mass;
         const double hip0 = Rho[5 + 3 * leg], hip1 = Rho[6 + 3 * leg], hip2 = Rho[7 + 3 * leg];
-        if (k0 == 0 && lane < 13) r[L.g + lane] = x[lane] - x[Mdl::xm_off(N) + lane];  // x_0 - x_measured (:266-268)
+        const double sdt0 = dt * iI0, sdt1 = dt * iI1, sdt2 = dt * iI2;
         asm volatile("cp.async.wait_group 0;" ::: "memory");
-        __syncwarp();
+        __syncthreads();
 
-        // ---- phase A: thread-per-node primal cores (lane 0 = halo node k0 - 1: only its rotation matrix) --------------
-        if (lane >= 1 && lane <= nodes) {
-            node_core(xs + lane * Q::NX, us + lane * Q::NU, ps + lane * Q::NP, dt, inv_m, g0, I0, I1, I2, iI0, iI1, iI2,
-                      cores + lane * Q::CORE);
-        } else if (lane == 0 && k0 > 0) {
+        // ---- phase A: thread-per-node primal cores (thread 0 = halo node k0 - 1: only its rotation matrix) -------------
+        if (tid >= 1 && tid <= nodes) {
+            node_core(xs + tid * Q::NX, us + tid * Q::NU, ps + tid * Q::NP, dt, inv_m, g0, I0, I1, I2, iI0, iI1, iI2,
+                      cores + tid * Q::CORE);
+        } else if (tid == 0 && k0 > 0) {
             rot_matrix(xs[3], xs[4], xs[5], xs[6], cores + Q::cR);
         }
-        __syncwarp();
+        __syncthreads();
 
-        // ---- previous-node foot kinematics of this lane's leg (contact rows), carried from node to node ----------------
-        double Rp0 = 0, Rp1 = 0, Rp2 = 0;  // column c3 of R(q_{k-1})
-        double Dp0 = 0, Dp1 = 0, Dp2 = 0;  // d(R r_{k-1,leg}) / d q_cq
-        double fp0, fp1, fp2, s_prev;      // previous foot position and contact flag
-        if (k0 > 0) {
-            const double* Rh = cores + Q::cR;
-            const double r0 = us[6 * leg + 3], r1 = us[6 * leg + 4], r2 = us[6 * leg + 5];
-            Rp0 = Rh[c3]; Rp1 = Rh[3 + c3]; Rp2 = Rh[6 + c3];
-            drot_dq(cq, xs[3], xs[4], xs[5], xs[6], r0, r1, r2, Dp0, Dp1, Dp2);
-            fp0 = xs[0] + Rh[0] * r0 + Rh[1] * r1 + Rh[2] * r2;
-            fp1 = xs[1] + Rh[3] * r0 + Rh[4] * r1 + Rh[5] * r2;
-            fp2 = xs[2] + Rh[6] * r0 + Rh[7] * r1 + Rh[8] * r2;
-            s_prev = ps[13 + 4 * leg];
-        } else {
-            fp0 = Rho[34 + 4 * leg]; fp1 = Rho[35 + 4 * leg]; fp2 = Rho[36 + 4 * leg];  // measured foot (:296)
-            s_prev = Rho[33 + 4 * leg];
+        double cost_acc = 0.0, bar_acc = 0.0, gmax = 0.0, hmax = -INFINITY;  // per-lane partials over this warp's nodes
+        if (k0 == 0 && w == 0 && lane < 13) {  // x_0 - x_measured (:266-268)
+            const double gv = x[lane] - x[Mdl::xm_off(N) + lane];
+            r[L.g + lane] = gv;
+            gmax = fabs(gv);
         }
 
-        // ---- phase B: warp-per-node block fill ------------------------------------------------------------------------
-        for (int n = 0; n < nodes; ++n) {
-            const int k = k0 + n, slot = n & 1;
-            double* const sA = stA + slot * Q::NA;
-            double* const sH = stH + slot * Q::TRI;
-            double* const sC = stC + slot * Q::NC;
+        // ---- phase B: warp-per-node block fill; warp w owns node 2 p + w of pair p -----------------------------------------
+        const int pairs = (nodes + 1) >> 1;
+        for (int p = 0; p < pairs; ++p) {
+            const int n = 2 * p + w, k = k0 + n;
+            const bool active = n < nodes;
             const double* __restrict__ xk = xs + (n + 1) * Q::NX;
-            const double* __restrict__ uk = us + (n + 1) * Q::NU;
+            const double* __restrict__ uk = us + (n + 1) * Q::NU + 6 * leg;
             const double* __restrict__ pk = ps + (n + 1) * Q::NP;
             const double* __restrict__ co = cores + (n + 1) * Q::CORE;
             const double* __restrict__ R  = co + Q::cR;
             const double* __restrict__ Qw = co + Q::cQ;
 
-            const double qx = xk[3], qy = xk[4], qz = xk[5], qw = xk[6];
-            const double f0 = uk[6 * leg], f1 = uk[6 * leg + 1], f2 = uk[6 * leg + 2];
-            const double r0 = uk[6 * leg + 3], r1 = uk[6 * leg + 4], r2 = uk[6 * leg + 5];
-            const double s = pk[13 + 4 * leg];
-            const double Rc0 = R[c3], Rc1 = R[3 + c3], Rc2 = R[6 + c3];  // column c3 of R
-
-            // this lane's column of W = d w+ / d z:  f column: dt I^-1 s (r x R[:, c]);  r column: dt I^-1 s (e_c x R f)
-            double W0, W1, W2;
-            {
-                const bool fcol = c < 3;
+            // -------- values that do not touch the staging image: computed while the previous bulk store drains ------------
+            double W0 = 0, W1 = 0, W2 = 0, z0 = 0, z1 = 0, z2 = 0, s = 0, f0 = 0, f1 = 0, f2 = 0, r0 = 0, r1 = 0, r2 = 0;
+            double qx = 0, qy = 0, qz = 0, qw = 1, Rc0 = 0, Rc1 = 0, Rc2 = 0;
+            if (active) {
+                qx = xk[3]; qy = xk[4]; qz = xk[5]; qw = xk[6];
+                f0 = uk[0]; f1 = uk[1]; f2 = uk[2]; r0 = uk[3]; r1 = uk[4]; r2 = uk[5];
+                s = pk[13 + 4 * leg];
+                Rc0 = R[c3]; Rc1 = R[3 + c3]; Rc2 = R[6 + c3];  // column c3 of R
+                // this lane's column of W = d w+ / d z:  f column: dt I^-1 s (r x R[:, c]);  r column: dt I^-1 s (e_c x R f)
                 const double Rf0 = R[0] * f0 + R[1] * f1 + R[2] * f2, Rf1 = R[3] * f0 + R[4] * f1 + R[5] * f2,
                              Rf2 = R[6] * f0 + R[7] * f1 + R[8] * f2;
-                const double u0 = fcol ? r0 : (c3 == 0 ? 1.0 : 0.0), u1 = fcol ? r1 : (c3 == 1 ? 1.0 : 0.0),
-                             u2 = fcol ? r2 : (c3 == 2 ? 1.0 : 0.0);
+                const double u0 = fcol ? r0 : ec0, u1 = fcol ? r1 : ec1, u2 = fcol ? r2 : ec2;
                 const double v0 = fcol ? Rc0 : Rf0, v1 = fcol ? Rc1 : Rf1, v2 = fcol ? Rc2 : Rf2;
-                const double sc = dt * s;
-                W0 = sc * iI0 * (u1 * v2 - u2 * v1); W1 = sc * iI1 * (u2 * v0 - u0 * v2); W2 = sc * iI2 * (u0 * v1 - u1 * v0);
-            }
-            // q columns: dt I^-1 sum_i s_i r_i x d(R f_i)/dq_c — every leg adds its part, xor-reduced over the 4 legs
-            double z0, z1, z2;
-            {
+                W0 = s * sdt0 * (u1 * v2 - u2 * v1); W1 = s * sdt1 * (u2 * v0 - u0 * v2); W2 = s * sdt2 * (u0 * v1 - u1 * v0);
+                // q columns: dt I^-1 sum_i s_i r_i x d(R f_i)/dq_c — every leg adds its part, xor-reduced over the 4 legs
                 double d0, d1, d2;
                 drot_dq(cq, qx, qy, qz, qw, f0, f1, f2, d0, d1, d2);
                 z0 = s * (r1 * d2 - r2 * d1); z1 = s * (r2 * d0 - r0 * d2); z2 = s * (r0 * d1 - r1 * d0);
-                z0 += __shfl_xor_sync(0xffffffffu, z0, 8);  z1 += __shfl_xor_sync(0xffffffffu, z1, 8);  z2 += __shfl_xor_sync(0xffffffffu, z2, 8);
-                z0 += __shfl_xor_sync(0xffffffffu, z0, 16); z1 += __shfl_xor_sync(0xffffffffu, z1, 16); z2 += __shfl_xor_sync(0xffffffffu, z2, 16);
             }
-            if (slot == 0 && pending) {  // the previous pair's bulk stores must have finished reading the image
-                if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-                __syncwarp();
+            z0 += __shfl_xor_sync(0xffffffffu, z0, 8);  z1 += __shfl_xor_sync(0xffffffffu, z1, 8);  z2 += __shfl_xor_sync(0xffffffffu, z2, 8);
+            z0 += __shfl_xor_sync(0xffffffffu, z0, 16); z1 += __shfl_xor_sync(0xffffffffu, z1, 16); z2 += __shfl_xor_sync(0xffffffffu, z2, 16);
+
+            if (pending) {  // the previous pair's bulk stores must have finished reading the image
+                if (tid == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
                 pending = false;
             }
-            // ---- A = d(x_{k+1} - f)/dz: rows w+ (10-12) = -W, rows q+ (3-6) = -(Qw W [+ Rmat(e)]), rows p+/v+ constants --
-            {
-                double G0 = W0, G1 = W1, G2 = W2, add0 = 0, add1 = 0, add2 = 0, add3 = 0;
-                int col = 13 + 6 * leg + c;
-                bool write = col_lane;
-                if (write) {
-                    sA[10 * 37 + col] = -G0; sA[11 * 37 + col] = -G1; sA[12 * 37 + col] = -G2;
-                    sA[3 * 37 + col] = -(add0 + Qw[0] * G0 + Qw[1] * G1 + Qw[2] * G2);
-                    sA[4 * 37 + col] = -(add1 + Qw[3] * G0 + Qw[4] * G1 + Qw[5] * G2);
-                    sA[5 * 37 + col] = -(add2 + Qw[6] * G0 + Qw[7] * G1 + Qw[8] * G2);
-                    sA[6 * 37 + col] = -(add3 + Qw[9] * G0 + Qw[10] * G1 + Qw[11] * G2);
-                    if (c < 3) {
-                        sA[c * 37 + col]       = -(dt * dt) * (s * inv_m);
-                        sA[(7 + c) * 37 + col] = -dt * (s * inv_m);
+            __syncthreads();
+
+            if (active) {
+                // ---- A = d(x_{k+1} - f)/dz: rows w+ (10-12) = -W, rows q+ (3-6) = -(Qw W [+ Rmat(e)]), rows p+/v+ constants --
+                if (col_lane) {
+                    aCol[10 * 37] = -W0; aCol[11 * 37] = -W1; aCol[12 * 37] = -W2;
+                    aCol[3 * 37] = -(Qw[0] * W0 + Qw[1] * W1 + Qw[2] * W2);
+                    aCol[4 * 37] = -(Qw[3] * W0 + Qw[4] * W1 + Qw[5] * W2);
+                    aCol[5 * 37] = -(Qw[6] * W0 + Qw[7] * W1 + Qw[8] * W2);
+                    aCol[6 * 37] = -(Qw[9] * W0 + Qw[10] * W1 + Qw[11] * W2);
+                    if (fcol) {
+                        const double sm = s * inv_m * dt;
+                        aCol[c * 37]       = -dt * sm;
+                        aCol[(7 + c) * 37] = -sm;
                     }
                 }
-                // state columns: lanes 0..3 -> q_c, lanes 8..10 -> w_c (second, short pass with the same store code)
-                const bool qcol = lane < 4, wcol = lane >= 8 && lane < 11;
-                if (qcol || wcol) {
-                    const double e0 = co[Q::cE], e1 = co[Q::cE + 1], e2 = co[Q::cE + 2], e3 = co[Q::cE + 3];
+                if (qcol || wcol) {  // state columns: lanes 0..3 -> q_c, lanes 8..10 -> w_c
+                    double G0, G1, G2, add0 = 0, add1 = 0, add2 = 0, add3 = 0;
                     if (qcol) {
-                        G0 = dt * iI0 * z0; G1 = dt * iI1 * z1; G2 = dt * iI2 * z2;
-                        // Rmat(e) column c: d(q (x) e)/dq_c
-                        add0 = c == 0 ? e3 : c == 1 ? e2 : c == 2 ? -e1 : e0;
+                        const double e0 = co[Q::cE], e1 = co[Q::cE + 1], e2 = co[Q::cE + 2], e3 = co[Q::cE + 3];
+                        G0 = sdt0 * z0; G1 = sdt1 * z1; G2 = sdt2 * z2;
+                        add0 = c == 0 ? e3 : c == 1 ? e2 : c == 2 ? -e1 : e0;   // Rmat(e) column c: d(q (x) e)/dq_c
                         add1 = c == 0 ? -e2 : c == 1 ? e3 : c == 2 ? e0 : e1;
                         add2 = c == 0 ? e1 : c == 1 ? -e0 : c == 2 ? e3 : e2;
                         add3 = c == 0 ? -e0 : c == 1 ? -e1 : c == 2 ? -e2 : e3;
-                        col = 3 + c;
                     } else {  // e_c + dt I^-1 (Iw x e_c - I_c (w x e_c))
                         const double w0 = xk[10], w1 = xk[11], w2 = xk[12];
                         const double Iw0 = I0 * w0, Iw1 = I1 * w1, Iw2 = I2 * w2;
-                        const double ec0 = c == 0 ? 1.0 : 0.0, ec1 = c == 1 ? 1.0 : 0.0, ec2 = c == 2 ? 1.0 : 0.0;
                         const double Ic = pick3(c, I0, I1, I2);
-                        G0 = ec0 + dt * iI0 * ((Iw1 * ec2 - Iw2 * ec1) - Ic * (w1 * ec2 - w2 * ec1));
-                        G1 = ec1 + dt * iI1 * ((Iw2 * ec0 - Iw0 * ec2) - Ic * (w2 * ec0 - w0 * ec2));
-                        G2 = ec2 + dt * iI2 * ((Iw0 * ec1 - Iw1 * ec0) - Ic * (w0 * ec1 - w1 * ec0));
-                        col = 10 + c;
+                        G0 = ec0 + sdt0 * ((Iw1 * ec2 - Iw2 * ec1) - Ic * (w1 * ec2 - w2 * ec1));
+                        G1 = ec1 + sdt1 * ((Iw2 * ec0 - Iw0 * ec2) - Ic * (w2 * ec0 - w0 * ec2));
+                        G2 = ec2 + sdt2 * ((Iw0 * ec1 - Iw1 * ec0) - Ic * (w0 * ec1 - w1 * ec0));
                     }
-                    sA[10 * 37 + col] = -G0; sA[11 * 37 + col] = -G1; sA[12 * 37 + col] = -G2;
-                    sA[3 * 37 + col] = -(add0 + Qw[0] * G0 + Qw[1] * G1 + Qw[2] * G2);
-                    sA[4 * 37 + col] = -(add1 + Qw[3] * G0 + Qw[4] * G1 + Qw[5] * G2);
-                    sA[5 * 37 + col] = -(add2 + Qw[6] * G0 + Qw[7] * G1 + Qw[8] * G2);
-                    sA[6 * 37 + col] = -(add3 + Qw[9] * G0 + Qw[10] * G1 + Qw[11] * G2);
+                    aSt[10 * 37] = -G0; aSt[11 * 37] = -G1; aSt[12 * 37] = -G2;
+                    aSt[3 * 37] = -(add0 + Qw[0] * G0 + Qw[1] * G1 + Qw[2] * G2);
+                    aSt[4 * 37] = -(add1 + Qw[3] * G0 + Qw[4] * G1 + Qw[5] * G2);
+                    aSt[5 * 37] = -(add2 + Qw[6] * G0 + Qw[7] * G1 + Qw[8] * G2);
+                    aSt[6 * 37] = -(add3 + Qw[9] * G0 + Qw[10] * G1 + Qw[11] * G2);
                 }
-                if (leg == 2 && c < 3) {  // lanes 16..18: the constant p / v entries
+                if (pvlane) {  // lanes 16..18: the constant p / v entries
                     sA[c * 37 + c] = -1.0; sA[c * 37 + 7 + c] = -dt; sA[(7 + c) * 37 + 7 + c] = -1.0;
                 }
-            }
 
-            // ---- state part of the objective and the defects: lanes 0..12 own state entry `lane` -----------------------------
-            double cost_part = 0.0, bar_part = 0.0;
-            if (lane < 13) {
-                const double sgn = co[Q::cSGN];
-                const double wgt = lane < 2 ? 0.1 : (lane == 2 ? 10.0 : 1.0);  // Vector3r{0.1, 0.1, 10} (:228)
-                const bool isq   = lane >= 3 && lane < 7;
-                const double res = wgt * (isq ? xk[lane] + sgn * pk[lane] : xk[lane] - pk[lane]);
-                cost_part = res * res;
-                r[L.grad + Mdl::x_off(N, k) + lane] = 2.0 * wgt * res;
-                sH[lane * 37 - (lane * (lane - 1)) / 2] = 2.0 * wgt * wgt + (BARRIER ? 1e-6 : 0.0);
-                r[L.g + 13 + 13 * k + lane] = xk[13 + lane] - co[Q::cXN + lane];  // x_{k+1} - f(x_k, u_k)   (:276)
-            }
+                // ---- state part of the objective and the defects: lanes 0..12 own state entry `lane` -----------------------
+                if (lane < 13) {
+                    const double sgn = co[Q::cSGN];
+                    const double wgt = lane < 2 ? 0.1 : (lane == 2 ? 10.0 : 1.0);  // Vector3r{0.1, 0.1, 10} (:228)
+                    const bool isq   = lane >= 3 && lane < 7;
+                    const double res = wgt * (isq ? xk[lane] + sgn * pk[lane] : xk[lane] - pk[lane]);
+                    cost_acc += res * res;
+                    r[L.grad + Mdl::x_off(N, k) + lane] = 2.0 * wgt * res;
+                    *hSt = 2.0 * wgt * wgt + (BARRIER ? 1e-6 : 0.0);
+                    const double gv = xk[13 + lane] - co[Q::cXN + lane];  // x_{k+1} - f(x_k, u_k)   (:276)
+                    r[L.g + 13 + 13 * k + lane] = gv;
+                    gmax = fmax(gmax, fabs(gv));
+                }
 
-            // ---- this lane's input entry: objective, inequalities of its leg, barrier, Gauss-Newton rows -----------------------
-            if (col_lane) {
-                const int zi   = 13 + 6 * leg + c;
-                const int diag = zi * 37 - (zi * (zi - 1)) / 2;
-                if (c < 3) {  // f_c:  h_A = -s f_z,  h_B = s |f_xy|_eps - mu f_z   (:330-331)
-                    const double fxy = sqrt(f0 * f0 + f1 * f1 + UB_EPS);
-                    const double hA = -s * f2, hB = s * fxy - mu * f2;
-                    double bA = 0, dA = 0, ddA = 0, bB = 0, dB = 0, ddB = 0;
-                    if (BARRIER) {
-                        barrier_eval(bar, hA, &bA, &dA, &ddA);
-                        barrier_eval(bar, hB, &bB, &dB, &ddB);
+                // ---- this lane's input entry: objective, inequalities of its leg, barrier, Gauss-Newton rows -----------------
+                if (col_lane) {
+                    if (fcol) {  // f_c:  h_A = -s f_z,  h_B = s |f_xy|_eps - mu f_z   (:330-331)
+                        const double f2xy = f0 * f0 + f1 * f1 + UB_EPS;
+                        const double inv_fxy = rsqrt(f2xy), fxy = f2xy * inv_fxy;
+                        const double hA = -s * f2, hB = s * fxy - mu * f2;
+                        double bA = 0, dA = 0, ddA = 0, bB = 0, dB = 0, ddB = 0;
+                        if (BARRIER) {
+                            barrier_eval_sel(bar, hA, bA, dA, ddA);
+                            barrier_eval_sel(bar, hB, bB, dB, ddB);
+                        }
+                        const double gB0 = s * f0 * inv_fxy, gB1 = s * f1 * inv_fxy, gB2 = -mu;  // grad h_B wrt f
+                        const double gA_c = c == 2 ? -s : 0.0, gB_c = pick3(c, gB0, gB1, gB2), fc = uk[c];
+                        cost_acc += 1e-8 * fc * fc;
+                        r[L.grad + Mdl::u_off(N, k) + 6 * leg + c] = 2e-8 * fc + dA * gA_c + dB * gB_c;
+                        if (c < 2) {
+                            const double hv = c == 0 ? hA : hB;
+                            r[L.h + 12 * k + 3 * leg + c] = hv;
+                            bar_acc += c == 0 ? bA : bB;
+                            hmax = fmax(hmax, hv);
+                        }
+                        hIn[0] = ddA * gA_c * gA_c + ddB * gB_c * gB_c + 2e-8 + (BARRIER ? 1e-6 : 0.0);
+                        if (c < 2) hIn[1] = ddA * gA_c * (c == 1 ? -s : 0.0) + ddB * gB_c * (c == 0 ? gB1 : gB2);
+                        if (c < 1) hIn[2] = ddA * gA_c * (-s) + ddB * gB_c * gB2;
+                    } else {  // r_c':  h_C = s |r - hip|_eps - L   (:332-333)
+                        const double dr0 = r0 - hip0, dr1 = r1 - hip1, dr2 = r2 - hip2;
+                        const double n2 = dr0 * dr0 + dr1 * dr1 + dr2 * dr2 + UB_EPS;
+                        const double inv_nr = rsqrt(n2), nr = n2 * inv_nr;
+                        const double hC = s * nr - Llen;
+                        double bC = 0, dC = 0, ddC = 0;
+                        if (BARRIER) barrier_eval_sel(bar, hC, bC, dC, ddC);
+                        const double gC0 = s * dr0 * inv_nr, gC1 = s * dr1 * inv_nr, gC2 = s * dr2 * inv_nr;
+                        const double gC_c = pick3(c3, gC0, gC1, gC2);
+                        const double rc = uk[c] - pk[14 + 4 * leg + c3];
+                        cost_acc += rc * rc;
+                        r[L.grad + Mdl::u_off(N, k) + 6 * leg + c] = 2.0 * rc + dC * gC_c;
+                        if (c == 3) {
+                            r[L.h + 12 * k + 3 * leg + 2] = hC;
+                            bar_acc += bC;
+                            hmax = fmax(hmax, hC);
+                        }
+                        hIn[0] = ddC * gC_c * gC_c + 2.0 + (BARRIER ? 1e-6 : 0.0);
+                        if (c3 < 2) hIn[1] = ddC * gC_c * (c3 == 0 ? gC1 : gC2);
+                        if (c3 < 1) hIn[2] = ddC * gC_c * gC2;
                     }
-                    const double inv_fxy = 1.0 / fxy;
-                    const double gB0 = s * f0 * inv_fxy, gB1 = s * f1 * inv_fxy, gB2 = -mu;  // grad h_B wrt f
-                    const double gA_c = c == 2 ? -s : 0.0, gB_c = pick3(c, gB0, gB1, gB2), fc = pick3(c, f0, f1, f2);
-                    cost_part += 1e-8 * fc * fc;
-                    r[L.grad + Mdl::u_off(N, k) + 6 * leg + c] = 2e-8 * fc + dA * gA_c + dB * gB_c;
-                    if (c < 2) {
-                        r[L.h + 12 * k + 3 * leg + c] = c == 0 ? hA : hB;
-                        bar_part = c == 0 ? bA : bB;
-                    }
-                    sH[diag] = ddA * gA_c * gA_c + ddB * gB_c * gB_c + 2e-8 + (BARRIER ? 1e-6 : 0.0);
-                    if (c < 2) sH[diag + 1] = ddA * gA_c * (c == 1 ? -s : 0.0) + ddB * gB_c * (c == 0 ? gB1 : gB2);
-                    if (c < 1) sH[diag + 2] = ddA * gA_c * (-s) + ddB * gB_c * gB2;
-                } else {  // r_c':  h_C = s |r - hip|_eps - L   (:332-333)
-                    const double dr0 = r0 - hip0, dr1 = r1 - hip1, dr2 = r2 - hip2;
-                    const double nr = sqrt(dr0 * dr0 + dr1 * dr1 + dr2 * dr2 + UB_EPS);
-                    const double hC = s * nr - Llen;
-                    double bC = 0, dC = 0, ddC = 0;
-                    if (BARRIER) barrier_eval(bar, hC, &bC, &dC, &ddC);
-                    const double inv_nr = 1.0 / nr;
-                    const double gC0 = s * dr0 * inv_nr, gC1 = s * dr1 * inv_nr, gC2 = s * dr2 * inv_nr;
-                    const double gC_c = pick3(c3, gC0, gC1, gC2);
-                    const double rc = pick3(c3, r0, r1, r2) - pk[14 + 4 * leg + c3];
-                    cost_part += rc * rc;
-                    r[L.grad + Mdl::u_off(N, k) + 6 * leg + c] = 2.0 * rc + dC * gC_c;
-                    if (c == 3) {
-                        r[L.h + 12 * k + 3 * leg + 2] = hC;
-                        bar_part = bC;
-                    }
-                    sH[diag] = ddC * gC_c * gC_c + 2.0 + (BARRIER ? 1e-6 : 0.0);
-                    if (c3 < 2) sH[diag + 1] = ddC * gC_c * (c3 == 0 ? gC1 : gC2);
-                    if (c3 < 1) sH[diag + 2] = ddC * gC_c * gC2;
                 }
-            }
-            // stage cost / barrier value: deterministic xor-tree over the warp
-            cost_part = warp_sum(cost_part);
-            bar_part  = warp_sum(bar_part);
-            if (lane == 0) {
-                stage_cost[((long long)b * (N + 1) + k) * 2]     = cost_part;
-                stage_cost[((long long)b * (N + 1) + k) * 2 + 1] = bar_part;
-            }
 
-            // ---- contact rows of this lane's leg (:279-303) ----------------------------------------------------------------------
-            {
-                const double ft0 = xk[0] + R[0] * r0 + R[1] * r1 + R[2] * r2;
-                const double ft1 = xk[1] + R[3] * r0 + R[4] * r1 + R[5] * r2;
-                const double ft2 = xk[2] + R[6] * r0 + R[7] * r1 + R[8] * r2;
-                const double c0 = (1.0 - s_prev) * s, ss = s_prev * s;
-                double D0, D1, D2;
-                drot_dq(cq, qx, qy, qz, qw, r0, r1, r2, D0, D1, D2);
-                double* const cl = sC + leg * 80;
-                if (c < 4) {  // d foot / d q_c, and the contact values (row c)
-                    cl[3 + c] = c0 * D2;
-                    cl[20 + 3 + c] = ss * D0; cl[40 + 3 + c] = ss * D1; cl[60 + 3 + c] = ss * D2;
-                    cl[20 + 13 + c] = -ss * Dp0; cl[40 + 13 + c] = -ss * Dp1; cl[60 + 13 + c] = -ss * Dp2;
-                    const double val = c == 0 ? c0 * ft2 : ss * (c == 1 ? ft0 - fp0 : c == 2 ? ft1 - fp1 : ft2 - fp2);
-                    r[L.g + 13 + 13 * N + 16 * k + 4 * leg + c] = val;
+                // ---- contact rows of this lane's leg (:279-303); previous-node kinematics recomputed from shared memory ---------
+                {
+                    const double ft0 = xk[0] + R[0] * r0 + R[1] * r1 + R[2] * r2;
+                    const double ft1 = xk[1] + R[3] * r0 + R[4] * r1 + R[5] * r2;
+                    const double ft2 = xk[2] + R[6] * r0 + R[7] * r1 + R[8] * r2;
+                    double Rp0 = 0, Rp1 = 0, Rp2 = 0, Dp0 = 0, Dp1 = 0, Dp2 = 0, fp0, fp1, fp2, s_prev;
+                    if (k > 0) {
+                        const double* xq = xk - Q::NX;
+                        const double* Rh = co - Q::CORE + Q::cR;
+                        const double q0 = uk[3 - Q::NU], q1 = uk[4 - Q::NU], q2 = uk[5 - Q::NU];  // r_{k-1, leg}
+                        Rp0 = Rh[c3]; Rp1 = Rh[3 + c3]; Rp2 = Rh[6 + c3];
+                        drot_dq(cq, xq[3], xq[4], xq[5], xq[6], q0, q1, q2, Dp0, Dp1, Dp2);
+                        fp0 = xq[0] + Rh[0] * q0 + Rh[1] * q1 + Rh[2] * q2;
+                        fp1 = xq[1] + Rh[3] * q0 + Rh[4] * q1 + Rh[5] * q2;
+                        fp2 = xq[2] + Rh[6] * q0 + Rh[7] * q1 + Rh[8] * q2;
+                        s_prev = pk[13 + 4 * leg - Q::NP];
+                    } else {
+                        fp0 = Rho[34 + 4 * leg]; fp1 = Rho[35 + 4 * leg]; fp2 = Rho[36 + 4 * leg];  // measured foot (:296)
+                        s_prev = Rho[33 + 4 * leg];
+                    }
+                    const double c0 = (1.0 - s_prev) * s, ss = s_prev * s;
+                    double D0, D1, D2;
+                    drot_dq(cq, qx, qy, qz, qw, r0, r1, r2, D0, D1, D2);
+                    if (c < 4) {  // d foot / d q_c, and the contact values (row c)
+                        cl[3 + c] = c0 * D2;
+                        cl[20 + 3 + c] = ss * D0; cl[40 + 3 + c] = ss * D1; cl[60 + 3 + c] = ss * D2;
+                        cl[20 + 13 + c] = -ss * Dp0; cl[40 + 13 + c] = -ss * Dp1; cl[60 + 13 + c] = -ss * Dp2;
+                        const double val = c == 0 ? c0 * ft2 : ss * (c == 1 ? ft0 - fp0 : c == 2 ? ft1 - fp1 : ft2 - fp2);
+                        r[L.g + 13 + 13 * N + 16 * k + 4 * leg + c] = val;
+                        gmax = fmax(gmax, fabs(val));
+                    }
+                    if (c < 3) {  // d foot / d r_c = R[:, c];  d foot / d p = I
+                        cl[7 + c] = c0 * Rc2;
+                        cl[20 + 7 + c] = ss * Rc0; cl[40 + 7 + c] = ss * Rc1; cl[60 + 7 + c] = ss * Rc2;
+                        cl[20 + 17 + c] = -ss * Rp0; cl[40 + 17 + c] = -ss * Rp1; cl[60 + 17 + c] = -ss * Rp2;
+                        cl[(c + 1) * 20 + c]      = ss;
+                        cl[(c + 1) * 20 + 10 + c] = k > 0 ? -ss : 0.0;
+                        if (c == 2) cl[2] = c0;
+                    }
                 }
-                if (c < 3) {  // d foot / d r_c = R[:, c];  d foot / d p = I
-                    cl[7 + c] = c0 * Rc2;
-                    cl[20 + 7 + c] = ss * Rc0; cl[40 + 7 + c] = ss * Rc1; cl[60 + 7 + c] = ss * Rc2;
-                    cl[20 + 17 + c] = -ss * Rp0; cl[40 + 17 + c] = -ss * Rp1; cl[60 + 17 + c] = -ss * Rp2;
-                    cl[(c + 1) * 20 + c]      = ss;
-                    cl[(c + 1) * 20 + 10 + c] = k > 0 ? -ss : 0.0;
-                    if (c == 2) cl[2] = c0;
-                }
-                Rp0 = Rc0; Rp1 = Rc1; Rp2 = Rc2; Dp0 = D0; Dp1 = D1; Dp2 = D2;  // carry to the next node
-                fp0 = ft0; fp1 = ft1; fp2 = ft2; s_prev = s;
             }
 
             // ---- node pair complete: hand the staged blocks to the TMA engine ------------------------------------------------------
-            if (slot == 1 || n + 1 == nodes) {
-                const int k_pair = k - slot;
-                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-                __syncwarp();
-                if (slot == 1) {
-                    if (lane == 0) {
-                        bulk_store(r + L.A + (long long)k_pair * Q::NA, stA, Q::PAIR_A * 8);
-                        bulk_store(r + L.H + (long long)k_pair * Q::TRI, stH, Q::PAIR_H * 8);
-                        bulk_store(r + L.C + (long long)k_pair * Q::NC, stC, Q::PAIR_C * 8);
-                        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-                    }
-                    pending = true;
-                } else {  // odd tail (never taken when the run length is even): plain coalesced stores
-                    for (int e = lane; e < Q::NA; e += 32) r[L.A + (long long)k_pair * Q::NA + e] = stA[e];
-                    for (int e = lane; e < Q::TRI; e += 32) r[L.H + (long long)k_pair * Q::TRI + e] = stH[e];
-                    for (int e = lane; e < Q::NC; e += 32) r[L.C + (long long)k_pair * Q::NC + e] = stC[e];
-                    __syncwarp();
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            __syncthreads();
+            const int k_pair = k0 + 2 * p;
+            if (2 * p + 1 < nodes) {
+                if (tid == 0) {
+                    bulk_store(r + L.A + (long long)k_pair * Q::NA, stA, Q::PAIR_A * 8);
+                    bulk_store(r + L.H + (long long)k_pair * Q::TRI, stH, Q::PAIR_H * 8);
+                    bulk_store(r + L.C + (long long)k_pair * Q::NC, stC, Q::PAIR_C * 8);
+                    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
                 }
+                pending = true;
+            } else {  // odd tail (never taken when the run length is even): plain coalesced stores of slot 0
+                for (int e = tid; e < Q::NA; e += 64) r[L.A + (long long)k_pair * Q::NA + e] = stA[e];
+                for (int e = tid; e < Q::TRI; e += 64) r[L.H + (long long)k_pair * Q::TRI + e] = stH[e];
+                for (int e = tid; e < Q::NC; e += 64) r[L.C + (long long)k_pair * Q::NC + e] = stC[e];
             }
         }
 
-        // ---- terminal state x_N: objective gradient and diagonal block (last run of the trajectory) -----------------------------
-        if (k0 + nodes == N) {
+        // ---- terminal state x_N: objective gradient and diagonal block (warp 0 of the trajectory's last run) ------------------------
+        if (k0 + nodes == N && w == 0) {
             const double* __restrict__ xN = xs + (nodes + 1) * Q::NX;
             const double* __restrict__ pN = x + Mdl::p_off(N, N);
             double dm = 0.0, dp = 0.0;
@@ -446,19 +451,14 @@ quadruped_structured_kernel(const double* __restrict__ xp_all, long long ld_xp, 
                 dm += a * a; dp += bq * bq;
             }
             const double sgn = dm > dp ? 1.0 : -1.0;
-            double cpart = 0.0, hdiag = 0.0;
+            double hdiag = 0.0;
             if (lane < 13) {
                 const double wgt = lane < 2 ? 0.1 : (lane == 2 ? 10.0 : 1.0);
                 const bool isq   = lane >= 3 && lane < 7;
                 const double res = wgt * (isq ? xN[lane] + sgn * pN[lane] : xN[lane] - pN[lane]);
-                cpart = res * res;
+                cost_acc += res * res;
                 hdiag = 2.0 * wgt * wgt + (BARRIER ? 1e-6 : 0.0);
                 r[L.grad + Mdl::x_off(N, N) + lane] = 2.0 * wgt * res;
-            }
-            cpart = warp_sum(cpart);
-            if (lane == 0) {
-                stage_cost[((long long)b * (N + 1) + N) * 2]     = cpart;
-                stage_cost[((long long)b * (N + 1) + N) * 2 + 1] = 0.0;
             }
             for (int row = 0; row < 13; ++row) {  // packed upper triangle, row by row
                 const double dv = __shfl_sync(0xffffffffu, hdiag, row);
@@ -466,9 +466,21 @@ quadruped_structured_kernel(const double* __restrict__ xp_all, long long ld_xp, 
                 if (lane < 13 - row) r[L.HN + base + lane] = lane == 0 ? dv : 0.0;
             }
         }
-        __syncwarp();  // all lanes are done with xs/us/ps/cores before the next run overwrites them
+        // ---- per-(run, warp) partials: objective, barrier, |g|_inf, max h — one xor-tree per run instead of per node ----------------
+        cost_acc = warp_sum(cost_acc);
+        bar_acc  = warp_sum(bar_acc);
+#pragma unroll
+        for (int o = 16; o; o >>= 1) {
+            gmax = fmax(gmax, __shfl_xor_sync(0xffffffffu, gmax, o));
+            hmax = fmax(hmax, __shfl_xor_sync(0xffffffffu, hmax, o));
+        }
+        if (lane == 0) {
+            double* pt = partials + ((long long)b * (2 * runs_per_traj) + 2 * run_in_traj + w) * 4;
+            pt[0] = cost_acc; pt[1] = bar_acc; pt[2] = gmax; pt[3] = hmax;
+        }
+        __syncthreads();  // everyone is done with xs/us/ps/cores before the next run overwrites them
     }
-    if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+    if (tid == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
 }
 
 }  // namespace ub

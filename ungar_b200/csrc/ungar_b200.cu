@@ -328,8 +328,7 @@ int launch_structured(ungar_b200_model& mdl, const double* xp, int64_t batch, in
     const int runs_per_traj = (mdl.N + 9) / 10;
     const int run_len       = 2 * ((mdl.N + 2 * runs_per_traj - 1) / (2 * runs_per_traj));
     const long long total_runs = (long long)batch * runs_per_traj;
-    const long long want = (total_runs + Q::WARPS - 1) / Q::WARPS;
-    const unsigned grid  = unsigned(std::min<long long>(want, (long long)sm_count * 3));  // persistent: 3 CTAs / SM
+    const unsigned grid = unsigned(std::min<long long>(total_runs, (long long)sm_count * 6));  // persistent: 6 teams / SM
     int slot = -1;
     if (g_ring.enabled) {
         slot = g_ring.head;
@@ -354,8 +353,9 @@ int launch_structured(ungar_b200_model& mdl, const double* xp, int64_t batch, in
 
 template <class Mdl, class T, int M>
 int launch_sweep_t(ungar_b200_model& mdl, const void* xp, int64_t batch, int64_t ld_xp, void* rec, int64_t ld_rec,
-                   int mode, cudaStream_t stream) {
-    if (int rc = mdl.stage_cost.reserve(size_t(batch) * (mdl.N + 1) * 2 * sizeof(T))) return rc;
+                   int mode, void* summaries, cudaStream_t stream) {
+    int entries = mdl.N + 1;  // partial entries per trajectory (generic sweep: one per node)
+    if (int rc = mdl.stage_cost.reserve(size_t(batch) * (mdl.N + 1) * 4 * sizeof(T))) return rc;
     const T* x = static_cast<const T*>(xp);
     T* r       = static_cast<T*>(rec);
     int rc;
@@ -366,36 +366,39 @@ int launch_sweep_t(ungar_b200_model& mdl, const void* xp, int64_t batch, int64_t
         return UNGAR_B200_OK;
     }
     if constexpr (std::is_same<Mdl, ub::Quadruped>::value && std::is_same<T, double>::value) {
-        if (structured_applicable(mdl, rec, ld_rec))
+        if (structured_applicable(mdl, rec, ld_rec)) {
+            entries = 2 * ((mdl.N + 9) / 10);  // structured sweep: one per (run, warp)
             rc = mode == MODE_KKT ? launch_structured<true>(mdl, x, batch, ld_xp, r, ld_rec, stream)
                                   : launch_structured<false>(mdl, x, batch, ld_xp, r, ld_rec, stream);
-        else
+        } else
             rc = mode == MODE_KKT ? launch_generic<Mdl, T, M, true>(mdl, x, batch, ld_xp, r, ld_rec, stream)
                                   : launch_generic<Mdl, T, M, false>(mdl, x, batch, ld_xp, r, ld_rec, stream);
     } else if (mode == MODE_KKT) rc = launch_generic<Mdl, T, M, true>(mdl, x, batch, ld_xp, r, ld_rec, stream);
     else rc = launch_generic<Mdl, T, M, false>(mdl, x, batch, ld_xp, r, ld_rec, stream);
     if (rc) return rc;
-    const int threads = 128;
-    ub::reduce_cost_kernel<T><<<unsigned((batch + threads - 1) / threads), threads, 0, stream>>>(
-        static_cast<const T*>(mdl.stage_cost.ptr), r, ld_rec, mdl.rl.cost, mdl.N, batch);
+    const ungar_b200_kkt_layout& L = mdl.layout;
+    const int threads = 128;  // 4 trajectories per CTA
+    ub::finalize_kernel<T><<<unsigned((batch * 32 + threads - 1) / threads), threads, 0, stream>>>(
+        static_cast<const T*>(mdl.stage_cost.ptr), entries, x, ld_xp, r, ld_rec, static_cast<T*>(summaries), mdl.rl.cost,
+        int(L.nx * (L.horizon + 1)), int(L.nu), int(L.nx), int(Mdl::xm_off(mdl.N)), batch);
     ++g_launches;
     UB_CUDA(cudaGetLastError());
     return UNGAR_B200_OK;
 }
 
 int launch_sweep(ungar_b200_model& mdl, const void* xp, int64_t batch, int64_t ld_xp, void* rec, int64_t ld_rec,
-                 int mode, cudaStream_t stream) {
+                 int mode, void* summaries, cudaStream_t stream) {
     const bool f64 = mdl.desc.dtype == UNGAR_B200_F64;
     switch (mdl.desc.kind) {
         case UNGAR_B200_QUADROTOR:
-            return f64 ? launch_sweep_t<ub::Quadrotor, double, 15>(mdl, xp, batch, ld_xp, rec, ld_rec, mode, stream)
-                       : launch_sweep_t<ub::Quadrotor, float, 15>(mdl, xp, batch, ld_xp, rec, ld_rec, mode, stream);
+            return f64 ? launch_sweep_t<ub::Quadrotor, double, 15>(mdl, xp, batch, ld_xp, rec, ld_rec, mode, summaries, stream)
+                       : launch_sweep_t<ub::Quadrotor, float, 15>(mdl, xp, batch, ld_xp, rec, ld_rec, mode, summaries, stream);
         case UNGAR_B200_RC_CAR:
-            return f64 ? launch_sweep_t<ub::RcCar, double, 30>(mdl, xp, batch, ld_xp, rec, ld_rec, mode, stream)
-                       : launch_sweep_t<ub::RcCar, float, 30>(mdl, xp, batch, ld_xp, rec, ld_rec, mode, stream);
+            return f64 ? launch_sweep_t<ub::RcCar, double, 30>(mdl, xp, batch, ld_xp, rec, ld_rec, mode, summaries, stream)
+                       : launch_sweep_t<ub::RcCar, float, 30>(mdl, xp, batch, ld_xp, rec, ld_rec, mode, summaries, stream);
         case UNGAR_B200_QUADRUPED:
-            return f64 ? launch_sweep_t<ub::Quadruped, double, 4>(mdl, xp, batch, ld_xp, rec, ld_rec, mode, stream)
-                       : launch_sweep_t<ub::Quadruped, float, 4>(mdl, xp, batch, ld_xp, rec, ld_rec, mode, stream);
+            return f64 ? launch_sweep_t<ub::Quadruped, double, 4>(mdl, xp, batch, ld_xp, rec, ld_rec, mode, summaries, stream)
+                       : launch_sweep_t<ub::Quadruped, float, 4>(mdl, xp, batch, ld_xp, rec, ld_rec, mode, summaries, stream);
     }
     return fail(UNGAR_B200_EINVAL, "unknown model kind %d", mdl.desc.kind);
 }
@@ -472,7 +475,7 @@ int reference_call(ungar_b200_model* mdl, int32_t function, int want, const void
     } else {
         if ((rc = mdl->ws_records.reserve(size_t(batch) * mdl->layout.size * es))) return rc;
         const int mode = (function == UNGAR_B200_INEQUALITIES && want == WANT_JAC) ? MODE_JH : MODE_PLAIN;
-        rc = launch_sweep(*mdl, d_xp, batch, d_ld_xp, mdl->ws_records.ptr, mdl->layout.size, mode, stream);
+        rc = launch_sweep(*mdl, d_xp, batch, d_ld_xp, mdl->ws_records.ptr, mdl->layout.size, mode, nullptr, stream);
         if (rc) return rc;
         const int32_t* src = want == WANT_Y ? F.d_y_src : want == WANT_JAC ? F.d_jac_src : F.d_hes_src;
         rc = launch_gather(*mdl, mdl->ws_records.ptr, mdl->layout.size, src, n_out, d_out, d_ld_out, batch, stream);
@@ -619,12 +622,12 @@ int ungar_b200_kkt_blocks(ungar_b200_model* model, const void* xp, int64_t batch
     UB_CUDA(cudaSetDevice(model->desc.device));
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
     const size_t es = model->elem;
-    if (mem == UNGAR_B200_MEM_DEVICE) return launch_sweep(*model, xp, batch, ld_xp, records, ld_rec, MODE_KKT, stream);
+    if (mem == UNGAR_B200_MEM_DEVICE) return launch_sweep(*model, xp, batch, ld_xp, records, ld_rec, MODE_KKT, nullptr, stream);
 
     if (int rc = model->ws_xp.reserve(size_t(batch) * n_in * es)) return rc;
     if (int rc = model->ws_records.reserve(size_t(batch) * L.size * es)) return rc;
     UB_CUDA(cudaMemcpy2DAsync(model->ws_xp.ptr, n_in * es, xp, ld_xp * es, n_in * es, batch, cudaMemcpyHostToDevice, stream));
-    if (int rc = launch_sweep(*model, model->ws_xp.ptr, batch, n_in, model->ws_records.ptr, L.size, MODE_KKT, stream)) return rc;
+    if (int rc = launch_sweep(*model, model->ws_xp.ptr, batch, n_in, model->ws_records.ptr, L.size, MODE_KKT, nullptr, stream)) return rc;
     UB_CUDA(cudaMemcpy2DAsync(records, ld_rec * es, model->ws_records.ptr, L.size * es, L.size * es, batch,
                               cudaMemcpyDeviceToHost, stream));
     UB_CUDA(cudaStreamSynchronize(stream));
@@ -679,8 +682,7 @@ int ungar_b200_kkt_step(ungar_b200_model* model, const void* xp, int64_t batch, 
         else UB_CUDA(cudaMemcpy2DAsync(model->ws_xp.ptr, n_in * es, xp, ld_xp * es, n_in * es, batch, cudaMemcpyHostToDevice, stream));
         d_xp = model->ws_xp.ptr; d_ld_xp = n_in; d_summ = model->ws_out.ptr;
     }
-    if (int rc = launch_sweep(*model, d_xp, batch, d_ld_xp, records_device, ld_rec, MODE_KKT, stream)) return rc;
-    if (int rc = ungar_b200_summaries(model, d_xp, batch, d_ld_xp, records_device, ld_rec, d_summ, stream)) return rc;
+    if (int rc = launch_sweep(*model, d_xp, batch, d_ld_xp, records_device, ld_rec, MODE_KKT, d_summ, stream)) return rc;
     if (mem == UNGAR_B200_MEM_HOST) {
         UB_CUDA(cudaMemcpyAsync(summaries, d_summ, size_t(batch) * UNGAR_B200_SUMMARY_SIZE * es, cudaMemcpyDeviceToHost, stream));
         UB_CUDA(cudaStreamSynchronize(stream));
