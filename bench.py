@@ -347,9 +347,14 @@ def ours(args, rank: int, local_rank: int, world: int):
         pool = xp_np.astype(np.float64)
         n = cpu_sample_size(run, threads, pool, args.cpu_seconds)
         t, ref = run(pool[:n])
-        cpu = {"value": n * N / t, "unit": UNIT, "cores": threads, "kind": "port",
-               "sample": f"first {n} of the {B} trajectories, one pass, fp64, oracle/stage_port.cpp on {threads} threads "
-                         f"({t:.2f} s)"}
+        passes, t_total = 1, t
+        while t_total < args.cpu_seconds and passes < 10000:  # ~10-30 s of CPU work on the bounded sample
+            t, ref = run(pool[:n])
+            t_total += t
+            passes += 1
+        cpu = {"value": n * N * passes / t_total, "unit": UNIT, "cores": threads, "kind": "port",
+               "sample": f"first {n} of the {B} trajectories x {passes} passes, fp64, oracle/stage_port.cpp "
+                         f"(-O3 -ffast-math) on {threads} threads ({t_total:.1f} s of wall time)"}
         got = d_rec_sample(model, d_xps[0], n, tdt, dev)
         tol = 1e-6 if args.dtype == "f64" else 1e-3
         err = float(np.max(np.abs(got - ref) / (np.abs(ref) + 1e-3 * np.max(np.abs(ref)))))
