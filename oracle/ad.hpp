@@ -33,6 +33,7 @@ inline double ad_atan(double x) { return std::atan(x); }
 inline double ad_abs(double x) { return std::fabs(x); }
 inline double cond_gt(double a, double b, double t, double f) { return a > b ? t : f; }
 inline double cond_lt(double a, double b, double t, double f) { return a < b ? t : f; }
+inline double cond_select(bool take_t, double t, double f) { return take_t ? t : f; }
 
 // ---------------------------------------------------------------------------------------------
 // Sparse forward dual.  `T` is double (first order) or SDual<double> (second order, nested).

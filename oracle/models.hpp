@@ -200,8 +200,12 @@ inline void quadrotor_dynamics(const QuadrotorLayout& L, const S* xp, const S* x
         const double sign = (i % 2 == 0) ? 1.0 : -1.0;  // Utils::Pow(-1.0, i)
         sumD = sumD + V3<S>{S(0.0), S(0.0), d * r2 * sign};
     }
-    // :171-174
-    const V3<S> qT  = rotate(q, sumT);
+    // :171-174.  The summed thrust is (0, 0, T): CppAD folds the products with the literal zeros of
+    // Vector3ad::UnitZ() (:162), so q * sumT is taped as the third column of R(q) times T — restated here in that
+    // folded form so that the structural sparsity equals the reference tape's (z row independent of q.z, q.w).
+    const S& Tz = sumT.z;
+    const V3<S> qT{2.0 * (q.w * q.y + q.z * q.x) * Tz, 2.0 * (q.z * q.y - q.w * q.x) * Tz,
+                   Tz - 2.0 * (q.x * q.x + q.y * q.y) * Tz};
     const V3<S> pdd{qT.x / m, qT.y / m, (qT.z - m * g0) / m};
     const V3<S> Iw{moi.x * w.x, moi.y * w.y, moi.z * w.z};
     const V3<S> rhs = sumM + sumD - cross(w, Iw);

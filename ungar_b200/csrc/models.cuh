@@ -82,8 +82,11 @@ struct Quadrotor {  // example/mpc/quadrotor.example.cpp
             mom.y -= P[5 + 3 * i + 0] * t;
             mom.z += ((i & 1) ? -d : d) * r2;             // drag moment d r^2 e_z (-1)^i
         }
-        const Quat<S> q{z[3], z[4], z[5], z[6]};
-        const Vec3<S> qT = rotate(q, Vec3<S>{S(T(0)), S(T(0)), Tz});
+        // q * (0, 0, Tz): third column of R(q) times Tz.  CppAD folds the literal zeros of Vector3ad::UnitZ()
+        // (quadrotor.example.cpp:162), so the reference tape's z row does not depend on q.z / q.w; same form here.
+        const S &qx = z[3], &qy = z[4], &qz = z[5], &qw = z[6];
+        const Vec3<S> qT{T(2) * (qw * qy + qz * qx) * Tz, T(2) * (qz * qy - qw * qx) * Tz,
+                         Tz - T(2) * (qx * qx + qy * qy) * Tz};
         const Vec3<S> pdd{qT.x / m, qT.y / m, (qT.z - m * g0) / m};
         const Vec3<S> w{z[10], z[11], z[12]};
         const Vec3<S> Iw{P[2] * w.x, P[3] * w.y, P[4] * w.z};
