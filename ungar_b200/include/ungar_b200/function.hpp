@@ -1,0 +1,163 @@
+// C++ host mirror of the reference's evaluator interface over the C ABI (include/ungar_b200.h).
+//
+// `ungar_b200::Function` keeps the method names of `Ungar::Autodiff::Function`
+// (include/ungar/autodiff/function.hpp:180-361): Evaluate / operator() / Jacobian / Hessian / Implements* / *Size, with
+// host buffers in and out (batch 1 = the reference call; batch B = B reference calls in one launch).  It is header-only,
+// needs no Eigen, and throws std::runtime_error where the reference asserts / throws (assert.hpp:97-108,
+// function.hpp:531-534).  With Eigen available, `JacobianCsr()` gives exactly the three arrays the reference wraps in its
+// `Eigen::Map<const SparseMatrix<real_t, RowMajor>>` (function.hpp:126-133); INTEGRATION.md shows that adaptor.
+//
+// `ungar_b200::Model` stands where MakeFunction x 3 + MakeNLPProblem stand in the examples
+// (quadruped.example.cpp:343-363) and adds the batched KKT sweep that replaces
+// SoftSQPOptimizer::AssembleOSQPInstance (optimization/soft_sqp.hpp:141-158).
+#pragma once
+
+#include <cstdint>
+#include <stdexcept>
+#include <string>
+#include <utility>
+#include <vector>
+
+#include "ungar_b200.h"
+
+namespace ungar_b200 {
+
+using index_t = std::int64_t;
+
+inline void check(int status) {
+    if (status != UNGAR_B200_OK) throw std::runtime_error(std::string("ungar_b200: ") + ungar_b200_last_error());
+}
+
+template <class Real>
+struct dtype_of;
+template <>
+struct dtype_of<float> {
+    static constexpr int value = UNGAR_B200_F32;
+};
+template <>
+struct dtype_of<double> {
+    static constexpr int value = UNGAR_B200_F64;
+};
+
+struct CsrPattern {  // row-major, rows ascending — what function.hpp:109-124 builds from (rows, cols)
+    std::vector<int> innerStarts, outerIndices;
+    index_t rows = 0, cols = 0;
+};
+
+template <class Real = double>
+class Model;
+
+template <class Real = double>
+class Function {
+  public:
+    index_t IndependentVariableSize() const { return _nx; }
+    index_t ParameterSize() const { return _np; }
+    index_t DependentVariableSize() const { return _ny; }
+    bool ImplementsFunction() const { return true; }
+    bool ImplementsJacobian() const { return true; }
+    bool ImplementsHessian() const { return _which == UNGAR_B200_OBJECTIVE || _which == UNGAR_B200_SOFT_INEQUALITIES; }
+    index_t JacobianNonZeros() const { return _nnzJac; }
+    index_t HessianNonZeros() const { return _nnzHes; }
+
+    // y = f(xp) for `batch` stacked vectors xp (host memory, row stride = size of xp).
+    void Evaluate(const Real* xp, Real* y, index_t batch = 1) const {
+        check(ungar_b200_forward_zero(_model, _which, xp, batch, _nx + _np, y, _ny, UNGAR_B200_MEM_HOST, nullptr));
+    }
+    std::vector<Real> operator()(const std::vector<Real>& xp) const {
+        if (static_cast<index_t>(xp.size()) != _nx + _np) throw std::runtime_error("ungar_b200: xp has the wrong size");
+        std::vector<Real> y(static_cast<std::size_t>(_ny));
+        Evaluate(xp.data(), y.data());
+        return y;
+    }
+    // Nonzeros of the Jacobian in JacobianCsr() order; returns a reference to an internal buffer that the next call
+    // overwrites — the ownership rule of the reference (function.hpp:380-383).
+    const std::vector<Real>& Jacobian(const std::vector<Real>& xp) const {
+        _jacobianData.resize(static_cast<std::size_t>(_nnzJac));
+        check(ungar_b200_sparse_jacobian(_model, _which, xp.data(), 1, _nx + _np, _jacobianData.data(), _nnzJac,
+                                         UNGAR_B200_MEM_HOST, nullptr));
+        return _jacobianData;
+    }
+    // Upper-triangular Hessian of a scalar function (function.hpp:232-258).
+    const std::vector<Real>& Hessian(const std::vector<Real>& xp) const {
+        _hessianData.resize(static_cast<std::size_t>(_nnzHes));
+        check(ungar_b200_sparse_hessian(_model, _which, xp.data(), 1, _nx + _np, _hessianData.data(), _nnzHes,
+                                        UNGAR_B200_MEM_HOST, nullptr));
+        return _hessianData;
+    }
+    const CsrPattern& JacobianCsr() const { return _jacobianCsr; }
+    const CsrPattern& HessianCsr() const { return _hessianCsr; }
+
+  private:
+    friend class Model<Real>;
+    Function(ungar_b200_model* model, int which) : _model(model), _which(which) {
+        check(ungar_b200_function_info(model, which, &_nx, &_np, &_ny, &_nnzJac, &_nnzHes));
+        const int64_t *rows, *cols;
+        int64_t nnz;
+        check(ungar_b200_jacobian_sparsity(model, which, &rows, &cols, &nnz));
+        _jacobianCsr = MakeCsr(rows, cols, nnz, _ny, _nx);
+        if (ImplementsHessian()) {
+            check(ungar_b200_hessian_sparsity(model, which, &rows, &cols, &nnz));
+            _hessianCsr = MakeCsr(rows, cols, nnz, _nx, _nx);
+        }
+    }
+    static CsrPattern MakeCsr(const int64_t* rows, const int64_t* cols, int64_t nnz, index_t nRows, index_t nCols) {
+        CsrPattern p;
+        p.rows = nRows;
+        p.cols = nCols;
+        p.innerStarts.assign(static_cast<std::size_t>(nRows) + 1, 0);
+        p.outerIndices.resize(static_cast<std::size_t>(nnz));
+        for (int64_t e = 0; e < nnz; ++e) {
+            ++p.innerStarts[static_cast<std::size_t>(rows[e]) + 1];
+            p.outerIndices[static_cast<std::size_t>(e)] = static_cast<int>(cols[e]);
+        }
+        for (index_t r = 0; r < nRows; ++r) p.innerStarts[r + 1] += p.innerStarts[r];
+        return p;
+    }
+
+    ungar_b200_model* _model;
+    int _which;
+    int64_t _nx = 0, _np = 0, _ny = 0, _nnzJac = 0, _nnzHes = 0;
+    CsrPattern _jacobianCsr, _hessianCsr;
+    mutable std::vector<Real> _jacobianData, _hessianData;
+};
+
+template <class Real>
+class Model {
+  public:
+    Model(int kind, int horizon, double barrierStiffness, double barrierEpsilon, int device = 0) {
+        ungar_b200_model_desc desc{kind, horizon, dtype_of<Real>::value, device, barrierStiffness, barrierEpsilon};
+        check(ungar_b200_model_create(&desc, &_handle));
+        check(ungar_b200_kkt_layout_get(_handle, &_layout));
+    }
+    ~Model() { ungar_b200_model_destroy(_handle); }
+    Model(const Model&)            = delete;
+    Model& operator=(const Model&) = delete;
+
+    Function<Real> objective() const { return Function<Real>(_handle, UNGAR_B200_OBJECTIVE); }
+    Function<Real> equalityConstraints() const { return Function<Real>(_handle, UNGAR_B200_EQUALITIES); }
+    Function<Real> inequalityConstraints() const { return Function<Real>(_handle, UNGAR_B200_INEQUALITIES); }
+    Function<Real> softInequalityConstraints() const { return Function<Real>(_handle, UNGAR_B200_SOFT_INEQUALITIES); }
+    const ungar_b200_kkt_layout& layout() const { return _layout; }
+    index_t VariableSize() const { return _layout.n_dec + _layout.n_par; }
+
+    // Device-resident sweep (pointers are device pointers; asynchronous on `stream`).
+    void KktBlocksDevice(const Real* xp, index_t batch, index_t ldXp, Real* records, index_t ldRec, void* stream = nullptr) {
+        check(ungar_b200_kkt_blocks(_handle, xp, batch, ldXp, records, ldRec, UNGAR_B200_MEM_DEVICE, stream));
+    }
+    // Host buffers in and out (H2D, sweep, D2H inside the call).
+    void KktBlocks(const Real* xp, index_t batch, Real* records) {
+        check(ungar_b200_kkt_blocks(_handle, xp, batch, VariableSize(), records, _layout.size, UNGAR_B200_MEM_HOST, nullptr));
+    }
+    // One outer-iteration step: records stay in HBM, [batch][32] summaries come back to the host.
+    void Step(const Real* xpHost, index_t batch, Real* summariesHost, Real* recordsDevice = nullptr, void* stream = nullptr) {
+        check(ungar_b200_kkt_step(_handle, xpHost, batch, VariableSize(), recordsDevice, _layout.size, summariesHost,
+                                  UNGAR_B200_MEM_HOST, stream));
+    }
+    ungar_b200_model* handle() const { return _handle; }
+
+  private:
+    ungar_b200_model* _handle = nullptr;
+    ungar_b200_kkt_layout _layout{};
+};
+
+}  // namespace ungar_b200
