@@ -46,20 +46,26 @@ UB_HD void tracking_terms(const S* z, const T* pref, const T* qref, const T* vre
     sink(T(1), w1 * (z[1] - pref[1]), true);
     sink(T(1), w2 * (z[2] - pref[2]), true);
     T dm = T(0), dp = T(0);
+#pragma unroll
     for (int i = 0; i < 4; ++i) {
         const T a = T(val(z[3 + i])) - qref[i], b = T(val(z[3 + i])) + qref[i];
         dm += a * a;
         dp += b * b;
     }
     const T sgn = dm > dp ? T(1) : T(-1);
+#pragma unroll
     for (int i = 0; i < 4; ++i) sink(T(1), z[3 + i] + sgn * qref[i], true);
+#pragma unroll
     for (int i = 0; i < 3; ++i) sink(T(1), z[7 + i] - vref[i], true);
+#pragma unroll
     for (int i = 0; i < 3; ++i) sink(T(1), z[10 + i] - wref[i], true);
 }
 
 // =============================================================================================
 struct Quadrotor {  // example/mpc/quadrotor.example.cpp
     static constexpr int KIND = 0, NX = 13, NU = 4, NZ = 17, NH = 8, LEGS = 0, HC = 1;
+    static constexpr bool INEQ_SEPARABLE = true;  // every inequality row touches one local variable (:280-288)
+    static constexpr bool TPN_DEFAULT = false, TPN_STRUCTURED_DEFAULT = true;  // measured defaults, DESIGN.md §5.3
     UB_HD static int n_dec(int N) { return NX * (N + 1) + NU * N; }
     UB_HD static int n_par(int N) { return 21 + 13 * (N + 1) + 13; }
     UB_HD static int m_eq(int N) { return NX * (N + 1); }
@@ -98,6 +104,7 @@ struct Quadrotor {  // example/mpc/quadrotor.example.cpp
     template <class S, class T>
     UB_HD static void inequalities(const T* xp, int N, int k, const S* z, S* h) {
         const T rmax = xp[n_dec(N) + 20];
+#pragma unroll
         for (int i = 0; i < 4; ++i) {
             h[2 * i]     = z[13 + i] - rmax;
             h[2 * i + 1] = -z[13 + i];
@@ -110,6 +117,7 @@ struct Quadrotor {  // example/mpc/quadrotor.example.cpp
         tracking_terms(z, P + 21 + 3 * k, P + 21 + 3 * (N + 1) + 4 * k, P + 21 + 7 * (N + 1) + 3 * k,
                        P + 21 + 10 * (N + 1) + 3 * k, T(1), T(1), T(1), sink);
         if (k == N) return;
+#pragma unroll
         for (int i = 0; i < 4; ++i) {
             if (k) sink(T(1e-6), z[13 + i] - xp[u_off(N, k - 1) + i], true);          // :219-225
             sink(T(1e-6), z[13 + i], true);                                            // :226-230
@@ -121,6 +129,8 @@ struct Quadrotor {  // example/mpc/quadrotor.example.cpp
 // =============================================================================================
 struct RcCar {  // example/mpc/rc_car.example.cpp
     static constexpr int KIND = 1, NX = 6, NU = 2, NZ = 8, NH = 3, LEGS = 0, HC = 1;
+    static constexpr bool INEQ_SEPARABLE = true;  // rc_car.example.cpp:271-282
+    static constexpr bool TPN_DEFAULT = true, TPN_STRUCTURED_DEFAULT = false;
     UB_HD static int n_dec(int N) { return NX * (N + 1) + NU * N; }
     UB_HD static int n_par(int N) { return 15 + 2 * (N + 1) + 6; }
     UB_HD static int m_eq(int N) { return NX * (N + 1); }
@@ -128,26 +138,34 @@ struct RcCar {  // example/mpc/rc_car.example.cpp
     UB_HD static int u_off(int N, int k) { return NX * (N + 1) + NU * k; }
     UB_HD static int xm_off(int N) { return n_dec(N) + 15 + 2 * (N + 1); }
 
-    // rcCarDynamics, rc_car.example.cpp:131-185.  z = [px py phi vx vy om | d delta]
+    // Force model of rcCarDynamics (rc_car.example.cpp:158-171): (vx, vy, om, d, delta) -> (vx', vy', om').  P = parameters.
     template <class S, class T>
-    UB_HD static void dynamics(const T* xp, int N, int k, const S* z, S* xn) {
-        const T* P = xp + n_dec(N);
-        const T dt = P[0], m = P[1], Iz = P[2], lf = P[3], lr = P[4], Bf = P[5], Cf = P[6], Df = P[7], Br = P[8],
-                Cr = P[9], Dr = P[10], Cm1 = P[11], Cm2 = P[12], Cr0 = P[13], Cr2 = P[14];
-        const S &phi = z[2], &vx = z[3], &vy = z[4], &om = z[5], &d = z[6], &delta = z[7];
+    UB_HD static void accelerations(const T* P, const S& vx, const S& vy, const S& om, const S& d, const S& delta, S* acc) {
+        const T m = P[1], Iz = P[2], lf = P[3], lr = P[4], Bf = P[5], Cf = P[6], Df = P[7], Br = P[8], Cr = P[9], Dr = P[10],
+                Cm1 = P[11], Cm2 = P[12], Cr0 = P[13], Cr2 = P[14];
         const S den    = vx + T(UB_EPS);
         const S alphaf = delta - m_atan((om * lf + vy) / den);
         const S alphar = m_atan((om * lr - vy) / den);
         const S Ffy    = Df * m_sin(Cf * m_atan(Bf * alphaf));
         const S Fry    = Dr * m_sin(Cr * m_atan(Br * alphar));
         const S Frx    = (Cm1 - Cm2 * vx) * d - Cr0 - Cr2 * (vx * vx);
-        S sd, cd, sp, cp;
+        S sd, cd;
         m_sincos(delta, &sd, &cd);
+        acc[0] = (Frx - Ffy * sd + m * vy * om) / m;
+        acc[1] = (Fry + Ffy * cd - m * vx * om) / m;
+        acc[2] = (Ffy * lf * cd - Fry * lr) / Iz;
+    }
+    // rcCarDynamics, rc_car.example.cpp:131-185.  z = [px py phi vx vy om | d delta]
+    template <class S, class T>
+    UB_HD static void dynamics(const T* xp, int N, int k, const S* z, S* xn) {
+        const T* P = xp + n_dec(N);
+        const T dt = P[0];
+        const S &phi = z[2], &vx = z[3], &vy = z[4], &om = z[5];
+        S acc[3];
+        accelerations(P, vx, vy, om, z[6], z[7], acc);
+        S sp, cp;
         m_sincos(phi, &sp, &cp);
-        const S vdx = (Frx - Ffy * sd + m * vy * om) / m;
-        const S vdy = (Fry + Ffy * cd - m * vx * om) / m;
-        const S omd = (Ffy * lf * cd - Fry * lr) / Iz;
-        const S vxn = vx + dt * vdx, vyn = vy + dt * vdy, omn = om + dt * omd;
+        const S vxn = vx + dt * acc[0], vyn = vy + dt * acc[1], omn = om + dt * acc[2];
         xn[0] = z[0] + dt * (vxn * cp - vyn * sp);
         xn[1] = z[1] + dt * (vxn * sp + vyn * cp);
         xn[2] = phi + dt * omn;
@@ -169,6 +187,7 @@ struct RcCar {  // example/mpc/rc_car.example.cpp
         sink(T(1), z[0] - pref[0], true);
         sink(T(1), z[1] - pref[1], true);
         if (k == N) return;
+#pragma unroll
         for (int i = 0; i < 2; ++i) {
             sink(T(1e-6), z[6 + i], true);
             if (k) sink(T(1e-6), z[6 + i] - xp[u_off(N, k - 1) + i], true);
@@ -180,6 +199,8 @@ struct RcCar {  // example/mpc/rc_car.example.cpp
 // =============================================================================================
 struct Quadruped {  // example/mpc/quadruped.example.cpp (single-rigid-body model)
     static constexpr int KIND = 2, NX = 13, NU = 24, NZ = 37, NH = 12, LEGS = 4, HC = 0;
+    static constexpr bool INEQ_SEPARABLE = false;  // friction-cone and leg-length rows couple three locals
+    static constexpr bool TPN_DEFAULT = false, TPN_STRUCTURED_DEFAULT = false;
     static constexpr int NP = 29;  // per-node parameter p_k (quadruped.example.cpp:94-95)
     UB_HD static int n_dec(int N) { return NX * (N + 1) + NU * N; }
     UB_HD static int n_par(int N) { return NP * (N + 1) + 49; }

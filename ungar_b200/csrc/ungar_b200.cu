@@ -15,6 +15,7 @@
 #include "../../include/ungar_b200.h"
 #include "sweep.cuh"
 #include "sweep_structured.cuh"
+#include "sweep_tpn.cuh"
 
 namespace {
 
@@ -351,6 +352,69 @@ int launch_structured(ungar_b200_model& mdl, const double* xp, int64_t batch, in
     return UNGAR_B200_OK;
 }
 
+// Thread-per-node sweep (sweep_tpn.cuh) for the models without contact rows; one CTA per trajectory, persistent.
+template <class Mdl, class T>
+bool tpn_applicable(const ungar_b200_model& mdl) {
+    const char* e = getenv("UNGAR_B200_FORCE_GENERIC");
+    if (e && e[0] == '1') return false;
+    const char* t = getenv("UNGAR_B200_FORCE_TPN");
+    if (!Mdl::TPN_DEFAULT && !(t && t[0] == '1')) return false;
+    const size_t smem = size_t(ub::TpnShape<Mdl>::offsets(mdl.N, int(mdl.layout.n_dec + mdl.layout.n_par)).total) * sizeof(T);
+    return Mdl::LEGS == 0 && mdl.N + 1 <= 1024 && smem <= 200 * 1024;
+}
+
+template <class Mdl, class T, bool BARRIER, bool STRUCT>
+int launch_tpn_s(ungar_b200_model& mdl, const T* xp, int64_t batch, int64_t ld_xp, T* rec, int64_t ld_rec, cudaStream_t stream) {
+    auto kernel = ub::tpn_sweep_kernel<Mdl, T, BARRIER, STRUCT>;
+    const int n_xp = int(mdl.layout.n_dec + mdl.layout.n_par);
+    const auto offs = ub::TpnShape<Mdl>::offsets(mdl.N, n_xp);
+    const int smem = offs.total * int(sizeof(T));
+    const int threads = ((mdl.N + 1 + 31) / 32) * 32;
+    // TMA bulk stores need 16-byte aligned global rows: record base and stride
+    const int bulk = ((reinterpret_cast<uintptr_t>(rec) & 15) == 0 && (ld_rec * sizeof(T)) % 16 == 0) ? 1 : 0;
+    static int configured_smem = 0, sm_count = 148;
+    if (configured_smem < smem) {
+        UB_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        UB_CUDA(cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, mdl.desc.device));
+        configured_smem = smem;
+    }
+    int per_sm = 1;
+    UB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, threads, smem));
+    const unsigned grid = unsigned(std::min<long long>(batch, (long long)sm_count * std::max(per_sm, 1)));
+    int slot = -1;
+    if (g_ring.enabled) {
+        slot = g_ring.head;
+        if (!g_ring.created[slot]) {
+            UB_CUDA(cudaEventCreate(&g_ring.start[slot]));
+            UB_CUDA(cudaEventCreate(&g_ring.stop[slot]));
+            g_ring.created[slot] = true;
+        }
+        UB_CUDA(cudaEventRecord(g_ring.start[slot], stream));
+    }
+    kernel<<<grid, threads, smem, stream>>>(xp, ld_xp, rec, ld_rec, static_cast<T*>(mdl.stage_cost.ptr), mdl.N, n_xp, batch,
+                                            mdl.rl, cast_barrier<T>(mdl.bar), offs, bulk);
+    if (slot >= 0) {
+        UB_CUDA(cudaEventRecord(g_ring.stop[slot], stream));
+        g_ring.head  = (g_ring.head + 1) % kRing;
+        g_ring.count = g_ring.count < kRing ? g_ring.count + 1 : kRing;
+    }
+    ++g_launches;
+    UB_CUDA(cudaGetLastError());
+    return UNGAR_B200_OK;
+}
+
+// UNGAR_B200_TPN_STRUCT=0/1 overrides the per-model default (hand-structured node Jacobian vs in-register vector duals).
+template <class Mdl, class T, bool BARRIER>
+int launch_tpn(ungar_b200_model& mdl, const T* xp, int64_t batch, int64_t ld_xp, T* rec, int64_t ld_rec, cudaStream_t stream) {
+    static const int forced = [] {
+        const char* e = getenv("UNGAR_B200_TPN_STRUCT");
+        return e ? (e[0] == '1' ? 1 : 0) : -1;
+    }();
+    const bool structured = forced >= 0 ? forced == 1 : Mdl::TPN_STRUCTURED_DEFAULT;
+    return structured ? launch_tpn_s<Mdl, T, BARRIER, true>(mdl, xp, batch, ld_xp, rec, ld_rec, stream)
+                      : launch_tpn_s<Mdl, T, BARRIER, false>(mdl, xp, batch, ld_xp, rec, ld_rec, stream);
+}
+
 template <class Mdl, class T, int M>
 int launch_sweep_t(ungar_b200_model& mdl, const void* xp, int64_t batch, int64_t ld_xp, void* rec, int64_t ld_rec,
                    int mode, void* summaries, cudaStream_t stream) {
@@ -371,6 +435,13 @@ int launch_sweep_t(ungar_b200_model& mdl, const void* xp, int64_t batch, int64_t
             rc = mode == MODE_KKT ? launch_structured<true>(mdl, x, batch, ld_xp, r, ld_rec, stream)
                                   : launch_structured<false>(mdl, x, batch, ld_xp, r, ld_rec, stream);
         } else
+            rc = mode == MODE_KKT ? launch_generic<Mdl, T, M, true>(mdl, x, batch, ld_xp, r, ld_rec, stream)
+                                  : launch_generic<Mdl, T, M, false>(mdl, x, batch, ld_xp, r, ld_rec, stream);
+    } else if constexpr (Mdl::LEGS == 0) {
+        if (tpn_applicable<Mdl, T>(mdl))
+            rc = mode == MODE_KKT ? launch_tpn<Mdl, T, true>(mdl, x, batch, ld_xp, r, ld_rec, stream)
+                                  : launch_tpn<Mdl, T, false>(mdl, x, batch, ld_xp, r, ld_rec, stream);
+        else
             rc = mode == MODE_KKT ? launch_generic<Mdl, T, M, true>(mdl, x, batch, ld_xp, r, ld_rec, stream)
                                   : launch_generic<Mdl, T, M, false>(mdl, x, batch, ld_xp, r, ld_rec, stream);
     } else if (mode == MODE_KKT) rc = launch_generic<Mdl, T, M, true>(mdl, x, batch, ld_xp, r, ld_rec, stream);
