@@ -68,7 +68,7 @@ def test_kkt_blocks_match_oracle(torch_cuda, oracle, name, N, dtype):
     assert model.layout["size"] == oracle.record_layout(mid, N)["size"]
     for key in ("g", "A", "C", "h", "cost", "grad", "H", "HN", "Hc"):
         assert model.layout[key] == oracle.record_layout(mid, N)[key]
-    xp64 = W.synthetic_batch(mid, N, B, seed=17)
+    xp64 = W.synthetic_batch(mid, N, B, seed=17, perturb_params=N % 2 == 1 or dtype == "f64")
     xp = xp64.astype(model.np_dtype)
     k, eps = EXAMPLE_BARRIER[mid]
     ref = oracle.stage_sweep(mid, N, xp.astype(np.float64), k, eps)  # oracle sees the rounded inputs

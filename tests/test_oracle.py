@@ -112,7 +112,7 @@ def test_poly_barrier_pieces(oracle):
 def test_ad_jacobians_match_central_differences(oracle, model):
     N = 4
     s = W.sizes(model, N)
-    xp = W.synthetic_batch(model, N, 3, seed=11)[2]
+    xp = W.synthetic_batch(model, N, 3, seed=11, perturb_params=True)[2]
     for fn, ny in ((OBJ, 1), (EQ, s["m_eq"]), (INEQ, s["m_ineq"])):
         r, c, v = oracle.jacobian(model, fn, N, xp)
         J = dense(r, c, v, (ny, s["n_dec"]))
@@ -153,7 +153,7 @@ def test_ad_hessian_matches_differences_of_gradients(oracle, model):
                                          (W.QUADRUPED, 30, (1.0, 1.0)), (W.QUADRUPED, 100, (1.0, 1.0))])
 def test_stage_port_equals_monolithic_assembly(oracle, model, N, bar):
     """soft_sqp.hpp:141-158 on the monolithic matrices == node-by-node port; the cut is lossless."""
-    xps = W.synthetic_batch(model, N, 3, seed=3)
+    xps = W.synthetic_batch(model, N, 3, seed=3, perturb_params=True)
     recs = oracle.stage_sweep(model, N, xps, bar[0], bar[1], threads=2)
     for b in (0, 2):
         mono = oracle.kkt_record(model, N, xps[b], bar[0], bar[1])  # raises if a nonzero is left out

@@ -14,7 +14,7 @@ for name, N, dtype, rtol in (("quadrotor", 30, "f32", 1e-3), ("quadrotor", 17, "
     mid = W.MODEL_IDS[name]
     k, eps = ungar_b200.EXAMPLE_BARRIER[mid]
     model = ungar_b200.Model(name, N, dtype=dtype, barrier=(k, eps))
-    xp = W.synthetic_batch(mid, N, 9, seed=31).astype(model.np_dtype)
+    xp = W.synthetic_batch(mid, N, 9, seed=31, perturb_params=True).astype(model.np_dtype)
     ref = model.split_record(orc.stage_sweep(mid, N, xp.astype(np.float64), k, eps))
     got = model.split_record(model.kkt_blocks(xp).astype(np.float64))
     worst = 0.0

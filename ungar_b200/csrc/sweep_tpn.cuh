@@ -183,8 +183,8 @@ struct NodeJacobian<Quadrotor> {
             const int c1i = (c + 1) % 3, c2i = (c + 2) % 3;
             T G[3];
             G[c]   = T(1);
-            G[c1i] = dt * iI[c1i] * (-Iw[c2i] + Iv[c] * wv[c2i]);   // (Iw x e_c)[c+1] = -Iw[c+2];  (w x e_c)[c+1] = -w[c+2]
-            G[c2i] = dt * iI[c2i] * (Iw[c1i] - Iv[c] * wv[c1i]);    // (Iw x e_c)[c+2] = +Iw[c+1]
+            G[c1i] = dt * iI[c1i] * (Iw[c2i] - Iv[c] * wv[c2i]);    // (Iw x e_c)[c+1] = +Iw[c+2];  (w x e_c)[c+1] = +w[c+2]
+            G[c2i] = dt * iI[c2i] * (-Iw[c1i] + Iv[c] * wv[c1i]);   // (Iw x e_c)[c+2] = -Iw[c+1];  (w x e_c)[c+2] = -w[c+1]
             const int col = 10 + c;
             A[10 * NZ + col] = -G[0]; A[11 * NZ + col] = -G[1]; A[12 * NZ + col] = -G[2];
 #pragma unroll

@@ -16,6 +16,7 @@
 #include "sweep.cuh"
 #include "sweep_structured.cuh"
 #include "sweep_tpn.cuh"
+#include "sweep_small.cuh"
 
 namespace {
 
@@ -403,6 +404,54 @@ int launch_tpn_s(ungar_b200_model& mdl, const T* xp, int64_t batch, int64_t ld_x
     return UNGAR_B200_OK;
 }
 
+// Warp-team sweep for the small models (sweep_small.cuh): 8 lanes per node, 4-node staging image, TMA bulk stores.
+template <class Mdl, class T>
+bool small_applicable(const ungar_b200_model& mdl, const void* rec, int64_t ld_rec) {
+    const char* e = getenv("UNGAR_B200_FORCE_GENERIC");
+    const char* t = getenv("UNGAR_B200_FORCE_TPN");
+    if ((e && e[0] == '1') || (t && t[0] == '1')) return false;
+    return Mdl::LEGS == 0 && (reinterpret_cast<uintptr_t>(rec) & 15) == 0 && (ld_rec * sizeof(T)) % 16 == 0;
+}
+
+template <class Mdl, class T, bool BARRIER>
+int launch_small(ungar_b200_model& mdl, const T* xp, int64_t batch, int64_t ld_xp, T* rec, int64_t ld_rec, cudaStream_t stream) {
+    constexpr int WARPS = 4;
+    auto kernel = ub::small_team_kernel<Mdl, T, BARRIER, WARPS>;
+    const int n_xp = int(mdl.layout.n_dec + mdl.layout.n_par);
+    const auto offs = ub::SmallShape<Mdl, T>::offsets(mdl.N, n_xp);
+    const int smem = WARPS * offs.total * int(sizeof(T));
+    static int configured_smem = 0, sm_count = 148;
+    if (configured_smem < smem) {
+        UB_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        UB_CUDA(cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, mdl.desc.device));
+        configured_smem = smem;
+    }
+    int per_sm = 1;
+    UB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, WARPS * 32, smem));
+    const long long want = (batch + WARPS - 1) / WARPS;
+    const unsigned grid = unsigned(std::min<long long>(want, (long long)sm_count * std::max(per_sm, 1)));
+    int slot = -1;
+    if (g_ring.enabled) {
+        slot = g_ring.head;
+        if (!g_ring.created[slot]) {
+            UB_CUDA(cudaEventCreate(&g_ring.start[slot]));
+            UB_CUDA(cudaEventCreate(&g_ring.stop[slot]));
+            g_ring.created[slot] = true;
+        }
+        UB_CUDA(cudaEventRecord(g_ring.start[slot], stream));
+    }
+    kernel<<<grid, WARPS * 32, smem, stream>>>(xp, ld_xp, rec, ld_rec, static_cast<T*>(mdl.stage_cost.ptr), mdl.N, n_xp, batch,
+                                               mdl.rl, cast_barrier<T>(mdl.bar), offs);
+    if (slot >= 0) {
+        UB_CUDA(cudaEventRecord(g_ring.stop[slot], stream));
+        g_ring.head  = (g_ring.head + 1) % kRing;
+        g_ring.count = g_ring.count < kRing ? g_ring.count + 1 : kRing;
+    }
+    ++g_launches;
+    UB_CUDA(cudaGetLastError());
+    return UNGAR_B200_OK;
+}
+
 // UNGAR_B200_TPN_STRUCT=0/1 overrides the per-model default (hand-structured node Jacobian vs in-register vector duals).
 template <class Mdl, class T, bool BARRIER>
 int launch_tpn(ungar_b200_model& mdl, const T* xp, int64_t batch, int64_t ld_xp, T* rec, int64_t ld_rec, cudaStream_t stream) {
@@ -438,7 +487,12 @@ int launch_sweep_t(ungar_b200_model& mdl, const void* xp, int64_t batch, int64_t
             rc = mode == MODE_KKT ? launch_generic<Mdl, T, M, true>(mdl, x, batch, ld_xp, r, ld_rec, stream)
                                   : launch_generic<Mdl, T, M, false>(mdl, x, batch, ld_xp, r, ld_rec, stream);
     } else if constexpr (Mdl::LEGS == 0) {
-        if (tpn_applicable<Mdl, T>(mdl))
+        const size_t small_smem = 4 * size_t(ub::SmallShape<Mdl, T>::offsets(mdl.N, int(mdl.layout.n_dec + mdl.layout.n_par)).total) * sizeof(T);
+        if (small_applicable<Mdl, T>(mdl, rec, ld_rec) && small_smem <= 200 * 1024) {
+            entries = 1;  // one partial per trajectory
+            rc = mode == MODE_KKT ? launch_small<Mdl, T, true>(mdl, x, batch, ld_xp, r, ld_rec, stream)
+                                  : launch_small<Mdl, T, false>(mdl, x, batch, ld_xp, r, ld_rec, stream);
+        } else if (tpn_applicable<Mdl, T>(mdl))
             rc = mode == MODE_KKT ? launch_tpn<Mdl, T, true>(mdl, x, batch, ld_xp, r, ld_rec, stream)
                                   : launch_tpn<Mdl, T, false>(mdl, x, batch, ld_xp, r, ld_rec, stream);
         else

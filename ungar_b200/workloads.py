@@ -140,7 +140,37 @@ def nominal(model: int, N: int, time: float | None = None) -> np.ndarray:
     return _NOMINAL[model](N, _DEFAULT_TIME[model] if time is None else time)
 
 
-def synthetic_batch(model: int, N: int, batch: int, seed: int = 20240807, time: float | None = None) -> np.ndarray:
+def perturb_parameters(model: int, N: int, xp: np.ndarray, rng) -> None:
+    """In-place, per-trajectory perturbation of the physical parameters and references (test coverage: anisotropic
+    inertia, asymmetric geometry, arbitrary contact schedules — nothing the nominal examples exercise)."""
+    s = sizes(model, N)
+    B, P = xp.shape[0], s["n_dec"]
+    scale = lambda n: rng.uniform(0.8, 1.25, (B, n))  # noqa: E731
+    if model == QUADROTOR:
+        xp[:, P + 1:P + 5] *= scale(4)              # mass, inertia (each axis separately)
+        xp[:, P + 5:P + 17] *= scale(12)            # propeller positions
+        xp[:, P + 18:P + 20] *= scale(2)            # thrust / drag constants
+        xp[:, P + 21:P + 21 + 3 * (N + 1)] += rng.uniform(-0.2, 0.2, (B, 3 * (N + 1)))
+        xp[:, P + 21 + 7 * (N + 1):P + 21 + 13 * (N + 1)] += 0.1 * rng.standard_normal((B, 6 * (N + 1)))
+    elif model == RC_CAR:
+        xp[:, P + 1:P + 15] *= scale(14)
+        xp[:, P + 15:P + 15 + 2 * (N + 1)] += rng.uniform(-0.2, 0.2, (B, 2 * (N + 1)))
+    else:
+        Rho = P + 29 * (N + 1)
+        xp[:, Rho + 1:Rho + 5] *= scale(4)          # mass, inertia
+        xp[:, Rho + 5:Rho + 18] *= scale(13)        # hips, leg length
+        xp[:, Rho + 19] *= scale(1)[:, 0]           # friction coefficient
+        par = xp[:, P:Rho].reshape(B, N + 1, 29)
+        par[:, :, 0:3] += rng.uniform(-0.05, 0.05, (B, N + 1, 3))
+        par[:, :, 7:13] += 0.1 * rng.standard_normal((B, N + 1, 6))
+        par[:, :, 13::4] = (rng.uniform(0, 1, (B, N + 1, 4)) > 0.4).astype(np.float64)   # contact schedule
+        par[:, :, 14:17] += rng.uniform(-0.03, 0.03, (B, N + 1, 3))
+        xp[:, Rho + 33:Rho + 49:4] = (rng.uniform(0, 1, (B, 4)) > 0.3).astype(np.float64)  # measured contacts
+        xp[:, Rho + 20:Rho + 23] += rng.uniform(-0.05, 0.05, (B, 3))
+
+
+def synthetic_batch(model: int, N: int, batch: int, seed: int = 20240807, time: float | None = None,
+                    perturb_params: bool = False) -> np.ndarray:
     """``[batch, n_xp]`` float64 trajectories: nominal point + seeded perturbation of X and U only.
 
     positions += U(-0.1, 0.1); quaternions = normalise(q + 0.1 N(0,1)^4) with the sign making q.q_ref > 0;
@@ -173,4 +203,6 @@ def synthetic_batch(model: int, N: int, batch: int, seed: int = 20240807, time: 
         X[:, :, 3:6] += 0.1 * rng.standard_normal((batch, N + 1, 3))
         X[:, :, 3] = np.maximum(X[:, :, 3], 0.5)
         U += 0.5 * rng.uniform(-1.0, 1.0, U.shape)
+    if perturb_params:
+        perturb_parameters(model, N, xp, rng)
     return np.ascontiguousarray(xp)
