@@ -150,6 +150,15 @@ int ungar_b200_summaries(ungar_b200_model* model, const void* xp, int64_t batch,
 int ungar_b200_kkt_step(ungar_b200_model* model, const void* xp, int64_t batch, int64_t ld_xp, void* records_device,
                         int64_t ld_rec, void* summaries, int32_t mem, void* stream);
 
+/* Replaces the QP solve SoftSQPOptimizer delegates to OSQP (optimization/soft_sqp.hpp:193-233) for the equality-
+ * constrained QP assembled by ungar_b200_kkt_blocks:  min 1/2 d^T P d + q^T d  s.t.  A d = -g.  Consumes the records in
+ * place (DEVICE pointers), writes the step `steps[b, 0:n_dec]` (the reference's `primal_solution()`, [X | U] order) and,
+ * if `multipliers` is not NULL, the equality multipliers `multipliers[b, 0:m_eq]` in the reference's row order.
+ * Exact stage-wise factorisation (block-tridiagonal Schur complement), not ADMM.  Quadruped, F64 only
+ * (UNGAR_B200_EUNSUPPORTED otherwise). */
+int ungar_b200_qp_solve(ungar_b200_model* model, const void* records_device, int64_t batch, int64_t ld_rec, void* steps,
+                        int64_t ld_steps, void* multipliers, int64_t ld_multipliers, void* stream);
+
 /* Device-side timing of the dominant kernel (the KKT sweep): when enabled, every sweep launch is bracketed by
  * CUDA events on the launching stream; ungar_b200_sweep_times synchronises and returns up to `cap` most recent
  * durations in milliseconds (oldest first) and clears the ring. */

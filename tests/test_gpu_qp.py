@@ -1,0 +1,78 @@
+"""Batched QP solve against the oracle: one sparse LU of the KKT system assembled from the same record
+(oracle/qp_reference.py::kkt_solve), plus size-independent optimality properties at the full BASELINE batch."""
+import numpy as np
+import pytest
+
+from ungar_b200 import EXAMPLE_BARRIER
+from ungar_b200 import workloads as W
+
+pytestmark = pytest.mark.gpu
+
+
+def layout_for_reference(model):
+    L = dict(model.layout)
+    return L
+
+
+@pytest.mark.parametrize("N,perturb", [(6, False), (30, True), (100, True), (100, False)])
+def test_qp_step_matches_sparse_kkt_solve(oracle, N, perturb):
+    import torch
+
+    import ungar_b200
+    from oracle import qp_reference as Q
+
+    k, eps = EXAMPLE_BARRIER[W.QUADRUPED]
+    model = ungar_b200.Model("quadruped", N, dtype="f64", barrier=(k, eps))
+    xp = W.synthetic_batch(W.QUADRUPED, N, 4, seed=41, perturb_params=perturb)
+    rec = model.kkt_blocks(torch.from_numpy(xp).cuda(), torch.zeros((4, model.layout["size"]), dtype=torch.float64, device="cuda"))
+    steps, mult = model.qp_solve(rec)
+    torch.cuda.synchronize()
+    steps, mult, rec_h = steps.cpu().numpy(), mult.cpu().numpy(), rec.cpu().numpy()
+    L = layout_for_reference(model)
+    for b in range(4):
+        d_ref, lam_ref = Q.kkt_solve(rec_h[b], L)
+        assert np.max(np.abs(steps[b] - d_ref)) <= 1e-7 * np.max(np.abs(d_ref)), (b, np.max(np.abs(steps[b] - d_ref)) / np.max(np.abs(d_ref)))
+        assert np.max(np.abs(mult[b] - lam_ref)) <= 1e-6 * max(1e-12, np.max(np.abs(lam_ref)))
+
+
+def test_qp_optimality_at_full_batch():
+    """KKT residuals of every trajectory of BASELINE config 4: A d = -g and P d + q + A^T lambda = 0."""
+    import torch
+
+    import ungar_b200
+    from oracle import qp_reference as Q
+
+    N, B = 100, 1024
+    k, eps = EXAMPLE_BARRIER[W.QUADRUPED]
+    model = ungar_b200.Model("quadruped", N, dtype="f64", barrier=(k, eps))
+    xp = W.synthetic_batch(W.QUADRUPED, N, B, seed=101)
+    d_xp = torch.from_numpy(xp).cuda()
+    rec = model.kkt_blocks(d_xp, torch.zeros((B, model.layout["size"]), dtype=torch.float64, device="cuda"))
+    steps, mult = model.qp_solve(rec)
+    torch.cuda.synchronize()
+    assert torch.isfinite(steps).all() and torch.isfinite(mult).all()
+    # residuals of a sample through the reference-format sparse matrices
+    L = model.layout
+    for b in (0, B // 3, B - 1):
+        x = xp[b]
+        Jg = model.equalityConstraints.Jacobian(x)
+        g = model.equalityConstraints(x)
+        d, lam = steps[b].cpu().numpy(), mult[b].cpu().numpy()
+        assert np.max(np.abs(Jg @ d + g)) < 1e-6 * max(1.0, np.max(np.abs(g)))  # A d = -g (up to the 1e-9 regulariser)
+        H, q, U, V, bb = Q.stage_blocks(rec[b].cpu().numpy(), dict(L))
+        r = Q.kkt_solve(rec[b].cpu().numpy(), dict(L))[0]
+        assert np.max(np.abs(d - r)) <= 1e-7 * np.max(np.abs(r))
+    # determinism
+    steps2, _ = model.qp_solve(rec)
+    assert torch.equal(steps2, steps)
+
+
+def test_qp_rejects_other_models():
+    import torch
+
+    import ungar_b200
+    from ungar_b200 import _lib
+
+    m = ungar_b200.Model("quadrotor", 30, dtype="f64")
+    with pytest.raises(_lib.UngarB200Error):
+        m.qp_solve(torch.zeros((1, m.layout["size"]), dtype=torch.float64, device="cuda"))

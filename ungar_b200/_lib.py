@@ -21,7 +21,7 @@ SYMBOLS = [
     "ungar_b200_jacobian_sparsity", "ungar_b200_hessian_sparsity", "ungar_b200_forward_zero",
     "ungar_b200_sparse_jacobian", "ungar_b200_sparse_hessian", "ungar_b200_kkt_layout_get",
     "ungar_b200_kkt_blocks", "ungar_b200_summaries", "ungar_b200_kkt_step", "ungar_b200_set_profiling",
-    "ungar_b200_sweep_times", "ungar_b200_launch_count", "ungar_b200_last_error",
+    "ungar_b200_sweep_times", "ungar_b200_qp_solve", "ungar_b200_launch_count", "ungar_b200_last_error",
     "ungar_b200_abi_version",
 ]
 
@@ -73,6 +73,7 @@ def load() -> ctypes.CDLL:
     L.ungar_b200_kkt_blocks.argtypes = [c_vp, c_vp, c_i64, c_i64, c_vp, c_i64, c_i32, c_vp]
     L.ungar_b200_summaries.argtypes = [c_vp, c_vp, c_i64, c_i64, c_vp, c_i64, c_vp, c_vp]
     L.ungar_b200_kkt_step.argtypes = [c_vp, c_vp, c_i64, c_i64, c_vp, c_i64, c_vp, c_i32, c_vp]
+    L.ungar_b200_qp_solve.argtypes = [c_vp, c_vp, c_i64, c_i64, c_vp, c_i64, c_vp, c_i64, c_vp]
     L.ungar_b200_set_profiling.argtypes = [c_i32]
     L.ungar_b200_sweep_times.argtypes = [ctypes.POINTER(ctypes.c_float), c_i32, ctypes.POINTER(c_i32)]
     L.ungar_b200_launch_count.restype = c_i64

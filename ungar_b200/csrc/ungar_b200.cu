@@ -17,6 +17,7 @@
 #include "sweep_structured.cuh"
 #include "sweep_tpn.cuh"
 #include "sweep_small.cuh"
+#include "qp_schur.cuh"
 
 namespace {
 
@@ -85,7 +86,7 @@ struct ungar_b200_model {
     ub::RecLayout rl{};
     ub::BarrierCoef<double> bar{};
     FunctionTables fn[4];
-    DeviceBuffer stage_cost, ws_records, ws_xp, ws_out;
+    DeviceBuffer stage_cost, ws_records, ws_xp, ws_out, ws_qp;
     size_t elem = 8;
 };
 
@@ -756,6 +757,34 @@ int ungar_b200_kkt_blocks(ungar_b200_model* model, const void* xp, int64_t batch
     UB_CUDA(cudaMemcpy2DAsync(records, ld_rec * es, model->ws_records.ptr, L.size * es, L.size * es, batch,
                               cudaMemcpyDeviceToHost, stream));
     UB_CUDA(cudaStreamSynchronize(stream));
+    return UNGAR_B200_OK;
+}
+
+int ungar_b200_qp_solve(ungar_b200_model* model, const void* records_device, int64_t batch, int64_t ld_rec, void* steps,
+                        int64_t ld_steps, void* multipliers, int64_t ld_multipliers, void* stream_) {
+    if (!model) return fail(UNGAR_B200_EINVAL, "null model");
+    if (model->desc.kind != UNGAR_B200_QUADRUPED || model->desc.dtype != UNGAR_B200_F64)
+        return fail(UNGAR_B200_EUNSUPPORTED, "qp_solve is implemented for the quadruped problem in F64");
+    if (batch < 0 || (batch > 0 && (!records_device || !steps))) return fail(UNGAR_B200_EINVAL, "null buffer");
+    const ungar_b200_kkt_layout& L = model->layout;
+    if (ld_rec < L.size || ld_steps < L.n_dec || (multipliers && ld_multipliers < L.m_eq))
+        return fail(UNGAR_B200_EINVAL, "stride smaller than the row it holds");
+    if (batch == 0) return UNGAR_B200_OK;
+    UB_CUDA(cudaSetDevice(model->desc.device));
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    using Q = ub::QpShape;
+    if (int rc = model->ws_qp.reserve(size_t(batch) * (model->N + 1) * Q::WS_GROUP * sizeof(double))) return rc;
+    static bool configured = false;
+    if (!configured) {
+        UB_CUDA(cudaFuncSetAttribute(ub::qp_schur_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, Q::SMEM_BYTES));
+        configured = true;
+    }
+    const unsigned grid = unsigned((batch + Q::WARPS - 1) / Q::WARPS);
+    ub::qp_schur_kernel<<<grid, Q::WARPS * 32, Q::SMEM_BYTES, stream>>>(
+        static_cast<const double*>(records_device), ld_rec, static_cast<double*>(model->ws_qp.ptr), static_cast<double*>(steps),
+        ld_steps, static_cast<double*>(multipliers), ld_multipliers, model->N, batch, model->rl, 1e-9);
+    ++g_launches;
+    UB_CUDA(cudaGetLastError());
     return UNGAR_B200_OK;
 }
 

@@ -133,6 +133,21 @@ class Model:
                                             self._ptr(out2), mem, stream))
         return out2
 
+    def qp_solve(self, records, steps=None, multipliers=None, want_multipliers: bool = True):
+        """Batched solve of the equality-constrained QP of the records (CUDA tensors): ``(steps[B, n_dec], multipliers[B, m_eq])``.
+        Replaces the OSQP call of SoftSQPOptimizer::SolveLocalQPProblem (soft_sqp.hpp:193-233); quadruped fp64 only."""
+        import torch
+
+        B = records.shape[0]
+        if steps is None:
+            steps = torch.empty((B, self.layout["n_dec"]), dtype=records.dtype, device=records.device)
+        if multipliers is None and want_multipliers:
+            multipliers = torch.empty((B, self.layout["m_eq"]), dtype=records.dtype, device=records.device)
+        mp, ml = (multipliers.data_ptr(), multipliers.stride(0)) if multipliers is not None else (None, 0)
+        check(self._lib.ungar_b200_qp_solve(self._handle, records.data_ptr(), B, records.stride(0), steps.data_ptr(),
+                                            steps.stride(0), mp, ml, _torch_stream()))
+        return steps, multipliers
+
     def set_profiling(self, enabled: bool) -> None:
         check(self._lib.ungar_b200_set_profiling(int(enabled)))
 
