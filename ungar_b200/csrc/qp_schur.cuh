@@ -42,6 +42,22 @@ __device__ __forceinline__ void inv_sym3(double a, double b, double c, double d,
     out[6] = out[2];   out[7] = out[5]; out[8] = (a * d - b * b) * id;
 }
 
+// y = P^-1 x cooperatively: lanes 0..12 the diagonal state part, lanes 13..20 one 3x3 input block each.
+__device__ __forceinline__ void apply_pinv_warp(const double* __restrict__ pinv, const double* __restrict__ x, double* __restrict__ y,
+                                                int nz, int lane) {
+    if (lane < 13) y[lane] = pinv[lane] * x[lane];
+    else if (lane < 21) {
+        const int blk = lane - 13;
+        const double* m = pinv + 13 + 9 * blk;
+        const double* xv = x + 13 + 3 * blk;
+        const bool on = nz > 13;
+        y[13 + 3 * blk + 0] = on ? m[0] * xv[0] + m[1] * xv[1] + m[2] * xv[2] : 0.0;
+        y[13 + 3 * blk + 1] = on ? m[3] * xv[0] + m[4] * xv[1] + m[5] * xv[2] : 0.0;
+        y[13 + 3 * blk + 2] = on ? m[6] * xv[0] + m[7] * xv[1] + m[8] * xv[2] : 0.0;
+    }
+    __syncwarp();
+}
+
 // y = P^-1 x for one stage (x, y: 37 entries; pinv: 13 reciprocals + 8 blocks of 9).  Executed by one lane.
 __device__ __forceinline__ void apply_pinv(const double* __restrict__ pinv, const double* __restrict__ x, double* __restrict__ y, int nz) {
 #pragma unroll
@@ -158,8 +174,7 @@ qp_schur_kernel(const double* __restrict__ rec_all, long long ld_rec, double* __
         for (int k = lane; k < 37; k += 32)
             sQ[k] = k < 13 ? rec[L.grad + Q::NX * j + k] : (j < N ? rec[L.grad + nX + Q::NU * j + (k - 13)] : 0.0);
         __syncwarp();
-        if (lane == 0) apply_pinv(sP, sQ, sT, nz);
-        __syncwarp();
+        apply_pinv_warp(sP, sQ, sT, nz, lane);
         // S_jj += U P^-1 U^T + delta I ;   rhs_j = -(b_j + U t_j + carry),  b_j = -g(rows of nu_j)
         times_pinv(sU, sP, sW, lane, nz);
         gemm_wmT(sW, sU, sS, lane, true);
@@ -176,24 +191,31 @@ qp_schur_kernel(const double* __restrict__ rec_all, long long ld_rec, double* __
         __syncwarp();
         // off-diagonal block S_{j,j-1} is in sE (from the previous stage): L_{j,j-1} = S_{j,j-1} L_{j-1,j-1}^-T ;  S_jj -= Lo Lo^T
         if (j > 0) {
-            if (lane < G) {
+            if (lane < G) {  // row `lane` of Lo, kept in registers (fully unrolled: no local memory)
                 double row[G];
+#pragma unroll
                 for (int c = 0; c < G; ++c) {
                     double acc = sE[lane * G + c];
+#pragma unroll
                     for (int k = 0; k < c; ++k) acc -= row[k] * sL[c * G + k];
                     row[c] = acc / sL[c * G + c];
                 }
-                for (int c = 0; c < G; ++c) sE[lane * G + c] = row[c];
+                double dot = 0.0;
+#pragma unroll
+                for (int c = 0; c < G; ++c) {
+                    sE[lane * G + c] = row[c];
+                    dot += row[c] * sY[c];
+                }
+                sR[lane] -= dot;  // rhs_j - Lo y_{j-1}
             }
             __syncwarp();
             if (lane < G) {
                 double lo[G];
+#pragma unroll
                 for (int k = 0; k < G; ++k) lo[k] = sE[lane * G + k];
-                double dot = 0.0;
-                for (int k = 0; k < G; ++k) dot += lo[k] * sY[k];
-                sR[lane] -= dot;  // rhs_j - Lo y_{j-1}
-                for (int c = 0; c < G; ++c) {
+                for (int c = 0; c <= lane; ++c) {  // only the lower triangle of S_jj is used by the Cholesky
                     double acc = 0.0;
+#pragma unroll
                     for (int k = 0; k < G; ++k) acc += lo[k] * sE[c * G + k];
                     sS[lane * G + c] -= acc;
                 }
@@ -214,12 +236,14 @@ qp_schur_kernel(const double* __restrict__ rec_all, long long ld_rec, double* __
             __syncwarp();
         }
         // forward substitution y_j = L_jj^-1 rhs_j (serial over rows, lane 0) — 29 x 29 / 2 operations
-        if (lane == 0) {
+        {  // column-oriented: y_i is final once columns < i have been eliminated; lane k owns entry k
+            double rk = lane < G ? sR[lane] : 0.0;
             for (int i = 0; i < G; ++i) {
-                double acc = sR[i];
-                for (int k = 0; k < i; ++k) acc -= sL[i * G + k] * sY[k];
-                sY[i] = acc / sL[i * G + i];
+                const double yi = __shfl_sync(0xffffffffu, rk, i) / sL[i * G + i];
+                if (lane == i) rk = yi;
+                else if (lane > i && lane < G) rk -= sL[lane * G + i] * yi;
             }
+            if (lane < G) sY[lane] = rk;
         }
         __syncwarp();
         for (int e = lane; e < G * G; e += 32) {
@@ -269,12 +293,15 @@ qp_schur_kernel(const double* __restrict__ rec_all, long long ld_rec, double* __
             sR[lane] -= acc;
         }
         __syncwarp();
-        if (lane == 0) {  // nu_j = L_jj^-T rhs
+        {  // nu_j = L_jj^-T rhs, column-oriented from the last row up; lane k owns entry k
+            double rk = lane < G ? sR[lane] : 0.0;
             for (int i = G - 1; i >= 0; --i) {
-                double acc = sR[i];
-                for (int k = i + 1; k < G; ++k) acc -= sL[k * G + i] * sY[k];
-                sY[i] = acc / sL[i * G + i];
+                const double ni = __shfl_sync(0xffffffffu, rk, i) / sL[i * G + i];
+                if (lane == i) rk = ni;
+                else if (lane < i) rk -= sL[i * G + lane] * ni;
             }
+            __syncwarp();
+            if (lane < G) sY[lane] = rk;
         }
         __syncwarp();
         for (int k = lane; k < 37; k += 32) {
@@ -283,8 +310,7 @@ qp_schur_kernel(const double* __restrict__ rec_all, long long ld_rec, double* __
             sQ[k] = acc;
         }
         __syncwarp();
-        if (lane == 0) apply_pinv(sP, sQ, sT, nz);
-        __syncwarp();
+        apply_pinv_warp(sP, sQ, sT, nz, lane);
         for (int k = lane; k < nz; k += 32) {
             const long long dst = k < 13 ? Q::NX * j + k : nX + Q::NU * j + (k - 13);
             step[dst] = -sT[k];
