@@ -14,27 +14,43 @@
 // and is factorised by a block Cholesky sweep; then nu from two block substitutions and d_j = -P_j^-1 (q_j + U_j^T nu_j +
 // V_j^T nu_{j+1}).  delta = 1e-9 keeps rank-deficient rows (swing legs: all-zero contact rows) harmless, like OSQP's rho/sigma.
 //
-// Lanes own rows: lane i < 29 holds row i of every 29x.. block; operands of the small products are broadcast from shared memory.
+// Mapping.  Lane i < 29 owns ROW i of every 29-row block and keeps it in REGISTERS (S_jj row, S_{j,j-1} row, V P^-1 row); only
+// the operands that every lane needs (rows of L_{j-1,j-1}, of Lo, of A_j, Cs_j, Cp_{j+1}) sit in shared memory and are read as
+// 16-byte broadcasts.  The sparsity of U and of the contact rows is unrolled at compile time: a contact row has ten non-zeros
+// (seven base-state columns + the foot position of its own leg), U's state rows are the identity.
+// Forward sweep per stage:  S_jj row update -> TRSM of the S_{j,j-1} row against L_{j-1,j-1} -> SYRK -> Cholesky fused with the
+// forward substitution (one column per step, pivot by shuffle, column through a 2-slot shared buffer) -> L_jj leaves through
+// the TMA engine (one cp.async.bulk per stage) -> V P^-1 row and its three products for stage j+1.
+// Backward sweep per stage: only L_jj and y_j are read back; Lo_{j+1}^T nu_{j+1} = L_jj^-1 U_j P_j^-1 V_j^T nu_{j+1} is rebuilt
+// from the stage data with sparse mat-vecs and one extra substitution, so Lo never goes to global memory.
+// Shared memory 22.6 KB per warp -> 8 warps per SM, 1184 trajectories per wave (the 1024-trajectory headline is one wave).
 #pragma once
 
 #include "sweep.cuh"
+#include "sweep_structured.cuh"  // bulk_store
 
 namespace ub {
 
 struct QpShape {
-    static constexpr int NX = 13, NU = 24, NZ = 37, TRI = 703, G = 29, LD = 37;  // G rows per group; LD = odd row stride
-    // per-warp shared memory (doubles)
-    static constexpr int oU = 0, oV = oU + G * LD, oW = oV + G * LD, oS = oW + G * LD, oE = oS + G * G, oL = oE + G * G,
-                         oP = oL + G * G, oT = oP + 13 + 8 * 9, total = ((oT + 2 * NZ + 2 * G + 3) & ~3);
+    static constexpr int NX = 13, NU = 24, NZ = 37, TRI = 703, G = 29;
+    static constexpr int LS = 30;  // row stride of the L / Lo images: even (16-byte rows); column 29 of L holds 1 / L_ii
+    static constexpr int LA = 38;  // row stride of the A image (column 37 is a zero pad)
+    // per-warp shared memory (doubles); every offset is even so that double2 accesses are aligned
+    static constexpr int oL = 0, oE = oL + G * LS, oA = oE + G * LS, oCs = oA + NX * LA, oCp = oCs + 160, oP = oCp + 160,
+                         oT = oP + 14 + 8 * 10, oQ = oT + 38, oY = oQ + 38, oC = oY + 32, total = oC + 64;
     static constexpr int WARPS = 4;
     static constexpr int SMEM_BYTES = WARPS * total * 8;
-    // per-trajectory global workspace (doubles): per group  Ld (G*G) | Lo (G*G) | y (G)
-    static constexpr int WS_GROUP = 2 * G * G + G;
+    // per-trajectory global workspace (doubles): per group  L_jj image (G * LS) | y_j (32)
+    static constexpr int WS_GROUP = G * LS + 32;
+    static_assert(total % 2 == 0 && oA % 2 == 0 && oCs % 2 == 0 && oCp % 2 == 0 && oP % 2 == 0 && oT % 2 == 0 && oC % 2 == 0, "alignment");
+    static_assert((WS_GROUP * 8) % 16 == 0, "bulk copies need 16-byte multiples");
 };
 
-// Closed-form inverse of a symmetric 3x3 block (row-major 9 entries out).
+__device__ __forceinline__ double2 qp_ld2(const double* p) { return *reinterpret_cast<const double2*>(p); }
+__device__ __forceinline__ void qp_st2(double* p, double a, double b) { *reinterpret_cast<double2*>(p) = make_double2(a, b); }
+
+// Closed-form inverse of a symmetric 3x3 block [a b c; b d e; c e f] (row-major 9 entries out).
 __device__ __forceinline__ void inv_sym3(double a, double b, double c, double d, double e, double f, double* out) {
-    // [a b c; b d e; c e f]
     const double c00 = d * f - e * e, c01 = c * e - b * f, c02 = b * e - c * d;
     const double det = a * c00 + b * c01 + c * c02, id = 1.0 / det;
     out[0] = c00 * id; out[1] = c01 * id; out[2] = c02 * id;
@@ -42,283 +58,378 @@ __device__ __forceinline__ void inv_sym3(double a, double b, double c, double d,
     out[6] = out[2];   out[7] = out[5]; out[8] = (a * d - b * b) * id;
 }
 
+// P^-1 image: 13 reciprocals at [0, 13), block `blk` (row-major 3x3) at 14 + 10 * blk.
 // y = P^-1 x cooperatively: lanes 0..12 the diagonal state part, lanes 13..20 one 3x3 input block each.
-__device__ __forceinline__ void apply_pinv_warp(const double* __restrict__ pinv, const double* __restrict__ x, double* __restrict__ y,
-                                                int nz, int lane) {
+__device__ __forceinline__ void apply_pinv_warp(const double* __restrict__ pinv, const double* __restrict__ x, double* __restrict__ y, int lane) {
     if (lane < 13) y[lane] = pinv[lane] * x[lane];
     else if (lane < 21) {
         const int blk = lane - 13;
-        const double* m = pinv + 13 + 9 * blk;
+        const double* m = pinv + 14 + 10 * blk;
         const double* xv = x + 13 + 3 * blk;
-        const bool on = nz > 13;
-        y[13 + 3 * blk + 0] = on ? m[0] * xv[0] + m[1] * xv[1] + m[2] * xv[2] : 0.0;
-        y[13 + 3 * blk + 1] = on ? m[3] * xv[0] + m[4] * xv[1] + m[5] * xv[2] : 0.0;
-        y[13 + 3 * blk + 2] = on ? m[6] * xv[0] + m[7] * xv[1] + m[8] * xv[2] : 0.0;
+        y[13 + 3 * blk + 0] = m[0] * xv[0] + m[1] * xv[1] + m[2] * xv[2];
+        y[13 + 3 * blk + 1] = m[3] * xv[0] + m[4] * xv[1] + m[5] * xv[2];
+        y[13 + 3 * blk + 2] = m[6] * xv[0] + m[7] * xv[1] + m[8] * xv[2];
     }
     __syncwarp();
 }
 
-// y = P^-1 x for one stage (x, y: 37 entries; pinv: 13 reciprocals + 8 blocks of 9).  Executed by one lane.
-__device__ __forceinline__ void apply_pinv(const double* __restrict__ pinv, const double* __restrict__ x, double* __restrict__ y, int nz) {
-#pragma unroll
-    for (int i = 0; i < 13; ++i) y[i] = pinv[i] * x[i];
-    if (nz > 13) {
-#pragma unroll
-        for (int blk = 0; blk < 8; ++blk) {
-            const double* m = pinv + 13 + 9 * blk;
-            const double* xv = x + 13 + 3 * blk;
-            y[13 + 3 * blk + 0] = m[0] * xv[0] + m[1] * xv[1] + m[2] * xv[2];
-            y[13 + 3 * blk + 1] = m[3] * xv[0] + m[4] * xv[1] + m[5] * xv[2];
-            y[13 + 3 * blk + 2] = m[6] * xv[0] + m[7] * xv[1] + m[8] * xv[2];
-        }
-    } else {
-#pragma unroll
-        for (int i = 13; i < 37; ++i) y[i] = 0.0;
-    }
-}
-
-// Loads stage j of a trajectory into shared memory: U_j (29 x 37), V_j (29 x 37, rows of nu_{j+1} on w_j), P_j^-1.
-// All 32 lanes participate.  For j = N only the state part exists (U = [I_x], V = 0).
-__device__ __forceinline__ void load_stage(const double* __restrict__ rec, const RecLayout& L, int N, int j, double* __restrict__ sU,
-                                           double* __restrict__ sV, double* __restrict__ sP, int lane) {
+// Stage j of a trajectory into shared memory: A_j (13 x 37), Cs_j / Cp_{j+1} (16 x 10 each: the non-zero columns of the contact rows
+// of stage j and of stage j+1 on w_j), P_j^-1, q_j.  Everything is zero-filled where the horizon ends (j = N: only the state part).
+__device__ __forceinline__ void qp_load_stage(const double* __restrict__ rec, const RecLayout& L, int N, int j, double* __restrict__ sm, int lane) {
     using Q = QpShape;
-    for (int e = lane; e < Q::G * Q::LD; e += 32) { sU[e] = 0.0; sV[e] = 0.0; }
-    __syncwarp();
-    if (lane < 13) sU[lane * Q::LD + lane] = 1.0;  // I_x rows (dynamics defect of stage j-1, or x_0 - x_measured)
-    if (j < N) {
-        // contact rows of stage j on w_j (Cs_j) and contact rows of stage j+1 on w_j (Cp_{j+1})
-        for (int e = lane; e < 16 * 10; e += 32) {
-            const int row = e / 10, col = e % 10, leg = row >> 2;
-            const int dst = col < 7 ? col : 13 + 6 * leg + 3 + (col - 7);
-            sU[(13 + row) * Q::LD + dst] = rec[L.C + (long long)j * 320 + row * 20 + col];
-            if (j + 1 < N) sV[(13 + row) * Q::LD + dst] = rec[L.C + (long long)(j + 1) * 320 + row * 20 + 10 + col];
+    double *sA = sm + Q::oA, *sCs = sm + Q::oCs, *sCp = sm + Q::oCp, *sP = sm + Q::oP, *sQ = sm + Q::oQ;
+    const bool live = j < N, next = j + 1 < N;
+    const int nX = Q::NX * (N + 1);
+    const double* cj = rec + L.C + (long long)j * 320;
+#pragma unroll
+    for (int it = 0; it < 5; ++it) {
+        const int e = lane + 32 * it, row = e / 10, col = e - 10 * row;
+        sCs[e] = live ? cj[row * 20 + col] : 0.0;
+        sCp[e] = next ? cj[320 + row * 20 + 10 + col] : 0.0;
+    }
+    const double* aj = rec + L.A + (long long)j * 481;
+#pragma unroll
+    for (int it = 0; it < 16; ++it) {
+        const int e = lane + 32 * it;
+        if (e < 481) {
+            const int row = e / 37, col = e - 37 * row;
+            sA[row * Q::LA + col] = live ? aj[e] : 0.0;
         }
-        for (int e = lane; e < 13 * 37; e += 32) sV[(e / 37) * Q::LD + e % 37] = rec[L.A + (long long)j * 481 + e];
-        // P_j^-1 from the packed upper triangle of H_j
+    }
+    for (int k = lane; k < 37; k += 32) sQ[k] = k < 13 ? rec[L.grad + Q::NX * j + k] : (live ? rec[L.grad + nX + Q::NU * j + (k - 13)] : 0.0);
+    if (live) {  // P_j^-1 from the packed upper triangle of H_j
         const double* H = rec + L.H + (long long)j * Q::TRI;
         if (lane < 13) sP[lane] = 1.0 / H[lane * 37 - (lane * (lane - 1)) / 2];
         else if (lane < 21) {
             const int a = 13 + 3 * (lane - 13);
             const int d0 = a * 37 - (a * (a - 1)) / 2, d1 = (a + 1) * 37 - ((a + 1) * a) / 2, d2 = (a + 2) * 37 - ((a + 2) * (a + 1)) / 2;
-            inv_sym3(H[d0], H[d0 + 1], H[d0 + 2], H[d1], H[d1 + 1], H[d2], sP + 13 + 9 * (lane - 13));
+            inv_sym3(H[d0], H[d0 + 1], H[d0 + 2], H[d1], H[d1 + 1], H[d2], sP + 14 + 10 * (lane - 13));
         }
     } else {
         const double* H = rec + L.HN;
         if (lane < 13) sP[lane] = 1.0 / H[lane * 13 - (lane * (lane - 1)) / 2];
+        else if (lane < 21)
+            for (int e = 0; e < 9; ++e) sP[14 + 10 * (lane - 13) + e] = 0.0;
     }
     __syncwarp();
 }
 
-// W = M P^-1 row by row (lane i < 29 owns row i).
-__device__ __forceinline__ void times_pinv(const double* __restrict__ sM, const double* __restrict__ sP, double* __restrict__ sW,
-                                           int lane, int nz) {
-    using Q = QpShape;
-    if (lane < Q::G) {
-        double x[37], y[37];
+// sum_r Cx[r][column k of w] * nu[13 + r] over the sixteen contact rows: entry k of Cx^T nu (Cx = Cs or Cp image).
+__device__ __forceinline__ double qp_contact_T(const double* __restrict__ sCx, const double* __restrict__ nu, int k) {
+    double acc = 0.0;
+    if (k < 7) {
 #pragma unroll
-        for (int k = 0; k < 37; ++k) x[k] = sM[lane * Q::LD + k];
-        apply_pinv(sP, x, y, nz);
+        for (int r = 0; r < 16; ++r) acc += sCx[r * 10 + k] * nu[13 + r];
+    } else if (k >= 13) {
+        const int q = k - 13, leg = q / 6, m = q - 6 * leg - 3;
+        if (m >= 0) {
 #pragma unroll
-        for (int k = 0; k < 37; ++k) sW[lane * Q::LD + k] = y[k];
-    }
-    __syncwarp();
-}
-
-// out[i][c] (+)= sum_k W[i][k] M[c][k]   (29 x 29; lane i owns row i; M rows broadcast from shared memory)
-__device__ __forceinline__ void gemm_wmT(const double* __restrict__ sW, const double* __restrict__ sM, double* __restrict__ out,
-                                         int lane, bool accumulate) {
-    using Q = QpShape;
-    if (lane < Q::G) {
-        double w[37];
-#pragma unroll
-        for (int k = 0; k < 37; ++k) w[k] = sW[lane * Q::LD + k];
-        for (int c = 0; c < Q::G; ++c) {
-            double acc = accumulate ? out[lane * Q::G + c] : 0.0;
-#pragma unroll
-            for (int k = 0; k < 37; ++k) acc += w[k] * sM[c * Q::LD + k];
-            out[lane * Q::G + c] = acc;
+            for (int i = 0; i < 4; ++i) acc += sCx[(4 * leg + i) * 10 + 7 + m] * nu[13 + 4 * leg + i];
         }
     }
-    __syncwarp();
+    return acc;
 }
 
 // Forward sweep (factorisation + forward substitution), then backward sweep (multipliers and step).
-__global__ void __launch_bounds__(QpShape::WARPS * 32)
+__global__ void __launch_bounds__(QpShape::WARPS * 32, 2)
 qp_schur_kernel(const double* __restrict__ rec_all, long long ld_rec, double* __restrict__ ws_all, double* __restrict__ step_all,
                 long long ld_step, double* __restrict__ mult_all, long long ld_mult, int N, long long batch, RecLayout L, double delta) {
     using Q = QpShape;
-    constexpr int G = Q::G, LD = Q::LD;
+    constexpr int G = Q::G, LS = Q::LS, LA = Q::LA;
+    constexpr unsigned FULL = 0xffffffffu;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     double* const sm = reinterpret_cast<double*>(smem_raw) + wib * Q::total;
-    double *sU = sm + Q::oU, *sV = sm + Q::oV, *sW = sm + Q::oW, *sS = sm + Q::oS, *sE = sm + Q::oE, *sL = sm + Q::oL,
-           *sP = sm + Q::oP, *sT = sm + Q::oT;  // sT: t_j = P^-1 q_j (37) | q_j (37) | y_prev (29) | scratch (29)
-    double* const sQ = sT + 37;
-    double* const sY = sQ + 37;
-    double* const sR = sY + G;
+    double *sL = sm + Q::oL, *sE = sm + Q::oE, *sA = sm + Q::oA, *sCs = sm + Q::oCs, *sCp = sm + Q::oCp, *sP = sm + Q::oP,
+           *sT = sm + Q::oT, *sQ = sm + Q::oQ, *sY = sm + Q::oY, *sC = sm + Q::oC;
     const long long b = (long long)blockIdx.x * Q::WARPS + wib;
     if (b >= batch) return;
     const double* __restrict__ rec = rec_all + b * ld_rec;
     double* __restrict__ ws = ws_all + b * (long long)(N + 1) * Q::WS_GROUP;
     const int nX = Q::NX * (N + 1);
 
-    // ================================================================ forward sweep over the groups nu_0 .. nu_N
-    // carry = V_{j-1} P_{j-1}^-1 V_{j-1}^T (into S_jj) and V_{j-1} t_{j-1} (into the right-hand side): computed at the end of stage j-1
-    for (int e = lane; e < G * G; e += 32) sS[e] = 0.0;
-    if (lane < G) sR[lane] = 0.0;
+    // lane roles: state rows (identity in U, A rows in V) or contact rows (Cs rows in U, Cp rows in V); lanes 29..31 shadow row 28
+    const bool act = lane < G, st = lane < 13;
+    const int r = st ? 0 : min(lane - 13, 15), leg = r >> 2;
+    const int my_row = min(lane, G - 1);
+
+    if (lane < 13) sA[lane * LA + 37] = 0.0;  // pad column of the A image, read by the 16-byte row loads
+    if (lane < 8) sP[14 + 10 * lane + 9] = 0.0;
+    if (lane == 0) sP[13] = 0.0;
+    sY[lane] = 0.0;
+    if (lane == 0) sT[37] = 0.0;
     __syncwarp();
+
+    // ================================================================ forward sweep over the groups nu_0 .. nu_N
+    double s[G], e[G];  // row `lane` of S_jj (lower triangle meaningful) and of S_{j,j-1} / Lo_j
+#pragma unroll
+    for (int c = 0; c < G; ++c) { s[c] = 0.0; e[c] = 0.0; }
+    double carry = 0.0;  // (V_{j-1} t_{j-1})[lane]
     for (int j = 0; j <= N; ++j) {
-        const int nz = j < N ? 37 : 13;
-        load_stage(rec, L, N, j, sU, sV, sP, lane);
-        // q_j and t_j = P_j^-1 q_j
-        for (int k = lane; k < 37; k += 32)
-            sQ[k] = k < 13 ? rec[L.grad + Q::NX * j + k] : (j < N ? rec[L.grad + nX + Q::NU * j + (k - 13)] : 0.0);
-        __syncwarp();
-        apply_pinv_warp(sP, sQ, sT, nz, lane);
-        // S_jj += U P^-1 U^T + delta I ;   rhs_j = -(b_j + U t_j + carry),  b_j = -g(rows of nu_j)
-        times_pinv(sU, sP, sW, lane, nz);
-        gemm_wmT(sW, sU, sS, lane, true);
-        if (lane < G) {
-            sS[lane * G + lane] += delta;
-            double ut = 0.0;
+        const bool live = j < N;
+        double gval = 0.0;
+        if (st) gval = rec[L.g + Q::NX * j + lane];
+        else if (live && act) gval = rec[L.g + nX + 16 * j + r];
+        qp_load_stage(rec, L, N, j, sm, lane);
+        apply_pinv_warp(sP, sQ, sT, lane);  // t_j = P_j^-1 q_j
+
+        // ---- own U row (contact lanes: the ten non-zeros) and its product with P^-1 -------------------------------------------
+        double cs[10], wu[10];
 #pragma unroll
-            for (int k = 0; k < 37; ++k) ut += sU[lane * LD + k] * sT[k];
-            double gval = 0.0;
-            if (lane < 13) gval = rec[L.g + Q::NX * j + lane];
-            else if (j < N) gval = rec[L.g + nX + 16 * j + (lane - 13)];
-            sR[lane] = gval - ut - sR[lane];  // -(b + U t + carry) with b = -g
+        for (int k = 0; k < 10; k += 2) { const double2 t2 = qp_ld2(sCs + r * 10 + k); cs[k] = t2.x; cs[k + 1] = t2.y; }
+#pragma unroll
+        for (int k = 0; k < 7; ++k) wu[k] = cs[k] * sP[k];
+        {
+            const double* Bm = sP + 14 + 10 * (2 * leg + 1);
+#pragma unroll
+            for (int m = 0; m < 3; ++m) wu[7 + m] = cs[7] * Bm[m] + cs[8] * Bm[3 + m] + cs[9] * Bm[6 + m];
         }
-        __syncwarp();
-        // off-diagonal block S_{j,j-1} is in sE (from the previous stage): L_{j,j-1} = S_{j,j-1} L_{j-1,j-1}^-T ;  S_jj -= Lo Lo^T
+        // ---- S_jj += U P^-1 U^T + delta I (lower triangle) ;  rhs_j = g_j - U t_j - carry --------------------------------------
+        const double dself = sP[min(lane, 12)];
+#pragma unroll
+        for (int c = 0; c < 13; ++c) s[c] += st ? (c == lane ? dself + delta : 0.0) : (c < 7 ? wu[c] : 0.0);
+#pragma unroll
+        for (int c = 13; c < G; ++c) {
+            const int rc = c - 13, legc = rc >> 2;
+            const double* row = sCs + rc * 10;
+            double a0 = 0.0, a1 = 0.0;
+#pragma unroll
+            for (int k = 0; k < 6; k += 2) { const double2 t2 = qp_ld2(row + k); a0 += wu[k] * t2.x; a1 += wu[k + 1] * t2.y; }
+            const double2 t6 = qp_ld2(row + 6), t8 = qp_ld2(row + 8);
+            a0 += wu[6] * t6.x;
+            const double own = wu[7] * t6.y + wu[8] * t8.x + wu[9] * t8.y;
+            s[c] += st ? 0.0 : a0 + a1 + (leg == legc ? own : 0.0) + (c == lane ? delta : 0.0);
+        }
+        double rhs;
+        {
+            double ut;
+            if (st) ut = sT[lane];
+            else {
+                ut = 0.0;
+#pragma unroll
+                for (int k = 0; k < 7; ++k) ut += cs[k] * sT[k];
+#pragma unroll
+                for (int m = 0; m < 3; ++m) ut += cs[7 + m] * sT[13 + 6 * leg + 3 + m];
+            }
+            rhs = gval - ut - carry;
+        }
         if (j > 0) {
-            if (lane < G) {  // row `lane` of Lo, kept in registers (fully unrolled: no local memory)
-                double row[G];
+            // ---- Lo_j row = S_{j,j-1} row * L_{j-1,j-1}^-T  (left-looking, L rows broadcast) -----------------------------------
 #pragma unroll
-                for (int c = 0; c < G; ++c) {
-                    double acc = sE[lane * G + c];
+            for (int c = 0; c < G; ++c) {
+                const double* Lr = sL + c * LS;
+                double a0 = e[c], a1 = 0.0;
 #pragma unroll
-                    for (int k = 0; k < c; ++k) acc -= row[k] * sL[c * G + k];
-                    row[c] = acc / sL[c * G + c];
-                }
-                double dot = 0.0;
+                for (int k = 0; k + 1 < c; k += 2) { const double2 t2 = qp_ld2(Lr + k); a0 -= e[k] * t2.x; a1 -= e[k + 1] * t2.y; }
+                if (c & 1) a0 -= e[c - 1] * Lr[c - 1];
+                e[c] = (a0 + a1) * Lr[G];
+            }
+            {
+                double d0 = 0.0, d1 = 0.0;  // rhs_j -= Lo_j y_{j-1}
 #pragma unroll
-                for (int c = 0; c < G; ++c) {
-                    sE[lane * G + c] = row[c];
-                    dot += row[c] * sY[c];
-                }
-                sR[lane] -= dot;  // rhs_j - Lo y_{j-1}
+                for (int c = 0; c + 1 < G; c += 2) { const double2 t2 = qp_ld2(sY + c); d0 += e[c] * t2.x; d1 += e[c + 1] * t2.y; }
+                d0 += e[G - 1] * sY[G - 1];
+                rhs -= d0 + d1;
+            }
+            if (act) {
+#pragma unroll
+                for (int c = 0; c + 1 < G; c += 2) qp_st2(sE + lane * LS + c, e[c], e[c + 1]);
+                qp_st2(sE + lane * LS + G - 1, e[G - 1], 0.0);
             }
             __syncwarp();
-            if (lane < G) {
-                double lo[G];
+            // ---- S_jj -= Lo_j Lo_j^T ----------------------------------------------------------------------------------------------
 #pragma unroll
-                for (int k = 0; k < G; ++k) lo[k] = sE[lane * G + k];
-                for (int c = 0; c <= lane; ++c) {  // only the lower triangle of S_jj is used by the Cholesky
-                    double acc = 0.0;
+            for (int c = 0; c < G; ++c) {
+                const double* row = sE + c * LS;
+                double a0 = 0.0, a1 = 0.0;
 #pragma unroll
-                    for (int k = 0; k < G; ++k) acc += lo[k] * sE[c * G + k];
-                    sS[lane * G + c] -= acc;
-                }
+                for (int k = 0; k + 1 < G; k += 2) { const double2 t2 = qp_ld2(row + k); a0 += e[k] * t2.x; a1 += e[k + 1] * t2.y; }
+                a0 += e[G - 1] * row[G - 1];
+                s[c] -= a0 + a1;
             }
-            __syncwarp();
-            for (int e = lane; e < G * G; e += 32) ws[(long long)j * Q::WS_GROUP + G * G + e] = sE[e];  // Lo_j
         }
-        // Cholesky of S_jj (right-looking; lane i owns row i), result in sL (lower)
+        // ---- Cholesky of S_jj fused with y_j = L_jj^-1 rhs_j: one column per step ---------------------------------------------------
+        double rk = rhs, inv_own = 0.0;
+#pragma unroll
         for (int c = 0; c < G; ++c) {
-            const double piv = sqrt(sS[c * G + c]);
+            const double rinv = rsqrt(__shfl_sync(FULL, s[c], c));
+            const double l = lane >= c ? s[c] * rinv : 0.0;
+            s[c] = l;
+            if (lane == c) inv_own = rinv;
+            double* col = sC + (c & 1) * 32;
+            col[lane] = l;
+            const double yc = __shfl_sync(FULL, rk, c) * rinv;
+            if (lane == c) rk = yc;
+            else if (lane > c) rk -= l * yc;
             __syncwarp();
-            if (lane < G && lane >= c) sL[lane * G + c] = lane == c ? piv : sS[lane * G + c] / piv;
-            __syncwarp();
-            if (lane < G && lane > c) {
-                const double lic = sL[lane * G + c];
-                for (int cc = c + 1; cc <= lane; ++cc) sS[lane * G + cc] -= lic * sL[cc * G + c];
-            }
-            __syncwarp();
-        }
-        // forward substitution y_j = L_jj^-1 rhs_j (serial over rows, lane 0) — 29 x 29 / 2 operations
-        {  // column-oriented: y_i is final once columns < i have been eliminated; lane k owns entry k
-            double rk = lane < G ? sR[lane] : 0.0;
-            for (int i = 0; i < G; ++i) {
-                const double yi = __shfl_sync(0xffffffffu, rk, i) / sL[i * G + i];
-                if (lane == i) rk = yi;
-                else if (lane > i && lane < G) rk -= sL[lane * G + i] * yi;
-            }
-            if (lane < G) sY[lane] = rk;
-        }
-        __syncwarp();
-        for (int e = lane; e < G * G; e += 32) {
-            const int i = e / G, c = e % G;
-            ws[(long long)j * Q::WS_GROUP + e] = c <= i ? sL[e] : 0.0;  // Ld_j
-        }
-        if (lane < G) ws[(long long)j * Q::WS_GROUP + 2 * G * G + lane] = sY[lane];
-        // prepare stage j+1: S_{j+1,j} = V P^-1 U^T -> sE ;  carry V P^-1 V^T -> sS ;  V t_j -> sR
-        if (j < N) {
-            times_pinv(sV, sP, sW, lane, nz);
-            gemm_wmT(sW, sU, sE, lane, false);
-            gemm_wmT(sW, sV, sS, lane, false);
-            if (lane < G) {
-                double vt = 0.0;
+            if (c + 1 < G) {
+                if ((c + 1) & 1) s[c + 1] -= l * col[c + 1];
 #pragma unroll
-                for (int k = 0; k < 37; ++k) vt += sV[lane * LD + k] * sT[k];
-                sR[lane] = vt;
+                for (int cc = (c + 2) & ~1; cc + 1 < G + 1; cc += 2) {
+                    const double2 t2 = qp_ld2(col + cc);
+                    s[cc] -= l * t2.x;
+                    if (cc + 1 < G) s[cc + 1] -= l * t2.y;
+                }
             }
-            __syncwarp();
+        }
+        // ---- L_jj (rows from registers) and y_j leave: the L image through the TMA engine -------------------------------------------
+        if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+        __syncwarp();
+        if (act) {
+#pragma unroll
+            for (int c = 0; c + 1 < G; c += 2) qp_st2(sL + lane * LS + c, s[c], s[c + 1]);
+            qp_st2(sL + lane * LS + G - 1, s[G - 1], inv_own);
+            sY[lane] = rk;
+            ws[(long long)j * Q::WS_GROUP + G * LS + lane] = rk;
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        __syncwarp();
+        if (lane == 0) {
+            bulk_store(ws + (long long)j * Q::WS_GROUP, sL, G * LS * 8);
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        }
+        // ---- stage j+1: S_{j+1,j} row = (V P^-1 U^T) row ;  carry rows (V P^-1 V^T) and V t_j -------------------------------------
+        if (live) {
+            double w[37];
+            {
+                double v[37];
+                if (st) {
+#pragma unroll
+                    for (int k = 0; k < 36; k += 2) { const double2 t2 = qp_ld2(sA + lane * LA + k); v[k] = t2.x; v[k + 1] = t2.y; }
+                    v[36] = sA[lane * LA + 36];
+                } else {
+                    double cp[10];
+#pragma unroll
+                    for (int k = 0; k < 10; k += 2) { const double2 t2 = qp_ld2(sCp + r * 10 + k); cp[k] = t2.x; cp[k + 1] = t2.y; }
+#pragma unroll
+                    for (int k = 0; k < 13; ++k) v[k] = k < 7 ? cp[k] : 0.0;
+#pragma unroll
+                    for (int lg = 0; lg < 4; ++lg)
+#pragma unroll
+                        for (int m = 0; m < 3; ++m) { v[13 + 6 * lg + m] = 0.0; v[13 + 6 * lg + 3 + m] = leg == lg ? cp[7 + m] : 0.0; }
+                }
+                double c0 = 0.0, c1 = 0.0;
+#pragma unroll
+                for (int k = 0; k < 36; k += 2) { const double2 t2 = qp_ld2(sT + k); c0 += v[k] * t2.x; c1 += v[k + 1] * t2.y; }
+                carry = c0 + c1 + v[36] * sT[36];
+#pragma unroll
+                for (int k = 0; k < 13; ++k) w[k] = v[k] * sP[k];
+#pragma unroll
+                for (int blk = 0; blk < 8; ++blk) {
+                    const double* Bm = sP + 14 + 10 * blk;
+                    const double2 b0 = qp_ld2(Bm), b2 = qp_ld2(Bm + 2), b4 = qp_ld2(Bm + 4), b6 = qp_ld2(Bm + 6);
+                    const double b8 = Bm[8];
+                    const double x0 = v[13 + 3 * blk], x1 = v[14 + 3 * blk], x2 = v[15 + 3 * blk];
+                    w[13 + 3 * blk + 0] = x0 * b0.x + x1 * b2.y + x2 * b6.x;
+                    w[13 + 3 * blk + 1] = x0 * b0.y + x1 * b4.x + x2 * b6.y;
+                    w[13 + 3 * blk + 2] = x0 * b2.x + x1 * b4.y + x2 * b8;
+                }
+            }
+#pragma unroll
+            for (int c = 0; c < 13; ++c) {
+                e[c] = w[c];
+                const double* row = sA + c * LA;
+                double a0 = 0.0, a1 = 0.0;
+#pragma unroll
+                for (int k = 0; k < 36; k += 2) { const double2 t2 = qp_ld2(row + k); a0 += w[k] * t2.x; a1 += w[k + 1] * t2.y; }
+                s[c] = a0 + a1 + w[36] * row[36];
+            }
+#pragma unroll
+            for (int c = 13; c < G; ++c) {
+                const int rc = c - 13, legc = rc >> 2, o = 13 + 6 * legc + 3;
+                {
+                    const double* row = sCs + rc * 10;
+                    const double2 t0 = qp_ld2(row), t2 = qp_ld2(row + 2), t4 = qp_ld2(row + 4), t6 = qp_ld2(row + 6), t8 = qp_ld2(row + 8);
+                    e[c] = (w[0] * t0.x + w[1] * t0.y + w[2] * t2.x + w[3] * t2.y) + (w[4] * t4.x + w[5] * t4.y + w[6] * t6.x) +
+                           (w[o] * t6.y + w[o + 1] * t8.x + w[o + 2] * t8.y);
+                }
+                {
+                    const double* row = sCp + rc * 10;
+                    const double2 t0 = qp_ld2(row), t2 = qp_ld2(row + 2), t4 = qp_ld2(row + 4), t6 = qp_ld2(row + 6), t8 = qp_ld2(row + 8);
+                    s[c] = (w[0] * t0.x + w[1] * t0.y + w[2] * t2.x + w[3] * t2.y) + (w[4] * t4.x + w[5] * t4.y + w[6] * t6.x) +
+                           (w[o] * t6.y + w[o + 1] * t8.x + w[o + 2] * t8.y);
+                }
+            }
         }
     }
+    if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+    __syncwarp();
 
     // ================================================================ backward sweep: nu_j, then d_j
-    // sY holds nu_{j+1} (zero beyond the horizon); sW row 0 is reused for the stage vector v = q + U^T nu_j + V^T nu_{j+1}
-    if (lane < G) sY[lane] = 0.0;
+    // sY holds nu_{j+1} (zero beyond the horizon)
+    sY[lane] = 0.0;
     __syncwarp();
     double* __restrict__ step = step_all + b * ld_step;
     for (int j = N; j >= 0; --j) {
         const int nz = j < N ? 37 : 13;
-        load_stage(rec, L, N, j, sU, sV, sP, lane);
-        for (int e = lane; e < G * G; e += 32) sL[e] = ws[(long long)j * Q::WS_GROUP + e];
-        if (j < N)
-            for (int e = lane; e < G * G; e += 32) sE[e] = ws[(long long)(j + 1) * Q::WS_GROUP + G * G + e];  // Lo_{j+1}
-        if (lane < G) sR[lane] = ws[(long long)j * Q::WS_GROUP + 2 * G * G + lane];                          // y_j
-        __syncwarp();
-        // V^T nu_{j+1} needs nu_{j+1} (still in sY) BEFORE it is overwritten: accumulate the stage vector first
-        for (int k = lane; k < 37; k += 32) {
-            double acc = k < 13 ? rec[L.grad + Q::NX * j + k] : (j < N ? rec[L.grad + nX + Q::NU * j + (k - 13)] : 0.0);
-            if (j < N)
-                for (int i = 0; i < G; ++i) acc += sV[i * LD + k] * sY[i];
-            sQ[k] = acc;
-        }
-        // rhs = y_j - Lo_{j+1}^T nu_{j+1}
-        if (lane < G && j < N) {
-            double acc = 0.0;
-            for (int i = 0; i < G; ++i) acc += sE[i * G + lane] * sY[i];
-            sR[lane] -= acc;
-        }
-        __syncwarp();
-        {  // nu_j = L_jj^-T rhs, column-oriented from the last row up; lane k owns entry k
-            double rk = lane < G ? sR[lane] : 0.0;
-            for (int i = G - 1; i >= 0; --i) {
-                const double ni = __shfl_sync(0xffffffffu, rk, i) / sL[i * G + i];
-                if (lane == i) rk = ni;
-                else if (lane < i) rk -= sL[i * G + lane] * ni;
+        const double* wj = ws + (long long)j * Q::WS_GROUP;
+        const double yj = act ? wj[G * LS + lane] : 0.0;
+        {
+            const double2* src = reinterpret_cast<const double2*>(wj);
+            double2* dst = reinterpret_cast<double2*>(sL);
+#pragma unroll
+            for (int it = 0; it < 14; ++it) {
+                const int q = lane + 32 * it;
+                if (q < G * LS / 2) dst[q] = src[q];
             }
-            __syncwarp();
-            if (lane < G) sY[lane] = rk;
         }
-        __syncwarp();
+        qp_load_stage(rec, L, N, j, sm, lane);
+        // a = V_j^T nu_{j+1}  (entries k = lane, lane + 32) -> sC ;  P^-1 a -> sT
         for (int k = lane; k < 37; k += 32) {
-            double acc = sQ[k];
-            for (int i = 0; i < G; ++i) acc += sU[i * LD + k] * sY[i];
-            sQ[k] = acc;
+            double acc = 0.0;
+#pragma unroll
+            for (int i = 0; i < 13; ++i) acc += sA[i * LA + k] * sY[i];
+            sC[k] = acc + qp_contact_T(sCp, sY, k);
         }
         __syncwarp();
-        apply_pinv_warp(sP, sQ, sT, nz, lane);
+        apply_pinv_warp(sP, sC, sT, lane);
+        // z = U_j P^-1 a (row per lane), then z' = L_jj^-1 z
+        double cs[10];
+#pragma unroll
+        for (int k = 0; k < 10; k += 2) { const double2 t2 = qp_ld2(sCs + r * 10 + k); cs[k] = t2.x; cs[k + 1] = t2.y; }
+        double rk;
+        if (st) rk = sT[lane];
+        else {
+            rk = 0.0;
+#pragma unroll
+            for (int k = 0; k < 7; ++k) rk += cs[k] * sT[k];
+#pragma unroll
+            for (int m = 0; m < 3; ++m) rk += cs[7 + m] * sT[13 + 6 * leg + 3 + m];
+        }
+        {
+            double lrow[G];
+#pragma unroll
+            for (int c = 0; c + 1 < G; c += 2) { const double2 t2 = qp_ld2(sL + my_row * LS + c); lrow[c] = t2.x; lrow[c + 1] = t2.y; }
+            lrow[G - 1] = sL[my_row * LS + G - 1];
+#pragma unroll
+            for (int i = 0; i < G; ++i) {
+                const double zi = __shfl_sync(FULL, rk, i) * sL[i * LS + G];
+                if (lane == i) rk = zi;
+                else if (lane > i) rk -= lrow[i] * zi;
+            }
+        }
+        rk = yj - rk;  // y_j - Lo_{j+1}^T nu_{j+1}
+#pragma unroll
+        for (int i = G - 1; i >= 0; --i) {  // nu_j = L_jj^-T rhs, column-oriented from the last row up; lane k owns entry k
+            const double ni = __shfl_sync(FULL, rk, i) * sL[i * LS + G];
+            if (lane == i) rk = ni;
+            else if (lane < i) rk -= sL[i * LS + lane] * ni;
+        }
+        __syncwarp();
+        if (act) sY[lane] = rk;
+        __syncwarp();
+        // d_j = -P^-1 (q_j + a + U_j^T nu_j)
+        for (int k = lane; k < 37; k += 32) sQ[k] += sC[k] + (k < 13 ? sY[k] : 0.0) + qp_contact_T(sCs, sY, k);
+        __syncwarp();
+        apply_pinv_warp(sP, sQ, sT, lane);
         for (int k = lane; k < nz; k += 32) {
             const long long dst = k < 13 ? Q::NX * j + k : nX + Q::NU * j + (k - 13);
             step[dst] = -sT[k];
         }
-        if (mult_all && lane < G) {  // multipliers in the reference's row order [x0 | defects | contact rows]
+        if (mult_all && act) {  // multipliers in the reference's row order [x0 | defects | contact rows]
             double* mult = mult_all + b * ld_mult;
-            if (lane < 13) mult[Q::NX * j + lane] = sY[lane];
-            else if (j < N) mult[nX + 16 * j + (lane - 13)] = sY[lane];
+            if (lane < 13) mult[Q::NX * j + lane] = rk;
+            else if (j < N) mult[nX + 16 * j + (lane - 13)] = rk;
         }
         __syncwarp();
     }
