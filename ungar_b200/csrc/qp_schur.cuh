@@ -23,7 +23,11 @@
 // the TMA engine (one cp.async.bulk per stage) -> V P^-1 row and its three products for stage j+1.
 // Backward sweep per stage: only L_jj and y_j are read back; Lo_{j+1}^T nu_{j+1} = L_jj^-1 U_j P_j^-1 V_j^T nu_{j+1} is rebuilt
 // from the stage data with sparse mat-vecs and one extra substitution, so Lo never goes to global memory.
-// Shared memory 22.6 KB per warp -> 8 warps per SM, 1184 trajectories per wave (the 1024-trajectory headline is one wave).
+// Global latency: the stage data of stage j+1 (A, Cs, Cp, q, g, the 61 entries of H that P^-1 needs) is fetched with cp.async
+// while stage j computes; the landing zone is whichever of two 870-double regions does not hold stage j's data, and the same
+// region serves as the Lo image in between (ping-pong, no extra shared memory).  The backward sweep re-carves the three big
+// regions into two (packed L, stage data) pairs and prefetches stage j-1 the same way.
+// Shared memory 24.1 KB per warp -> 8 warps per SM, 1184 trajectories per wave (the 1024-trajectory headline is one wave).
 #pragma once
 
 #include "sweep.cuh"
@@ -36,18 +40,28 @@ struct QpShape {
     static constexpr int LS = 30;  // row stride of the L / Lo images: even (16-byte rows); column 29 of L holds 1 / L_ii
     static constexpr int LA = 38;  // row stride of the A image (column 37 is a zero pad)
     // per-warp shared memory (doubles); every offset is even so that double2 accesses are aligned
-    static constexpr int oL = 0, oE = oL + G * LS, oA = oE + G * LS, oCs = oA + NX * LA, oCp = oCs + 160, oP = oCp + 160,
-                         oT = oP + 14 + 8 * 10, oQ = oT + 38, oY = oQ + 38, oC = oY + 32, total = oC + 64;
+    // forward:  L image (870) | X (870) | Y (870), X and Y alternating between "stage data" and "Lo image"
+    // backward: packed L (464) x 2 | stage data (814) x 2 in the same 2610 doubles
+    static constexpr int oL = 0, oX = G * LS, oY = 2 * G * LS, big = 3 * G * LS;
+    static constexpr int dA = 0, dCs = NX * LA, dCp = dCs + 160, dTotal = dCp + 160;  // inside a stage-data region
+    static constexpr int LP = 464;                                                   // packed lower triangle (435) + 1 / L_ii (29)
+    static constexpr int bD0 = 2 * LP;
+    static constexpr int oP = big, oT = oP + 14 + 8 * 10, oQ = oT + 38, oNu = oQ + 38, oC = oNu + 32, oSt = oC + 64, total = oSt + 136;
+    static constexpr int stQ = 0, stG = 38, stH = 70;  // staging of the small per-stage vectors: q (38) | g or y (32) | H entries (64)
     static constexpr int WARPS = 4;
     static constexpr int SMEM_BYTES = WARPS * total * 8;
     // per-trajectory global workspace (doubles): per group  L_jj image (G * LS) | y_j (32)
     static constexpr int WS_GROUP = G * LS + 32;
-    static_assert(total % 2 == 0 && oA % 2 == 0 && oCs % 2 == 0 && oCp % 2 == 0 && oP % 2 == 0 && oT % 2 == 0 && oC % 2 == 0, "alignment");
+    static_assert(dTotal <= G * LS && bD0 + 2 * dTotal <= big, "region carving");
+    static_assert(total % 2 == 0 && dCs % 2 == 0 && oP % 2 == 0 && oT % 2 == 0 && oNu % 2 == 0 && oC % 2 == 0 && oSt % 2 == 0, "alignment");
     static_assert((WS_GROUP * 8) % 16 == 0, "bulk copies need 16-byte multiples");
 };
 
 __device__ __forceinline__ double2 qp_ld2(const double* p) { return *reinterpret_cast<const double2*>(p); }
 __device__ __forceinline__ void qp_st2(double* p, double a, double b) { *reinterpret_cast<double2*>(p) = make_double2(a, b); }
+__device__ __forceinline__ void qp_cp8(double* dst, const double* src) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((unsigned)__cvta_generic_to_shared(dst)), "l"(src) : "memory");
+}
 
 // Closed-form inverse of a symmetric 3x3 block [a b c; b d e; c e f] (row-major 9 entries out).
 __device__ __forceinline__ void inv_sym3(double a, double b, double c, double d, double e, double f, double* out) {
@@ -73,19 +87,20 @@ __device__ __forceinline__ void apply_pinv_warp(const double* __restrict__ pinv,
     __syncwarp();
 }
 
-// Stage j of a trajectory into shared memory: A_j (13 x 37), Cs_j / Cp_{j+1} (16 x 10 each: the non-zero columns of the contact rows
-// of stage j and of stage j+1 on w_j), P_j^-1, q_j.  Everything is zero-filled where the horizon ends (j = N: only the state part).
-__device__ __forceinline__ void qp_load_stage(const double* __restrict__ rec, const RecLayout& L, int N, int j, double* __restrict__ sm, int lane) {
+// Starts the asynchronous fetch of stage j into a stage-data region sD (A_j 13 x 37 at stride 38, Cs_j / Cp_{j+1} 16 x 10 each: the
+// non-zero columns of the contact rows of stage j and of stage j+1 on w_j) and into the staging area sSt (q_j, the entries of H_j
+// that P_j^-1 needs, and g_j when `with_g`).  Zero-filled where the horizon ends (j = N: only the state part).  No commit.
+__device__ __forceinline__ void qp_fetch_stage(const double* __restrict__ rec, const RecLayout& L, int N, int j, double* __restrict__ sD,
+                                               double* __restrict__ sSt, int lane, bool with_g) {
     using Q = QpShape;
-    double *sA = sm + Q::oA, *sCs = sm + Q::oCs, *sCp = sm + Q::oCp, *sP = sm + Q::oP, *sQ = sm + Q::oQ;
     const bool live = j < N, next = j + 1 < N;
     const int nX = Q::NX * (N + 1);
     const double* cj = rec + L.C + (long long)j * 320;
 #pragma unroll
     for (int it = 0; it < 5; ++it) {
         const int e = lane + 32 * it, row = e / 10, col = e - 10 * row;
-        sCs[e] = live ? cj[row * 20 + col] : 0.0;
-        sCp[e] = next ? cj[320 + row * 20 + 10 + col] : 0.0;
+        if (live) qp_cp8(sD + Q::dCs + e, cj + row * 20 + col); else sD[Q::dCs + e] = 0.0;
+        if (next) qp_cp8(sD + Q::dCp + e, cj + 320 + row * 20 + 10 + col); else sD[Q::dCp + e] = 0.0;
     }
     const double* aj = rec + L.A + (long long)j * 481;
 #pragma unroll
@@ -93,23 +108,46 @@ __device__ __forceinline__ void qp_load_stage(const double* __restrict__ rec, co
         const int e = lane + 32 * it;
         if (e < 481) {
             const int row = e / 37, col = e - 37 * row;
-            sA[row * Q::LA + col] = live ? aj[e] : 0.0;
+            if (live) qp_cp8(sD + Q::dA + row * Q::LA + col, aj + e); else sD[Q::dA + row * Q::LA + col] = 0.0;
         }
     }
-    for (int k = lane; k < 37; k += 32) sQ[k] = k < 13 ? rec[L.grad + Q::NX * j + k] : (live ? rec[L.grad + nX + Q::NU * j + (k - 13)] : 0.0);
-    if (live) {  // P_j^-1 from the packed upper triangle of H_j
+    if (lane < 13) sD[Q::dA + lane * Q::LA + 37] = 0.0;  // pad column, read by the 16-byte row loads
+    for (int k = lane; k < 37; k += 32) {
+        if (k < 13) qp_cp8(sSt + Q::stQ + k, rec + L.grad + Q::NX * j + k);
+        else if (live) qp_cp8(sSt + Q::stQ + k, rec + L.grad + nX + Q::NU * j + (k - 13));
+        else sSt[Q::stQ + k] = 0.0;
+    }
+    if (with_g) {
+        if (lane < 13) qp_cp8(sSt + Q::stG + lane, rec + L.g + Q::NX * j + lane);
+        else if (live && lane < Q::G) qp_cp8(sSt + Q::stG + lane, rec + L.g + nX + 16 * j + (lane - 13));
+        else sSt[Q::stG + lane] = 0.0;
+    }
+    if (live) {  // diagonal of the state block and the six distinct entries of each 3x3 input block, from the packed upper triangle of H_j
         const double* H = rec + L.H + (long long)j * Q::TRI;
-        if (lane < 13) sP[lane] = 1.0 / H[lane * 37 - (lane * (lane - 1)) / 2];
+        if (lane < 13) qp_cp8(sSt + Q::stH + lane, H + (lane * 37 - (lane * (lane - 1)) / 2));
         else if (lane < 21) {
             const int a = 13 + 3 * (lane - 13);
             const int d0 = a * 37 - (a * (a - 1)) / 2, d1 = (a + 1) * 37 - ((a + 1) * a) / 2, d2 = (a + 2) * 37 - ((a + 2) * (a + 1)) / 2;
-            inv_sym3(H[d0], H[d0 + 1], H[d0 + 2], H[d1], H[d1 + 1], H[d2], sP + 14 + 10 * (lane - 13));
+            double* dst = sSt + Q::stH + 16 + 6 * (lane - 13);
+            qp_cp8(dst + 0, H + d0); qp_cp8(dst + 1, H + d0 + 1); qp_cp8(dst + 2, H + d0 + 2);
+            qp_cp8(dst + 3, H + d1); qp_cp8(dst + 4, H + d1 + 1); qp_cp8(dst + 5, H + d2);
         }
-    } else {
-        const double* H = rec + L.HN;
-        if (lane < 13) sP[lane] = 1.0 / H[lane * 13 - (lane * (lane - 1)) / 2];
-        else if (lane < 21)
-            for (int e = 0; e < 9; ++e) sP[14 + 10 * (lane - 13) + e] = 0.0;
+    } else if (lane < 13) qp_cp8(sSt + Q::stH + lane, rec + L.HN + (lane * 13 - (lane * (lane - 1)) / 2));
+}
+
+// P_j^-1 from the staged entries of H_j.
+__device__ __forceinline__ void qp_build_pinv(const double* __restrict__ sSt, double* __restrict__ sP, bool live, int lane) {
+    using Q = QpShape;
+    if (lane < 13) sP[lane] = 1.0 / sSt[Q::stH + lane];
+    else if (lane < 21) {
+        double* out = sP + 14 + 10 * (lane - 13);
+        if (live) {
+            const double* h = sSt + Q::stH + 16 + 6 * (lane - 13);
+            inv_sym3(h[0], h[1], h[2], h[3], h[4], h[5], out);
+        } else {
+#pragma unroll
+            for (int e = 0; e < 9; ++e) out[e] = 0.0;
+        }
     }
     __syncwarp();
 }
@@ -140,8 +178,7 @@ qp_schur_kernel(const double* __restrict__ rec_all, long long ld_rec, double* __
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     double* const sm = reinterpret_cast<double*>(smem_raw) + wib * Q::total;
-    double *sL = sm + Q::oL, *sE = sm + Q::oE, *sA = sm + Q::oA, *sCs = sm + Q::oCs, *sCp = sm + Q::oCp, *sP = sm + Q::oP,
-           *sT = sm + Q::oT, *sQ = sm + Q::oQ, *sY = sm + Q::oY, *sC = sm + Q::oC;
+    double *sL = sm + Q::oL, *sP = sm + Q::oP, *sT = sm + Q::oT, *sQ = sm + Q::oQ, *sY = sm + Q::oNu, *sC = sm + Q::oC, *sSt = sm + Q::oSt;
     const long long b = (long long)blockIdx.x * Q::WARPS + wib;
     if (b >= batch) return;
     const double* __restrict__ rec = rec_all + b * ld_rec;
@@ -151,14 +188,14 @@ qp_schur_kernel(const double* __restrict__ rec_all, long long ld_rec, double* __
     // lane roles: state rows (identity in U, A rows in V) or contact rows (Cs rows in U, Cp rows in V); lanes 29..31 shadow row 28
     const bool act = lane < G, st = lane < 13;
     const int r = st ? 0 : min(lane - 13, 15), leg = r >> 2;
-    const int my_row = min(lane, G - 1);
 
-    if (lane < 13) sA[lane * LA + 37] = 0.0;  // pad column of the A image, read by the 16-byte row loads
     if (lane < 8) sP[14 + 10 * lane + 9] = 0.0;
-    if (lane == 0) sP[13] = 0.0;
+    if (lane == 0) { sP[13] = 0.0; sT[37] = 0.0; }
     sY[lane] = 0.0;
-    if (lane == 0) sT[37] = 0.0;
-    __syncwarp();
+    double* sD = sm + Q::oX;  // stage data of the current stage
+    double* sO = sm + Q::oY;  // the other region: Lo image, then landing zone of the next stage's data
+    qp_fetch_stage(rec, L, N, 0, sD, sSt, lane, true);
+    asm volatile("cp.async.commit_group;" ::: "memory");
 
     // ================================================================ forward sweep over the groups nu_0 .. nu_N
     double s[G], e[G];  // row `lane` of S_jj (lower triangle meaningful) and of S_{j,j-1} / Lo_j
@@ -167,11 +204,12 @@ qp_schur_kernel(const double* __restrict__ rec_all, long long ld_rec, double* __
     double carry = 0.0;  // (V_{j-1} t_{j-1})[lane]
     for (int j = 0; j <= N; ++j) {
         const bool live = j < N;
-        double gval = 0.0;
-        if (st) gval = rec[L.g + Q::NX * j + lane];
-        else if (live && act) gval = rec[L.g + nX + 16 * j + r];
-        qp_load_stage(rec, L, N, j, sm, lane);
-        apply_pinv_warp(sP, sQ, sT, lane);  // t_j = P_j^-1 q_j
+        const double *sA = sD + Q::dA, *sCs = sD + Q::dCs, *sCp = sD + Q::dCp;
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+        __syncwarp();
+        const double gval = sSt[Q::stG + lane];
+        qp_build_pinv(sSt, sP, live, lane);
+        apply_pinv_warp(sP, sSt + Q::stQ, sT, lane);  // t_j = P_j^-1 q_j
 
         // ---- own U row (contact lanes: the ten non-zeros) and its product with P^-1 -------------------------------------------
         double cs[10], wu[10];
@@ -233,20 +271,29 @@ qp_schur_kernel(const double* __restrict__ rec_all, long long ld_rec, double* __
             }
             if (act) {
 #pragma unroll
-                for (int c = 0; c + 1 < G; c += 2) qp_st2(sE + lane * LS + c, e[c], e[c + 1]);
-                qp_st2(sE + lane * LS + G - 1, e[G - 1], 0.0);
+                for (int c = 0; c + 1 < G; c += 2) qp_st2(sO + lane * LS + c, e[c], e[c + 1]);
+                qp_st2(sO + lane * LS + G - 1, e[G - 1], 0.0);
             }
             __syncwarp();
             // ---- S_jj -= Lo_j Lo_j^T ----------------------------------------------------------------------------------------------
 #pragma unroll
             for (int c = 0; c < G; ++c) {
-                const double* row = sE + c * LS;
-                double a0 = 0.0, a1 = 0.0;
+                const double* row = sO + c * LS;
+                double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
 #pragma unroll
-                for (int k = 0; k + 1 < G; k += 2) { const double2 t2 = qp_ld2(row + k); a0 += e[k] * t2.x; a1 += e[k + 1] * t2.y; }
+                for (int k = 0; k + 3 < G; k += 4) {
+                    const double2 t0 = qp_ld2(row + k), t2 = qp_ld2(row + k + 2);
+                    a0 += e[k] * t0.x; a1 += e[k + 1] * t0.y; a2 += e[k + 2] * t2.x; a3 += e[k + 3] * t2.y;
+                }
                 a0 += e[G - 1] * row[G - 1];
-                s[c] -= a0 + a1;
+                s[c] -= (a0 + a1) + (a2 + a3);
             }
+            __syncwarp();  // every lane is done with the Lo image
+        }
+        // ---- the other region is free until the next stage's TRSM: fetch stage j+1 into it while this stage factorises ----------------
+        if (live) {
+            qp_fetch_stage(rec, L, N, j + 1, sO, sSt, lane, true);
+            asm volatile("cp.async.commit_group;" ::: "memory");
         }
         // ---- Cholesky of S_jj fused with y_j = L_jj^-1 rhs_j: one column per step ---------------------------------------------------
         double rk = rhs, inv_own = 0.0;
@@ -329,10 +376,13 @@ qp_schur_kernel(const double* __restrict__ rec_all, long long ld_rec, double* __
             for (int c = 0; c < 13; ++c) {
                 e[c] = w[c];
                 const double* row = sA + c * LA;
-                double a0 = 0.0, a1 = 0.0;
+                double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
 #pragma unroll
-                for (int k = 0; k < 36; k += 2) { const double2 t2 = qp_ld2(row + k); a0 += w[k] * t2.x; a1 += w[k + 1] * t2.y; }
-                s[c] = a0 + a1 + w[36] * row[36];
+                for (int k = 0; k < 36; k += 4) {
+                    const double2 t0 = qp_ld2(row + k), t2 = qp_ld2(row + k + 2);
+                    a0 += w[k] * t0.x; a1 += w[k + 1] * t0.y; a2 += w[k + 2] * t2.x; a3 += w[k + 3] * t2.y;
+                }
+                s[c] = (a0 + a1) + (a2 + a3) + w[36] * row[36];
             }
 #pragma unroll
             for (int c = 13; c < G; ++c) {
@@ -351,29 +401,41 @@ qp_schur_kernel(const double* __restrict__ rec_all, long long ld_rec, double* __
                 }
             }
         }
+        double* const tmp = sD; sD = sO; sO = tmp;
     }
     if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
     __syncwarp();
 
     // ================================================================ backward sweep: nu_j, then d_j
-    // sY holds nu_{j+1} (zero beyond the horizon)
+    // sY holds nu_{j+1} (zero beyond the horizon).  The big regions become two (packed L_jj, stage data) pairs.
     sY[lane] = 0.0;
-    __syncwarp();
     double* __restrict__ step = step_all + b * ld_step;
-    for (int j = N; j >= 0; --j) {
-        const int nz = j < N ? 37 : 13;
+    auto fetch_back = [&](int j, int buf) {
+        qp_fetch_stage(rec, L, N, j, sm + Q::bD0 + buf * Q::dTotal, sSt, lane, false);
         const double* wj = ws + (long long)j * Q::WS_GROUP;
-        const double yj = act ? wj[G * LS + lane] : 0.0;
-        {
-            const double2* src = reinterpret_cast<const double2*>(wj);
-            double2* dst = reinterpret_cast<double2*>(sL);
-#pragma unroll
-            for (int it = 0; it < 14; ++it) {
-                const int q = lane + 32 * it;
-                if (q < G * LS / 2) dst[q] = src[q];
-            }
+        double* sLp = sm + buf * Q::LP;
+        if (act) {
+            qp_cp8(sSt + Q::stG + lane, wj + G * LS + lane);  // y_j
+            qp_cp8(sLp + 435 + lane, wj + lane * LS + G);      // 1 / L_ii
         }
-        qp_load_stage(rec, L, N, j, sm, lane);
+#pragma unroll
+        for (int i = 0; i < G; ++i)
+            if (lane <= i) qp_cp8(sLp + (i * (i + 1)) / 2 + lane, wj + i * LS + lane);
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+    __syncwarp();
+    fetch_back(N, 0);
+    for (int j = N; j >= 0; --j) {
+        const int nz = j < N ? 37 : 13, buf = (N - j) & 1;
+        const double* sLp = sm + buf * Q::LP;
+        const double* sDb = sm + Q::bD0 + buf * Q::dTotal;
+        const double *sA = sDb + Q::dA, *sCs = sDb + Q::dCs, *sCp = sDb + Q::dCp;
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+        __syncwarp();
+        const double yj = act ? sSt[Q::stG + lane] : 0.0;
+        for (int k = lane; k < 37; k += 32) sQ[k] = sSt[Q::stQ + k];
+        qp_build_pinv(sSt, sP, j < N, lane);
+        if (j > 0) fetch_back(j - 1, buf ^ 1);
         // a = V_j^T nu_{j+1}  (entries k = lane, lane + 32) -> sC ;  P^-1 a -> sT
         for (int k = lane; k < 37; k += 32) {
             double acc = 0.0;
@@ -397,23 +459,20 @@ qp_schur_kernel(const double* __restrict__ rec_all, long long ld_rec, double* __
             for (int m = 0; m < 3; ++m) rk += cs[7 + m] * sT[13 + 6 * leg + 3 + m];
         }
         {
-            double lrow[G];
-#pragma unroll
-            for (int c = 0; c + 1 < G; c += 2) { const double2 t2 = qp_ld2(sL + my_row * LS + c); lrow[c] = t2.x; lrow[c + 1] = t2.y; }
-            lrow[G - 1] = sL[my_row * LS + G - 1];
+            const double* own = sLp + (min(lane, G - 1) * (min(lane, G - 1) + 1)) / 2;  // own packed row: entries 0..lane
 #pragma unroll
             for (int i = 0; i < G; ++i) {
-                const double zi = __shfl_sync(FULL, rk, i) * sL[i * LS + G];
+                const double zi = __shfl_sync(FULL, rk, i) * sLp[435 + i];
                 if (lane == i) rk = zi;
-                else if (lane > i) rk -= lrow[i] * zi;
+                else if (lane > i && act) rk -= own[i] * zi;
             }
         }
         rk = yj - rk;  // y_j - Lo_{j+1}^T nu_{j+1}
 #pragma unroll
         for (int i = G - 1; i >= 0; --i) {  // nu_j = L_jj^-T rhs, column-oriented from the last row up; lane k owns entry k
-            const double ni = __shfl_sync(FULL, rk, i) * sL[i * LS + G];
+            const double ni = __shfl_sync(FULL, rk, i) * sLp[435 + i];
             if (lane == i) rk = ni;
-            else if (lane < i) rk -= sL[i * LS + lane] * ni;
+            else if (lane < i) rk -= sLp[(i * (i + 1)) / 2 + lane] * ni;
         }
         __syncwarp();
         if (act) sY[lane] = rk;
