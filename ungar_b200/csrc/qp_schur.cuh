@@ -63,6 +63,11 @@ __device__ __forceinline__ void qp_cp8(double* dst, const double* src) {
     asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((unsigned)__cvta_generic_to_shared(dst)), "l"(src) : "memory");
 }
 
+// D (8x8) += A (8x4, row) * B (4x8, col) in fp64: lane holds A[lane / 4][lane % 4], B[lane % 4][lane / 4], D[lane / 4][2 (lane % 4) + {0, 1}].
+__device__ __forceinline__ void qp_dmma(double& d0, double& d1, double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(d0), "+d"(d1) : "d"(a), "d"(b));
+}
+
 // Closed-form inverse of a symmetric 3x3 block [a b c; b d e; c e f] (row-major 9 entries out).
 __device__ __forceinline__ void inv_sym3(double a, double b, double c, double d, double e, double f, double* out) {
     const double c00 = d * f - e * e, c01 = c * e - b * f, c02 = b * e - c * d;
@@ -275,18 +280,39 @@ qp_schur_kernel(const double* __restrict__ rec_all, long long ld_rec, double* __
                 qp_st2(sO + lane * LS + G - 1, e[G - 1], 0.0);
             }
             __syncwarp();
-            // ---- S_jj -= Lo_j Lo_j^T ----------------------------------------------------------------------------------------------
+            // ---- S_jj -= Lo_j Lo_j^T on the FP64 tensor cores: ten lower 8x8 tiles x eight k-steps of mma.m8n8k4 -------------------------
+            // fragment (I, kk) = Lo[8 I + lane / 4][4 kk + lane % 4] serves as the A operand of tile row I and the B operand of tile column I
+            {
+                double acc[10][2];
 #pragma unroll
-            for (int c = 0; c < G; ++c) {
-                const double* row = sO + c * LS;
-                double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+                for (int t = 0; t < 10; ++t) { acc[t][0] = 0.0; acc[t][1] = 0.0; }
+                const int fr = lane >> 2, fq = lane & 3;
 #pragma unroll
-                for (int k = 0; k + 3 < G; k += 4) {
-                    const double2 t0 = qp_ld2(row + k), t2 = qp_ld2(row + k + 2);
-                    a0 += e[k] * t0.x; a1 += e[k + 1] * t0.y; a2 += e[k + 2] * t2.x; a3 += e[k + 3] * t2.y;
+                for (int kk = 0; kk < 8; ++kk) {
+                    double f[4];
+#pragma unroll
+                    for (int I = 0; I < 4; ++I) {
+                        f[I] = sO[min(8 * I + fr, G - 1) * LS + 4 * kk + fq];  // rows 29..31 shadow row 28 (their tiles' rows are dropped)
+                        if (kk == 7 && fq != 0) f[I] = 0.0;                     // k = 29..31 do not exist
+                    }
+#pragma unroll
+                    for (int I = 0; I < 4; ++I)
+#pragma unroll
+                        for (int J = 0; J <= I; ++J) qp_dmma(acc[(I * (I + 1)) / 2 + J][0], acc[(I * (I + 1)) / 2 + J][1], f[I], f[J]);
                 }
-                a0 += e[G - 1] * row[G - 1];
-                s[c] -= (a0 + a1) + (a2 + a3);
+                __syncwarp();  // all fragments are read: the product overwrites the Lo image, then every lane subtracts its row
+#pragma unroll
+                for (int I = 0; I < 4; ++I)
+#pragma unroll
+                    for (int J = 0; J <= I; ++J) {
+                        const int row = 8 * I + fr, col = 8 * J + 2 * fq;
+                        if (row < G && col < LS) qp_st2(sO + row * LS + col, acc[(I * (I + 1)) / 2 + J][0], acc[(I * (I + 1)) / 2 + J][1]);
+                    }
+                __syncwarp();
+                const double* mine = sO + min(lane, G - 1) * LS;
+#pragma unroll
+                for (int c = 0; c + 1 < G; c += 2) { const double2 t2 = qp_ld2(mine + c); s[c] -= t2.x; s[c + 1] -= t2.y; }
+                s[G - 1] -= mine[G - 1];
             }
             __syncwarp();  // every lane is done with the Lo image
         }
