@@ -159,6 +159,51 @@ int ungar_b200_kkt_step(ungar_b200_model* model, const void* xp, int64_t batch, 
 int ungar_b200_qp_solve(ungar_b200_model* model, const void* records_device, int64_t batch, int64_t ld_rec, void* steps,
                         int64_t ld_steps, void* multipliers, int64_t ld_multipliers, void* stream);
 
+/* Options of the outer loop: SoftSQPOptimizer's constructor arguments (optimization/soft_sqp.hpp:44-50; the barrier
+ * stiffness / epsilon belong to the model descriptor) and BacktrackingLineSearch::Parameters
+ * (optimization/backtracking_line_search.hpp:57-76).  ungar_b200_sqp_options_default fills the reference defaults:
+ * max_iterations 10, multiplier 1, alpha_min 1e-4, theta_min 1e-6, theta_max 1e-2, eta 1e-4, gamma_phi 1e-6,
+ * gamma_theta 1e-6, gamma_alpha 0.5, objective_tolerance 1e-6 (the literal of soft_sqp.hpp:103). */
+typedef struct ungar_b200_sqp_options {
+    int32_t max_iterations;
+    int32_t reserved;
+    double constraint_violation_multiplier;
+    double alpha_min, theta_min, theta_max, eta, gamma_phi, gamma_theta, gamma_alpha;
+    double objective_tolerance;
+} ungar_b200_sqp_options;
+
+int ungar_b200_sqp_options_default(ungar_b200_sqp_options* out);
+
+/* Per-trajectory state of the outer loop, two int32 per trajectory: { status, iterations started }. */
+enum ungar_b200_sqp_status {
+    UNGAR_B200_SQP_RUNNING            = 0, /* after ungar_b200_sqp_solve: stopped by max_iterations */
+    UNGAR_B200_SQP_CONVERGED          = 1, /* objective decreased by less than objective_tolerance (soft_sqp.hpp:101-108) */
+    UNGAR_B200_SQP_LINE_SEARCH_FAILED = 2  /* no step size >= alpha_min accepted; the iterate is unchanged (:100-102) */
+};
+/* Per-trajectory line-search report, 8 scalars of the model dtype:
+ * { alpha (0 = rejected), theta, phi, f after the step | theta, phi, f before it, grad f . dw }. */
+#define UNGAR_B200_LINE_SEARCH_INFO_SIZE 8
+
+/* Replaces BacktrackingLineSearch::Do (optimization/backtracking_line_search.hpp:81-165) with the merit functions
+ * SoftSQPOptimizer::Optimize passes (optimization/soft_sqp.hpp:81-99): cost phi = f + Zsoft(h), constraint violation
+ * theta = multiplier * |g|_2, both evaluated on the device at every trial point w + alpha dw.  All DEVICE pointers.
+ * On acceptance xp[b, 0:n_dec] += alpha * steps[b, :] in place.  `status` (int32 [batch][2], may be NULL) skips the
+ * trajectories whose status is not RUNNING and receives the bookkeeping of soft_sqp.hpp:100-108; `info`
+ * ([batch][8], may be NULL) receives the report above.  F64 models only: the acceptance tests compare relative
+ * changes of 1e-6 (EUNSUPPORTED for F32). */
+int ungar_b200_line_search(ungar_b200_model* model, void* xp, int64_t batch, int64_t ld_xp, const void* steps,
+                           int64_t ld_steps, const ungar_b200_sqp_options* options, int32_t* status, void* info,
+                           void* stream);
+
+/* Replaces SoftSQPOptimizer::Optimize (optimization/soft_sqp.hpp:63-109) for a batch of independent problems:
+ * max_iterations times { KKT sweep -> QP solve -> line search }, entirely on the device, no host round trip inside
+ * the loop.  `xp` is updated in place (the reference returns _cache.xp.head(n_dec)); `status` (int32 [batch][2])
+ * and `info` ([batch][8], may be NULL; report of the last line search) are host or device buffers per `mem`.
+ * Trajectories that stop early are frozen exactly where the reference's loop breaks.  Quadruped, F64 (the models
+ * ungar_b200_qp_solve supports). */
+int ungar_b200_sqp_solve(ungar_b200_model* model, void* xp, int64_t batch, int64_t ld_xp,
+                         const ungar_b200_sqp_options* options, int32_t* status, void* info, int32_t mem, void* stream);
+
 /* Device-side timing of the dominant kernel (the KKT sweep): when enabled, every sweep launch is bracketed by
  * CUDA events on the launching stream; ungar_b200_sweep_times synchronises and returns up to `cap` most recent
  * durations in milliseconds (oldest first) and clears the ring. */

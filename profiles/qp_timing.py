@@ -1,5 +1,10 @@
 """Times the batched QP solve next to the KKT sweep that feeds it (quadruped N = 100, 1024 trajectories, fp64)."""
+import os
+import sys
+
 import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 
 import ungar_b200
 from ungar_b200 import workloads as W

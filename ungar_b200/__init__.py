@@ -3,7 +3,7 @@
 The product path is: this package -> ctypes -> C ABI (include/ungar_b200.h) -> hand-written sm_100a CUDA
 kernels (ungar_b200/csrc).  It fails loudly when the CUDA library or a CUDA device is missing.
 """
-from .function import Function, Model  # noqa: F401
+from .function import Function, Model, SoftSQPOptimizer  # noqa: F401
 from .workloads import MODEL_IDS, MODEL_NAMES, QUADROTOR, QUADRUPED, RC_CAR  # noqa: F401
 
 # RelaxedPolyBarrierFunction (stiffness, epsilon) each reference example passes to SoftSQPOptimizer

@@ -14,6 +14,8 @@ F32, F64 = 0, 1
 OBJECTIVE, EQUALITIES, INEQUALITIES, SOFT_INEQUALITIES = 0, 1, 2, 3
 MEM_DEVICE, MEM_HOST = 0, 1
 SUMMARY_SIZE = 32
+LINE_SEARCH_INFO_SIZE = 8
+SQP_RUNNING, SQP_CONVERGED, SQP_LINE_SEARCH_FAILED = 0, 1, 2
 
 # every symbol include/ungar_b200.h declares (checked by tests/test_abi.py)
 SYMBOLS = [
@@ -22,7 +24,7 @@ SYMBOLS = [
     "ungar_b200_sparse_jacobian", "ungar_b200_sparse_hessian", "ungar_b200_kkt_layout_get",
     "ungar_b200_kkt_blocks", "ungar_b200_summaries", "ungar_b200_kkt_step", "ungar_b200_set_profiling",
     "ungar_b200_sweep_times", "ungar_b200_qp_solve", "ungar_b200_launch_count", "ungar_b200_last_error",
-    "ungar_b200_abi_version",
+    "ungar_b200_abi_version", "ungar_b200_sqp_options_default", "ungar_b200_line_search", "ungar_b200_sqp_solve",
 ]
 
 
@@ -38,6 +40,12 @@ class KktLayout(ctypes.Structure):
 
     def as_dict(self) -> dict:
         return {n: int(getattr(self, n)) for n in self._names}
+
+
+class SqpOptions(ctypes.Structure):
+    _fields_ = [("max_iterations", c_i32), ("reserved", c_i32), ("constraint_violation_multiplier", c_f64),
+                ("alpha_min", c_f64), ("theta_min", c_f64), ("theta_max", c_f64), ("eta", c_f64), ("gamma_phi", c_f64),
+                ("gamma_theta", c_f64), ("gamma_alpha", c_f64), ("objective_tolerance", c_f64)]
 
 
 class UngarB200Error(RuntimeError):
@@ -74,6 +82,9 @@ def load() -> ctypes.CDLL:
     L.ungar_b200_summaries.argtypes = [c_vp, c_vp, c_i64, c_i64, c_vp, c_i64, c_vp, c_vp]
     L.ungar_b200_kkt_step.argtypes = [c_vp, c_vp, c_i64, c_i64, c_vp, c_i64, c_vp, c_i32, c_vp]
     L.ungar_b200_qp_solve.argtypes = [c_vp, c_vp, c_i64, c_i64, c_vp, c_i64, c_vp, c_i64, c_vp]
+    L.ungar_b200_sqp_options_default.argtypes = [ctypes.POINTER(SqpOptions)]
+    L.ungar_b200_line_search.argtypes = [c_vp, c_vp, c_i64, c_i64, c_vp, c_i64, ctypes.POINTER(SqpOptions), c_vp, c_vp, c_vp]
+    L.ungar_b200_sqp_solve.argtypes = [c_vp, c_vp, c_i64, c_i64, ctypes.POINTER(SqpOptions), c_vp, c_vp, c_i32, c_vp]
     L.ungar_b200_set_profiling.argtypes = [c_i32]
     L.ungar_b200_sweep_times.argtypes = [ctypes.POINTER(ctypes.c_float), c_i32, ctypes.POINTER(c_i32)]
     L.ungar_b200_launch_count.restype = c_i64

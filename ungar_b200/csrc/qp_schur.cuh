@@ -176,7 +176,8 @@ __device__ __forceinline__ double qp_contact_T(const double* __restrict__ sCx, c
 // Forward sweep (factorisation + forward substitution), then backward sweep (multipliers and step).
 __global__ void __launch_bounds__(QpShape::WARPS * 32, 2)
 qp_schur_kernel(const double* __restrict__ rec_all, long long ld_rec, double* __restrict__ ws_all, double* __restrict__ step_all,
-                long long ld_step, double* __restrict__ mult_all, long long ld_mult, int N, long long batch, RecLayout L, double delta) {
+                long long ld_step, double* __restrict__ mult_all, long long ld_mult, int N, long long batch, RecLayout L, double delta,
+                const int* __restrict__ skip_status) {
     using Q = QpShape;
     constexpr int G = Q::G, LS = Q::LS, LA = Q::LA;
     constexpr unsigned FULL = 0xffffffffu;
@@ -186,6 +187,7 @@ qp_schur_kernel(const double* __restrict__ rec_all, long long ld_rec, double* __
     double *sL = sm + Q::oL, *sP = sm + Q::oP, *sT = sm + Q::oT, *sQ = sm + Q::oQ, *sY = sm + Q::oNu, *sC = sm + Q::oC, *sSt = sm + Q::oSt;
     const long long b = (long long)blockIdx.x * Q::WARPS + wib;
     if (b >= batch) return;
+    if (skip_status && skip_status[2 * b] != 0) return;  // SQP loop: this trajectory has stopped (warp-uniform)
     const double* __restrict__ rec = rec_all + b * ld_rec;
     double* __restrict__ ws = ws_all + b * (long long)(N + 1) * Q::WS_GROUP;
     const int nX = Q::NX * (N + 1);

@@ -18,6 +18,7 @@
 #include "sweep_tpn.cuh"
 #include "sweep_small.cuh"
 #include "qp_schur.cuh"
+#include "line_search.cuh"
 
 namespace {
 
@@ -86,7 +87,7 @@ struct ungar_b200_model {
     ub::RecLayout rl{};
     ub::BarrierCoef<double> bar{};
     FunctionTables fn[4];
-    DeviceBuffer stage_cost, ws_records, ws_xp, ws_out, ws_qp;
+    DeviceBuffer stage_cost, ws_records, ws_xp, ws_out, ws_qp, ws_steps, ws_status, ws_info;
     size_t elem = 8;
 };
 
@@ -560,6 +561,61 @@ int launch_barrier_t(ungar_b200_model& mdl, const void* z, int64_t ld_z, void* o
     return UNGAR_B200_OK;
 }
 
+// QP solve launch (qp_schur.cuh).  `skip_status` (may be null): trajectories whose status is not RUNNING are skipped.
+int launch_qp(ungar_b200_model& mdl, const void* rec, int64_t batch, int64_t ld_rec, void* steps, int64_t ld_steps, void* mult,
+              int64_t ld_mult, const int32_t* skip_status, cudaStream_t stream) {
+    using Q = ub::QpShape;
+    if (int rc = mdl.ws_qp.reserve(size_t(batch) * (mdl.N + 1) * Q::WS_GROUP * sizeof(double))) return rc;
+    static bool configured = false;
+    if (!configured) {
+        UB_CUDA(cudaFuncSetAttribute(ub::qp_schur_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, Q::SMEM_BYTES));
+        configured = true;
+    }
+    const unsigned grid = unsigned((batch + Q::WARPS - 1) / Q::WARPS);
+    ub::qp_schur_kernel<<<grid, Q::WARPS * 32, Q::SMEM_BYTES, stream>>>(
+        static_cast<const double*>(rec), ld_rec, static_cast<double*>(mdl.ws_qp.ptr), static_cast<double*>(steps), ld_steps,
+        static_cast<double*>(mult), ld_mult, mdl.N, batch, mdl.rl, 1e-9, skip_status);
+    ++g_launches;
+    UB_CUDA(cudaGetLastError());
+    return UNGAR_B200_OK;
+}
+
+int check_options(const ungar_b200_sqp_options& o) {
+    if (o.max_iterations < 0) return fail(UNGAR_B200_EINVAL, "max_iterations %d < 0", o.max_iterations);
+    if (!(o.gamma_alpha > 0.0 && o.gamma_alpha < 1.0)) return fail(UNGAR_B200_EINVAL, "gamma_alpha must lie in (0, 1)");
+    if (!(o.alpha_min > 0.0)) return fail(UNGAR_B200_EINVAL, "alpha_min must be positive (the backtracking loop would not end)");
+    return UNGAR_B200_OK;
+}
+
+template <class Mdl>
+int launch_line_search_t(ungar_b200_model& mdl, double* xp, int64_t batch, int64_t ld_xp, const double* steps, int64_t ld_steps,
+                         const ungar_b200_sqp_options& o, int32_t* status, double* info, cudaStream_t stream) {
+    auto kernel = ub::line_search_kernel<Mdl, double>;
+    const int smem = int((mdl.layout.n_dec + mdl.layout.n_par) * sizeof(double));
+    if (smem > 220 * 1024) return fail(UNGAR_B200_EUNSUPPORTED, "horizon too long for the shared-memory trial point (%d bytes)", smem);
+    static int configured = 0;  // per instantiation: largest size configured so far
+    if (smem > configured) {
+        UB_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        configured = smem;
+    }
+    const ub::LineSearchParams P{o.alpha_min, o.theta_min, o.theta_max, o.eta, o.gamma_phi, o.gamma_theta, o.gamma_alpha,
+                                 o.constraint_violation_multiplier, o.objective_tolerance};
+    kernel<<<unsigned(batch), ub::LS_THREADS, smem, stream>>>(xp, ld_xp, steps, ld_steps, mdl.N, mdl.bar, P, status, info);
+    ++g_launches;
+    UB_CUDA(cudaGetLastError());
+    return UNGAR_B200_OK;
+}
+
+int launch_line_search(ungar_b200_model& mdl, double* xp, int64_t batch, int64_t ld_xp, const double* steps, int64_t ld_steps,
+                       const ungar_b200_sqp_options& o, int32_t* status, double* info, cudaStream_t stream) {
+    switch (mdl.desc.kind) {
+        case UNGAR_B200_QUADROTOR: return launch_line_search_t<ub::Quadrotor>(mdl, xp, batch, ld_xp, steps, ld_steps, o, status, info, stream);
+        case UNGAR_B200_RC_CAR: return launch_line_search_t<ub::RcCar>(mdl, xp, batch, ld_xp, steps, ld_steps, o, status, info, stream);
+        case UNGAR_B200_QUADRUPED: return launch_line_search_t<ub::Quadruped>(mdl, xp, batch, ld_xp, steps, ld_steps, o, status, info, stream);
+    }
+    return fail(UNGAR_B200_EINVAL, "unknown model kind %d", mdl.desc.kind);
+}
+
 bool valid_fn(int32_t f) { return f >= 0 && f <= 3; }
 
 // What a reference-format call needs: which sweep mode fills the slots its gather map points at.
@@ -771,20 +827,78 @@ int ungar_b200_qp_solve(ungar_b200_model* model, const void* records_device, int
         return fail(UNGAR_B200_EINVAL, "stride smaller than the row it holds");
     if (batch == 0) return UNGAR_B200_OK;
     UB_CUDA(cudaSetDevice(model->desc.device));
+    return launch_qp(*model, records_device, batch, ld_rec, steps, ld_steps, multipliers, ld_multipliers, nullptr,
+                     static_cast<cudaStream_t>(stream_));
+}
+
+int ungar_b200_sqp_options_default(ungar_b200_sqp_options* out) {
+    if (!out) return fail(UNGAR_B200_EINVAL, "null argument");
+    *out = ungar_b200_sqp_options{10, 0, 1.0, 1e-4, 1e-6, 1e-2, 1e-4, 1e-6, 1e-6, 0.5, 1e-6};
+    return UNGAR_B200_OK;
+}
+
+int ungar_b200_line_search(ungar_b200_model* model, void* xp, int64_t batch, int64_t ld_xp, const void* steps, int64_t ld_steps,
+                           const ungar_b200_sqp_options* options, int32_t* status, void* info, void* stream_) {
+    if (!model || !options) return fail(UNGAR_B200_EINVAL, "null argument");
+    if (model->desc.dtype != UNGAR_B200_F64)
+        return fail(UNGAR_B200_EUNSUPPORTED, "the line search compares relative changes of 1e-6: F64 models only");
+    if (batch < 0 || (batch > 0 && (!xp || !steps))) return fail(UNGAR_B200_EINVAL, "null buffer");
+    const ungar_b200_kkt_layout& L = model->layout;
+    if (ld_xp < L.n_dec + L.n_par || ld_steps < L.n_dec) return fail(UNGAR_B200_EINVAL, "stride smaller than the row it holds");
+    if (int rc = check_options(*options)) return rc;
+    if (batch == 0) return UNGAR_B200_OK;
+    UB_CUDA(cudaSetDevice(model->desc.device));
+    return launch_line_search(*model, static_cast<double*>(xp), batch, ld_xp, static_cast<const double*>(steps), ld_steps, *options,
+                              status, static_cast<double*>(info), static_cast<cudaStream_t>(stream_));
+}
+
+int ungar_b200_sqp_solve(ungar_b200_model* model, void* xp, int64_t batch, int64_t ld_xp, const ungar_b200_sqp_options* options,
+                         int32_t* status, void* info, int32_t mem, void* stream_) {
+    if (!model || !options) return fail(UNGAR_B200_EINVAL, "null argument");
+    if (model->desc.kind != UNGAR_B200_QUADRUPED || model->desc.dtype != UNGAR_B200_F64)
+        return fail(UNGAR_B200_EUNSUPPORTED, "sqp_solve needs qp_solve: quadruped problem in F64");
+    if (batch < 0 || (batch > 0 && (!xp || !status))) return fail(UNGAR_B200_EINVAL, "null buffer");
+    if (mem != UNGAR_B200_MEM_DEVICE && mem != UNGAR_B200_MEM_HOST) return fail(UNGAR_B200_EINVAL, "unknown mem %d", mem);
+    const ungar_b200_kkt_layout& L = model->layout;
+    const int64_t n_in = L.n_dec + L.n_par;
+    if (ld_xp < n_in) return fail(UNGAR_B200_EINVAL, "ld_xp %lld < %lld", (long long)ld_xp, (long long)n_in);
+    if (int rc = check_options(*options)) return rc;
+    if (batch == 0) return UNGAR_B200_OK;
+    UB_CUDA(cudaSetDevice(model->desc.device));
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
-    using Q = ub::QpShape;
-    if (int rc = model->ws_qp.reserve(size_t(batch) * (model->N + 1) * Q::WS_GROUP * sizeof(double))) return rc;
-    static bool configured = false;
-    if (!configured) {
-        UB_CUDA(cudaFuncSetAttribute(ub::qp_schur_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, Q::SMEM_BYTES));
-        configured = true;
+    const size_t es = sizeof(double);
+    if (int rc = model->ws_records.reserve(size_t(batch) * L.size * es)) return rc;
+    if (int rc = model->ws_steps.reserve(size_t(batch) * L.n_dec * es)) return rc;
+    double* d_xp    = static_cast<double*>(xp);
+    int64_t d_ld_xp = ld_xp;
+    int32_t* d_status = status;
+    double* d_info    = static_cast<double*>(info);
+    if (mem == UNGAR_B200_MEM_HOST) {
+        if (int rc = model->ws_xp.reserve(size_t(batch) * n_in * es)) return rc;
+        if (int rc = model->ws_status.reserve(size_t(batch) * 2 * sizeof(int32_t))) return rc;
+        if (info) {
+            if (int rc = model->ws_info.reserve(size_t(batch) * UNGAR_B200_LINE_SEARCH_INFO_SIZE * es)) return rc;
+        }
+        UB_CUDA(cudaMemcpy2DAsync(model->ws_xp.ptr, n_in * es, xp, ld_xp * es, n_in * es, batch, cudaMemcpyHostToDevice, stream));
+        d_xp = static_cast<double*>(model->ws_xp.ptr); d_ld_xp = n_in;
+        d_status = static_cast<int32_t*>(model->ws_status.ptr);
+        d_info   = info ? static_cast<double*>(model->ws_info.ptr) : nullptr;
     }
-    const unsigned grid = unsigned((batch + Q::WARPS - 1) / Q::WARPS);
-    ub::qp_schur_kernel<<<grid, Q::WARPS * 32, Q::SMEM_BYTES, stream>>>(
-        static_cast<const double*>(records_device), ld_rec, static_cast<double*>(model->ws_qp.ptr), static_cast<double*>(steps),
-        ld_steps, static_cast<double*>(multipliers), ld_multipliers, model->N, batch, model->rl, 1e-9);
-    ++g_launches;
-    UB_CUDA(cudaGetLastError());
+    UB_CUDA(cudaMemsetAsync(d_status, 0, size_t(batch) * 2 * sizeof(int32_t), stream));
+    if (d_info) UB_CUDA(cudaMemsetAsync(d_info, 0, size_t(batch) * UNGAR_B200_LINE_SEARCH_INFO_SIZE * es, stream));
+    for (int it = 0; it < options->max_iterations; ++it) {
+        // AssembleOSQPInstance -> Solve -> BacktrackingLineSearch::Do (soft_sqp.hpp:76-99), stream-ordered
+        if (int rc = launch_sweep(*model, d_xp, batch, d_ld_xp, model->ws_records.ptr, L.size, MODE_KKT, nullptr, stream)) return rc;
+        if (int rc = launch_qp(*model, model->ws_records.ptr, batch, L.size, model->ws_steps.ptr, L.n_dec, nullptr, 0, d_status, stream)) return rc;
+        if (int rc = launch_line_search(*model, d_xp, batch, d_ld_xp, static_cast<const double*>(model->ws_steps.ptr), L.n_dec, *options,
+                                        d_status, d_info, stream)) return rc;
+    }
+    if (mem == UNGAR_B200_MEM_HOST) {
+        UB_CUDA(cudaMemcpy2DAsync(xp, ld_xp * es, d_xp, n_in * es, L.n_dec * es, batch, cudaMemcpyDeviceToHost, stream));
+        UB_CUDA(cudaMemcpyAsync(status, d_status, size_t(batch) * 2 * sizeof(int32_t), cudaMemcpyDeviceToHost, stream));
+        if (info) UB_CUDA(cudaMemcpyAsync(info, d_info, size_t(batch) * UNGAR_B200_LINE_SEARCH_INFO_SIZE * es, cudaMemcpyDeviceToHost, stream));
+        UB_CUDA(cudaStreamSynchronize(stream));
+    }
     return UNGAR_B200_OK;
 }
 

@@ -44,6 +44,7 @@ class Model:
         self.np_dtype = _NP_DTYPE[self.dtype]
         self.device = int(device)
         self._lib = _lib.load()
+        self.barrier = (float(barrier[0]), float(barrier[1]))
         desc = ModelDesc(self.kind, self.horizon, self.dtype, self.device, float(barrier[0]), float(barrier[1]))
         handle = ctypes.c_void_p()
         check(self._lib.ungar_b200_model_create(ctypes.byref(desc), ctypes.byref(handle)))
@@ -148,6 +149,53 @@ class Model:
                                             steps.stride(0), mp, ml, _torch_stream()))
         return steps, multipliers
 
+    def sqp_options(self, **overrides) -> "_lib.SqpOptions":
+        """Reference defaults (soft_sqp.hpp:44-50, backtracking_line_search.hpp:70-76) with keyword overrides."""
+        opts = _lib.SqpOptions()
+        check(self._lib.ungar_b200_sqp_options_default(ctypes.byref(opts)))
+        for k, v in overrides.items():
+            if not hasattr(opts, k):
+                raise TypeError(f"unknown SQP option {k!r}")
+            setattr(opts, k, v)
+        return opts
+
+    def line_search(self, xp, steps, options=None, status=None, info=None):
+        """Batched BacktrackingLineSearch::Do (backtracking_line_search.hpp:81-165) on CUDA tensors: updates ``xp[:, :n_dec]``
+        in place where a step is accepted and returns ``info[B, 8]`` = (alpha, theta, phi, f | theta0, phi0, f0, grad f . dw)."""
+        import torch
+
+        options = options or self.sqp_options()
+        if info is None:
+            info = torch.empty((xp.shape[0], _lib.LINE_SEARCH_INFO_SIZE), dtype=xp.dtype, device=xp.device)
+        check(self._lib.ungar_b200_line_search(self._handle, xp.data_ptr(), xp.shape[0], xp.stride(0), steps.data_ptr(),
+                                               steps.stride(0), ctypes.byref(options),
+                                               status.data_ptr() if status is not None else None, info.data_ptr(),
+                                               _torch_stream()))
+        return info
+
+    def sqp_solve(self, xp, options=None, want_info: bool = True):
+        """SoftSQPOptimizer::Optimize (soft_sqp.hpp:63-109) for a batch, on the device.  ``xp`` (CUDA tensor or numpy array
+        ``[B, n_xp]``) is updated in place; returns ``(status[B, 2] int32 = (status, iterations), info[B, 8] | None)``."""
+        options = options or self.sqp_options()
+        if _is_torch(xp):
+            import torch
+
+            B = xp.shape[0]
+            status = torch.empty((B, 2), dtype=torch.int32, device=xp.device)
+            info = torch.empty((B, _lib.LINE_SEARCH_INFO_SIZE), dtype=xp.dtype, device=xp.device) if want_info else None
+            check(self._lib.ungar_b200_sqp_solve(self._handle, xp.data_ptr(), B, xp.stride(0), ctypes.byref(options),
+                                                 status.data_ptr(), info.data_ptr() if want_info else None, MEM_DEVICE,
+                                                 _torch_stream()))
+            return status, info
+        if not (isinstance(xp, np.ndarray) and xp.dtype == self.np_dtype and xp.ndim == 2 and xp.flags.c_contiguous):
+            raise ValueError("host xp must be a C-contiguous [B, n_xp] array of the model dtype (it is updated in place)")
+        B = xp.shape[0]
+        status = np.empty((B, 2), dtype=np.int32)
+        info = np.empty((B, _lib.LINE_SEARCH_INFO_SIZE), dtype=self.np_dtype) if want_info else None
+        check(self._lib.ungar_b200_sqp_solve(self._handle, xp.ctypes.data, B, xp.shape[1], ctypes.byref(options),
+                                             status.ctypes.data, info.ctypes.data if want_info else None, MEM_HOST, None))
+        return status, info
+
     def set_profiling(self, enabled: bool) -> None:
         check(self._lib.ungar_b200_set_profiling(int(enabled)))
 
@@ -179,6 +227,32 @@ class Model:
         if L["hc_per_node"]:
             out["Hc"] = cut(L["Hc"], (N - 1) * nu, N - 1, nu)
         return out
+
+
+class SoftSQPOptimizer:
+    """Mirror of ``Ungar::SoftSQPOptimizer`` (optimization/soft_sqp.hpp:42-61): same constructor arguments, ``Optimize`` takes
+    the NLP problem (a ``Model``) and the flat vector(s) ``xp``.  The barrier (stiffness, epsilon) lives in the model handle,
+    where the reference JIT-compiles it into its own Function (soft_sqp.hpp:114-138); ``Optimize`` checks they agree."""
+
+    def __init__(self, verbose: bool = False, constraintViolationMultiplier: float = 1.0, maxIterations: int = 10,
+                 stiffness: float = 100.0, epsilon: float = 2e-5):
+        self.verbose = verbose
+        self.constraintViolationMultiplier = float(constraintViolationMultiplier)
+        self.maxIterations = int(maxIterations)
+        self.stiffness, self.epsilon = float(stiffness), float(epsilon)
+        self.status = None
+        self.info = None
+
+    def Optimize(self, nlpProblem: "Model", xp):
+        if (nlpProblem.barrier[0], nlpProblem.barrier[1]) != (self.stiffness, self.epsilon):
+            raise ValueError("the model was created with a different barrier (stiffness, epsilon) than this optimizer")
+        opts = nlpProblem.sqp_options(max_iterations=self.maxIterations,
+                                      constraint_violation_multiplier=self.constraintViolationMultiplier)
+        single = not _is_torch(xp) and np.ndim(xp) == 1
+        buf = np.array(xp, dtype=nlpProblem.np_dtype)[None] if single else xp
+        self.status, self.info = nlpProblem.sqp_solve(buf, opts)
+        n = nlpProblem.layout["n_dec"]
+        return buf[0, :n] if single else buf[:, :n]
 
 
 class Function:
