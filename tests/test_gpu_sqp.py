@@ -113,8 +113,6 @@ def test_sqp_solve_matches_reference_loop(oracle, N, iters, perturb):
         assert np.array_equal(got[b, n:], xp[b, n:])
     # lock-step: feeding the DEVICE QP step of every iteration into the CPU loop removes the solver difference; what remains is
     # the line search and the bookkeeping, which must agree to rounding
-    state = torch.from_numpy(xp.copy()).cuda()
-
     def device_step(b):
         def qp(x):
             rec = m.kkt_blocks(torch.from_numpy(x[None].copy()).cuda(), torch.zeros((1, m.layout["size"]), dtype=torch.float64, device="cuda"))
@@ -125,7 +123,6 @@ def test_sqp_solve_matches_reference_loop(oracle, N, iters, perturb):
         ref, ref_status, ref_iters, _ = S.soft_sqp(oracle, W.QUADRUPED, N, xp[b], k, eps, mult, iters, qp=device_step(b))
         assert (st[b, 0], st[b, 1]) == (ref_status, ref_iters)
         assert np.max(np.abs(got[b, :n] - ref[:n])) <= 1e-10 * np.max(np.abs(ref[:n]))
-    del state
     # host-buffer entry point (MEM_HOST) and the SoftSQPOptimizer mirror give the same iterates
     host = xp.copy()
     opt = ungar_b200.SoftSQPOptimizer(False, mult, iters, k, eps)
