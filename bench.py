@@ -369,7 +369,7 @@ def ours(args, rank: int, local_rank: int, world: int):
         "dtype": args.dtype, "data": "synthetic", "config": workload_config(args, world), "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": B * model.n_xp * elem,
                 "d2h_bytes_per_step": B * 32 * elem, "steps": e2e_steps,
-                "path": "ungar_b200_kkt_step(MEM_HOST): pinned host xp -> H2D -> sweep (records stay in HBM) -> summaries -> D2H"},
+                "path": "ungar_b200_kkt_step(MEM_HOST): pinned host xp -> H2D in 4 chunks overlapped with the sweep of the previous chunk (records stay in HBM) -> summaries -> D2H"},
         "e2e_full_record_d2h": ({"value": full_value, "unit": UNIT, "d2h_bytes_per_step": B * L["size"] * elem,
                                  "path": "ungar_b200_kkt_blocks(MEM_HOST): whole record back to the host every step"}
                                 if full_value else None),
