@@ -154,8 +154,10 @@ int ungar_b200_kkt_step(ungar_b200_model* model, const void* xp, int64_t batch, 
  * constrained QP assembled by ungar_b200_kkt_blocks:  min 1/2 d^T P d + q^T d  s.t.  A d = -g.  Consumes the records in
  * place (DEVICE pointers), writes the step `steps[b, 0:n_dec]` (the reference's `primal_solution()`, [X | U] order) and,
  * if `multipliers` is not NULL, the equality multipliers `multipliers[b, 0:m_eq]` in the reference's row order.
- * Exact stage-wise factorisation (block-tridiagonal Schur complement), not ADMM.  Quadruped, F64 only
- * (UNGAR_B200_EUNSUPPORTED otherwise). */
+ * Exact stage-wise factorisations, not ADMM: quadrotor and RC car by a Riccati recursion (the input-rate coupling of
+ * the objective is carried by augmenting the state with the previous input), quadruped by a block-tridiagonal Schur
+ * complement on the multipliers (its contact rows are extra equalities).  F64 models only (UNGAR_B200_EUNSUPPORTED
+ * otherwise). */
 int ungar_b200_qp_solve(ungar_b200_model* model, const void* records_device, int64_t batch, int64_t ld_rec, void* steps,
                         int64_t ld_steps, void* multipliers, int64_t ld_multipliers, void* stream);
 
@@ -199,8 +201,7 @@ int ungar_b200_line_search(ungar_b200_model* model, void* xp, int64_t batch, int
  * max_iterations times { KKT sweep -> QP solve -> line search }, entirely on the device, no host round trip inside
  * the loop.  `xp` is updated in place (the reference returns _cache.xp.head(n_dec)); `status` (int32 [batch][2])
  * and `info` ([batch][8], may be NULL; report of the last line search) are host or device buffers per `mem`.
- * Trajectories that stop early are frozen exactly where the reference's loop breaks.  Quadruped, F64 (the models
- * ungar_b200_qp_solve supports). */
+ * Trajectories that stop early are frozen exactly where the reference's loop breaks.  F64 models only. */
 int ungar_b200_sqp_solve(ungar_b200_model* model, void* xp, int64_t batch, int64_t ld_xp,
                          const ungar_b200_sqp_options* options, int32_t* status, void* info, int32_t mem, void* stream);
 

@@ -67,12 +67,42 @@ def test_qp_optimality_at_full_batch():
     assert torch.equal(steps2, steps)
 
 
-def test_qp_rejects_other_models():
+@pytest.mark.parametrize("name,N", [("quadrotor", 30), ("quadrotor", 7), ("rc_car", 60), ("rc_car", 2)])
+def test_riccati_qp_matches_monolithic_kkt_solve(oracle, name, N):
+    """Quadrotor / RC car: the Riccati step and multipliers against one sparse LU of the KKT system assembled the way
+    AssembleOSQPInstance does (oracle/sqp_reference.py::monolithic_qp, soft_sqp.hpp:141-158) — including the u_k - u_{k+1}
+    coupling of the input-rate cost, which the recursion carries in the augmented state."""
+    import torch
+
+    import ungar_b200
+    from oracle import sqp_reference as S
+
+    mid = W.MODEL_IDS[name]
+    k, eps = EXAMPLE_BARRIER[mid]
+    model = ungar_b200.Model(name, N, dtype="f64", barrier=(k, eps))
+    B = 5
+    xp = W.synthetic_batch(mid, N, B, seed=43)
+    xp[1, model.layout["nx"] * (N + 1):model.layout["n_dec"]] *= 1.5  # push some inputs into the barrier's active region
+    rec = model.kkt_blocks(torch.from_numpy(xp).cuda(), torch.zeros((B, model.layout["size"]), dtype=torch.float64, device="cuda"))
+    steps, mult = model.qp_solve(rec)
+    torch.cuda.synchronize()
+    steps, mult = steps.cpu().numpy(), mult.cpu().numpy()
+    for b in range(B):
+        P, q, A, g, _ = S.monolithic_qp(oracle, mid, N, xp[b], k, eps)
+        d_ref, lam_ref = S.solve_qp(P, q, A, g, delta=0.0)
+        assert np.max(np.abs(steps[b] - d_ref)) <= 1e-7 * np.max(np.abs(d_ref)), (b, np.max(np.abs(steps[b] - d_ref)) / np.max(np.abs(d_ref)))
+        assert np.max(np.abs(mult[b] - lam_ref)) <= 1e-6 * max(1e-12, np.max(np.abs(lam_ref)))
+        # optimality of the device solution on its own: A d = -g,  P d + q + A^T lambda = 0
+        assert np.max(np.abs(A @ steps[b] + g)) <= 1e-9 * max(1.0, np.max(np.abs(g)))
+        assert np.max(np.abs(P @ steps[b] + q + A.T @ mult[b])) <= 1e-7 * max(1.0, np.max(np.abs(q)))
+
+
+def test_qp_rejects_f32():
     import torch
 
     import ungar_b200
     from ungar_b200 import _lib
 
-    m = ungar_b200.Model("quadrotor", 30, dtype="f64")
+    m = ungar_b200.Model("quadrotor", 30, dtype="f32")
     with pytest.raises(_lib.UngarB200Error):
-        m.qp_solve(torch.zeros((1, m.layout["size"]), dtype=torch.float64, device="cuda"))
+        m.qp_solve(torch.zeros((1, m.layout["size"]), dtype=torch.float32, device="cuda"))

@@ -85,25 +85,27 @@ def test_line_search_skips_stopped_trajectories_and_rejects_f32():
         m32.line_search(xp.float(), dw.float())
 
 
-@pytest.mark.parametrize("N,iters,perturb", [(10, 5, False), (30, 4, True)])
-def test_sqp_solve_matches_reference_loop(oracle, N, iters, perturb):
+@pytest.mark.parametrize("name,N,iters,perturb", [("quadruped", 10, 5, False), ("quadruped", 30, 4, True), ("quadrotor", 30, 6, False),
+                                                  ("rc_car", 30, 6, False)])
+def test_sqp_solve_matches_reference_loop(oracle, name, N, iters, perturb):
     """Whole loop on the device vs SoftSQPOptimizer::Optimize restated on the CPU (exact sparse-LU QP), same iterates."""
     import torch
 
     import ungar_b200
     from oracle import sqp_reference as S
 
-    k, eps = EXAMPLE_BARRIER[W.QUADRUPED]
-    mult = 1.0 / N
-    m = ungar_b200.Model("quadruped", N, dtype="f64", barrier=(k, eps))
+    mid = W.MODEL_IDS[name]
+    k, eps = EXAMPLE_BARRIER[mid]
+    mult = multiplier(mid, N)
+    m = ungar_b200.Model(name, N, dtype="f64", barrier=(k, eps))
     n = m.layout["n_dec"]
     B = 4
-    xp = W.synthetic_batch(W.QUADRUPED, N, B, seed=23, perturb_params=perturb)
+    xp = W.synthetic_batch(mid, N, B, seed=23, perturb_params=perturb)
     d_xp = torch.from_numpy(xp.copy()).cuda()
     status, info = m.sqp_solve(d_xp, m.sqp_options(max_iterations=iters, constraint_violation_multiplier=mult))
     got, st, info = d_xp.cpu().numpy(), status.cpu().numpy(), info.cpu().numpy()
     for b in range(B):
-        ref, ref_status, ref_iters, log = S.soft_sqp(oracle, W.QUADRUPED, N, xp[b], k, eps, mult, iters)
+        ref, ref_status, ref_iters, log = S.soft_sqp(oracle, mid, N, xp[b], k, eps, mult, iters)
         assert (st[b, 0], st[b, 1]) == (ref_status, ref_iters), (b, st[b], ref_status, ref_iters)
         assert info[b, 0] == log[-1]["ls"].alpha
         # Two exact QP solvers (stage-wise Schur complement on the device, sparse LU of the KKT system here) agree to ~1e-7 per
@@ -120,7 +122,7 @@ def test_sqp_solve_matches_reference_loop(oracle, N, iters, perturb):
         return qp
 
     for b in range(2):
-        ref, ref_status, ref_iters, _ = S.soft_sqp(oracle, W.QUADRUPED, N, xp[b], k, eps, mult, iters, qp=device_step(b))
+        ref, ref_status, ref_iters, _ = S.soft_sqp(oracle, mid, N, xp[b], k, eps, mult, iters, qp=device_step(b))
         assert (st[b, 0], st[b, 1]) == (ref_status, ref_iters)
         assert np.max(np.abs(got[b, :n] - ref[:n])) <= 1e-10 * np.max(np.abs(ref[:n]))
     # host-buffer entry point (MEM_HOST) and the SoftSQPOptimizer mirror give the same iterates
@@ -171,8 +173,8 @@ def test_sqp_solve_full_batch_properties():
     d2 = torch.from_numpy(xp0.copy()).cuda()
     s2, _ = m.sqp_solve(d2, opts)
     assert torch.equal(d2, d_xp) and torch.equal(s2, status)
-    # the unsupported models fail loudly
+    # F32 models fail loudly
     from ungar_b200 import _lib
-    q = ungar_b200.Model("quadrotor", 30, dtype="f64")
+    q = ungar_b200.Model("quadrotor", 30, dtype="f32")
     with pytest.raises(_lib.UngarB200Error):
-        q.sqp_solve(torch.zeros((1, q.n_xp), dtype=torch.float64, device="cuda"))
+        q.sqp_solve(torch.zeros((1, q.n_xp), dtype=torch.float32, device="cuda"))

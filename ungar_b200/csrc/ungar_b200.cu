@@ -18,6 +18,7 @@
 #include "sweep_tpn.cuh"
 #include "sweep_small.cuh"
 #include "qp_schur.cuh"
+#include "qp_riccati.cuh"
 #include "line_search.cuh"
 
 namespace {
@@ -565,9 +566,10 @@ int launch_barrier_t(ungar_b200_model& mdl, const void* z, int64_t ld_z, void* o
     return UNGAR_B200_OK;
 }
 
-// QP solve launch (qp_schur.cuh).  `skip_status` (may be null): trajectories whose status is not RUNNING are skipped.
-int launch_qp(ungar_b200_model& mdl, const void* rec, int64_t batch, int64_t ld_rec, void* steps, int64_t ld_steps, void* mult,
-              int64_t ld_mult, const int32_t* skip_status, cudaStream_t stream) {
+// QP solve launches.  `skip_status` (may be null): trajectories whose status is not RUNNING are skipped.
+// Quadruped: stage-wise Schur complement (qp_schur.cuh; the contact rows are extra equalities).
+int launch_qp_schur(ungar_b200_model& mdl, const void* rec, int64_t batch, int64_t ld_rec, void* steps, int64_t ld_steps, void* mult,
+                    int64_t ld_mult, const int32_t* skip_status, cudaStream_t stream) {
     using Q = ub::QpShape;
     if (int rc = mdl.ws_qp.reserve(size_t(batch) * (mdl.N + 1) * Q::WS_GROUP * sizeof(double))) return rc;
     static bool configured = false;
@@ -582,6 +584,37 @@ int launch_qp(ungar_b200_model& mdl, const void* rec, int64_t batch, int64_t ld_
     ++g_launches;
     UB_CUDA(cudaGetLastError());
     return UNGAR_B200_OK;
+}
+
+// Quadrotor, RC car: Riccati recursion (qp_riccati.cuh; only the initial condition and the defects are equalities).
+template <class Mdl>
+int launch_qp_riccati(ungar_b200_model& mdl, const void* rec, int64_t batch, int64_t ld_rec, void* steps, int64_t ld_steps, void* mult,
+                      int64_t ld_mult, const int32_t* skip_status, cudaStream_t stream) {
+    using R = ub::RiccatiShape<Mdl>;
+    if (int rc = mdl.ws_qp.reserve(size_t(batch) * mdl.N * R::WS_STAGE * sizeof(double))) return rc;
+    auto kernel = ub::qp_riccati_kernel<Mdl>;
+    static bool configured = false;
+    if (!configured) {
+        UB_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, R::SMEM_BYTES));
+        configured = true;
+    }
+    const unsigned grid = unsigned((batch + R::WARPS - 1) / R::WARPS);
+    kernel<<<grid, R::WARPS * 32, R::SMEM_BYTES, stream>>>(static_cast<const double*>(rec), ld_rec, static_cast<double*>(mdl.ws_qp.ptr),
+                                                           static_cast<double*>(steps), ld_steps, static_cast<double*>(mult), ld_mult,
+                                                           mdl.N, batch, mdl.rl, skip_status);
+    ++g_launches;
+    UB_CUDA(cudaGetLastError());
+    return UNGAR_B200_OK;
+}
+
+int launch_qp(ungar_b200_model& mdl, const void* rec, int64_t batch, int64_t ld_rec, void* steps, int64_t ld_steps, void* mult,
+              int64_t ld_mult, const int32_t* skip_status, cudaStream_t stream) {
+    switch (mdl.desc.kind) {
+        case UNGAR_B200_QUADROTOR: return launch_qp_riccati<ub::Quadrotor>(mdl, rec, batch, ld_rec, steps, ld_steps, mult, ld_mult, skip_status, stream);
+        case UNGAR_B200_RC_CAR: return launch_qp_riccati<ub::RcCar>(mdl, rec, batch, ld_rec, steps, ld_steps, mult, ld_mult, skip_status, stream);
+        case UNGAR_B200_QUADRUPED: return launch_qp_schur(mdl, rec, batch, ld_rec, steps, ld_steps, mult, ld_mult, skip_status, stream);
+    }
+    return fail(UNGAR_B200_EINVAL, "unknown model kind %d", mdl.desc.kind);
 }
 
 int check_options(const ungar_b200_sqp_options& o) {
@@ -827,8 +860,8 @@ int ungar_b200_kkt_blocks(ungar_b200_model* model, const void* xp, int64_t batch
 int ungar_b200_qp_solve(ungar_b200_model* model, const void* records_device, int64_t batch, int64_t ld_rec, void* steps,
                         int64_t ld_steps, void* multipliers, int64_t ld_multipliers, void* stream_) {
     if (!model) return fail(UNGAR_B200_EINVAL, "null model");
-    if (model->desc.kind != UNGAR_B200_QUADRUPED || model->desc.dtype != UNGAR_B200_F64)
-        return fail(UNGAR_B200_EUNSUPPORTED, "qp_solve is implemented for the quadruped problem in F64");
+    if (model->desc.dtype != UNGAR_B200_F64)
+        return fail(UNGAR_B200_EUNSUPPORTED, "qp_solve factorises in fp64: F64 models only (the reference computes in double, data_types.hpp:89)");
     if (batch < 0 || (batch > 0 && (!records_device || !steps))) return fail(UNGAR_B200_EINVAL, "null buffer");
     const ungar_b200_kkt_layout& L = model->layout;
     if (ld_rec < L.size || ld_steps < L.n_dec || (multipliers && ld_multipliers < L.m_eq))
@@ -863,8 +896,8 @@ int ungar_b200_line_search(ungar_b200_model* model, void* xp, int64_t batch, int
 int ungar_b200_sqp_solve(ungar_b200_model* model, void* xp, int64_t batch, int64_t ld_xp, const ungar_b200_sqp_options* options,
                          int32_t* status, void* info, int32_t mem, void* stream_) {
     if (!model || !options) return fail(UNGAR_B200_EINVAL, "null argument");
-    if (model->desc.kind != UNGAR_B200_QUADRUPED || model->desc.dtype != UNGAR_B200_F64)
-        return fail(UNGAR_B200_EUNSUPPORTED, "sqp_solve needs qp_solve: quadruped problem in F64");
+    if (model->desc.dtype != UNGAR_B200_F64)
+        return fail(UNGAR_B200_EUNSUPPORTED, "sqp_solve needs qp_solve and the line search: F64 models only");
     if (batch < 0 || (batch > 0 && (!xp || !status))) return fail(UNGAR_B200_EINVAL, "null buffer");
     if (mem != UNGAR_B200_MEM_DEVICE && mem != UNGAR_B200_MEM_HOST) return fail(UNGAR_B200_EINVAL, "unknown mem %d", mem);
     const ungar_b200_kkt_layout& L = model->layout;
