@@ -1,6 +1,6 @@
 // Minimal C++ user of the drop-in boundary: builds the quadruped NMPC problem (example/mpc/quadruped.example.cpp at
-// N = 30), evaluates its three functions in the reference's format at the example's initial guess and runs one batched
-// KKT sweep.  Build:  g++ -std=c++17 -Iinclude -Iungar_b200/include examples/kkt_sweep.cpp ungar_b200/libungar_b200.so
+// N = 30), evaluates its three functions in the reference's format at the example's initial guess, runs one batched
+// KKT sweep and one soft-SQP solve on the device.  Build:  g++ -std=c++17 -Iinclude -Iungar_b200/include examples/kkt_sweep.cpp ungar_b200/libungar_b200.so
 #include <cmath>
 #include <cstdio>
 #include <vector>
@@ -47,7 +47,16 @@ int main() {
         std::vector<double> rec(static_cast<std::size_t>(L.size));
         model.KktBlocks(xp.data(), 1, rec.data());
         std::printf("KKT record: %lld scalars, objective f = %.6f, barrier = %.6f\n", (long long)L.size, rec[L.cost], rec[L.cost + 1]);
-        return (defect < 1e-12 && std::fabs(g[13 + 13 * N + 3] - 0.38) < 1e-12) ? 0 : 1;
+        // one MPC solve like quadruped.example.cpp:444, :512-522: the measured base is 3 cm lower than the stance guess
+        std::vector<double> xq(xp);
+        xq[Rho + 22] = 0.35;
+        SoftSQPOptimizer optimizer{false, 1.0 / N, 4, 1.0, 1.0};
+        const std::vector<double> sol = optimizer.Optimize(model, xq);
+        const double* info = optimizer.LineSearchInfo().data();
+        std::printf("soft SQP: status %d after %d iterations, last step size %.4g, constraint violation %.3e, base height x_0 = %.4f\n",
+                    optimizer.Status()[0].status, optimizer.Status()[0].iterations, info[0], info[1], sol[2]);
+        const bool sqp_ok = optimizer.Status()[0].iterations >= 1 && sol[2] < 0.38 - 1e-4;  // x_0 moved towards the measurement
+        return (defect < 1e-12 && std::fabs(g[13 + 13 * N + 3] - 0.38) < 1e-12 && sqp_ok) ? 0 : 1;
     } catch (const std::exception& e) {
         std::fprintf(stderr, "%s\n", e.what());
         return 2;

@@ -126,33 +126,113 @@ def monolithic_qp(oracle, model: int, N: int, xp: np.ndarray, stiffness: float, 
 def solve_qp(P, q, A, g, delta: float = 1e-9):
     """argmin 1/2 d^T P d + q^T d  s.t.  A d = -g, via the quasi-definite KKT system (same delta as the CUDA kernel)."""
     n, m = P.shape[0], A.shape[0]
+    if m == 0:
+        return spla.spsolve(sp.csc_matrix(P), -q), np.zeros(0)
     K = sp.bmat([[P, A.T], [A, -delta * sp.identity(m)]], format="csc")
     sol = spla.spsolve(K, np.concatenate([-q, -g]))
     return sol[:n], sol[n:]
 
 
-def soft_sqp(oracle, model: int, N: int, xp: np.ndarray, stiffness: float, epsilon: float, multiplier: float = 1.0,
-             max_iterations: int = 10, params: LineSearchParameters = LineSearchParameters(), qp=None):
-    """SoftSQPOptimizer::Optimize for one trajectory.  ``qp(xp) -> d`` overrides the QP solve (tests pass the GPU step in to
-    isolate the line search).  Returns (xp_final, status, iterations, log) with one log entry per started iteration."""
-    s = oracle.sizes(model, N)
-    n = s["n_dec"]
-    xp = np.array(xp, dtype=np.float64)
-    merit = Merit(oracle, model, N, xp, stiffness, epsilon, multiplier)
+class OracleProblem:
+    """One trajectory of an example NLP problem (objective / equalities / inequalities Functions + relaxed barrier), evaluated by
+    the fp64 oracle.  ``x`` is the decision part; the parameters stay fixed."""
+
+    def __init__(self, oracle, model: int, N: int, xp: np.ndarray, stiffness: float, epsilon: float):
+        self.o, self.model, self.N = oracle, model, N
+        self.xp = np.array(xp, dtype=np.float64)
+        self.k, self.eps = stiffness, epsilon
+        self.n = oracle.sizes(model, N)["n_dec"]
+
+    def _full(self, x):
+        self.xp[:self.n] = x
+        return self.xp
+
+    def objective(self, x) -> float:
+        return float(self.o.evaluate(self.model, OBJECTIVE, self.N, self._full(x))[0])
+
+    def equalities(self, x):
+        return self.o.evaluate(self.model, EQUALITIES, self.N, self._full(x))
+
+    def inequalities(self, x):
+        return self.o.evaluate(self.model, INEQUALITIES, self.N, self._full(x))
+
+    def barrier(self, h):
+        return self.o.barrier(self.k, self.eps, h)
+
+    def qp_data(self, x):
+        """(P, q, A, g, grad f) of AssembleOSQPInstance at x."""
+        return monolithic_qp(self.o, self.model, self.N, self._full(x).copy(), self.k, self.eps)
+
+
+class DenseProblem:
+    """An NLP problem given by numpy callables (tests of the loop itself against test/optimization/soft_sqp.test.cpp):
+    f, grad f, hess f; g, J_g (or None: `hana::nothing`); h, J_h; the barrier comes from the oracle's restatement."""
+
+    def __init__(self, oracle, n, f, grad, hess, g=None, Jg=None, h=None, Jh=None, stiffness=100.0, epsilon=2e-5):
+        self.o, self.n, self.k, self.eps = oracle, n, stiffness, epsilon
+        self.f, self.grad, self.hess, self.g, self.Jg, self.h, self.Jh = f, grad, hess, g, Jg, h, Jh
+
+    def objective(self, x) -> float:
+        return float(self.f(x))
+
+    def equalities(self, x):
+        return np.atleast_1d(self.g(x)).astype(float) if self.g else np.zeros(0)
+
+    def inequalities(self, x):
+        return np.atleast_1d(self.h(x)).astype(float) if self.h else np.zeros(0)
+
+    def barrier(self, h):
+        return self.o.barrier(self.k, self.eps, h) if h.size else (0.0, np.zeros(0), np.zeros(0))
+
+    def qp_data(self, x):
+        n = self.n
+        Jh = np.atleast_2d(self.Jh(x)) if self.h else np.zeros((0, n))
+        Jg = np.atleast_2d(self.Jg(x)) if self.g else np.zeros((0, n))
+        _, dz, d2z = self.barrier(self.inequalities(x))
+        gf = np.asarray(self.grad(x), dtype=float)
+        P = np.triu(self.hess(x))
+        P = P + np.triu(P, 1).T + Jh.T @ np.diag(d2z) @ Jh + 1e-6 * np.eye(n)
+        return sp.csc_matrix(P), gf + Jh.T @ dz, sp.csc_matrix(Jg), self.equalities(x), gf
+
+
+def soft_sqp_loop(problem, x0: np.ndarray, multiplier: float = 1.0, max_iterations: int = 10,
+                  params: LineSearchParameters = LineSearchParameters(), qp=None):
+    """SoftSQPOptimizer::Optimize (soft_sqp.hpp:63-109) on a problem object.  Returns (x, status, iterations, log)."""
+    x = np.array(x0, dtype=np.float64)
+
+    def phi(w):  # soft_sqp.hpp:85-89
+        return problem.objective(w) + problem.barrier(problem.inequalities(w))[0]
+
+    def theta(w):  # soft_sqp.hpp:90-98
+        g = problem.equalities(w)
+        return multiplier * float(np.sqrt(np.dot(g, g)))
+
     status, iterations, log = RUNNING, 0, []
     for _ in range(max_iterations):
-        objective = merit.objective(xp[:n])
-        P, q, A, g, grad_f = monolithic_qp(oracle, model, N, xp, stiffness, epsilon)
-        d = qp(xp) if qp is not None else solve_qp(P, q, A, g)[0]
-        res, w_next = line_search(grad_f, d, merit.phi, merit.theta, xp[:n].copy(), params)
+        objective = problem.objective(x)
+        P, q, A, g, grad_f = problem.qp_data(x)
+        d = qp(x) if qp is not None else solve_qp(P, q, A, g)[0]
+        res, w_next = line_search(grad_f, d, phi, theta, x.copy(), params)
         iterations += 1
         log.append(dict(objective=objective, step=d, ls=res))
         if not res.accepted:
             status = LINE_SEARCH_FAILED
             break
-        xp[:n] = w_next
-        diff = merit.objective(xp[:n]) - objective
+        x = w_next
+        diff = problem.objective(x) - objective
         if diff < 0.0 and abs(diff) < 1e-6:
             status = CONVERGED
             break
-    return xp, status, iterations, log
+    return x, status, iterations, log
+
+
+def soft_sqp(oracle, model: int, N: int, xp: np.ndarray, stiffness: float, epsilon: float, multiplier: float = 1.0,
+             max_iterations: int = 10, params: LineSearchParameters = LineSearchParameters(), qp=None):
+    """SoftSQPOptimizer::Optimize for one trajectory of an example problem.  ``qp(xp) -> d`` overrides the QP solve (tests pass
+    the GPU step in to isolate the line search).  Returns (xp_final, status, iterations, log)."""
+    prob = OracleProblem(oracle, model, N, xp, stiffness, epsilon)
+    qp_x = (lambda x: qp(prob._full(x).copy())) if qp is not None else None
+    x, status, iterations, log = soft_sqp_loop(prob, np.array(xp[:prob.n], dtype=np.float64), multiplier, max_iterations, params, qp_x)
+    out = np.array(xp, dtype=np.float64)
+    out[:prob.n] = x
+    return out, status, iterations, log

@@ -40,3 +40,4 @@ def test_cpp_example_reproduces_the_stance_known_answers(tmp_path):
     proc = subprocess.run([compile_example(tmp_path)], capture_output=True, text=True)
     assert proc.returncode == 0, proc.stdout + proc.stderr
     assert "nnz(J_g)=14167" in proc.stdout and "foot row = 0.38" in proc.stdout
+    assert "soft SQP: status" in proc.stdout

@@ -10,9 +10,14 @@
 // `ungar_b200::Model` stands where MakeFunction x 3 + MakeNLPProblem stand in the examples
 // (quadruped.example.cpp:343-363) and adds the batched KKT sweep that replaces
 // SoftSQPOptimizer::AssembleOSQPInstance (optimization/soft_sqp.hpp:141-158).
+//
+// `ungar_b200::SoftSQPOptimizer` keeps the constructor arguments and the `Optimize(nlpProblem, xp)` call of
+// `Ungar::SoftSQPOptimizer` (optimization/soft_sqp.hpp:42-109); the whole loop (KKT sweep, QP solve, backtracking line
+// search) runs on the device.
 #pragma once
 
 #include <cstdint>
+#include <cstdio>
 #include <stdexcept>
 #include <string>
 #include <utility>
@@ -128,6 +133,8 @@ class Model {
         ungar_b200_model_desc desc{kind, horizon, dtype_of<Real>::value, device, barrierStiffness, barrierEpsilon};
         check(ungar_b200_model_create(&desc, &_handle));
         check(ungar_b200_kkt_layout_get(_handle, &_layout));
+        _stiffness = barrierStiffness;
+        _epsilon   = barrierEpsilon;
     }
     ~Model() { ungar_b200_model_destroy(_handle); }
     Model(const Model&)            = delete;
@@ -154,10 +161,66 @@ class Model {
                                   UNGAR_B200_MEM_HOST, stream));
     }
     ungar_b200_model* handle() const { return _handle; }
+    double BarrierStiffness() const { return _stiffness; }
+    double BarrierEpsilon() const { return _epsilon; }
 
   private:
     ungar_b200_model* _handle = nullptr;
     ungar_b200_kkt_layout _layout{};
+    double _stiffness = 0.0, _epsilon = 0.0;
+};
+
+// Mirror of Ungar::SoftSQPOptimizer (optimization/soft_sqp.hpp:42-61).  The relaxed barrier (stiffness, epsilon) is part of
+// the model handle here — the reference JIT-compiles it into a Function of its own on first use (soft_sqp.hpp:114-138, :162) —
+// so Optimize checks that both agree.  Only the POLY barrier exists (the reference's default, soft_sqp.hpp:49).
+class SoftSQPOptimizer {
+  public:
+    struct TrajectoryStatus {
+        std::int32_t status;      // ungar_b200_sqp_status
+        std::int32_t iterations;  // iterations started
+    };
+
+    explicit SoftSQPOptimizer(bool verbose, double constraintViolationMultiplier = 1.0, index_t maxIterations = 10,
+                              double stiffness = 100.0, double epsilon = 2e-5)
+        : _verbose(verbose), _stiffness(stiffness), _epsilon(epsilon) {
+        check(ungar_b200_sqp_options_default(&_options));
+        _options.max_iterations                  = static_cast<std::int32_t>(maxIterations);
+        _options.constraint_violation_multiplier = constraintViolationMultiplier;
+    }
+    ungar_b200_sqp_options& Options() { return _options; }  // BacktrackingLineSearch::SetParameters equivalent
+
+    // xp: `batch` stacked flat vectors [X | U | parameters] (host).  Returns the optimised decision variables, `batch` rows of
+    // n_dec (the reference returns _cache.xp.head(n_dec), soft_sqp.hpp:108).
+    std::vector<double> Optimize(Model<double>& nlpProblem, const std::vector<double>& xp, index_t batch = 1) {
+        if (nlpProblem.BarrierStiffness() != _stiffness || nlpProblem.BarrierEpsilon() != _epsilon)
+            throw std::runtime_error("ungar_b200: the model was created with a different barrier than this optimizer");
+        const index_t n = nlpProblem.VariableSize(), nDec = nlpProblem.layout().n_dec;
+        if (static_cast<index_t>(xp.size()) != batch * n) throw std::runtime_error("ungar_b200: xp has the wrong size");
+        std::vector<double> work(xp);
+        _status.assign(static_cast<std::size_t>(batch), TrajectoryStatus{0, 0});
+        _info.assign(static_cast<std::size_t>(batch) * UNGAR_B200_LINE_SEARCH_INFO_SIZE, 0.0);
+        check(ungar_b200_sqp_solve(nlpProblem.handle(), work.data(), batch, n, &_options, reinterpret_cast<std::int32_t*>(_status.data()),
+                                   _info.data(), UNGAR_B200_MEM_HOST, nullptr));
+        std::vector<double> x(static_cast<std::size_t>(batch * nDec));
+        for (index_t b = 0; b < batch; ++b)
+            for (index_t i = 0; i < nDec; ++i) x[static_cast<std::size_t>(b * nDec + i)] = work[static_cast<std::size_t>(b * n + i)];
+        if (_verbose)
+            for (index_t b = 0; b < batch; ++b)
+                std::fprintf(stderr, "soft SQP [%lld]: status %d after %d iteration(s), last step size %g\n", (long long)b,
+                             _status[static_cast<std::size_t>(b)].status, _status[static_cast<std::size_t>(b)].iterations,
+                             _info[static_cast<std::size_t>(b) * UNGAR_B200_LINE_SEARCH_INFO_SIZE]);
+        return x;
+    }
+    const std::vector<TrajectoryStatus>& Status() const { return _status; }
+    // [batch][8] report of the last line search: alpha, theta, phi, f | theta, phi, f before the step, grad f . dw
+    const std::vector<double>& LineSearchInfo() const { return _info; }
+
+  private:
+    bool _verbose;
+    double _stiffness, _epsilon;
+    ungar_b200_sqp_options _options{};
+    std::vector<TrajectoryStatus> _status;
+    std::vector<double> _info;
 };
 
 }  // namespace ungar_b200
