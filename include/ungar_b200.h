@@ -205,6 +205,70 @@ int ungar_b200_line_search(ungar_b200_model* model, void* xp, int64_t batch, int
 int ungar_b200_sqp_solve(ungar_b200_model* model, void* xp, int64_t batch, int64_t ld_xp,
                          const ungar_b200_sqp_options* options, int32_t* status, void* info, int32_t mem, void* stream);
 
+/* ---------------------------------------------------------------------------------------------------------------
+ * Generic path: a recorded operation tape of an arbitrary user lambda, evaluated on the GPU.
+ *
+ * This is the seam of the reference's own plugin boundary: Ungar::Autodiff::Function calls a
+ * CppAD::cg::GenericModel<double> loaded from a JIT-compiled library (autodiff/function.hpp:364-365, :433-438,
+ * :505-514).  ungar_b200/include/cppad/cg.hpp supplies that class (and the tracing AD scalar that records the
+ * tape) on top of the entry points below, so the reference's unchanged function.hpp / tests / examples evaluate
+ * their lambdas on the device.  Where the reference tapes -> generates C -> runs gcc -> dlopens
+ * (function.hpp:453-503), a tape handle is analysed once on the host (dead-node elimination, slot allocation by
+ * liveness, structural sparsity by dependency propagation, column colouring) and then interpreted by a register
+ * machine kernel, one thread per (xp vector, seed direction).
+ *
+ * Node encoding: node i may only reference nodes < i.  INDEP: a = index of the independent.  CONST: k = value.
+ * Unary ops: a.  Binary ops: a, b (POW: a^b, ATAN2: atan2(a, b)).  Conditionals CppAD::CondExp{Lt,Le,Gt,Ge,Eq}(a, b,
+ * c, d): c if a OP b else d.  `dependents[r]` = node id of dependent r, or -1 for a constant dependent with value
+ * `dependent_constants[r]`. */
+enum ungar_b200_tape_op {
+    UNGAR_B200_OP_INDEP = 0, UNGAR_B200_OP_CONST, UNGAR_B200_OP_ADD, UNGAR_B200_OP_SUB, UNGAR_B200_OP_MUL, UNGAR_B200_OP_DIV,
+    UNGAR_B200_OP_NEG, UNGAR_B200_OP_SQRT, UNGAR_B200_OP_SIN, UNGAR_B200_OP_COS, UNGAR_B200_OP_TAN, UNGAR_B200_OP_ATAN,
+    UNGAR_B200_OP_ACOS, UNGAR_B200_OP_ASIN, UNGAR_B200_OP_EXP, UNGAR_B200_OP_LOG, UNGAR_B200_OP_ABS, UNGAR_B200_OP_POW,
+    UNGAR_B200_OP_ATAN2, UNGAR_B200_OP_CLT, UNGAR_B200_OP_CLE, UNGAR_B200_OP_CGT, UNGAR_B200_OP_CGE, UNGAR_B200_OP_CEQ,
+    UNGAR_B200_OP_COUNT
+};
+
+typedef struct ungar_b200_tape_node {
+    uint8_t op; /* ungar_b200_tape_op */
+    int32_t a, b, c, d;
+    double k;
+} ungar_b200_tape_node;
+
+typedef struct ungar_b200_tape ungar_b200_tape;
+
+/* CppAD::ADFun + ModelCSourceGen + compile + dlopen (function.hpp:456-503): host-side analysis only, no device work
+ * (the program is uploaded on first evaluation), so sizes and sparsity are available without a GPU. */
+int ungar_b200_tape_create(const ungar_b200_tape_node* nodes, int64_t n_nodes, int64_t n_independent,
+                           const int32_t* dependents, const double* dependent_constants, int64_t n_dependent,
+                           int32_t device, ungar_b200_tape** out);
+int ungar_b200_tape_destroy(ungar_b200_tape* tape);
+/* info[6] = independents, dependents, nodes kept after dead-node elimination, scratch slots, Jacobian colours,
+ * Hessian directions (the last two are 0 until the element sets below are chosen). */
+int ungar_b200_tape_info(const ungar_b200_tape* tape, int64_t* info);
+
+/* GenericModel::JacobianSparsitySet (function.hpp:531): structural pattern over ALL independents [x; p], row-major,
+ * columns ascending.  GenericModel::HessianSparsitySet (:559): full symmetric pattern, union over the dependents. */
+int ungar_b200_tape_jacobian_pattern(ungar_b200_tape* tape, const int64_t** rows, const int64_t** cols, int64_t* nnz);
+int ungar_b200_tape_hessian_pattern(ungar_b200_tape* tape, const int64_t** rows, const int64_t** cols, int64_t* nnz);
+
+/* ModelCSourceGen::setCustomSparseJacobianElements / setCustomSparseHessianElements (function.hpp:549, :573): the
+ * elements the evaluation calls return, in this order (the reference passes the structural pattern with the
+ * parameter columns trimmed, and for the Hessian only the upper triangle).  Every element must be structurally
+ * non-zero.  NULL rows selects the whole structural pattern. */
+int ungar_b200_tape_set_jacobian_elements(ungar_b200_tape* tape, const int64_t* rows, const int64_t* cols, int64_t nnz);
+int ungar_b200_tape_set_hessian_elements(ungar_b200_tape* tape, const int64_t* rows, const int64_t* cols, int64_t nnz);
+
+/* GenericModel::ForwardZero / SparseJacobian / SparseHessian (function.hpp:186-189, :224-228, :252-257) for `batch`
+ * vectors x[b, 0:n_independent] (stride ld_x); F64; host or device buffers per `mem` like every other entry point.
+ * `weights` (HOST pointer, n_dependent values; NULL = all ones): the Hessian is that of sum_r weights[r] * y_r. */
+int ungar_b200_tape_forward_zero(ungar_b200_tape* tape, const double* x, int64_t batch, int64_t ld_x, double* y,
+                                 int64_t ld_y, int32_t mem, void* stream);
+int ungar_b200_tape_sparse_jacobian(ungar_b200_tape* tape, const double* x, int64_t batch, int64_t ld_x, double* vals,
+                                    int64_t ld_vals, int32_t mem, void* stream);
+int ungar_b200_tape_sparse_hessian(ungar_b200_tape* tape, const double* x, const double* weights, int64_t batch,
+                                   int64_t ld_x, double* vals, int64_t ld_vals, int32_t mem, void* stream);
+
 /* Device-side timing of the dominant kernel (the KKT sweep): when enabled, every sweep launch is bracketed by
  * CUDA events on the launching stream; ungar_b200_sweep_times synchronises and returns up to `cap` most recent
  * durations in milliseconds (oldest first) and clears the ring. */

@@ -10,13 +10,15 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import ungar_b200
 from ungar_b200 import workloads as W
 
-N, B = 100, 1024
-m = ungar_b200.Model("quadruped", N, dtype="f64", barrier=(1.0, 1.0))
-xp0 = torch.from_numpy(W.synthetic_batch(2, N, B)).cuda()
+name = sys.argv[1] if len(sys.argv) > 1 else "quadruped"
+N, B = {"quadruped": (100, 1024), "quadrotor": (30, 4096), "rc_car": (60, 8192)}[name]
+mid = W.MODEL_IDS[name]
+m = ungar_b200.Model(name, N, dtype="f64", barrier=ungar_b200.EXAMPLE_BARRIER[mid])
+xp0 = torch.from_numpy(W.synthetic_batch(mid, N, B)).cuda()
 xp = xp0.clone()
 rec = m.kkt_blocks(xp)
 steps, _ = m.qp_solve(rec, want_multipliers=False)
-opts = m.sqp_options(max_iterations=4, constraint_violation_multiplier=1.0 / N)
+opts = m.sqp_options(max_iterations=4, constraint_violation_multiplier=1.0 if name == "quadrotor" else 1.0 / N)
 torch.cuda.synchronize()
 
 
@@ -34,6 +36,7 @@ def timed(fn, reps=10, setup=None):
     return tot / reps
 
 
+print(name)
 print("kkt_blocks  %d x N=%d: %.3f ms" % (B, N, timed(lambda: m.kkt_blocks(xp0, rec))))
 print("qp_solve    %d x N=%d: %.3f ms" % (B, N, timed(lambda: m.qp_solve(rec, steps, want_multipliers=False))))
 info = m.line_search(xp, steps, opts)

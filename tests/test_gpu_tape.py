@@ -1,0 +1,215 @@
+"""Generic tape path on the GPU (ungar_b200_tape_*, csrc/tape_machine.cuh) — parity anchors:
+
+  * the reference's own known answers for Function: test/autodiff/function.test.cpp:33-59 (ApproximateExponentialMap), :70-96
+    (y = [p |x|^2, 2 x0^2], J = [[2 p x], [4 x0, 0, 0, 0]]), :120-136 (H = 2 p I), each at 1024 random points like the reference;
+  * symbolic differentiation (sympy) of a function that uses every tape operation, first and second order;
+  * the reference's OWN MPC lambdas: the tapes that oracle/_ref recorded from the unchanged example sources, evaluated by the
+    register machine and compared with the restated oracle and with the hand-written kernels (three independent computations).
+"""
+import glob
+import os
+
+import numpy as np
+import pytest
+
+from ungar_b200 import EXAMPLE_BARRIER
+from ungar_b200 import autodiff as A
+from ungar_b200 import workloads as W
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_function_test_known_answers():
+    rng = np.random.default_rng(0)
+    f = A.MakeFunction(A.Blueprint(lambda xp: [xp[4] * sum(x * x for x in xp[:4]), 2.0 * A.pow(xp[0], 2)], 4, 1, "jacobian_test", A.JACOBIAN))
+    xp = rng.uniform(-1, 1, (1024, 5))
+    y = f(xp)
+    x, p = xp[:, :4], xp[:, 4]
+    assert np.allclose(y[:, 0], p * (x * x).sum(1), rtol=1e-14) and np.allclose(y[:, 1], 2 * x[:, 0] ** 2, rtol=1e-14)
+    J = f.JacobianValues(xp)  # order (0,0) (0,1) (0,2) (0,3) (1,0)
+    assert np.allclose(J[:, :4], 2 * p[:, None] * x, rtol=1e-14, atol=1e-15) and np.allclose(J[:, 4], 4 * x[:, 0], rtol=1e-14)
+    Jm = f.Jacobian(xp[3]).toarray()
+    assert np.allclose(Jm, np.vstack([2 * p[3] * x[3], [4 * x[3, 0], 0, 0, 0]]))
+    h = A.MakeFunction(A.Blueprint(lambda xp: [xp[4] * sum(x * x for x in xp[:4])], 4, 1, "hessian_test", A.ALL))
+    H = h.HessianValues(xp)
+    assert np.allclose(H, 2 * p[:, None] * np.ones((1, 4)), rtol=1e-13, atol=1e-14)
+    assert np.allclose(h.Hessian(0, xp[5]).toarray(), 2 * p[5] * np.eye(4))
+
+
+def approximate_exponential_map(v):  # Utils::ApproximateExponentialMap (utils/utils.hpp:731-749)
+    n = A.sqrt(v[0] * v[0] + v[1] * v[1] + v[2] * v[2] + 2.220446049250313e-16)
+    k = A.sin(0.5 * n) / n
+    return [v[0] * k, v[1] * k, v[2] * k, A.cos(0.5 * n)]
+
+
+def test_exponential_map_known_answers():
+    f = A.MakeFunction(A.Blueprint(approximate_exponential_map, 3, 0, "exponential_map_test", A.JACOBIAN))
+    assert np.allclose(f(np.zeros(3)), [0, 0, 0, 1], atol=1e-8)
+    assert np.allclose(f.Jacobian(np.zeros(3)).toarray(), np.vstack([0.5 * np.eye(3), np.zeros((1, 3))]), atol=1e-7)
+    v = np.random.default_rng(1).uniform(-1, 1, (1024, 3))
+    th = np.linalg.norm(v, axis=1, keepdims=True)
+    exact = np.hstack([v / th * np.sin(th / 2), np.cos(th / 2)])
+    assert np.allclose(f(v), exact, atol=1e-8)
+
+
+def zoo(ops, xp):
+    """One function through every tape operation; `ops` is the namespace (ungar_b200.autodiff or a sympy adaptor)."""
+    a, b, c, d, p = xp
+    u = ops.sin(a * b) + ops.cos(c) * ops.exp(-d * d) + ops.sqrt(a * a + 1.5) / (b * b + 2.0)
+    w = ops.atan(c * d) + ops.tan(0.3 * a) + ops.log(b * b + c * c + 1.0) + ops.acos(0.5 * ops.sin(d)) + ops.asin(0.4 * ops.cos(a))
+    z = ops.atan2(a + 2.0, b * c + 3.0) + ops.pow(a * a + 1.0, 1.7) + ops.pow(b, 3) - ops.abs_(c - 0.1) * d
+    return [p * u + w * z, u - z, ops.CondExpGt(a, b, a * a * c, ops.sin(b) * d) + ops.CondExpLe(c, d, c * d * d, a)]
+
+
+class SympyOps:
+    def __init__(self):
+        import sympy as sp
+
+        self.sp = sp
+        for name in ("sin", "cos", "tan", "exp", "log", "sqrt", "atan", "acos", "asin", "atan2"):
+            setattr(self, name, getattr(sp, name))
+
+    def pow(self, x, e): return x ** e  # noqa: E704
+    def abs_(self, x): return self.sp.sqrt(x * x)  # noqa: E704  smooth away from 0, derivative sign(x) like CppAD
+    def CondExpGt(self, a, b, t, f): return self.sp.Piecewise((t, a > b), (f, True))  # noqa: E704
+    def CondExpLe(self, a, b, t, f): return self.sp.Piecewise((t, a <= b), (f, True))  # noqa: E704
+
+
+def test_every_operation_against_symbolic_derivatives():
+    import sympy as sp
+
+    syms = sp.symbols("a b c d p")
+    exprs = zoo(SympyOps(), syms)
+    J_sym = [[sp.diff(e, s) for s in syms[:4]] for e in exprs]
+    f = A.MakeFunction(A.Blueprint(lambda xp: zoo(A, xp), 4, 1, "zoo", A.JACOBIAN))
+    rows, cols = f.JacobianSparsity()
+    assert rows.size == 12  # dense 3 x 4
+    rng = np.random.default_rng(2)
+    xp = rng.uniform(-0.9, 0.9, (64, 5))
+    y, J = f(xp), f.JacobianValues(xp)
+    fy = sp.lambdify(syms, exprs, "numpy")
+    fJ = sp.lambdify(syms, J_sym, "numpy")
+    for b in range(64):
+        assert np.allclose(y[b], np.array(fy(*xp[b]), dtype=float), rtol=1e-12, atol=1e-13)
+        ref = np.array(fJ(*xp[b]), dtype=float)
+        assert np.allclose(J[b], ref[rows, cols], rtol=1e-11, atol=1e-12), (b, J[b], ref[rows, cols])
+    # second order, one scalar function at a time (weights select the dependent)
+    for i in range(3):
+        g = A.MakeFunction(A.Blueprint(lambda xp, i=i: [zoo(A, xp)[i]], 4, 1, f"zoo{i}", A.ALL))
+        hr, hc = g.HessianSparsity()
+        H_sym = sp.hessian(exprs[i], syms[:4])
+        fH = sp.lambdify(syms, H_sym, "numpy")
+        H = g.HessianValues(xp)
+        for b in range(64):
+            ref = np.array(fH(*xp[b]), dtype=float)
+            dense = np.zeros((4, 4))
+            dense[hr, hc] = H[b]
+            assert np.allclose(dense, np.triu(ref), rtol=1e-10, atol=1e-11), (i, b)
+    # the whole weighted sum through the raw tape interface: H(sum_r w_r y_r)
+    t = f._tape
+    r, c = t.hessian_pattern()
+    t.set_hessian_elements(r, c)
+    w = np.array([0.3, -1.2, 2.0])
+    Hw = t.sparse_hessian(xp[:4], w)
+    Hs = sp.lambdify(syms, sp.hessian(sum(wi * e for wi, e in zip(w, exprs)), syms), "numpy")
+    for b in range(4):
+        ref = np.array(Hs(*xp[b]), dtype=float)
+        assert np.allclose(Hw[b], ref[r, c], rtol=1e-10, atol=1e-11)
+
+
+def test_cppad_semantics_at_kinks_and_branches():
+    f = A.MakeFunction(A.Blueprint(lambda xp: [A.abs_(xp[0]), A.CondExpLt(xp[0], xp[1], xp[0] * xp[0], 3.0 * xp[1])], 2, 0, "kinks", A.JACOBIAN))
+    J = f.JacobianValues(np.array([[0.0, 1.0], [2.0, 1.0], [-2.0, 1.0]]))  # pattern: (0,0) (1,0) (1,1)
+    assert J[0].tolist() == [0.0, 0.0, 0.0]   # abs'(0) = 0; branch x0^2 at x0 = 0
+    assert J[1].tolist() == [1.0, 0.0, 3.0]   # the branch is chosen at the EVALUATION point, not at the taping point
+    assert J[2].tolist() == [-1.0, -4.0, 0.0]
+
+
+def test_device_buffers_and_batch_consistency():
+    import torch
+
+    f = A.MakeFunction(A.Blueprint(lambda xp: zoo(A, xp), 4, 1, "zoo", A.JACOBIAN))
+    xp = np.random.default_rng(3).uniform(-0.9, 0.9, (300, 5))
+    d = torch.from_numpy(xp).cuda()
+    Jd = f.JacobianValues(d)
+    torch.cuda.synchronize()
+    Jh = f.JacobianValues(xp)
+    assert np.array_equal(Jd.cpu().numpy(), Jh)
+    one = np.stack([f.JacobianValues(xp[b]) for b in (0, 17, 299)])
+    assert np.array_equal(one, Jh[[0, 17, 299]])
+
+
+# ---------------------------------------------------------------------------------------------------------------------------
+# The reference's own lambdas, as taped by oracle/_ref from the unchanged example sources
+# ---------------------------------------------------------------------------------------------------------------------------
+def load_reference_tape(path):
+    """Tape file written by oracle/refshim (CppAD-compatible tracing of the reference's lambdas): header, nodes, dependents."""
+    raw = open(path, "rb").read()
+    magic, nn, nd, ni, flags = np.frombuffer(raw, dtype=np.int64, count=5)
+    assert int(magic) == 0x32455041545F4255
+    off = 40
+    nodes = np.frombuffer(raw, dtype=A.NODE_DTYPE, count=int(nn), offset=off)
+    off += int(nn) * 32
+    dep_id = np.frombuffer(raw, dtype=np.int32, count=int(nd), offset=off)
+    off += int(nd) * 4
+    dep_const = np.frombuffer(raw, dtype=np.float64, count=int(nd), offset=off)
+    return nodes, int(ni), dep_id, dep_const
+
+
+def tape_path(config, function):
+    hits = glob.glob(os.path.join(ROOT, "oracle", "_ref", "tapes", config, function, "cppad_cg", "*_lib.so"))
+    return hits[0] if hits else None
+
+
+@pytest.mark.parametrize("name,N,batch", [("quadrotor", 30, 16), ("rc_car", 60, 16), ("quadruped", 30, 8), ("quadruped", 100, 2)])
+def test_reference_lambda_tapes_on_the_register_machine(oracle, name, N, batch):
+    import ungar_b200
+
+    mid = W.MODEL_IDS[name]
+    config = f"{name}_N{N}"
+    if tape_path(config, f"{name}_mpc_eqs") is None:
+        pytest.skip("oracle/_ref tapes were not built (needs /root/reference at build time)")
+    s = W.sizes(mid, N)
+    nx = s["n_dec"]
+    xp = W.synthetic_batch(mid, N, batch, seed=11)
+    model = ungar_b200.Model(name, N, dtype="f64", barrier=EXAMPLE_BARRIER[mid])
+    hand = {0: model.objective, 1: model.equalityConstraints, 2: model.inequalityConstraints}
+    for fn, suffix in ((0, "obj"), (1, "eqs"), (2, "ineqs")):
+        nodes, ni, dep_id, dep_const = load_reference_tape(tape_path(config, f"{name}_mpc_{suffix}"))
+        assert ni == s["n_xp"]
+        t = A.TapeHandle(nodes, ni, dep_id, dep_const)
+        y = t.forward_zero(xp)
+        ref_y = np.stack([oracle.evaluate(mid, fn, N, xp[b]) for b in range(batch)])
+        scale = max(1.0, np.max(np.abs(xp[:, :nx])))
+        assert np.max(np.abs(y - ref_y)) <= 1e-12 * max(scale, np.max(np.abs(ref_y)))
+        # Jacobian: structural pattern trimmed like function.hpp:529-550 must equal the oracle's, values to rounding
+        r, c = t.jacobian_pattern()
+        keep = c < nx
+        r, c = r[keep], c[keep]
+        t.set_jacobian_elements(r, c)
+        o_r, o_c, _ = oracle.jacobian(mid, fn, N, xp[0])
+        assert np.array_equal(r, o_r) and np.array_equal(c, o_c)
+        J = t.sparse_jacobian(xp)
+        for b in (0, batch - 1):
+            ref_J = oracle.jacobian(mid, fn, N, xp[b])[2]
+            assert np.max(np.abs(J[b] - ref_J)) <= 1e-11 * max(1.0, np.max(np.abs(ref_J))), (suffix, b)
+        # ... and the hand-written kernels agree with the register machine (same reference-format arrays)
+        Jk = hand[fn].JacobianValues(xp[:2])
+        hr, hc = hand[fn].JacobianSparsity()
+        assert np.array_equal(hr, r) and np.array_equal(hc, c)
+        assert np.max(np.abs(Jk - J[:2])) <= 1e-9 * max(1.0, np.max(np.abs(J[:2])))
+        if fn == 0:  # objective Hessian, upper triangle of the x-x block (function.hpp:552-574)
+            r2, c2 = t.hessian_pattern()
+            keep = (r2 < nx) & (c2 < nx) & (c2 >= r2)
+            r2, c2 = r2[keep], c2[keep]
+            t.set_hessian_elements(r2, c2)
+            H = t.sparse_hessian(xp[:2])
+            o_r, o_c, o_v = oracle.hessian(mid, N, xp[0])
+            got = {(int(i), int(j)): v for i, j, v in zip(r2, c2, H[0])}
+            ref = {(int(i), int(j)): v for i, j, v in zip(o_r, o_c, o_v)}
+            assert set(ref) <= set(got)  # the structural pattern may only be a superset of the oracle's
+            for key, v in got.items():
+                assert abs(v - ref.get(key, 0.0)) <= 1e-10 * max(1.0, abs(ref.get(key, 0.0))), key
+        info = t.info()
+        assert info["slots"] < 0.2 * info["live_nodes"] + 64  # liveness-based slots: the scratch is far smaller than the tape

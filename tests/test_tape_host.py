@@ -1,0 +1,87 @@
+"""Host side of the generic tape path (no GPU needed): tracing scalar, tape analysis in ungar_b200_tape_create, structural sparsity,
+parameter trimming and colouring.  Known patterns: test/autodiff/function.test.cpp:70-96 (J = [[2 p x], [4 x0, 0, 0, 0]]), :120-136
+(H = 2 p I)."""
+import ctypes
+
+import numpy as np
+import pytest
+
+from ungar_b200 import _lib
+from ungar_b200 import autodiff as A
+
+
+def norm2_times_p(xp):
+    x, p = xp[:4], xp[4]
+    return p * (x[0] * x[0] + x[1] * x[1] + x[2] * x[2] + x[3] * x[3])
+
+
+def test_reference_test_functions_have_the_reference_patterns():
+    f = A.MakeFunction(A.Blueprint(lambda xp: [norm2_times_p(xp), 2.0 * A.pow(xp[0], 2)], 4, 1, "jacobian_test", A.JACOBIAN))
+    assert (f.IndependentVariableSize(), f.ParameterSize(), f.DependentVariableSize()) == (4, 1, 2)
+    rows, cols = f.JacobianSparsity()
+    assert rows.tolist() == [0, 0, 0, 0, 1] and cols.tolist() == [0, 1, 2, 3, 0]  # parameter column trimmed (function.hpp:529-550)
+    assert f.ImplementsJacobian() and not f.ImplementsHessian()
+    h = A.MakeFunction(A.Blueprint(lambda xp: [norm2_times_p(xp)], 4, 1, "hessian_test", A.ALL))
+    rows, cols = h.HessianSparsity()
+    assert rows.tolist() == [0, 1, 2, 3] and cols.tolist() == [0, 1, 2, 3]  # upper triangle of the x-x block (function.hpp:552-574)
+    full_r, full_c = h._tape.hessian_pattern()  # over all independents: x_i interacts with p
+    assert {(0, 4), (4, 0), (3, 4)} <= set(zip(full_r.tolist(), full_c.tolist())) and (4, 4) not in set(zip(full_r.tolist(), full_c.tolist()))
+    # a vector-valued function has no Hessian (function.hpp:136-137)
+    v = A.MakeFunction(A.Blueprint(lambda xp: [xp[0] * xp[1], xp[1]], 2, 0, "vec", A.ALL))
+    assert not v.ImplementsHessian()
+    with pytest.raises(_lib.UngarB200Error):
+        v.HessianValues(np.zeros(2))
+
+
+def test_folding_rules_and_dead_nodes():
+    def f(xp):
+        x, y = xp
+        dead = A.sin(x) * A.cos(y)  # noqa: F841  never reaches a dependent
+        return [x * 0.0 + y * 1.0, (x + 0.0) / 1.0, 0.0 / x, A.pow(x, 3), 2.0 * 3.0, A.CondExpGt(1.0, 0.0, x, y)]
+    nodes, deps, consts = A.record(f, [0.5, 0.7])
+    ops = nodes["op"].tolist()
+    # y*1 -> y, x*0 -> 0, 0 + y -> y; (x+0)/1 -> x; 0/x -> 0; x^3 = two multiplications; 6 is a parameter; CondExp decided by parameters
+    assert deps[0] == 1 and deps[1] == 0 and deps[2] == -1 and consts[2] == 0.0 and deps[4] == -1 and consts[4] == 6.0 and deps[5] == 0
+    assert ops.count(A.OP_MUL) == 1 + 2 and ops.count(A.OP_SIN) == 1  # the dead product + x*x, (x*x)*x
+    t = A.TapeHandle(nodes, 2, deps, consts)
+    info = t.info()
+    assert info["live_nodes"] == 2 + 2  # the two independents and the two products of x^3; sin / cos / their product are eliminated
+    rows, cols = t.jacobian_pattern()
+    assert list(zip(rows.tolist(), cols.tolist())) == [(0, 1), (1, 0), (3, 0), (5, 0)]
+
+
+def test_conditional_pattern_is_the_union_of_both_branches():
+    f = A.MakeFunction(A.Blueprint(lambda xp: [A.CondExpLt(xp[0], xp[1], xp[2] * xp[2], A.sin(xp[3]))], 4, 0, "cond", A.ALL))
+    assert f.JacobianSparsity()[1].tolist() == [2, 3]  # the compared values carry no derivative
+    assert list(zip(*[a.tolist() for a in f.HessianSparsity()])) == [(2, 2), (3, 3)]
+
+
+def test_colouring_separates_columns_that_share_a_row():
+    n = 40
+
+    def chain(xp):  # banded: row k touches x_k, x_{k+1}, x_{k+2}
+        return [xp[k] * xp[k + 1] + A.sin(xp[k + 2]) for k in range(n - 2)]
+    f = A.MakeFunction(A.Blueprint(chain, n, 0, "banded", A.JACOBIAN))
+    info = f.tape_info()
+    assert info["jacobian_colors"] == 3 and info["slots"] <= 8  # bandwidth 3 -> 3 directions; liveness keeps the scratch tiny
+    rows, cols = f.JacobianSparsity()
+    assert rows.size == 3 * (n - 2)
+
+
+def test_tape_validation_errors():
+    lib = _lib.load()
+    nodes = np.zeros(2, dtype=A.NODE_DTYPE)
+    nodes[0] = (A.OP_INDEP, 0, -1, -1, -1, 0.0)
+    nodes[1] = (A.OP_ADD, 0, 1, -1, -1, 0.0)  # operand 1 is the node itself: not yet defined
+    deps = np.array([1], dtype=np.int32)
+    h = ctypes.c_void_p()
+    assert lib.ungar_b200_tape_create(nodes.ctypes.data, 2, 1, deps.ctypes.data, None, 1, 0, ctypes.byref(h)) == _lib.EINVAL
+    assert b"operand out of range" in lib.ungar_b200_last_error()
+    nodes[1] = (77, 0, 0, -1, -1, 0.0)
+    assert lib.ungar_b200_tape_create(nodes.ctypes.data, 2, 1, deps.ctypes.data, None, 1, 0, ctypes.byref(h)) == _lib.EINVAL
+    nodes[1] = (A.OP_MUL, 0, 0, -1, -1, 0.0)
+    assert lib.ungar_b200_tape_create(nodes.ctypes.data, 2, 1, deps.ctypes.data, None, 1, 0, ctypes.byref(h)) == _lib.OK
+    rows = np.array([0], dtype=np.int64)
+    cols = np.array([5], dtype=np.int64)
+    assert lib.ungar_b200_tape_set_jacobian_elements(h, rows.ctypes.data, cols.ctypes.data, 1) == _lib.EINVAL
+    lib.ungar_b200_tape_destroy(h)

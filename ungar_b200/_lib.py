@@ -25,6 +25,9 @@ SYMBOLS = [
     "ungar_b200_kkt_blocks", "ungar_b200_summaries", "ungar_b200_kkt_step", "ungar_b200_set_profiling",
     "ungar_b200_sweep_times", "ungar_b200_qp_solve", "ungar_b200_launch_count", "ungar_b200_last_error",
     "ungar_b200_abi_version", "ungar_b200_sqp_options_default", "ungar_b200_line_search", "ungar_b200_sqp_solve",
+    "ungar_b200_tape_create", "ungar_b200_tape_destroy", "ungar_b200_tape_info", "ungar_b200_tape_jacobian_pattern",
+    "ungar_b200_tape_hessian_pattern", "ungar_b200_tape_set_jacobian_elements", "ungar_b200_tape_set_hessian_elements",
+    "ungar_b200_tape_forward_zero", "ungar_b200_tape_sparse_jacobian", "ungar_b200_tape_sparse_hessian",
 ]
 
 
@@ -85,6 +88,16 @@ def load() -> ctypes.CDLL:
     L.ungar_b200_sqp_options_default.argtypes = [ctypes.POINTER(SqpOptions)]
     L.ungar_b200_line_search.argtypes = [c_vp, c_vp, c_i64, c_i64, c_vp, c_i64, ctypes.POINTER(SqpOptions), c_vp, c_vp, c_vp]
     L.ungar_b200_sqp_solve.argtypes = [c_vp, c_vp, c_i64, c_i64, ctypes.POINTER(SqpOptions), c_vp, c_vp, c_i32, c_vp]
+    L.ungar_b200_tape_create.argtypes = [c_vp, c_i64, c_i64, c_vp, c_vp, c_i64, c_i32, ctypes.POINTER(c_vp)]
+    L.ungar_b200_tape_destroy.argtypes = [c_vp]
+    L.ungar_b200_tape_info.argtypes = [c_vp, c_i64_p]
+    for name in ("ungar_b200_tape_jacobian_pattern", "ungar_b200_tape_hessian_pattern"):
+        getattr(L, name).argtypes = [c_vp, ctypes.POINTER(c_i64_p), ctypes.POINTER(c_i64_p), c_i64_p]
+    for name in ("ungar_b200_tape_set_jacobian_elements", "ungar_b200_tape_set_hessian_elements"):
+        getattr(L, name).argtypes = [c_vp, c_vp, c_vp, c_i64]
+    for name in ("ungar_b200_tape_forward_zero", "ungar_b200_tape_sparse_jacobian"):
+        getattr(L, name).argtypes = [c_vp, c_vp, c_i64, c_i64, c_vp, c_i64, c_i32, c_vp]
+    L.ungar_b200_tape_sparse_hessian.argtypes = [c_vp, c_vp, c_vp, c_i64, c_i64, c_vp, c_i64, c_i32, c_vp]
     L.ungar_b200_set_profiling.argtypes = [c_i32]
     L.ungar_b200_sweep_times.argtypes = [ctypes.POINTER(ctypes.c_float), c_i32, ctypes.POINTER(c_i32)]
     L.ungar_b200_launch_count.restype = c_i64

@@ -1,0 +1,417 @@
+"""Generic path behind ``MakeFunction``: arbitrary user lambdas, taped on the host and evaluated on the GPU.
+
+Python mirror of the reference's autodiff front end (include/ungar/autodiff/function.hpp, data_types.hpp):
+
+* ``AD``            — the tracing scalar standing where ``ad_scalar_t = CppAD::AD<CppAD::cg::CG<double>>`` stands
+                      (autodiff/data_types.hpp:39-41): records an operation tape with CppAD's folding rules (operations on
+                      parameters are folded; ``x * 0``, ``x + 0``, ``x * 1``, ``x / 1``, ``0 / x`` are identities; integer powers
+                      are repeated products; ``CondExp*`` differentiates the selected branch; ``abs'(0) = 0``);
+* ``Blueprint``     — ``Function::Blueprint`` (function.hpp:44-75): the lambda ``f(xp, y)`` plus sizes, name, enabled derivatives;
+* ``MakeFunction``  — ``Autodiff::MakeFunction`` (function.hpp:607-613): where the reference tapes, generates C, runs gcc and
+                      dlopens, this tapes and hands the tape to ``ungar_b200_tape_create``;
+* ``TapeFunction``  — ``Autodiff::Function`` (function.hpp:77-361) over a tape handle: same sizes, the parameter columns trimmed
+                      from the Jacobian pattern (function.hpp:529-550), upper-triangular x-x Hessian of scalar functions
+                      (function.hpp:552-574), ``Evaluate / Jacobian / Hessian``; every call also takes a batch ``xp[B, nx + np]``.
+
+All values and derivatives are computed by the register-machine kernels of ``csrc/tape_machine.cuh``; there is no CPU
+evaluation path here (tracing records operations, it does not evaluate the function for the caller).
+"""
+from __future__ import annotations
+
+import ctypes
+import math
+
+import numpy as np
+
+from . import _lib
+from ._lib import MEM_DEVICE, MEM_HOST, check
+
+(OP_INDEP, OP_CONST, OP_ADD, OP_SUB, OP_MUL, OP_DIV, OP_NEG, OP_SQRT, OP_SIN, OP_COS, OP_TAN, OP_ATAN, OP_ACOS, OP_ASIN, OP_EXP,
+ OP_LOG, OP_ABS, OP_POW, OP_ATAN2, OP_CLT, OP_CLE, OP_CGT, OP_CGE, OP_CEQ) = range(24)
+
+NODE_DTYPE = np.dtype([("op", "u1"), ("a", "i4"), ("b", "i4"), ("c", "i4"), ("d", "i4"), ("k", "f8")], align=True)
+assert NODE_DTYPE.itemsize == 32  # sizeof(ungar_b200_tape_node)
+
+# EnabledDerivatives bitmask (autodiff/data_types.hpp:95-111)
+NONE, JACOBIAN, HESSIAN, ALL = 0, 1, 2, 3
+
+
+class Tape:
+    def __init__(self, n_indep: int):
+        self.nodes = []  # (op, a, b, c, d, k)
+        self.n_indep = n_indep
+
+    def push(self, op, a=-1, b=-1, c=-1, d=-1, k=0.0) -> int:
+        self.nodes.append((op, a, b, c, d, k))
+        return len(self.nodes) - 1
+
+    def array(self) -> np.ndarray:
+        arr = np.zeros(len(self.nodes), dtype=NODE_DTYPE)
+        if self.nodes:
+            cols = list(zip(*self.nodes))
+            for name, col in zip(("op", "a", "b", "c", "d", "k"), cols):
+                arr[name] = col
+        return arr
+
+
+_recording: Tape | None = None
+
+
+class AD:
+    """Tracing scalar: ``v`` is the value at the taping point, ``id`` the tape node (-1: a parameter/constant)."""
+
+    __slots__ = ("v", "id")
+
+    def __init__(self, v=0.0, id=-1):
+        self.v = float(v)
+        self.id = id
+
+    @property
+    def variable(self) -> bool:
+        return self.id >= 0
+
+    # -- arithmetic with CppAD's "identical" folding rules -----------------------------------------------------------------
+    def __add__(self, o):
+        o = _ad(o)
+        if self.variable and not o.variable and o.v == 0.0:
+            return self
+        if o.variable and not self.variable and self.v == 0.0:
+            return o
+        return _binary(OP_ADD, self, o, self.v + o.v)
+
+    __radd__ = __add__
+
+    def __sub__(self, o):
+        o = _ad(o)
+        if self.variable and not o.variable and o.v == 0.0:
+            return self
+        return _binary(OP_SUB, self, o, self.v - o.v)
+
+    def __rsub__(self, o):
+        return _ad(o).__sub__(self)
+
+    def __mul__(self, o):
+        o = _ad(o)
+        for x, c in ((self, o), (o, self)):
+            if x.variable and not c.variable:
+                if c.v == 0.0:
+                    return AD(0.0)
+                if c.v == 1.0:
+                    return x
+        return _binary(OP_MUL, self, o, self.v * o.v)
+
+    __rmul__ = __mul__
+
+    def __truediv__(self, o):
+        o = _ad(o)
+        if self.variable and not o.variable and o.v == 1.0:
+            return self
+        if o.variable and not self.variable and self.v == 0.0:
+            return AD(0.0)
+        return _binary(OP_DIV, self, o, self.v / o.v if o.v != 0.0 else math.copysign(math.inf, self.v) if self.v else math.nan)
+
+    def __rtruediv__(self, o):
+        return _ad(o).__truediv__(self)
+
+    def __neg__(self):
+        return _unary(OP_NEG, self, -self.v)
+
+    def __pos__(self):
+        return self
+
+    def __pow__(self, e):
+        return pow(self, e)
+
+    def __abs__(self):
+        return abs_(self)
+
+    # comparisons act on the taping-point values (the reference records with "no_compare_op", function.hpp:466)
+    def __lt__(self, o): return self.v < _ad(o).v  # noqa: E704
+    def __le__(self, o): return self.v <= _ad(o).v  # noqa: E704
+    def __gt__(self, o): return self.v > _ad(o).v  # noqa: E704
+    def __ge__(self, o): return self.v >= _ad(o).v  # noqa: E704
+    def __float__(self): return self.v  # noqa: E704
+
+    def __repr__(self):
+        return f"AD({self.v}, node={self.id})"
+
+
+def _ad(x) -> AD:
+    return x if isinstance(x, AD) else AD(x)
+
+
+def _node_of(x: AD) -> int:
+    return x.id if x.variable else _recording.push(OP_CONST, k=x.v)
+
+
+def _unary(op, x: AD, value: float) -> AD:
+    if not x.variable or _recording is None:
+        return AD(value)
+    return AD(value, _recording.push(op, x.id))
+
+
+def _binary(op, a: AD, b: AD, value: float) -> AD:
+    if (not a.variable and not b.variable) or _recording is None:
+        return AD(value)
+    ia, ib = _node_of(a), _node_of(b)
+    return AD(value, _recording.push(op, ia, ib))
+
+
+def _safe(fn, x, default=math.nan):
+    try:
+        return fn(x)
+    except (ValueError, OverflowError):
+        return default
+
+
+def sqrt(x): x = _ad(x); return _unary(OP_SQRT, x, _safe(math.sqrt, x.v))  # noqa: E702
+def sin(x): x = _ad(x); return _unary(OP_SIN, x, math.sin(x.v))  # noqa: E702
+def cos(x): x = _ad(x); return _unary(OP_COS, x, math.cos(x.v))  # noqa: E702
+def tan(x): x = _ad(x); return _unary(OP_TAN, x, math.tan(x.v))  # noqa: E702
+def atan(x): x = _ad(x); return _unary(OP_ATAN, x, math.atan(x.v))  # noqa: E702
+def acos(x): x = _ad(x); return _unary(OP_ACOS, x, _safe(math.acos, x.v))  # noqa: E702
+def asin(x): x = _ad(x); return _unary(OP_ASIN, x, _safe(math.asin, x.v))  # noqa: E702
+def exp(x): x = _ad(x); return _unary(OP_EXP, x, _safe(math.exp, x.v, math.inf))  # noqa: E702
+def log(x): x = _ad(x); return _unary(OP_LOG, x, _safe(math.log, x.v))  # noqa: E702
+def abs_(x): x = _ad(x); return _unary(OP_ABS, x, math.fabs(x.v))  # noqa: E702
+
+
+def atan2(y, x):
+    y, x = _ad(y), _ad(x)
+    return _binary(OP_ATAN2, y, x, math.atan2(y.v, x.v))
+
+
+def pow(x, e):  # noqa: A001  (mirrors CppAD::pow / Utils::Pow, utils.hpp:820-837)
+    x = _ad(x)
+    if isinstance(e, int) and not isinstance(e, bool):  # CppAD: integer powers by repeated multiplication
+        if e < 0:
+            return AD(1.0) / pow(x, -e)
+        p = AD(1.0)
+        for _ in range(e):
+            p = p * x
+        return p
+    e = _ad(e)
+    try:
+        value = math.pow(x.v, e.v)
+    except (ValueError, OverflowError):
+        value = math.nan
+    return _binary(OP_POW, x, e, value)
+
+
+def _cond(op, take_true: bool, a, b, t, f) -> AD:
+    a, b, t, f = _ad(a), _ad(b), _ad(t), _ad(f)
+    sel = t if take_true else f
+    if _recording is None or (not a.variable and not b.variable):
+        return sel  # decided by parameters: no operation
+    if not t.variable and not f.variable and t.v == f.v:
+        return sel
+    return AD(sel.v, _recording.push(op, _node_of(a), _node_of(b), _node_of(t), _node_of(f)))
+
+
+def CondExpLt(a, b, t, f): return _cond(OP_CLT, _ad(a).v < _ad(b).v, a, b, t, f)  # noqa: E704
+def CondExpLe(a, b, t, f): return _cond(OP_CLE, _ad(a).v <= _ad(b).v, a, b, t, f)  # noqa: E704
+def CondExpGt(a, b, t, f): return _cond(OP_CGT, _ad(a).v > _ad(b).v, a, b, t, f)  # noqa: E704
+def CondExpGe(a, b, t, f): return _cond(OP_CGE, _ad(a).v >= _ad(b).v, a, b, t, f)  # noqa: E704
+def CondExpEq(a, b, t, f): return _cond(OP_CEQ, _ad(a).v == _ad(b).v, a, b, t, f)  # noqa: E704
+
+
+def record(fn, x0) -> tuple:
+    """CppAD::Independent(x) ... CppAD::ADFun(x, y) (function.hpp:456-465): returns (node array, dependents, dependent constants)."""
+    global _recording
+    x0 = np.asarray(x0, dtype=np.float64)
+    if _recording is not None:
+        raise RuntimeError("a tape is already being recorded")
+    _recording = Tape(x0.size)
+    try:
+        xs = [AD(float(v), _recording.push(OP_INDEP, i)) for i, v in enumerate(x0)]
+        ys = fn(xs)
+        ys = [_ad(y) for y in (ys if isinstance(ys, (list, tuple)) else [ys])]
+        nodes = _recording.array()
+    finally:
+        _recording = None
+    return nodes, np.array([y.id for y in ys], dtype=np.int32), np.array([y.v for y in ys], dtype=np.float64)
+
+
+class TapeHandle:
+    """Owner of one ``ungar_b200_tape`` (raw tape in, analysed program out).  Host-side analysis only until the first evaluation."""
+
+    def __init__(self, nodes: np.ndarray, n_independent: int, dependents, dependent_constants=None, device: int = 0):
+        self._lib = _lib.load()
+        nodes = np.ascontiguousarray(nodes, dtype=NODE_DTYPE)
+        deps = np.ascontiguousarray(dependents, dtype=np.int32)
+        consts = np.ascontiguousarray(dependent_constants if dependent_constants is not None else np.zeros(deps.size), dtype=np.float64)
+        handle = ctypes.c_void_p()
+        check(self._lib.ungar_b200_tape_create(nodes.ctypes.data, nodes.size, int(n_independent), deps.ctypes.data, consts.ctypes.data,
+                                               deps.size, int(device), ctypes.byref(handle)))
+        self._h = handle
+        self.n_independent, self.n_dependent = int(n_independent), int(deps.size)
+        self._nnz_jac = self._nnz_hes = None
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.ungar_b200_tape_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def info(self) -> dict:
+        buf = (ctypes.c_int64 * 6)()
+        check(self._lib.ungar_b200_tape_info(self._h, buf))
+        return dict(zip(("independents", "dependents", "live_nodes", "slots", "jacobian_colors", "hessian_directions"), map(int, buf)))
+
+    def _pattern(self, entry):
+        rows, cols, nnz = _lib.c_i64_p(), _lib.c_i64_p(), ctypes.c_int64()
+        check(getattr(self._lib, entry)(self._h, ctypes.byref(rows), ctypes.byref(cols), ctypes.byref(nnz)))
+        n = int(nnz.value)
+        if n == 0:
+            return np.zeros(0, np.int64), np.zeros(0, np.int64)
+        return np.ctypeslib.as_array(rows, (n,)).copy(), np.ctypeslib.as_array(cols, (n,)).copy()
+
+    def jacobian_pattern(self):
+        """GenericModel::JacobianSparsitySet over ALL independents (rows, cols), row-major."""
+        return self._pattern("ungar_b200_tape_jacobian_pattern")
+
+    def hessian_pattern(self):
+        """GenericModel::HessianSparsitySet: full symmetric pattern, union over the dependents."""
+        return self._pattern("ungar_b200_tape_hessian_pattern")
+
+    def set_jacobian_elements(self, rows, cols):
+        rows, cols = np.ascontiguousarray(rows, dtype=np.int64), np.ascontiguousarray(cols, dtype=np.int64)
+        check(self._lib.ungar_b200_tape_set_jacobian_elements(self._h, rows.ctypes.data, cols.ctypes.data, rows.size))
+        self._nnz_jac = rows.size
+
+    def set_hessian_elements(self, rows, cols):
+        rows, cols = np.ascontiguousarray(rows, dtype=np.int64), np.ascontiguousarray(cols, dtype=np.int64)
+        check(self._lib.ungar_b200_tape_set_hessian_elements(self._h, rows.ctypes.data, cols.ctypes.data, rows.size))
+        self._nnz_hes = rows.size
+
+    # ---- evaluation (numpy = host buffers, torch CUDA tensors = device buffers on the current stream) ---------------------------
+    def _run(self, entry, x, n_out, extra=()):
+        if type(x).__module__.startswith("torch"):
+            import torch
+
+            if not x.is_cuda or x.dtype != torch.float64:
+                raise ValueError("torch inputs must be float64 CUDA tensors")
+            x2 = x.unsqueeze(0) if x.dim() == 1 else x
+            out = torch.empty((x2.shape[0], max(n_out, 1)), dtype=torch.float64, device=x.device)
+            check(getattr(self._lib, entry)(self._h, x2.data_ptr(), *extra, x2.shape[0], x2.stride(0), out.data_ptr(), out.stride(0),
+                                            MEM_DEVICE, torch.cuda.current_stream().cuda_stream))
+            out = out[:, :n_out]
+            return out[0] if x.dim() == 1 else out
+        x2 = np.ascontiguousarray(x, dtype=np.float64)
+        squeeze = x2.ndim == 1
+        if squeeze:
+            x2 = x2[None]
+        if x2.shape[1] != self.n_independent:
+            raise ValueError(f"x has {x2.shape[1]} entries, expected {self.n_independent}")
+        out = np.empty((x2.shape[0], max(n_out, 1)))
+        check(getattr(self._lib, entry)(self._h, x2.ctypes.data, *extra, x2.shape[0], x2.shape[1], out.ctypes.data, out.shape[1], MEM_HOST,
+                                        None))
+        out = out[:, :n_out]
+        return out[0] if squeeze else out
+
+    def forward_zero(self, x):
+        return self._run("ungar_b200_tape_forward_zero", x, self.n_dependent)
+
+    def sparse_jacobian(self, x):
+        if self._nnz_jac is None:
+            r, c = self.jacobian_pattern()
+            self.set_jacobian_elements(r, c)
+        return self._run("ungar_b200_tape_sparse_jacobian", x, self._nnz_jac)
+
+    def sparse_hessian(self, x, weights=None):
+        if self._nnz_hes is None:
+            r, c = self.hessian_pattern()
+            self.set_hessian_elements(r, c)
+        w = np.ones(self.n_dependent) if weights is None else np.ascontiguousarray(weights, dtype=np.float64)
+        self._w_keepalive = w
+        return self._run("ungar_b200_tape_sparse_hessian", x, self._nnz_hes, extra=(w.ctypes.data,))
+
+
+class Blueprint:
+    """Function::Blueprint (function.hpp:44-75): ``functionImpl(xp) -> y`` (a list of AD / floats), sizes, name, enabled derivatives.
+    Like the reference (:53-58) the lambda is evaluated once, on a fixed pseudo-random point, to learn the number of dependents."""
+
+    def __init__(self, functionImpl, independentVariableSize: int, parameterSize: int, name: str = "function",
+                 enabledDerivatives: int = ALL):
+        self.functionImpl = functionImpl
+        self.independentVariableSize = int(independentVariableSize)
+        self.parameterSize = int(parameterSize)
+        self.name = name
+        self.enabledDerivatives = enabledDerivatives
+        n = self.independentVariableSize + self.parameterSize
+        self.tapingPoint = 0.25 + 0.5 * np.random.default_rng(20240807).random(n)
+
+
+class TapeFunction:
+    """Mirror of Ungar::Autodiff::Function (function.hpp:77-361) for an arbitrary taped lambda."""
+
+    def __init__(self, blueprint: Blueprint, device: int = 0):
+        bp = blueprint
+        self._nx, self._np = bp.independentVariableSize, bp.parameterSize
+        nodes, deps, consts = record(bp.functionImpl, bp.tapingPoint)
+        self._tape = TapeHandle(nodes, self._nx + self._np, deps, consts, device)
+        self._ny = deps.size
+        self.name = bp.name
+        self._jac = bool(bp.enabledDerivatives & JACOBIAN)
+        self._hes = bool(bp.enabledDerivatives & HESSIAN) and self._ny == 1  # scalar functions only (function.hpp:136-137)
+        self._jr = self._jc = self._hr = self._hc = np.zeros(0, np.int64)
+        if self._jac:  # parameter columns trimmed (function.hpp:529-550)
+            r, c = self._tape.jacobian_pattern()
+            keep = c < self._nx
+            self._jr, self._jc = r[keep], c[keep]
+            self._tape.set_jacobian_elements(self._jr, self._jc)
+        if self._hes:  # x-x block, upper triangle (function.hpp:552-574)
+            r, c = self._tape.hessian_pattern()
+            keep = (r < self._nx) & (c < self._nx) & (c >= r)
+            self._hr, self._hc = r[keep], c[keep]
+            self._tape.set_hessian_elements(self._hr, self._hc)
+
+    def IndependentVariableSize(self): return self._nx  # noqa: E704
+    def ParameterSize(self): return self._np  # noqa: E704
+    def DependentVariableSize(self): return self._ny  # noqa: E704
+    def ImplementsFunction(self): return True  # noqa: E704
+    def ImplementsJacobian(self): return self._jac  # noqa: E704
+    def ImplementsHessian(self): return self._hes  # noqa: E704
+    def JacobianSparsity(self): return self._jr.copy(), self._jc.copy()  # noqa: E704
+    def HessianSparsity(self): return self._hr.copy(), self._hc.copy()  # noqa: E704
+    def tape_info(self): return self._tape.info()  # noqa: E704
+
+    def Evaluate(self, xp):
+        return self._tape.forward_zero(xp)
+
+    __call__ = Evaluate
+
+    def JacobianValues(self, xp):
+        if not self._jac:
+            raise _lib.UngarB200Error(_lib.EUNSUPPORTED, "the Jacobian was not enabled in the blueprint")
+        return self._tape.sparse_jacobian(xp)
+
+    def HessianValues(self, xp, dependentVariableIndex: int = 0):
+        if not self._hes:
+            raise _lib.UngarB200Error(_lib.EUNSUPPORTED, "the Hessian is implemented only for scalar functions (function.hpp:136-137)")
+        w = np.zeros(self._ny)
+        w[dependentVariableIndex] = 1.0
+        return self._tape.sparse_hessian(xp, w)
+
+    def Jacobian(self, xp):
+        import scipy.sparse as sp
+
+        return sp.csr_matrix((np.asarray(self.JacobianValues(np.asarray(xp))), (self._jr, self._jc)), shape=(self._ny, self._nx))
+
+    def Hessian(self, dependentVariableIndex: int, xp):
+        """Upper-triangular view, like the reference (function.hpp:232-258)."""
+        import scipy.sparse as sp
+
+        return sp.csr_matrix((np.asarray(self.HessianValues(np.asarray(xp), dependentVariableIndex)), (self._hr, self._hc)),
+                             shape=(self._nx, self._nx))
+
+
+def MakeFunction(blueprint: Blueprint, recompileLibraries: bool = False, device: int = 0) -> TapeFunction:
+    """Autodiff::MakeFunction (function.hpp:607-613).  ``recompileLibraries`` is accepted for signature parity: nothing is compiled,
+    so there is no stale-library hazard (the reference caches by NAME only, function.hpp:420-451)."""
+    return TapeFunction(blueprint, device)

@@ -9,8 +9,8 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
 LIB = os.path.join(HERE, "libungar_b200.so")
-SOURCES = [os.path.join(HERE, "csrc", "ungar_b200.cu")]
-HEADERS = [os.path.join(HERE, "csrc", f) for f in ("dual.cuh", "models.cuh", "sweep.cuh", "sweep_structured.cuh", "sweep_tpn.cuh", "sweep_small.cuh", "qp_schur.cuh", "qp_riccati.cuh", "line_search.cuh")] + [
+SOURCES = [os.path.join(HERE, "csrc", "ungar_b200.cu"), os.path.join(HERE, "csrc", "tape.cu")]
+HEADERS = [os.path.join(HERE, "csrc", f) for f in ("dual.cuh", "models.cuh", "sweep.cuh", "sweep_structured.cuh", "sweep_tpn.cuh", "sweep_small.cuh", "qp_schur.cuh", "qp_riccati.cuh", "line_search.cuh", "tape_machine.cuh", "abi_internal.h")] + [
     os.path.join(ROOT, "include", "ungar_b200.h")]
 
 NVCC_FLAGS = [

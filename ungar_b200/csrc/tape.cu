@@ -1,0 +1,624 @@
+// Generic tape path of the C ABI (include/ungar_b200.h, "Generic path"): host-side analysis of a recorded tape and the
+// launches of the register-machine kernels (tape_machine.cuh).  The only host arithmetic here is structural (liveness,
+// dependency sets, colouring); every value and derivative is computed on the device.
+#include <algorithm>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <new>
+#include <set>
+#include <string>
+#include <vector>
+
+#include "../../include/ungar_b200.h"
+#include "abi_internal.h"
+#include "tape_machine.cuh"
+
+namespace {
+
+using ub::tape::Instr;
+static_assert(int(UNGAR_B200_OP_CEQ) == int(ub::tape::T_CEQ) && int(UNGAR_B200_OP_COUNT) == int(ub::tape::T_OUTPUT) &&
+                  int(UNGAR_B200_OP_SQRT) == int(ub::tape::T_SQRT),
+              "the ABI op codes are the machine's op codes");
+
+int tfail(int code, const char* fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    return ub_set_error(code, buf);
+}
+
+#define UBT_CUDA(call)                                                                                                  \
+    do {                                                                                                                \
+        cudaError_t e_ = (call);                                                                                        \
+        if (e_ != cudaSuccess) return tfail(UNGAR_B200_ECUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+    } while (0)
+
+struct DevBuf {
+    void* ptr  = nullptr;
+    size_t cap = 0;
+    int reserve(size_t bytes) {
+        if (bytes <= cap) return UNGAR_B200_OK;
+        if (ptr) cudaFree(ptr);
+        ptr = nullptr;
+        cap = 0;
+        cudaError_t e = cudaMalloc(&ptr, bytes);
+        if (e != cudaSuccess) return tfail(UNGAR_B200_ENOMEM, "cudaMalloc(%zu) failed: %s", bytes, cudaGetErrorString(e));
+        cap = bytes;
+        return UNGAR_B200_OK;
+    }
+    template <class T>
+    int upload(const std::vector<T>& host) {
+        if (int rc = reserve(std::max<size_t>(host.size(), 1) * sizeof(T))) return rc;
+        if (!host.empty()) {
+            cudaError_t e = cudaMemcpy(ptr, host.data(), host.size() * sizeof(T), cudaMemcpyHostToDevice);
+            if (e != cudaSuccess) return tfail(UNGAR_B200_ECUDA, "cudaMemcpy failed: %s", cudaGetErrorString(e));
+        }
+        return UNGAR_B200_OK;
+    }
+    ~DevBuf() {
+        if (ptr) cudaFree(ptr);
+    }
+};
+
+bool is_unary(int op) {
+    return op == UNGAR_B200_OP_NEG || (op >= UNGAR_B200_OP_SQRT && op <= UNGAR_B200_OP_ABS);
+}
+bool is_binary(int op) {
+    return (op >= UNGAR_B200_OP_ADD && op <= UNGAR_B200_OP_DIV) || op == UNGAR_B200_OP_POW || op == UNGAR_B200_OP_ATAN2;
+}
+bool is_cond(int op) { return op >= UNGAR_B200_OP_CLT && op <= UNGAR_B200_OP_CEQ; }
+// d2/d(operands)2 != 0: the operation makes its operands interact in the Hessian.
+bool is_nonlinear_unary(int op) { return is_unary(op) && op != UNGAR_B200_OP_NEG && op != UNGAR_B200_OP_ABS; }
+
+using IndexSet = std::vector<int32_t>;  // sorted, unique
+IndexSet set_union(const IndexSet& a, const IndexSet& b) {
+    IndexSet r;
+    r.reserve(a.size() + b.size());
+    std::set_union(a.begin(), a.end(), b.begin(), b.end(), std::back_inserter(r));
+    return r;
+}
+
+}  // namespace
+
+struct ungar_b200_tape {
+    int device = 0;
+    int64_t n_indep = 0, n_dep = 0;
+    std::vector<ungar_b200_tape_node> nodes;
+    std::vector<int32_t> dep_id;
+    std::vector<double> dep_const;
+    std::vector<char> live;  // node reaches a dependent
+    int64_t n_live = 0;
+
+    // program
+    std::vector<Instr> code;
+    std::vector<double> consts;
+    int n_slots = 0;
+
+    // structural patterns (lazy)
+    bool jp_done = false, hp_done = false;
+    std::vector<int64_t> jp_rows, jp_cols, hp_rows, hp_cols;
+
+    // selected elements
+    bool j_set = false, h_set = false;
+    std::vector<int64_t> j_rows, j_cols, h_rows, h_cols;
+    std::vector<int> color;     // [n_indep], -1: no selected element in that column
+    int n_colors = 0;
+    std::vector<int> jac_slot;  // [n_dep * n_colors]
+    std::vector<int> h_pi, h_pj;               // Hessian directions
+    std::vector<int> h_di, h_dj, h_pr;         // per element: direction of e_i, of e_j, of e_i + e_j (-1 on the diagonal)
+
+    // device state
+    bool uploaded = false, j_uploaded = false, h_uploaded = false;
+    DevBuf d_code, d_consts, d_color, d_jac_slot, d_pi, d_pj, d_di, d_dj, d_pr, d_w, scratch, ws_x, ws_out, ws_q;
+};
+
+namespace {
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Analysis
+// ---------------------------------------------------------------------------------------------------------------------
+int validate(const ungar_b200_tape& T) {
+    const int64_t n = int64_t(T.nodes.size());
+    for (int64_t i = 0; i < n; ++i) {
+        const ungar_b200_tape_node& nd = T.nodes[i];
+        auto ok = [&](int32_t r) { return r >= 0 && r < i; };
+        if (nd.op >= UNGAR_B200_OP_COUNT) return tfail(UNGAR_B200_EINVAL, "node %lld: unknown op %d", (long long)i, int(nd.op));
+        if (nd.op == UNGAR_B200_OP_INDEP) {
+            if (nd.a < 0 || nd.a >= T.n_indep) return tfail(UNGAR_B200_EINVAL, "node %lld: independent %d out of range", (long long)i, nd.a);
+        } else if (nd.op == UNGAR_B200_OP_CONST) {
+        } else if (is_unary(nd.op)) {
+            if (!ok(nd.a)) return tfail(UNGAR_B200_EINVAL, "node %lld: operand out of range", (long long)i);
+        } else if (is_binary(nd.op)) {
+            if (!ok(nd.a) || !ok(nd.b)) return tfail(UNGAR_B200_EINVAL, "node %lld: operand out of range", (long long)i);
+        } else if (!ok(nd.a) || !ok(nd.b) || !ok(nd.c) || !ok(nd.d)) {
+            return tfail(UNGAR_B200_EINVAL, "node %lld: operand out of range", (long long)i);
+        }
+    }
+    for (int64_t r = 0; r < T.n_dep; ++r)
+        if (T.dep_id[r] >= n) return tfail(UNGAR_B200_EINVAL, "dependent %lld: node %d out of range", (long long)r, T.dep_id[r]);
+    return UNGAR_B200_OK;
+}
+
+template <class F>
+void for_operands(const ungar_b200_tape_node& nd, F&& f) {
+    if (nd.op == UNGAR_B200_OP_INDEP || nd.op == UNGAR_B200_OP_CONST) return;
+    f(nd.a);
+    if (is_unary(nd.op)) return;
+    f(nd.b);
+    if (is_binary(nd.op)) return;
+    f(nd.c);
+    f(nd.d);
+}
+
+// Dead-node elimination, slot allocation by liveness (free list), instruction stream with the dependents written out right
+// after the node that defines them.
+void build_program(ungar_b200_tape& T) {
+    const int64_t n = int64_t(T.nodes.size());
+    T.live.assign(size_t(n), 0);
+    for (int32_t id : T.dep_id)
+        if (id >= 0) T.live[size_t(id)] = 1;
+    for (int64_t i = n - 1; i >= 0; --i)
+        if (T.live[size_t(i)]) for_operands(T.nodes[size_t(i)], [&](int32_t o) { T.live[size_t(o)] = 1; });
+    std::vector<int32_t> uses(size_t(n), 0);
+    for (int64_t i = 0; i < n; ++i)
+        if (T.live[size_t(i)]) for_operands(T.nodes[size_t(i)], [&](int32_t o) { ++uses[size_t(o)]; });
+    std::multimap<int32_t, int64_t> outputs_of;  // node -> dependents it defines
+    for (int64_t r = 0; r < T.n_dep; ++r)
+        if (T.dep_id[size_t(r)] >= 0) { outputs_of.emplace(T.dep_id[size_t(r)], r); ++uses[size_t(T.dep_id[size_t(r)])]; }
+
+    std::vector<int32_t> slot(size_t(n), -1), free_slots;
+    int next_slot = 0;
+    T.code.clear();
+    T.consts.clear();
+    T.n_live = 0;
+    auto release = [&](int32_t o) {
+        if (--uses[size_t(o)] == 0) free_slots.push_back(slot[size_t(o)]);
+    };
+    auto take_slot = [&]() {
+        if (!free_slots.empty()) { const int32_t s = free_slots.back(); free_slots.pop_back(); return s; }
+        return int32_t(next_slot++);
+    };
+    // Independents are loaded right before their first use, not where Independent() recorded them (all at the start): otherwise every
+    // one of them would hold a slot from the beginning and the scratch would be as large as the input vector.
+    auto materialize = [&](int32_t o) {
+        if (slot[size_t(o)] >= 0) return;
+        slot[size_t(o)] = take_slot();
+        T.code.push_back(Instr{ub::tape::T_INDEP, slot[size_t(o)], T.nodes[size_t(o)].a, 0, 0, 0});
+    };
+    auto emit_outputs = [&](int64_t i) {
+        auto range = outputs_of.equal_range(int32_t(i));
+        for (auto it = range.first; it != range.second; ++it) {
+            T.code.push_back(Instr{ub::tape::T_OUTPUT, 0, slot[size_t(i)], int(it->second), 0, 0});
+            release(int32_t(i));
+        }
+    };
+    for (int64_t i = 0; i < n; ++i) {
+        if (!T.live[size_t(i)]) continue;
+        ++T.n_live;
+        const ungar_b200_tape_node& nd = T.nodes[size_t(i)];
+        if (nd.op == UNGAR_B200_OP_INDEP) {
+            if (outputs_of.count(int32_t(i))) { materialize(int32_t(i)); emit_outputs(i); }  // a dependent that IS an independent
+            continue;
+        }
+        Instr in{int(nd.op), 0, 0, 0, 0, 0};
+        if (nd.op == UNGAR_B200_OP_CONST) { in.a = int(T.consts.size()); T.consts.push_back(nd.k); }
+        else {
+            for_operands(nd, [&](int32_t o) { materialize(o); });
+            in.a = slot[size_t(nd.a)];
+            if (!is_unary(nd.op)) in.b = slot[size_t(nd.b)];
+            if (is_cond(nd.op)) { in.c = slot[size_t(nd.c)]; in.d = slot[size_t(nd.d)]; }
+        }
+        // operands may be released before the destination is chosen: every instruction reads all operands before it writes
+        for_operands(nd, [&](int32_t o) { release(o); });
+        slot[size_t(i)] = take_slot();
+        in.dst = slot[size_t(i)];
+        T.code.push_back(in);
+        emit_outputs(i);
+    }
+    for (int64_t r = 0; r < T.n_dep; ++r)
+        if (T.dep_id[size_t(r)] < 0) {
+            T.code.push_back(Instr{ub::tape::T_OUTPUT_CONST, 0, int(T.consts.size()), int(r), 0, 0});
+            T.consts.push_back(T.dep_const[size_t(r)]);
+        }
+    T.n_slots = std::max(next_slot, 1);
+}
+
+// Dependency sets of the live nodes (freed at last use); calls visit(i, node, sets) for every live node after its set is built.
+template <class Visit>
+void propagate_sets(const ungar_b200_tape& T, Visit&& visit) {
+    const int64_t n = int64_t(T.nodes.size());
+    std::vector<int32_t> uses(size_t(n), 0);
+    for (int64_t i = 0; i < n; ++i)
+        if (T.live[size_t(i)]) for_operands(T.nodes[size_t(i)], [&](int32_t o) { ++uses[size_t(o)]; });
+    for (int32_t id : T.dep_id)
+        if (id >= 0) ++uses[size_t(id)];  // kept until the end
+    std::vector<IndexSet> sets(static_cast<size_t>(n), IndexSet());
+    for (int64_t i = 0; i < n; ++i) {
+        if (!T.live[size_t(i)]) continue;
+        const ungar_b200_tape_node& nd = T.nodes[size_t(i)];
+        IndexSet* const base = sets.data();
+        IndexSet cur;
+        if (nd.op == UNGAR_B200_OP_INDEP) cur.push_back(nd.a);
+        else if (nd.op == UNGAR_B200_OP_CONST) cur.clear();
+        else if (is_unary(nd.op)) cur = base[nd.a];
+        else if (is_binary(nd.op)) cur = set_union(base[nd.a], base[nd.b]);
+        else cur = set_union(base[nd.c], base[nd.d]);  // CondExp: the union of both branches; the compared values carry no derivative
+        base[i].swap(cur);
+        visit(i, nd, sets);
+        for_operands(nd, [&](int32_t o) {
+            if (--uses[size_t(o)] == 0) IndexSet().swap(sets[size_t(o)]);
+        });
+    }
+}
+
+void jacobian_pattern(ungar_b200_tape& T) {
+    if (T.jp_done) return;
+    std::vector<IndexSet> rows(size_t(T.n_dep));
+    std::multimap<int32_t, int64_t> outputs_of;
+    for (int64_t r = 0; r < T.n_dep; ++r)
+        if (T.dep_id[size_t(r)] >= 0) outputs_of.emplace(T.dep_id[size_t(r)], r);
+    propagate_sets(T, [&](int64_t i, const ungar_b200_tape_node&, const std::vector<IndexSet>& sets) {
+        auto range = outputs_of.equal_range(int32_t(i));
+        for (auto it = range.first; it != range.second; ++it) rows[size_t(it->second)] = sets[size_t(i)];
+    });
+    T.jp_rows.clear();
+    T.jp_cols.clear();
+    for (int64_t r = 0; r < T.n_dep; ++r)
+        for (int32_t c : rows[size_t(r)]) { T.jp_rows.push_back(r); T.jp_cols.push_back(c); }
+    T.jp_done = true;
+}
+
+// Index pairs that interact through a nonlinear operation on the way to a dependent (full symmetric pattern).
+void hessian_pattern(ungar_b200_tape& T) {
+    if (T.hp_done) return;
+    std::vector<std::set<int32_t>> H(size_t(T.n_indep));
+    auto cross = [&](const IndexSet& a, const IndexSet& b) {
+        for (int32_t i : a)
+            for (int32_t j : b) { H[size_t(i)].insert(j); H[size_t(j)].insert(i); }
+    };
+    propagate_sets(T, [&](int64_t, const ungar_b200_tape_node& nd, const std::vector<IndexSet>& sets) {
+        const IndexSet& a = nd.op == UNGAR_B200_OP_INDEP || nd.op == UNGAR_B200_OP_CONST ? sets[0] : sets[size_t(nd.a)];
+        if (is_nonlinear_unary(nd.op)) cross(a, a);
+        else if (nd.op == UNGAR_B200_OP_MUL) cross(a, sets[size_t(nd.b)]);
+        else if (nd.op == UNGAR_B200_OP_DIV) { cross(a, sets[size_t(nd.b)]); cross(sets[size_t(nd.b)], sets[size_t(nd.b)]); }
+        else if (nd.op == UNGAR_B200_OP_POW || nd.op == UNGAR_B200_OP_ATAN2) {
+            const IndexSet u = set_union(a, sets[size_t(nd.b)]);
+            cross(u, u);
+        }
+    });
+    T.hp_rows.clear();
+    T.hp_cols.clear();
+    for (int64_t i = 0; i < T.n_indep; ++i)
+        for (int32_t j : H[size_t(i)]) { T.hp_rows.push_back(i); T.hp_cols.push_back(j); }
+    T.hp_done = true;
+}
+
+// Column compression: columns that share no row of the STRUCTURAL pattern get the same colour (greedy, column order), so
+// each selected element is read from exactly one direction.
+int choose_jacobian(ungar_b200_tape& T, const int64_t* rows, const int64_t* cols, int64_t nnz) {
+    jacobian_pattern(T);
+    std::vector<std::vector<int32_t>> row_cols(size_t(T.n_dep)), col_rows(size_t(T.n_indep));
+    for (size_t e = 0; e < T.jp_rows.size(); ++e) {
+        row_cols[size_t(T.jp_rows[e])].push_back(int32_t(T.jp_cols[e]));
+        col_rows[size_t(T.jp_cols[e])].push_back(int32_t(T.jp_rows[e]));
+    }
+    std::vector<int64_t> sel_rows, sel_cols;
+    if (rows) {
+        for (int64_t e = 0; e < nnz; ++e) {
+            if (rows[e] < 0 || rows[e] >= T.n_dep || cols[e] < 0 || cols[e] >= T.n_indep)
+                return tfail(UNGAR_B200_EINVAL, "Jacobian element %lld (%lld, %lld) out of range", (long long)e, (long long)rows[e], (long long)cols[e]);
+            const auto& rc = row_cols[size_t(rows[e])];
+            if (!std::binary_search(rc.begin(), rc.end(), int32_t(cols[e])))
+                return tfail(UNGAR_B200_EINVAL, "Jacobian element (%lld, %lld) is structurally zero", (long long)rows[e], (long long)cols[e]);
+        }
+        sel_rows.assign(rows, rows + nnz);
+        sel_cols.assign(cols, cols + nnz);
+    } else {
+        sel_rows = T.jp_rows;
+        sel_cols = T.jp_cols;
+    }
+    std::vector<char> wanted(size_t(T.n_indep), 0);
+    for (int64_t c : sel_cols) wanted[size_t(c)] = 1;
+    T.color.assign(size_t(T.n_indep), -1);
+    T.n_colors = 0;
+    std::vector<int> stamp;
+    for (int64_t j = 0; j < T.n_indep; ++j) {
+        if (!wanted[size_t(j)]) continue;
+        stamp.assign(size_t(T.n_colors) + 1, 0);
+        for (int32_t r : col_rows[size_t(j)])
+            for (int32_t c : row_cols[size_t(r)])
+                if (T.color[size_t(c)] >= 0) stamp[size_t(T.color[size_t(c)])] = 1;
+        int col = 0;
+        while (stamp[size_t(col)]) ++col;
+        T.color[size_t(j)] = col;
+        T.n_colors = std::max(T.n_colors, col + 1);
+    }
+    T.n_colors = std::max(T.n_colors, 1);
+    T.jac_slot.assign(size_t(T.n_dep) * size_t(T.n_colors), -1);
+    for (size_t e = 0; e < sel_rows.size(); ++e) {
+        int& s = T.jac_slot[size_t(sel_rows[e]) * size_t(T.n_colors) + size_t(T.color[size_t(sel_cols[e])])];
+        if (s >= 0) return tfail(UNGAR_B200_EINVAL, "Jacobian element (%lld, %lld) listed twice", (long long)sel_rows[e], (long long)sel_cols[e]);
+        s = int(e);
+    }
+    T.j_rows.swap(sel_rows);
+    T.j_cols.swap(sel_cols);
+    T.j_set = true;
+    T.j_uploaded = false;
+    return UNGAR_B200_OK;
+}
+
+int choose_hessian(ungar_b200_tape& T, const int64_t* rows, const int64_t* cols, int64_t nnz) {
+    hessian_pattern(T);
+    std::vector<int64_t> sel_rows, sel_cols;
+    if (rows) {
+        std::set<std::pair<int64_t, int64_t>> pattern;
+        for (size_t e = 0; e < T.hp_rows.size(); ++e) pattern.emplace(T.hp_rows[e], T.hp_cols[e]);
+        for (int64_t e = 0; e < nnz; ++e) {
+            if (rows[e] < 0 || rows[e] >= T.n_indep || cols[e] < 0 || cols[e] >= T.n_indep)
+                return tfail(UNGAR_B200_EINVAL, "Hessian element %lld out of range", (long long)e);
+            if (!pattern.count({rows[e], cols[e]}))
+                return tfail(UNGAR_B200_EINVAL, "Hessian element (%lld, %lld) is structurally zero", (long long)rows[e], (long long)cols[e]);
+        }
+        sel_rows.assign(rows, rows + nnz);
+        sel_cols.assign(cols, cols + nnz);
+    } else {
+        sel_rows = T.hp_rows;
+        sel_cols = T.hp_cols;
+    }
+    T.h_pi.clear(); T.h_pj.clear();
+    std::map<int64_t, int> diag_dir;
+    std::map<std::pair<int64_t, int64_t>, int> pair_dir;
+    auto diag = [&](int64_t i) {
+        auto it = diag_dir.find(i);
+        if (it != diag_dir.end()) return it->second;
+        const int d = int(T.h_pi.size());
+        T.h_pi.push_back(int(i)); T.h_pj.push_back(int(i));
+        diag_dir.emplace(i, d);
+        return d;
+    };
+    T.h_di.assign(sel_rows.size(), 0); T.h_dj.assign(sel_rows.size(), 0); T.h_pr.assign(sel_rows.size(), -1);
+    for (size_t e = 0; e < sel_rows.size(); ++e) {
+        const int64_t i = std::min(sel_rows[e], sel_cols[e]), j = std::max(sel_rows[e], sel_cols[e]);
+        T.h_di[e] = diag(i);
+        T.h_dj[e] = diag(j);
+        if (i != j) {
+            auto it = pair_dir.find({i, j});
+            if (it == pair_dir.end()) {
+                it = pair_dir.emplace(std::make_pair(i, j), int(T.h_pi.size())).first;
+                T.h_pi.push_back(int(i)); T.h_pj.push_back(int(j));
+            }
+            T.h_pr[e] = it->second;
+        }
+    }
+    if (T.h_pi.empty()) { T.h_pi.push_back(0); T.h_pj.push_back(0); }  // keep the launch geometry non-empty
+    T.h_rows.swap(sel_rows);
+    T.h_cols.swap(sel_cols);
+    T.h_set = true;
+    T.h_uploaded = false;
+    return UNGAR_B200_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Device side
+// ---------------------------------------------------------------------------------------------------------------------
+int ensure_device(ungar_b200_tape& T) {
+    int count = 0;
+    if (cudaGetDeviceCount(&count) != cudaSuccess || count <= 0 || T.device >= count)
+        return tfail(UNGAR_B200_ECUDA, "no usable CUDA device %d (there is no CPU fallback for tape evaluation)", T.device);
+    UBT_CUDA(cudaSetDevice(T.device));
+    if (!T.uploaded) {
+        if (int rc = T.d_code.upload(T.code)) return rc;
+        if (int rc = T.d_consts.upload(T.consts)) return rc;
+        T.uploaded = true;
+    }
+    return UNGAR_B200_OK;
+}
+
+struct Staged {
+    const double* d_x;
+    int64_t ld_x;
+    double* d_out;
+    int64_t ld_out;
+};
+
+int stage_in(ungar_b200_tape& T, const double* x, int64_t batch, int64_t ld_x, double* out, int64_t ld_out, int64_t n_out, int32_t mem,
+             cudaStream_t stream, Staged& s) {
+    s = Staged{x, ld_x, out, ld_out};
+    if (mem == UNGAR_B200_MEM_HOST) {
+        if (int rc = T.ws_x.reserve(size_t(batch) * T.n_indep * sizeof(double))) return rc;
+        if (int rc = T.ws_out.reserve(size_t(batch) * std::max<int64_t>(n_out, 1) * sizeof(double))) return rc;
+        UBT_CUDA(cudaMemcpy2DAsync(T.ws_x.ptr, T.n_indep * sizeof(double), x, ld_x * sizeof(double), T.n_indep * sizeof(double), batch,
+                                   cudaMemcpyHostToDevice, stream));
+        s = Staged{static_cast<const double*>(T.ws_x.ptr), T.n_indep, static_cast<double*>(T.ws_out.ptr), std::max<int64_t>(n_out, 1)};
+    }
+    return UNGAR_B200_OK;
+}
+
+int stage_out(const Staged& s, double* out, int64_t ld_out, int64_t n_out, int64_t batch, int32_t mem, cudaStream_t stream) {
+    if (mem == UNGAR_B200_MEM_HOST) {
+        if (n_out)
+            UBT_CUDA(cudaMemcpy2DAsync(out, ld_out * sizeof(double), s.d_out, s.ld_out * sizeof(double), n_out * sizeof(double), batch,
+                                       cudaMemcpyDeviceToHost, stream));
+        UBT_CUDA(cudaStreamSynchronize(stream));
+    }
+    return UNGAR_B200_OK;
+}
+
+int check_call(const ungar_b200_tape* T, const void* x, int64_t batch, int64_t ld_x, const void* out, int64_t ld_out, int64_t n_out, int32_t mem) {
+    if (!T) return tfail(UNGAR_B200_EINVAL, "null tape");
+    if (batch < 0 || (batch > 0 && (!x || (!out && n_out > 0)))) return tfail(UNGAR_B200_EINVAL, "null buffer");
+    if (ld_x < T->n_indep) return tfail(UNGAR_B200_EINVAL, "ld_x %lld < %lld", (long long)ld_x, (long long)T->n_indep);
+    if (ld_out < n_out) return tfail(UNGAR_B200_EINVAL, "output stride %lld < %lld", (long long)ld_out, (long long)n_out);
+    if (mem != UNGAR_B200_MEM_DEVICE && mem != UNGAR_B200_MEM_HOST) return tfail(UNGAR_B200_EINVAL, "unknown mem %d", mem);
+    return UNGAR_B200_OK;
+}
+
+template <int ORDER>
+int launch(ungar_b200_tape& T, const ub::tape::Seeds& seeds, const double* d_x, int64_t ld_x, int64_t batch, int ndir, double* d_out,
+           int64_t ld_out, const int* out_slot, const double* weights, cudaStream_t stream) {
+    const long long threads = (long long)batch * ndir;
+    const long long stride  = (threads + 31) & ~31LL;
+    if (int rc = T.scratch.reserve(size_t(T.n_slots) * (ORDER + 1) * size_t(stride) * sizeof(double))) return rc;
+    const ub::tape::Program P{static_cast<const Instr*>(T.d_code.ptr), static_cast<const double*>(T.d_consts.ptr), int(T.code.size()),
+                              T.n_slots, int(T.n_indep), int(T.n_dep)};
+    const long long blocks = (threads + 127) / 128;
+    if (blocks > 2147483647LL) return tfail(UNGAR_B200_EINVAL, "batch x directions too large for one launch");
+    ub::tape::tape_kernel<ORDER><<<unsigned(blocks), 128, 0, stream>>>(P, seeds, d_x, ld_x, batch, ndir, static_cast<double*>(T.scratch.ptr),
+                                                                         stride, d_out, ld_out, out_slot, weights);
+    ub_count_launch();
+    UBT_CUDA(cudaGetLastError());
+    return UNGAR_B200_OK;
+}
+
+}  // namespace
+
+// =====================================================================================================================
+extern "C" {
+
+int ungar_b200_tape_create(const ungar_b200_tape_node* nodes, int64_t n_nodes, int64_t n_independent, const int32_t* dependents,
+                           const double* dependent_constants, int64_t n_dependent, int32_t device, ungar_b200_tape** out) {
+    if (!out) return tfail(UNGAR_B200_EINVAL, "null output handle");
+    *out = nullptr;
+    if (n_nodes < 0 || n_independent < 0 || n_dependent < 0 || (n_nodes > 0 && !nodes) || (n_dependent > 0 && !dependents))
+        return tfail(UNGAR_B200_EINVAL, "bad tape sizes or null arrays");
+    if (n_nodes > 2000000000LL || n_independent > 2000000000LL) return tfail(UNGAR_B200_EINVAL, "tape too large");
+    ungar_b200_tape* T = new (std::nothrow) ungar_b200_tape;
+    if (!T) return tfail(UNGAR_B200_ENOMEM, "out of host memory");
+    T->device  = device;
+    T->n_indep = n_independent;
+    T->n_dep   = n_dependent;
+    T->nodes.assign(nodes, nodes + n_nodes);
+    T->dep_id.assign(dependents, dependents + n_dependent);
+    T->dep_const.assign(size_t(n_dependent), 0.0);
+    if (dependent_constants) T->dep_const.assign(dependent_constants, dependent_constants + n_dependent);
+    if (int rc = validate(*T)) {
+        delete T;
+        return rc;
+    }
+    build_program(*T);
+    *out = T;
+    return UNGAR_B200_OK;
+}
+
+int ungar_b200_tape_destroy(ungar_b200_tape* tape) {
+    if (!tape) return UNGAR_B200_OK;
+    int count = 0;
+    if (cudaGetDeviceCount(&count) == cudaSuccess && tape->device < count) cudaSetDevice(tape->device);
+    delete tape;
+    return UNGAR_B200_OK;
+}
+
+int ungar_b200_tape_info(const ungar_b200_tape* tape, int64_t* info) {
+    if (!tape || !info) return tfail(UNGAR_B200_EINVAL, "null argument");
+    info[0] = tape->n_indep; info[1] = tape->n_dep; info[2] = tape->n_live; info[3] = tape->n_slots;
+    info[4] = tape->j_set ? tape->n_colors : 0;
+    info[5] = tape->h_set ? int64_t(tape->h_pi.size()) : 0;
+    return UNGAR_B200_OK;
+}
+
+int ungar_b200_tape_jacobian_pattern(ungar_b200_tape* tape, const int64_t** rows, const int64_t** cols, int64_t* nnz) {
+    if (!tape || !rows || !cols || !nnz) return tfail(UNGAR_B200_EINVAL, "null argument");
+    jacobian_pattern(*tape);
+    *rows = tape->jp_rows.data(); *cols = tape->jp_cols.data(); *nnz = int64_t(tape->jp_rows.size());
+    return UNGAR_B200_OK;
+}
+
+int ungar_b200_tape_hessian_pattern(ungar_b200_tape* tape, const int64_t** rows, const int64_t** cols, int64_t* nnz) {
+    if (!tape || !rows || !cols || !nnz) return tfail(UNGAR_B200_EINVAL, "null argument");
+    hessian_pattern(*tape);
+    *rows = tape->hp_rows.data(); *cols = tape->hp_cols.data(); *nnz = int64_t(tape->hp_rows.size());
+    return UNGAR_B200_OK;
+}
+
+int ungar_b200_tape_set_jacobian_elements(ungar_b200_tape* tape, const int64_t* rows, const int64_t* cols, int64_t nnz) {
+    if (!tape || (rows && !cols) || nnz < 0) return tfail(UNGAR_B200_EINVAL, "bad argument");
+    return choose_jacobian(*tape, rows, cols, nnz);
+}
+
+int ungar_b200_tape_set_hessian_elements(ungar_b200_tape* tape, const int64_t* rows, const int64_t* cols, int64_t nnz) {
+    if (!tape || (rows && !cols) || nnz < 0) return tfail(UNGAR_B200_EINVAL, "bad argument");
+    return choose_hessian(*tape, rows, cols, nnz);
+}
+
+int ungar_b200_tape_forward_zero(ungar_b200_tape* tape, const double* x, int64_t batch, int64_t ld_x, double* y, int64_t ld_y, int32_t mem,
+                                 void* stream_) {
+    if (int rc = check_call(tape, x, batch, ld_x, y, ld_y, tape ? tape->n_dep : 0, mem)) return rc;
+    if (batch == 0) return UNGAR_B200_OK;
+    if (int rc = ensure_device(*tape)) return rc;
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    Staged s;
+    if (int rc = stage_in(*tape, x, batch, ld_x, y, ld_y, tape->n_dep, mem, stream, s)) return rc;
+    if (int rc = launch<0>(*tape, ub::tape::Seeds{0, nullptr, nullptr, nullptr}, s.d_x, s.ld_x, batch, 1, s.d_out, s.ld_out, nullptr, nullptr, stream))
+        return rc;
+    return stage_out(s, y, ld_y, tape->n_dep, batch, mem, stream);
+}
+
+int ungar_b200_tape_sparse_jacobian(ungar_b200_tape* tape, const double* x, int64_t batch, int64_t ld_x, double* vals, int64_t ld_vals,
+                                    int32_t mem, void* stream_) {
+    if (!tape) return tfail(UNGAR_B200_EINVAL, "null tape");
+    if (!tape->j_set)
+        if (int rc = choose_jacobian(*tape, nullptr, nullptr, 0)) return rc;
+    const int64_t nnz = int64_t(tape->j_rows.size());
+    if (int rc = check_call(tape, x, batch, ld_x, vals, ld_vals, nnz, mem)) return rc;
+    if (batch == 0 || nnz == 0) return UNGAR_B200_OK;
+    if (int rc = ensure_device(*tape)) return rc;
+    if (!tape->j_uploaded) {
+        if (int rc = tape->d_color.upload(tape->color)) return rc;
+        if (int rc = tape->d_jac_slot.upload(tape->jac_slot)) return rc;
+        tape->j_uploaded = true;
+    }
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    Staged s;
+    if (int rc = stage_in(*tape, x, batch, ld_x, vals, ld_vals, nnz, mem, stream, s)) return rc;
+    const ub::tape::Seeds seeds{0, static_cast<const int*>(tape->d_color.ptr), nullptr, nullptr};
+    if (int rc = launch<1>(*tape, seeds, s.d_x, s.ld_x, batch, tape->n_colors, s.d_out, s.ld_out, static_cast<const int*>(tape->d_jac_slot.ptr),
+                           nullptr, stream))
+        return rc;
+    return stage_out(s, vals, ld_vals, nnz, batch, mem, stream);
+}
+
+int ungar_b200_tape_sparse_hessian(ungar_b200_tape* tape, const double* x, const double* weights, int64_t batch, int64_t ld_x, double* vals,
+                                   int64_t ld_vals, int32_t mem, void* stream_) {
+    if (!tape) return tfail(UNGAR_B200_EINVAL, "null tape");
+    if (!tape->h_set)
+        if (int rc = choose_hessian(*tape, nullptr, nullptr, 0)) return rc;
+    const int64_t nnz = int64_t(tape->h_rows.size());
+    if (int rc = check_call(tape, x, batch, ld_x, vals, ld_vals, nnz, mem)) return rc;
+    if (batch == 0 || nnz == 0) return UNGAR_B200_OK;
+    if (int rc = ensure_device(*tape)) return rc;
+    if (!tape->h_uploaded) {
+        if (int rc = tape->d_pi.upload(tape->h_pi)) return rc;
+        if (int rc = tape->d_pj.upload(tape->h_pj)) return rc;
+        if (int rc = tape->d_di.upload(tape->h_di)) return rc;
+        if (int rc = tape->d_dj.upload(tape->h_dj)) return rc;
+        if (int rc = tape->d_pr.upload(tape->h_pr)) return rc;
+        tape->h_uploaded = true;
+    }
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    std::vector<double> w(size_t(tape->n_dep), 1.0);
+    if (weights) w.assign(weights, weights + tape->n_dep);
+    if (int rc = tape->d_w.reserve(std::max<size_t>(w.size(), 1) * sizeof(double))) return rc;
+    UBT_CUDA(cudaMemcpyAsync(tape->d_w.ptr, w.data(), w.size() * sizeof(double), cudaMemcpyHostToDevice, stream));
+    UBT_CUDA(cudaStreamSynchronize(stream));  // `w` is a stack-lifetime staging buffer
+    const int ndir = int(tape->h_pi.size());
+    if (int rc = tape->ws_q.reserve(size_t(batch) * ndir * sizeof(double))) return rc;
+    Staged s;
+    if (int rc = stage_in(*tape, x, batch, ld_x, vals, ld_vals, nnz, mem, stream, s)) return rc;
+    const ub::tape::Seeds seeds{1, nullptr, static_cast<const int*>(tape->d_pi.ptr), static_cast<const int*>(tape->d_pj.ptr)};
+    if (int rc = launch<2>(*tape, seeds, s.d_x, s.ld_x, batch, ndir, static_cast<double*>(tape->ws_q.ptr), ndir, nullptr,
+                           static_cast<const double*>(tape->d_w.ptr), stream))
+        return rc;
+    const long long total = (long long)batch * nnz;
+    ub::tape::hessian_combine_kernel<<<unsigned((total + 255) / 256), 256, 0, stream>>>(
+        static_cast<const double*>(tape->ws_q.ptr), ndir, static_cast<const int*>(tape->d_di.ptr), static_cast<const int*>(tape->d_dj.ptr),
+        static_cast<const int*>(tape->d_pr.ptr), int(nnz), s.d_out, s.ld_out, batch);
+    ub_count_launch();
+    UBT_CUDA(cudaGetLastError());
+    return stage_out(s, vals, ld_vals, nnz, batch, mem, stream);
+}
+
+}  // extern "C"

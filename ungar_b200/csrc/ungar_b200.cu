@@ -44,6 +44,16 @@ int fail(int code, const char* fmt, ...) {
     g_last_error = buf;
     return code;
 }
+}  // namespace
+
+// Shared with the other translation units of the library (abi_internal.h).
+int ub_set_error(int code, const char* message) {
+    g_last_error = message;
+    return code;
+}
+void ub_count_launch() { ++g_launches; }
+
+namespace {
 
 #define UB_CUDA(call)                                                                              \
     do {                                                                                           \
