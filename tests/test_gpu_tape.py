@@ -213,3 +213,22 @@ def test_reference_lambda_tapes_on_the_register_machine(oracle, name, N, batch):
                 assert abs(v - ref.get(key, 0.0)) <= 1e-10 * max(1.0, abs(ref.get(key, 0.0))), key
         info = t.info()
         assert info["slots"] < 0.2 * info["live_nodes"] + 64  # liveness-based slots: the scratch is far smaller than the tape
+
+
+# ---------------------------------------------------------------------------------------------------------------------------
+# The reference's UNCHANGED Function class and example over the product's CppAD-compatible header (tests/build_ref_gpu.py)
+# ---------------------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("binary", ["function_tests_gpu", "function_example_gpu"])
+def test_reference_sources_run_on_the_gpu_through_the_product_header(binary):
+    """function_tests_gpu: known answers of test/autodiff/function.test.cpp:33-142 through include/ungar/autodiff/function.hpp;
+    function_example_gpu: example/autodiff/function.example.cpp as it lies (VariableMap + MakeFunction + TestJacobian/TestHessian,
+    UNGAR_ASSERT active).  Both evaluate every value and derivative with the register-machine kernels."""
+    import subprocess
+
+    exe = os.path.join(ROOT, "tests", "_ref_gpu", binary)
+    if not os.path.exists(exe):
+        pytest.skip("tests/_ref_gpu was not built (needs /root/reference at build time)")
+    proc = subprocess.run([exe], capture_output=True, text=True, timeout=600)
+    assert proc.returncode == 0, proc.stdout[-2000:] + proc.stderr[-2000:]
+    if binary == "function_tests_gpu":
+        assert "all reference known answers reproduced" in proc.stdout

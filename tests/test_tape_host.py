@@ -85,3 +85,23 @@ def test_tape_validation_errors():
     cols = np.array([5], dtype=np.int64)
     assert lib.ungar_b200_tape_set_jacobian_elements(h, rows.ctypes.data, cols.ctypes.data, 1) == _lib.EINVAL
     lib.ungar_b200_tape_destroy(h)
+
+
+def test_reference_binaries_over_the_product_header_fail_loudly_without_a_gpu():
+    """tests/_ref_gpu (the reference's unchanged function.hpp / function.example.cpp compiled against ungar_b200/include/cppad/cg.hpp):
+    taping and analysis run on the host, the first evaluation needs the device — there is no CPU fallback behind the header."""
+    import os
+    import subprocess
+
+    try:
+        import torch
+
+        if torch.cuda.is_available():
+            pytest.skip("behaviour without a GPU")
+    except ImportError:
+        pass
+    exe = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_ref_gpu", "function_example_gpu")
+    if not os.path.exists(exe):
+        pytest.skip("tests/_ref_gpu was not built (needs /root/reference at build time)")
+    proc = subprocess.run([exe], capture_output=True, text=True)
+    assert proc.returncode != 0 and "no CPU fallback" in proc.stderr

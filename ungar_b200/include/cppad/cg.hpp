@@ -1,0 +1,592 @@
+// Product header — the reference's plugin boundary, implemented on the GPU.
+//
+// A from-scratch implementation of the subset of the CppAD 20230000.0 + CppADCodeGen v2.4.3-ungar API that Ungar uses
+// (call sites: include/ungar/autodiff/function.hpp:42-613, include/ungar/utils/utils.hpp, include/ungar/autodiff/support/
+// quaternion.hpp, include/ungar/optimization/soft_inequality_constraint.hpp), so that the reference's UNCHANGED headers,
+// tests and examples compile against it with `-I ungar_b200/include` in place of the two libraries:
+//
+//   * CppAD::AD<CppAD::cg::CG<double>> is a tracing scalar that records an operation tape (CppAD's folding rules: operations
+//     on parameters are folded; `x * 0`, `x + 0`, `x * 1`, `x / 1`, `0 / x` are identities; pow(x, int) is a repeated
+//     product; CondExp differentiates the selected branch and its sparsity is the union of both branches; abs'(0) = 0);
+//   * CppAD::cg::GenericModel<double> — the class Ungar::Autodiff::Function holds (function.hpp:364-365) — forwards
+//     ForwardZero / SparseJacobian / SparseHessian / *Sparsity to the ungar_b200_tape_* entry points of
+//     include/ungar_b200.h: the lambda is evaluated by the register-machine kernels on the device
+//     (ungar_b200/csrc/tape_machine.cuh).  There is no CPU evaluation in this header;
+//   * where the reference generates C, runs gcc and dlopens a library (function.hpp:453-503), the "dynamic library" written
+//     to UNGAR_CODEGEN_FOLDER is the tape itself plus the options of its model, and loading it creates the device program.
+//
+// Link with -lungar_b200.
+#pragma once
+
+#include <cmath>
+#include <cstdint>
+#include <cstring>
+#include <filesystem>
+#include <fstream>
+#include <limits>
+#include <memory>
+#include <set>
+#include <stdexcept>
+#include <string>
+#include <type_traits>
+#include <vector>
+
+#include "ungar_b200.h"
+
+namespace CppAD {
+
+namespace cg {
+template <class Base>
+class CG {  // the code-generation scalar: only its value survives here
+  public:
+    CG() = default;
+    CG(Base v) : _v(v) {}  // NOLINT
+    Base getValue() const { return _v; }
+    bool isParameter() const { return true; }
+
+  private:
+    Base _v{};
+};
+}  // namespace cg
+
+namespace ub200 {
+
+using Node = ungar_b200_tape_node;
+
+struct Tape {
+    std::vector<Node> nodes;
+    std::int32_t n_indep = 0;
+    std::vector<std::int32_t> dep_id;  // node id, or -1 for a constant dependent
+    std::vector<double> dep_const;
+    std::int32_t push(std::uint8_t op, std::int32_t a = -1, std::int32_t b = -1, std::int32_t c = -1, std::int32_t d = -1,
+                      double k = 0.0) {
+        nodes.push_back(Node{op, a, b, c, d, k});
+        return static_cast<std::int32_t>(nodes.size()) - 1;
+    }
+};
+
+inline thread_local std::shared_ptr<Tape> g_recording;  // active between Independent() and ADFun's constructor
+
+inline void check(int status) {
+    if (status != UNGAR_B200_OK) throw std::runtime_error(std::string("ungar_b200: ") + ungar_b200_last_error());
+}
+
+enum : std::uint8_t {
+    OP_INDEP = UNGAR_B200_OP_INDEP, OP_CONST = UNGAR_B200_OP_CONST, OP_ADD = UNGAR_B200_OP_ADD, OP_SUB = UNGAR_B200_OP_SUB,
+    OP_MUL = UNGAR_B200_OP_MUL, OP_DIV = UNGAR_B200_OP_DIV, OP_NEG = UNGAR_B200_OP_NEG, OP_SQRT = UNGAR_B200_OP_SQRT,
+    OP_SIN = UNGAR_B200_OP_SIN, OP_COS = UNGAR_B200_OP_COS, OP_TAN = UNGAR_B200_OP_TAN, OP_ATAN = UNGAR_B200_OP_ATAN,
+    OP_ACOS = UNGAR_B200_OP_ACOS, OP_ASIN = UNGAR_B200_OP_ASIN, OP_EXP = UNGAR_B200_OP_EXP, OP_LOG = UNGAR_B200_OP_LOG,
+    OP_ABS = UNGAR_B200_OP_ABS, OP_POW = UNGAR_B200_OP_POW, OP_ATAN2 = UNGAR_B200_OP_ATAN2, OP_CLT = UNGAR_B200_OP_CLT,
+    OP_CLE = UNGAR_B200_OP_CLE, OP_CGT = UNGAR_B200_OP_CGT, OP_CGE = UNGAR_B200_OP_CGE, OP_CEQ = UNGAR_B200_OP_CEQ
+};
+
+using SparsitySets = std::vector<std::set<std::size_t>>;
+
+struct LibraryImage {  // what a "dynamic library" file holds: the tape and the options of its model
+    std::shared_ptr<Tape> tape;
+    bool jac = false, hes = false;
+    SparsitySets customJac, customHes;
+};
+inline void write_sets(std::ostream& f, const SparsitySets& s) {
+    const std::uint64_t n = s.size();
+    f.write(reinterpret_cast<const char*>(&n), 8);
+    for (const auto& row : s) {
+        const std::uint64_t m = row.size();
+        f.write(reinterpret_cast<const char*>(&m), 8);
+        for (std::size_t c : row) {
+            const std::uint64_t cc = c;
+            f.write(reinterpret_cast<const char*>(&cc), 8);
+        }
+    }
+}
+inline void read_sets(std::istream& f, SparsitySets& s) {
+    std::uint64_t n = 0;
+    f.read(reinterpret_cast<char*>(&n), 8);
+    s.assign(n, {});
+    for (auto& row : s) {
+        std::uint64_t m = 0;
+        f.read(reinterpret_cast<char*>(&m), 8);
+        for (std::uint64_t e = 0; e < m; ++e) {
+            std::uint64_t c = 0;
+            f.read(reinterpret_cast<char*>(&c), 8);
+            row.insert(static_cast<std::size_t>(c));
+        }
+    }
+}
+
+inline void save(const LibraryImage& img, const std::string& path) {
+    const Tape& t = *img.tape;
+    std::ofstream f(path, std::ios::binary);
+    const std::uint64_t magic = 0x3130505430303242ull, nn = t.nodes.size(), nd = t.dep_id.size();  // "B200TP01"
+    const std::int64_t ni = t.n_indep, flags = (img.jac ? 1 : 0) | (img.hes ? 2 : 0);
+    f.write(reinterpret_cast<const char*>(&magic), 8);
+    f.write(reinterpret_cast<const char*>(&nn), 8);
+    f.write(reinterpret_cast<const char*>(&nd), 8);
+    f.write(reinterpret_cast<const char*>(&ni), 8);
+    f.write(reinterpret_cast<const char*>(&flags), 8);
+    f.write(reinterpret_cast<const char*>(t.nodes.data()), nn * sizeof(Node));
+    f.write(reinterpret_cast<const char*>(t.dep_id.data()), nd * sizeof(std::int32_t));
+    f.write(reinterpret_cast<const char*>(t.dep_const.data()), nd * sizeof(double));
+    write_sets(f, img.customJac);
+    write_sets(f, img.customHes);
+    if (!f) throw std::runtime_error("ungar_b200: cannot write tape " + path);
+}
+
+inline LibraryImage load(const std::string& path) {
+    std::ifstream f(path, std::ios::binary);
+    std::uint64_t magic = 0, nn = 0, nd = 0;
+    std::int64_t ni = 0, flags = 0;
+    f.read(reinterpret_cast<char*>(&magic), 8);
+    f.read(reinterpret_cast<char*>(&nn), 8);
+    f.read(reinterpret_cast<char*>(&nd), 8);
+    f.read(reinterpret_cast<char*>(&ni), 8);
+    f.read(reinterpret_cast<char*>(&flags), 8);
+    if (!f || magic != 0x3130505430303242ull) throw std::runtime_error("ungar_b200: not a tape file: " + path);
+    LibraryImage img;
+    img.tape = std::make_shared<Tape>();
+    Tape& t = *img.tape;
+    t.nodes.resize(nn);
+    t.dep_id.resize(nd);
+    t.dep_const.resize(nd);
+    t.n_indep = static_cast<std::int32_t>(ni);
+    img.jac = flags & 1;
+    img.hes = flags & 2;
+    f.read(reinterpret_cast<char*>(t.nodes.data()), nn * sizeof(Node));
+    f.read(reinterpret_cast<char*>(t.dep_id.data()), nd * sizeof(std::int32_t));
+    f.read(reinterpret_cast<char*>(t.dep_const.data()), nd * sizeof(double));
+    read_sets(f, img.customJac);
+    read_sets(f, img.customHes);
+    if (!f) throw std::runtime_error("ungar_b200: truncated tape file: " + path);
+    return img;
+}
+
+}  // namespace ub200
+
+// ------------------------------------------------------------------------------------------------------------------
+// The tracing scalar.
+// ------------------------------------------------------------------------------------------------------------------
+template <class Base>
+class AD;
+
+template <>
+class AD<cg::CG<double>> {
+  public:
+    double v = 0.0;
+    std::int32_t id = -1;  // tape node, or -1 for a parameter (constant)
+
+    AD() = default;
+    template <class T, class = std::enable_if_t<std::is_arithmetic<T>::value>>
+    AD(T x) : v(static_cast<double>(x)) {}  // NOLINT
+    AD(const cg::CG<double>& x) : v(x.getValue()) {}  // NOLINT
+    AD(double value, std::int32_t node) : v(value), id(node) {}
+
+    bool variable() const { return id >= 0; }
+    AD& operator+=(const AD& o);
+    AD& operator-=(const AD& o);
+    AD& operator*=(const AD& o);
+    AD& operator/=(const AD& o);
+    AD operator-() const;
+    AD operator+() const { return *this; }
+    explicit operator double() const { return v; }
+};
+
+using ADCGD = AD<cg::CG<double>>;
+
+namespace ub200 {
+inline std::int32_t node_of(const ADCGD& x) {  // node id of an operand, materialising constants
+    return x.variable() ? x.id : g_recording->push(OP_CONST, -1, -1, -1, -1, x.v);
+}
+inline ADCGD unary(std::uint8_t op, const ADCGD& x, double value) {
+    if (!x.variable() || !g_recording) return ADCGD(value);
+    return ADCGD(value, g_recording->push(op, x.id));
+}
+inline ADCGD binary(std::uint8_t op, const ADCGD& a, const ADCGD& b, double value) {
+    if ((!a.variable() && !b.variable()) || !g_recording) return ADCGD(value);
+    const std::int32_t ia = node_of(a), ib = node_of(b);
+    return ADCGD(value, g_recording->push(op, ia, ib));
+}
+}  // namespace ub200
+
+// Binary operators with CppAD's "identical" folding rules.
+inline ADCGD operator+(const ADCGD& a, const ADCGD& b) {
+    if (a.variable() && !b.variable() && b.v == 0.0) return a;
+    if (b.variable() && !a.variable() && a.v == 0.0) return b;
+    return ub200::binary(ub200::OP_ADD, a, b, a.v + b.v);
+}
+inline ADCGD operator-(const ADCGD& a, const ADCGD& b) {
+    if (a.variable() && !b.variable() && b.v == 0.0) return a;
+    return ub200::binary(ub200::OP_SUB, a, b, a.v - b.v);
+}
+inline ADCGD operator*(const ADCGD& a, const ADCGD& b) {
+    if (a.variable() && !b.variable()) {
+        if (b.v == 0.0) return ADCGD(0.0);
+        if (b.v == 1.0) return a;
+    }
+    if (b.variable() && !a.variable()) {
+        if (a.v == 0.0) return ADCGD(0.0);
+        if (a.v == 1.0) return b;
+    }
+    return ub200::binary(ub200::OP_MUL, a, b, a.v * b.v);
+}
+inline ADCGD operator/(const ADCGD& a, const ADCGD& b) {
+    if (a.variable() && !b.variable() && b.v == 1.0) return a;
+    if (b.variable() && !a.variable() && a.v == 0.0) return ADCGD(0.0);
+    return ub200::binary(ub200::OP_DIV, a, b, a.v / b.v);
+}
+inline ADCGD ADCGD::operator-() const { return ub200::unary(ub200::OP_NEG, *this, -v); }
+inline ADCGD& ADCGD::operator+=(const ADCGD& o) { return *this = *this + o; }
+inline ADCGD& ADCGD::operator-=(const ADCGD& o) { return *this = *this - o; }
+inline ADCGD& ADCGD::operator*=(const ADCGD& o) { return *this = *this * o; }
+inline ADCGD& ADCGD::operator/=(const ADCGD& o) { return *this = *this / o; }
+
+#define UB200_AD_MIXED(op)                                                                                   \
+    template <class T, class = std::enable_if_t<std::is_arithmetic<T>::value>>                              \
+    inline ADCGD operator op(const ADCGD& a, T b) { return a op ADCGD(b); }                                 \
+    template <class T, class = std::enable_if_t<std::is_arithmetic<T>::value>>                              \
+    inline ADCGD operator op(T a, const ADCGD& b) { return ADCGD(a) op b; }
+UB200_AD_MIXED(+)
+UB200_AD_MIXED(-)
+UB200_AD_MIXED(*)
+UB200_AD_MIXED(/)
+#undef UB200_AD_MIXED
+
+// Comparisons act on values (the reference records with "no_compare_op", function.hpp:466).
+#define UB200_AD_CMP(op)                                                                                     \
+    inline bool operator op(const ADCGD& a, const ADCGD& b) { return a.v op b.v; }                          \
+    template <class T, class = std::enable_if_t<std::is_arithmetic<T>::value>>                              \
+    inline bool operator op(const ADCGD& a, T b) { return a.v op static_cast<double>(b); }                  \
+    template <class T, class = std::enable_if_t<std::is_arithmetic<T>::value>>                              \
+    inline bool operator op(T a, const ADCGD& b) { return static_cast<double>(a) op b.v; }
+UB200_AD_CMP(<)
+UB200_AD_CMP(<=)
+UB200_AD_CMP(>)
+UB200_AD_CMP(>=)
+UB200_AD_CMP(==)
+UB200_AD_CMP(!=)
+#undef UB200_AD_CMP
+
+// CppAD also defines its math functions for the base types (utils.hpp:958-966 calls CppAD::atan2 / sqrt on doubles).
+inline double atan2(double y, double x) { return std::atan2(y, x); }
+inline double sqrt(double x) { return std::sqrt(x); }
+inline double abs(double x) { return std::fabs(x); }
+inline double sin(double x) { return std::sin(x); }
+inline double cos(double x) { return std::cos(x); }
+inline double atan(double x) { return std::atan(x); }
+inline double log(double x) { return std::log(x); }
+inline double exp(double x) { return std::exp(x); }
+inline double pow(double x, double y) { return std::pow(x, y); }
+inline double pow(double x, int n) { return std::pow(x, n); }
+
+inline ADCGD sqrt(const ADCGD& x) { return ub200::unary(ub200::OP_SQRT, x, std::sqrt(x.v)); }
+inline ADCGD sin(const ADCGD& x) { return ub200::unary(ub200::OP_SIN, x, std::sin(x.v)); }
+inline ADCGD cos(const ADCGD& x) { return ub200::unary(ub200::OP_COS, x, std::cos(x.v)); }
+inline ADCGD tan(const ADCGD& x) { return ub200::unary(ub200::OP_TAN, x, std::tan(x.v)); }
+inline ADCGD atan(const ADCGD& x) { return ub200::unary(ub200::OP_ATAN, x, std::atan(x.v)); }
+inline ADCGD acos(const ADCGD& x) { return ub200::unary(ub200::OP_ACOS, x, std::acos(x.v)); }
+inline ADCGD asin(const ADCGD& x) { return ub200::unary(ub200::OP_ASIN, x, std::asin(x.v)); }
+inline ADCGD exp(const ADCGD& x) { return ub200::unary(ub200::OP_EXP, x, std::exp(x.v)); }
+inline ADCGD log(const ADCGD& x) { return ub200::unary(ub200::OP_LOG, x, std::log(x.v)); }
+inline ADCGD abs(const ADCGD& x) { return ub200::unary(ub200::OP_ABS, x, std::fabs(x.v)); }
+inline ADCGD fabs(const ADCGD& x) { return abs(x); }
+inline ADCGD atan2(const ADCGD& y, const ADCGD& x) { return ub200::binary(ub200::OP_ATAN2, y, x, std::atan2(y.v, x.v)); }
+inline ADCGD pow(const ADCGD& x, const ADCGD& y) { return ub200::binary(ub200::OP_POW, x, y, std::pow(x.v, y.v)); }
+inline ADCGD pow(const ADCGD& x, double y) { return pow(x, ADCGD(y)); }
+inline ADCGD pow(double x, const ADCGD& y) { return pow(ADCGD(x), y); }
+inline ADCGD pow(const ADCGD& x, int n) {  // CppAD: integer powers by repeated multiplication
+    if (n < 0) return ADCGD(1.0) / pow(x, -n);
+    ADCGD p(1.0);
+    for (int i = 0; i < n; ++i) p = p * x;
+    return p;
+}
+inline bool isfinite(const ADCGD& x) { return std::isfinite(x.v); }
+inline bool isnan(const ADCGD& x) { return std::isnan(x.v); }
+inline bool isinf(const ADCGD& x) { return std::isinf(x.v); }
+inline ADCGD conj(const ADCGD& x) { return x; }
+inline ADCGD real(const ADCGD& x) { return x; }
+inline ADCGD imag(const ADCGD&) { return ADCGD(0.0); }
+inline ADCGD abs2(const ADCGD& x) { return x * x; }
+inline cg::CG<double> Value(const ADCGD& x) {
+    if (x.variable() && ub200::g_recording) throw std::runtime_error("ungar_b200: Value() of a variable");
+    return cg::CG<double>(x.v);
+}
+
+namespace ub200 {
+inline ADCGD cond(std::uint8_t op, bool take_t, const ADCGD& a, const ADCGD& b, const ADCGD& t, const ADCGD& f) {
+    const ADCGD& sel = take_t ? t : f;
+    if (!g_recording || (!a.variable() && !b.variable())) return sel;  // decided by parameters: no operation
+    if (!t.variable() && !f.variable() && t.v == f.v) return sel;
+    const std::int32_t ia = node_of(a), ib = node_of(b), it = node_of(t), jf = node_of(f);
+    return ADCGD(sel.v, g_recording->push(op, ia, ib, it, jf));
+}
+}  // namespace ub200
+inline ADCGD CondExpLt(const ADCGD& a, const ADCGD& b, const ADCGD& t, const ADCGD& f) { return ub200::cond(ub200::OP_CLT, a.v < b.v, a, b, t, f); }
+inline ADCGD CondExpLe(const ADCGD& a, const ADCGD& b, const ADCGD& t, const ADCGD& f) { return ub200::cond(ub200::OP_CLE, a.v <= b.v, a, b, t, f); }
+inline ADCGD CondExpGt(const ADCGD& a, const ADCGD& b, const ADCGD& t, const ADCGD& f) { return ub200::cond(ub200::OP_CGT, a.v > b.v, a, b, t, f); }
+inline ADCGD CondExpGe(const ADCGD& a, const ADCGD& b, const ADCGD& t, const ADCGD& f) { return ub200::cond(ub200::OP_CGE, a.v >= b.v, a, b, t, f); }
+inline ADCGD CondExpEq(const ADCGD& a, const ADCGD& b, const ADCGD& t, const ADCGD& f) { return ub200::cond(ub200::OP_CEQ, a.v == b.v, a, b, t, f); }
+
+// CppAD::Independent(x): start recording with x as the independent variables (function.hpp:456-458).
+template <class Vector>
+void Independent(Vector& x) {
+    ub200::g_recording = std::make_shared<ub200::Tape>();
+    ub200::g_recording->n_indep = static_cast<std::int32_t>(x.size());
+    for (std::int32_t i = 0; i < static_cast<std::int32_t>(x.size()); ++i) {
+        const std::int32_t id = ub200::g_recording->push(ub200::OP_INDEP, i);
+        x[i] = ADCGD(x[i].v, id);
+    }
+}
+
+// CppAD::ADFun<Base>(x, y): stop recording; y are the dependents (function.hpp:465).
+template <class Base>
+class ADFun {
+  public:
+    template <class VectorX, class VectorY>
+    ADFun(const VectorX& x, const VectorY& y) : tape(ub200::g_recording) {
+        if (!tape) throw std::runtime_error("ungar_b200: ADFun without Independent()");
+        (void)x;
+        for (std::int64_t i = 0; i < static_cast<std::int64_t>(y.size()); ++i) {
+            tape->dep_id.push_back(y[i].variable() ? y[i].id : -1);
+            tape->dep_const.push_back(y[i].v);
+        }
+        ub200::g_recording.reset();
+    }
+    void optimize(const std::string& = "") {}
+    std::shared_ptr<ub200::Tape> tape;
+};
+
+// ------------------------------------------------------------------------------------------------------------------
+// CppADCodeGen subset: model sources, "compiler", dynamic library = tape file, GenericModel = device program.
+// ------------------------------------------------------------------------------------------------------------------
+namespace cg {
+
+template <class T>
+class ArrayView {
+  public:
+    ArrayView(T* data, std::size_t size) : _d(data), _n(size) {}
+    template <class U>
+    ArrayView(std::vector<U>& v) : _d(v.data()), _n(v.size()) {}  // NOLINT
+    T* data() const { return _d; }
+    std::size_t size() const { return _n; }
+    T& operator[](std::size_t i) const { return _d[i]; }
+
+  private:
+    T* _d;
+    std::size_t _n;
+};
+
+namespace system {
+template <class = void>
+struct SystemInfo {
+    static inline const std::string DYNAMIC_LIB_EXTENSION = ".so";
+};
+}  // namespace system
+
+using ub200::SparsitySets;
+
+// The model Ungar::Autodiff::Function evaluates (function.hpp:186-189, :224-228, :252-257): every call is one launch of the
+// register machine on the device through the C ABI (host buffers in and out, like the generated library's entry points).
+template <class Base>
+class GenericModel {
+    static_assert(std::is_same<Base, double>::value, "the reference instantiates GenericModel<double> only");
+
+  public:
+    GenericModel(std::string name, std::shared_ptr<ub200::Tape> tape, bool jac, bool hes, SparsitySets customJac,
+                 SparsitySets customHes, int device = 0)
+        : _name(std::move(name)), _tape(std::move(tape)), _jac(jac), _hes(hes) {
+        ub200::check(ungar_b200_tape_create(_tape->nodes.data(), static_cast<std::int64_t>(_tape->nodes.size()), _tape->n_indep,
+                                            _tape->dep_id.data(), _tape->dep_const.data(),
+                                            static_cast<std::int64_t>(_tape->dep_id.size()), device, &_handle));
+        if (_jac) {
+            flatten(customJac.empty() ? JacobianSparsitySet() : customJac, _jrows, _jcols);
+            select(_jrows, _jcols, &ungar_b200_tape_set_jacobian_elements);
+        }
+        if (_hes) {
+            flatten(customHes.empty() ? HessianSparsitySet() : customHes, _hrows, _hcols);
+            select(_hrows, _hcols, &ungar_b200_tape_set_hessian_elements);
+        }
+        _customJac = !customJac.empty();
+        _customHes = !customHes.empty();
+    }
+    ~GenericModel() { ungar_b200_tape_destroy(_handle); }
+    GenericModel(const GenericModel&)            = delete;
+    GenericModel& operator=(const GenericModel&) = delete;
+
+    const std::string& getName() const { return _name; }
+    bool isForwardZeroAvailable() const { return true; }
+    bool isSparseJacobianAvailable() const { return _jac; }
+    bool isSparseHessianAvailable() const { return _hes; }
+    bool isJacobianSparsityAvailable() const { return _jac; }
+    bool isHessianSparsityAvailable() const { return _hes; }
+    std::size_t Domain() const { return static_cast<std::size_t>(_tape->n_indep); }
+    std::size_t Range() const { return _tape->dep_id.size(); }
+
+    // Structural patterns over ALL independents [x; p] — the reference trims the parameter columns itself through
+    // setCustomSparse*Elements (function.hpp:529-574), after which the model reports the custom pattern.
+    SparsitySets JacobianSparsitySet() const {
+        if (_customJac) return unflatten(_jrows, _jcols, Range());
+        const std::int64_t *rows, *cols;
+        std::int64_t nnz;
+        ub200::check(ungar_b200_tape_jacobian_pattern(_handle, &rows, &cols, &nnz));
+        return unflatten(rows, cols, nnz, Range());
+    }
+    SparsitySets HessianSparsitySet() const {
+        if (_customHes) return unflatten(_hrows, _hcols, Domain());
+        const std::int64_t *rows, *cols;
+        std::int64_t nnz;
+        ub200::check(ungar_b200_tape_hessian_pattern(_handle, &rows, &cols, &nnz));
+        return unflatten(rows, cols, nnz, Domain());
+    }
+    void JacobianSparsity(std::vector<std::size_t>& rows, std::vector<std::size_t>& cols) const { rows = _jrows; cols = _jcols; }
+    void HessianSparsity(std::size_t, std::vector<std::size_t>& rows, std::vector<std::size_t>& cols) const { rows = _hrows; cols = _hcols; }
+
+    void ForwardZero(ArrayView<const Base> x, ArrayView<Base> y) const {
+        ub200::check(ungar_b200_tape_forward_zero(_handle, x.data(), 1, static_cast<std::int64_t>(x.size()), y.data(),
+                                                  static_cast<std::int64_t>(y.size()), UNGAR_B200_MEM_HOST, nullptr));
+    }
+    void SparseJacobian(ArrayView<const Base> x, ArrayView<Base> jac, const std::size_t** rows, const std::size_t** cols) const {
+        ub200::check(ungar_b200_tape_sparse_jacobian(_handle, x.data(), 1, static_cast<std::int64_t>(x.size()), jac.data(),
+                                                     static_cast<std::int64_t>(jac.size()), UNGAR_B200_MEM_HOST, nullptr));
+        *rows = _jrows.data();
+        *cols = _jcols.data();
+    }
+    void SparseHessian(ArrayView<const Base> x, ArrayView<const Base> w, ArrayView<Base> hess, const std::size_t** rows,
+                       const std::size_t** cols) const {
+        ub200::check(ungar_b200_tape_sparse_hessian(_handle, x.data(), w.data(), 1, static_cast<std::int64_t>(x.size()), hess.data(),
+                                                    static_cast<std::int64_t>(hess.size()), UNGAR_B200_MEM_HOST, nullptr));
+        *rows = _hrows.data();
+        *cols = _hcols.data();
+    }
+    // Beyond the CppADCodeGen API: the device program behind this model, for the batched entry points of include/ungar_b200.h.
+    ungar_b200_tape* deviceProgram() const { return _handle; }
+
+  private:
+    static void flatten(const SparsitySets& s, std::vector<std::size_t>& rows, std::vector<std::size_t>& cols) {
+        rows.clear();
+        cols.clear();
+        for (std::size_t r = 0; r < s.size(); ++r)
+            for (std::size_t c : s[r]) { rows.push_back(r); cols.push_back(c); }
+    }
+    static SparsitySets unflatten(const std::int64_t* rows, const std::int64_t* cols, std::int64_t nnz, std::size_t n) {
+        SparsitySets s(n);
+        for (std::int64_t e = 0; e < nnz; ++e) s[static_cast<std::size_t>(rows[e])].insert(static_cast<std::size_t>(cols[e]));
+        return s;
+    }
+    static SparsitySets unflatten(const std::vector<std::size_t>& rows, const std::vector<std::size_t>& cols, std::size_t n) {
+        SparsitySets s(n);
+        for (std::size_t e = 0; e < rows.size(); ++e) s[rows[e]].insert(cols[e]);
+        return s;
+    }
+    template <class Setter>
+    void select(const std::vector<std::size_t>& rows, const std::vector<std::size_t>& cols, Setter setter) {
+        std::vector<std::int64_t> r(rows.begin(), rows.end()), c(cols.begin(), cols.end());
+        static const std::int64_t none = 0;  // an empty selection still needs non-null arrays
+        ub200::check(setter(_handle, r.empty() ? &none : r.data(), c.empty() ? &none : c.data(), static_cast<std::int64_t>(r.size())));
+    }
+
+    std::string _name;
+    std::shared_ptr<ub200::Tape> _tape;
+    bool _jac, _hes, _customJac = false, _customHes = false;
+    ungar_b200_tape* _handle = nullptr;
+    std::vector<std::size_t> _jrows, _jcols, _hrows, _hcols;
+};
+
+template <class Base>
+class ModelCSourceGen {
+  public:
+    template <class ADFunT>
+    ModelCSourceGen(ADFunT& fun, std::string name) : tape(fun.tape), name(std::move(name)) {}
+    void setCreateSparseJacobian(bool b) { jac = b; }
+    void setCreateSparseHessian(bool b) { hes = b; }
+    void setCreateHessianSparsityByEquation(bool) {}
+    template <class Pattern>
+    void setCustomSparseJacobianElements(const Pattern& p) { customJac = convert(p); }
+    template <class Pattern>
+    void setCustomSparseHessianElements(const Pattern& p) { customHes = convert(p); }
+    std::shared_ptr<ub200::Tape> tape;
+    std::string name;
+    bool jac = false, hes = false;
+    SparsitySets customJac, customHes;
+
+  private:
+    template <class Pattern>
+    static SparsitySets convert(const Pattern& p) {
+        SparsitySets s(p.size());
+        for (std::size_t r = 0; r < p.size(); ++r) s[r].insert(p[r].begin(), p[r].end());
+        return s;
+    }
+};
+
+template <class Base>
+class ModelLibraryCSourceGen {
+  public:
+    explicit ModelLibraryCSourceGen(ModelCSourceGen<Base>& m) : model(&m) {}
+    ModelCSourceGen<Base>* model;
+};
+
+template <class Base>
+class GccCompiler {  // nothing is compiled: the flags of function.hpp:516-522 are accepted and ignored
+  public:
+    void setCompileLibFlags(const std::vector<std::string>&) {}
+    void addCompileLibFlag(const std::string&) {}
+    void setTemporaryFolder(const std::filesystem::path&) {}
+    void setSourcesFolder(const std::filesystem::path&) {}
+    void setSaveToDiskFirst(bool) {}
+};
+
+template <class Base>
+class DynamicLib {
+  public:
+    virtual ~DynamicLib() = default;
+    std::unique_ptr<GenericModel<Base>> model(const std::string& name) const {
+        return std::make_unique<GenericModel<Base>>(name, tape, jac, hes, customJac, customHes);
+    }
+    std::shared_ptr<ub200::Tape> tape;
+    bool jac = false, hes = false;
+    SparsitySets customJac, customHes;
+};
+
+// The "shared library" is one file: the tape plus the options of its model (the reference finds it again by name on the next
+// run, function.hpp:420-451).
+template <class Base>
+class LinuxDynamicLib : public DynamicLib<Base> {
+  public:
+    explicit LinuxDynamicLib(const std::filesystem::path& path) {
+        ub200::LibraryImage img = ub200::load(path.string());
+        this->tape = img.tape; this->jac = img.jac; this->hes = img.hes;
+        this->customJac = std::move(img.customJac); this->customHes = std::move(img.customHes);
+    }
+};
+
+template <class Base>
+class DynamicModelLibraryProcessor {
+  public:
+    DynamicModelLibraryProcessor(ModelLibraryCSourceGen<Base>& lib, std::string nameWithoutExtension)
+        : _lib(&lib), _path(std::move(nameWithoutExtension) + system::SystemInfo<>::DYNAMIC_LIB_EXTENSION) {}
+    std::unique_ptr<DynamicLib<Base>> createDynamicLibrary(GccCompiler<Base>&) {
+        const ModelCSourceGen<Base>& m = *_lib->model;
+        ub200::save(ub200::LibraryImage{m.tape, m.jac, m.hes, m.customJac, m.customHes}, _path);
+        auto lib = std::make_unique<DynamicLib<Base>>();
+        lib->tape = m.tape; lib->jac = m.jac; lib->hes = m.hes; lib->customJac = m.customJac; lib->customHes = m.customHes;
+        return lib;
+    }
+
+  private:
+    ModelLibraryCSourceGen<Base>* _lib;
+    std::string _path;
+};
+
+}  // namespace cg
+}  // namespace CppAD
+
+namespace std {
+template <>
+class numeric_limits<CppAD::ADCGD> : public numeric_limits<double> {
+  public:
+    static CppAD::ADCGD epsilon() { return numeric_limits<double>::epsilon(); }
+    static CppAD::ADCGD min() { return numeric_limits<double>::min(); }
+    static CppAD::ADCGD max() { return numeric_limits<double>::max(); }
+    static CppAD::ADCGD lowest() { return numeric_limits<double>::lowest(); }
+    static CppAD::ADCGD quiet_NaN() { return numeric_limits<double>::quiet_NaN(); }
+    static CppAD::ADCGD infinity() { return numeric_limits<double>::infinity(); }
+};
+}  // namespace std
