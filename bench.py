@@ -307,6 +307,20 @@ def ours(args, rank: int, local_rank: int, world: int):
         dist.all_reduce(e2e_ms, op=dist.ReduceOp.MAX)
     e2e_value = world * B * N * e2e_steps / (float(e2e_ms.item()) * 1e-3)
 
+    # the collective alone (report it separately): one all-gather of the [B, 32] summaries per outer iteration
+    collective = None
+    if world > 1:
+        fence()
+        e0.record()
+        for _ in range(args.steps):
+            dist.all_gather_into_tensor(gathered, d_sum)
+        e1.record()
+        fence()
+        coll_ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+        dist.all_reduce(coll_ms, op=dist.ReduceOp.MAX)
+        collective = {"op": "all_gather_into_tensor (NCCL)", "bytes_per_rank": B * 32 * elem, "ms_per_call": float(coll_ms.item()) / args.steps,
+                      "share_of_step": float(coll_ms.item()) / elapsed_ms}
+
     # full drop-in variant: the whole record goes back to the host every step (what a host-side QP solver needs)
     full_value = None
     if world == 1:
@@ -320,6 +334,30 @@ def ours(args, rank: int, local_rank: int, world: int):
             full_value = B * N * reps / (time.perf_counter() - t0)
         except Exception:
             full_value = None
+    # auxiliary: the loop that consumes the records — sweep + QP solve + line search, all on the device
+    sqp = None
+    if world == 1 and args.dtype == "f64":
+        try:
+            iters = 4  # quadruped.example.cpp:444
+            mult = 1.0 if args.model == "quadrotor" else 1.0 / N
+            opts = model.sqp_options(max_iterations=iters, constraint_violation_multiplier=mult)
+            work = d_xps[0].clone()
+            model.sqp_solve(work, opts, want_info=False)
+            reps, ms = 3, 0.0
+            for _ in range(reps):
+                work.copy_(d_xps[0])
+                e0.record()
+                status, _ = model.sqp_solve(work, opts, want_info=False)
+                e1.record()
+                torch.cuda.synchronize()
+                ms += e0.elapsed_time(e1)
+            counts = torch.bincount(status[:, 0], minlength=3).tolist()
+            sqp = {"ms_per_solve": ms / reps, "iterations": iters, "trajectories": B,
+                   "trajectory_iterations_per_sec": B * iters / (ms / reps * 1e-3),
+                   "status_counts": {"max_iterations": counts[0], "converged": counts[1], "line_search_failed": counts[2]},
+                   "path": "ungar_b200_sqp_solve(MEM_DEVICE): iterations x {KKT sweep, QP solve, backtracking line search}, no host round trip"}
+        except Exception as exc:  # auxiliary figure: never fails the bench line
+            sqp = {"error": str(exc)}
     clocks = sampler.stop() if sampler else None
 
     if rank != 0:
@@ -373,7 +411,8 @@ def ours(args, rank: int, local_rank: int, world: int):
         "e2e_full_record_d2h": ({"value": full_value, "unit": UNIT, "d2h_bytes_per_step": B * L["size"] * elem,
                                  "path": "ungar_b200_kkt_blocks(MEM_HOST): whole record back to the host every step"}
                                 if full_value else None),
-        "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu, "parity": parity,
+        "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu, "parity": parity, "sqp_loop": sqp,
+        "collective": collective,
     }
     print(json.dumps(line), flush=True)
     if world > 1:
