@@ -59,6 +59,17 @@ def _worker(rank, world, port, total, ragged, result_dir):
         assert status["trajectories"] == total
         assert np.isclose(status["total_cost"], expect[:, 24].sum())
         assert np.isclose(status["worst_eq_inf_norm"], expect[:, 26].max())
+        # overlapped exchange (double-buffered async all-gather): every posted iteration arrives intact, in rank order
+        if not ragged:
+            ex = sharding.SummaryExchange(b - a, torch.float64, "cpu")
+            for it in range(5):
+                k = ex.slot()
+                ex.local[k].copy_(local + it)
+                ex.post(k)
+                if it % 2 == 1:
+                    assert np.array_equal(ex.latest().numpy(), expect + it)
+            ex.drain()
+            assert np.array_equal(ex.latest().numpy(), expect + 4)
         # max-over-ranks timing reduction used by bench.py
         t = torch.tensor([float(rank + 1)], dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)

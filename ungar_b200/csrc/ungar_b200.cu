@@ -63,6 +63,14 @@ namespace {
                         __FILE__, __LINE__);                                                       \
     } while (0)
 
+// cudaFuncSetAttribute and the SM count are per DEVICE: a process that drives several GPUs through several handles must configure
+// each kernel once per device, not once per process.
+constexpr int kMaxDevices = 64;
+struct PerDevice {
+    int v[kMaxDevices] = {};
+    int& operator[](int device) { return v[device & (kMaxDevices - 1)]; }
+};
+
 struct DeviceBuffer {
     void* ptr  = nullptr;
     size_t cap = 0;
@@ -291,10 +299,10 @@ int launch_generic(ungar_b200_model& mdl, const T* xp, int64_t batch, int64_t ld
     using Sh = ub::SweepShape<Mdl, M>;
     auto kernel = ub::kkt_sweep_kernel<Mdl, T, M, BARRIER>;
     const int smem = Sh::total * int(sizeof(T));
-    static bool configured = false;  // per instantiation
-    if (!configured) {
+    static PerDevice configured;  // per instantiation and device
+    if (!configured[mdl.desc.device]) {
         UB_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        configured = true;
+        configured[mdl.desc.device] = 1;
     }
     const int tiles = (mdl.N + M - 1) / M;
     const long long grid = (long long)batch * tiles;
@@ -337,13 +345,13 @@ int launch_structured(ungar_b200_model& mdl, const double* xp, int64_t batch, in
                       cudaStream_t stream) {
     using Q = ub::QuadrupedStructured;
     auto kernel = ub::quadruped_structured_kernel<BARRIER>;
-    static bool configured = false;
-    static int sm_count = 148;
-    if (!configured) {
+    static PerDevice configured, sm_counts;
+    if (!configured[mdl.desc.device]) {
         UB_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, Q::SMEM_BYTES));
-        UB_CUDA(cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, mdl.desc.device));
-        configured = true;
+        UB_CUDA(cudaDeviceGetAttribute(&sm_counts[mdl.desc.device], cudaDevAttrMultiProcessorCount, mdl.desc.device));
+        configured[mdl.desc.device] = 1;
     }
+    const int sm_count = sm_counts[mdl.desc.device];
     const int runs_per_traj = (mdl.N + 9) / 10;
     const int run_len       = 2 * ((mdl.N + 2 * runs_per_traj - 1) / (2 * runs_per_traj));
     const long long total_runs = (long long)batch * runs_per_traj;
@@ -390,12 +398,13 @@ int launch_tpn_s(ungar_b200_model& mdl, const T* xp, int64_t batch, int64_t ld_x
     const int threads = ((mdl.N + 1 + 31) / 32) * 32;
     // TMA bulk stores need 16-byte aligned global rows: record base and stride
     const int bulk = ((reinterpret_cast<uintptr_t>(rec) & 15) == 0 && (ld_rec * sizeof(T)) % 16 == 0) ? 1 : 0;
-    static int configured_smem = 0, sm_count = 148;
-    if (configured_smem < smem) {
+    static PerDevice configured_smem, sm_counts;
+    if (configured_smem[mdl.desc.device] < smem) {
         UB_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        UB_CUDA(cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, mdl.desc.device));
-        configured_smem = smem;
+        UB_CUDA(cudaDeviceGetAttribute(&sm_counts[mdl.desc.device], cudaDevAttrMultiProcessorCount, mdl.desc.device));
+        configured_smem[mdl.desc.device] = smem;
     }
+    const int sm_count = sm_counts[mdl.desc.device];
     int per_sm = 1;
     UB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, threads, smem));
     const unsigned grid = unsigned(std::min<long long>(batch, (long long)sm_count * std::max(per_sm, 1)));
@@ -437,12 +446,13 @@ int launch_small(ungar_b200_model& mdl, const T* xp, int64_t batch, int64_t ld_x
     const int n_xp = int(mdl.layout.n_dec + mdl.layout.n_par);
     const auto offs = ub::SmallShape<Mdl, T>::offsets(mdl.N, n_xp);
     const int smem = WARPS * offs.total * int(sizeof(T));
-    static int configured_smem = 0, sm_count = 148;
-    if (configured_smem < smem) {
+    static PerDevice configured_smem, sm_counts;
+    if (configured_smem[mdl.desc.device] < smem) {
         UB_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        UB_CUDA(cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, mdl.desc.device));
-        configured_smem = smem;
+        UB_CUDA(cudaDeviceGetAttribute(&sm_counts[mdl.desc.device], cudaDevAttrMultiProcessorCount, mdl.desc.device));
+        configured_smem[mdl.desc.device] = smem;
     }
+    const int sm_count = sm_counts[mdl.desc.device];
     int per_sm = 1;
     UB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, WARPS * 32, smem));
     const long long want = (batch + WARPS - 1) / WARPS;
@@ -582,10 +592,10 @@ int launch_qp_schur(ungar_b200_model& mdl, const void* rec, int64_t batch, int64
                     int64_t ld_mult, const int32_t* skip_status, cudaStream_t stream) {
     using Q = ub::QpShape;
     if (int rc = mdl.ws_qp.reserve(size_t(batch) * (mdl.N + 1) * Q::WS_GROUP * sizeof(double))) return rc;
-    static bool configured = false;
-    if (!configured) {
+    static PerDevice configured;
+    if (!configured[mdl.desc.device]) {
         UB_CUDA(cudaFuncSetAttribute(ub::qp_schur_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, Q::SMEM_BYTES));
-        configured = true;
+        configured[mdl.desc.device] = 1;
     }
     const unsigned grid = unsigned((batch + Q::WARPS - 1) / Q::WARPS);
     ub::qp_schur_kernel<<<grid, Q::WARPS * 32, Q::SMEM_BYTES, stream>>>(
@@ -603,10 +613,10 @@ int launch_qp_riccati(ungar_b200_model& mdl, const void* rec, int64_t batch, int
     using R = ub::RiccatiShape<Mdl>;
     if (int rc = mdl.ws_qp.reserve(size_t(batch) * mdl.N * R::WS_STAGE * sizeof(double))) return rc;
     auto kernel = ub::qp_riccati_kernel<Mdl>;
-    static bool configured = false;
-    if (!configured) {
+    static PerDevice configured;
+    if (!configured[mdl.desc.device]) {
         UB_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, R::SMEM_BYTES));
-        configured = true;
+        configured[mdl.desc.device] = 1;
     }
     const unsigned grid = unsigned((batch + R::WARPS - 1) / R::WARPS);
     kernel<<<grid, R::WARPS * 32, R::SMEM_BYTES, stream>>>(static_cast<const double*>(rec), ld_rec, static_cast<double*>(mdl.ws_qp.ptr),
@@ -640,10 +650,10 @@ int launch_line_search_t(ungar_b200_model& mdl, double* xp, int64_t batch, int64
     auto kernel = ub::line_search_kernel<Mdl, double>;
     const int smem = int((mdl.layout.n_dec + mdl.layout.n_par) * sizeof(double));
     if (smem > 220 * 1024) return fail(UNGAR_B200_EUNSUPPORTED, "horizon too long for the shared-memory trial point (%d bytes)", smem);
-    static int configured = 0;  // per instantiation: largest size configured so far
-    if (smem > configured) {
+    static PerDevice configured;  // per instantiation and device: largest size configured so far
+    if (smem > configured[mdl.desc.device]) {
         UB_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        configured = smem;
+        configured[mdl.desc.device] = smem;
     }
     const ub::LineSearchParams P{o.alpha_min, o.theta_min, o.theta_max, o.eta, o.gamma_phi, o.gamma_theta, o.gamma_alpha,
                                  o.constraint_violation_multiplier, o.objective_tolerance};

@@ -41,6 +41,60 @@ def gather_summaries(local, group=None):
     return torch.cat([out[r * width:r * width + n] for r, n in enumerate(sizes)], dim=0)
 
 
+class SummaryExchange:
+    """The per-iteration all-gather, overlapped with the next iteration's sweep.
+
+    ``slot()`` hands out one of two local summary buffers; ``post(slot)`` starts the all-gather of that buffer with ``async_op=True``
+    (NCCL runs it on its own stream, ordered after the work already queued on the current stream), so the sweep of iteration i + 1
+    runs while the summaries of iteration i cross NVLink.  A buffer is reused two iterations later, after ``slot()`` has made the
+    current stream wait for the collective that read it.  ``latest()`` waits for the newest posted gather and returns
+    ``[world * B_local, 32]`` in rank order.  Equal shard sizes only (the bench's weak-scaling layout)."""
+
+    def __init__(self, batch_local: int, dtype, device, group=None):
+        import torch
+        import torch.distributed as dist
+
+        self.group = group
+        self.world = dist.get_world_size(group) if dist.is_available() and dist.is_initialized() else 1
+        self.local = [torch.zeros((batch_local, SUMMARY_SIZE), dtype=dtype, device=device) for _ in range(2)]
+        self.gathered = [torch.zeros((self.world * batch_local, SUMMARY_SIZE), dtype=dtype, device=device) for _ in range(2)]
+        self.pending = [None, None]
+        self.turn = 0
+        self.newest = None
+
+    def slot(self) -> int:
+        k = self.turn
+        self.turn ^= 1
+        if self.pending[k] is not None:  # the gather posted two iterations ago still owns this buffer
+            self.pending[k].wait()
+            self.pending[k] = None
+        return k
+
+    def post(self, k: int) -> None:
+        import torch.distributed as dist
+
+        if self.world == 1:
+            self.gathered[k] = self.local[k]
+        else:
+            self.pending[k] = dist.all_gather_into_tensor(self.gathered[k], self.local[k], group=self.group, async_op=True)
+        self.newest = k
+
+    def latest(self):
+        if self.newest is None:
+            raise RuntimeError("no summaries were posted yet")
+        k = self.newest
+        if self.pending[k] is not None:
+            self.pending[k].wait()
+            self.pending[k] = None
+        return self.gathered[k]
+
+    def drain(self) -> None:
+        for k in (0, 1):
+            if self.pending[k] is not None:
+                self.pending[k].wait()
+                self.pending[k] = None
+
+
 def fleet_status(summaries) -> dict:
     """What an outer loop looks at after the gather: total objective, worst constraint violations."""
     return {"trajectories": int(summaries.shape[0]), "total_cost": float(summaries[:, SUMMARY_FIELDS["cost"]].sum()),
