@@ -269,6 +269,17 @@ int ungar_b200_tape_sparse_jacobian(ungar_b200_tape* tape, const double* x, int6
 int ungar_b200_tape_sparse_hessian(ungar_b200_tape* tape, const double* x, const double* weights, int64_t batch,
                                    int64_t ld_x, double* vals, int64_t ld_vals, int32_t mem, void* stream);
 
+/* Replaces osqp::OsqpSolver::Solve (optimization/soft_sqp.hpp:226) for ANY equality-constrained QP — the only kind
+ * SoftSQPOptimizer poses (l = u = -g, soft_sqp.hpp:155-157) — when the problem has no stage-wise solver:
+ *     min 1/2 x^T P x + q^T x   s.t.  A x = b
+ * P (n x n, upper triangle used, like OSQP) and A (m x n) in compressed-sparse-column form, HOST arrays; x[n] and y[m]
+ * (multipliers, may be NULL) HOST outputs.  One dense LU of the quasi-definite KKT matrix [P + sigma I, A^T; A, -rho I]
+ * on the device (scatter kernel + cuSOLVER getrf/getrs); n + m <= 16384.  This is the back end of the osqp++.h
+ * stand-in in ungar_b200/include, which lets the reference's unchanged SoftSQPOptimizer run on the GPU. */
+int ungar_b200_kkt_solve_csc(int64_t n, int64_t m, const int32_t* P_colptr, const int32_t* P_rowidx, const double* P_vals,
+                             const double* q, const int32_t* A_colptr, const int32_t* A_rowidx, const double* A_vals,
+                             const double* b, double sigma, double rho, double* x, double* y, int32_t device);
+
 /* Device-side timing of the dominant kernel (the KKT sweep): when enabled, every sweep launch is bracketed by
  * CUDA events on the launching stream; ungar_b200_sweep_times synchronises and returns up to `cap` most recent
  * durations in milliseconds (oldest first) and clears the ring. */

@@ -7,6 +7,10 @@ evaluate their lambdas on the GPU.
                          with plain checks in oracle/ref_drivers/function_tests.cpp) through the reference's include/ungar/autodiff/function.hpp
   function_example_gpu   example/autodiff/function.example.cpp compiled as it lies: VariableMap + MakeFunction + TestJacobian /
                          TestHessian (AD vs finite differences) with UNGAR_ASSERT active
+  soft_sqp_tests_gpu     the reference's unchanged SoftSQPOptimizer on the three NLPs of test/optimization/soft_sqp.test.cpp:34-111
+                         (tests/ref_drivers/soft_sqp_tests.cpp): functions AND local QPs on the device (osqp++.h stand-in)
+  example_<name>_gpu     example/mpc/{quadrotor,rc_car}.example.cpp compiled as they lie (tests/ref_drivers/example_driver.cpp bounds
+                         their endless MPC loop through UNGAR_B200_MAX_QP_SOLVES)
 
 Needs /root/reference (absent on the GPU box: the prebuilt binaries travel with the snapshot; tests/_ref_gpu is git-ignored).
 Nothing of the reference is copied into the repository.
@@ -43,7 +47,7 @@ def main(force: bool = False) -> bool:
             open(marker, "w").close()
     spdlog = glob.glob("/opt/prime-rl/.venv/lib/python3*/site-packages/flashinfer/data/spdlog/include")
     os.makedirs(os.path.join(OUT, "tapes"), exist_ok=True)
-    flags = ["-std=c++20", "-O1", "-DUNGAR_CONFIG_ENABLE_AUTODIFF", "-DFMT_HEADER_ONLY", f'-DUNGAR_CODEGEN_FOLDER="{OUT}/tapes"',
+    flags = ["-std=c++20", "-O1", "-DUNGAR_CONFIG_ENABLE_AUTODIFF", "-DUNGAR_CONFIG_ENABLE_OPTIMIZATION", "-DFMT_HEADER_ONLY", f'-DUNGAR_CODEGEN_FOLDER="{OUT}/tapes"',
              "-ftemplate-backtrace-limit=1", "-fconstexpr-depth=2147483647", "-fconstexpr-loop-limit=2147483647",
              "-fconstexpr-cache-depth=2147483647", "-fconstexpr-ops-limit=2147483647",
              f"-I{ROOT}/ungar_b200/include", f"-I{ROOT}/include", f"-I{REF}/include", f"-I{DEPS}/eigen-3.4.0",
@@ -51,14 +55,18 @@ def main(force: bool = False) -> bool:
     if spdlog:
         flags += ["-DUNGAR_CONFIG_ENABLE_LOGGING", f"-I{spdlog[0]}"]
     link = [lib, f"-Wl,-rpath,{os.path.dirname(lib)}", "-Wl,-rpath,$ORIGIN/../../ungar_b200"]
-    header = os.path.join(ROOT, "ungar_b200/include/cppad/cg.hpp")
-    targets = [("function_tests_gpu", os.path.join(ROOT, "oracle/ref_drivers/function_tests.cpp")),
-               ("function_example_gpu", os.path.join(REF, "example/autodiff/function.example.cpp"))]
-    for name, src in targets:
+    headers = [os.path.join(ROOT, "ungar_b200/include", h) for h in ("cppad/cg.hpp", "osqp++.h")] + [os.path.join(ROOT, "include/ungar_b200.h")]
+    driver = os.path.join(HERE, "ref_drivers/example_driver.cpp")
+    targets = [("function_tests_gpu", os.path.join(ROOT, "oracle/ref_drivers/function_tests.cpp"), []),
+               ("function_example_gpu", os.path.join(REF, "example/autodiff/function.example.cpp"), []),
+               ("soft_sqp_tests_gpu", os.path.join(HERE, "ref_drivers/soft_sqp_tests.cpp"), [])]
+    for example in ("quadrotor", "rc_car"):
+        targets.append((f"example_{example}_gpu", driver, [f'-DUNGAR_EXAMPLE_SOURCE="{REF}/example/mpc/{example}.example.cpp"']))
+    for name, src, extra in targets:
         exe = os.path.join(OUT, name)
-        if not force and os.path.exists(exe) and os.path.getmtime(exe) >= max(os.path.getmtime(src), os.path.getmtime(header)):
+        if not force and os.path.exists(exe) and os.path.getmtime(exe) >= max([os.path.getmtime(src)] + [os.path.getmtime(h) for h in headers]):
             continue
-        cmd = [CXX] + flags + ["-o", exe, src] + link
+        cmd = [CXX] + flags + extra + ["-o", exe, src] + link
         print("+", " ".join(cmd[:4]), "...", src, flush=True)
         subprocess.run(cmd, check=True)
     print("build_ref_gpu: ok")

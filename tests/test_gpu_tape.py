@@ -232,3 +232,47 @@ def test_reference_sources_run_on_the_gpu_through_the_product_header(binary):
     assert proc.returncode == 0, proc.stdout[-2000:] + proc.stderr[-2000:]
     if binary == "function_tests_gpu":
         assert "all reference known answers reproduced" in proc.stdout
+
+
+def test_reference_soft_sqp_test_runs_on_the_gpu_through_the_product_headers():
+    """test/optimization/soft_sqp.test.cpp:34-111 through the reference's UNCHANGED SoftSQPOptimizer: functions taped and evaluated
+    on the device (cppad/cg.hpp), local QPs solved on the device (osqp++.h -> ungar_b200_kkt_solve_csc)."""
+    import subprocess
+
+    exe = os.path.join(ROOT, "tests", "_ref_gpu", "soft_sqp_tests_gpu")
+    if not os.path.exists(exe):
+        pytest.skip("tests/_ref_gpu was not built (needs /root/reference at build time)")
+    proc = subprocess.run([exe], capture_output=True, text=True, timeout=900)
+    assert proc.returncode == 0, proc.stdout[-2000:] + proc.stderr[-2000:]
+    assert "all reference optima reproduced" in proc.stdout
+
+
+def _mpc_log(exe, env_name, solves):
+    """Numbers of every 't = ..., obj = ..., eqs = ...' line an example logs (quadrotor.example.cpp:412-426)."""
+    import re
+    import subprocess
+
+    proc = subprocess.run([exe], capture_output=True, text=True, timeout=1200, env=dict(os.environ, **{env_name: str(solves)}),
+                          cwd=os.path.dirname(exe))
+    assert proc.returncode == 0, proc.stdout[-1500:] + proc.stderr[-1500:]
+    rows = []
+    for line in (proc.stdout + proc.stderr).splitlines():
+        if " t = " in line:
+            rows.append([float(v) for v in re.findall(r"-?\d+\.\d+", line.split(" t = ", 1)[1])])
+    return rows
+
+
+@pytest.mark.parametrize("example,solves", [("rc_car", 60), ("quadrotor", 60)])
+def test_unchanged_mpc_examples_on_the_gpu_match_the_cpu_build(example, solves):
+    """example/mpc/{rc_car,quadrotor}.example.cpp compiled AS THEY LIE twice: against oracle/refshim (CPU tape evaluator + CPU sparse
+    LU: the oracle) and against the product headers (register machine + device KKT solve).  The closed-loop MPC logs — time, objective,
+    constraint violations, tracked outputs, applied inputs, printed with three decimals — must agree step by step."""
+    gpu = os.path.join(ROOT, "tests", "_ref_gpu", f"example_{example}_gpu")
+    cpu = os.path.join(ROOT, "oracle", "_ref", f"example_{example}_N30")
+    if not (os.path.exists(gpu) and os.path.exists(cpu)):
+        pytest.skip("reference example binaries were not built (needs /root/reference at build time)")
+    got = _mpc_log(gpu, "UNGAR_B200_MAX_QP_SOLVES", solves)
+    ref = _mpc_log(cpu, "UNGAR_REF_MAX_SOLVES", solves)
+    assert len(ref) >= 5 and len(got) == len(ref), (len(got), len(ref))
+    for step, (a, b) in enumerate(zip(got, ref)):
+        assert len(a) == len(b) and np.allclose(a, b, rtol=0, atol=2.1e-3), (step, a, b)  # three printed decimals

@@ -27,7 +27,7 @@ SYMBOLS = [
     "ungar_b200_abi_version", "ungar_b200_sqp_options_default", "ungar_b200_line_search", "ungar_b200_sqp_solve",
     "ungar_b200_tape_create", "ungar_b200_tape_destroy", "ungar_b200_tape_info", "ungar_b200_tape_jacobian_pattern",
     "ungar_b200_tape_hessian_pattern", "ungar_b200_tape_set_jacobian_elements", "ungar_b200_tape_set_hessian_elements",
-    "ungar_b200_tape_forward_zero", "ungar_b200_tape_sparse_jacobian", "ungar_b200_tape_sparse_hessian",
+    "ungar_b200_tape_forward_zero", "ungar_b200_tape_sparse_jacobian", "ungar_b200_tape_sparse_hessian", "ungar_b200_kkt_solve_csc",
 ]
 
 
@@ -98,6 +98,7 @@ def load() -> ctypes.CDLL:
     for name in ("ungar_b200_tape_forward_zero", "ungar_b200_tape_sparse_jacobian"):
         getattr(L, name).argtypes = [c_vp, c_vp, c_i64, c_i64, c_vp, c_i64, c_i32, c_vp]
     L.ungar_b200_tape_sparse_hessian.argtypes = [c_vp, c_vp, c_vp, c_i64, c_i64, c_vp, c_i64, c_i32, c_vp]
+    L.ungar_b200_kkt_solve_csc.argtypes = [c_i64, c_i64, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_f64, c_f64, c_vp, c_vp, c_i32]
     L.ungar_b200_set_profiling.argtypes = [c_i32]
     L.ungar_b200_sweep_times.argtypes = [ctypes.POINTER(ctypes.c_float), c_i32, ctypes.POINTER(c_i32)]
     L.ungar_b200_launch_count.restype = c_i64

@@ -9,7 +9,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
 LIB = os.path.join(HERE, "libungar_b200.so")
-SOURCES = [os.path.join(HERE, "csrc", "ungar_b200.cu"), os.path.join(HERE, "csrc", "tape.cu")]
+SOURCES = [os.path.join(HERE, "csrc", f) for f in ("ungar_b200.cu", "tape.cu", "kkt_dense.cu")]
 HEADERS = [os.path.join(HERE, "csrc", f) for f in ("dual.cuh", "models.cuh", "sweep.cuh", "sweep_structured.cuh", "sweep_tpn.cuh", "sweep_small.cuh", "qp_schur.cuh", "qp_riccati.cuh", "line_search.cuh", "tape_machine.cuh", "abi_internal.h")] + [
     os.path.join(ROOT, "include", "ungar_b200.h")]
 
@@ -18,6 +18,8 @@ NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "--expt-relaxed-constexpr", "-diag-suppress", "20011,20013,20014,20015",
     "-Xcompiler", "-fPIC", "-shared",
+    # cuSOLVER's dense LU backs the generic QP fallback (csrc/kkt_dense.cu); everything else is hand-written
+    "-lcusolver", "-Xlinker", "-rpath=/usr/local/cuda/lib64",
 ]
 
 
