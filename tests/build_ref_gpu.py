@@ -9,7 +9,7 @@ evaluate their lambdas on the GPU.
                          TestHessian (AD vs finite differences) with UNGAR_ASSERT active
   soft_sqp_tests_gpu     the reference's unchanged SoftSQPOptimizer on the three NLPs of test/optimization/soft_sqp.test.cpp:34-111
                          (tests/ref_drivers/soft_sqp_tests.cpp): functions AND local QPs on the device (osqp++.h stand-in)
-  example_<name>_gpu     example/mpc/{quadrotor,rc_car}.example.cpp compiled as they lie (tests/ref_drivers/example_driver.cpp bounds
+  example_<name>_gpu     example/mpc/{quadrotor,rc_car,quadruped}.example.cpp compiled as they lie (tests/ref_drivers/example_driver.cpp bounds
                          their endless MPC loop through UNGAR_B200_MAX_QP_SOLVES)
 
 Needs /root/reference (absent on the GPU box: the prebuilt binaries travel with the snapshot; tests/_ref_gpu is git-ignored).
@@ -60,7 +60,7 @@ def main(force: bool = False) -> bool:
     targets = [("function_tests_gpu", os.path.join(ROOT, "oracle/ref_drivers/function_tests.cpp"), []),
                ("function_example_gpu", os.path.join(REF, "example/autodiff/function.example.cpp"), []),
                ("soft_sqp_tests_gpu", os.path.join(HERE, "ref_drivers/soft_sqp_tests.cpp"), [])]
-    for example in ("quadrotor", "rc_car"):
+    for example in ("quadrotor", "rc_car", "quadruped"):
         targets.append((f"example_{example}_gpu", driver, [f'-DUNGAR_EXAMPLE_SOURCE="{REF}/example/mpc/{example}.example.cpp"']))
     for name, src, extra in targets:
         exe = os.path.join(OUT, name)

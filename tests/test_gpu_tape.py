@@ -262,9 +262,9 @@ def _mpc_log(exe, env_name, solves):
     return rows
 
 
-@pytest.mark.parametrize("example,solves", [("rc_car", 60), ("quadrotor", 60)])
+@pytest.mark.parametrize("example,solves", [("rc_car", 60), ("quadrotor", 60), ("quadruped", 24)])
 def test_unchanged_mpc_examples_on_the_gpu_match_the_cpu_build(example, solves):
-    """example/mpc/{rc_car,quadrotor}.example.cpp compiled AS THEY LIE twice: against oracle/refshim (CPU tape evaluator + CPU sparse
+    """example/mpc/{rc_car,quadrotor,quadruped}.example.cpp compiled AS THEY LIE twice: against oracle/refshim (CPU tape evaluator + CPU sparse
     LU: the oracle) and against the product headers (register machine + device KKT solve).  The closed-loop MPC logs — time, objective,
     constraint violations, tracked outputs, applied inputs, printed with three decimals — must agree step by step."""
     gpu = os.path.join(ROOT, "tests", "_ref_gpu", f"example_{example}_gpu")
