@@ -304,7 +304,8 @@ def ours(args, rank: int, local_rank: int, world: int):
     e0.record()
     for _ in range(e2e_steps):
         model.step(xp_host_np, records=d_rec, summaries=sum_host_np)
-        if world > 1:
+        if world > 1:  # the step's own summaries (they landed on the host) are what the ranks exchange
+            d_sum.copy_(sum_host, non_blocking=True)
             dist.all_gather_into_tensor(gathered, d_sum)
     e1.record()
     fence()
