@@ -32,39 +32,49 @@ struct QuadrupedStructured {
     static constexpr int PAIR_A = 2 * NA, PAIR_H = 2 * TRI, PAIR_C = 2 * NC;
     static constexpr int STAGE = PAIR_A + PAIR_H + PAIR_C;  // 3008 doubles
     static constexpr int RUN = 10;                          // nodes per run (even)
-    static constexpr int CORE = 41;                         // doubles per node core (odd stride: conflict-free)
-    static constexpr int oCORE = STAGE, oXS = oCORE + 452, oUS = oXS + (RUN + 2) * NX, oPS = oUS + (RUN + 1) * NU,
-                         PER_WARP = 4200;                   // doubles per team (33 600 B, multiple of 16)
-    static_assert(oPS + (RUN + 1) * NP <= PER_WARP, "per-warp shared memory layout");
+    static constexpr int CORE = 77;                         // doubles per node core (odd stride: conflict-free)
+    static constexpr int NRHO = 49;                         // the shared parameter block Rho (quadruped.example.cpp:129-134)
+    static constexpr int oCORE = STAGE, oXS = oCORE + 848, oUS = oXS + (RUN + 2) * NX, oPS = oUS + (RUN + 1) * NU,
+                         oRHO = oPS + (RUN + 1) * NP + 1,   // 4596
+                         PER_WARP = 4646;                   // doubles per team (37 168 B, multiple of 16; 6 teams per SM)
+    static_assert(oRHO + NRHO <= PER_WARP && (PER_WARP * 8) % 16 == 0, "per-warp shared memory layout");
+    static_assert((RUN + 1) * CORE <= 848, "core slots: halo node + RUN nodes");
     static constexpr int WARPS = 2;                         // one team of two warps per CTA; 6 CTAs / SM -> 12 warps
     static constexpr int SMEM_BYTES = PER_WARP * 8;         // the team shares one staging image + inputs (33 600 B)
     // core slot layout
-    static constexpr int cR = 0, cQ = 9, cE = 21, cXN = 25, cSGN = 38;
+    static constexpr int cR = 0, cQ = 9, cE = 21, cXN = 25, cSGN = 38, cM = 39;  // cM: the four 3x3 matrices d(R(q) v)/dq_c
 };
 
 __device__ __forceinline__ double pick3(int c, double a0, double a1, double a2) { return c == 0 ? a0 : (c == 1 ? a1 : a2); }
-
-// d (R(q) v) / d q_c for the Eigen rotation formula v + 2 w (qv x v) + 2 qv x (qv x v); c = 0..2 -> qv_c, 3 -> w.
-__device__ __forceinline__ void drot_dq(int c, double qx, double qy, double qz, double qw, double v0, double v1, double v2,
-                                        double& o0, double& o1, double& o2) {
-    const double e0 = c == 0 ? 1.0 : 0.0, e1 = c == 1 ? 1.0 : 0.0, e2 = c == 2 ? 1.0 : 0.0;
-    const double qv_v = qx * v0 + qy * v1 + qz * v2;
-    const double vc = pick3(c, v0, v1, v2), qc = pick3(c, qx, qy, qz);
-    // c < 3: 2 [ e_c (qv.v) + qv v_c - 2 v qv_c ] + 2 w (e_c x v)
-    const double a0 = 2.0 * (e0 * qv_v + qx * vc - 2.0 * v0 * qc) + 2.0 * qw * (e1 * v2 - e2 * v1);
-    const double a1 = 2.0 * (e1 * qv_v + qy * vc - 2.0 * v1 * qc) + 2.0 * qw * (e2 * v0 - e0 * v2);
-    const double a2 = 2.0 * (e2 * qv_v + qz * vc - 2.0 * v2 * qc) + 2.0 * qw * (e0 * v1 - e1 * v0);
-    const bool isw = c == 3;  // 2 (qv x v)
-    o0 = isw ? 2.0 * (qy * v2 - qz * v1) : a0;
-    o1 = isw ? 2.0 * (qz * v0 - qx * v2) : a1;
-    o2 = isw ? 2.0 * (qx * v1 - qy * v0) : a2;
-}
 
 // R with R v = v + 2 w (qv x v) + 2 qv x (qv x v)  (Eigen/src/Geometry/Quaternion.h:531-541), row-major into out[9].
 __device__ __forceinline__ void rot_matrix(double x, double y, double z, double w, double* out) {
     out[0] = 1.0 - 2.0 * (y * y + z * z); out[1] = 2.0 * (x * y - w * z);       out[2] = 2.0 * (x * z + w * y);
     out[3] = 2.0 * (x * y + w * z);       out[4] = 1.0 - 2.0 * (x * x + z * z); out[5] = 2.0 * (y * z - w * x);
     out[6] = 2.0 * (x * z - w * y);       out[7] = 2.0 * (y * z + w * x);       out[8] = 1.0 - 2.0 * (x * x + y * y);
+}
+
+// The four matrices M_c with d(R(q) v)/dq_c = M_c v for the Eigen rotation formula (R v = v + 2 w (qv x v) + 2 qv x (qv x v)):
+//   c < 3:  M_c = 2 w [e_c]x + 2 (e_c qv^T + qv e_c^T - 2 q_c I),      c = 3 (w):  M_3 = 2 [qv]x.        Row-major, 9 entries each.
+// Computed once per node in phase A (thread-per-node); phase B applies them to f, r and the previous node's r as 3x3 mat-vecs.
+__device__ __forceinline__ void drot_matrices(double x, double y, double z, double w, double* __restrict__ M) {
+    const double tx = 2.0 * x, ty = 2.0 * y, tz = 2.0 * z, tw = 2.0 * w;
+    // c = 0
+    M[0] = 0.0;        M[1] = ty;         M[2] = tz;
+    M[3] = ty;         M[4] = -2.0 * tx;  M[5] = -tw;
+    M[6] = tz;         M[7] = tw;         M[8] = -2.0 * tx;
+    // c = 1
+    M[9]  = -2.0 * ty; M[10] = tx;        M[11] = tw;
+    M[12] = tx;        M[13] = 0.0;       M[14] = tz;
+    M[15] = -tw;       M[16] = tz;        M[17] = -2.0 * ty;
+    // c = 2
+    M[18] = -2.0 * tz; M[19] = -tw;       M[20] = tx;
+    M[21] = tw;        M[22] = -2.0 * tz; M[23] = ty;
+    M[24] = tx;        M[25] = ty;        M[26] = 0.0;
+    // c = 3
+    M[27] = 0.0;       M[28] = -tz;       M[29] = ty;
+    M[30] = tz;        M[31] = 0.0;       M[32] = -tx;
+    M[33] = -ty;       M[34] = tx;        M[35] = 0.0;
 }
 
 __device__ __forceinline__ double warp_sum(double v) {
@@ -141,6 +151,7 @@ __device__ __forceinline__ void node_core(const double* __restrict__ xk, const d
         dm += a * a; dp += bq * bq;
     }
     core[Q::cSGN] = dm > dp ? 1.0 : -1.0;
+    drot_matrices(qx, qy, qz, qw, core + Q::cM);
 }
 
 // Branch-free RelaxedPolyBarrierFunction pieces (same polynomials as barrier_eval, selected instead of branched).
@@ -173,6 +184,7 @@ quadruped_structured_kernel(const double* __restrict__ xp_all, long long ld_xp, 
     double* const xs    = wsm + Q::oXS;
     double* const us    = wsm + Q::oUS;
     double* const ps    = wsm + Q::oPS;
+    double* const rs    = wsm + Q::oRHO;
     for (int e = tid; e < Q::STAGE; e += 64) wsm[e] = 0.0;
     __syncthreads();
 
@@ -211,15 +223,15 @@ quadruped_structured_kernel(const double* __restrict__ xp_all, long long ld_xp, 
             for (int e = tid + halo * Q::NU; e < (nodes + 1) * Q::NU; e += 64) async_copy8(us + e, gu + (e - halo * Q::NU));
             const double* gp = x + Mdl::p_off(N, k0 - 1 + halo);
             for (int e = tid + halo * Q::NP; e < (nodes + 1) * Q::NP; e += 64) async_copy8(ps + e, gp + (e - halo * Q::NP));
+            if (tid < Q::NRHO) async_copy8(rs + tid, Rho + tid);  // the shared parameters travel with the same group: one exposed latency
             asm volatile("cp.async.commit_group;" ::: "memory");
         }
-        const double dt = Rho[0], mass = Rho[1], I0 = Rho[2], I1 = Rho[3], I2 = Rho[4], Llen = Rho[17], g0 = Rho[18],
-                     mu = Rho[19];
-        const double iI0 = 1.0 / I0, iI1 = 1.0 / I1, iI2 = 1.0 / I2, inv_m = 1.0 / mass;
-        const double hip0 = Rho[5 + 3 * leg], hip1 = Rho[6 + 3 * leg], hip2 = Rho[7 + 3 * leg];
-        const double sdt0 = dt * iI0, sdt1 = dt * iI1, sdt2 = dt * iI2;
         asm volatile("cp.async.wait_group 0;" ::: "memory");
         __syncthreads();
+        const double dt = rs[0], mass = rs[1], I0 = rs[2], I1 = rs[3], I2 = rs[4], Llen = rs[17], g0 = rs[18], mu = rs[19];
+        const double iI0 = __drcp_rn(I0), iI1 = __drcp_rn(I1), iI2 = __drcp_rn(I2), inv_m = __drcp_rn(mass);  // = 1.0 / x, correctly rounded
+        const double hip0 = rs[5 + 3 * leg], hip1 = rs[6 + 3 * leg], hip2 = rs[7 + 3 * leg];
+        const double sdt0 = dt * iI0, sdt1 = dt * iI1, sdt2 = dt * iI2;
 
         // ---- phase A: thread-per-node primal cores (thread 0 = halo node k0 - 1: only its rotation matrix) -------------
         if (tid >= 1 && tid <= nodes) {
@@ -227,6 +239,7 @@ quadruped_structured_kernel(const double* __restrict__ xp_all, long long ld_xp, 
                       cores + tid * Q::CORE);
         } else if (tid == 0 && k0 > 0) {
             rot_matrix(xs[3], xs[4], xs[5], xs[6], cores + Q::cR);
+            drot_matrices(xs[3], xs[4], xs[5], xs[6], cores + Q::cM);
         }
         __syncthreads();
 
@@ -251,9 +264,12 @@ quadruped_structured_kernel(const double* __restrict__ xp_all, long long ld_xp, 
 
             // -------- values that do not touch the staging image: computed while the previous bulk store drains ------------
             double W0 = 0, W1 = 0, W2 = 0, z0 = 0, z1 = 0, z2 = 0, s = 0, f0 = 0, f1 = 0, f2 = 0, r0 = 0, r1 = 0, r2 = 0;
-            double qx = 0, qy = 0, qz = 0, qw = 1, Rc0 = 0, Rc1 = 0, Rc2 = 0;
+            double Rc0 = 0, Rc1 = 0, Rc2 = 0, M0 = 0, M1 = 0, M2 = 0, M3 = 0, M4 = 0, M5 = 0, M6 = 0, M7 = 0, M8 = 0;
             if (active) {
-                qx = xk[3]; qy = xk[4]; qz = xk[5]; qw = xk[6];
+                {  // this lane's matrix d(R v)/dq_cq of the node (used for f here and for r in the contact rows)
+                    const double* __restrict__ Mc = co + Q::cM + 9 * cq;
+                    M0 = Mc[0]; M1 = Mc[1]; M2 = Mc[2]; M3 = Mc[3]; M4 = Mc[4]; M5 = Mc[5]; M6 = Mc[6]; M7 = Mc[7]; M8 = Mc[8];
+                }
                 f0 = uk[0]; f1 = uk[1]; f2 = uk[2]; r0 = uk[3]; r1 = uk[4]; r2 = uk[5];
                 s = pk[13 + 4 * leg];
                 Rc0 = R[c3]; Rc1 = R[3 + c3]; Rc2 = R[6 + c3];  // column c3 of R
@@ -264,8 +280,7 @@ quadruped_structured_kernel(const double* __restrict__ xp_all, long long ld_xp, 
                 const double v0 = fcol ? Rc0 : Rf0, v1 = fcol ? Rc1 : Rf1, v2 = fcol ? Rc2 : Rf2;
                 W0 = s * sdt0 * (u1 * v2 - u2 * v1); W1 = s * sdt1 * (u2 * v0 - u0 * v2); W2 = s * sdt2 * (u0 * v1 - u1 * v0);
                 // q columns: dt I^-1 sum_i s_i r_i x d(R f_i)/dq_c — every leg adds its part, xor-reduced over the 4 legs
-                double d0, d1, d2;
-                drot_dq(cq, qx, qy, qz, qw, f0, f1, f2, d0, d1, d2);
+                const double d0 = M0 * f0 + M1 * f1 + M2 * f2, d1 = M3 * f0 + M4 * f1 + M5 * f2, d2 = M6 * f0 + M7 * f1 + M8 * f2;
                 z0 = s * (r1 * d2 - r2 * d1); z1 = s * (r2 * d0 - r0 * d2); z2 = s * (r0 * d1 - r1 * d0);
             }
             z0 += __shfl_xor_sync(0xffffffffu, z0, 8);  z1 += __shfl_xor_sync(0xffffffffu, z1, 8);  z2 += __shfl_xor_sync(0xffffffffu, z2, 8);
@@ -390,18 +405,20 @@ quadruped_structured_kernel(const double* __restrict__ xp_all, long long ld_xp, 
                         const double* Rh = co - Q::CORE + Q::cR;
                         const double q0 = uk[3 - Q::NU], q1 = uk[4 - Q::NU], q2 = uk[5 - Q::NU];  // r_{k-1, leg}
                         Rp0 = Rh[c3]; Rp1 = Rh[3 + c3]; Rp2 = Rh[6 + c3];
-                        drot_dq(cq, xq[3], xq[4], xq[5], xq[6], q0, q1, q2, Dp0, Dp1, Dp2);
+                        const double* __restrict__ Mp = co - Q::CORE + Q::cM + 9 * cq;  // previous node's d(R v)/dq_cq
+                        Dp0 = Mp[0] * q0 + Mp[1] * q1 + Mp[2] * q2;
+                        Dp1 = Mp[3] * q0 + Mp[4] * q1 + Mp[5] * q2;
+                        Dp2 = Mp[6] * q0 + Mp[7] * q1 + Mp[8] * q2;
                         fp0 = xq[0] + Rh[0] * q0 + Rh[1] * q1 + Rh[2] * q2;
                         fp1 = xq[1] + Rh[3] * q0 + Rh[4] * q1 + Rh[5] * q2;
                         fp2 = xq[2] + Rh[6] * q0 + Rh[7] * q1 + Rh[8] * q2;
                         s_prev = pk[13 + 4 * leg - Q::NP];
                     } else {
-                        fp0 = Rho[34 + 4 * leg]; fp1 = Rho[35 + 4 * leg]; fp2 = Rho[36 + 4 * leg];  // measured foot (:296)
-                        s_prev = Rho[33 + 4 * leg];
+                        fp0 = rs[34 + 4 * leg]; fp1 = rs[35 + 4 * leg]; fp2 = rs[36 + 4 * leg];  // measured foot (:296)
+                        s_prev = rs[33 + 4 * leg];
                     }
                     const double c0 = (1.0 - s_prev) * s, ss = s_prev * s;
-                    double D0, D1, D2;
-                    drot_dq(cq, qx, qy, qz, qw, r0, r1, r2, D0, D1, D2);
+                    const double D0 = M0 * r0 + M1 * r1 + M2 * r2, D1 = M3 * r0 + M4 * r1 + M5 * r2, D2 = M6 * r0 + M7 * r1 + M8 * r2;
                     if (c < 4) {  // d foot / d q_c, and the contact values (row c)
                         cl[3 + c] = c0 * D2;
                         cl[20 + 3 + c] = ss * D0; cl[40 + 3 + c] = ss * D1; cl[60 + 3 + c] = ss * D2;
