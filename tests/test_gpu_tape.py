@@ -276,3 +276,19 @@ def test_unchanged_mpc_examples_on_the_gpu_match_the_cpu_build(example, solves):
     assert len(ref) >= 5 and len(got) == len(ref), (len(got), len(ref))
     for step, (a, b) in enumerate(zip(got, ref)):
         assert len(a) == len(b) and np.allclose(a, b, rtol=0, atol=2.1e-3), (step, a, b)  # three printed decimals
+
+
+def test_python_soft_sqp_reaches_the_reference_optima():
+    """test/optimization/soft_sqp.test.cpp:34-111 through the Python mirror: taped objective / constraints / barrier Functions on the
+    register machine, local QPs through ungar_b200_kkt_solve_csc; optima (3, 1), (2, 1), (1, 1) within isApprox(1e-1)."""
+    obj = lambda: A.MakeFunction(A.Blueprint(lambda v: [A.pow(v[0] - 3.0, 2) + A.pow(v[1] - 2.0, 2)], 2, 0, "obj_soft_sqp_test"))  # noqa: E731
+    eqs = lambda: A.MakeFunction(A.Blueprint(lambda v: [v[0] - v[1]], 2, 0, "eqs_soft_sqp_test", A.JACOBIAN))  # noqa: E731
+    ineqs1 = lambda: A.MakeFunction(A.Blueprint(lambda v: [v[1] - 1.0, -v[0]], 2, 0, "ineqs_1_soft_sqp_test", A.JACOBIAN))  # noqa: E731
+    ineqs2 = lambda: A.MakeFunction(A.Blueprint(lambda v: [A.pow(v[0], 2) - v[1] - 3.0, v[1] - 1.0, -v[0]], 2, 0,  # noqa: E731
+                                                "ineqs_2_soft_sqp_test", A.JACOBIAN))
+    cases = [(A.MakeNLPProblem(obj(), None, ineqs1()), (3.0, 1.0)), (A.MakeNLPProblem(obj(), None, ineqs2()), (2.0, 1.0)),
+             (A.MakeNLPProblem(obj(), eqs(), ineqs2()), (1.0, 1.0))]
+    for nlp, optimum in cases:
+        x = A.SoftSQPOptimizer(False, 1.0, 100, 100.0, 2e-8).Optimize(nlp, np.zeros(2))
+        ref = np.array(optimum)
+        assert np.linalg.norm(x - ref) <= 1e-1 * min(np.linalg.norm(x), np.linalg.norm(ref)), (x, optimum)

@@ -415,3 +415,161 @@ def MakeFunction(blueprint: Blueprint, recompileLibraries: bool = False, device:
     """Autodiff::MakeFunction (function.hpp:607-613).  ``recompileLibraries`` is accepted for signature parity: nothing is compiled,
     so there is no stale-library hazard (the reference caches by NAME only, function.hpp:420-451)."""
     return TapeFunction(blueprint, device)
+
+
+# ---------------------------------------------------------------------------------------------------------------------------
+# The optimiser over taped functions: mirror of Ungar::SoftSQPOptimizer for ARBITRARY NLP problems
+# ---------------------------------------------------------------------------------------------------------------------------
+class RelaxedPolyBarrierFunction:
+    """optimization/soft_inequality_constraint.hpp:131-205: coefficients (:136-145) and the taped evaluation (:181-190)."""
+
+    def __init__(self, rhs: float, stiffness: float = 1.0, epsilon: float = 2e-5):
+        self.rhs, self.eps = rhs, epsilon
+        self.a1 = stiffness
+        self.b1 = -0.5 * self.a1 * epsilon
+        self.c1 = -1.0 / 3.0 * (-self.b1 - self.a1 * epsilon) * epsilon - 0.5 * self.a1 * epsilon ** 2 - self.b1 * epsilon
+        self.a2 = (-self.b1 - self.a1 * epsilon) / epsilon ** 2
+        self.b2, self.c2, self.d2 = self.a1, self.b1, self.c1
+
+    def Evaluate(self, lhs):
+        """Sum over the entries of ``lhs`` (a list of AD) of the piecewise barrier of ``lhs_i - rhs``."""
+        total = AD(0.0)
+        for v in lhs:
+            x = _ad(v) - self.rhs
+            quad = 0.5 * self.a1 * pow(x, 2) + self.b1 * x + self.c1
+            cubic = 1.0 / 3.0 * self.a2 * pow(x, 3) + 0.5 * self.b2 * pow(x, 2) + self.c2 * x + self.d2
+            total = total + CondExpLt(x, AD(0.0), quad, CondExpLt(x, AD(self.eps), cubic, AD(0.0)))
+        return total
+
+
+class NLPProblem:
+    """optimization/concepts.hpp:153-161; ``None`` stands for ``hana::nothing`` (MakeNLPProblem overloads, :190-262)."""
+
+    def __init__(self, objective, equalityConstraints=None, inequalityConstraints=None):
+        self.objective, self.equalityConstraints, self.inequalityConstraints = objective, equalityConstraints, inequalityConstraints
+
+
+def MakeNLPProblem(objective, equalityConstraints=None, inequalityConstraints=None) -> NLPProblem:
+    return NLPProblem(objective, equalityConstraints, inequalityConstraints)
+
+
+class SoftSQPOptimizer:
+    """Ungar::SoftSQPOptimizer (optimization/soft_sqp.hpp:42-109) for NLP problems made of TapeFunctions.  The control flow of
+    Optimize and of BacktrackingLineSearch::Do (backtracking_line_search.hpp:81-165) runs on the host exactly as in the reference;
+    every function value, Jacobian, Hessian and the local QP (ungar_b200_kkt_solve_csc) are evaluated on the device.  For the three
+    reference MPC problems use ungar_b200.SoftSQPOptimizer / Model.sqp_solve instead: there the loop itself runs on the device."""
+
+    def __init__(self, verbose: bool = False, constraintViolationMultiplier: float = 1.0, maxIterations: int = 10,
+                 stiffness: float = 100.0, epsilon: float = 2e-5, device: int = 0):
+        self.verbose, self.mult, self.maxIterations = verbose, float(constraintViolationMultiplier), int(maxIterations)
+        self.stiffness, self.epsilon, self.device = float(stiffness), float(epsilon), device
+        self._soft = None
+        self.iterations = 0
+        self.lineSearchParameters = dict(alphaMin=1e-4, thetaMin=1e-6, thetaMax=1e-2, eta=1e-4, gammaPhi=1e-6, gammaTheta=1e-6,
+                                         gammaAlpha=0.5)
+
+    def MakeSoftInequalityConstraintFunction(self, nlp: NLPProblem) -> TapeFunction:
+        """soft_sqp.hpp:114-138: Zsoft(z) = RelaxedPolyBarrierFunction{0, stiffness, epsilon}.Evaluate(-z), its own taped Function."""
+        m = nlp.inequalityConstraints.DependentVariableSize()
+        barrier = RelaxedPolyBarrierFunction(0.0, self.stiffness, self.epsilon)
+        return MakeFunction(Blueprint(lambda z: [barrier.Evaluate([-v for v in z])], m, 0,
+                                      f"soft_sqp_relaxed_poly__sz_{m}_k_{self.stiffness}_eps_{self.epsilon}", ALL), device=self.device)
+
+    # -- pieces of AssembleOSQPInstance (soft_sqp.hpp:141-158, :236-264) -------------------------------------------------------
+    def _soft_value(self, nlp, xp) -> float:
+        if nlp.inequalityConstraints is None:
+            return 0.0
+        return float(self._soft(nlp.inequalityConstraints(xp))[0])
+
+    def _qp(self, nlp, xp):
+        import scipy.sparse as sp
+
+        n = nlp.objective.IndependentVariableSize()
+        Hu = nlp.objective.Hessian(0, xp)
+        P = Hu + sp.identity(n) * 1e-6                       # upper triangle, as handed to OSQP
+        grad_f = np.asarray(nlp.objective.Jacobian(xp).todense()).ravel()
+        q = grad_f.copy()
+        if nlp.inequalityConstraints is not None:
+            z = nlp.inequalityConstraints(xp)
+            Jh = nlp.inequalityConstraints.Jacobian(xp)
+            q += (self._soft.Jacobian(z) @ Jh).toarray().ravel()
+            GN = Jh.T @ self._soft.Hessian(0, z) @ Jh        # the soft Hessian is diagonal: its upper triangle is all of it
+            P = P + sp.triu(GN)
+        if nlp.equalityConstraints is not None:
+            A = nlp.equalityConstraints.Jacobian(xp)
+            b = -nlp.equalityConstraints(xp)
+        else:
+            A, b = sp.csr_matrix((0, n)), np.zeros(0)
+        return sp.csc_matrix(P), q, sp.csc_matrix(A), b, grad_f
+
+    def _solve_qp(self, P, q, A, b):
+        lib = _lib.load()
+        n, m = P.shape[0], A.shape[0]
+        P.sort_indices()
+        A.sort_indices()
+        x, y = np.zeros(n), np.zeros(max(m, 1))
+        pc, pr, pv = P.indptr.astype(np.int32), P.indices.astype(np.int32), np.ascontiguousarray(P.data, dtype=np.float64)
+        ac, ar, av = A.indptr.astype(np.int32), A.indices.astype(np.int32), np.ascontiguousarray(A.data, dtype=np.float64)
+        q = np.ascontiguousarray(q, dtype=np.float64)
+        b = np.ascontiguousarray(b, dtype=np.float64)
+        check(lib.ungar_b200_kkt_solve_csc(n, m, pc.ctypes.data, pr.ctypes.data, pv.ctypes.data, q.ctypes.data,
+                                           ac.ctypes.data if m else None, ar.ctypes.data if m else None, av.ctypes.data if m else None,
+                                           b.ctypes.data if m else None, 1e-9, 1e-9, x.ctypes.data, y.ctypes.data if m else None,
+                                           self.device))
+        return x
+
+    def _line_search(self, grad, dw, phi, theta, w):
+        """BacktrackingLineSearch::Do (backtracking_line_search.hpp:81-165)."""
+        p = self.lineSearchParameters
+        proj = float(np.sum(grad * dw))
+        alpha, th0, ph0 = 1.0, theta(w), phi(w)
+        while alpha >= p["alphaMin"]:
+            wn = w + alpha * dw
+            thn, phn = theta(wn), phi(wn)
+            if thn > p["thetaMax"]:
+                ok = thn < (1.0 - p["gammaTheta"]) * th0
+            elif max(th0, thn) < p["thetaMin"] and proj < 0.0:
+                ok = phn < ph0 + p["eta"] * alpha * proj
+            else:
+                ok = phn < (1.0 - p["gammaPhi"]) * ph0 or thn < (1.0 - p["gammaTheta"]) * th0
+            if ok:
+                return True, wn
+            alpha *= p["gammaAlpha"]
+        return False, w
+
+    def Optimize(self, nlp: NLPProblem, xp):
+        """soft_sqp.hpp:63-109.  Returns the optimised decision variables (the reference returns _cache.xp.head(n))."""
+        xp = np.array(xp, dtype=np.float64)
+        n = nlp.objective.IndependentVariableSize()
+        assert xp.size == n + nlp.objective.ParameterSize()
+        if nlp.inequalityConstraints is not None and self._soft is None:
+            self._soft = self.MakeSoftInequalityConstraintFunction(nlp)
+
+        def full(x):
+            v = xp.copy()
+            v[:n] = x
+            return v
+
+        def phi(x):
+            return float(nlp.objective(full(x))[0]) + self._soft_value(nlp, full(x))
+
+        def theta(x):
+            if nlp.equalityConstraints is None:
+                return 0.0
+            g = nlp.equalityConstraints(full(x))
+            return self.mult * float(np.sqrt(np.dot(g, g)))
+
+        self.iterations = 0
+        for _ in range(self.maxIterations):
+            self.iterations += 1
+            objective = float(nlp.objective(xp)[0])
+            P, q, A, b, grad_f = self._qp(nlp, xp)
+            d = self._solve_qp(P, q, A, b)
+            accepted, w = self._line_search(grad_f, d, phi, theta, xp[:n].copy())
+            if not accepted:
+                break
+            xp[:n] = w
+            diff = float(nlp.objective(xp)[0]) - objective
+            if diff < 0.0 and abs(diff) < 1e-6:
+                break
+        return xp[:n].copy()
