@@ -20,9 +20,10 @@
 //     lambda_N = -(HN dx_N + q_N),    lambda_k = -(H_xx dx_k + H_xu du_k + q_x,k + A_x,k^T lambda_{k+1}).
 // Exact (no ADMM iterations); the reference's OSQP v0.6.3 is absent from the tree.
 //
-// Mapping: one warp per trajectory; every matrix of a stage lives in shared memory (quadrotor: 11 KB per warp) and the lanes
-// stride over output entries.  The blocks are tiny (13 x 17, 6 x 8): the kernel is latency-bound by design and runs next to
-// sweeps that are 10-100x larger.
+// Mapping: one warp per trajectory; every matrix of a stage lives in shared memory (quadrotor: 16 KB per warp) and the lanes
+// stride over output entries.  The stage data (A_k, H_k, q_k, g_{k+1}, Hc_{k-1}; in the rollout also the gains Y_k) is fetched with
+// cp.async ONE STAGE AHEAD into the other of two stage buffers, so the three sweeps never wait on HBM inside a stage.  The blocks
+// are tiny (13 x 17, 6 x 8): the kernel runs next to sweeps that are 10-100x larger.
 #pragma once
 
 #include "sweep.cuh"
@@ -32,8 +33,11 @@ namespace ub {
 template <class Mdl>
 struct RiccatiShape {
     static constexpr int NX = Mdl::NX, NU = Mdl::NU, NZ = Mdl::NZ, NS = NX + NU, TRI = NZ * (NZ + 1) / 2;
+    // stage buffer (one of two, filled with cp.async one stage ahead):  A_k | packed H_k | q_k | g_{k+1} | diag(Hc_{k-1}) | Y_k
+    static constexpr int bA = 0, bH = bA + NX * NZ, bQ = bH + TRI, bG = bQ + NZ, bD = bG + NX, bY = bD + NU,
+                         STAGE = (bY + NU * (NS + 1) + 1) & ~1;
     // per-warp shared memory (doubles)
-    static constexpr int oA = 0, oM = oA + NX * NZ, oW = oM + NZ * NZ, oPxx = oW + NX * NZ, oPxv = oPxx + NX * NX, oPvv = oPxv + NX * NU,
+    static constexpr int oS = 0, oM = oS + 2 * STAGE, oW = oM + NZ * NZ, oPxx = oW + NX * NZ, oPxv = oPxx + NX * NX, oPvv = oPxv + NX * NU,
                          oT = oPvv + NU * NU, oY = oT + NZ * NU, oVec = oY + NU * (NS + 1),
                          // small vectors: px (NX) pv (NU) wx (NX) wv (NU) m (NZ) g (NX) q (NZ) D (NU) s (NS) du (NU) lam (NX)
                          vPx = 0, vPv = vPx + NX, vWx = vPv + NU, vWv = vWx + NX, vM = vWv + NU, vG = vM + NZ, vQ = vG + NX, vD = vQ + NZ,
@@ -54,10 +58,10 @@ qp_riccati_kernel(const double* __restrict__ rec_all, long long ld_rec, double* 
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     double* const sm = reinterpret_cast<double*>(smem_raw) + wib * R::total;
-    double *sA = sm + R::oA, *sM = sm + R::oM, *sW = sm + R::oW, *sPxx = sm + R::oPxx, *sPxv = sm + R::oPxv, *sPvv = sm + R::oPvv,
+    double *sS = sm + R::oS, *sM = sm + R::oM, *sW = sm + R::oW, *sPxx = sm + R::oPxx, *sPxv = sm + R::oPxv, *sPvv = sm + R::oPvv,
            *sT = sm + R::oT, *sY = sm + R::oY, *sv = sm + R::oVec;
-    double *px = sv + R::vPx, *pv = sv + R::vPv, *wx = sv + R::vWx, *wv = sv + R::vWv, *mv = sv + R::vM, *sg = sv + R::vG, *sq = sv + R::vQ,
-           *sD = sv + R::vD, *ss = sv + R::vS, *sdu = sv + R::vDu, *slam = sv + R::vLam;
+    double *px = sv + R::vPx, *pv = sv + R::vPv, *wx = sv + R::vWx, *wv = sv + R::vWv, *mv = sv + R::vM, *ss = sv + R::vS,
+           *sdu = sv + R::vDu, *slam = sv + R::vLam;
     const long long b = (long long)blockIdx.x * R::WARPS + wib;
     if (b >= batch) return;
     if (skip_status && skip_status[2 * b] != 0) return;  // SQP loop: this trajectory has stopped (warp-uniform)
@@ -65,6 +69,32 @@ qp_riccati_kernel(const double* __restrict__ rec_all, long long ld_rec, double* 
     double* __restrict__ ws = ws_all + b * (long long)N * R::WS_STAGE;
     const int uoff = NX * (N + 1);  // first input entry of the decision vector / gradient
 
+    auto cp8 = [](double* dst, const double* src) {
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((unsigned)__cvta_generic_to_shared(dst)), "l"(src) : "memory");
+    };
+    // Asynchronous fetch of stage k into buffer `buf`; `gains`: also Y_k from the workspace (forward rollout).
+    auto fetch = [&](int k, int buf, bool gains) {
+        double* S = sS + buf * R::STAGE;
+        const double* Ak = rec + L.A + (long long)k * NX * NZ;
+        const double* Hk = rec + L.H + (long long)k * TRI;
+        for (int e = lane; e < NX * NZ; e += 32) cp8(S + R::bA + e, Ak + e);
+        for (int e = lane; e < TRI; e += 32) cp8(S + R::bH + e, Hk + e);
+        for (int e = lane; e < NZ; e += 32) cp8(S + R::bQ + e, e < NX ? rec + L.grad + NX * k + e : rec + L.grad + uoff + NU * k + (e - NX));
+        for (int e = lane; e < NX; e += 32) cp8(S + R::bG + e, rec + L.g + NX * (k + 1) + e);
+        for (int e = lane; e < NU; e += 32) {
+            if (k > 0) cp8(S + R::bD + e, rec + L.Hc + NU * (k - 1) + e);
+            else S[R::bD + e] = 0.0;
+        }
+        if (gains)
+            for (int e = lane; e < R::WS_STAGE; e += 32) cp8(S + R::bY + e, ws + (long long)k * R::WS_STAGE + e);
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+    auto arrive = [] {
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+        __syncwarp();
+    };
+
+    fetch(N - 1, 0, false);
     // ---- terminal value function: Pxx = HN, px = q_N, everything else zero --------------------------------------------------------
     for (int e = lane; e < NX * NX; e += 32) {
         const int i = e / NX, j = e - i * NX;
@@ -78,17 +108,12 @@ qp_riccati_kernel(const double* __restrict__ rec_all, long long ld_rec, double* 
 
     // ================================================================ backward Riccati sweep
     for (int k = N - 1; k >= 0; --k) {
-        const double* Ak = rec + L.A + (long long)k * NX * NZ;
-        const double* Hk = rec + L.H + (long long)k * TRI;
-        for (int e = lane; e < NX * NZ; e += 32) sA[e] = Ak[e];
-        for (int e = lane; e < NZ * NZ; e += 32) {
-            const int i = e / NZ, j = e - i * NZ;
-            sM[e] = Hk[i <= j ? tri_index(NZ, i, j) : tri_index(NZ, j, i)];
-        }
-        for (int e = lane; e < NZ; e += 32) sq[e] = e < NX ? rec[L.grad + NX * k + e] : rec[L.grad + uoff + NU * k + (e - NX)];
-        for (int e = lane; e < NX; e += 32) sg[e] = rec[L.g + NX * (k + 1) + e];
-        for (int e = lane; e < NU; e += 32) sD[e] = k > 0 ? rec[L.Hc + NU * (k - 1) + e] : 0.0;
-        __syncwarp();
+        const int buf = (N - 1 - k) & 1;
+        arrive();
+        if (k > 0) fetch(k - 1, buf ^ 1, false);
+        else fetch(0, buf ^ 1, false);  // first stage of the forward rollout (its gains Y_0 stay in sY)
+        const double* S = sS + buf * R::STAGE;
+        const double *sA = S + R::bA, *sHp = S + R::bH, *sq = S + R::bQ, *sg = S + R::bG, *sD = S + R::bD;
         // wx = px - Pxx g,  wv = pv - Pxv^T g
         for (int e = lane; e < NS; e += 32) {
             double acc = e < NX ? px[e] : pv[e - NX];
@@ -114,7 +139,7 @@ qp_riccati_kernel(const double* __restrict__ rec_all, long long ld_rec, double* 
         // M = H + A^T W - [0 T] - [0 T]^T + [0 0; 0 Pvv] ;  m = q - A^T wx + [0; wv]
         for (int e = lane; e < NZ * NZ; e += 32) {
             const int i = e / NZ, j = e - i * NZ;
-            double acc = sM[e];
+            double acc = sHp[i <= j ? tri_index(NZ, i, j) : tri_index(NZ, j, i)];
 #pragma unroll
             for (int r = 0; r < NX; ++r) acc += sA[r * NZ + i] * sW[r * NZ + j];
             if (j >= NX) acc -= sT[i * NU + (j - NX)];
@@ -161,7 +186,8 @@ qp_riccati_kernel(const double* __restrict__ rec_all, long long ld_rec, double* 
             for (int a = 0; a < NU; ++a) sY[a * (NS + 1) + c] = y[a];
         }
         __syncwarp();
-        for (int e = lane; e < R::WS_STAGE; e += 32) ws[(long long)k * R::WS_STAGE + e] = sY[e];
+        if (k > 0)
+            for (int e = lane; e < R::WS_STAGE; e += 32) ws[(long long)k * R::WS_STAGE + e] = sY[e];
         // value function of stage k
         for (int e = lane; e < NX * NX; e += 32) {
             const int i = e / NX, j = e - i * NX;
@@ -193,20 +219,21 @@ qp_riccati_kernel(const double* __restrict__ rec_all, long long ld_rec, double* 
     }
 
     // ================================================================ forward rollout: s_0 = [-g_0; 0]
+    // Stage 0 was fetched (buffer N & 1) while the backward sweep finished; its gains Y_0 are still in sY (never written to the
+    // workspace), every later stage's gains come back from the workspace one stage ahead.
     double* __restrict__ step = step_all + b * ld_step;
     for (int e = lane; e < NS; e += 32) ss[e] = e < NX ? -rec[L.g + e] : 0.0;
     __syncwarp();
     for (int k = 0; k < N; ++k) {
-        const double* Ak = rec + L.A + (long long)k * NX * NZ;
-        const double* Yk = ws + (long long)k * R::WS_STAGE;
-        for (int e = lane; e < NX * NZ; e += 32) sA[e] = Ak[e];
-        for (int e = lane; e < R::WS_STAGE; e += 32) sY[e] = Yk[e];
-        for (int e = lane; e < NX; e += 32) sg[e] = rec[L.g + NX * (k + 1) + e];
-        __syncwarp();
+        const int buf = (N + k) & 1;
+        arrive();
+        if (k + 1 < N) fetch(k + 1, buf ^ 1, true);
+        const double* S = sS + buf * R::STAGE;
+        const double *sA = S + R::bA, *sg = S + R::bG, *Yk = k == 0 ? sY : S + R::bY;
         for (int a = lane; a < NU; a += 32) {
-            double acc = -sY[a * (NS + 1) + NS];
+            double acc = -Yk[a * (NS + 1) + NS];
 #pragma unroll
-            for (int c = 0; c < NS; ++c) acc -= sY[a * (NS + 1) + c] * ss[c];
+            for (int c = 0; c < NS; ++c) acc -= Yk[a * (NS + 1) + c] * ss[c];
             sdu[a] = acc;
         }
         __syncwarp();
