@@ -30,7 +30,8 @@ def main(tag):
     total = sum(v[1] for v in agg.values())
     with open(os.path.join(HERE, f"{tag}_launches.md"), "w") as f:
         f.write(f"# ncu launch list, tag {tag}\n\n`ncu --metrics gpu__time_duration.sum --clock-control none -c 200 python bench.py "
-                f"--steps 20 --warmup 3 --no-cpu-baseline` (cold-cache, serialised launches: compare shares, not absolutes)\n\n"
+                f"--steps 20 --warmup 3 --no-cpu-baseline` (cold-cache, serialised launches: compare shares, not absolutes; the capture "
+                f"spans the device-resident leg, one launch per step, and the host-buffer leg, whose steps launch one sweep per H2D chunk)\n\n"
                 "| kernel | launches | total us | mean us | share |\n|---|---:|---:|---:|---:|\n")
         for k, v in sorted(agg.items(), key=lambda kv: -kv[1][1]):
             f.write(f"| `{k[:90]}` | {v[0]} | {v[1] / 1e3:.1f} | {v[1] / 1e3 / v[0]:.1f} | {v[1] / total:.3f} |\n")

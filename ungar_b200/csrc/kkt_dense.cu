@@ -66,6 +66,27 @@ __global__ void regularise(double* __restrict__ K, long long ld, int n, int m, d
     else if (i < n + m) K[i + i * ld] -= rho;
 }
 
+// Per-device context kept across calls (an SQP loop solves a QP of the same size every iteration): the cuSOLVER handle and the
+// device buffers.  Like a model handle, it must be used from one thread at a time.
+struct Growable {
+    void* ptr  = nullptr;
+    size_t cap = 0;
+    cudaError_t reserve(size_t bytes) {
+        if (bytes <= cap) return cudaSuccess;
+        if (ptr) cudaFree(ptr);
+        ptr = nullptr;
+        cap = 0;
+        cudaError_t e = cudaMalloc(&ptr, bytes);
+        if (e == cudaSuccess) cap = bytes;
+        return e;
+    }
+};
+struct KktContext {
+    cusolverDnHandle_t handle = nullptr;
+    Growable K, r, vals, work, ptr, idx, piv, info;
+};
+KktContext g_ctx[64];
+
 }  // namespace
 
 extern "C" int ungar_b200_kkt_solve_csc(int64_t n, int64_t m, const int32_t* P_colptr, const int32_t* P_rowidx, const double* P_vals,
@@ -80,24 +101,28 @@ extern "C" int ungar_b200_kkt_solve_csc(int64_t n, int64_t m, const int32_t* P_c
         return kfail(UNGAR_B200_ECUDA, "no usable CUDA device %d (there is no CPU fallback for the QP solve)", device);
     int rc = UNGAR_B200_OK;
     const int nnzP = P_colptr[n], nnzA = m > 0 ? A_colptr[n] : 0;
+    KktContext& C = g_ctx[device & 63];
     double *dK = nullptr, *dr = nullptr, *dvals = nullptr, *dwork = nullptr;
     int *dptr = nullptr, *didx = nullptr, *dpiv = nullptr, *dinfo = nullptr;
-    cusolverDnHandle_t handle = nullptr;
     std::vector<double> rhs(static_cast<size_t>(N), 0.0), sol(static_cast<size_t>(N), 0.0);
     int lwork = 0, info = 0;
     const int threads = 128;
+    const size_t nnz_max = size_t(std::max(std::max(nnzP, nnzA), 1));
     for (int64_t i = 0; i < n; ++i) rhs[size_t(i)] = -q[i];
     for (int64_t i = 0; i < m; ++i) rhs[size_t(n + i)] = b[i];
 
     UBK_CUDA(cudaSetDevice(device));
-    UBK_CUDA(cudaMalloc(&dK, size_t(N) * size_t(N) * sizeof(double)));
+    UBK_CUDA(C.K.reserve(size_t(N) * size_t(N) * sizeof(double)));
+    UBK_CUDA(C.r.reserve(size_t(N) * sizeof(double)));
+    UBK_CUDA(C.ptr.reserve(size_t(n + 1) * sizeof(int)));
+    UBK_CUDA(C.idx.reserve(nnz_max * sizeof(int)));
+    UBK_CUDA(C.vals.reserve(nnz_max * sizeof(double)));
+    UBK_CUDA(C.piv.reserve(size_t(N) * sizeof(int)));
+    UBK_CUDA(C.info.reserve(sizeof(int)));
+    dK = static_cast<double*>(C.K.ptr); dr = static_cast<double*>(C.r.ptr); dvals = static_cast<double*>(C.vals.ptr);
+    dptr = static_cast<int*>(C.ptr.ptr); didx = static_cast<int*>(C.idx.ptr); dpiv = static_cast<int*>(C.piv.ptr);
+    dinfo = static_cast<int*>(C.info.ptr);
     UBK_CUDA(cudaMemset(dK, 0, size_t(N) * size_t(N) * sizeof(double)));
-    UBK_CUDA(cudaMalloc(&dr, size_t(N) * sizeof(double)));
-    UBK_CUDA(cudaMalloc(&dptr, size_t(n + 1) * sizeof(int)));
-    UBK_CUDA(cudaMalloc(&didx, size_t(std::max(std::max(nnzP, nnzA), 1)) * sizeof(int)));
-    UBK_CUDA(cudaMalloc(&dvals, size_t(std::max(std::max(nnzP, nnzA), 1)) * sizeof(double)));
-    UBK_CUDA(cudaMalloc(&dpiv, size_t(N) * sizeof(int)));
-    UBK_CUDA(cudaMalloc(&dinfo, sizeof(int)));
     // P (upper triangle mirrored)
     UBK_CUDA(cudaMemcpy(dptr, P_colptr, size_t(n + 1) * sizeof(int), cudaMemcpyHostToDevice));
     if (nnzP) {
@@ -117,19 +142,18 @@ extern "C" int ungar_b200_kkt_solve_csc(int64_t n, int64_t m, const int32_t* P_c
     ub_count_launch();
     UBK_CUDA(cudaGetLastError());
     UBK_CUDA(cudaMemcpy(dr, rhs.data(), size_t(N) * sizeof(double), cudaMemcpyHostToDevice));
-    UBK_SOLVER(cusolverDnCreate(&handle));
-    UBK_SOLVER(cusolverDnDgetrf_bufferSize(handle, int(N), int(N), dK, int(N), &lwork));
-    UBK_CUDA(cudaMalloc(&dwork, size_t(std::max(lwork, 1)) * sizeof(double)));
-    UBK_SOLVER(cusolverDnDgetrf(handle, int(N), int(N), dK, int(N), dwork, dpiv, dinfo));
+    if (!C.handle) UBK_SOLVER(cusolverDnCreate(&C.handle));
+    UBK_SOLVER(cusolverDnDgetrf_bufferSize(C.handle, int(N), int(N), dK, int(N), &lwork));
+    UBK_CUDA(C.work.reserve(size_t(std::max(lwork, 1)) * sizeof(double)));
+    dwork = static_cast<double*>(C.work.ptr);
+    UBK_SOLVER(cusolverDnDgetrf(C.handle, int(N), int(N), dK, int(N), dwork, dpiv, dinfo));
     UBK_CUDA(cudaMemcpy(&info, dinfo, sizeof(int), cudaMemcpyDeviceToHost));
     if (info != 0) { rc = kfail(UNGAR_B200_EINVAL, "the KKT matrix is singular (LU pivot %d is zero)", info); goto done; }
-    UBK_SOLVER(cusolverDnDgetrs(handle, CUBLAS_OP_N, int(N), 1, dK, int(N), dpiv, dr, int(N), dinfo));
+    UBK_SOLVER(cusolverDnDgetrs(C.handle, CUBLAS_OP_N, int(N), 1, dK, int(N), dpiv, dr, int(N), dinfo));
     UBK_CUDA(cudaMemcpy(sol.data(), dr, size_t(N) * sizeof(double), cudaMemcpyDeviceToHost));
     for (int64_t i = 0; i < n; ++i) x[i] = sol[size_t(i)];
     if (y)
         for (int64_t i = 0; i < m; ++i) y[i] = sol[size_t(n + i)];
 done:
-    if (handle) cusolverDnDestroy(handle);
-    cudaFree(dK); cudaFree(dr); cudaFree(dvals); cudaFree(dwork); cudaFree(dptr); cudaFree(didx); cudaFree(dpiv); cudaFree(dinfo);
     return rc;
 }
