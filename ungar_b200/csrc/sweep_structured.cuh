@@ -171,7 +171,7 @@ template <bool BARRIER>
 __global__ void __launch_bounds__(64, 6)
 quadruped_structured_kernel(const double* __restrict__ xp_all, long long ld_xp, double* __restrict__ rec_all, long long ld_rec,
                             double* __restrict__ partials, int N, int run_len, int runs_per_traj, long long total_runs,
-                            RecLayout L, BarrierCoef<double> bar) {
+                            RecLayout L, BarrierCoef<double> bar, unsigned int* __restrict__ sched) {
     using Q = QuadrupedStructured;
     using Mdl = Quadruped;
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -205,7 +205,12 @@ quadruped_structured_kernel(const double* __restrict__ xp_all, long long ld_xp, 
     const double ec0 = c3 == 0 ? 1.0 : 0.0, ec1 = c3 == 1 ? 1.0 : 0.0, ec2 = c3 == 2 ? 1.0 : 0.0;
     bool pending = false;  // a bulk store may still be reading the staging image (CTA-uniform)
 
-    for (long long run = blockIdx.x; run < total_runs; run += gridDim.x) {
+    // Runs are CLAIMED, not statically strided: the first one is the CTA's index, every further one comes from an atomic counter
+    // (sched[0]).  A CTA that becomes resident late — another kernel (the NCCL all-gather of the previous step, a neighbour's H2D
+    // chunk sweep) holds part of an SM — then simply claims fewer runs instead of stretching the launch by a second wave.
+    __shared__ long long s_next;
+    long long run = blockIdx.x;
+    while (run < total_runs) {
         const long long b = run / runs_per_traj;
         const int run_in_traj = int(run - b * runs_per_traj);
         const int k0    = run_in_traj * run_len;
@@ -495,9 +500,20 @@ quadruped_structured_kernel(const double* __restrict__ xp_all, long long ld_xp, 
             double* pt = partials + ((long long)b * (2 * runs_per_traj) + 2 * run_in_traj + w) * 4;
             pt[0] = cost_acc; pt[1] = bar_acc; pt[2] = gmax; pt[3] = hmax;
         }
+        if (tid == 0) s_next = (long long)gridDim.x + atomicAdd(&sched[0], 1u);
         __syncthreads();  // everyone is done with xs/us/ps/cores before the next run overwrites them
+        run = s_next;
     }
-    if (tid == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+    if (tid == 0) {
+        asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+        // the last CTA to leave re-arms the scheduler for the next launch (stream order makes the zeros visible to it)
+        __threadfence();
+        if (atomicAdd(&sched[1], 1u) == gridDim.x - 1) {
+            sched[0] = 0u;
+            sched[1] = 0u;
+            __threadfence();
+        }
+    }
 }
 
 }  // namespace ub

@@ -106,7 +106,7 @@ struct ungar_b200_model {
     ub::RecLayout rl{};
     ub::BarrierCoef<double> bar{};
     FunctionTables fn[4];
-    DeviceBuffer stage_cost, ws_records, ws_xp, ws_out, ws_qp, ws_steps, ws_status, ws_info;
+    DeviceBuffer stage_cost, ws_records, ws_xp, ws_out, ws_qp, ws_steps, ws_status, ws_info, sched;
     size_t elem = 8;
     // host-buffer pipeline of ungar_b200_kkt_step: H2D of chunk c + 1 on `copy_stream` overlaps the sweep of chunk c
     static constexpr int kChunks = 4;
@@ -356,6 +356,10 @@ int launch_structured(ungar_b200_model& mdl, const double* xp, int64_t batch, in
     const int run_len       = 2 * ((mdl.N + 2 * runs_per_traj - 1) / (2 * runs_per_traj));
     const long long total_runs = (long long)batch * runs_per_traj;
     const unsigned grid = unsigned(std::min<long long>(total_runs, (long long)sm_count * 6));  // persistent: 6 teams / SM
+    if (!mdl.sched.ptr) {  // run-claim counters of the persistent grid: zeroed once, re-armed by the kernel itself
+        if (int rc = mdl.sched.reserve(2 * sizeof(unsigned int))) return rc;
+        UB_CUDA(cudaMemsetAsync(mdl.sched.ptr, 0, 2 * sizeof(unsigned int), stream));
+    }
     int slot = -1;
     if (g_ring.enabled) {
         slot = g_ring.head;
@@ -367,7 +371,7 @@ int launch_structured(ungar_b200_model& mdl, const double* xp, int64_t batch, in
         UB_CUDA(cudaEventRecord(g_ring.start[slot], stream));
     }
     kernel<<<grid, Q::WARPS * 32, Q::SMEM_BYTES, stream>>>(xp, ld_xp, rec, ld_rec, static_cast<double*>(mdl.stage_cost.ptr),
-                                                           mdl.N, run_len, runs_per_traj, total_runs, mdl.rl, mdl.bar);
+                                                           mdl.N, run_len, runs_per_traj, total_runs, mdl.rl, mdl.bar, static_cast<unsigned int*>(mdl.sched.ptr));
     if (slot >= 0) {
         UB_CUDA(cudaEventRecord(g_ring.stop[slot], stream));
         g_ring.head  = (g_ring.head + 1) % kRing;
