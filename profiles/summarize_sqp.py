@@ -35,7 +35,7 @@ def main(tag):
         for k, v in sorted(agg.items(), key=lambda kv: -kv[1][1]):
             f.write(f"| `{k[:90]}` | {v[0]} | {v[1] / 1e3:.1f} | {v[1] / 1e3 / v[0]:.1f} | {v[1] / total:.3f} |\n")
     summ = []
-    for rep in (f"sqp_{tag}.ncu-rep", f"riccati_{tag}.ncu-rep"):
+    for rep in (f"sqp_{tag}.ncu-rep", f"ls_{tag}.ncu-rep", f"riccati_{tag}.ncu-rep"):
         path = os.path.join(out, rep)
         if not os.path.exists(path):
             continue

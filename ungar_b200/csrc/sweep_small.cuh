@@ -314,7 +314,7 @@ template <class Mdl, class T, bool BARRIER, int WARPS>
 __global__ void __launch_bounds__(WARPS * 32)
 small_team_kernel(const T* __restrict__ xp_all, long long ld_xp, T* __restrict__ rec_all, long long ld_rec,
                   T* __restrict__ partials, int N, int n_xp, long long batch, RecLayout L, BarrierCoef<T> bar,
-                  typename SmallShape<Mdl, T>::Offsets O) {
+                  typename SmallShape<Mdl, T>::Offsets O, unsigned int* __restrict__ sched) {
     using Sh = SmallShape<Mdl, T>;
     using Pol = SmallPolicy<Mdl>;
     constexpr int NX = Sh::NX, NU = Sh::NU, NZ = Sh::NZ, TRI = Sh::TRI, G = Sh::G, NA = NX * NZ;
@@ -333,7 +333,10 @@ small_team_kernel(const T* __restrict__ xp_all, long long ld_xp, T* __restrict__
     const long long warp_id = (long long)blockIdx.x * WARPS + wib, n_warps = (long long)gridDim.x * WARPS;
     bool pending = false;
 
-    for (long long b = warp_id; b < batch; b += n_warps) {
+    // Trajectories are claimed from an atomic counter (sched[0]); the first one is the warp's index.  A warp that becomes resident
+    // late then claims fewer trajectories instead of stretching the launch (same scheme as the quadruped sweep).
+    long long b = warp_id;
+    while (b < batch) {
         const T* __restrict__ x = xp_all + b * ld_xp;
         T* __restrict__ r       = rec_all + b * ld_rec;
         // ---- phase 0 ------------------------------------------------------------------------------------------------------
@@ -447,13 +450,23 @@ small_team_kernel(const T* __restrict__ xp_all, long long ld_xp, T* __restrict__
             gmax = fmax(gmax, __shfl_xor_sync(0xffffffffu, gmax, o));
             hmax = fmax(hmax, __shfl_xor_sync(0xffffffffu, hmax, o));
         }
+        unsigned int claimed = 0;
         if (lane == 0) {
             T* pt = partials + b * 4;
             pt[0] = cost; pt[1] = bsum; pt[2] = gmax; pt[3] = hmax;
+            claimed = atomicAdd(&sched[0], 1u);
         }
-        __syncwarp();
+        b = n_warps + (long long)__shfl_sync(0xffffffffu, claimed, 0);
     }
-    if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+    if (lane == 0) {
+        asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+        __threadfence();
+        if (atomicAdd(&sched[1], 1u) == (unsigned int)(n_warps - 1)) {  // the last warp to leave re-arms the counters
+            sched[0] = 0u;
+            sched[1] = 0u;
+            __threadfence();
+        }
+    }
 }
 
 }  // namespace ub

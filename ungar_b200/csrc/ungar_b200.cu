@@ -329,6 +329,14 @@ int launch_generic(ungar_b200_model& mdl, const T* xp, int64_t batch, int64_t ld
     return UNGAR_B200_OK;
 }
 
+// Work-claim counters of the persistent grids: zeroed once, re-armed by the kernels themselves (the last CTA / warp to leave).
+int ensure_sched(ungar_b200_model& mdl, cudaStream_t stream) {
+    if (mdl.sched.ptr) return UNGAR_B200_OK;
+    if (int rc = mdl.sched.reserve(2 * sizeof(unsigned int))) return rc;
+    UB_CUDA(cudaMemsetAsync(mdl.sched.ptr, 0, 2 * sizeof(unsigned int), stream));
+    return UNGAR_B200_OK;
+}
+
 // Structured quadruped fp64 sweep (sweep_structured.cuh).  Needs paired nodes (even horizon) and 16-byte aligned
 // block slices for the TMA bulk stores; anything else takes the generic kernel.
 bool structured_applicable(const ungar_b200_model& mdl, const void* rec, int64_t ld_rec) {
@@ -356,10 +364,7 @@ int launch_structured(ungar_b200_model& mdl, const double* xp, int64_t batch, in
     const int run_len       = 2 * ((mdl.N + 2 * runs_per_traj - 1) / (2 * runs_per_traj));
     const long long total_runs = (long long)batch * runs_per_traj;
     const unsigned grid = unsigned(std::min<long long>(total_runs, (long long)sm_count * 6));  // persistent: 6 teams / SM
-    if (!mdl.sched.ptr) {  // run-claim counters of the persistent grid: zeroed once, re-armed by the kernel itself
-        if (int rc = mdl.sched.reserve(2 * sizeof(unsigned int))) return rc;
-        UB_CUDA(cudaMemsetAsync(mdl.sched.ptr, 0, 2 * sizeof(unsigned int), stream));
-    }
+    if (int rc = ensure_sched(mdl, stream)) return rc;
     int slot = -1;
     if (g_ring.enabled) {
         slot = g_ring.head;
@@ -461,6 +466,7 @@ int launch_small(ungar_b200_model& mdl, const T* xp, int64_t batch, int64_t ld_x
     UB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, WARPS * 32, smem));
     const long long want = (batch + WARPS - 1) / WARPS;
     const unsigned grid = unsigned(std::min<long long>(want, (long long)sm_count * std::max(per_sm, 1)));
+    if (int rc = ensure_sched(mdl, stream)) return rc;
     int slot = -1;
     if (g_ring.enabled) {
         slot = g_ring.head;
@@ -472,7 +478,7 @@ int launch_small(ungar_b200_model& mdl, const T* xp, int64_t batch, int64_t ld_x
         UB_CUDA(cudaEventRecord(g_ring.start[slot], stream));
     }
     kernel<<<grid, WARPS * 32, smem, stream>>>(xp, ld_xp, rec, ld_rec, static_cast<T*>(mdl.stage_cost.ptr), mdl.N, n_xp, batch,
-                                               mdl.rl, cast_barrier<T>(mdl.bar), offs);
+                                               mdl.rl, cast_barrier<T>(mdl.bar), offs, static_cast<unsigned int*>(mdl.sched.ptr));
     if (slot >= 0) {
         UB_CUDA(cudaEventRecord(g_ring.stop[slot], stream));
         g_ring.head  = (g_ring.head + 1) % kRing;
