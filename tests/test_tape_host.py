@@ -105,3 +105,54 @@ def test_reference_binaries_over_the_product_header_fail_loudly_without_a_gpu():
         pytest.skip("tests/_ref_gpu was not built (needs /root/reference at build time)")
     proc = subprocess.run([exe], capture_output=True, text=True)
     assert proc.returncode != 0 and "no CPU fallback" in proc.stderr
+
+
+def _reference_tape(config, function):
+    """Tape recorded by oracle/_ref from the reference's own lambda (see tests/test_gpu_tape.py::load_reference_tape)."""
+    import glob
+    import os
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    hits = glob.glob(os.path.join(root, "oracle", "_ref", "tapes", config, function, "cppad_cg", "*_lib.so"))
+    if not hits:
+        pytest.skip("oracle/_ref tapes were not built (needs /root/reference at build time)")
+    raw = open(hits[0], "rb").read()
+    magic, nn, nd, ni, flags = np.frombuffer(raw, dtype=np.int64, count=5)
+    assert int(magic) == 0x32455041545F4255
+    nodes = np.frombuffer(raw, dtype=A.NODE_DTYPE, count=int(nn), offset=40)
+    dep_id = np.frombuffer(raw, dtype=np.int32, count=int(nd), offset=40 + int(nn) * 32)
+    dep_const = np.frombuffer(raw, dtype=np.float64, count=int(nd), offset=40 + int(nn) * 32 + int(nd) * 4)
+    return nodes, int(ni), dep_id, dep_const
+
+
+@pytest.mark.parametrize("name,N", [("quadrotor", 30), ("rc_car", 60), ("quadruped", 30), ("quadruped", 100)])
+def test_structural_analysis_of_the_reference_lambdas_matches_the_oracle(oracle, name, N):
+    """Host-side analysis of the reference's OWN taped lambdas (no device needed): the Jacobian patterns of the three functions, trimmed
+    like function.hpp:529-550, equal the restated oracle's CSR patterns entry for entry; the objective's Hessian pattern (upper
+    triangle of the x-x block, function.hpp:552-574) contains the oracle's; liveness keeps the scratch far below the tape length."""
+    from ungar_b200 import workloads as W
+
+    mid = W.MODEL_IDS[name]
+    s = W.sizes(mid, N)
+    nx = s["n_dec"]
+    xp = W.synthetic_batch(mid, N, 1, seed=11)[0]
+    for fn, suffix in ((0, "obj"), (1, "eqs"), (2, "ineqs")):
+        nodes, ni, dep_id, dep_const = _reference_tape(f"{name}_N{N}", f"{name}_mpc_{suffix}")
+        assert ni == s["n_xp"]
+        t = A.TapeHandle(nodes, ni, dep_id, dep_const)
+        r, c = t.jacobian_pattern()
+        keep = c < nx
+        o_r, o_c, _ = oracle.jacobian(mid, fn, N, xp)
+        assert np.array_equal(r[keep], o_r) and np.array_equal(c[keep], o_c), suffix
+        t.set_jacobian_elements(r[keep], c[keep])
+        info = t.info()
+        assert info["live_nodes"] <= nodes.size and info["slots"] < 0.2 * info["live_nodes"] + 64
+        if fn == 0:  # a scalar function has one dense row: forward-mode column compression cannot merge its columns (no reverse sweep)
+            assert info["jacobian_colors"] == int(keep.sum())
+        else:        # block-banded: a few stage widths
+            assert 1 <= info["jacobian_colors"] <= 3 * (s["nx"] + s["nu"])
+        if fn == 0:
+            r2, c2 = t.hessian_pattern()
+            keep2 = (r2 < nx) & (c2 < nx) & (c2 >= r2)
+            o_r, o_c, _ = oracle.hessian(mid, N, xp)
+            assert set(zip(o_r.tolist(), o_c.tolist())) <= set(zip(r2[keep2].tolist(), c2[keep2].tolist()))
