@@ -50,29 +50,39 @@ def parse_args():
     ap.add_argument("--dtype", default="f64", choices=["f32", "f64"])
     ap.add_argument("--cpu-seconds", type=float, default=15.0, help="CPU work budget of the cpu_baseline leg")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--mode", default="kkt", choices=["kkt", "jacobian"],
+                    help="kkt: full KKT block set (default, BASELINE configs[2..4]); jacobian: g + A only (configs[1], ungar_b200_jacobian_blocks)")
     return ap.parse_args()
 
 
 # ------------------------------------------------------------------------------------------------------
 # Workload description shared by both arms
 # ------------------------------------------------------------------------------------------------------
-def workload_config(args, world: int) -> dict:
+BASELINE_CONFIG = {("quadrotor", "jacobian"): 1, ("quadrotor", "kkt"): 1, ("rc_car", "kkt"): 2, ("quadruped", "kkt"): 3}
+
+
+def workload_config(args, world: int, record_bytes: int = 0, input_bytes: int = 0) -> dict:
+    what = "KKT sweep" if args.mode == "kkt" else "Jacobian sweep (g + A only)"
+    cfg = BASELINE_CONFIG.get((args.model, args.mode))
     return {
-        "workload": f"{args.model} NMPC KKT sweep, N={args.horizon}, {args.batch} trajectories/GPU, {args.dtype} "
-                    f"(BASELINE.json configs[3]; {world} GPU(s) -> {args.batch * world} trajectories)",
-        "model_problem": args.model, "horizon": args.horizon, "batch_per_gpu": args.batch,
+        "workload": f"{args.model} NMPC {what}, N={args.horizon}, {args.batch} trajectories/GPU, {args.dtype} "
+                    f"({'BASELINE.json configs[%d]' % cfg if cfg is not None else 'not a BASELINE config'}; {world} GPU(s) -> "
+                    f"{args.batch * world} trajectories)",
+        "model_problem": args.model, "horizon": args.horizon, "batch_per_gpu": args.batch, "mode": args.mode,
         "global_batch": args.batch * world, "parallelism": f"independent trajectories sharded over {world} rank(s)",
-        "l2_policy": "no flush: each step streams 1.35 GB of records (> 126 MB L2) and the inputs rotate over 4 buffers "
-                     "(220 MB > L2)",
+        "l2_policy": f"no flush: each step streams {record_bytes / 1e9:.2f} GB of records through the 126 MB L2 (evicting whatever the "
+                     f"previous step left there) and the inputs rotate over 4 buffers ({4 * input_bytes / 1e6:.0f} MB)",
     }
 
 
-def algorithmic_bytes_per_trajectory(layout: dict, elem: int) -> int:
+def algorithmic_bytes_per_trajectory(layout: dict, elem: int, mode: str = "kkt") -> int:
     """SURVEY.md §8(d): every input scalar read once + every output scalar written once (padding excluded;
-    quadruped contact rows in their compact 4x20 form, 4x10 for k = 0)."""
+    quadruped contact rows in their compact 4x20 form, 4x10 for k = 0).  mode "jacobian": inputs + g + A (+ C) only (config 2)."""
     L = layout
     N = L["horizon"]
     contact = N * L["legs"] * 80 - L["legs"] * 40 if L["legs"] else 0
+    if mode == "jacobian":
+        return (L["n_dec"] + L["n_par"] + L["m_eq"] + N * L["nx"] * L["nz"] + contact) * elem
     scalars = (L["n_dec"] + L["n_par"] + L["m_eq"] + N * L["nx"] * L["nz"] + contact + L["m_ineq"] + 2 + L["n_dec"] +
                N * L["tri"] + L["tri_terminal"] + (N - 1) * L["hc_per_node"])
     return scalars * elem
@@ -187,6 +197,9 @@ def reference_arm(args, rank: int, world: int):
         return  # the CPU arm has no multi-process path: rank 0 alone runs and prints it
     mid = W.MODEL_IDS[args.model]
     run, threads = cpu_sweep_runner(args)
+    import oracle as oracle_pkg  # the CPU arm may execute oracle/ (it IS the thing timed here)
+
+    ref_record_size = oracle_pkg.Oracle().record_layout(mid, args.horizon)["size"]  # same layout as ungar_b200_kkt_layout
     pool = W.synthetic_batch(mid, args.horizon, min(args.batch, 1024), seed=20240807)
     total_steps = args.steps + args.warmup
     per_step = min(60.0 / max(total_steps, 1), 10.0)  # whole run within ~1-2 minutes
@@ -204,7 +217,8 @@ def reference_arm(args, rank: int, world: int):
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": 1e3 * t_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "f64", "data": "synthetic", "impl": "reference", "config": workload_config(args, 1),
+        "dtype": "f64", "data": "synthetic", "impl": "reference",
+        "config": workload_config(args, max(args.gpus, 1), args.batch * ref_record_size * 8, args.batch * W.sizes(mid, args.horizon)["n_xp"] * 8),
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": desc},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -246,10 +260,15 @@ def ours(args, rank: int, local_rank: int, world: int):
     gathered = torch.empty((world * B, 32), dtype=tdt, device=dev) if world > 1 else None
     sum_host = torch.empty((B, 32), dtype=tdt, pin_memory=True)
 
-    exchange = sharding.SummaryExchange(B, tdt, dev) if world > 1 else None
+    exchange = sharding.SummaryExchange(B, tdt, dev) if world > 1 and args.mode == "kkt" else None
+
+    jac = args.mode == "jacobian"
 
     def step(i):
         # the all-gather of step i is posted asynchronously and overlaps the sweep of step i + 1 (double-buffered summaries)
+        if jac:
+            model.jacobian_blocks(d_xps[i % 4], d_rec)
+            return
         if exchange is None:
             model.step(d_xps[i % 4], records=d_rec, summaries=d_sum)
             return
@@ -297,16 +316,26 @@ def ours(args, rank: int, local_rank: int, world: int):
     # ---- end-to-end leg: host buffers through the C ABI, H2D of the inputs + D2H of the summaries per step ----
     e2e_steps = max(10, min(args.steps, 100))
     xp_host_np, sum_host_np = xp_host.numpy(), sum_host.numpy()
-    for _ in range(3):
-        model.step(xp_host_np, records=d_rec, summaries=sum_host_np)
-    fence()
-    t0 = time.time()
-    e0.record()
-    for _ in range(e2e_steps):
+    rec_host_np = torch.empty((B, L["size"]), dtype=tdt, pin_memory=True).numpy() if jac else None
+
+    def e2e_step():
+        if jac:  # the ABI returns the record to the host (g and A valid): H2D of xp, sweep, D2H of the record
+            model.jacobian_blocks(xp_host_np, rec_host_np)
+            return
         model.step(xp_host_np, records=d_rec, summaries=sum_host_np)
         if world > 1:  # the step's own summaries (they landed on the host) are what the ranks exchange
             d_sum.copy_(sum_host, non_blocking=True)
             dist.all_gather_into_tensor(gathered, d_sum)
+
+    if jac:
+        e2e_steps = min(e2e_steps, 20)
+    for _ in range(3):
+        e2e_step()
+    fence()
+    t0 = time.time()
+    e0.record()
+    for _ in range(e2e_steps):
+        e2e_step()
     e1.record()
     fence()
     t1 = time.time()
@@ -333,7 +362,7 @@ def ours(args, rank: int, local_rank: int, world: int):
 
     # full drop-in variant: the whole record goes back to the host every step (what a host-side QP solver needs)
     full_value = None
-    if world == 1:
+    if world == 1 and not jac:
         try:
             rec_host = torch.empty((B, L["size"]), dtype=tdt, pin_memory=True).numpy()
             model.kkt_blocks(xp_host_np, rec_host)
@@ -346,7 +375,7 @@ def ours(args, rank: int, local_rank: int, world: int):
             full_value = None
     # auxiliary: the loop that consumes the records — sweep + QP solve + line search, all on the device
     sqp = None
-    if world == 1 and args.dtype == "f64":
+    if world == 1 and args.dtype == "f64" and not jac:
         try:
             iters = 4  # quadruped.example.cpp:444
             mult = 1.0 if args.model == "quadrotor" else 1.0 / N
@@ -377,11 +406,11 @@ def ours(args, rank: int, local_rank: int, world: int):
         return
 
     # ---- roofline of the dominant kernel (the sweep), from device events around each launch ---------------
-    bytes_per_launch = algorithmic_bytes_per_trajectory(L, elem) * B
+    bytes_per_launch = algorithmic_bytes_per_trajectory(L, elem, args.mode) * B
     peak, peak_src = measured_peak_gbs()
     mean_sweep_ms = statistics.fmean(sweep_ms) if sweep_ms else elapsed_ms / args.steps
     achieved = bytes_per_launch / (mean_sweep_ms * 1e-3) / 1e9
-    key = f"{args.model}_{args.dtype}_N{N}_B{B}"
+    key = f"{args.model}_{args.dtype}_N{N}_B{B}" + ("_jacobian" if jac else "")
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": recorded_traffic(key), "kernel": "kkt_sweep", "kernel_ms": mean_sweep_ms,
                 "algorithmic_bytes_per_launch": bytes_per_launch, "peak_source": peak_src,
@@ -403,8 +432,11 @@ def ours(args, rank: int, local_rank: int, world: int):
         cpu = {"value": n * N * passes / t_total, "unit": UNIT, "cores": threads, "kind": "port",
                "sample": f"first {n} of the {B} trajectories x {passes} passes, fp64, oracle/stage_port.cpp "
                          f"(-O3 -ffast-math) on {threads} threads ({t_total:.1f} s of wall time)"}
-        got = d_rec_sample(model, d_xps[0], n, tdt, dev)
+        got = d_rec_sample(model, d_xps[0], n, tdt, dev, jac)
         tol = 1e-6 if args.dtype == "f64" else 1e-3
+        if jac:  # only g and A are specified after the Jacobian sweep
+            cols = np.r_[L["g"]:L["g"] + L["m_eq"], L["A"]:L["A"] + N * L["nx"] * L["nz"]]
+            got, ref = got[:, cols], ref[:, cols]
         err = float(np.max(np.abs(got - ref) / (np.abs(ref) + 1e-3 * np.max(np.abs(ref)))))
         parity = {"checked_trajectories": n, "max_rel_err": err, "tolerance": tol, "ok": bool(err <= tol)}
         if not parity["ok"]:
@@ -414,10 +446,11 @@ def ours(args, rank: int, local_rank: int, world: int):
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
         "ms_per_step": elapsed_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": args.dtype, "data": "synthetic", "config": workload_config(args, world), "clocks": clocks,
+        "dtype": args.dtype, "data": "synthetic",
+        "config": workload_config(args, world, B * L["size"] * elem, B * model.n_xp * elem), "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": B * model.n_xp * elem,
-                "d2h_bytes_per_step": B * 32 * elem, "steps": e2e_steps,
-                "path": "ungar_b200_kkt_step(MEM_HOST): pinned host xp -> H2D in 4 chunks overlapped with the sweep of the previous chunk (records stay in HBM) -> summaries -> D2H"},
+                "d2h_bytes_per_step": B * (L["size"] if jac else 32) * elem, "steps": e2e_steps,
+                "path": "ungar_b200_jacobian_blocks(MEM_HOST): pinned host xp -> H2D -> Jacobian sweep -> record -> D2H" if jac else "ungar_b200_kkt_step(MEM_HOST): pinned host xp -> H2D in 4 chunks overlapped with the sweep of the previous chunk (records stay in HBM) -> summaries -> D2H"},
         "e2e_full_record_d2h": ({"value": full_value, "unit": UNIT, "d2h_bytes_per_step": B * L["size"] * elem,
                                  "path": "ungar_b200_kkt_blocks(MEM_HOST): whole record back to the host every step"}
                                 if full_value else None),
@@ -430,11 +463,11 @@ def ours(args, rank: int, local_rank: int, world: int):
         dist.destroy_process_group()
 
 
-def d_rec_sample(model, d_xp, n, tdt, dev):
+def d_rec_sample(model, d_xp, n, tdt, dev, jac=False):
     import torch
 
     out = torch.zeros((n, model.layout["size"]), dtype=tdt, device=dev)
-    model.kkt_blocks(d_xp[:n], out)
+    (model.jacobian_blocks if jac else model.kkt_blocks)(d_xp[:n], out)
     torch.cuda.synchronize()
     return out.cpu().numpy().astype(np.float64)
 

@@ -137,6 +137,14 @@ int ungar_b200_kkt_layout_get(const ungar_b200_model* model, ungar_b200_kkt_layo
 int ungar_b200_kkt_blocks(ungar_b200_model* model, const void* xp, int64_t batch, int64_t ld_xp,
                           void* records, int64_t ld_rec, int32_t mem, void* stream);
 
+/* The "Jacobian sweep" alone (BASELINE.json configs[1]): after the call the blocks `g` (equality residuals) and `A`
+ * (dynamics Jacobians; for the quadruped also `C`) of every record are those ungar_b200_kkt_blocks would write; the other
+ * blocks of the record are unspecified.  Quadrotor and RC car skip the objective / inequality / Gauss-Newton work and
+ * the `H` stores (about 40 % of the bytes); the quadruped runs the full sweep.  Replaces Function::Evaluate + Function::Jacobian
+ * of the equality constraints (function.hpp:180-230) for every shooting interval. */
+int ungar_b200_jacobian_blocks(ungar_b200_model* model, const void* xp, int64_t batch, int64_t ld_xp, void* records,
+                               int64_t ld_rec, int32_t mem, void* stream);
+
 /* Per-trajectory summary (32 scalars: u_0 [nu<=24], cost f, barrier, |g|_inf, max h, pad) read back from
  * the records — the payload of the one all-gather per outer iteration. */
 #define UNGAR_B200_SUMMARY_SIZE 32

@@ -244,3 +244,25 @@ def test_host_step_pipeline_equals_device_step(torch_cuda, name, N, dtype, B):
                                                       sum_h.ctypes.data, _lib.MEM_HOST, None))
         assert np.array_equal(sum_h, sum_d.cpu().numpy())
         assert torch.equal(rec_h, rec_d)
+
+
+@pytest.mark.parametrize("name,N,dtype,B", [("quadrotor", 30, "f32", 257), ("quadrotor", 17, "f64", 9), ("rc_car", 60, "f32", 130),
+                                            ("rc_car", 31, "f64", 5), ("quadruped", 100, "f64", 12), ("quadruped", 7, "f32", 3)])
+def test_jacobian_blocks_equal_the_full_sweep(torch_cuda, name, N, dtype, B):
+    """ungar_b200_jacobian_blocks (the Jacobian sweep of BASELINE configs[1]): g and A (quadruped: also C) are bit-identical to what
+    ungar_b200_kkt_blocks writes; ragged horizons and batch sizes exercise the tails; the host-buffer path agrees with the device one."""
+    torch = torch_cuda
+    mid = W.MODEL_IDS[name]
+    model = make_model(name, N, dtype)
+    xp = W.synthetic_batch(mid, N, B, seed=19).astype(model.np_dtype)
+    d_xp = torch.from_numpy(xp).cuda()
+    tdt = torch.float64 if dtype == "f64" else torch.float32
+    full = model.kkt_blocks(d_xp, torch.zeros((B, model.layout["size"]), dtype=tdt, device="cuda"))
+    jac = model.jacobian_blocks(d_xp, torch.full((B, model.layout["size"]), float("nan"), dtype=tdt, device="cuda"))
+    torch.cuda.synchronize()
+    fb, jb = model.split_record(full.cpu().numpy()), model.split_record(jac.cpu().numpy())
+    for key in ("g", "A") + (("C",) if model.layout["legs"] else ()):
+        assert np.array_equal(fb[key], jb[key]), key
+    host = model.jacobian_blocks(xp)
+    hb = model.split_record(host)
+    assert np.array_equal(hb["g"], fb["g"]) and np.array_equal(hb["A"], fb["A"])

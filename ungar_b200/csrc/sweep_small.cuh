@@ -310,7 +310,9 @@ struct SmallShape {
     }
 };
 
-template <class Mdl, class T, bool BARRIER, int WARPS>
+// JAC: the "Jacobian sweep" alone (BASELINE config 2): only the equality residuals g and the dynamics Jacobian blocks A are computed
+// and stored; the objective / inequality / Gauss-Newton work and the H image are skipped.
+template <class Mdl, class T, bool BARRIER, int WARPS, bool JAC = false>
 __global__ void __launch_bounds__(WARPS * 32)
 small_team_kernel(const T* __restrict__ xp_all, long long ld_xp, T* __restrict__ rec_all, long long ld_rec,
                   T* __restrict__ partials, int N, int n_xp, long long batch, RecLayout L, BarrierCoef<T> bar,
@@ -377,6 +379,7 @@ small_team_kernel(const T* __restrict__ xp_all, long long ld_xp, T* __restrict__
                     const T gv = sx[Mdl::x_off(N, k + 1) + i] - co[Pol::oXN + i];
                     r[L.g + NX + NX * k + i] = gv;
                     gmax = fmax(gmax, m_abs(gv));
+                    if constexpr (JAC) continue;
                     const T wgt = Pol::template state_weight<T>(i);
                     T gq = T(0), hd = BARRIER ? T(1e-6) : T(0);
                     if (wgt != T(0)) {
@@ -400,7 +403,7 @@ small_team_kernel(const T* __restrict__ xp_all, long long ld_xp, T* __restrict__
                     r[L.grad + Mdl::x_off(N, k) + i] = gq;
                     sH[tri_index(NZ, i, i)] = hd;
                 }
-                Pol::template fill_inputs<T, BARRIER>(c, sx, N, k, bar, r, L, sH, cost, bsum, hmax);
+                if constexpr (!JAC) Pol::template fill_inputs<T, BARRIER>(c, sx, N, k, bar, r, L, sH, cost, bsum, hmax);
             }
             // ---- hand the 4-node image to the TMA engine ----------------------------------------------------------------------
             const int k0 = g * G, cnt = min(G, N - k0);
@@ -409,18 +412,19 @@ small_team_kernel(const T* __restrict__ xp_all, long long ld_xp, T* __restrict__
             if (cnt == G) {
                 if (lane == 0) {
                     tpn_bulk_store(r + L.A + (long long)k0 * NA, stA, G * NA * sizeof(T));
-                    tpn_bulk_store(r + L.H + (long long)k0 * TRI, stH, G * TRI * sizeof(T));
+                    if constexpr (!JAC) tpn_bulk_store(r + L.H + (long long)k0 * TRI, stH, G * TRI * sizeof(T));
                     asm volatile("cp.async.bulk.commit_group;" ::: "memory");
                 }
                 pending = true;
             } else {  // ragged tail of the horizon: plain coalesced stores
                 for (int e = lane; e < cnt * NA; e += 32) r[L.A + (long long)k0 * NA + e] = stA[e];
-                for (int e = lane; e < cnt * TRI; e += 32) r[L.H + (long long)k0 * TRI + e] = stH[e];
+                if constexpr (!JAC)
+                    for (int e = lane; e < cnt * TRI; e += 32) r[L.H + (long long)k0 * TRI + e] = stH[e];
                 __syncwarp();
             }
         }
         // ---- terminal state x_N ---------------------------------------------------------------------------------------------------
-        if (lane < NX) {
+        if (!JAC && lane < NX) {
             const int i = lane;
             const T wgt = Pol::template state_weight<T>(i);
             T gq = T(0), hd = BARRIER ? T(1e-6) : T(0);

@@ -291,7 +291,7 @@ ub::BarrierCoef<T> cast_barrier(const ub::BarrierCoef<double>& b) {
 // ---------------------------------------------------------------------------------------------
 // Launches
 // ---------------------------------------------------------------------------------------------
-enum SweepMode { MODE_KKT = 0, MODE_PLAIN = 1, MODE_JH = 2 };
+enum SweepMode { MODE_KKT = 0, MODE_PLAIN = 1, MODE_JH = 2, MODE_JAC = 3 };  // MODE_JAC: g and A only (the rest of the record unspecified)
 
 template <class Mdl, class T, int M, bool BARRIER>
 int launch_generic(ungar_b200_model& mdl, const T* xp, int64_t batch, int64_t ld_xp, T* rec, int64_t ld_rec,
@@ -448,10 +448,10 @@ bool small_applicable(const ungar_b200_model& mdl, const void* rec, int64_t ld_r
     return Mdl::LEGS == 0 && (reinterpret_cast<uintptr_t>(rec) & 15) == 0 && (ld_rec * sizeof(T)) % 16 == 0;
 }
 
-template <class Mdl, class T, bool BARRIER>
+template <class Mdl, class T, bool BARRIER, bool JAC = false>
 int launch_small(ungar_b200_model& mdl, const T* xp, int64_t batch, int64_t ld_xp, T* rec, int64_t ld_rec, cudaStream_t stream) {
     constexpr int WARPS = 4;
-    auto kernel = ub::small_team_kernel<Mdl, T, BARRIER, WARPS>;
+    auto kernel = ub::small_team_kernel<Mdl, T, BARRIER, WARPS, JAC>;
     const int n_xp = int(mdl.layout.n_dec + mdl.layout.n_par);
     const auto offs = ub::SmallShape<Mdl, T>::offsets(mdl.N, n_xp);
     const int smem = WARPS * offs.total * int(sizeof(T));
@@ -527,8 +527,9 @@ int launch_sweep_t(ungar_b200_model& mdl, const void* xp, int64_t batch, int64_t
         const size_t small_smem = 4 * size_t(ub::SmallShape<Mdl, T>::offsets(mdl.N, int(mdl.layout.n_dec + mdl.layout.n_par)).total) * sizeof(T);
         if (small_applicable<Mdl, T>(mdl, rec, ld_rec) && small_smem <= 200 * 1024) {
             entries = 1;  // one partial per trajectory
-            rc = mode == MODE_KKT ? launch_small<Mdl, T, true>(mdl, x, batch, ld_xp, r, ld_rec, stream)
-                                  : launch_small<Mdl, T, false>(mdl, x, batch, ld_xp, r, ld_rec, stream);
+            rc = mode == MODE_KKT   ? launch_small<Mdl, T, true>(mdl, x, batch, ld_xp, r, ld_rec, stream)
+                 : mode == MODE_JAC ? launch_small<Mdl, T, false, true>(mdl, x, batch, ld_xp, r, ld_rec, stream)
+                                    : launch_small<Mdl, T, false>(mdl, x, batch, ld_xp, r, ld_rec, stream);
         } else if (tpn_applicable<Mdl, T>(mdl))
             rc = mode == MODE_KKT ? launch_tpn<Mdl, T, true>(mdl, x, batch, ld_xp, r, ld_rec, stream)
                                   : launch_tpn<Mdl, T, false>(mdl, x, batch, ld_xp, r, ld_rec, stream);
@@ -538,6 +539,7 @@ int launch_sweep_t(ungar_b200_model& mdl, const void* xp, int64_t batch, int64_t
     } else if (mode == MODE_KKT) rc = launch_generic<Mdl, T, M, true>(mdl, x, batch, ld_xp, r, ld_rec, stream);
     else rc = launch_generic<Mdl, T, M, false>(mdl, x, batch, ld_xp, r, ld_rec, stream);
     if (rc) return rc;
+    if (mode == MODE_JAC) return UNGAR_B200_OK;  // no objective / barrier partials to reduce
     const ungar_b200_kkt_layout& L = mdl.layout;
     const int threads = 128;  // 4 trajectories per CTA
     ub::finalize_kernel<T><<<unsigned((batch * 32 + threads - 1) / threads), threads, 0, stream>>>(
@@ -862,8 +864,8 @@ int ungar_b200_kkt_layout_get(const ungar_b200_model* model, ungar_b200_kkt_layo
     return UNGAR_B200_OK;
 }
 
-int ungar_b200_kkt_blocks(ungar_b200_model* model, const void* xp, int64_t batch, int64_t ld_xp, void* records,
-                          int64_t ld_rec, int32_t mem, void* stream_) {
+static int blocks_call(ungar_b200_model* model, const void* xp, int64_t batch, int64_t ld_xp, void* records, int64_t ld_rec,
+                       int32_t mem, void* stream_, int mode) {
     if (!model) return fail(UNGAR_B200_EINVAL, "null model");
     if (batch < 0 || (batch > 0 && (!xp || !records))) return fail(UNGAR_B200_EINVAL, "null buffer");
     const ungar_b200_kkt_layout& L = model->layout;
@@ -875,16 +877,26 @@ int ungar_b200_kkt_blocks(ungar_b200_model* model, const void* xp, int64_t batch
     UB_CUDA(cudaSetDevice(model->desc.device));
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
     const size_t es = model->elem;
-    if (mem == UNGAR_B200_MEM_DEVICE) return launch_sweep(*model, xp, batch, ld_xp, records, ld_rec, MODE_KKT, nullptr, stream);
+    if (mem == UNGAR_B200_MEM_DEVICE) return launch_sweep(*model, xp, batch, ld_xp, records, ld_rec, mode, nullptr, stream);
 
     if (int rc = model->ws_xp.reserve(size_t(batch) * n_in * es)) return rc;
     if (int rc = model->ws_records.reserve(size_t(batch) * L.size * es)) return rc;
     UB_CUDA(cudaMemcpy2DAsync(model->ws_xp.ptr, n_in * es, xp, ld_xp * es, n_in * es, batch, cudaMemcpyHostToDevice, stream));
-    if (int rc = launch_sweep(*model, model->ws_xp.ptr, batch, n_in, model->ws_records.ptr, L.size, MODE_KKT, nullptr, stream)) return rc;
+    if (int rc = launch_sweep(*model, model->ws_xp.ptr, batch, n_in, model->ws_records.ptr, L.size, mode, nullptr, stream)) return rc;
     UB_CUDA(cudaMemcpy2DAsync(records, ld_rec * es, model->ws_records.ptr, L.size * es, L.size * es, batch,
                               cudaMemcpyDeviceToHost, stream));
     UB_CUDA(cudaStreamSynchronize(stream));
     return UNGAR_B200_OK;
+}
+
+int ungar_b200_kkt_blocks(ungar_b200_model* model, const void* xp, int64_t batch, int64_t ld_xp, void* records,
+                          int64_t ld_rec, int32_t mem, void* stream_) {
+    return blocks_call(model, xp, batch, ld_xp, records, ld_rec, mem, stream_, MODE_KKT);
+}
+
+int ungar_b200_jacobian_blocks(ungar_b200_model* model, const void* xp, int64_t batch, int64_t ld_xp, void* records,
+                               int64_t ld_rec, int32_t mem, void* stream_) {
+    return blocks_call(model, xp, batch, ld_xp, records, ld_rec, mem, stream_, MODE_JAC);
 }
 
 int ungar_b200_qp_solve(ungar_b200_model* model, const void* records_device, int64_t batch, int64_t ld_rec, void* steps,

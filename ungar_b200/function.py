@@ -115,6 +115,13 @@ class Model:
                                               self._ld(out2), mem, stream))
         return out2[0] if squeeze else out2
 
+    def jacobian_blocks(self, xp, out=None):
+        """The Jacobian sweep alone: ``g`` and ``A`` (quadruped: also ``C``) of ``records[B, layout.size]``; other blocks unspecified."""
+        xp2, out2, mem, stream, squeeze = self._buffers(xp, out, self.layout["size"])
+        check(self._lib.ungar_b200_jacobian_blocks(self._handle, self._ptr(xp2), xp2.shape[0], self._ld(xp2), self._ptr(out2),
+                                                   self._ld(out2), mem, stream))
+        return out2[0] if squeeze else out2
+
     def summaries(self, xp, records, out=None):
         """``[B, 32]`` per-trajectory summaries (device tensors only): the all-gather payload."""
         import torch
