@@ -160,6 +160,19 @@ class Model {
         check(ungar_b200_kkt_step(_handle, xpHost, batch, VariableSize(), recordsDevice, _layout.size, summariesHost,
                                   UNGAR_B200_MEM_HOST, stream));
     }
+    // The Jacobian sweep alone (g, A and, for the quadruped, C of the record; device pointers).
+    void JacobianBlocksDevice(const Real* xp, index_t batch, index_t ldXp, Real* records, index_t ldRec, void* stream = nullptr) {
+        check(ungar_b200_jacobian_blocks(_handle, xp, batch, ldXp, records, ldRec, UNGAR_B200_MEM_DEVICE, stream));
+    }
+    // Exact solve of the QP of the records (device pointers): steps[batch][n_dec], optional multipliers[batch][m_eq].  F64 models.
+    void QpSolveDevice(const Real* records, index_t batch, index_t ldRec, Real* steps, Real* multipliers = nullptr, void* stream = nullptr) {
+        check(ungar_b200_qp_solve(_handle, records, batch, ldRec, steps, _layout.n_dec, multipliers, _layout.m_eq, stream));
+    }
+    // BacktrackingLineSearch::Do for the whole batch (device pointers): xp[:, 0:n_dec] += alpha * steps where a step is accepted.
+    void LineSearchDevice(Real* xp, index_t batch, index_t ldXp, const Real* steps, const ungar_b200_sqp_options& options,
+                          std::int32_t* status = nullptr, Real* info = nullptr, void* stream = nullptr) {
+        check(ungar_b200_line_search(_handle, xp, batch, ldXp, steps, _layout.n_dec, &options, status, info, stream));
+    }
     ungar_b200_model* handle() const { return _handle; }
     double BarrierStiffness() const { return _stiffness; }
     double BarrierEpsilon() const { return _epsilon; }
