@@ -365,3 +365,21 @@ int oracle_approx_exp(const double* v, double* q, double* jac) {
 }
 
 }  // extern "C"
+
+// Value and directional derivative dy/dx . dir of one function (dir has n_dec entries; the parameters carry no tangent):
+// the `dwProjection` of BacktrackingLineSearch::Do (backtracking_line_search.hpp:92) without forming the gradient.
+extern "C" int oracle_directional(int model, int fn, int N, const double* xp, const double* dir, double* y, double* dy) {
+    using namespace oracle;
+    Sizes s;
+    if (!get_sizes(model, N, s)) return -1;
+    std::vector<Dual1> v(s.n_dec + s.n_par);
+    for (int i = 0; i < s.n_dec; ++i) v[i] = Dual1(xp[i], {{0, dir[i]}});
+    for (int i = s.n_dec; i < s.n_dec + s.n_par; ++i) v[i] = Dual1(xp[i]);
+    std::vector<Dual1> out;
+    if (!eval_fn(model, fn, N, v.data(), out)) return -1;
+    for (std::size_t r = 0; r < out.size(); ++r) {
+        y[r]  = out[r].v;
+        dy[r] = out[r].d.empty() ? 0.0 : out[r].d[0].second;
+    }
+    return static_cast<int>(out.size());
+}

@@ -77,3 +77,38 @@ def test_monolithic_qp_step_is_a_kkt_point(oracle, model, N):
         L.update(horizon=N, n_dec=s["n_dec"], m_eq=s["m_eq"])
         d2, _ = Q.kkt_solve(rec, L)
         assert np.max(np.abs(d - d2)) < 1e-6 * np.max(np.abs(d))
+
+
+@pytest.mark.parametrize("N,perturb", [(6, False), (30, True)])
+def test_cpp_qp_port_equals_the_sparse_kkt_solve(oracle, N, perturb):
+    """oracle/sqp_port.cpp (the timed CPU baseline of the SQP loop) against the sparse-LU oracle of the same record."""
+    from oracle import qp_reference as Q
+    from ungar_b200 import workloads as W
+
+    xp = W.synthetic_batch(W.QUADRUPED, N, 3, seed=41, perturb_params=perturb)
+    rec = oracle.stage_sweep(W.QUADRUPED, N, xp, 1.0, 1.0)
+    steps = oracle.qp_solve_port(N, rec, threads=2)
+    L = oracle.record_layout(W.QUADRUPED, N)
+    s = oracle.sizes(W.QUADRUPED, N)
+    L.update(horizon=N, n_dec=s["n_dec"], m_eq=s["m_eq"])
+    for b in range(3):
+        d_ref, _ = Q.kkt_solve(rec[b], L)
+        assert np.max(np.abs(steps[b] - d_ref)) <= 1e-8 * np.max(np.abs(d_ref))
+
+
+def test_cpp_sqp_port_equals_the_python_restatement(oracle):
+    """Same statuses, iteration counts and iterates as oracle/sqp_reference.py::soft_sqp (two exact QP solvers: 1e-5 like the device
+    loop's test), with trajectories split over threads."""
+    from ungar_b200 import workloads as W
+
+    N, iters = 10, 5
+    xp = W.synthetic_batch(W.QUADRUPED, N, 4, seed=23)
+    out, status = oracle.sqp_solve_port(N, xp, 1.0, 1.0, 1.0 / N, iters, threads=3)
+    n = oracle.sizes(W.QUADRUPED, N)["n_dec"]
+    for b in range(4):
+        ref, ref_status, ref_iters, _ = S.soft_sqp(oracle, W.QUADRUPED, N, xp[b], 1.0, 1.0, 1.0 / N, iters)
+        assert (status[b, 0], status[b, 1]) == (ref_status, ref_iters)
+        assert np.max(np.abs(out[b, :n] - ref[:n])) <= 1e-5 * np.max(np.abs(ref[:n]))
+        assert np.array_equal(out[b, n:], xp[b, n:])
+    with pytest.raises(RuntimeError):
+        oracle.sqp_solve_port(N, xp[:, :50], 1.0, 1.0, 1.0 / N, 1)
