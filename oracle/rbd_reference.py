@@ -186,3 +186,49 @@ def kinetic_energy(tree: Tree, q, v):
     for i in range(1, tree.nb):
         vel.append(X[i] @ vel[tree.parent[i]] + S[i][:, 0] * v[5 + i])
     return 0.5 * sum(vel[i] @ tree.I[i] @ vel[i] for i in range(tree.nb))
+
+
+def world_poses(tree: Tree, q):
+    """(R, p) of every movable body in the world, from the products of the Pluecker transforms."""
+    X, _ = tree.transforms(q)
+    Xw = [X[0]]
+    for i in range(1, tree.nb):
+        Xw.append(X[i] @ Xw[tree.parent[i]])   # world -> body i
+    poses = []
+    for Xi in Xw:
+        E = Xi[:3, :3]
+        rx = -E.T @ Xi[3:, :3]                  # skew(r)
+        poses.append((E.T, np.array([rx[2, 1], rx[0, 2], rx[1, 0]])))
+    return poses, Xw
+
+
+def body_mass_com(I6):
+    m = I6[3, 3]
+    h = np.array([I6[2, 4], I6[0, 5], I6[1, 3]])   # m * skew(c) block
+    return m, (h / m if m > 0 else np.zeros(3))
+
+
+def com(tree: Tree, q):
+    poses, _ = world_poses(tree, q)
+    tot, M = np.zeros(3), 0.0
+    for (R, p), I6 in zip(poses, tree.I):
+        m, c = body_mass_com(I6)
+        tot += m * (p + R @ c)
+        M += m
+    return tot / M, M
+
+
+def centroidal_momentum(tree: Tree, q, v):
+    """[linear; angular about the centre of mass] in world-aligned axes: sum of the body momenta moved with force transforms."""
+    X, S = tree.transforms(q)
+    poses, Xw = world_poses(tree, q)
+    c, _ = com(tree, q)
+    vel = [P @ v[:6]]
+    for i in range(1, tree.nb):
+        vel.append(X[i] @ vel[tree.parent[i]] + S[i][:, 0] * v[5 + i])
+    Xc = plucker(np.eye(3), c)                   # world -> frame at the centre of mass, world axes
+    h = np.zeros(6)
+    for i in range(tree.nb):
+        # momentum of body i in its own coordinates -> world coordinates (X^T) -> centre-of-mass frame (X^-T)
+        h += np.linalg.inv(Xc).T @ (Xw[i].T @ (tree.I[i] @ vel[i]))
+    return P @ h

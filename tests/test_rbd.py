@@ -111,3 +111,72 @@ def test_taped_forward_dynamics_on_the_gpu_matches_the_oracle():
     J = f.Jacobian(X[0]).toarray()                   # d a / d tau = M^-1
     Minv = np.linalg.inv(R.mass_matrix(tree, X[0, :m.nq]))
     assert np.allclose(J[:, m.nq + m.nv:], Minv, rtol=1e-8, atol=1e-10)
+
+
+def test_remaining_quantities_against_the_oracle_and_finite_differences():
+    """The other quantities of rbd/quantities/*.hpp: centre of mass (position / velocity / acceleration), centroidal momentum and its
+    matrix, composite inertia, energies, gravity and nonlinear terms, M^-1, frames — against the numpy oracle where it has the
+    quantity and against finite differences along pinocchio::integrate otherwise (which also pins the body-frame velocity convention)."""
+    from oracle import rbd_reference as R
+
+    for urdf, seed in ((URDF, 3),) + (((ANYMAL, 4),) if os.path.exists(ANYMAL) else ()):
+        model, tree = rbd.load_urdf(urdf), R.Tree(urdf)
+        rng = np.random.default_rng(seed)
+        q, v, a = random_state(model, rng)
+        ql, vl, al = list(q), list(v), list(a)
+        c = np.array(rbd.com_position(model, ql))
+        c_ref, mass = R.com(tree, q)
+        assert np.allclose(c, c_ref, atol=1e-12) and abs(mass - model.total_mass) < 1e-9
+        # velocity / acceleration of the centre of mass by central differences along the flow of (v, a)
+        dt = 1e-5
+        cp = np.array(rbd.com_position(model, rbd.integrate(model, ql, vl, dt)))
+        cm = np.array(rbd.com_position(model, rbd.integrate(model, ql, vl, -dt)))
+        vc = np.array(rbd.com_velocity(model, ql, vl))
+        assert np.allclose(vc, (cp - cm) / (2 * dt), atol=1e-7)
+        vcp = np.array(rbd.com_velocity(model, rbd.integrate(model, ql, vl, dt), list(v + a * dt)))
+        vcm = np.array(rbd.com_velocity(model, rbd.integrate(model, ql, vl, -dt), list(v - a * dt)))
+        assert np.allclose(np.array(rbd.com_acceleration(model, ql, vl, al)), (vcp - vcm) / (2 * dt), atol=1e-6)
+        # centroidal momentum: oracle, linear part = M v_com, hg = Ag v
+        hg = np.array(rbd.centroidal_momentum(model, ql, vl))
+        assert np.allclose(hg, R.centroidal_momentum(tree, q, v), rtol=1e-10, atol=1e-10)
+        assert np.allclose(hg[:3], model.total_mass * vc, atol=1e-10)
+        Ag = np.array(rbd.centroidal_momentum_matrix(model, ql))
+        assert Ag.shape == (6, model.nv) and np.allclose(Ag @ v, hg, atol=1e-10)
+        # composite inertia: a rigid rotation of the frozen tree about its centre of mass carries angular momentum I_g w
+        mass_g, Ig = rbd.composite_rigid_body_inertia(model, ql)
+        Ig = np.array(Ig)
+        assert abs(mass_g - model.total_mass) < 1e-12 and np.allclose(Ig, Ig.T, atol=1e-12) and np.linalg.eigvalsh(Ig).min() > 0
+        Rwb = R.quat_matrix(*q[3:7])
+        w_world = np.array([0.3, -0.2, 0.5])
+        v_rigid = np.zeros(model.nv)
+        v_rigid[3:6] = Rwb.T @ w_world
+        v_rigid[0:3] = Rwb.T @ np.cross(w_world, q[:3] - c)          # base origin velocity of a rotation about the centre of mass
+        h_rigid = np.array(rbd.centroidal_momentum(model, ql, list(v_rigid)))
+        assert np.allclose(h_rigid[:3], 0.0, atol=1e-10) and np.allclose(h_rigid[3:], Ig @ w_world, atol=1e-10)
+        # energies, gravity, nonlinear effects, inverse mass matrix, frames
+        M = R.mass_matrix(tree, q)
+        assert abs(rbd.kinetic_energy(model, ql, vl) - 0.5 * v @ M @ v) < 1e-10 * max(1.0, v @ M @ v)
+        assert abs(rbd.potential_energy(model, ql) - model.total_mass * rbd.GRAVITY * c[2]) < 1e-10
+        g = np.array(rbd.generalized_gravity(model, ql))
+        up = np.array(rbd.potential_energy(model, rbd.integrate(model, ql, list(np.eye(model.nv)[7 % model.nv]), dt)))
+        um = np.array(rbd.potential_energy(model, rbd.integrate(model, ql, list(np.eye(model.nv)[7 % model.nv]), -dt)))
+        assert abs(g[7 % model.nv] - (up - um) / (2 * dt)) < 1e-6                       # g = dU/dq along a joint direction
+        assert np.allclose(np.array(rbd.nonlinear_effects(model, ql, vl)), R.bias_forces(tree, q, v), rtol=1e-10, atol=1e-10)
+        assert np.allclose(np.array(rbd.joint_space_inertia_matrix_inverse(model, ql)) @ M, np.eye(model.nv), atol=1e-8)
+        poses, _ = R.world_poses(tree, q)
+        for (name, (Rw, pw)), (Rr, pr) in zip(rbd.frames(model, ql).items(), poses):
+            assert np.allclose(np.array(Rw), Rr, atol=1e-12) and np.allclose(np.array(pw), pr, atol=1e-12), name
+
+
+def test_every_quantity_is_taped():
+    robot = rbd.Robot(URDF)
+    m = robot.Model()
+    expect = {"generalized_accelerations": m.nv, "joint_torques": m.nv, "joint_space_inertia_matrix": m.nv ** 2,
+              "joint_space_inertia_matrix_inverse": m.nv ** 2, "generalized_gravity": m.nv, "nonlinear_effects": m.nv, "com_position": 3,
+              "com_velocity": 3, "com_acceleration": 3, "centroidal_momentum": 6, "centroidal_momentum_matrix": 6 * m.nv,
+              "composite_rigid_body_inertia": 10, "kinetic_energy": 1, "potential_energy": 1, "frames": 12 * len(m.bodies)}
+    assert set(expect) == set(rbd.QUANTITIES)       # the fifteen headers of include/ungar/rbd/quantities/
+    for quantity, ny in expect.items():
+        f = robot.MakeFunction(quantity)
+        assert f.DependentVariableSize() == ny, quantity
+        assert f.tape_info()["live_nodes"] > 0

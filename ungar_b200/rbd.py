@@ -393,31 +393,250 @@ def crba(model: RobotModel, q):
     return [[cols[j][i] for j in range(model.nv)] for i in range(model.nv)]
 
 
-class Robot:
-    """Mirror of ``Ungar::Robot`` (rbd/robot.hpp:40-104) for the quantities that are functions of (q, v, tau) / (q, v, a)."""
+# ---------------------------------------------------------------------------------------------------------------------------
+# The remaining quantities of include/ungar/rbd/quantities/*.hpp (generic scalar, world frame where Pinocchio uses it)
+# ---------------------------------------------------------------------------------------------------------------------------
+def _world_kinematics(model, q, v=None, a=None):
+    """World pose (R, p) of every body; with v (and a): body-coordinate spatial velocities (and gravity-free accelerations)."""
+    X, S = _joint_transforms(model, q)
+    nb = len(model.bodies)
+    Rw, pw = [None] * nb, [None] * nb
+    Rw[0], pw[0] = _tr(X[0][0]), list(X[0][1])
+    for i in range(1, nb):
+        par = model.bodies[i].parent
+        Rw[i] = _mm(Rw[par], _tr(X[i][0]))
+        pw[i] = _add(pw[par], _mv(Rw[par], X[i][1]))
+    vel = acc = None
+    if v is not None:
+        vel = [None] * nb
+        vel[0] = _split_v(v)
+        if a is not None:
+            acc = [None] * nb
+            acc[0] = _split_v(a)
+        for i in range(1, nb):
+            par = model.bodies[i].parent
+            vj = (_scale(v[5 + i], S[i][0]), _scale(v[5 + i], S[i][1]))
+            vp = _xm(X[i][0], X[i][1], vel[par])
+            vel[i] = (_add(vp[0], vj[0]), _add(vp[1], vj[1]))
+            if a is not None:
+                ap = _xm(X[i][0], X[i][1], acc[par])
+                c = _crm(vel[i], vj)
+                acc[i] = (_add(_add(ap[0], _scale(a[5 + i], S[i][0])), c[0]), _add(_add(ap[1], _scale(a[5 + i], S[i][1])), c[1]))
+    return Rw, pw, vel, acc
 
-    def __init__(self, urdf: str, gravity: float = GRAVITY):
+
+def com_position(model, q):
+    """pinocchio::centerOfMass(q) -> data.com[0]: centre of mass of the whole tree in the world frame."""
+    Rw, pw, _, _ = _world_kinematics(model, q)
+    tot = [0.0, 0.0, 0.0]
+    for i, b in enumerate(model.bodies):
+        tot = _add(tot, _add(_scale(b.mass, pw[i]), _mv(Rw[i], b.h)))
+    return _scale(1.0 / model.total_mass, tot)
+
+
+def com_velocity(model, q, v):
+    """data.vcom[0]: velocity of the centre of mass in the world frame."""
+    Rw, _, vel, _ = _world_kinematics(model, q, v)
+    tot = [0.0, 0.0, 0.0]
+    for i, b in enumerate(model.bodies):  # m (v_o + w x c) = m v_o + w x h
+        tot = _add(tot, _mv(Rw[i], _add(_scale(b.mass, vel[i][1]), _cross(vel[i][0], b.h))))
+    return _scale(1.0 / model.total_mass, tot)
+
+
+def com_acceleration(model, q, v, a):
+    """data.acom[0]: classical acceleration of the centre of mass in the world frame (gravity is not part of it)."""
+    Rw, _, vel, acc = _world_kinematics(model, q, v, a)
+    tot = [0.0, 0.0, 0.0]
+    for i, b in enumerate(model.bodies):
+        w, vo = vel[i]
+        al, ao = acc[i]
+        lin = _add(_scale(b.mass, _add(ao, _cross(w, vo))), _add(_cross(al, b.h), _cross(w, _cross(w, b.h))))
+        tot = _add(tot, _mv(Rw[i], lin))
+    return _scale(1.0 / model.total_mass, tot)
+
+
+def centroidal_momentum(model, q, v):
+    """pinocchio::ccrba -> data.hg: [linear momentum; angular momentum about the centre of mass], world-aligned axes."""
+    Rw, pw, vel, _ = _world_kinematics(model, q, v)
+    com = com_position(model, q)
+    lin, ang = [0.0, 0.0, 0.0], [0.0, 0.0, 0.0]
+    for i, b in enumerate(model.bodies):
+        n, l = b.inertia_apply(vel[i])                 # momentum about the body origin, body coordinates
+        lw = _mv(Rw[i], l)
+        lin = _add(lin, lw)
+        ang = _add(ang, _add(_mv(Rw[i], n), _cross(_sub(pw[i], com), lw)))
+    return lin + ang
+
+
+def centroidal_momentum_matrix(model, q):
+    """data.Ag (6 x nv): hg = Ag v, one unit velocity per column."""
+    cols = []
+    for j in range(model.nv):
+        e = [0.0] * model.nv
+        e[j] = 1.0
+        cols.append(centroidal_momentum(model, q, e))
+    return [[cols[j][i] for j in range(model.nv)] for i in range(6)]
+
+
+def composite_rigid_body_inertia(model, q):
+    """data.Ig: (total mass, rotational inertia of the whole tree about its centre of mass in world-aligned axes, 3 x 3)."""
+    Rw, pw, _, _ = _world_kinematics(model, q)
+    com = com_position(model, q)
+    I = [[0.0] * 3 for _ in range(3)]
+    for i, b in enumerate(model.bodies):
+        # inertia about the body origin rotated to world axes, moved to the centre of mass with the parallel-axis theorem twice:
+        # I_com_total += R I_o R^T - m [(c.c) 1 - c c^T] + m [(d.d) 1 - d d^T],  c = body com - body origin, d = body com - total com
+        Iw = _mm(_mm(Rw[i], b.I), _tr(Rw[i]))
+        if b.mass == 0.0:
+            continue
+        c = _mv(Rw[i], _scale(1.0 / b.mass, b.h))
+        d = _sub(_add(pw[i], c), com)
+        cc, dd = c[0] * c[0] + c[1] * c[1] + c[2] * c[2], d[0] * d[0] + d[1] * d[1] + d[2] * d[2]
+        for r in range(3):
+            for s_ in range(3):
+                I[r][s_] = I[r][s_] + Iw[r][s_] - b.mass * ((cc if r == s_ else 0.0) - c[r] * c[s_]) + b.mass * ((dd if r == s_ else 0.0) - d[r] * d[s_])
+    return model.total_mass, I
+
+
+def kinetic_energy(model, q, v):
+    """pinocchio::computeKineticEnergy."""
+    _, _, vel, _ = _world_kinematics(model, q, v)
+    e = 0.0
+    for i, b in enumerate(model.bodies):
+        n, l = b.inertia_apply(vel[i])
+        e = e + 0.5 * sum(vel[i][0][k] * n[k] + vel[i][1][k] * l[k] for k in range(3))
+    return e
+
+
+def potential_energy(model, q, gravity: float = GRAVITY):
+    """pinocchio::computePotentialEnergy: -m g . com with g = (0, 0, -gravity)."""
+    return model.total_mass * gravity * com_position(model, q)[2]
+
+
+def generalized_gravity(model, q, gravity: float = GRAVITY):
+    """pinocchio::computeGeneralizedGravity: rnea(q, 0, 0)."""
+    z = [0.0] * model.nv
+    return rnea(model, q, z, z, gravity)
+
+
+def nonlinear_effects(model, q, v, gravity: float = GRAVITY):
+    """pinocchio::nonLinearEffects: rnea(q, v, 0) = Coriolis + centrifugal + gravity."""
+    return rnea(model, q, v, [0.0] * model.nv, gravity)
+
+
+def joint_space_inertia_matrix_inverse(model, q):
+    """pinocchio::computeMinverse: columns of unit generalized forces through the articulated-body algorithm (no velocity, no gravity)."""
+    zero = [0.0] * model.nv
+    cols = []
+    for j in range(model.nv):
+        e = list(zero)
+        e[j] = 1.0
+        cols.append(aba(model, q, zero, e, gravity=0.0))
+    return [[cols[j][i] for j in range(model.nv)] for i in range(model.nv)]
+
+
+def frames(model, q):
+    """pinocchio::framesForwardKinematics -> data.oMf for the movable bodies: {joint name: (R world<-body, p world)}."""
+    Rw, pw, _, _ = _world_kinematics(model, q)
+    return {b.name: (Rw[i], pw[i]) for i, b in enumerate(model.bodies)}
+
+
+def integrate(model, q, v, dt: float = 1.0):
+    """pinocchio::integrate(q, v dt): the base moves by its body-frame twist (SE(3) exponential), the joints by v dt.  Floats only."""
+    w = np.array(v[3:6], dtype=float) * dt
+    u = np.array(v[0:3], dtype=float) * dt
+    th = float(np.linalg.norm(w))
+    K = np.array([[0, -w[2], w[1]], [w[2], 0, -w[0]], [-w[1], w[0], 0.0]])
+    if th < 1e-9:
+        Rinc, V = np.eye(3) + K, np.eye(3) + 0.5 * K
+    else:
+        Rinc = np.eye(3) + np.sin(th) / th * K + (1 - np.cos(th)) / th ** 2 * K @ K
+        V = np.eye(3) + (1 - np.cos(th)) / th ** 2 * K + (th - np.sin(th)) / th ** 3 * K @ K
+    R = np.array(_quat_matrix(*[float(x) for x in q[3:7]]))
+    p = np.array(q[0:3], dtype=float) + R @ (V @ u)
+    Rn = R @ Rinc
+    qw = 0.5 * math.sqrt(max(1e-300, 1.0 + Rn[0, 0] + Rn[1, 1] + Rn[2, 2]))
+    quat = [(Rn[2, 1] - Rn[1, 2]) / (4 * qw), (Rn[0, 2] - Rn[2, 0]) / (4 * qw), (Rn[1, 0] - Rn[0, 1]) / (4 * qw), qw]
+    return list(p) + quat + [float(q[7 + i]) + float(v[6 + i]) * dt for i in range(model.nq - 7)]
+
+
+QUANTITIES = {  # include/ungar/rbd/quantities/*.hpp -> (function, arguments)
+    "generalized_accelerations": (aba, "qvt"), "joint_torques": (rnea, "qva"), "joint_space_inertia_matrix": (crba, "q"),
+    "joint_space_inertia_matrix_inverse": (joint_space_inertia_matrix_inverse, "q"), "generalized_gravity": (generalized_gravity, "q"),
+    "nonlinear_effects": (nonlinear_effects, "qv"), "com_position": (com_position, "q"), "com_velocity": (com_velocity, "qv"),
+    "com_acceleration": (com_acceleration, "qva"), "centroidal_momentum": (centroidal_momentum, "qv"),
+    "centroidal_momentum_matrix": (centroidal_momentum_matrix, "q"), "composite_rigid_body_inertia": (composite_rigid_body_inertia, "q"),
+    "kinetic_energy": (kinetic_energy, "qv"), "potential_energy": (potential_energy, "q"), "frames": (frames, "q"),
+}
+
+
+def _flatten(y):
+    """Quantity value -> flat list of scalars (matrices row-major; the composite inertia as [mass, I row-major]; frames as
+    [R row-major, p] per body in tree order)."""
+    if isinstance(y, dict):
+        return [x for R, p in y.values() for x in ([e for row in R for e in row] + list(p))]
+    if isinstance(y, tuple):
+        return [y[0]] + [e for row in y[1] for e in row]
+    if isinstance(y, list) and y and isinstance(y[0], list):
+        return [e for row in y for e in row]
+    return list(y) if isinstance(y, list) else [y]
+
+
+class _Evaluator:
+    """``robot.Compute(quantity).At(q, v, ...)`` (rbd/evaluator.hpp:45-58): evaluates the taped quantity on the GPU."""
+
+    def __init__(self, robot, quantity):
+        self.robot, self.quantity = robot, quantity
+
+    def At(self, *args):
+        f = self.robot.MakeFunction(self.quantity)
+        x = np.concatenate([np.asarray(a, dtype=np.float64).ravel() for a in args])
+        self.robot._results[self.quantity] = np.asarray(f(x))
+        return self
+
+
+class Robot:
+    """Mirror of ``Ungar::Robot`` (rbd/robot.hpp:40-104): ``Compute(quantity).At(q, v, ...)`` / ``Get(quantity)`` for the fifteen
+    quantities of rbd/quantities/*.hpp, each a taped Function of the stacked arguments evaluated by the register machine."""
+
+    def __init__(self, urdf: str, gravity: float = GRAVITY, device: int = 0):
         self.model = load_urdf(urdf)
-        self.gravity = gravity
+        self.gravity, self.device = gravity, device
+        self._functions, self._results = {}, {}
 
     def Model(self):
         return self.model
 
-    def MakeFunction(self, quantity: str = "generalized_accelerations", name: str | None = None, scale: float = 1.0, device: int = 0):
-        """The Autodiff::Function of test/rbd/robot.test.cpp:121-133: input [q; v; tau] (or [q; v; a] for "joint_torques"), output
-        the quantity times ``scale``; values and Jacobian are evaluated on the GPU by the register machine."""
+    def Compute(self, quantity: str) -> _Evaluator:
+        return _Evaluator(self, quantity)
+
+    def Get(self, quantity: str):
+        return self._results[quantity]
+
+    def MakeFunction(self, quantity: str = "generalized_accelerations", name: str | None = None, scale: float = 1.0):
+        """The Autodiff::Function of test/rbd/robot.test.cpp:121-133: input = the quantity's arguments stacked ([q; v; tau] for the
+        generalized accelerations), output = the flattened quantity times ``scale``; Jacobian enabled."""
+        key = (quantity, scale)
+        if key in self._functions:
+            return self._functions[key]
         m = self.model
-        algo = {"generalized_accelerations": aba, "joint_torques": rnea}[quantity]
+        algo, args = QUANTITIES[quantity]
+        sizes = [m.nq if c == "q" else m.nv for c in args]
+        takes_gravity = quantity in ("generalized_accelerations", "joint_torques", "generalized_gravity", "nonlinear_effects", "potential_energy")
 
         def impl(x):
-            q, v, w = x[:m.nq], x[m.nq:m.nq + m.nv], x[m.nq + m.nv:]
-            return [scale * y for y in algo(m, q, v, w, self.gravity)]
+            parts, off = [], 0
+            for n in sizes:
+                parts.append(x[off:off + n])
+                off += n
+            y = algo(m, *parts, self.gravity) if takes_gravity else algo(m, *parts)
+            return [scale * e for e in _flatten(y)]
 
-        bp = A.Blueprint(impl, m.nq + 2 * m.nv, 0, name or f"{m.name}_{quantity}", A.JACOBIAN)
-        # tape at a regular configuration: unit quaternion, small joint angles
-        x0 = np.zeros(m.nq + 2 * m.nv)
-        x0[6] = 1.0
-        x0[7:m.nq] = 0.1 * np.arange(1, m.nq - 6)
-        x0[m.nq:] = 0.05
-        bp.tapingPoint = x0
-        return A.MakeFunction(bp, device=device)
+        bp = A.Blueprint(impl, sum(sizes), 0, name or f"{m.name}_{quantity}", A.JACOBIAN)
+        x0 = []  # tape at a regular point: unit quaternion, distinct small joint angles, small rates
+        for c in args:
+            x0 += ([0.0] * 6 + [1.0] + [0.1 * k for k in range(1, m.nq - 6)]) if c == "q" else [0.05] * m.nv
+        bp.tapingPoint = np.array(x0)
+        f = A.MakeFunction(bp, device=self.device)
+        self._functions[key] = f
+        return f
