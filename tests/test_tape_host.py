@@ -156,3 +156,37 @@ def test_structural_analysis_of_the_reference_lambdas_matches_the_oracle(oracle,
             keep2 = (r2 < nx) & (c2 < nx) & (c2 >= r2)
             o_r, o_c, _ = oracle.hessian(mid, N, xp)
             assert set(zip(o_r.tolist(), o_c.tolist())) <= set(zip(r2[keep2].tolist(), c2[keep2].tolist()))
+
+
+@pytest.mark.parametrize("example,functions", [("quadrotor", ("quadrotor_mpc_obj", "quadrotor_mpc_eqs", "quadrotor_mpc_ineqs")),
+                                               ("rc_car", ("rc_car_mpc_obj", "rc_car_mpc_eqs", "rc_car_mpc_ineqs"))])
+def test_product_header_records_the_same_tapes_as_the_oracle_shim(example, functions, tmp_path):
+    """The UNCHANGED reference example compiled against the product's cppad/cg.hpp (tests/_ref_gpu) tapes its three lambdas through
+    the reference's own MakeFunction before it evaluates anything, so the tapes exist even without a GPU.  Node for node they equal
+    the tapes the oracle shim recorded from the same source (oracle/_ref/tapes) — the ones the golden fixtures were made from."""
+    import glob
+    import os
+    import subprocess
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = os.path.join(root, "tests", "_ref_gpu", f"example_{example}_gpu")
+    if not os.path.exists(exe) or not os.path.isdir(os.path.join(root, "oracle", "_ref", "tapes", f"{example}_N30")):
+        pytest.skip("reference example binaries / oracle tapes were not built (needs /root/reference at build time)")
+    subprocess.run([exe], capture_output=True, env=dict(os.environ, UNGAR_B200_MAX_QP_SOLVES="0"), cwd=os.path.dirname(exe))
+
+    def load(path, magic_expected):
+        raw = open(path, "rb").read()
+        magic, nn, nd, ni, _ = np.frombuffer(raw, dtype=np.int64, count=5)
+        assert int(magic) == magic_expected
+        nodes = np.frombuffer(raw, dtype=A.NODE_DTYPE, count=int(nn), offset=40)
+        deps = np.frombuffer(raw, dtype=np.int32, count=int(nd), offset=40 + int(nn) * 32)
+        return nodes, int(ni), deps
+
+    for fn in functions:
+        mine = glob.glob(os.path.join(root, "tests", "_ref_gpu", "tapes", fn, "cppad_cg", "*_lib.so"))
+        theirs = glob.glob(os.path.join(root, "oracle", "_ref", "tapes", f"{example}_N30", fn, "cppad_cg", "*_lib.so"))
+        assert mine and theirs, fn
+        a, b = load(mine[0], 0x3130505430303242), load(theirs[0], 0x32455041545F4255)
+        assert a[1] == b[1] and np.array_equal(a[2], b[2]) and a[0].size == b[0].size
+        for field in ("op", "a", "b", "c", "d", "k"):
+            assert np.array_equal(a[0][field], b[0][field]), (fn, field)
