@@ -178,3 +178,28 @@ def test_sqp_solve_full_batch_properties():
     q = ungar_b200.Model("quadrotor", 30, dtype="f32")
     with pytest.raises(_lib.UngarB200Error):
         q.sqp_solve(torch.zeros((1, q.n_xp), dtype=torch.float32, device="cuda"))
+
+
+@pytest.mark.parametrize("name,N", [("quadruped", 10), ("quadrotor", 30), ("rc_car", 30)])
+def test_sqp_solve_matches_the_committed_golden_vectors(name, N):
+    """The same comparison as test_sqp_solve_matches_reference_loop, against tests/golden/sqp_*.npz (written by
+    oracle/make_golden_sqp.py from the restated SoftSQPOptimizer::Optimize; kept current by tests/test_oracle_sqp.py)."""
+    import os
+
+    import torch
+
+    import ungar_b200
+
+    fx = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", f"sqp_{name}_N{N}.npz"))
+    m = ungar_b200.Model(name, N, dtype="f64", barrier=(float(fx["stiffness"]), float(fx["epsilon"])))
+    n = m.layout["n_dec"]
+    d_xp = torch.from_numpy(fx["xp"].copy()).cuda()
+    status, info = m.sqp_solve(d_xp, m.sqp_options(max_iterations=int(fx["iterations"]), constraint_violation_multiplier=float(fx["multiplier"])))
+    got, st, info = d_xp.cpu().numpy(), status.cpu().numpy(), info.cpu().numpy()
+    assert np.array_equal(st, fx["status"])
+    for b in range(got.shape[0]):
+        last = [a for a in fx["alphas"][b] if a >= 0][-1]
+        assert info[b, 0] == last
+        scale = np.max(np.abs(fx["final"][b, :n]))
+        assert np.max(np.abs(got[b, :n] - fx["final"][b, :n])) <= 1e-5 * scale
+        assert np.array_equal(got[b, n:], fx["xp"][b, n:])

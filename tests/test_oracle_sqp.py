@@ -112,3 +112,26 @@ def test_cpp_sqp_port_equals_the_python_restatement(oracle):
         assert np.array_equal(out[b, n:], xp[b, n:])
     with pytest.raises(RuntimeError):
         oracle.sqp_solve_port(N, xp[:, :50], 1.0, 1.0, 1.0 / N, 1)
+
+
+@pytest.mark.parametrize("name,N", [("quadruped", 10), ("quadrotor", 30), ("rc_car", 30)])
+def test_sqp_golden_vectors_are_current(oracle, name, N):
+    """tests/golden/sqp_*.npz (oracle/make_golden_sqp.py) still equal what the oracle computes; the quadruped fixture also equals
+    the C++ port.  The device loop is compared with the same files in tests/test_gpu_sqp.py."""
+    import os
+
+    from ungar_b200 import workloads as W
+
+    fx = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", f"sqp_{name}_N{N}.npz"))
+    mid = W.MODEL_IDS[name]
+    xp, iters = fx["xp"], int(fx["iterations"])
+    assert np.array_equal(xp, W.synthetic_batch(mid, N, xp.shape[0], seed=int(fx["seed"])))
+    for b in (0, xp.shape[0] - 1):
+        x, st, it, log = S.soft_sqp(oracle, mid, N, xp[b], float(fx["stiffness"]), float(fx["epsilon"]), float(fx["multiplier"]), iters)
+        assert (st, it) == tuple(fx["status"][b]) and np.allclose(x, fx["final"][b], rtol=0, atol=1e-12 * np.max(np.abs(x)))
+        assert [l["ls"].alpha for l in log] == [a for a in fx["alphas"][b] if a >= 0]
+    if name == "quadruped":
+        out, status = oracle.sqp_solve_port(N, xp, float(fx["stiffness"]), float(fx["epsilon"]), float(fx["multiplier"]), iters, threads=2)
+        n = oracle.sizes(mid, N)["n_dec"]
+        assert np.array_equal(status, fx["status"])
+        assert np.max(np.abs(out[:, :n] - fx["final"][:, :n])) <= 1e-5 * np.max(np.abs(fx["final"][:, :n]))
