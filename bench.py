@@ -397,8 +397,8 @@ def ours(args, rank: int, local_rank: int, world: int):
                    "path": "ungar_b200_sqp_solve(MEM_DEVICE): iterations x {KKT sweep, QP solve, backtracking line search}, no host round trip"}
         except Exception as exc:  # auxiliary figure: never fails the bench line
             sqp = {"error": str(exc)}
-        if sqp and "error" not in sqp and args.model == "quadruped" and not args.no_cpu_baseline:
-            sqp["cpu_baseline"] = sqp_cpu_baseline(xp_np, N, BARRIER[mid], sqp["iterations"], 1.0 / N)
+        if sqp and "error" not in sqp and not args.no_cpu_baseline:
+            sqp["cpu_baseline"] = sqp_cpu_baseline(xp_np, N, BARRIER[mid], sqp["iterations"], mult, model=mid)
     clocks = sampler.stop() if sampler else None
 
     if rank != 0:
@@ -465,7 +465,7 @@ def ours(args, rank: int, local_rank: int, world: int):
         dist.destroy_process_group()
 
 
-def sqp_cpu_baseline(xp_np, N, barrier, iterations, multiplier, seconds=8.0):
+def sqp_cpu_baseline(xp_np, N, barrier, iterations, multiplier, seconds=8.0, model=W.QUADRUPED):
     """The same soft-SQP solve on the host cores: oracle/sqp_port.cpp (stage sweep -> exact stage-wise QP -> line search), all
     threads, on a bounded sample of the bench's trajectories.  Never raises: an auxiliary figure must not fail the bench line."""
     try:
@@ -476,16 +476,16 @@ def sqp_cpu_baseline(xp_np, N, barrier, iterations, multiplier, seconds=8.0):
         pool = np.ascontiguousarray(xp_np, dtype=np.float64)
         n = min(len(pool), threads)
         t0 = time.perf_counter()
-        orc.sqp_solve_port(N, pool[:n], barrier[0], barrier[1], multiplier, iterations, threads=threads)
+        orc.sqp_solve_port(N, pool[:n], barrier[0], barrier[1], multiplier, iterations, threads=threads, model=model)
         per_round = max(time.perf_counter() - t0, 1e-6)  # one trajectory per thread
         n = int(min(len(pool), max(threads, threads * int(seconds / per_round))))
         t0 = time.perf_counter()
-        _, status = orc.sqp_solve_port(N, pool[:n], barrier[0], barrier[1], multiplier, iterations, threads=threads)
+        _, status = orc.sqp_solve_port(N, pool[:n], barrier[0], barrier[1], multiplier, iterations, threads=threads, model=model)
         dt = time.perf_counter() - t0
         done = int(status[:, 1].sum())
         return {"value": done / dt, "unit": "trajectory-iterations/s", "cores": threads, "kind": "port",
                 "sample": f"first {n} trajectories x {iterations} iterations, fp64, oracle/sqp_port.cpp (-O3 -ffast-math: stage sweep, dense "
-                          f"stage-wise Schur QP, backtracking line search) on {threads} threads ({dt:.1f} s); the reference itself hands the "
+                          f"stage-wise QP (Schur complement / Riccati), backtracking line search) on {threads} threads ({dt:.1f} s); the reference itself hands the "
                           f"QP to OSQP (ADMM), absent here"}
     except Exception as exc:
         return {"error": str(exc)}

@@ -66,6 +66,8 @@ class Oracle:
         L.oracle_qp_solve.argtypes = [ctypes.c_int, _c_dbl_p, ctypes.c_int64, ctypes.c_int64, _c_dbl_p, ctypes.c_int64, ctypes.c_int]
         L.oracle_sqp_solve.argtypes = [ctypes.c_int, _c_dbl_p, ctypes.c_int64, ctypes.c_int64, ctypes.c_double, ctypes.c_double,
                                        ctypes.c_double, ctypes.c_int, ctypes.POINTER(ctypes.c_int32), ctypes.c_int]
+        L.oracle_qp_solve_model.argtypes = [ctypes.c_int] + L.oracle_qp_solve.argtypes
+        L.oracle_sqp_solve_model.argtypes = [ctypes.c_int] + L.oracle_sqp_solve.argtypes
 
     # ------------------------------------------------------------------ sizes / layout
     def sizes(self, model: int, N: int) -> dict:
@@ -159,23 +161,23 @@ class Oracle:
         return out
 
     # ------------------------------------------------------------------ CPU port of the consumers of the record (quadruped)
-    def qp_solve_port(self, N: int, records: np.ndarray, threads: int = 1) -> np.ndarray:
-        """Stage-wise exact QP solve of quadruped block records ``[B, size]`` -> steps ``[B, n_dec]`` (sqp_port.cpp)."""
+    def qp_solve_port(self, N: int, records: np.ndarray, threads: int = 1, model: int = 2) -> np.ndarray:
+        """Stage-wise exact QP solve of block records ``[B, size]`` -> steps ``[B, n_dec]`` (sqp_port.cpp; quadruped by default)."""
         records = np.ascontiguousarray(records, dtype=np.float64)
         B = records.shape[0]
-        steps = np.zeros((B, self.sizes(2, N)["n_dec"]))
-        if self.lib.oracle_qp_solve(N, _dp(records), B, records.shape[1], _dp(steps), steps.shape[1], threads) != 0:
+        steps = np.zeros((B, self.sizes(model, N)["n_dec"]))
+        if self.lib.oracle_qp_solve_model(model, N, _dp(records), B, records.shape[1], _dp(steps), steps.shape[1], threads) != 0:
             raise RuntimeError("oracle_qp_solve failed")
         return steps
 
     def sqp_solve_port(self, N: int, xp: np.ndarray, stiffness: float, epsilon: float, multiplier: float, iterations: int,
-                       threads: int = 1):
-        """SoftSQPOptimizer::Optimize for a batch of quadruped problems on the CPU (sqp_port.cpp): returns (xp_final, status[B, 2])."""
+                       threads: int = 1, model: int = 2):
+        """SoftSQPOptimizer::Optimize for a batch of problems on the CPU (sqp_port.cpp): returns (xp_final, status[B, 2])."""
         out = np.array(xp, dtype=np.float64, order="C")
         B = out.shape[0]
         status = np.zeros((B, 2), dtype=np.int32)
-        rc = self.lib.oracle_sqp_solve(N, _dp(out), B, out.shape[1], stiffness, epsilon, multiplier, iterations,
-                                       status.ctypes.data_as(ctypes.POINTER(ctypes.c_int32)), threads)
+        rc = self.lib.oracle_sqp_solve_model(model, N, _dp(out), B, out.shape[1], stiffness, epsilon, multiplier, iterations,
+                                             status.ctypes.data_as(ctypes.POINTER(ctypes.c_int32)), threads)
         if rc != 0:
             raise RuntimeError("oracle_sqp_solve failed")
         return out, status

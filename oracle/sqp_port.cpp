@@ -1,6 +1,6 @@
 // ORACLE — TEST INFRASTRUCTURE ONLY.  Nothing under oracle/ is part of the product path.
 //
-// CPU port of the loop that consumes the KKT block records of the quadruped problem — the timed CPU baseline of the `sqp_loop`
+// CPU port of the loop that consumes the KKT block records (quadruped: stage-wise Schur complement; quadrotor, RC car: Riccati) — the timed CPU baseline of the `sqp_loop`
 // figure of bench.py and a third implementation for the parity tests (next to oracle/sqp_reference.py and the device kernels):
 //   * oracle_qp_solve   the equality-constrained QP SoftSQPOptimizer hands to OSQP (include/ungar/optimization/soft_sqp.hpp:141-158,
 //                       :193-233), solved exactly by the stage-wise Schur complement of oracle/qp_reference.py::schur_stagewise
@@ -34,9 +34,9 @@ struct Lay {
     int g, A, C, h, cost, grad, H, HN, Hc, size;
 };
 
-Lay layout(int N) {
+Lay layout(int model, int N) {
     int v[15];
-    oracle_record_layout(QUADRUPED, N, v);
+    oracle_record_layout(model, N, v);
     return Lay{v[0], v[1], v[2], v[3], v[4], v[5], v[6], v[7], v[8], v[9]};
 }
 
@@ -222,6 +222,133 @@ void qp_schur_cpu(const double* rec, const Lay& L, int N, double delta, double* 
     }
 }
 
+// Quadrotor / RC car: the only equalities are the initial condition and the defects, and the objective couples u_k with u_{k+1}
+// (the Hc blocks).  Riccati recursion on the state augmented with the previous input — the algebra of ungar_b200/csrc/qp_riccati.cuh
+// written with plain dense loops.
+template <int PX, int PU>
+void qp_riccati_cpu(const double* rec, const Lay& L, int N, double* d) {
+    constexpr int PZ = PX + PU, PS = PX + PU, PT = PZ * (PZ + 1) / 2;
+    const int uoff = PX * (N + 1);
+    std::vector<double> Pxx(PX * PX), Pxv(PX * PU, 0.0), Pvv(PU * PU, 0.0), px(PX), pv(PU, 0.0), Y((size_t)N * PU * (PS + 1));
+    for (int i = 0; i < PX; ++i) {
+        for (int j = 0; j < PX; ++j) Pxx[i * PX + j] = rec[L.HN + (i <= j ? tri(PX, i, j) : tri(PX, j, i))];
+        px[i] = rec[L.grad + PX * N + i];
+    }
+    std::vector<double> W(PX * PZ), T(PZ * PU), M(PZ * PZ), m(PZ), wx(PX), wv(PU), Lc(PU * PU), nPxx(PX * PX), nPxv(PX * PU), nPvv(PU * PU);
+    for (int k = N - 1; k >= 0; --k) {
+        const double* A = rec + L.A + (int64_t)k * PX * PZ;
+        const double* H = rec + L.H + (int64_t)k * PT;
+        const double* g = rec + L.g + PX * (k + 1);
+        double D[PU];
+        for (int a = 0; a < PU; ++a) D[a] = k > 0 ? rec[L.Hc + PU * (k - 1) + a] : 0.0;
+        for (int i = 0; i < PX; ++i) {
+            double acc = px[i];
+            for (int r = 0; r < PX; ++r) acc -= Pxx[i * PX + r] * g[r];
+            wx[i] = acc;
+        }
+        for (int a = 0; a < PU; ++a) {
+            double acc = pv[a];
+            for (int r = 0; r < PX; ++r) acc -= Pxv[r * PU + a] * g[r];
+            wv[a] = acc;
+        }
+        for (int i = 0; i < PX; ++i)
+            for (int j = 0; j < PZ; ++j) {
+                double acc = 0.0;
+                for (int r = 0; r < PX; ++r) acc += Pxx[i * PX + r] * A[r * PZ + j];
+                W[i * PZ + j] = acc;
+            }
+        for (int i = 0; i < PZ; ++i)
+            for (int a = 0; a < PU; ++a) {
+                double acc = 0.0;
+                for (int r = 0; r < PX; ++r) acc += A[r * PZ + i] * Pxv[r * PU + a];
+                T[i * PU + a] = acc;
+            }
+        for (int i = 0; i < PZ; ++i) {
+            for (int j = 0; j < PZ; ++j) {
+                double acc = H[i <= j ? tri(PZ, i, j) : tri(PZ, j, i)];
+                for (int r = 0; r < PX; ++r) acc += A[r * PZ + i] * W[r * PZ + j];
+                if (j >= PX) acc -= T[i * PU + (j - PX)];
+                if (i >= PX) acc -= T[j * PU + (i - PX)];
+                if (i >= PX && j >= PX) acc += Pvv[(i - PX) * PU + (j - PX)];
+                M[i * PZ + j] = acc;
+            }
+            double acc = i < PX ? rec[L.grad + PX * k + i] : rec[L.grad + uoff + PU * k + (i - PX)];
+            for (int r = 0; r < PX; ++r) acc -= A[r * PZ + i] * wx[r];
+            if (i >= PX) acc += wv[i - PX];
+            m[i] = acc;
+        }
+        for (int i = 0; i < PU; ++i)  // Cholesky of M_uu
+            for (int j = 0; j <= i; ++j) {
+                double acc = M[(PX + i) * PZ + PX + j];
+                for (int r = 0; r < j; ++r) acc -= Lc[i * PU + r] * Lc[j * PU + r];
+                Lc[i * PU + j] = i == j ? std::sqrt(acc) : acc / Lc[j * PU + j];
+            }
+        double* Yk = Y.data() + (size_t)k * PU * (PS + 1);  // Y = M_uu^-1 [M_ux | D | m_u]
+        for (int c = 0; c <= PS; ++c) {
+            double y[PU];
+            for (int a = 0; a < PU; ++a) y[a] = c < PX ? M[(PX + a) * PZ + c] : c < PS ? (a == c - PX ? D[a] : 0.0) : m[PX + a];
+            for (int a = 0; a < PU; ++a) {
+                for (int r = 0; r < a; ++r) y[a] -= Lc[a * PU + r] * y[r];
+                y[a] /= Lc[a * PU + a];
+            }
+            for (int a = PU - 1; a >= 0; --a) {
+                for (int r = a + 1; r < PU; ++r) y[a] -= Lc[r * PU + a] * y[r];
+                y[a] /= Lc[a * PU + a];
+            }
+            for (int a = 0; a < PU; ++a) Yk[a * (PS + 1) + c] = y[a];
+        }
+        for (int i = 0; i < PX; ++i) {
+            for (int j = 0; j < PX; ++j) {
+                double acc = M[i * PZ + j];
+                for (int a = 0; a < PU; ++a) acc -= M[i * PZ + PX + a] * Yk[a * (PS + 1) + j];
+                nPxx[i * PX + j] = acc;
+            }
+            for (int b = 0; b < PU; ++b) {
+                double acc = 0.0;
+                for (int a = 0; a < PU; ++a) acc -= M[i * PZ + PX + a] * Yk[a * (PS + 1) + PX + b];
+                nPxv[i * PU + b] = acc;
+            }
+            double acc = m[i];
+            for (int a = 0; a < PU; ++a) acc -= M[i * PZ + PX + a] * Yk[a * (PS + 1) + PS];
+            px[i] = acc;
+        }
+        for (int a = 0; a < PU; ++a) {
+            for (int b = 0; b < PU; ++b) nPvv[a * PU + b] = -D[a] * Yk[a * (PS + 1) + PX + b];
+            pv[a] = -D[a] * Yk[a * (PS + 1) + PS];
+        }
+        Pxx = nPxx; Pxv = nPxv; Pvv = nPvv;
+    }
+    double sv[PS];  // forward rollout from s_0 = [-g_0; 0]
+    for (int i = 0; i < PS; ++i) sv[i] = i < PX ? -rec[L.g + i] : 0.0;
+    for (int k = 0; k < N; ++k) {
+        const double* A = rec + L.A + (int64_t)k * PX * PZ;
+        const double* Yk = Y.data() + (size_t)k * PU * (PS + 1);
+        double du[PU], nx[PX];
+        for (int a = 0; a < PU; ++a) {
+            double acc = -Yk[a * (PS + 1) + PS];
+            for (int c = 0; c < PS; ++c) acc -= Yk[a * (PS + 1) + c] * sv[c];
+            du[a] = acc;
+        }
+        for (int i = 0; i < PX; ++i) d[PX * k + i] = sv[i];
+        for (int a = 0; a < PU; ++a) d[uoff + PU * k + a] = du[a];
+        for (int i = 0; i < PX; ++i) {
+            double acc = -rec[L.g + PX * (k + 1) + i];
+            for (int c = 0; c < PX; ++c) acc -= A[i * PZ + c] * sv[c];
+            for (int a = 0; a < PU; ++a) acc -= A[i * PZ + PX + a] * du[a];
+            nx[i] = acc;
+        }
+        for (int i = 0; i < PX; ++i) sv[i] = nx[i];
+        for (int a = 0; a < PU; ++a) sv[PX + a] = du[a];
+    }
+    for (int i = 0; i < PX; ++i) d[PX * N + i] = sv[i];
+}
+
+void qp_cpu(int model, const double* rec, const Lay& L, int N, double* d) {
+    if (model == 0) qp_riccati_cpu<13, 4>(rec, L, N, d);
+    else if (model == 1) qp_riccati_cpu<6, 2>(rec, L, N, d);
+    else qp_schur_cpu(rec, L, N, 1e-9, d);
+}
+
 // Zsoft(h) = sum_i b(-h_i), RelaxedPolyBarrierFunction{0, stiffness, epsilon} (soft_inequality_constraint.hpp:133-145, :171-179;
 // soft_sqp.hpp:116-125), in closed form.
 double barrier_sum(const double* h, int n, double stiffness, double eps) {
@@ -237,26 +364,26 @@ double barrier_sum(const double* h, int n, double stiffness, double eps) {
 }
 
 struct Merit {
-    int N, n_dec, m_eq, m_ineq;
+    int model, N, n_dec, m_eq, m_ineq;
     double stiffness, epsilon, mult;
     std::vector<double> g, h;
-    Merit(int N_, double k, double eps, double m) : N(N_), stiffness(k), epsilon(eps), mult(m) {
+    Merit(int model_, int N_, double k, double eps, double m) : model(model_), N(N_), stiffness(k), epsilon(eps), mult(m) {
         int s[7];
-        oracle_sizes(QUADRUPED, N, s);
+        oracle_sizes(model, N, s);
         n_dec = s[3]; m_eq = s[5]; m_ineq = s[6];
         g.resize(m_eq); h.resize(m_ineq);
     }
     double objective(const double* xp) {
         double f;
-        oracle_eval(QUADRUPED, 0, N, xp, &f);
+        oracle_eval(model, 0, N, xp, &f);
         return f;
     }
     double phi(const double* xp) {  // soft_sqp.hpp:85-89
-        oracle_eval(QUADRUPED, 2, N, xp, h.data());
+        oracle_eval(model, 2, N, xp, h.data());
         return objective(xp) + barrier_sum(h.data(), m_ineq, stiffness, epsilon);
     }
     double theta(const double* xp) {  // soft_sqp.hpp:90-98
-        oracle_eval(QUADRUPED, 1, N, xp, g.data());
+        oracle_eval(model, 1, N, xp, g.data());
         double s = 0.0;
         for (double v : g) s += v * v;
         return mult * std::sqrt(s);
@@ -264,18 +391,19 @@ struct Merit {
 };
 
 // One trajectory of SoftSQPOptimizer::Optimize.  status: 0 max iterations, 1 converged, 2 line search failed.
-void sqp_one(int N, double* xp, int64_t n_xp, double stiffness, double epsilon, double mult, int iterations, const Lay& L, int32_t* status) {
-    Merit m(N, stiffness, epsilon, mult);
+void sqp_one(int model, int N, double* xp, int64_t n_xp, double stiffness, double epsilon, double mult, int iterations, const Lay& L,
+             int32_t* status) {
+    Merit m(model, N, stiffness, epsilon, mult);
     std::vector<double> rec(L.size), d(m.n_dec), trial(xp, xp + n_xp);
     status[0] = 0;
     status[1] = 0;
     for (int it = 0; it < iterations; ++it) {
         ++status[1];
         const double objective = m.objective(xp);
-        oracle_stage_sweep(QUADRUPED, N, xp, 1, n_xp, stiffness, epsilon, rec.data(), L.size, 1);
-        qp_schur_cpu(rec.data(), L, N, 1e-9, d.data());
+        oracle_stage_sweep(model, N, xp, 1, n_xp, stiffness, epsilon, rec.data(), L.size, 1);
+        qp_cpu(model, rec.data(), L, N, d.data());
         double f0, proj;
-        oracle_directional(QUADRUPED, 0, N, xp, d.data(), &f0, &proj);
+        oracle_directional(model, 0, N, xp, d.data(), &f0, &proj);
         // BacktrackingLineSearch::Do, defaults of backtracking_line_search.hpp:70-76
         const double theta = m.theta(xp), phi = m.phi(xp);
         double alpha = 1.0;
@@ -317,21 +445,32 @@ void parallel_for(int64_t n, int threads, F&& body) {
 
 }  // namespace
 
-extern "C" int oracle_qp_solve(int N, const double* records, int64_t batch, int64_t ld_rec, double* steps, int64_t ld_steps, int threads) {
-    if (N < 1 || batch < 0 || threads < 1) return -1;
-    const Lay L = layout(N);
+extern "C" int oracle_qp_solve_model(int model, int N, const double* records, int64_t batch, int64_t ld_rec, double* steps,
+                                     int64_t ld_steps, int threads) {
+    if (model < 0 || model > 2 || N < 1 || batch < 0 || threads < 1) return -1;
+    const Lay L = layout(model, N);
     if (ld_rec < L.size) return -2;
-    parallel_for(batch, threads, [&](int64_t b) { qp_schur_cpu(records + b * ld_rec, L, N, 1e-9, steps + b * ld_steps); });
+    parallel_for(batch, threads, [&](int64_t b) { qp_cpu(model, records + b * ld_rec, L, N, steps + b * ld_steps); });
+    return 0;
+}
+
+extern "C" int oracle_qp_solve(int N, const double* records, int64_t batch, int64_t ld_rec, double* steps, int64_t ld_steps, int threads) {
+    return oracle_qp_solve_model(QUADRUPED, N, records, batch, ld_rec, steps, ld_steps, threads);
+}
+
+extern "C" int oracle_sqp_solve_model(int model, int N, double* xp, int64_t batch, int64_t ld_xp, double stiffness, double epsilon,
+                                      double multiplier, int iterations, int32_t* status, int threads) {
+    if (model < 0 || model > 2 || N < 1 || batch < 0 || threads < 1 || iterations < 0) return -1;
+    int sizes[7];
+    oracle_sizes(model, N, sizes);
+    if (ld_xp < sizes[3] + sizes[4]) return -2;  // rows shorter than [X | U | parameters]
+    const Lay L = layout(model, N);
+    parallel_for(batch, threads,
+                 [&](int64_t b) { sqp_one(model, N, xp + b * ld_xp, ld_xp, stiffness, epsilon, multiplier, iterations, L, status + 2 * b); });
     return 0;
 }
 
 extern "C" int oracle_sqp_solve(int N, double* xp, int64_t batch, int64_t ld_xp, double stiffness, double epsilon, double multiplier,
                                 int iterations, int32_t* status, int threads) {
-    if (N < 1 || batch < 0 || threads < 1 || iterations < 0) return -1;
-    int sizes[7];
-    oracle_sizes(QUADRUPED, N, sizes);
-    if (ld_xp < sizes[3] + sizes[4]) return -2;  // rows shorter than [X | U | parameters]
-    const Lay L = layout(N);
-    parallel_for(batch, threads, [&](int64_t b) { sqp_one(N, xp + b * ld_xp, ld_xp, stiffness, epsilon, multiplier, iterations, L, status + 2 * b); });
-    return 0;
+    return oracle_sqp_solve_model(QUADRUPED, N, xp, batch, ld_xp, stiffness, epsilon, multiplier, iterations, status, threads);
 }

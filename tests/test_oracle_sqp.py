@@ -116,7 +116,7 @@ def test_cpp_sqp_port_equals_the_python_restatement(oracle):
 
 @pytest.mark.parametrize("name,N", [("quadruped", 10), ("quadrotor", 30), ("rc_car", 30)])
 def test_sqp_golden_vectors_are_current(oracle, name, N):
-    """tests/golden/sqp_*.npz (oracle/make_golden_sqp.py) still equal what the oracle computes; the quadruped fixture also equals
+    """tests/golden/sqp_*.npz (oracle/make_golden_sqp.py) still equal what the oracle computes; the fixtures also equal
     the C++ port.  The device loop is compared with the same files in tests/test_gpu_sqp.py."""
     import os
 
@@ -130,8 +130,25 @@ def test_sqp_golden_vectors_are_current(oracle, name, N):
         x, st, it, log = S.soft_sqp(oracle, mid, N, xp[b], float(fx["stiffness"]), float(fx["epsilon"]), float(fx["multiplier"]), iters)
         assert (st, it) == tuple(fx["status"][b]) and np.allclose(x, fx["final"][b], rtol=0, atol=1e-12 * np.max(np.abs(x)))
         assert [l["ls"].alpha for l in log] == [a for a in fx["alphas"][b] if a >= 0]
-    if name == "quadruped":
-        out, status = oracle.sqp_solve_port(N, xp, float(fx["stiffness"]), float(fx["epsilon"]), float(fx["multiplier"]), iters, threads=2)
-        n = oracle.sizes(mid, N)["n_dec"]
-        assert np.array_equal(status, fx["status"])
-        assert np.max(np.abs(out[:, :n] - fx["final"][:, :n])) <= 1e-5 * np.max(np.abs(fx["final"][:, :n]))
+    # the C++ port (Schur complement for the quadruped, Riccati for the other two) reaches the same statuses and iterates
+    out, status = oracle.sqp_solve_port(N, xp, float(fx["stiffness"]), float(fx["epsilon"]), float(fx["multiplier"]), iters, threads=2,
+                                        model=mid)
+    n = oracle.sizes(mid, N)["n_dec"]
+    assert np.array_equal(status, fx["status"])
+    assert np.max(np.abs(out[:, :n] - fx["final"][:, :n])) <= 1e-5 * np.max(np.abs(fx["final"][:, :n]))
+
+
+@pytest.mark.parametrize("model,N", [(0, 30), (0, 7), (1, 60), (1, 2)])
+def test_cpp_riccati_port_equals_the_monolithic_kkt_solve(oracle, model, N):
+    """Quadrotor / RC car: the Riccati port (input-rate coupling in the augmented state) against the QP assembled as
+    AssembleOSQPInstance does and solved by one sparse LU."""
+    from ungar_b200 import EXAMPLE_BARRIER
+    from ungar_b200 import workloads as W
+
+    k, eps = EXAMPLE_BARRIER[model]
+    xp = W.synthetic_batch(model, N, 3, seed=43)
+    steps = oracle.qp_solve_port(N, oracle.stage_sweep(model, N, xp, k, eps), threads=2, model=model)
+    for b in range(3):
+        P, q, A, g, _ = S.monolithic_qp(oracle, model, N, xp[b], k, eps)
+        d_ref, _ = S.solve_qp(P, q, A, g, delta=0.0)
+        assert np.max(np.abs(steps[b] - d_ref)) <= 1e-8 * np.max(np.abs(d_ref))
