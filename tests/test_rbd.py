@@ -1,8 +1,8 @@
 """Rigid-body dynamics behind the generic path (ungar_b200/rbd.py) against the independent numpy oracle
 (oracle/rbd_reference.py: CRBA + RNEA, 6x6 spatial matrices) and physical identities.  The reference pins this layer only against
 Pinocchio (test/rbd/robot.test.cpp:109-162), which is absent: parity with Pinocchio is UNPINNED; these tests pin the algorithm that
-gets taped for the GPU.  The GPU evaluation itself (the taped function on the register machine) has not been run on hardware yet:
-its test is opt-in (UNGAR_B200_RUN_UNVALIDATED=1)."""
+gets taped for the GPU.  The GPU evaluation of the taped function (register machine) ran green on a B200 in round 2 and is a regular
+gpu-marked test now; the hand-written batched ABA kernel has its own parity tests in tests/test_gpu_rbd.py."""
 import os
 
 import numpy as np
@@ -90,8 +90,6 @@ def test_forward_dynamics_is_taped_for_the_generic_path():
 
 
 @pytest.mark.gpu
-@pytest.mark.skipif(os.environ.get("UNGAR_B200_RUN_UNVALIDATED") != "1",
-                    reason="written after the round's GPU budget was spent: never run on hardware yet (set UNGAR_B200_RUN_UNVALIDATED=1)")
 def test_taped_forward_dynamics_on_the_gpu_matches_the_oracle():
     from oracle import rbd_reference as R
 
