@@ -34,7 +34,7 @@
 extern "C" {
 #endif
 
-#define UNGAR_B200_ABI_VERSION 1
+#define UNGAR_B200_ABI_VERSION 2
 
 typedef struct ungar_b200_model ungar_b200_model;
 
@@ -64,6 +64,15 @@ enum ungar_b200_function {
 
 enum ungar_b200_mem { UNGAR_B200_MEM_DEVICE = 0, UNGAR_B200_MEM_HOST = 1 };
 
+/* Format of the per-trajectory KKT block record (ungar_b200_kkt_layout below).
+ *   DENSE    every block dense, as SURVEY.md §8d counts them (A_k 13x37, H_k packed 37x37, C_k 4x4x20 ...): ~65 % of the bytes are
+ *            structural zeros for the quadruped.
+ *   COMPACT  only the structurally non-zero slots (quadruped.example.cpp:162-200, :216-244, :269-303), one contiguous 16-byte aligned
+ *            chunk per shooting node: 2.5x fewer bytes to write, to read back in the QP solve and to copy to the host.  Quadruped
+ *            only (UNGAR_B200_EUNSUPPORTED otherwise).  ungar_b200_kkt_compact_map gives, for every compact slot, its offset in the
+ *            dense record, so dense-from-compact is one scatter.  Records passed in must be 16-byte aligned with an even stride. */
+enum ungar_b200_record_format { UNGAR_B200_RECORD_DENSE = 0, UNGAR_B200_RECORD_COMPACT = 1 };
+
 typedef struct ungar_b200_model_desc {
     int32_t kind;    /* ungar_b200_model_kind */
     int32_t horizon; /* N; the reference hard-codes 30 (quadrotor.example.cpp:52) */
@@ -73,6 +82,8 @@ typedef struct ungar_b200_model_desc {
      * per example: quadrotor (100, 2e-5), rc_car (100, 1e-2), quadruped (1, 1). */
     double barrier_stiffness;
     double barrier_epsilon;
+    int32_t record_format; /* ungar_b200_record_format: the format of every `records` argument of this handle */
+    int32_t reserved;      /* 0 */
 } ungar_b200_model_desc;
 
 /* Replaces FunctionFactory::Make / MakeFunction (function.hpp:589-613): where the reference tapes,
@@ -125,11 +136,24 @@ int ungar_b200_sparse_hessian(ungar_b200_model* model, int32_t function, const v
  *   HN   [nx(nx+1)/2]           the same for the terminal state x_N
  *   Hc   [N-1][nu]              diagonal of the u_{k}-u_{k+1} coupling block (quadrotor, rc_car) */
 typedef struct ungar_b200_kkt_layout {
-    int64_t g, A, C, h, cost, grad, H, HN, Hc, size;
+    int64_t g, A, C, h, cost, grad, H, HN, Hc, size; /* block offsets of the DENSE arrangement; `size` = record length in the handle's format */
     int64_t nx, nu, nz, horizon, n_dec, n_par, m_eq, m_ineq, tri, tri_terminal, legs, hc_per_node;
+    /* round 2 (ABI 2) */
+    int64_t compact;    /* 1 if the handle's records are COMPACT */
+    int64_t dense_size; /* length of the dense arrangement (= size for DENSE handles) */
+    /* COMPACT records: chunk k starts at k * node_stride; offsets inside a chunk; `tail` after the N chunks (csrc/compact.cuh):
+     *   Cs [legs][4][8]  contact rows wrt (p_c, q, r_leg) of node k        Cp [legs][3][8]  rows 1..3 wrt the same columns of node k-1
+     *   g  [29] defects | contact values     q [37] QP vector of [x_k; u_k]     Hd [13] state diagonal    Hb [8][6] 3x3 input blocks
+     *   h  [12]                              AQ [7][32] q+ / w+ rows wrt (q, w, u)                  AP [6][6] p+ / v+ rows
+     *   tail: g0 [13] (x_0 - x_measured) | qN [13] | HN diagonal [13] | cost [2]   (at tail + t_*) */
+    int64_t node_stride, c_Cs, c_Cp, c_g, c_q, c_Hd, c_Hb, c_h, c_AQ, c_AP, tail, t_g0, t_qN, t_HN, t_cost;
 } ungar_b200_kkt_layout;
 
 int ungar_b200_kkt_layout_get(const ungar_b200_model* model, ungar_b200_kkt_layout* out);
+
+/* COMPACT handles: map[e] = offset in the dense arrangement of compact slot e (e < layout.size), or -2 for a pad slot (always 0).
+ * The array belongs to the handle.  UNGAR_B200_EUNSUPPORTED for DENSE handles. */
+int ungar_b200_kkt_compact_map(const ungar_b200_model* model, const int32_t** map, int64_t* count);
 
 /* Replaces one pass of SoftSQPOptimizer::AssembleOSQPInstance (soft_sqp.hpp:141-158, :236-264): every
  * value, Jacobian block and Gauss-Newton Hessian block of every shooting node of every trajectory, in one

@@ -140,3 +140,70 @@ def schur_stagewise(rec: np.ndarray, L: dict, delta: float = DELTA):
         if j < N:
             d[NX * (N + 1) + NU * j:NX * (N + 1) + NU * j + NU] = dw[NX:]
     return d, to_reference_rows(np.concatenate(nu), N), dict(D=D, E=E, r=r)
+
+
+def schur_twisted(rec: np.ndarray, L: dict, delta: float = DELTA, middle: int | None = None):
+    """The round-2 CUDA kernel's algorithm: the same block-tridiagonal Schur complement, eliminated from BOTH ends at once
+    (a "twisted" block Cholesky).  Groups 0 .. m-1 are eliminated top-down, groups N .. m+1 bottom-up — two independent
+    dependent chains of half the length (one warp each on the device) — and meet at group m; the substitutions then run
+    outward from m in both directions.  Exact; only the elimination order differs from `schur_stagewise`."""
+    N = L["horizon"]
+    m = N // 2 if middle is None else middle
+    H, q, U, V, b = stage_blocks(rec, L)
+    Pinv = [np.linalg.inv(h) for h in H]
+    t = [Pinv[j] @ q[j] for j in range(N + 1)]
+    D, r = [], []
+    for j in range(N + 1):
+        Sjj = U[j] @ Pinv[j] @ U[j].T + delta * np.eye(U[j].shape[0])
+        rj = b[j] + U[j] @ t[j]
+        if j > 0:
+            Sjj += V[j - 1] @ Pinv[j - 1] @ V[j - 1].T
+            rj += V[j - 1] @ t[j - 1]
+        D.append(Sjj)
+        r.append(-rj)
+    E = [V[j] @ Pinv[j] @ U[j].T for j in range(N)]  # E[j] = S_{j+1, j}
+    Ld, y = [None] * (N + 1), [None] * (N + 1)
+    Lo = [None] * (N + 1)  # Lo[j] = S_{j, j-1} L_{j-1}^-T   (top chain, j = 1 .. m)
+    Uo = [None] * (N + 1)  # Uo[j] = S_{j, j+1} M_{j+1}^-T   (bottom chain, j = m .. N-1)
+    for j in range(m):  # top-down
+        S = D[j].copy()
+        rhs = r[j].copy()
+        if j > 0:
+            S -= Lo[j] @ Lo[j].T
+            rhs -= Lo[j] @ y[j - 1]
+        Ld[j] = np.linalg.cholesky(S)
+        y[j] = np.linalg.solve(Ld[j], rhs)
+        Lo[j + 1] = np.linalg.solve(Ld[j], E[j].T).T
+    for j in range(N, m, -1):  # bottom-up
+        S = D[j].copy()
+        rhs = r[j].copy()
+        if j < N:
+            S -= Uo[j] @ Uo[j].T
+            rhs -= Uo[j] @ y[j + 1]
+        Ld[j] = np.linalg.cholesky(S)
+        y[j] = np.linalg.solve(Ld[j], rhs)
+        Uo[j - 1] = np.linalg.solve(Ld[j], E[j - 1]).T  # S_{j-1, j} M_j^-T = E[j-1]^T M_j^-T
+    S = D[m].copy()
+    rhs = r[m].copy()
+    if m > 0:
+        S -= Lo[m] @ Lo[m].T
+        rhs -= Lo[m] @ y[m - 1]
+    if m < N:
+        S -= Uo[m] @ Uo[m].T
+        rhs -= Uo[m] @ y[m + 1]
+    Ld[m] = np.linalg.cholesky(S)
+    y[m] = np.linalg.solve(Ld[m], rhs)
+    nu = [None] * (N + 1)
+    nu[m] = np.linalg.solve(Ld[m].T, y[m])
+    for j in range(m - 1, -1, -1):
+        nu[j] = np.linalg.solve(Ld[j].T, y[j] - Lo[j + 1].T @ nu[j + 1])
+    for j in range(m + 1, N + 1):
+        nu[j] = np.linalg.solve(Ld[j].T, y[j] - Uo[j - 1].T @ nu[j - 1])
+    d = np.zeros(L["n_dec"])
+    for j in range(N + 1):
+        v = q[j] + U[j].T @ nu[j] + (V[j].T @ nu[j + 1] if j < N else 0.0)
+        dw = -Pinv[j] @ v
+        d[NX * j:NX * j + NX] = dw[:NX]
+        if j < N:
+            d[NX * (N + 1) + NU * j:NX * (N + 1) + NU * j + NU] = dw[NX:]
+    return d, to_reference_rows(np.concatenate(nu), N)

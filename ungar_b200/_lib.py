@@ -13,6 +13,8 @@ OK, EINVAL, ECUDA, ENOMEM, EUNSUPPORTED = 0, 1, 2, 3, 4
 F32, F64 = 0, 1
 OBJECTIVE, EQUALITIES, INEQUALITIES, SOFT_INEQUALITIES = 0, 1, 2, 3
 MEM_DEVICE, MEM_HOST = 0, 1
+RECORD_DENSE, RECORD_COMPACT = 0, 1
+EXPECTED_ABI = 2  # include/ungar_b200.h UNGAR_B200_ABI_VERSION the signatures below were written for
 SUMMARY_SIZE = 32
 LINE_SEARCH_INFO_SIZE = 8
 SQP_RUNNING, SQP_CONVERGED, SQP_LINE_SEARCH_FAILED = 0, 1, 2
@@ -28,18 +30,19 @@ SYMBOLS = [
     "ungar_b200_tape_create", "ungar_b200_tape_destroy", "ungar_b200_tape_info", "ungar_b200_tape_jacobian_pattern",
     "ungar_b200_tape_hessian_pattern", "ungar_b200_tape_set_jacobian_elements", "ungar_b200_tape_set_hessian_elements",
     "ungar_b200_tape_forward_zero", "ungar_b200_tape_sparse_jacobian", "ungar_b200_tape_sparse_hessian", "ungar_b200_kkt_solve_csc",
-    "ungar_b200_jacobian_blocks",
+    "ungar_b200_jacobian_blocks", "ungar_b200_kkt_compact_map",
 ]
 
 
 class ModelDesc(ctypes.Structure):
     _fields_ = [("kind", c_i32), ("horizon", c_i32), ("dtype", c_i32), ("device", c_i32),
-                ("barrier_stiffness", c_f64), ("barrier_epsilon", c_f64)]
+                ("barrier_stiffness", c_f64), ("barrier_epsilon", c_f64), ("record_format", c_i32), ("reserved", c_i32)]
 
 
 class KktLayout(ctypes.Structure):
     _names = ["g", "A", "C", "h", "cost", "grad", "H", "HN", "Hc", "size", "nx", "nu", "nz", "horizon", "n_dec",
-              "n_par", "m_eq", "m_ineq", "tri", "tri_terminal", "legs", "hc_per_node"]
+              "n_par", "m_eq", "m_ineq", "tri", "tri_terminal", "legs", "hc_per_node", "compact", "dense_size", "node_stride",
+              "c_Cs", "c_Cp", "c_g", "c_q", "c_Hd", "c_Hb", "c_h", "c_AQ", "c_AP", "tail", "t_g0", "t_qN", "t_HN", "t_cost"]
     _fields_ = [(n, c_i64) for n in _names]
 
     def as_dict(self) -> dict:
@@ -73,7 +76,19 @@ def load() -> ctypes.CDLL:
         except Exception as exc:  # no nvcc on the box: use the prebuilt library if there is one
             if not os.path.exists(path):
                 raise RuntimeError(f"ungar_b200: CUDA library missing and cannot be built: {exc}") from exc
+            import warnings
+
+            warnings.warn(f"ungar_b200: the CUDA library is older than its sources and the rebuild failed ({exc}); "
+                          f"binding the stale library (its ABI version is checked below)")
     L = ctypes.CDLL(path)
+    missing = [name for name in SYMBOLS if not hasattr(L, name)]
+    if missing:
+        raise RuntimeError(f"ungar_b200: {path} does not export {missing}: stale build, run `python -m ungar_b200.build --force`")
+    L.ungar_b200_abi_version.restype = c_i32
+    abi = int(L.ungar_b200_abi_version())
+    if abi != EXPECTED_ABI:
+        raise RuntimeError(f"ungar_b200: {path} implements ABI {abi}, these bindings were written for ABI {EXPECTED_ABI}: "
+                           f"stale build, run `python -m ungar_b200.build --force`")
     L.ungar_b200_model_create.argtypes = [ctypes.POINTER(ModelDesc), ctypes.POINTER(c_vp)]
     L.ungar_b200_model_destroy.argtypes = [c_vp]
     L.ungar_b200_function_info.argtypes = [c_vp, c_i32, c_i64_p, c_i64_p, c_i64_p, c_i64_p, c_i64_p]
@@ -82,6 +97,7 @@ def load() -> ctypes.CDLL:
     for name in ("ungar_b200_forward_zero", "ungar_b200_sparse_jacobian", "ungar_b200_sparse_hessian"):
         getattr(L, name).argtypes = [c_vp, c_i32, c_vp, c_i64, c_i64, c_vp, c_i64, c_i32, c_vp]
     L.ungar_b200_kkt_layout_get.argtypes = [c_vp, ctypes.POINTER(KktLayout)]
+    L.ungar_b200_kkt_compact_map.argtypes = [c_vp, ctypes.POINTER(ctypes.POINTER(c_i32)), c_i64_p]
     L.ungar_b200_kkt_blocks.argtypes = [c_vp, c_vp, c_i64, c_i64, c_vp, c_i64, c_i32, c_vp]
     L.ungar_b200_jacobian_blocks.argtypes = [c_vp, c_vp, c_i64, c_i64, c_vp, c_i64, c_i32, c_vp]
     L.ungar_b200_summaries.argtypes = [c_vp, c_vp, c_i64, c_i64, c_vp, c_i64, c_vp, c_vp]

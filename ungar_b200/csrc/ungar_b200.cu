@@ -18,6 +18,7 @@
 #include "sweep_tpn.cuh"
 #include "sweep_small.cuh"
 #include "qp_schur.cuh"
+#include "qp_twisted.cuh"
 #include "qp_riccati.cuh"
 #include "line_search.cuh"
 
@@ -106,8 +107,13 @@ struct ungar_b200_model {
     ub::RecLayout rl{};
     ub::BarrierCoef<double> bar{};
     FunctionTables fn[4];
-    DeviceBuffer stage_cost, ws_records, ws_xp, ws_out, ws_qp, ws_steps, ws_status, ws_info, sched;
+    DeviceBuffer stage_cost, ws_records, ws_xp, ws_out, ws_qp, ws_steps, ws_status, ws_info, sched, ws_compact, ws_dense;
     size_t elem = 8;
+    // compact record (quadruped): compact slot -> dense offset (or -2: pad), host copy for the ABI and device copy for the gather
+    bool compact = false;
+    std::vector<int32_t> c2d;
+    int32_t* d_c2d = nullptr;
+    int64_t dense_size = 0, rec_size = 0;  // rec_size: length of a record in the handle's format
     // host-buffer pipeline of ungar_b200_kkt_step: H2D of chunk c + 1 on `copy_stream` overlaps the sweep of chunk c
     static constexpr int kChunks = 4;
     cudaStream_t copy_stream = nullptr;
@@ -140,6 +146,11 @@ void make_layout(int N, ungar_b200_kkt_layout& L) {
     L.HN = off;   off = round4(off + L.tri_terminal);
     L.Hc = off;   off = round4(off + (N - 1) * L.hc_per_node);
     L.size = off;
+    L.dense_size = off;
+    L.compact = 0;
+    using K = ub::Compact;
+    L.node_stride = K::NODE; L.c_Cs = K::oCs; L.c_Cp = K::oCp; L.c_g = K::oG; L.c_q = K::oQ; L.c_Hd = K::oHd; L.c_Hb = K::oHb; L.c_h = K::oHi;
+    L.c_AQ = K::oAQ; L.c_AP = K::oAP; L.tail = K::tail(N); L.t_g0 = K::tG0; L.t_qN = K::tQN; L.t_HN = K::tHN; L.t_cost = K::tCost;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -599,20 +610,46 @@ int launch_barrier_t(ungar_b200_model& mdl, const void* z, int64_t ld_z, void* o
 }
 
 // QP solve launches.  `skip_status` (may be null): trajectories whose status is not RUNNING are skipped.
-// Quadruped: stage-wise Schur complement (qp_schur.cuh; the contact rows are extra equalities).
-int launch_qp_schur(ungar_b200_model& mdl, const void* rec, int64_t batch, int64_t ld_rec, void* steps, int64_t ld_steps, void* mult,
-                    int64_t ld_mult, const int32_t* skip_status, cudaStream_t stream) {
-    using Q = ub::QpShape;
+// Quadruped: twisted stage-wise Schur complement on the COMPACT record (qp_twisted.cuh; the contact rows are extra equalities).
+// `rec_is_compact` false: the caller's records are dense -> one gather pass into the handle's compact workspace first.
+int ensure_c2d(ungar_b200_model& mdl) {
+    if (mdl.d_c2d) return UNGAR_B200_OK;
+    if (mdl.c2d.empty()) {
+        const ungar_b200_kkt_layout& L = mdl.layout;
+        mdl.c2d = ub::compact_to_dense_map(mdl.N, ub::DenseOffsets{L.g, L.A, L.C, L.h, L.cost, L.grad, L.H, L.HN});
+    }
+    UB_CUDA(cudaMalloc(reinterpret_cast<void**>(&mdl.d_c2d), mdl.c2d.size() * sizeof(int32_t)));
+    UB_CUDA(cudaMemcpy(mdl.d_c2d, mdl.c2d.data(), mdl.c2d.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
+    return UNGAR_B200_OK;
+}
+
+int launch_qp_twisted(ungar_b200_model& mdl, const void* rec, bool rec_is_compact, int64_t batch, int64_t ld_rec, void* steps, int64_t ld_steps,
+                      void* mult, int64_t ld_mult, const int32_t* skip_status, cudaStream_t stream) {
+    using Q = ub::QpT;
+    const int64_t csize = ub::Compact::size(mdl.N);
+    if (!rec_is_compact) {
+        if (int rc = ensure_c2d(mdl)) return rc;
+        if (int rc = mdl.ws_compact.reserve(size_t(batch) * csize * sizeof(double))) return rc;
+        for (int64_t b0 = 0; b0 < batch; b0 += 65535) {  // gather grid: blockIdx.y = trajectory
+            const int64_t nb = std::min<int64_t>(65535, batch - b0);
+            if (int rc = launch_gather_t<double>(static_cast<const double*>(rec) + b0 * ld_rec, ld_rec, mdl.d_c2d, csize,
+                                                 static_cast<double*>(mdl.ws_compact.ptr) + b0 * csize, csize, nb, stream)) return rc;
+        }
+        rec = mdl.ws_compact.ptr;
+        ld_rec = csize;
+    } else if ((reinterpret_cast<uintptr_t>(rec) & 15) != 0 || (ld_rec & 1) != 0) {
+        return fail(UNGAR_B200_EINVAL, "compact records must be 16-byte aligned with an even stride (TMA bulk loads)");
+    }
     if (int rc = mdl.ws_qp.reserve(size_t(batch) * (mdl.N + 1) * Q::WS_GROUP * sizeof(double))) return rc;
     static PerDevice configured;
     if (!configured[mdl.desc.device]) {
-        UB_CUDA(cudaFuncSetAttribute(ub::qp_schur_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, Q::SMEM_BYTES));
+        UB_CUDA(cudaFuncSetAttribute(ub::qp_twisted_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, Q::SMEM_BYTES));
         configured[mdl.desc.device] = 1;
     }
-    const unsigned grid = unsigned((batch + Q::WARPS - 1) / Q::WARPS);
-    ub::qp_schur_kernel<<<grid, Q::WARPS * 32, Q::SMEM_BYTES, stream>>>(
+    if (batch > 2147483647LL) return fail(UNGAR_B200_EINVAL, "batch too large for one launch");
+    ub::qp_twisted_kernel<<<unsigned(batch), 64, Q::SMEM_BYTES, stream>>>(
         static_cast<const double*>(rec), ld_rec, static_cast<double*>(mdl.ws_qp.ptr), static_cast<double*>(steps), ld_steps,
-        static_cast<double*>(mult), ld_mult, mdl.N, batch, mdl.rl, 1e-9, skip_status);
+        static_cast<double*>(mult), ld_mult, mdl.N, batch, 1e-9, skip_status);
     ++g_launches;
     UB_CUDA(cudaGetLastError());
     return UNGAR_B200_OK;
@@ -639,12 +676,12 @@ int launch_qp_riccati(ungar_b200_model& mdl, const void* rec, int64_t batch, int
     return UNGAR_B200_OK;
 }
 
-int launch_qp(ungar_b200_model& mdl, const void* rec, int64_t batch, int64_t ld_rec, void* steps, int64_t ld_steps, void* mult,
+int launch_qp(ungar_b200_model& mdl, const void* rec, bool rec_is_compact, int64_t batch, int64_t ld_rec, void* steps, int64_t ld_steps, void* mult,
               int64_t ld_mult, const int32_t* skip_status, cudaStream_t stream) {
     switch (mdl.desc.kind) {
         case UNGAR_B200_QUADROTOR: return launch_qp_riccati<ub::Quadrotor>(mdl, rec, batch, ld_rec, steps, ld_steps, mult, ld_mult, skip_status, stream);
         case UNGAR_B200_RC_CAR: return launch_qp_riccati<ub::RcCar>(mdl, rec, batch, ld_rec, steps, ld_steps, mult, ld_mult, skip_status, stream);
-        case UNGAR_B200_QUADRUPED: return launch_qp_schur(mdl, rec, batch, ld_rec, steps, ld_steps, mult, ld_mult, skip_status, stream);
+        case UNGAR_B200_QUADRUPED: return launch_qp_twisted(mdl, rec, rec_is_compact, batch, ld_rec, steps, ld_steps, mult, ld_mult, skip_status, stream);
     }
     return fail(UNGAR_B200_EINVAL, "unknown model kind %d", mdl.desc.kind);
 }
@@ -757,6 +794,10 @@ int ungar_b200_model_create(const ungar_b200_model_desc* desc, ungar_b200_model*
     if (desc->horizon < 2 || desc->horizon > 4096) return fail(UNGAR_B200_EINVAL, "horizon %d out of range [2, 4096]", desc->horizon);
     if (!(desc->barrier_stiffness > 0.0) || !(desc->barrier_epsilon > 0.0))
         return fail(UNGAR_B200_EINVAL, "barrier stiffness and epsilon must be positive");
+    if (desc->record_format != UNGAR_B200_RECORD_DENSE && desc->record_format != UNGAR_B200_RECORD_COMPACT)
+        return fail(UNGAR_B200_EINVAL, "unknown record format %d", desc->record_format);
+    if (desc->record_format == UNGAR_B200_RECORD_COMPACT && (desc->kind != UNGAR_B200_QUADRUPED || desc->dtype != UNGAR_B200_F64))
+        return fail(UNGAR_B200_EUNSUPPORTED, "compact records exist for the quadruped in F64 only (the other two problems have 2-7x smaller, denser blocks)");
     int ndev = 0;
     cudaError_t e = cudaGetDeviceCount(&ndev);
     if (e != cudaSuccess || ndev == 0)
@@ -774,9 +815,18 @@ int ungar_b200_model_create(const ungar_b200_model_desc* desc, ungar_b200_model*
         case UNGAR_B200_RC_CAR: make_layout<ub::RcCar>(M->N, M->layout); build_tables<ub::RcCar>(*M); break;
         default: make_layout<ub::Quadruped>(M->N, M->layout); build_tables<ub::Quadruped>(*M); break;
     }
-    const ungar_b200_kkt_layout& L = M->layout;
+    ungar_b200_kkt_layout& L = M->layout;
     if (L.size > 2147483647LL) { delete M; return fail(UNGAR_B200_EINVAL, "record too large"); }
     M->rl = {int(L.g), int(L.A), int(L.C), int(L.h), int(L.cost), int(L.grad), int(L.H), int(L.HN), int(L.Hc), int(L.size)};
+    M->dense_size = L.dense_size;
+    M->rec_size   = L.dense_size;
+    if (desc->record_format == UNGAR_B200_RECORD_COMPACT) {
+        M->compact  = true;
+        M->rec_size = ub::Compact::size(M->N);
+        L.compact   = 1;
+        L.size      = M->rec_size;
+        M->c2d      = ub::compact_to_dense_map(M->N, ub::DenseOffsets{L.g, L.A, L.C, L.h, L.cost, L.grad, L.H, L.HN});
+    }
     {  // soft_inequality_constraint.hpp:133-145
         const double a1 = desc->barrier_stiffness, eps = desc->barrier_epsilon;
         const double b1 = -0.5 * a1 * eps;
@@ -801,6 +851,7 @@ int ungar_b200_model_destroy(ungar_b200_model* model) {
         if (f.d_jac_src) cudaFree(f.d_jac_src);
         if (f.d_hes_src) cudaFree(f.d_hes_src);
     }
+    if (model->d_c2d) cudaFree(model->d_c2d);
     if (model->copy_stream) cudaStreamDestroy(model->copy_stream);
     if (model->ev_entry) cudaEventDestroy(model->ev_entry);
     for (auto& e : model->ev_chunk)
@@ -864,6 +915,14 @@ int ungar_b200_kkt_layout_get(const ungar_b200_model* model, ungar_b200_kkt_layo
     return UNGAR_B200_OK;
 }
 
+int ungar_b200_kkt_compact_map(const ungar_b200_model* model, const int32_t** map, int64_t* count) {
+    if (!model || !map || !count) return fail(UNGAR_B200_EINVAL, "null argument");
+    if (!model->compact) return fail(UNGAR_B200_EUNSUPPORTED, "the handle's records are dense");
+    *map = model->c2d.data();
+    *count = int64_t(model->c2d.size());
+    return UNGAR_B200_OK;
+}
+
 static int blocks_call(ungar_b200_model* model, const void* xp, int64_t batch, int64_t ld_xp, void* records, int64_t ld_rec,
                        int32_t mem, void* stream_, int mode) {
     if (!model) return fail(UNGAR_B200_EINVAL, "null model");
@@ -910,7 +969,7 @@ int ungar_b200_qp_solve(ungar_b200_model* model, const void* records_device, int
         return fail(UNGAR_B200_EINVAL, "stride smaller than the row it holds");
     if (batch == 0) return UNGAR_B200_OK;
     UB_CUDA(cudaSetDevice(model->desc.device));
-    return launch_qp(*model, records_device, batch, ld_rec, steps, ld_steps, multipliers, ld_multipliers, nullptr,
+    return launch_qp(*model, records_device, model->compact, batch, ld_rec, steps, ld_steps, multipliers, ld_multipliers, nullptr,
                      static_cast<cudaStream_t>(stream_));
 }
 
@@ -972,7 +1031,7 @@ int ungar_b200_sqp_solve(ungar_b200_model* model, void* xp, int64_t batch, int64
     for (int it = 0; it < options->max_iterations; ++it) {
         // AssembleOSQPInstance -> Solve -> BacktrackingLineSearch::Do (soft_sqp.hpp:76-99), stream-ordered
         if (int rc = launch_sweep(*model, d_xp, batch, d_ld_xp, model->ws_records.ptr, L.size, MODE_KKT, nullptr, stream)) return rc;
-        if (int rc = launch_qp(*model, model->ws_records.ptr, batch, L.size, model->ws_steps.ptr, L.n_dec, nullptr, 0, d_status, stream)) return rc;
+        if (int rc = launch_qp(*model, model->ws_records.ptr, false, batch, L.size, model->ws_steps.ptr, L.n_dec, nullptr, 0, d_status, stream)) return rc;
         if (int rc = launch_line_search(*model, d_xp, batch, d_ld_xp, static_cast<const double*>(model->ws_steps.ptr), L.n_dec, *options,
                                         d_status, d_info, stream)) return rc;
     }

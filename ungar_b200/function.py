@@ -37,7 +37,7 @@ def _torch_stream() -> int:
 class Model:
     """One of the three reference NMPC problems at horizon N, backed by the sm_100a kernels."""
 
-    def __init__(self, kind, horizon: int, dtype: str = "f64", device: int = 0, barrier=(100.0, 2e-5)):
+    def __init__(self, kind, horizon: int, dtype: str = "f64", device: int = 0, barrier=(100.0, 2e-5), record_format: str = "dense"):
         self.kind = MODEL_IDS[kind] if isinstance(kind, str) else int(kind)
         self.horizon = int(horizon)
         self.dtype = {"f32": F32, "f64": F64}[dtype]
@@ -45,7 +45,8 @@ class Model:
         self.device = int(device)
         self._lib = _lib.load()
         self.barrier = (float(barrier[0]), float(barrier[1]))
-        desc = ModelDesc(self.kind, self.horizon, self.dtype, self.device, float(barrier[0]), float(barrier[1]))
+        self.record_format = {"dense": _lib.RECORD_DENSE, "compact": _lib.RECORD_COMPACT}[record_format]
+        desc = ModelDesc(self.kind, self.horizon, self.dtype, self.device, float(barrier[0]), float(barrier[1]), self.record_format, 0)
         handle = ctypes.c_void_p()
         check(self._lib.ungar_b200_model_create(ctypes.byref(desc), ctypes.byref(handle)))
         self._handle = handle
@@ -53,6 +54,8 @@ class Model:
         check(self._lib.ungar_b200_kkt_layout_get(self._handle, ctypes.byref(lay)))
         self.layout = lay.as_dict()
         self.n_xp = self.layout["n_dec"] + self.layout["n_par"]
+        self.compact = bool(self.layout["compact"])
+        self._c2d = None
         self.objective = Function(self, OBJECTIVE)
         self.equalityConstraints = Function(self, EQUALITIES)
         self.inequalityConstraints = Function(self, INEQUALITIES)
@@ -216,8 +219,31 @@ class Model:
     def launch_count(self) -> int:
         return int(self._lib.ungar_b200_launch_count())
 
+    def compact_map(self) -> np.ndarray:
+        """COMPACT handles: int32 ``map[e]`` = offset of compact slot ``e`` in the dense arrangement, -2 for pad slots."""
+        if self._c2d is None:
+            ptr, n = ctypes.POINTER(ctypes.c_int32)(), ctypes.c_int64()
+            check(self._lib.ungar_b200_kkt_compact_map(self._handle, ctypes.byref(ptr), ctypes.byref(n)))
+            self._c2d = np.ctypeslib.as_array(ptr, (int(n.value),)).copy()
+        return self._c2d
+
+    def to_dense(self, rec):
+        """Dense arrangement of COMPACT record(s) (numpy): one scatter through ``compact_map``; slots the compact record does not
+        hold are structural zeros.  DENSE handles return ``rec`` unchanged."""
+        if not self.compact:
+            return rec
+        rec = np.asarray(rec)
+        m = self.compact_map()
+        keep = m >= 0
+        out = np.zeros(rec.shape[:-1] + (self.layout["dense_size"],), dtype=rec.dtype)
+        out[..., m[keep]] = rec[..., :m.size][..., keep]
+        return out
+
     def split_record(self, rec) -> dict:
-        """Views of one record (or a batch of records) by block name, reshaped per ungar_b200_kkt_layout."""
+        """Views of one record (or a batch of records) by block name, reshaped per ungar_b200_kkt_layout (COMPACT records are
+        expanded to the dense arrangement first)."""
+        if self.compact and rec.shape[-1] != self.layout["dense_size"]:
+            rec = self.to_dense(rec)
         L = self.layout
         N, nx, nu, nz = L["horizon"], L["nx"], L["nu"], L["nz"]
         lead = rec.shape[:-1]
