@@ -13,7 +13,7 @@
 //   q  [37]  QP vector entries of [x_k; u_k]                                                                 (+1 pad)       38
 //   Hd [13]  state diagonal of H_k (+1 pad) | Hb [8 blocks][6] upper triangles of the 3 x 3 input blocks                    62
 //   h  [12]  inequality values                                                                                              12
-//   AQ [7 rows: q+ 0..3, w+ 0..2][32]  columns (q0..q3, w0..w2, u0..u23, pad)                                              224
+//   AQ [7 rows: q+ 0..3, w+ 0..2][32]  columns (q0..q3, w0..w2, pad, u0..u23): the inputs start on an even column       224
 //   AP [6 rows: p+ 0..2, v+ 0..2][6]   p+ row c: (A[c][c], A[c][7+c], f_{leg,c} x 4); v+ row c: (A[7+c][7+c], f_{leg,c} x 4, pad)  36
 // = 626 doubles (5008 B) per node.  After the N chunks: tail = g0 [13] (+1) | q_N [13] (+1) | HN diagonal [13] (+1) | cost [2].
 // Twelve AQ slots per node (d w+_c / d r_{leg,c}) are structurally zero in the reference's CppAD pattern; they are kept so that the
@@ -34,7 +34,7 @@ struct Compact {
     __host__ __device__ static constexpr long long size(int N) { return (long long)N * NODE + TAIL; }
     __host__ __device__ static constexpr long long tail(int N) { return (long long)N * NODE; }
     // AQ column of local variable z (0..36), or -1 when the column lies outside the q+/w+ pattern (p and v columns)
-    __host__ __device__ static constexpr int aq_col(int z) { return z < 3 ? -1 : z < 7 ? z - 3 : z < 10 ? -1 : z < 13 ? z - 6 : z - 6; }
+    __host__ __device__ static constexpr int aq_col(int z) { return z < 3 ? -1 : z < 7 ? z - 3 : z < 10 ? -1 : z < 13 ? z - 6 : z - 5; }
     __host__ __device__ static constexpr int aq_row(int row) { return row >= 3 && row < 7 ? row - 3 : row >= 10 ? row - 6 : -1; }
 };
 

@@ -8,18 +8,18 @@
 //
 // What changed against round 1 (2.27 ms, 0.24 of the HBM peak, 255 registers with spills, 7 warps / SM):
 //   * TWISTED elimination: groups 0 .. m-1 are eliminated top-down by warp 0, groups N .. m+1 bottom-up by warp 1 of the same
-//     64-thread CTA; the two dependent chains are half as long and run concurrently (14 warps / SM for 1024 trajectories); they
-//     meet at group m = N / 2 and the substitutions run outward from there, again one direction per warp.
+//     64-thread CTA; the two dependent chains are half as long and run concurrently (7 CTAs = 14 warps per SM: the 1024
+//     trajectories of the headline configuration are one wave); they meet at group m = N / 2 and the substitutions run outward
+//     from there, again one direction per warp.
 //   * the record is the compact one: a stage is two TMA bulk loads (2832 B + 2080 B, cp.async.bulk + mbarrier) instead of ~90
 //     8-byte cp.async with index arithmetic, and 2.6x fewer bytes.
-//   * the triangular solve of the off-diagonal block is FUSED into the Cholesky sweep of the diagonal block that produces its
-//     operand: column c of L is broadcast once through shared memory and serves both the trailing update of S and the
-//     right-looking update of the next group's coupling rows.  No L image in shared memory, no separate TRSM pass.
-//   * L leaves as packed columns with coalesced 8-byte stores straight from registers (3.9 KB per group instead of 7.2 KB).
-//   * rows are handled in two register forms, a dense 31-column "pattern" row (q, w and the 24 inputs) plus two scalars for the
-//     p / v columns, and a 12-entry sparse row for U; the register peak is the fused sweep (two 29-entry rows), so the kernel fits
-//     7 CTAs per SM without the 24 KB images of round 1.
-// Lane i < 29 owns ROW i of every 29-row block.  FP64 tensor cores (mma.sync.m8n8k4.f64) do the rank-29 update S -= Lo Lo^T.
+//   * registers: a lane owns ROW i of every 29-row block, but only ONE 29-entry row is live at a time (S during the Cholesky
+//     sweep, then the coupling row during the triangular solve); the operands V P^-1 are formed in pieces (state part + one leg
+//     at a time).  128 registers, no spills (round 1: 255 with 319 k local loads).
+//   * the Cholesky sweep keeps the columns UNSCALED in shared memory (column c = S'[:, c], pivot on top): no pivot shuffle, no
+//     per-column selects; 1 / sqrt(pivot) is folded into the scalar every update is multiplied with.  The same image serves the
+//     triangular solve of the next group's coupling rows and leaves for the workspace with one coalesced store per column.
+// FP64 tensor cores (mma.sync.m8n8k4.f64) do the rank-29 update S -= Lo Lo^T.
 #pragma once
 
 #include <cstdint>
@@ -33,16 +33,18 @@ struct QpT {
     static constexpr int G = 29, LS = 30;
     using K = Compact;
     // per-warp shared memory (doubles)
-    static constexpr int oLO = 0, oSM0 = G * LS, oSM1 = oSM0 + K::SMALL, oAB = oSM1 + K::SMALL, oY = oAB + K::APART, oCOL = oY + 32,
-                         oBAR = oCOL + 64, PER_WARP = oBAR + 4;
+    static constexpr int oLO = 0, oSM0 = G * LS, oSM1 = oSM0 + K::SMALL, oAB = oSM1 + K::SMALL, oY = oAB + K::APART, oMISC = oY + 32,
+                         oBAR = oMISC + 4, PER_WARP = oBAR + 4;
     static constexpr int SMEM_BYTES = 2 * PER_WARP * 8;
-    // per-group global workspace (doubles): packed columns of L (column c: rows c..28), 1 / L_ii, y
-    static constexpr int wsInv = 435, wsY = 464, WS_GROUP = 494;
-    // scratch vectors of the outward pass live behind the L image in the LO region
-    static constexpr int oVA = 496, oVC = 536, oNU2 = 576;
+    // factor image (shared memory during a group, global workspace afterwards): unscaled columns, 1 / sqrt(pivot), y
+    static constexpr int fRI = 450, fY = 480, WS_GROUP = 510;
+    // scratch vectors of the outward pass live behind the factor image in the LO region
+    static constexpr int oVA = 512, oVC = 552, oNU2 = 592;
     static_assert((PER_WARP * 8) % 16 == 0 && (oSM0 * 8) % 16 == 0 && (oSM1 * 8) % 16 == 0 && (oAB * 8) % 16 == 0 && (WS_GROUP * 8) % 16 == 0, "TMA alignment");
-    __host__ __device__ static constexpr int colstart(int c) { return 29 * c - (c * (c - 1)) / 2; }
+    // column c of the factor (rows c .. 28) sits at bc(c) + row: even bases, so that rows (2k, 2k+1) are one 16-byte load
+    __host__ __device__ static constexpr int bc(int c) { return 28 * c - (c * (c - 1)) / 2 + c / 2; }
 };
+static_assert(QpT::bc(28) + 28 < QpT::fRI, "factor image");
 
 // ---------------------------------------------------------------------------------------------------------------------------------
 // mbarrier + bulk-copy helpers (one barrier per buffer per warp; lane 0 arms and issues, every lane waits on the phase)
@@ -71,7 +73,8 @@ struct QtBuf {
     unsigned phase;
     __device__ __forceinline__ void load(const double* src, unsigned bytes, int lane) {
         if (lane == 0) {
-            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // the buffer was modified in place through the generic proxy
+            // the buffer was modified in place, and the factor image in the workspace was written, through the generic proxy
+            asm volatile("fence.proxy.async;" ::: "memory");
             qt_bar_expect(bar, bytes);
             qt_bulk_load(buf, src, bytes, bar);
         }
@@ -83,7 +86,7 @@ struct QtBuf {
 };
 
 // ---------------------------------------------------------------------------------------------------------------------------------
-// Stage data accessors.  `sm`: small part of a chunk (Cs, Cp, g, q -> t, Hd/Hb -> P^-1 in place); `ab`: AQ | AP of a chunk.
+// Stage data.  `sm`: small part of a chunk (Cs, Cp, g, q -> t, Hd/Hb -> P^-1 in place); `ab`: AQ | AP of a chunk.
 // ---------------------------------------------------------------------------------------------------------------------------------
 using QK = Compact;
 
@@ -115,7 +118,7 @@ __device__ __forceinline__ void qt_pinv_t(double* __restrict__ sm, int lane, boo
     __syncwarp();
 }
 
-// y = P^-1 x for a 37-vector in shared memory (lanes 0..12 the diagonal part, lanes 13..20 one 3x3 block each); in place allowed.
+// y = P^-1 x for a 37-vector in shared memory (lanes 0..12 the diagonal part, lanes 13..20 one 3x3 block each).
 __device__ __forceinline__ void qt_apply_pinv(const double* __restrict__ sm, const double* x, double* y, int lane) {
     if (lane < 13) y[lane] = sm[QK::oHd + lane] * x[lane];
     else if (lane < 21) {
@@ -129,242 +132,338 @@ __device__ __forceinline__ void qt_apply_pinv(const double* __restrict__ sm, con
     __syncwarp();
 }
 
-// Dense "pattern" row: entries at the 31 columns (q0..q3, w0..w2, u0..u23) + one entry at column p_xc + one at column v_xc.
-struct QtRow {
-    double p[31];
-    double xp, xv;
-    int xc;
-};
-// Sparse row of U: p_xc, q0..q3, v_xc, w0..w2, r0..r2 of leg `leg`.
-struct QtRowU {
-    double xp, xv, q[4], w[3], r[3];
-    int xc, leg;
+// Which row of V_j = [A_j (13 rows); Cp_{j+1} (16 rows)] / U_j = [I 0; Cs_j] a lane owns: decoded once per kernel.
+struct QtLane {
+    int qr;    // AQ row (0..6) for the q+ / w+ rows, else -1
+    int pc;    // p+ row c (0..2), else -1
+    int vc;    // v+ row c (0..2), else -1
+    int leg;   // contact lanes: leg 0..3 (else 0)
+    int rr;    // contact lanes: row 0..3 within the leg (else -1)
+    __device__ __forceinline__ explicit QtLane(int lane) {
+        qr = lane >= 3 && lane < 7 ? lane - 3 : (lane >= 10 && lane < 13 ? lane - 6 : -1);
+        pc = lane < 3 ? lane : -1;
+        vc = lane >= 7 && lane < 10 ? lane - 7 : -1;
+        const int r = lane - 13;
+        leg = lane >= 13 && lane < 29 ? r >> 2 : 0;
+        rr  = lane >= 13 && lane < 29 ? r & 3 : -1;
+    }
 };
 
-// Row `lane` of V_j = [A_j (13 rows); Cp_{j+1} (16 rows)].  `smc`: the small part that holds Cp_{j+1} (null rows when `have_cp` is false).
-__device__ __forceinline__ void qt_load_v_row(const double* __restrict__ ab, const double* __restrict__ smc, bool have_cp, int lane, QtRow& v) {
+// A row of V in pieces: the state part ...
+struct QtV0 {
+    double q[4], w[3], xp[3], xv[3];  // entries at the columns q, w, p_c, v_c
+};
+// ... and the input part of one leg.
+struct QtVL {
+    double f[3], r[3];
+};
+
+__device__ __forceinline__ void qt_load_v0(const double* __restrict__ ab, const double* __restrict__ smc, const QtLane& L, QtV0& v) {
 #pragma unroll
-    for (int k = 0; k < 31; ++k) v.p[k] = 0.0;
-    v.xp = 0.0; v.xv = 0.0; v.xc = 0;
-    const int qr = lane >= 3 && lane < 7 ? lane - 3 : (lane >= 10 && lane < 13 ? lane - 6 : -1);
-    if (qr >= 0) {
-        const double* row = ab + qr * 32;
+    for (int i = 0; i < 4; ++i) v.q[i] = 0.0;
 #pragma unroll
-        for (int k = 0; k < 30; k += 2) { const double2 t2 = qp_ld2(row + k); v.p[k] = t2.x; v.p[k + 1] = t2.y; }
-        v.p[30] = row[30];
-    } else if (lane < 13) {
-        const bool prow = lane < 3;
-        const int c = prow ? lane : lane - 7;
-        const double* ap = ab + 224 + (prow ? c : 3 + c) * 6;
-        v.xc = c;
-        v.xp = prow ? ap[0] : 0.0;
-        v.xv = prow ? ap[1] : ap[0];
+    for (int i = 0; i < 3; ++i) { v.w[i] = 0.0; v.xp[i] = 0.0; v.xv[i] = 0.0; }
+    if (L.qr >= 0) {
+        const double* row = ab + L.qr * 32;
+        const double2 a = qp_ld2(row), b = qp_ld2(row + 2), c = qp_ld2(row + 4);
+        v.q[0] = a.x; v.q[1] = a.y; v.q[2] = b.x; v.q[3] = b.y; v.w[0] = c.x; v.w[1] = c.y; v.w[2] = row[6];
+    } else if (L.pc >= 0) {
+        const double2 d = qp_ld2(ab + 224 + L.pc * 6);
 #pragma unroll
-        for (int l = 0; l < 4; ++l) {
-            const double fl = prow ? ap[2 + l] : ap[1 + l];
+        for (int i = 0; i < 3; ++i) { v.xp[i] = i == L.pc ? d.x : 0.0; v.xv[i] = i == L.pc ? d.y : 0.0; }
+    } else if (L.vc >= 0) {
+        const double d = ab[224 + (3 + L.vc) * 6];
 #pragma unroll
-            for (int m = 0; m < 3; ++m) v.p[7 + 6 * l + m] = m == c ? fl : 0.0;
-        }
-    } else if (lane < 29 && have_cp) {
-        const int r = lane - 13, leg = r >> 2, rr = r & 3;
-        if (rr > 0) {
-            const double* cp = smc + QK::oCp + (leg * 3 + rr - 1) * 8;
-            v.xc = rr - 1;
-            v.xp = cp[0];
+        for (int i = 0; i < 3; ++i) v.xv[i] = i == L.vc ? d : 0.0;
+    } else if (L.rr > 0) {
+        const double* cp = smc + QK::oCp + (L.leg * 3 + L.rr - 1) * 8;
+        const double2 a = qp_ld2(cp), b = qp_ld2(cp + 2);
+        const double c4 = cp[4];
 #pragma unroll
-            for (int i = 0; i < 4; ++i) v.p[i] = cp[1 + i];
-#pragma unroll
-            for (int l = 0; l < 4; ++l)
-#pragma unroll
-                for (int m = 0; m < 3; ++m) v.p[7 + 6 * l + 3 + m] = l == leg ? cp[5 + m] : 0.0;
-        }
+        for (int i = 0; i < 3; ++i) v.xp[i] = i == L.rr - 1 ? a.x : 0.0;
+        v.q[0] = a.y; v.q[1] = b.x; v.q[2] = b.y; v.q[3] = c4;
     }
 }
 
-// v . t  (t = P^-1 q in place of q in `sm`)
-__device__ __forceinline__ double qt_row_dot_t(const QtRow& v, const double* __restrict__ sm) {
-    const double* t = sm + QK::oQ;
-    double a0 = v.xp * t[v.xc], a1 = v.xv * t[7 + v.xc];
+template <int LEG>
+__device__ __forceinline__ void qt_load_vl(const double* __restrict__ ab, const double* __restrict__ smc, const QtLane& L, QtVL& v) {
 #pragma unroll
-    for (int i = 0; i < 4; ++i) a0 += v.p[i] * t[3 + i];
+    for (int i = 0; i < 3; ++i) { v.f[i] = 0.0; v.r[i] = 0.0; }
+    if (L.qr >= 0) {
+        const double* row = ab + L.qr * 32 + 8 + 6 * LEG;
+        const double2 a = qp_ld2(row), b = qp_ld2(row + 2), c = qp_ld2(row + 4);
+        v.f[0] = a.x; v.f[1] = a.y; v.f[2] = b.x; v.r[0] = b.y; v.r[1] = c.x; v.r[2] = c.y;
+    } else if (L.pc >= 0) {
+        const double fl = ab[224 + L.pc * 6 + 2 + LEG];
 #pragma unroll
-    for (int i = 0; i < 3; ++i) a1 += v.p[4 + i] * t[10 + i];
+        for (int i = 0; i < 3; ++i) v.f[i] = i == L.pc ? fl : 0.0;
+    } else if (L.vc >= 0) {
+        const double fl = ab[224 + (3 + L.vc) * 6 + 1 + LEG];
 #pragma unroll
-    for (int n = 0; n < 24; n += 2) { a0 += v.p[7 + n] * t[13 + n]; a1 += v.p[8 + n] * t[14 + n]; }
+        for (int i = 0; i < 3; ++i) v.f[i] = i == L.vc ? fl : 0.0;
+    } else if (L.rr > 0 && L.leg == LEG) {
+        const double* cp = smc + QK::oCp + (LEG * 3 + L.rr - 1) * 8;
+        v.r[0] = cp[5]; v.r[1] = cp[6]; v.r[2] = cp[7];
+    }
+}
+
+// piece . x  for a 37-vector x in shared memory
+__device__ __forceinline__ double qt_v0_dot(const QtV0& v, const double* __restrict__ x) {
+    double a0 = 0.0, a1 = 0.0;
+#pragma unroll
+    for (int i = 0; i < 3; ++i) { a0 += v.xp[i] * x[i]; a1 += v.xv[i] * x[7 + i]; a0 += v.w[i] * x[10 + i]; }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) a1 += v.q[i] * x[3 + i];
+    return a0 + a1;
+}
+template <int LEG>
+__device__ __forceinline__ double qt_vl_dot(const QtVL& v, const double* __restrict__ x) {
+    double a0 = 0.0, a1 = 0.0;
+#pragma unroll
+    for (int i = 0; i < 3; ++i) { a0 += v.f[i] * x[13 + 6 * LEG + i]; a1 += v.r[i] * x[16 + 6 * LEG + i]; }
     return a0 + a1;
 }
 
-// w = v P^-1 in place
-__device__ __forceinline__ void qt_row_times_pinv(QtRow& v, const double* __restrict__ sm) {
+// piece <- piece P^-1
+__device__ __forceinline__ void qt_v0_pinv(QtV0& v, const double* __restrict__ sm) {
     const double* pd = sm + QK::oHd;
-    v.xp *= pd[v.xc];
-    v.xv *= pd[7 + v.xc];
 #pragma unroll
-    for (int i = 0; i < 4; ++i) v.p[i] *= pd[3 + i];
+    for (int i = 0; i < 3; ++i) { v.xp[i] *= pd[i]; v.xv[i] *= pd[7 + i]; v.w[i] *= pd[10 + i]; }
 #pragma unroll
-    for (int i = 0; i < 3; ++i) v.p[4 + i] *= pd[10 + i];
-#pragma unroll
-    for (int b = 0; b < 8; ++b) {
-        const double* h = sm + QK::oHb + 6 * b;
-        const double2 h01 = qp_ld2(h), h23 = qp_ld2(h + 2), h45 = qp_ld2(h + 4);
-        const double x0 = v.p[7 + 3 * b], x1 = v.p[8 + 3 * b], x2 = v.p[9 + 3 * b];
-        v.p[7 + 3 * b] = x0 * h01.x + x1 * h01.y + x2 * h23.x;
-        v.p[8 + 3 * b] = x0 * h01.y + x1 * h23.y + x2 * h45.x;
-        v.p[9 + 3 * b] = x0 * h23.x + x1 * h45.x + x2 * h45.y;
-    }
+    for (int i = 0; i < 4; ++i) v.q[i] *= pd[3 + i];
+}
+__device__ __forceinline__ void qt_block3(const double* __restrict__ h, double* x) {  // x <- x B, B symmetric 3x3 given by its upper triangle
+    const double2 h01 = qp_ld2(h), h23 = qp_ld2(h + 2), h45 = qp_ld2(h + 4);
+    const double x0 = x[0], x1 = x[1], x2 = x[2];
+    x[0] = x0 * h01.x + x1 * h01.y + x2 * h23.x;
+    x[1] = x0 * h01.y + x1 * h23.y + x2 * h45.x;
+    x[2] = x0 * h23.x + x1 * h45.x + x2 * h45.y;
+}
+template <int LEG>
+__device__ __forceinline__ void qt_vl_pinv(QtVL& v, const double* __restrict__ sm) {
+    qt_block3(sm + QK::oHb + 6 * (2 * LEG), v.f);
+    qt_block3(sm + QK::oHb + 6 * (2 * LEG + 1), v.r);
 }
 
-// out[c] (+)= w . (row c of V),  c = 0 .. 28.  `smc` holds the Cp rows of V (have_cp false: they are null).
+// out[c] (+)= piece . (row c of V),  c = 0 .. 28   (state piece: sets or adds; leg pieces: add)
 template <bool ADD>
-__device__ __forceinline__ void qt_row_dot_v_rows(const QtRow& w, const double* __restrict__ ab, const double* __restrict__ smc, bool have_cp, double* out) {
+__device__ __forceinline__ void qt_v0_dot_v_rows(const QtV0& w, const double* __restrict__ ab, const double* __restrict__ smc, double* out) {
 #pragma unroll
     for (int c = 0; c < 29; ++c) {
         double acc;
         if ((c >= 3 && c < 7) || (c >= 10 && c < 13)) {
             const double* row = ab + (c < 7 ? c - 3 : c - 6) * 32;
-            double a0 = 0.0, a1 = 0.0;
-#pragma unroll
-            for (int k = 0; k < 30; k += 2) { const double2 t2 = qp_ld2(row + k); a0 += w.p[k] * t2.x; a1 += w.p[k + 1] * t2.y; }
-            acc = a0 + a1 + w.p[30] * row[30];
+            const double2 a = qp_ld2(row), b = qp_ld2(row + 2), d = qp_ld2(row + 4);
+            acc = (w.q[0] * a.x + w.q[1] * a.y) + (w.q[2] * b.x + w.q[3] * b.y) + (w.w[0] * d.x + w.w[1] * d.y) + w.w[2] * row[6];
         } else if (c < 3) {
-            const double* ap = ab + 224 + c * 6;
-            const double2 d2 = qp_ld2(ap), f01 = qp_ld2(ap + 2), f23 = qp_ld2(ap + 4);
-            acc = (w.xc == c ? w.xp * d2.x + w.xv * d2.y : 0.0) + (w.p[7 + c] * f01.x + w.p[13 + c] * f01.y) + (w.p[19 + c] * f23.x + w.p[25 + c] * f23.y);
+            const double2 d = qp_ld2(ab + 224 + c * 6);
+            acc = w.xp[c] * d.x + w.xv[c] * d.y;
         } else if (c < 10) {
-            const int cc = c - 7;
-            const double* ap = ab + 224 + (3 + cc) * 6;
-            const double2 d2 = qp_ld2(ap), f12 = qp_ld2(ap + 2);
-            acc = (w.xc == cc ? w.xv * d2.x : 0.0) + (w.p[7 + cc] * d2.y + w.p[13 + cc] * f12.x) + (w.p[19 + cc] * f12.y + w.p[25 + cc] * ap[4]);
+            acc = w.xv[c - 7] * ab[224 + (3 + c - 7) * 6];
         } else {
             const int rc = c - 13, legc = rc >> 2, rrc = rc & 3;
             if (rrc == 0) acc = 0.0;
             else {
                 const double* cp = smc + QK::oCp + (legc * 3 + rrc - 1) * 8;
-                const double2 c01 = qp_ld2(cp), c23 = qp_ld2(cp + 2), c45 = qp_ld2(cp + 4), c67 = qp_ld2(cp + 6);
-                acc = (w.xc == rrc - 1 ? w.xp * c01.x : 0.0) + (w.p[0] * c01.y + w.p[1] * c23.x) + (w.p[2] * c23.y + w.p[3] * c45.x) +
-                      (w.p[7 + 6 * legc + 3] * c45.y + w.p[7 + 6 * legc + 4] * c67.x + w.p[7 + 6 * legc + 5] * c67.y);
-                acc = have_cp ? acc : 0.0;
+                const double2 a = qp_ld2(cp), b = qp_ld2(cp + 2);
+                acc = w.xp[rrc - 1] * a.x + (w.q[0] * a.y + w.q[1] * b.x) + (w.q[2] * b.y + w.q[3] * cp[4]);
             }
         }
         if (ADD) out[c] += acc; else out[c] = acc;
     }
 }
+template <int LEG>
+__device__ __forceinline__ void qt_vl_dot_v_rows(const QtVL& w, const double* __restrict__ ab, const double* __restrict__ smc, double* out) {
+#pragma unroll
+    for (int c = 0; c < 29; ++c) {
+        if ((c >= 3 && c < 7) || (c >= 10 && c < 13)) {
+            const double* row = ab + (c < 7 ? c - 3 : c - 6) * 32 + 8 + 6 * LEG;
+            const double2 a = qp_ld2(row), b = qp_ld2(row + 2), d = qp_ld2(row + 4);
+            out[c] += (w.f[0] * a.x + w.f[1] * a.y) + (w.f[2] * b.x + w.r[0] * b.y) + (w.r[1] * d.x + w.r[2] * d.y);
+        } else if (c < 3) {
+            out[c] += w.f[c] * ab[224 + c * 6 + 2 + LEG];
+        } else if (c < 10) {
+            out[c] += w.f[c - 7] * ab[224 + (3 + c - 7) * 6 + 1 + LEG];
+        } else {
+            const int rc = c - 13, legc = rc >> 2, rrc = rc & 3;
+            if (legc == LEG && rrc > 0) {
+                const double* cp = smc + QK::oCp + (legc * 3 + rrc - 1) * 8;
+                out[c] += w.r[0] * cp[5] + w.r[1] * cp[6] + w.r[2] * cp[7];
+            }
+        }
+    }
+}
 
-// e[c] = w . (row c of U_j),  U_j = [I 0; Cs_j]
-__device__ __forceinline__ void qt_row_dot_u_rows(const QtRow& w, const double* __restrict__ sm, double* e) {
+// e[c] = piece . (row c of U_j),  U_j = [I 0; Cs_j]: the state piece sets all 29 entries, a leg piece adds to its four contact rows
+__device__ __forceinline__ void qt_v0_dot_u_rows(const QtV0& w, const double* __restrict__ sm, double* e) {
+#pragma unroll
+    for (int c = 0; c < 3; ++c) { e[c] = w.xp[c]; e[7 + c] = w.xv[c]; e[10 + c] = w.w[c]; }
+#pragma unroll
+    for (int c = 0; c < 4; ++c) e[3 + c] = w.q[c];
 #pragma unroll
     for (int c = 13; c < 29; ++c) {
         const int rc = c - 13, legc = rc >> 2, rrc = rc & 3, pcc = rrc == 0 ? 2 : rrc - 1;
         const double* cs = sm + QK::oCs + (legc * 4 + rrc) * 8;
-        const double2 c01 = qp_ld2(cs), c23 = qp_ld2(cs + 2), c45 = qp_ld2(cs + 4), c67 = qp_ld2(cs + 6);
-        e[c] = (w.xc == pcc ? w.xp * c01.x : 0.0) + (w.p[0] * c01.y + w.p[1] * c23.x) + (w.p[2] * c23.y + w.p[3] * c45.x) +
-               (w.p[7 + 6 * legc + 3] * c45.y + w.p[7 + 6 * legc + 4] * c67.x + w.p[7 + 6 * legc + 5] * c67.y);
+        const double2 a = qp_ld2(cs), b = qp_ld2(cs + 2);
+        e[c] = w.xp[pcc] * a.x + (w.q[0] * a.y + w.q[1] * b.x) + (w.q[2] * b.y + w.q[3] * cs[4]);
     }
-#pragma unroll
-    for (int c = 0; c < 3; ++c) { e[c] = w.xc == c ? w.xp : 0.0; e[7 + c] = w.xc == c ? w.xv : 0.0; e[10 + c] = w.p[4 + c]; }
-#pragma unroll
-    for (int c = 0; c < 4; ++c) e[3 + c] = w.p[c];
 }
-
-// Row `lane` of U_j in sparse form (state lanes: unit vectors; contact lanes: the Cs row; lanes >= 29: null).
-__device__ __forceinline__ void qt_load_u_row(const double* __restrict__ sm, int lane, QtRowU& u) {
-    u.xp = 0.0; u.xv = 0.0; u.xc = 0; u.leg = 0;
+template <int LEG>
+__device__ __forceinline__ void qt_vl_dot_u_rows(const QtVL& w, const double* __restrict__ sm, double* e) {
 #pragma unroll
-    for (int i = 0; i < 4; ++i) u.q[i] = 0.0;
-#pragma unroll
-    for (int i = 0; i < 3; ++i) { u.w[i] = 0.0; u.r[i] = 0.0; }
-    if (lane < 13) {
-        if (lane < 3) { u.xp = 1.0; u.xc = lane; }
-        else if (lane < 7) {
-#pragma unroll
-            for (int i = 0; i < 4; ++i) u.q[i] = lane - 3 == i ? 1.0 : 0.0;
-        } else if (lane < 10) { u.xv = 1.0; u.xc = lane - 7; }
-        else {
-#pragma unroll
-            for (int i = 0; i < 3; ++i) u.w[i] = lane - 10 == i ? 1.0 : 0.0;
-        }
-    } else if (lane < 29) {
-        const int r = lane - 13, leg = r >> 2, rr = r & 3;
-        const double* cs = sm + QK::oCs + (leg * 4 + rr) * 8;
-        u.leg = leg;
-        u.xc = rr == 0 ? 2 : rr - 1;
-        u.xp = cs[0];
-#pragma unroll
-        for (int i = 0; i < 4; ++i) u.q[i] = cs[1 + i];
-#pragma unroll
-        for (int i = 0; i < 3; ++i) u.r[i] = cs[5 + i];
+    for (int rrc = 0; rrc < 4; ++rrc) {
+        const double* cs = sm + QK::oCs + (LEG * 4 + rrc) * 8;
+        e[13 + 4 * LEG + rrc] += w.r[0] * cs[5] + w.r[1] * cs[6] + w.r[2] * cs[7];
     }
 }
 
-__device__ __forceinline__ double qt_urow_dot(const QtRowU& u, const double* __restrict__ x) {  // u . x for a 37-vector x in shared memory
-    double a = u.xp * x[u.xc] + u.xv * x[7 + u.xc];
+// Row `lane` of U_j in sparse form (state lanes: unit vectors; contact lanes: the Cs row; lanes >= 29: null).  lm = indicator of the leg.
+struct QtU {
+    double xp[3], xv[3], q[4], w[3], r[3], lm[4];
+    int leg;
+};
+__device__ __forceinline__ void qt_load_u(const double* __restrict__ sm, int lane, const QtLane& L, QtU& u) {
 #pragma unroll
-    for (int i = 0; i < 4; ++i) a += u.q[i] * x[3 + i];
+    for (int i = 0; i < 3; ++i) { u.xp[i] = lane == i ? 1.0 : 0.0; u.xv[i] = lane == 7 + i ? 1.0 : 0.0; u.w[i] = lane == 10 + i ? 1.0 : 0.0; u.r[i] = 0.0; }
 #pragma unroll
-    for (int i = 0; i < 3; ++i) a += u.w[i] * x[10 + i] + u.r[i] * x[13 + 6 * u.leg + 3 + i];
-    return a;
+    for (int i = 0; i < 4; ++i) { u.q[i] = lane == 3 + i ? 1.0 : 0.0; u.lm[i] = 0.0; }
+    u.leg = L.leg;
+    if (L.rr >= 0) {
+        const double* cs = sm + QK::oCs + (L.leg * 4 + L.rr) * 8;
+        const double2 a = qp_ld2(cs), b = qp_ld2(cs + 2), c = qp_ld2(cs + 4), d = qp_ld2(cs + 6);
+        const int pc = L.rr == 0 ? 2 : L.rr - 1;
+#pragma unroll
+        for (int i = 0; i < 3; ++i) u.xp[i] = i == pc ? a.x : 0.0;
+        u.q[0] = a.y; u.q[1] = b.x; u.q[2] = b.y; u.q[3] = c.x;
+        u.r[0] = c.y; u.r[1] = d.x; u.r[2] = d.y;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) u.lm[i] = i == L.leg ? 1.0 : 0.0;
+    }
 }
-
-__device__ __forceinline__ void qt_urow_times_pinv(QtRowU& u, const double* __restrict__ sm) {
+__device__ __forceinline__ double qt_u_dot(const QtU& u, const double* __restrict__ x) {  // u . x for a 37-vector x in shared memory
+    double a0 = 0.0, a1 = 0.0;
+    const double* xr = x + 13 + 6 * u.leg + 3;
+#pragma unroll
+    for (int i = 0; i < 3; ++i) { a0 += u.xp[i] * x[i] + u.w[i] * x[10 + i]; a1 += u.xv[i] * x[7 + i] + u.r[i] * xr[i]; }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) a0 += u.q[i] * x[3 + i];
+    return a0 + a1;
+}
+__device__ __forceinline__ void qt_u_pinv(QtU& u, const double* __restrict__ sm) {
     const double* pd = sm + QK::oHd;
-    u.xp *= pd[u.xc];
-    u.xv *= pd[7 + u.xc];
+#pragma unroll
+    for (int i = 0; i < 3; ++i) { u.xp[i] *= pd[i]; u.xv[i] *= pd[7 + i]; u.w[i] *= pd[10 + i]; }
 #pragma unroll
     for (int i = 0; i < 4; ++i) u.q[i] *= pd[3 + i];
-#pragma unroll
-    for (int i = 0; i < 3; ++i) u.w[i] *= pd[10 + i];
-    const double* h = sm + QK::oHb + 6 * (2 * u.leg + 1);
-    const double x0 = u.r[0], x1 = u.r[1], x2 = u.r[2];
-    u.r[0] = x0 * h[0] + x1 * h[1] + x2 * h[2];
-    u.r[1] = x0 * h[1] + x1 * h[3] + x2 * h[4];
-    u.r[2] = x0 * h[2] + x1 * h[4] + x2 * h[5];
+    qt_block3(sm + QK::oHb + 6 * (2 * u.leg + 1), u.r);
 }
-
 // out[c] += wu . (row c of U_j)
-__device__ __forceinline__ void qt_urow_dot_u_rows(const QtRowU& wu, const double* __restrict__ sm, double* out) {
+__device__ __forceinline__ void qt_u_dot_u_rows(const QtU& wu, const double* __restrict__ sm, double* out) {
 #pragma unroll
-    for (int c = 0; c < 3; ++c) { out[c] += wu.xc == c ? wu.xp : 0.0; out[7 + c] += wu.xc == c ? wu.xv : 0.0; out[10 + c] += wu.w[c]; }
+    for (int c = 0; c < 3; ++c) { out[c] += wu.xp[c]; out[7 + c] += wu.xv[c]; out[10 + c] += wu.w[c]; }
 #pragma unroll
     for (int c = 0; c < 4; ++c) out[3 + c] += wu.q[c];
 #pragma unroll
     for (int c = 13; c < 29; ++c) {
         const int rc = c - 13, legc = rc >> 2, rrc = rc & 3, pcc = rrc == 0 ? 2 : rrc - 1;
         const double* cs = sm + QK::oCs + (legc * 4 + rrc) * 8;
-        const double2 c01 = qp_ld2(cs), c23 = qp_ld2(cs + 2), c45 = qp_ld2(cs + 4), c67 = qp_ld2(cs + 6);
-        const double own = wu.r[0] * c45.y + wu.r[1] * c67.x + wu.r[2] * c67.y;
-        out[c] += (wu.xc == pcc ? wu.xp * c01.x : 0.0) + (wu.q[0] * c01.y + wu.q[1] * c23.x) + (wu.q[2] * c23.y + wu.q[3] * c45.x) + (wu.leg == legc ? own : 0.0);
+        const double2 a = qp_ld2(cs), b = qp_ld2(cs + 2), d = qp_ld2(cs + 4), f = qp_ld2(cs + 6);
+        const double own = wu.r[0] * d.y + wu.r[1] * f.x + wu.r[2] * f.y;
+        out[c] += wu.xp[pcc] * a.x + (wu.q[0] * a.y + wu.q[1] * b.x) + (wu.q[2] * b.y + wu.q[3] * d.x) + wu.lm[legc] * own;
+    }
+}
+// e[c] = wu . (row c of V)
+__device__ __forceinline__ void qt_u_dot_v_rows(const QtU& wu, const double* __restrict__ ab, const double* __restrict__ smc, double* e) {
+    const int ro = 8 + 6 * wu.leg + 3;
+#pragma unroll
+    for (int c = 0; c < 29; ++c) {
+        if ((c >= 3 && c < 7) || (c >= 10 && c < 13)) {
+            const double* row = ab + (c < 7 ? c - 3 : c - 6) * 32;
+            const double2 a = qp_ld2(row), b = qp_ld2(row + 2), d = qp_ld2(row + 4);
+            e[c] = (wu.q[0] * a.x + wu.q[1] * a.y) + (wu.q[2] * b.x + wu.q[3] * b.y) + (wu.w[0] * d.x + wu.w[1] * d.y) + wu.w[2] * row[6] +
+                   (wu.r[0] * row[ro] + wu.r[1] * row[ro + 1] + wu.r[2] * row[ro + 2]);
+        } else if (c < 3) {
+            const double2 d = qp_ld2(ab + 224 + c * 6);
+            e[c] = wu.xp[c] * d.x + wu.xv[c] * d.y;
+        } else if (c < 10) {
+            e[c] = wu.xv[c - 7] * ab[224 + (3 + c - 7) * 6];
+        } else {
+            const int rc = c - 13, legc = rc >> 2, rrc = rc & 3;
+            if (rrc == 0) e[c] = 0.0;
+            else {
+                const double* cp = smc + QK::oCp + (legc * 3 + rrc - 1) * 8;
+                const double2 a = qp_ld2(cp), b = qp_ld2(cp + 2), d = qp_ld2(cp + 4), f = qp_ld2(cp + 6);
+                const double own = wu.r[0] * d.y + wu.r[1] * f.x + wu.r[2] * f.y;
+                e[c] = wu.xp[rrc - 1] * a.x + (wu.q[0] * a.y + wu.q[1] * b.x) + (wu.q[2] * b.y + wu.q[3] * d.x) + wu.lm[legc] * own;
+            }
+        }
     }
 }
 
-// e[c] = wu . (row c of V)
-__device__ __forceinline__ void qt_urow_dot_v_rows(const QtRowU& wu, const double* __restrict__ ab, const double* __restrict__ smc, bool have_cp, double* e) {
-    const int ro = 7 + 6 * wu.leg + 3;
-#pragma unroll
-    for (int c = 0; c < 29; ++c) {
-        double acc;
-        if ((c >= 3 && c < 7) || (c >= 10 && c < 13)) {
-            const double* row = ab + (c < 7 ? c - 3 : c - 6) * 32;
-            const double2 r01 = qp_ld2(row), r23 = qp_ld2(row + 2), r45 = qp_ld2(row + 4);
-            acc = (wu.q[0] * r01.x + wu.q[1] * r01.y) + (wu.q[2] * r23.x + wu.q[3] * r23.y) + (wu.w[0] * r45.x + wu.w[1] * r45.y) + wu.w[2] * row[6] +
-                  (wu.r[0] * row[ro] + wu.r[1] * row[ro + 1] + wu.r[2] * row[ro + 2]);
-        } else if (c < 3) {
-            const double2 d2 = qp_ld2(ab + 224 + c * 6);
-            acc = wu.xc == c ? wu.xp * d2.x + wu.xv * d2.y : 0.0;
-        } else if (c < 10) {
-            acc = wu.xc == c - 7 ? wu.xv * ab[224 + (3 + c - 7) * 6] : 0.0;
-        } else {
-            const int rc = c - 13, legc = rc >> 2, rrc = rc & 3;
-            if (rrc == 0) acc = 0.0;
-            else {
-                const double* cp = smc + QK::oCp + (legc * 3 + rrc - 1) * 8;
-                const double2 c01 = qp_ld2(cp), c23 = qp_ld2(cp + 2), c45 = qp_ld2(cp + 4), c67 = qp_ld2(cp + 6);
-                const double own = wu.r[0] * c45.y + wu.r[1] * c67.x + wu.r[2] * c67.y;
-                acc = (wu.xc == rrc - 1 ? wu.xp * c01.x : 0.0) + (wu.q[0] * c01.y + wu.q[1] * c23.x) + (wu.q[2] * c23.y + wu.q[3] * c45.x) + (wu.leg == legc ? own : 0.0);
-                acc = have_cp ? acc : 0.0;
-            }
-        }
-        e[c] = acc;
+// S (+)= (V_j P_j^-1 V_j^T) row, formed piece by piece; returns (V_j t_j) entry of the lane.  SET: the sum starts from zero.
+template <bool SET>
+__device__ __forceinline__ double qt_vpv(const double* __restrict__ ab, const double* __restrict__ smc, const double* __restrict__ smp, const QtLane& L, double* s) {
+    double vt;
+    {
+        QtV0 v;
+        qt_load_v0(ab, smc, L, v);
+        vt = qt_v0_dot(v, smp + QK::oQ);
+        qt_v0_pinv(v, smp);
+        qt_v0_dot_v_rows<!SET>(v, ab, smc, s);
     }
+#define QT_LEG_PIECE(LEG)                                  \
+    {                                                      \
+        QtVL v;                                            \
+        qt_load_vl<LEG>(ab, smc, L, v);                    \
+        vt += qt_vl_dot<LEG>(v, smp + QK::oQ);             \
+        qt_vl_pinv<LEG>(v, smp);                           \
+        qt_vl_dot_v_rows<LEG>(v, ab, smc, s);              \
+    }
+    QT_LEG_PIECE(0) QT_LEG_PIECE(1) QT_LEG_PIECE(2) QT_LEG_PIECE(3)
+#undef QT_LEG_PIECE
+    return vt;
+}
+
+// e = (V_j P_j^-1 U_j^T) row; returns (V_j t_j) entry of the lane.
+__device__ __forceinline__ double qt_vpu(const double* __restrict__ ab, const double* __restrict__ smc, const double* __restrict__ smp, const QtLane& L, double* e) {
+    double vt;
+    {
+        QtV0 v;
+        qt_load_v0(ab, smc, L, v);
+        vt = qt_v0_dot(v, smp + QK::oQ);
+        qt_v0_pinv(v, smp);
+        qt_v0_dot_u_rows(v, smp, e);
+    }
+#define QT_LEG_PIECE(LEG)                                  \
+    {                                                      \
+        QtVL v;                                            \
+        qt_load_vl<LEG>(ab, smc, L, v);                    \
+        vt += qt_vl_dot<LEG>(v, smp + QK::oQ);             \
+        qt_vl_pinv<LEG>(v, smp);                           \
+        qt_vl_dot_u_rows<LEG>(v, smp, e);                  \
+    }
+    QT_LEG_PIECE(0) QT_LEG_PIECE(1) QT_LEG_PIECE(2) QT_LEG_PIECE(3)
+#undef QT_LEG_PIECE
+    return vt;
+}
+
+// (V_j x) entry of the lane for a 37-vector x in shared memory
+__device__ __forceinline__ double qt_v_dot(const double* __restrict__ ab, const double* __restrict__ smc, const QtLane& L, const double* __restrict__ x) {
+    double acc;
+    {
+        QtV0 v;
+        qt_load_v0(ab, smc, L, v);
+        acc = qt_v0_dot(v, x);
+    }
+#define QT_LEG_PIECE(LEG)                    \
+    {                                        \
+        QtVL v;                              \
+        qt_load_vl<LEG>(ab, smc, L, v);      \
+        acc += qt_vl_dot<LEG>(v, x);         \
+    }
+    QT_LEG_PIECE(0) QT_LEG_PIECE(1) QT_LEG_PIECE(2) QT_LEG_PIECE(3)
+#undef QT_LEG_PIECE
+    return acc;
 }
 
 // S -= Lo Lo^T on the FP64 tensor cores.  The image (29 rows, stride LS) holds Lo; it is overwritten by the product, of which every
@@ -404,88 +503,100 @@ __device__ __forceinline__ void qt_syrk(double* __restrict__ img, double* s, int
     __syncwarp();
 }
 
-// Cholesky of the block held row-per-lane in s[] (lower triangle), fused with y = L^-1 rhs and — when TRSM — with the right-looking
-// solve e <- e L^-T of the NEXT group's coupling rows.  Column c of L goes through a 2-slot shared buffer once and serves both
-// updates; it leaves for the workspace with one coalesced store.  Returns y (entry `lane`); inv_own = 1 / L_ii of the own row.
-template <bool TRSM>
-__device__ __forceinline__ double qt_cholesky(double* s, double* e, double rhs, double* __restrict__ col2, double* __restrict__ wsg, int lane, double& inv_own) {
+// Cholesky of the block held row-per-lane in s[] (lower triangle), fused with y = L^-1 rhs.  Column c is parked UNSCALED in the
+// factor image (fimg[bc(c) + row] = S'[row][c], the pivot on top) and in the workspace; r_c = 1 / sqrt(pivot) goes to fimg[fRI + c].
+// L[row][c] = S'[row][c] r_c; every update multiplies with r_c^2 instead.  Returns y (entry `lane`).
+// (`stash` is re-read every other column after another lane wrote it: volatile, and no __restrict__ on the shared-memory operands.)
+__device__ __forceinline__ double qt_cholesky(double* s, double rhs, double* fimg, double* __restrict__ wsg, volatile double* stash, int lane) {
     constexpr int G = QpT::G;
-    constexpr unsigned FULL = 0xffffffffu;
     double rk = rhs;
-    inv_own = 0.0;
+    double* const il = fimg + lane;
+    double* const wl = wsg + lane;
 #pragma unroll
     for (int c = 0; c < G; ++c) {
-        const double rinv = rsqrt(__shfl_sync(FULL, s[c], c));
-        const double l = lane >= c ? s[c] * rinv : 0.0;
-        s[c] = l;
-        if (lane == c) inv_own = rinv;
-        double* col = col2 + (c & 1) * 32;
-        col[lane] = l;
-        if (lane >= c && lane < G) wsg[QpT::colstart(c) + lane - c] = l;
-        const double yc = __shfl_sync(FULL, rk, c) * rinv;
-        if (lane == c) rk = yc;
-        else if (lane > c) rk -= l * yc;
-        double ec = 0.0;
-        if (TRSM) { ec = e[c] * rinv; e[c] = ec; }
+        if (unsigned(lane - c) < unsigned(G - c)) {  // c <= lane < 29
+            il[QpT::bc(c)] = s[c];
+            wl[QpT::bc(c)] = s[c];
+        }
+        if (lane == c) stash[c & 1] = rk;
         __syncwarp();
+        const double rinv = rsqrt(fimg[QpT::bc(c) + c]);
+        const double r2 = rinv * rinv;
+        fimg[QpT::fRI + c] = rinv;  // every lane writes the same value
+        const double tc = stash[c & 1] * r2;
+        if (lane > c) rk -= s[c] * tc;
         if (c + 1 < G) {
-            if ((c + 1) & 1) {
-                const double lc = col[c + 1];
-                s[c + 1] -= l * lc;
-                if (TRSM) e[c + 1] -= ec * lc;
-            }
+            const double l2 = s[c] * r2;
+            const double* col = fimg + QpT::bc(c);
+            if ((c + 1) & 1) s[c + 1] -= l2 * col[c + 1];
 #pragma unroll
             for (int cc = (c + 2) & ~1; cc < G; cc += 2) {
                 const double2 t2 = qp_ld2(col + cc);
-                s[cc] -= l * t2.x;
-                if (TRSM) e[cc] -= ec * t2.x;
-                if (cc + 1 < G) {
-                    s[cc + 1] -= l * t2.y;
-                    if (TRSM) e[cc + 1] -= ec * t2.y;
-                }
+                s[cc] -= l2 * t2.x;
+                if (cc + 1 < G) s[cc + 1] -= l2 * t2.y;
             }
         }
     }
-    return rk;
+    __syncwarp();
+    const double ri = fimg[QpT::fRI + min(lane, G - 1)];
+    if (lane < G) wsg[QpT::fRI + lane] = ri;
+    return rk * ri;
+}
+
+// e <- e L^-T (right-looking) with the unscaled factor image: the coupling row of the next group.
+__device__ __forceinline__ void qt_trsm(double* e, const double* __restrict__ fimg) {
+    constexpr int G = QpT::G;
+#pragma unroll
+    for (int c = 0; c < G; ++c) {
+        const double rinv = fimg[QpT::fRI + c];
+        const double e2 = e[c] * (rinv * rinv);
+        e[c] *= rinv;
+        if (c + 1 < G) {
+            const double* col = fimg + QpT::bc(c);
+            if ((c + 1) & 1) e[c + 1] -= e2 * col[c + 1];
+#pragma unroll
+            for (int cc = (c + 2) & ~1; cc < G; cc += 2) {
+                const double2 t2 = qp_ld2(col + cc);
+                e[cc] -= e2 * t2.x;
+                if (cc + 1 < G) e[cc + 1] -= e2 * t2.y;
+            }
+        }
+    }
 }
 
 // (V_j^T nu)[k] for the local variable k = 0..36: nu = multipliers of group j+1 (29 entries in shared memory); `smc` holds Cp_{j+1}.
-__device__ __forceinline__ double qt_vT_nu(const double* __restrict__ ab, const double* __restrict__ smc, bool have_cp, const double* __restrict__ nu, int k) {
+__device__ __forceinline__ double qt_vT_nu(const double* __restrict__ ab, const double* __restrict__ smc, const double* __restrict__ nu, int k) {
     double acc = 0.0;
-    const int col = k < 3 ? -1 : k < 7 ? k - 3 : k < 10 ? -1 : k - 6;
+    const int col = k < 3 ? -1 : k < 7 ? k - 3 : k < 10 ? -1 : k < 13 ? k - 6 : k - 5;
     if (col >= 0) {
 #pragma unroll
         for (int qr = 0; qr < 7; ++qr) acc += ab[qr * 32 + col] * nu[qr < 4 ? 3 + qr : 6 + qr];
     }
     const double* ap = ab + 224;
-    if (k < 3) acc += ap[k * 6] * nu[k];
-    else if (k >= 7 && k < 10) acc += ap[(k - 7) * 6 + 1] * nu[k - 7] + ap[(3 + k - 7) * 6] * nu[k];
+    if (k < 3) {
+        acc += ap[k * 6] * nu[k];
+#pragma unroll
+        for (int l = 0; l < 4; ++l) acc += smc[QK::oCp + (l * 3 + k) * 8] * nu[13 + 4 * l + k + 1];
+    } else if (k < 7) {
+#pragma unroll
+        for (int l = 0; l < 4; ++l)
+#pragma unroll
+            for (int r1 = 0; r1 < 3; ++r1) acc += smc[QK::oCp + (l * 3 + r1) * 8 + 1 + k - 3] * nu[13 + 4 * l + r1 + 1];
+    } else if (k < 10) acc += ap[(k - 7) * 6 + 1] * nu[k - 7] + ap[(3 + k - 7) * 6] * nu[k];
     else if (k >= 13) {
         const int n = k - 13, l = n / 6, mm = n - 6 * l;
         if (mm < 3) acc += ap[mm * 6 + 2 + l] * nu[mm] + ap[(3 + mm) * 6 + 1 + l] * nu[7 + mm];
-        else if (have_cp) {
+        else {
 #pragma unroll
             for (int r1 = 0; r1 < 3; ++r1) acc += smc[QK::oCp + (l * 3 + r1) * 8 + 5 + mm - 3] * nu[13 + 4 * l + r1 + 1];
-        }
-    }
-    if (have_cp) {
-        if (k < 3) {
-#pragma unroll
-            for (int l = 0; l < 4; ++l) acc += smc[QK::oCp + (l * 3 + k) * 8] * nu[13 + 4 * l + k + 1];
-        } else if (k < 7) {
-#pragma unroll
-            for (int l = 0; l < 4; ++l)
-#pragma unroll
-                for (int r1 = 0; r1 < 3; ++r1) acc += smc[QK::oCp + (l * 3 + r1) * 8 + 1 + k - 3] * nu[13 + 4 * l + r1 + 1];
         }
     }
     return acc;
 }
 
 // (U_j^T nu)[k]: nu = multipliers of group j; U_j = [I 0; Cs_j].
-__device__ __forceinline__ double qt_uT_nu(const double* __restrict__ sm, bool have_cs, const double* __restrict__ nu, int k) {
+__device__ __forceinline__ double qt_uT_nu(const double* __restrict__ sm, const double* __restrict__ nu, int k) {
     double acc = k < 13 ? nu[k] : 0.0;
-    if (!have_cs) return acc;
     const double* cs = sm + QK::oCs;
     if (k < 3) {
 #pragma unroll
@@ -508,66 +619,91 @@ __device__ __forceinline__ double qt_uT_nu(const double* __restrict__ sm, bool h
     return acc;
 }
 
-// Solves L z = x then L^T nu = y - z with the packed-column image of L (`lp`: columns, then 1 / L_ii at wsInv, y at wsY): returns nu_lane.
-__device__ __forceinline__ double qt_outward_solve(const double* __restrict__ lp, double x, int lane) {
+// Solves L z = x, then L^T nu = y - z, with the factor image `f` (unscaled columns, r = 1 / sqrt(pivot) at fRI, y at fY): returns nu_lane.
+// Both sweeps keep the running entries unnormalised (z_i = rk_i r_i, nu_i = u_i r_i^2), so no lane needs a per-step select.
+__device__ __forceinline__ double qt_outward_solve(const double* __restrict__ f, double x, int lane) {
     constexpr int G = QpT::G;
     constexpr unsigned FULL = 0xffffffffu;
     const int ln = min(lane, G - 1);
+    const double* own_row = f + ln;           // raw[ln][i] = f[bc(i) + ln]
+    const double* own_col = f + QpT::bc(ln);  // raw[i][ln] = f[bc(ln) + i]
+    const double r_own = f[QpT::fRI + ln];
     double rk = x;
 #pragma unroll
-    for (int i = 0; i < G; ++i) {  // forward: lane > i needs L[lane][i]
-        const double zi = __shfl_sync(FULL, rk, i) * lp[QpT::wsInv + i];
-        const double lv = lp[QpT::colstart(i) + max(ln - i, 0)];
-        if (lane == i) rk = zi;
-        else if (lane > i) rk -= lv * zi;
+    for (int i = 0; i < G - 1; ++i) {
+        const double ri = f[QpT::fRI + i];
+        const double ti = __shfl_sync(FULL, rk, i) * (ri * ri);
+        if (lane > i) rk -= own_row[QpT::bc(i)] * ti;
     }
-    rk = (lane < G ? lp[QpT::wsY + ln] : 0.0) - rk;
-    const int cs = QpT::colstart(ln);
+    double u = ((lane < G ? f[QpT::fY + ln] : 0.0) - rk * r_own) * (own_col[ln] * r_own);  // (y - z) d,  d = pivot r = sqrt(pivot)
 #pragma unroll
-    for (int i = G - 1; i >= 0; --i) {  // backward with L^T: lane < i needs L[i][lane] = column `lane`, row i
-        const double ni = __shfl_sync(FULL, rk, i) * lp[QpT::wsInv + i];
-        const double lv = lp[cs + max(i - ln, 0)];
-        if (lane == i) rk = ni;
-        else if (lane < i) rk -= lv * ni;
+    for (int i = G - 1; i > 0; --i) {
+        const double ri = f[QpT::fRI + i];
+        const double ni = __shfl_sync(FULL, u, i) * (ri * ri);
+        if (lane < i) u -= own_col[i] * ni;
     }
-    return lane < G ? rk : 0.0;
+    return lane < G ? u * (r_own * r_own) : 0.0;
 }
 
 // =================================================================================================================================
-// One CTA of two warps per trajectory.  The two chains are separate (non-inlined) functions so that each gets its own register
-// allocation: inlined into one kernel, the union of the two paths spilled ~1.5 KB per thread.
+// One CTA of two warps per trajectory; the chains are separate (non-inlined) functions so that each gets its own register allocation.
 // =================================================================================================================================
-__device__ __noinline__ void qt_top_chain(const double* __restrict__ rec_all, long long ld_rec, double* __restrict__ ws_all, double* __restrict__ step_all, long long ld_step,
-        double* __restrict__ mult_all, long long ld_mult, int N, double delta, long long b, int lane, int wib, unsigned char* smem_raw) {
-    using Q = QpT;
-    constexpr int G = Q::G, LS = Q::LS;
-    constexpr unsigned SMALL_B = QK::SMALL * 8, APART_B = QK::APART * 8, WS_B = Q::WS_GROUP * 8;
-    double* const cta = reinterpret_cast<double*>(smem_raw);
-    double* const sm  = cta + wib * Q::PER_WARP;
-    double* const img = sm + Q::oLO;
-    double* const sY  = sm + Q::oY;
-    double* const sC  = sm + Q::oCOL;
-    double* const other_img = cta + (wib ^ 1) * Q::PER_WARP + Q::oLO;
-    double* const other_y   = cta + (wib ^ 1) * Q::PER_WARP + Q::oY;
-    uint64_t* const bars = reinterpret_cast<uint64_t*>(sm + Q::oBAR);
-    QtBuf sa{sm + Q::oSM0, bars + 0, 0u}, sb{sm + Q::oSM1, bars + 1, 0u}, abuf{sm + Q::oAB, bars + 2, 0u}, lbuf{img, bars + 3, 0u};
+struct QtArgs {
+    const double* rec;   // this trajectory's compact record
+    double* ws;          // this trajectory's workspace, (N + 1) groups
+    double* step;
+    double* mult;        // may be null
+    int N;
+    double delta;
+};
 
-    const double* __restrict__ rec  = rec_all + b * ld_rec;
-    const double* __restrict__ tail = rec + QK::tail(N);
-    double* __restrict__ ws   = ws_all + b * (long long)(N + 1) * Q::WS_GROUP;
-    double* __restrict__ step = step_all + b * ld_step;
-    double* __restrict__ mult = mult_all ? mult_all + b * ld_mult : nullptr;
-    const int nX = 13 * (N + 1);
-    const int m  = N / 2;  // the groups meet here
-    const bool act = lane < G, st = lane < 13;
-    auto chunk = [&](int j) { return rec + (long long)j * QK::NODE; };
-    auto swap_bufs = [&]() { const QtBuf t = sa; sa = sb; sb = t; };
+#define QT_COMMON                                                                                                            \
+    using Q = QpT;                                                                                                           \
+    constexpr int G = Q::G, LS = Q::LS;                                                                                      \
+    constexpr unsigned SMALL_B = QK::SMALL * 8, APART_B = QK::APART * 8, WS_B = Q::WS_GROUP * 8;                             \
+    double* const cta = reinterpret_cast<double*>(smem_raw);                                                                 \
+    double* const sm  = cta + wib * Q::PER_WARP;                                                                             \
+    double* const img = sm + Q::oLO;                                                                                         \
+    double* const sY  = sm + Q::oY;                                                                                          \
+    double* const stash = sm + Q::oMISC;                                                                                     \
+    double* const other_img = cta + (wib ^ 1) * Q::PER_WARP + Q::oLO;                                                        \
+    double* const other_y   = cta + (wib ^ 1) * Q::PER_WARP + Q::oY;                                                         \
+    uint64_t* const bars = reinterpret_cast<uint64_t*>(sm + Q::oBAR);                                                        \
+    QtBuf sa{sm + Q::oSM0, bars + 0, 0u}, sb{sm + Q::oSM1, bars + 1, 0u}, abuf{sm + Q::oAB, bars + 2, 0u}, lbuf{img, bars + 3, 0u}; \
+    const double* __restrict__ rec  = a.rec;                                                                                 \
+    const double* __restrict__ tail = rec + QK::tail(a.N);                                                                   \
+    double* __restrict__ ws   = a.ws;                                                                                        \
+    double* __restrict__ step = a.step;                                                                                      \
+    double* __restrict__ mult = a.mult;                                                                                      \
+    const int N = a.N, nX = 13 * (N + 1), m = N / 2;                                                                         \
+    const double delta = a.delta;                                                                                            \
+    const bool act = lane < G, st = lane < 13;                                                                               \
+    const QtLane LN(lane);                                                                                                   \
+    auto chunk = [&](int j) { return rec + (long long)j * QK::NODE; };                                                       \
+    auto swap_bufs = [&]() { const QtBuf t = sa; sa = sb; sb = t; };                                                         \
+    double s[G];                                                                                                             \
+    double rpart = 0.0
 
-    double s[G], e[G];
+// Coupling row -> image, and the part of the next right-hand side it carries: returns -(row . y).
+__device__ __forceinline__ double qt_store_coupling(const double* e, double* __restrict__ img, const double* __restrict__ sY, int lane) {
+    constexpr int G = QpT::G, LS = QpT::LS;
+    if (lane < G) {
 #pragma unroll
-    for (int c = 0; c < G; ++c) { s[c] = 0.0; e[c] = 0.0; }
-    double rpart = 0.0, inv_own;
+        for (int c = 0; c + 1 < G; c += 2) qp_st2(img + lane * LS + c, e[c], e[c + 1]);
+        qp_st2(img + lane * LS + G - 1, e[G - 1], 0.0);
+    }
+    double d0 = 0.0, d1 = 0.0;
+#pragma unroll
+    for (int c = 0; c + 1 < G; c += 2) { const double2 t2 = qp_ld2(sY + c); d0 += e[c] * t2.x; d1 += e[c + 1] * t2.y; }
+    d0 += e[G - 1] * sY[G - 1];
+    return -(d0 + d1);
+}
+
+__device__ __noinline__ void qt_top_chain(const QtArgs a, int lane, int wib, unsigned char* smem_raw) {
+    QT_COMMON;
     // ======================================================== top-down: groups 0 .. m-1
+#pragma unroll
+    for (int c = 0; c < G; ++c) s[c] = 0.0;
     sa.load(chunk(0), SMALL_B, lane);
     sb.load(chunk(1), SMALL_B, lane);
     abuf.load(chunk(0) + QK::oAQ, APART_B, lane);
@@ -576,51 +712,32 @@ __device__ __noinline__ void qt_top_chain(const double* __restrict__ rec_all, lo
     for (int j = 0; j < m; ++j) {  // sa = small_j (landed), sb = small_{j+1} and abuf = A_j (in flight)
         qt_pinv_t(sa.buf, lane, true);
         {   // S_jj += U P^-1 U^T + delta I ;  rhs = g - U t + rpart
-            QtRowU u;
-            qt_load_u_row(sa.buf, lane, u);
-            const double ut = qt_urow_dot(u, sa.buf + QK::oQ);
-            rpart += (st ? gdef : (act ? sa.buf[QK::oG + lane] : 0.0)) - ut;
-            qt_urow_times_pinv(u, sa.buf);
-            qt_urow_dot_u_rows(u, sa.buf, s);
+            QtU u;
+            qt_load_u(sa.buf, lane, LN, u);
+            rpart += (st ? gdef : (act ? sa.buf[QK::oG + lane] : 0.0)) - qt_u_dot(u, sa.buf + QK::oQ);
+            qt_u_pinv(u, sa.buf);
+            qt_u_dot_u_rows(u, sa.buf, s);
 #pragma unroll
             for (int c = 0; c < G; ++c) s[c] += c == lane ? delta : 0.0;
         }
         if (j > 0) qt_syrk(img, s, lane);
-        sb.wait();
-        abuf.wait();
-        double carry;
-        {   // coupling rows of group j+1: e = (V P^-1 U^T) row
-            QtRow v;
-            qt_load_v_row(abuf.buf, sb.buf, true, lane, v);
-            carry = qt_row_dot_t(v, sa.buf);
-            qt_row_times_pinv(v, sa.buf);
-            qt_row_dot_u_rows(v, sa.buf, e);
-        }
         double* wsg = ws + (long long)j * Q::WS_GROUP;
-        const double yj = qt_cholesky<true>(s, e, rpart, sC, wsg, lane, inv_own);
+        const double yj = qt_cholesky(s, rpart, img, wsg, stash, lane);
         if (act) {
             sY[lane] = yj;
-            wsg[Q::wsY + lane] = yj;
-            wsg[Q::wsInv + lane] = inv_own;
-#pragma unroll
-            for (int c = 0; c + 1 < G; c += 2) qp_st2(img + lane * LS + c, e[c], e[c + 1]);
-            qp_st2(img + lane * LS + G - 1, e[G - 1], 0.0);
+            wsg[Q::fY + lane] = yj;
         }
-        __syncwarp();
-        {   // rpart of group j+1 = -Lo y_j - V t_j
-            double d0 = 0.0, d1 = 0.0;
-#pragma unroll
-            for (int c = 0; c + 1 < G; c += 2) { const double2 t2 = qp_ld2(sY + c); d0 += e[c] * t2.x; d1 += e[c + 1] * t2.y; }
-            d0 += e[G - 1] * sY[G - 1];
-            rpart = -(d0 + d1) - carry;
+        sb.wait();
+        abuf.wait();
+        {   // coupling rows of group j+1: (V P^-1 U^T) row, solved against L_j, parked in the image
+            double e[G];
+            const double carry = qt_vpu(abuf.buf, sb.buf, sa.buf, LN, e);
+            qt_trsm(e, img);
+            __syncwarp();
+            rpart = qt_store_coupling(e, img, sY, lane) - carry;  // -Lo y_j - V t_j
         }
-        {   // S_{j+1,j+1} part: V P^-1 V^T row
-            QtRow v;
-            qt_load_v_row(abuf.buf, sb.buf, true, lane, v);
-            qt_row_times_pinv(v, sa.buf);
-            qt_row_dot_v_rows<false>(v, abuf.buf, sb.buf, true, s);
-        }
-        gdef = st ? sa.buf[QK::oG + lane] : 0.0;  // defect of stage j: the state rows of group j+1
+        qt_vpv<true>(abuf.buf, sb.buf, sa.buf, LN, s);  // S_{j+1,j+1} part: V P^-1 V^T row
+        gdef = st ? sa.buf[QK::oG + lane] : 0.0;        // defect of stage j: the state rows of group j+1
         __syncwarp();
         swap_bufs();  // sa = small_{j+1}
         if (j + 1 < m) {
@@ -640,26 +757,20 @@ __device__ __noinline__ void qt_top_chain(const double* __restrict__ rec_all, lo
         s[G - 1] += t2.x;
         rpart += t2.y;
     }
-    double* wsg = ws + (long long)m * Q::WS_GROUP;
-    const double ym = qt_cholesky<false>(s, e, rpart, sC, wsg, lane, inv_own);
-    // nu_m = L^-T y_m from the rows in registers (column access = across lanes: one warp reduction per entry)
-    double num = 0.0;
-#pragma unroll
-    for (int i = G - 1; i >= 0; --i) {
-        double part = lane > i && act ? s[i] * num : 0.0;
-#pragma unroll
-        for (int o = 16; o; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
-        const double yi = __shfl_sync(0xffffffffu, ym, i), ii = __shfl_sync(0xffffffffu, inv_own, i);
-        if (lane == i) num = (yi - part) * ii;
-    }
-    if (act) {
+    {
+        double* wsg = ws + (long long)m * Q::WS_GROUP;
+        const double ym = qt_cholesky(s, rpart, img, wsg, stash, lane);
+        if (act) img[Q::fY + lane] = ym;
+        __syncwarp();
+        const double num = qt_outward_solve(img, 0.0, lane);  // nu_m = L^-T y_m
+        __syncwarp();
         sY[lane] = num;
         other_y[lane] = num;
-        if (mult) {
+        if (mult && act) {
             if (st) mult[13 * m + lane] = num;
             else mult[nX + 16 * m + (lane - 13)] = num;
         }
-    } else { sY[lane] = 0.0; other_y[lane] = 0.0; }
+    }
     __syncthreads();  // nu_m is visible to the bottom warp
 
     // ======================================================== outward: groups m-1 .. 0
@@ -674,18 +785,18 @@ __device__ __noinline__ void qt_top_chain(const double* __restrict__ rec_all, lo
         sa.wait();
         abuf.wait();
         qt_pinv_t(sa.buf, lane, true);
-        for (int k = lane; k < 37; k += 32) vA[k] = qt_vT_nu(abuf.buf, sb.buf, true, sY, k);  // a = V_j^T nu_{j+1}
+        for (int k = lane; k < 37; k += 32) vA[k] = qt_vT_nu(abuf.buf, sb.buf, sY, k);  // a = V_j^T nu_{j+1}
         __syncwarp();
         qt_apply_pinv(sa.buf, vA, vC, lane);
-        QtRowU u;
-        qt_load_u_row(sa.buf, lane, u);
-        const double z = qt_urow_dot(u, vC);  // (U P^-1 a) row
+        QtU u;
+        qt_load_u(sa.buf, lane, LN, u);
+        const double z = qt_u_dot(u, vC);  // (U P^-1 a) row
         lbuf.wait();
         const double nu = qt_outward_solve(img, z, lane);
         __syncwarp();
         sY[lane] = nu;
         __syncwarp();
-        for (int k = lane; k < 37; k += 32) vA[k] += qt_uT_nu(sa.buf, true, sY, k);
+        for (int k = lane; k < 37; k += 32) vA[k] += qt_uT_nu(sa.buf, sY, k);
         __syncwarp();
         qt_apply_pinv(sa.buf, vA, vC, lane);
         for (int k = lane; k < 37; k += 32) {
@@ -701,36 +812,8 @@ __device__ __noinline__ void qt_top_chain(const double* __restrict__ rec_all, lo
     }
 }
 
-__device__ __noinline__ void qt_bottom_chain(const double* __restrict__ rec_all, long long ld_rec, double* __restrict__ ws_all, double* __restrict__ step_all, long long ld_step,
-        double* __restrict__ mult_all, long long ld_mult, int N, double delta, long long b, int lane, int wib, unsigned char* smem_raw) {
-    using Q = QpT;
-    constexpr int G = Q::G, LS = Q::LS;
-    constexpr unsigned SMALL_B = QK::SMALL * 8, APART_B = QK::APART * 8, WS_B = Q::WS_GROUP * 8;
-    double* const cta = reinterpret_cast<double*>(smem_raw);
-    double* const sm  = cta + wib * Q::PER_WARP;
-    double* const img = sm + Q::oLO;
-    double* const sY  = sm + Q::oY;
-    double* const sC  = sm + Q::oCOL;
-    double* const other_img = cta + (wib ^ 1) * Q::PER_WARP + Q::oLO;
-    double* const other_y   = cta + (wib ^ 1) * Q::PER_WARP + Q::oY;
-    uint64_t* const bars = reinterpret_cast<uint64_t*>(sm + Q::oBAR);
-    QtBuf sa{sm + Q::oSM0, bars + 0, 0u}, sb{sm + Q::oSM1, bars + 1, 0u}, abuf{sm + Q::oAB, bars + 2, 0u}, lbuf{img, bars + 3, 0u};
-
-    const double* __restrict__ rec  = rec_all + b * ld_rec;
-    const double* __restrict__ tail = rec + QK::tail(N);
-    double* __restrict__ ws   = ws_all + b * (long long)(N + 1) * Q::WS_GROUP;
-    double* __restrict__ step = step_all + b * ld_step;
-    double* __restrict__ mult = mult_all ? mult_all + b * ld_mult : nullptr;
-    const int nX = 13 * (N + 1);
-    const int m  = N / 2;  // the groups meet here
-    const bool act = lane < G, st = lane < 13;
-    auto chunk = [&](int j) { return rec + (long long)j * QK::NODE; };
-    auto swap_bufs = [&]() { const QtBuf t = sa; sa = sb; sb = t; };
-
-    double s[G], e[G];
-#pragma unroll
-    for (int c = 0; c < G; ++c) { s[c] = 0.0; e[c] = 0.0; }
-    double rpart = 0.0, inv_own;
+__device__ __noinline__ void qt_bottom_chain(const QtArgs a, int lane, int wib, unsigned char* smem_raw) {
+    QT_COMMON;
     // ======================================================== bottom-up: groups N .. m+1
     // sa = small_j (synthesised for j = N: no inputs, no contact rows), sb = small_{j-1}, abuf = A_{j-1}
     for (int k = lane; k < QK::SMALL; k += 32) sa.buf[k] = 0.0;
@@ -744,55 +827,38 @@ __device__ __noinline__ void qt_bottom_chain(const double* __restrict__ rec_all,
     abuf.load(chunk(N - 1) + QK::oAQ, APART_B, lane);
     qt_pinv_t(sa.buf, lane, false);
     for (int j = N; j > m; --j) {
-        const bool last = j == N;  // group N: 13 rows, no contact rows
-        {   // S_jj = U P^-1 U^T + delta I ;  rhs = contact values - U t + rpart
-            QtRowU u;
-            qt_load_u_row(sa.buf, lane, u);
-            if (last && !st) { u.xp = 0.0; u.q[0] = u.q[1] = u.q[2] = u.q[3] = 0.0; u.r[0] = u.r[1] = u.r[2] = 0.0; }
-            const double ut = qt_urow_dot(u, sa.buf + QK::oQ);
-            rpart += (!st && act ? sa.buf[QK::oG + lane] : 0.0) - ut;
-            qt_urow_times_pinv(u, sa.buf);
+        {   // S_jj = U P^-1 U^T + delta I ;  rhs = contact values - U t + rpart   (group N: the synthesised chunk has null contact rows)
+            QtU u;
+            qt_load_u(sa.buf, lane, LN, u);
+            rpart += (!st && act ? sa.buf[QK::oG + lane] : 0.0) - qt_u_dot(u, sa.buf + QK::oQ);
+            qt_u_pinv(u, sa.buf);
 #pragma unroll
             for (int c = 0; c < G; ++c) s[c] = c == lane ? delta : 0.0;
-            qt_urow_dot_u_rows(u, sa.buf, s);
+            qt_u_dot_u_rows(u, sa.buf, s);
         }
-        if (!last) qt_syrk(img, s, lane);
+        if (j < N) qt_syrk(img, s, lane);
         sb.wait();
         abuf.wait();
         qt_pinv_t(sb.buf, lane, true);
-        rpart += st ? sb.buf[QK::oG + lane] : 0.0;  // defect of stage j-1
-        {   // S_jj += V P^-1 V^T ;  rhs -= V t_{j-1}
-            QtRow v;
-            qt_load_v_row(abuf.buf, sa.buf, !last, lane, v);
-            rpart -= qt_row_dot_t(v, sb.buf);
-            qt_row_times_pinv(v, sb.buf);
-            qt_row_dot_v_rows<true>(v, abuf.buf, sa.buf, !last, s);
-        }
-        {   // coupling rows of group j-1: e = (U_{j-1} P^-1 V^T) row
-            QtRowU u;
-            qt_load_u_row(sb.buf, lane, u);
-            qt_urow_times_pinv(u, sb.buf);
-            qt_urow_dot_v_rows(u, abuf.buf, sa.buf, !last, e);
-        }
-        __syncwarp();
-        if (j - 2 >= m) abuf.load(chunk(j - 2) + QK::oAQ, APART_B, lane);
+        rpart += st ? sb.buf[QK::oG + lane] : 0.0;                     // defect of stage j-1
+        rpart -= qt_vpv<false>(abuf.buf, sa.buf, sb.buf, LN, s);       // S_jj += V P^-1 V^T ;  rhs -= V t_{j-1}
         double* wsg = ws + (long long)j * Q::WS_GROUP;
-        const double yj = qt_cholesky<true>(s, e, rpart, sC, wsg, lane, inv_own);
+        const double yj = qt_cholesky(s, rpart, img, wsg, stash, lane);
         if (act) {
             sY[lane] = yj;
-            wsg[Q::wsY + lane] = yj;
-            wsg[Q::wsInv + lane] = inv_own;
-#pragma unroll
-            for (int c = 0; c + 1 < G; c += 2) qp_st2(img + lane * LS + c, e[c], e[c + 1]);
-            qp_st2(img + lane * LS + G - 1, e[G - 1], 0.0);
+            wsg[Q::fY + lane] = yj;
         }
-        __syncwarp();
-        {
-            double d0 = 0.0, d1 = 0.0;
-#pragma unroll
-            for (int c = 0; c + 1 < G; c += 2) { const double2 t2 = qp_ld2(sY + c); d0 += e[c] * t2.x; d1 += e[c + 1] * t2.y; }
-            d0 += e[G - 1] * sY[G - 1];
-            rpart = -(d0 + d1);
+        {   // coupling rows of group j-1: (U_{j-1} P^-1 V^T) row, solved against M_j, parked in the image
+            double e[G];
+            QtU u;
+            qt_load_u(sb.buf, lane, LN, u);
+            qt_u_pinv(u, sb.buf);
+            qt_u_dot_v_rows(u, abuf.buf, sa.buf, e);
+            __syncwarp();
+            if (j - 2 >= m) abuf.load(chunk(j - 2) + QK::oAQ, APART_B, lane);
+            qt_trsm(e, img);
+            __syncwarp();
+            rpart = qt_store_coupling(e, img, sY, lane);  // -Uo y_j
         }
         __syncwarp();
         swap_bufs();  // sa = small_{j-1} (P^-1 and t already in place)
@@ -800,14 +866,13 @@ __device__ __noinline__ void qt_bottom_chain(const double* __restrict__ rec_all,
     }
     // ---- middle group m, bottom part: U P^-1 U^T + delta I - Uo Uo^T ; rhs = contact values - U t - Uo y   (sa = small_m)
     {
-        QtRowU u;
-        qt_load_u_row(sa.buf, lane, u);
-        const double ut = qt_urow_dot(u, sa.buf + QK::oQ);
-        rpart += (!st && act ? sa.buf[QK::oG + lane] : 0.0) - ut;
-        qt_urow_times_pinv(u, sa.buf);
+        QtU u;
+        qt_load_u(sa.buf, lane, LN, u);
+        rpart += (!st && act ? sa.buf[QK::oG + lane] : 0.0) - qt_u_dot(u, sa.buf + QK::oQ);
+        qt_u_pinv(u, sa.buf);
 #pragma unroll
         for (int c = 0; c < G; ++c) s[c] = c == lane ? delta : 0.0;
-        qt_urow_dot_u_rows(u, sa.buf, s);
+        qt_u_dot_u_rows(u, sa.buf, s);
     }
     qt_syrk(img, s, lane);
     if (act) {
@@ -831,30 +896,20 @@ __device__ __noinline__ void qt_bottom_chain(const double* __restrict__ rec_all,
         if (!last) {
             sb.load(chunk(j), SMALL_B, lane);
             sb.wait();
+        } else {
+            for (int k = lane; k < 96; k += 32) sb.buf[QK::oCp + k] = 0.0;  // group N has no contact rows
+            __syncwarp();
         }
-        for (int k = lane; k < 37; k += 32) vA[k] = qt_uT_nu(sa.buf, true, sY, k);  // b = U_{j-1}^T nu_{j-1}
+        for (int k = lane; k < 37; k += 32) vA[k] = qt_uT_nu(sa.buf, sY, k);  // b = U_{j-1}^T nu_{j-1}
         __syncwarp();
         qt_apply_pinv(sa.buf, vA, vC, lane);
-        double z;
-        {   // (V_{j-1} P^-1 b) row
-            QtRow v;
-            qt_load_v_row(abuf.buf, sb.buf, !last, lane, v);
-            const double* x = vC;
-            double a0 = v.xp * x[v.xc], a1 = v.xv * x[7 + v.xc];
-#pragma unroll
-            for (int i = 0; i < 4; ++i) a0 += v.p[i] * x[3 + i];
-#pragma unroll
-            for (int i = 0; i < 3; ++i) a1 += v.p[4 + i] * x[10 + i];
-#pragma unroll
-            for (int n = 0; n < 24; n += 2) { a0 += v.p[7 + n] * x[13 + n]; a1 += v.p[8 + n] * x[14 + n]; }
-            z = a0 + a1;
-        }
+        const double z = qt_v_dot(abuf.buf, sb.buf, LN, vC);  // (V_{j-1} P^-1 b) row
         lbuf.wait();
         const double nu = qt_outward_solve(img, z, lane);
         __syncwarp();
         nu2[lane] = nu;
         __syncwarp();
-        for (int k = lane; k < 37; k += 32) vA[k] += qt_vT_nu(abuf.buf, sb.buf, !last, nu2, k);
+        for (int k = lane; k < 37; k += 32) vA[k] += qt_vT_nu(abuf.buf, sb.buf, nu2, k);
         __syncwarp();
         qt_apply_pinv(sa.buf, vA, vC, lane);
         for (int k = lane; k < 37; k += 32) {
@@ -877,8 +932,9 @@ __device__ __noinline__ void qt_bottom_chain(const double* __restrict__ rec_all,
     // d_N = -P_N^-1 (q_N + nu_N)
     if (st) step[13 * N + lane] = -(tail[QK::tQN + lane] + sY[lane]) / tail[QK::tHN + lane];
 }
+#undef QT_COMMON
 
-__global__ void __maxnreg__(144)
+__global__ void __launch_bounds__(64, 7)
 qp_twisted_kernel(const double* __restrict__ rec_all, long long ld_rec, double* __restrict__ ws_all, double* __restrict__ step_all, long long ld_step,
                   double* __restrict__ mult_all, long long ld_mult, int N, long long batch, double delta, const int* __restrict__ skip_status) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -892,8 +948,10 @@ qp_twisted_kernel(const double* __restrict__ rec_all, long long ld_rec, double* 
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         __syncwarp();
     }
-    if (wib == 0) qt_top_chain(rec_all, ld_rec, ws_all, step_all, ld_step, mult_all, ld_mult, N, delta, b, lane, wib, smem_raw);
-    else qt_bottom_chain(rec_all, ld_rec, ws_all, step_all, ld_step, mult_all, ld_mult, N, delta, b, lane, wib, smem_raw);
+    const QtArgs a{rec_all + b * ld_rec, ws_all + b * (long long)(N + 1) * QpT::WS_GROUP, step_all + b * ld_step,
+                   mult_all ? mult_all + b * ld_mult : nullptr, N, delta};
+    if (wib == 0) qt_top_chain(a, lane, wib, smem_raw);
+    else qt_bottom_chain(a, lane, wib, smem_raw);
 }
 
 }  // namespace ub

@@ -644,6 +644,8 @@ int launch_qp_twisted(ungar_b200_model& mdl, const void* rec, bool rec_is_compac
     static PerDevice configured;
     if (!configured[mdl.desc.device]) {
         UB_CUDA(cudaFuncSetAttribute(ub::qp_twisted_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, Q::SMEM_BYTES));
+        // 7 CTAs x 31.5 KB need the largest shared-memory carveout (the driver's default pick was 196 KB: 6 CTAs, a second wave)
+        UB_CUDA(cudaFuncSetAttribute(ub::qp_twisted_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
         configured[mdl.desc.device] = 1;
     }
     if (batch > 2147483647LL) return fail(UNGAR_B200_EINVAL, "batch too large for one launch");
@@ -971,6 +973,17 @@ int ungar_b200_qp_solve(ungar_b200_model* model, const void* records_device, int
     UB_CUDA(cudaSetDevice(model->desc.device));
     return launch_qp(*model, records_device, model->compact, batch, ld_rec, steps, ld_steps, multipliers, ld_multipliers, nullptr,
                      static_cast<cudaStream_t>(stream_));
+}
+
+// Test hook (not part of include/ungar_b200.h): copies the first `count` doubles of the QP workspace (per trajectory and group: the
+// factor image of qp_twisted.cuh) to the host, so that tests can compare the kernel's intermediate blocks with oracle/qp_reference.py.
+int ungar_b200_debug_qp_workspace(ungar_b200_model* model, double* host_out, int64_t count) {
+    if (!model || !host_out || count < 0) return fail(UNGAR_B200_EINVAL, "null argument");
+    if (size_t(count) * sizeof(double) > model->ws_qp.cap) return fail(UNGAR_B200_EINVAL, "workspace holds fewer than %lld doubles", (long long)count);
+    UB_CUDA(cudaSetDevice(model->desc.device));
+    UB_CUDA(cudaDeviceSynchronize());
+    UB_CUDA(cudaMemcpy(host_out, model->ws_qp.ptr, size_t(count) * sizeof(double), cudaMemcpyDeviceToHost));
+    return UNGAR_B200_OK;
 }
 
 int ungar_b200_sqp_options_default(ungar_b200_sqp_options* out) {
