@@ -35,7 +35,7 @@ struct QpT {
     // per-warp shared memory (doubles)
     static constexpr int oLO = 0, oSM0 = G * LS, oSM1 = oSM0 + K::SMALL, oAB = oSM1 + K::SMALL, oY = oAB + K::APART, oMISC = oY + 32,
                          oBAR = oMISC + 4, PER_WARP = oBAR + 4;
-    static constexpr int SMEM_BYTES = 2 * PER_WARP * 8;
+    static constexpr int SMEM_BYTES = 2 * PER_WARP * 8 + 64;  // + the trajectory's pointers (QtArgs) behind the two warps' regions
     // factor image (shared memory during a group, global workspace afterwards): unscaled columns, 1 / sqrt(pivot), y
     static constexpr int fRI = 450, fY = 480, WS_GROUP = 510;
     // scratch vectors of the outward pass live behind the factor image in the LO region
@@ -66,23 +66,42 @@ __device__ __forceinline__ void qt_bar_wait(uint64_t* bar, unsigned parity) {
         : "memory");
 }
 
-// One buffer with its barrier and phase bit.  load(): all lanes must have finished reading the buffer (the caller syncs the warp).
-struct QtBuf {
-    double* buf;
-    uint64_t* bar;
-    unsigned phase;
-    __device__ __forceinline__ void load(const double* src, unsigned bytes, int lane) {
+// Per-warp context.  Deliberately tiny: everything else (buffer addresses, barrier addresses, the trajectory's pointers, which live in
+// shared memory behind the two warps' regions) is recomputed at the point of use, because the chains keep a 29-entry row in registers
+// and ptxas needs slack to batch the broadcast loads (with ~75 registers of loop invariants it serialised every load -> FMA pair).
+struct QtArgs {
+    const double* rec;   // this trajectory's compact record
+    double* ws;          // this trajectory's workspace, (N + 1) groups
+    double* step;
+    double* mult;        // may be null
+    int N;
+    double delta;
+};
+struct QtCtx {
+    double* sm;       // this warp's shared memory
+    int lane;
+    int cur;          // which of the two small buffers is "a"
+    unsigned phases;  // bit b: phase of barrier b (0, 1: small buffers; 2: A part; 3: factor image)
+    __device__ __forceinline__ double* small(int which) const { return sm + QpT::oSM0 + ((cur ^ which) & 1) * Compact::SMALL; }  // 0: a, 1: b
+    __device__ __forceinline__ double* ab() const { return sm + QpT::oAB; }
+    __device__ __forceinline__ uint64_t* bar(int b) const { return reinterpret_cast<uint64_t*>(sm + QpT::oBAR) + b; }
+    __device__ __forceinline__ void issue(int b, double* dst, const double* src, unsigned bytes) const {
         if (lane == 0) {
-            // the buffer was modified in place, and the factor image in the workspace was written, through the generic proxy
-            asm volatile("fence.proxy.async;" ::: "memory");
-            qt_bar_expect(bar, bytes);
-            qt_bulk_load(buf, src, bytes, bar);
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // the buffer was modified in place through the generic proxy
+            qt_bar_expect(bar(b), bytes);
+            qt_bulk_load(dst, src, bytes, bar(b));
         }
     }
-    __device__ __forceinline__ void wait() {
-        qt_bar_wait(bar, phase);
-        phase ^= 1u;
+    __device__ __forceinline__ void wait(int b) {
+        qt_bar_wait(bar(b), (phases >> b) & 1u);
+        phases ^= 1u << b;
     }
+    // all lanes must have finished reading the destination (the caller syncs the warp)
+    __device__ __forceinline__ void load_small(int which, const double* chunk) const { issue((cur ^ which) & 1, small(which), chunk, Compact::SMALL * 8); }
+    __device__ __forceinline__ void wait_small(int which) { wait((cur ^ which) & 1); }
+    __device__ __forceinline__ void load_ab(const double* chunk) const { issue(2, ab(), chunk + Compact::oAQ, Compact::APART * 8); }
+    __device__ __forceinline__ void load_factor(const double* wsg) const { issue(3, sm + QpT::oLO, wsg, QpT::WS_GROUP * 8); }
+    __device__ __forceinline__ void swap() { cur ^= 1; }
 };
 
 // ---------------------------------------------------------------------------------------------------------------------------------
@@ -503,6 +522,27 @@ __device__ __forceinline__ void qt_syrk(double* __restrict__ img, double* s, int
     __syncwarp();
 }
 
+// x[cc] += a * col[cc] for cc = FIRST .. 28, the column read from shared memory in batches of up to eight 16-byte loads that are
+// all issued before the first dependent FMA (left to itself the compiler reuses one load register and serialises load -> FMA pairs).
+// (`first` is a compile-time constant at every call site once the column loops are unrolled.)
+__device__ __forceinline__ void qt_axpy_column(double* x, double a, const double* col, const int first) {
+    constexpr int G = QpT::G;
+    if (first & 1) x[first] += a * col[first];
+    const int e0 = (first + 1) & ~1;  // first even index
+#pragma unroll
+    for (int base = e0; base < G; base += 16) {
+        double2 t[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k)
+            if (base + 2 * k < G) t[k] = qp_ld2(col + base + 2 * k);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            if (base + 2 * k < G) x[base + 2 * k] += a * t[k].x;
+            if (base + 2 * k + 1 < G) x[base + 2 * k + 1] += a * t[k].y;
+        }
+    }
+}
+
 // Cholesky of the block held row-per-lane in s[] (lower triangle), fused with y = L^-1 rhs.  Column c is parked UNSCALED in the
 // factor image (fimg[bc(c) + row] = S'[row][c], the pivot on top) and in the workspace; r_c = 1 / sqrt(pivot) goes to fimg[fRI + c].
 // L[row][c] = S'[row][c] r_c; every update multiplies with r_c^2 instead.  Returns y (entry `lane`).
@@ -527,14 +567,7 @@ __device__ __forceinline__ double qt_cholesky(double* s, double rhs, double* fim
         if (lane > c) rk -= s[c] * tc;
         if (c + 1 < G) {
             const double l2 = s[c] * r2;
-            const double* col = fimg + QpT::bc(c);
-            if ((c + 1) & 1) s[c + 1] -= l2 * col[c + 1];
-#pragma unroll
-            for (int cc = (c + 2) & ~1; cc < G; cc += 2) {
-                const double2 t2 = qp_ld2(col + cc);
-                s[cc] -= l2 * t2.x;
-                if (cc + 1 < G) s[cc + 1] -= l2 * t2.y;
-            }
+            qt_axpy_column(s, -l2, fimg + QpT::bc(c), c + 1);
         }
     }
     __syncwarp();
@@ -551,16 +584,7 @@ __device__ __forceinline__ void qt_trsm(double* e, const double* __restrict__ fi
         const double rinv = fimg[QpT::fRI + c];
         const double e2 = e[c] * (rinv * rinv);
         e[c] *= rinv;
-        if (c + 1 < G) {
-            const double* col = fimg + QpT::bc(c);
-            if ((c + 1) & 1) e[c + 1] -= e2 * col[c + 1];
-#pragma unroll
-            for (int cc = (c + 2) & ~1; cc < G; cc += 2) {
-                const double2 t2 = qp_ld2(col + cc);
-                e[cc] -= e2 * t2.x;
-                if (cc + 1 < G) e[cc + 1] -= e2 * t2.y;
-            }
-        }
+        if (c + 1 < G) qt_axpy_column(e, -e2, fimg + QpT::bc(c), c + 1);
     }
 }
 
@@ -648,44 +672,9 @@ __device__ __forceinline__ double qt_outward_solve(const double* __restrict__ f,
 // =================================================================================================================================
 // One CTA of two warps per trajectory; the chains are separate (non-inlined) functions so that each gets its own register allocation.
 // =================================================================================================================================
-struct QtArgs {
-    const double* rec;   // this trajectory's compact record
-    double* ws;          // this trajectory's workspace, (N + 1) groups
-    double* step;
-    double* mult;        // may be null
-    int N;
-    double delta;
-};
-
-#define QT_COMMON                                                                                                            \
-    using Q = QpT;                                                                                                           \
-    constexpr int G = Q::G, LS = Q::LS;                                                                                      \
-    constexpr unsigned SMALL_B = QK::SMALL * 8, APART_B = QK::APART * 8, WS_B = Q::WS_GROUP * 8;                             \
-    double* const cta = reinterpret_cast<double*>(smem_raw);                                                                 \
-    double* const sm  = cta + wib * Q::PER_WARP;                                                                             \
-    double* const img = sm + Q::oLO;                                                                                         \
-    double* const sY  = sm + Q::oY;                                                                                          \
-    double* const stash = sm + Q::oMISC;                                                                                     \
-    double* const other_img = cta + (wib ^ 1) * Q::PER_WARP + Q::oLO;                                                        \
-    double* const other_y   = cta + (wib ^ 1) * Q::PER_WARP + Q::oY;                                                         \
-    uint64_t* const bars = reinterpret_cast<uint64_t*>(sm + Q::oBAR);                                                        \
-    QtBuf sa{sm + Q::oSM0, bars + 0, 0u}, sb{sm + Q::oSM1, bars + 1, 0u}, abuf{sm + Q::oAB, bars + 2, 0u}, lbuf{img, bars + 3, 0u}; \
-    const double* __restrict__ rec  = a.rec;                                                                                 \
-    const double* __restrict__ tail = rec + QK::tail(a.N);                                                                   \
-    double* __restrict__ ws   = a.ws;                                                                                        \
-    double* __restrict__ step = a.step;                                                                                      \
-    double* __restrict__ mult = a.mult;                                                                                      \
-    const int N = a.N, nX = 13 * (N + 1), m = N / 2;                                                                         \
-    const double delta = a.delta;                                                                                            \
-    const bool act = lane < G, st = lane < 13;                                                                               \
-    const QtLane LN(lane);                                                                                                   \
-    auto chunk = [&](int j) { return rec + (long long)j * QK::NODE; };                                                       \
-    auto swap_bufs = [&]() { const QtBuf t = sa; sa = sb; sb = t; };                                                         \
-    double s[G];                                                                                                             \
-    double rpart = 0.0
 
 // Coupling row -> image, and the part of the next right-hand side it carries: returns -(row . y).
-__device__ __forceinline__ double qt_store_coupling(const double* e, double* __restrict__ img, const double* __restrict__ sY, int lane) {
+__device__ __forceinline__ double qt_store_coupling(const double* e, double* img, const double* sY, int lane) {
     constexpr int G = QpT::G, LS = QpT::LS;
     if (lane < G) {
 #pragma unroll
@@ -699,58 +688,103 @@ __device__ __forceinline__ double qt_store_coupling(const double* e, double* __r
     return -(d0 + d1);
 }
 
-__device__ __noinline__ void qt_top_chain(const QtArgs a, int lane, int wib, unsigned char* smem_raw) {
-    QT_COMMON;
+// S (+)= U P^-1 U^T + delta I of the chunk in `sma`;  returns the lane's part of the right-hand side: g - U t (contact lanes; state
+// lanes: -t, their g comes from the neighbouring chunk).
+template <bool SET>
+__device__ __forceinline__ double qt_upu(const double* sma, int lane, double delta, double* s) {
+    constexpr int G = QpT::G;
+    const QtLane LN(lane);
+    QtU u;
+    qt_load_u(sma, lane, LN, u);
+    const double r = (lane >= 13 && lane < G ? sma[QK::oG + lane] : 0.0) - qt_u_dot(u, sma + QK::oQ);
+    qt_u_pinv(u, sma);
+    if (SET) {
+#pragma unroll
+        for (int c = 0; c < G; ++c) s[c] = c == lane ? delta : 0.0;
+    } else {
+#pragma unroll
+        for (int c = 0; c < G; ++c) s[c] += c == lane ? delta : 0.0;
+    }
+    qt_u_dot_u_rows(u, sma, s);
+    return r;
+}
+
+#define QT_ARGS (*reinterpret_cast<const QtArgs*>(reinterpret_cast<const double*>(smem_raw) + 2 * QpT::PER_WARP))
+#define QT_CHUNK(j) (QT_ARGS.rec + (long long)(j) * QK::NODE)
+#define QT_WSG(j) (QT_ARGS.ws + (long long)(j) * QpT::WS_GROUP)
+
+__device__ __forceinline__ void qt_store_step(const unsigned char* smem_raw, const double* sma, const double* vC, int j, int lane) {
+    const int N = QT_ARGS.N;
+    double* step = QT_ARGS.step;
+    for (int k = lane; k < 37; k += 32) {
+        const long long dst = k < 13 ? 13 * j + k : 13 * (N + 1) + 24 * j + (k - 13);
+        step[dst] = -(sma[QK::oQ + k] + vC[k]);  // d_j = -(t_j + P^-1 (...))
+    }
+}
+__device__ __forceinline__ void qt_store_mult(const unsigned char* smem_raw, double nu, int j, int lane) {
+    double* mult = QT_ARGS.mult;
+    const int N = QT_ARGS.N;
+    if (mult && lane < QpT::G) {
+        if (lane < 13) mult[13 * j + lane] = nu;
+        else if (j < N) mult[13 * (N + 1) + 16 * j + (lane - 13)] = nu;
+    }
+}
+
+__device__ __noinline__ void qt_top_chain(int lane, unsigned char* smem_raw) {
+    using Q = QpT;
+    constexpr int G = Q::G, LS = Q::LS;
+    QtCtx cx{reinterpret_cast<double*>(smem_raw), lane, 0, 0u};
+    double* const img = cx.sm + Q::oLO;
+    double* const sY  = cx.sm + Q::oY;
+    const int m = QT_ARGS.N / 2;
+    const bool act = lane < G, st = lane < 13;
+    double s[G];
+    double rpart = 0.0;
     // ======================================================== top-down: groups 0 .. m-1
 #pragma unroll
     for (int c = 0; c < G; ++c) s[c] = 0.0;
-    sa.load(chunk(0), SMALL_B, lane);
-    sb.load(chunk(1), SMALL_B, lane);
-    abuf.load(chunk(0) + QK::oAQ, APART_B, lane);
-    double gdef = st ? tail[QK::tG0 + lane] : 0.0;  // x_0 - x_measured
-    sa.wait();
-    for (int j = 0; j < m; ++j) {  // sa = small_j (landed), sb = small_{j+1} and abuf = A_j (in flight)
-        qt_pinv_t(sa.buf, lane, true);
-        {   // S_jj += U P^-1 U^T + delta I ;  rhs = g - U t + rpart
-            QtU u;
-            qt_load_u(sa.buf, lane, LN, u);
-            rpart += (st ? gdef : (act ? sa.buf[QK::oG + lane] : 0.0)) - qt_u_dot(u, sa.buf + QK::oQ);
-            qt_u_pinv(u, sa.buf);
-            qt_u_dot_u_rows(u, sa.buf, s);
-#pragma unroll
-            for (int c = 0; c < G; ++c) s[c] += c == lane ? delta : 0.0;
-        }
+    cx.load_small(0, QT_CHUNK(0));
+    cx.load_small(1, QT_CHUNK(1));
+    cx.load_ab(QT_CHUNK(0));
+    double gdef = st ? QT_ARGS.rec[QK::tail(QT_ARGS.N) + QK::tG0 + lane] : 0.0;  // x_0 - x_measured
+    cx.wait_small(0);
+    for (int j = 0; j < m; ++j) {  // a = small_j (landed), b = small_{j+1} and A_j (in flight)
+        qt_pinv_t(cx.small(0), lane, true);
+        rpart += gdef + qt_upu<false>(cx.small(0), lane, QT_ARGS.delta, s);  // S_jj += U P^-1 U^T + delta I ;  rhs = g - U t + rpart
         if (j > 0) qt_syrk(img, s, lane);
-        double* wsg = ws + (long long)j * Q::WS_GROUP;
-        const double yj = qt_cholesky(s, rpart, img, wsg, stash, lane);
+        const double yj = qt_cholesky(s, rpart, img, QT_WSG(j), cx.sm + Q::oMISC, lane);
         if (act) {
             sY[lane] = yj;
-            wsg[Q::fY + lane] = yj;
+            QT_WSG(j)[Q::fY + lane] = yj;
         }
-        sb.wait();
-        abuf.wait();
+        cx.wait_small(1);
+        cx.wait(2);
         {   // coupling rows of group j+1: (V P^-1 U^T) row, solved against L_j, parked in the image
             double e[G];
-            const double carry = qt_vpu(abuf.buf, sb.buf, sa.buf, LN, e);
+            const QtLane LN(lane);
+            const double carry = qt_vpu(cx.ab(), cx.small(1), cx.small(0), LN, e);
             qt_trsm(e, img);
             __syncwarp();
             rpart = qt_store_coupling(e, img, sY, lane) - carry;  // -Lo y_j - V t_j
         }
-        qt_vpv<true>(abuf.buf, sb.buf, sa.buf, LN, s);  // S_{j+1,j+1} part: V P^-1 V^T row
-        gdef = st ? sa.buf[QK::oG + lane] : 0.0;        // defect of stage j: the state rows of group j+1
+        {
+            const QtLane LN(lane);
+            qt_vpv<true>(cx.ab(), cx.small(1), cx.small(0), LN, s);  // S_{j+1,j+1} part: V P^-1 V^T row
+        }
+        gdef = st ? cx.small(0)[QK::oG + lane] : 0.0;  // defect of stage j: the state rows of group j+1
         __syncwarp();
-        swap_bufs();  // sa = small_{j+1}
+        cx.swap();  // a = small_{j+1}
         if (j + 1 < m) {
-            sb.load(chunk(j + 2), SMALL_B, lane);
-            abuf.load(chunk(j + 1) + QK::oAQ, APART_B, lane);
+            cx.load_small(1, QT_CHUNK(j + 2));
+            cx.load_ab(QT_CHUNK(j + 1));
         }
     }
     // ---- middle group m: top part S = V P^-1 V^T - Lo Lo^T, rhs = defect - V t - Lo y
     qt_syrk(img, s, lane);
-    rpart += st ? gdef : 0.0;
+    rpart += gdef;
     __syncthreads();  // the bottom warp has parked its part of S_mm and of the right-hand side in its image
     if (act) {
-        const double* mine = other_img + lane * LS;
+        const double* mine = cx.sm + Q::PER_WARP + Q::oLO + lane * LS;
 #pragma unroll
         for (int c = 0; c + 1 < G; c += 2) { const double2 t2 = qp_ld2(mine + c); s[c] += t2.x; s[c + 1] += t2.y; }
         const double2 t2 = qp_ld2(mine + G - 1);
@@ -758,122 +792,115 @@ __device__ __noinline__ void qt_top_chain(const QtArgs a, int lane, int wib, uns
         rpart += t2.y;
     }
     {
-        double* wsg = ws + (long long)m * Q::WS_GROUP;
-        const double ym = qt_cholesky(s, rpart, img, wsg, stash, lane);
+        const double ym = qt_cholesky(s, rpart, img, QT_WSG(m), cx.sm + Q::oMISC, lane);
         if (act) img[Q::fY + lane] = ym;
         __syncwarp();
         const double num = qt_outward_solve(img, 0.0, lane);  // nu_m = L^-T y_m
         __syncwarp();
         sY[lane] = num;
-        other_y[lane] = num;
-        if (mult && act) {
-            if (st) mult[13 * m + lane] = num;
-            else mult[nX + 16 * m + (lane - 13)] = num;
-        }
+        cx.sm[Q::PER_WARP + Q::oY + lane] = num;
+        qt_store_mult(smem_raw, num, m, lane);
     }
     __syncthreads();  // nu_m is visible to the bottom warp
 
     // ======================================================== outward: groups m-1 .. 0
+    // the factor images in the workspace were written through the generic proxy and come back through the async proxy (TMA)
+    asm volatile("fence.proxy.async.global;" ::: "memory");
+    __syncwarp();
     double* const vA = img + Q::oVA;
     double* const vC = img + Q::oVC;
-    sb.load(chunk(m), SMALL_B, lane);  // Cp_m
-    sb.wait();
+    cx.load_small(1, QT_CHUNK(m));  // Cp_m
+    cx.wait_small(1);
     for (int j = m - 1; j >= 0; --j) {
-        sa.load(chunk(j), SMALL_B, lane);
-        abuf.load(chunk(j) + QK::oAQ, APART_B, lane);
-        lbuf.load(ws + (long long)j * Q::WS_GROUP, WS_B, lane);
-        sa.wait();
-        abuf.wait();
-        qt_pinv_t(sa.buf, lane, true);
-        for (int k = lane; k < 37; k += 32) vA[k] = qt_vT_nu(abuf.buf, sb.buf, sY, k);  // a = V_j^T nu_{j+1}
+        cx.load_small(0, QT_CHUNK(j));
+        cx.load_ab(QT_CHUNK(j));
+        cx.load_factor(QT_WSG(j));
+        cx.wait_small(0);
+        cx.wait(2);
+        qt_pinv_t(cx.small(0), lane, true);
+        for (int k = lane; k < 37; k += 32) vA[k] = qt_vT_nu(cx.ab(), cx.small(1), sY, k);  // a = V_j^T nu_{j+1}
         __syncwarp();
-        qt_apply_pinv(sa.buf, vA, vC, lane);
-        QtU u;
-        qt_load_u(sa.buf, lane, LN, u);
-        const double z = qt_u_dot(u, vC);  // (U P^-1 a) row
-        lbuf.wait();
+        qt_apply_pinv(cx.small(0), vA, vC, lane);
+        double z;
+        {
+            const QtLane LN(lane);
+            QtU u;
+            qt_load_u(cx.small(0), lane, LN, u);
+            z = qt_u_dot(u, vC);  // (U P^-1 a) row
+        }
+        cx.wait(3);
         const double nu = qt_outward_solve(img, z, lane);
         __syncwarp();
         sY[lane] = nu;
         __syncwarp();
-        for (int k = lane; k < 37; k += 32) vA[k] += qt_uT_nu(sa.buf, sY, k);
+        for (int k = lane; k < 37; k += 32) vA[k] += qt_uT_nu(cx.small(0), sY, k);
         __syncwarp();
-        qt_apply_pinv(sa.buf, vA, vC, lane);
-        for (int k = lane; k < 37; k += 32) {
-            const long long dst = k < 13 ? 13 * j + k : nX + 24 * j + (k - 13);
-            step[dst] = -(sa.buf[QK::oQ + k] + vC[k]);  // d_j = -(t_j + P^-1 (a + U^T nu_j))
-        }
-        if (mult && act) {
-            if (st) mult[13 * j + lane] = nu;
-            else mult[nX + 16 * j + (lane - 13)] = nu;
-        }
+        qt_apply_pinv(cx.small(0), vA, vC, lane);
+        qt_store_step(smem_raw, cx.small(0), vC, j, lane);
+        qt_store_mult(smem_raw, nu, j, lane);
         __syncwarp();
-        swap_bufs();  // sb = small_j: group j-1 needs its Cp rows
+        cx.swap();  // b = small_j: group j-1 needs its Cp rows
     }
 }
 
-__device__ __noinline__ void qt_bottom_chain(const QtArgs a, int lane, int wib, unsigned char* smem_raw) {
-    QT_COMMON;
+__device__ __noinline__ void qt_bottom_chain(int lane, unsigned char* smem_raw) {
+    using Q = QpT;
+    constexpr int G = Q::G, LS = Q::LS;
+    QtCtx cx{reinterpret_cast<double*>(smem_raw) + Q::PER_WARP, lane, 0, 0u};
+    double* const img = cx.sm + Q::oLO;
+    double* const sY  = cx.sm + Q::oY;
+    const int N = QT_ARGS.N, m = N / 2;
+    const bool act = lane < G, st = lane < 13;
+    double s[G];
+    double rpart = 0.0;
     // ======================================================== bottom-up: groups N .. m+1
-    // sa = small_j (synthesised for j = N: no inputs, no contact rows), sb = small_{j-1}, abuf = A_{j-1}
-    for (int k = lane; k < QK::SMALL; k += 32) sa.buf[k] = 0.0;
+    // a = small_j (synthesised for j = N: no inputs, no contact rows), b = small_{j-1}, A_{j-1}
+    for (int k = lane; k < QK::SMALL; k += 32) cx.small(0)[k] = 0.0;
     __syncwarp();
     if (st) {
-        sa.buf[QK::oQ + lane]  = tail[QK::tQN + lane];
-        sa.buf[QK::oHd + lane] = tail[QK::tHN + lane];
+        const double* tail = QT_ARGS.rec + QK::tail(N);
+        cx.small(0)[QK::oQ + lane]  = tail[QK::tQN + lane];
+        cx.small(0)[QK::oHd + lane] = tail[QK::tHN + lane];
     }
     __syncwarp();
-    sb.load(chunk(N - 1), SMALL_B, lane);
-    abuf.load(chunk(N - 1) + QK::oAQ, APART_B, lane);
-    qt_pinv_t(sa.buf, lane, false);
+    cx.load_small(1, QT_CHUNK(N - 1));
+    cx.load_ab(QT_CHUNK(N - 1));
+    qt_pinv_t(cx.small(0), lane, false);
     for (int j = N; j > m; --j) {
-        {   // S_jj = U P^-1 U^T + delta I ;  rhs = contact values - U t + rpart   (group N: the synthesised chunk has null contact rows)
-            QtU u;
-            qt_load_u(sa.buf, lane, LN, u);
-            rpart += (!st && act ? sa.buf[QK::oG + lane] : 0.0) - qt_u_dot(u, sa.buf + QK::oQ);
-            qt_u_pinv(u, sa.buf);
-#pragma unroll
-            for (int c = 0; c < G; ++c) s[c] = c == lane ? delta : 0.0;
-            qt_u_dot_u_rows(u, sa.buf, s);
-        }
+        rpart += qt_upu<true>(cx.small(0), lane, QT_ARGS.delta, s);  // S_jj = U P^-1 U^T + delta I ;  rhs = contact values - U t + rpart
         if (j < N) qt_syrk(img, s, lane);
-        sb.wait();
-        abuf.wait();
-        qt_pinv_t(sb.buf, lane, true);
-        rpart += st ? sb.buf[QK::oG + lane] : 0.0;                     // defect of stage j-1
-        rpart -= qt_vpv<false>(abuf.buf, sa.buf, sb.buf, LN, s);       // S_jj += V P^-1 V^T ;  rhs -= V t_{j-1}
-        double* wsg = ws + (long long)j * Q::WS_GROUP;
-        const double yj = qt_cholesky(s, rpart, img, wsg, stash, lane);
+        cx.wait_small(1);
+        cx.wait(2);
+        qt_pinv_t(cx.small(1), lane, true);
+        rpart += st ? cx.small(1)[QK::oG + lane] : 0.0;  // defect of stage j-1
+        {
+            const QtLane LN(lane);
+            rpart -= qt_vpv<false>(cx.ab(), cx.small(0), cx.small(1), LN, s);  // S_jj += V P^-1 V^T ;  rhs -= V t_{j-1}
+        }
+        const double yj = qt_cholesky(s, rpart, img, QT_WSG(j), cx.sm + Q::oMISC, lane);
         if (act) {
             sY[lane] = yj;
-            wsg[Q::fY + lane] = yj;
+            QT_WSG(j)[Q::fY + lane] = yj;
         }
         {   // coupling rows of group j-1: (U_{j-1} P^-1 V^T) row, solved against M_j, parked in the image
             double e[G];
+            const QtLane LN(lane);
             QtU u;
-            qt_load_u(sb.buf, lane, LN, u);
-            qt_u_pinv(u, sb.buf);
-            qt_u_dot_v_rows(u, abuf.buf, sa.buf, e);
+            qt_load_u(cx.small(1), lane, LN, u);
+            qt_u_pinv(u, cx.small(1));
+            qt_u_dot_v_rows(u, cx.ab(), cx.small(0), e);
             __syncwarp();
-            if (j - 2 >= m) abuf.load(chunk(j - 2) + QK::oAQ, APART_B, lane);
+            if (j - 2 >= m) cx.load_ab(QT_CHUNK(j - 2));
             qt_trsm(e, img);
             __syncwarp();
             rpart = qt_store_coupling(e, img, sY, lane);  // -Uo y_j
         }
         __syncwarp();
-        swap_bufs();  // sa = small_{j-1} (P^-1 and t already in place)
-        if (j - 2 >= m) sb.load(chunk(j - 2), SMALL_B, lane);
+        cx.swap();  // a = small_{j-1} (P^-1 and t already in place)
+        if (j - 2 >= m) cx.load_small(1, QT_CHUNK(j - 2));
     }
-    // ---- middle group m, bottom part: U P^-1 U^T + delta I - Uo Uo^T ; rhs = contact values - U t - Uo y   (sa = small_m)
-    {
-        QtU u;
-        qt_load_u(sa.buf, lane, LN, u);
-        rpart += (!st && act ? sa.buf[QK::oG + lane] : 0.0) - qt_u_dot(u, sa.buf + QK::oQ);
-        qt_u_pinv(u, sa.buf);
-#pragma unroll
-        for (int c = 0; c < G; ++c) s[c] = c == lane ? delta : 0.0;
-        qt_u_dot_u_rows(u, sa.buf, s);
-    }
+    // ---- middle group m, bottom part: U P^-1 U^T + delta I - Uo Uo^T ; rhs = contact values - U t - Uo y   (a = small_m)
+    rpart += qt_upu<true>(cx.small(0), lane, QT_ARGS.delta, s);
     qt_syrk(img, s, lane);
     if (act) {
 #pragma unroll
@@ -884,55 +911,60 @@ __device__ __noinline__ void qt_bottom_chain(const QtArgs a, int lane, int wib, 
     __syncthreads();  // nu_m has arrived in sY
 
     // ======================================================== outward: groups m+1 .. N (and the steps d_m .. d_N)
-    // invariant at group j: sa = small_{j-1} (P^-1, t in place), abuf = A_{j-1}, sY = nu_{j-1}
+    // invariant at group j: a = small_{j-1} (P^-1, t in place), A_{j-1} landed, sY = nu_{j-1}
+    asm volatile("fence.proxy.async.global;" ::: "memory");  // factor images: generic-proxy stores, async-proxy (TMA) loads
+    __syncwarp();
     double* const vA = img + Q::oVA;
     double* const vC = img + Q::oVC;
     double* const nu2 = img + Q::oNU2;
-    abuf.load(chunk(m) + QK::oAQ, APART_B, lane);
-    abuf.wait();
+    cx.load_ab(QT_CHUNK(m));
+    cx.wait(2);
     for (int j = m + 1; j <= N; ++j) {
         const bool last = j == N;
-        lbuf.load(ws + (long long)j * Q::WS_GROUP, WS_B, lane);
+        cx.load_factor(QT_WSG(j));
         if (!last) {
-            sb.load(chunk(j), SMALL_B, lane);
-            sb.wait();
+            cx.load_small(1, QT_CHUNK(j));
+            cx.wait_small(1);
         } else {
-            for (int k = lane; k < 96; k += 32) sb.buf[QK::oCp + k] = 0.0;  // group N has no contact rows
+            for (int k = lane; k < 96; k += 32) cx.small(1)[QK::oCp + k] = 0.0;  // group N has no contact rows
             __syncwarp();
         }
-        for (int k = lane; k < 37; k += 32) vA[k] = qt_uT_nu(sa.buf, sY, k);  // b = U_{j-1}^T nu_{j-1}
+        for (int k = lane; k < 37; k += 32) vA[k] = qt_uT_nu(cx.small(0), sY, k);  // b = U_{j-1}^T nu_{j-1}
         __syncwarp();
-        qt_apply_pinv(sa.buf, vA, vC, lane);
-        const double z = qt_v_dot(abuf.buf, sb.buf, LN, vC);  // (V_{j-1} P^-1 b) row
-        lbuf.wait();
+        qt_apply_pinv(cx.small(0), vA, vC, lane);
+        double z;
+        {
+            const QtLane LN(lane);
+            z = qt_v_dot(cx.ab(), cx.small(1), LN, vC);  // (V_{j-1} P^-1 b) row
+        }
+        cx.wait(3);
         const double nu = qt_outward_solve(img, z, lane);
         __syncwarp();
         nu2[lane] = nu;
         __syncwarp();
-        for (int k = lane; k < 37; k += 32) vA[k] += qt_vT_nu(abuf.buf, sb.buf, nu2, k);
+        for (int k = lane; k < 37; k += 32) vA[k] += qt_vT_nu(cx.ab(), cx.small(1), nu2, k);
         __syncwarp();
-        qt_apply_pinv(sa.buf, vA, vC, lane);
-        for (int k = lane; k < 37; k += 32) {
-            const long long dst = k < 13 ? 13 * (j - 1) + k : nX + 24 * (j - 1) + (k - 13);
-            step[dst] = -(sa.buf[QK::oQ + k] + vC[k]);  // d_{j-1}
-        }
-        if (mult && act) {
-            if (st) mult[13 * j + lane] = nu;
-            else if (!last) mult[nX + 16 * j + (lane - 13)] = nu;
-        }
+        qt_apply_pinv(cx.small(0), vA, vC, lane);
+        qt_store_step(smem_raw, cx.small(0), vC, j - 1, lane);  // d_{j-1}
+        qt_store_mult(smem_raw, nu, j, lane);
         sY[lane] = nu;
         __syncwarp();
         if (!last) {
-            swap_bufs();  // sa = small_j
-            qt_pinv_t(sa.buf, lane, true);
-            abuf.load(chunk(j) + QK::oAQ, APART_B, lane);
-            abuf.wait();
+            cx.swap();  // a = small_j
+            qt_pinv_t(cx.small(0), lane, true);
+            cx.load_ab(QT_CHUNK(j));
+            cx.wait(2);
         }
     }
     // d_N = -P_N^-1 (q_N + nu_N)
-    if (st) step[13 * N + lane] = -(tail[QK::tQN + lane] + sY[lane]) / tail[QK::tHN + lane];
+    if (st) {
+        const double* tail = QT_ARGS.rec + QK::tail(N);
+        QT_ARGS.step[13 * N + lane] = -(tail[QK::tQN + lane] + sY[lane]) / tail[QK::tHN + lane];
+    }
 }
-#undef QT_COMMON
+#undef QT_ARGS
+#undef QT_CHUNK
+#undef QT_WSG
 
 __global__ void __launch_bounds__(64, 7)
 qp_twisted_kernel(const double* __restrict__ rec_all, long long ld_rec, double* __restrict__ ws_all, double* __restrict__ step_all, long long ld_step,
@@ -946,12 +978,14 @@ qp_twisted_kernel(const double* __restrict__ rec_all, long long ld_rec, double* 
         uint64_t* const bars = reinterpret_cast<uint64_t*>(reinterpret_cast<double*>(smem_raw) + wib * QpT::PER_WARP + QpT::oBAR);
         if (lane < 4) qt_bar_init(bars + lane);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-        __syncwarp();
+        if (threadIdx.x == 0)
+            *reinterpret_cast<QtArgs*>(reinterpret_cast<double*>(smem_raw) + 2 * QpT::PER_WARP) =
+                QtArgs{rec_all + b * ld_rec, ws_all + b * (long long)(N + 1) * QpT::WS_GROUP, step_all + b * ld_step,
+                       mult_all ? mult_all + b * ld_mult : nullptr, N, delta};
     }
-    const QtArgs a{rec_all + b * ld_rec, ws_all + b * (long long)(N + 1) * QpT::WS_GROUP, step_all + b * ld_step,
-                   mult_all ? mult_all + b * ld_mult : nullptr, N, delta};
-    if (wib == 0) qt_top_chain(a, lane, wib, smem_raw);
-    else qt_bottom_chain(a, lane, wib, smem_raw);
+    __syncthreads();
+    if (wib == 0) qt_top_chain(lane, smem_raw);
+    else qt_bottom_chain(lane, smem_raw);
 }
 
 }  // namespace ub
