@@ -28,3 +28,10 @@ def timed(fn, reps=20):
 
 print("kkt_blocks 1024 x N=100: %.3f ms" % timed(lambda: m.kkt_blocks(xp, rec)))
 print("qp_solve   1024 x N=100: %.3f ms" % timed(lambda: m.qp_solve(rec, steps, mult)))
+
+mc = ungar_b200.Model("quadruped", 100, dtype="f64", barrier=(1.0, 1.0), record_format="compact")
+recc = mc.kkt_blocks(xp)
+sc, mu = mc.qp_solve(recc)
+torch.cuda.synchronize()
+print("compact kkt_blocks 1024 x N=100: %.3f ms" % timed(lambda: mc.kkt_blocks(xp, recc)))
+print("compact qp_solve   1024 x N=100: %.3f ms" % timed(lambda: mc.qp_solve(recc, sc, mu)))

@@ -10,7 +10,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
 LIB = os.path.join(HERE, "libungar_b200.so")
 SOURCES = [os.path.join(HERE, "csrc", f) for f in ("ungar_b200.cu", "tape.cu", "kkt_dense.cu")]
-HEADERS = [os.path.join(HERE, "csrc", f) for f in ("dual.cuh", "models.cuh", "sweep.cuh", "sweep_structured.cuh", "sweep_tpn.cuh", "sweep_small.cuh", "qp_schur.cuh", "qp_twisted.cuh", "compact.cuh", "qp_riccati.cuh", "line_search.cuh", "tape_machine.cuh", "abi_internal.h")] + [
+HEADERS = [os.path.join(HERE, "csrc", f) for f in ("dual.cuh", "models.cuh", "sweep.cuh", "sweep_structured.cuh", "sweep_structured_compact.cuh", "sweep_tpn.cuh", "sweep_small.cuh", "qp_schur.cuh", "qp_twisted.cuh", "compact.cuh", "qp_riccati.cuh", "line_search.cuh", "tape_machine.cuh", "abi_internal.h")] + [
     os.path.join(ROOT, "include", "ungar_b200.h")]
 
 NVCC_FLAGS = [

@@ -15,6 +15,7 @@
 #include "../../include/ungar_b200.h"
 #include "sweep.cuh"
 #include "sweep_structured.cuh"
+#include "sweep_structured_compact.cuh"
 #include "sweep_tpn.cuh"
 #include "sweep_small.cuh"
 #include "qp_schur.cuh"
@@ -398,6 +399,49 @@ int launch_structured(ungar_b200_model& mdl, const double* xp, int64_t batch, in
     return UNGAR_B200_OK;
 }
 
+// Structured quadruped fp64 sweep writing the COMPACT record (sweep_structured_compact.cuh): any horizon; the record must be
+// 16-byte aligned with an even stride (one TMA bulk store per node).
+template <bool BARRIER>
+int launch_structured_compact(ungar_b200_model& mdl, const double* xp, int64_t batch, int64_t ld_xp, double* rec, int64_t ld_rec,
+                              cudaStream_t stream) {
+    using Q = ub::QuadrupedCompactSweep;
+    auto kernel = ub::quadruped_compact_kernel<BARRIER>;
+    static PerDevice configured, sm_counts;
+    if (!configured[mdl.desc.device]) {
+        UB_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, Q::SMEM_BYTES));
+        UB_CUDA(cudaDeviceGetAttribute(&sm_counts[mdl.desc.device], cudaDevAttrMultiProcessorCount, mdl.desc.device));
+        configured[mdl.desc.device] = 1;
+    }
+    if ((reinterpret_cast<uintptr_t>(rec) & 15) != 0 || (ld_rec & 1) != 0)
+        return fail(UNGAR_B200_EINVAL, "compact records must be 16-byte aligned with an even stride (TMA bulk stores)");
+    const int sm_count = sm_counts[mdl.desc.device];
+    const int runs_per_traj = (mdl.N + 9) / 10;
+    const int run_len       = 2 * ((mdl.N + 2 * runs_per_traj - 1) / (2 * runs_per_traj));
+    const long long total_runs = (long long)batch * runs_per_traj;
+    const unsigned grid = unsigned(std::min<long long>(total_runs, (long long)sm_count * 6));  // persistent: 6 teams / SM
+    if (int rc = ensure_sched(mdl, stream)) return rc;
+    int slot = -1;
+    if (g_ring.enabled) {
+        slot = g_ring.head;
+        if (!g_ring.created[slot]) {
+            UB_CUDA(cudaEventCreate(&g_ring.start[slot]));
+            UB_CUDA(cudaEventCreate(&g_ring.stop[slot]));
+            g_ring.created[slot] = true;
+        }
+        UB_CUDA(cudaEventRecord(g_ring.start[slot], stream));
+    }
+    kernel<<<grid, Q::WARPS * 32, Q::SMEM_BYTES, stream>>>(xp, ld_xp, rec, ld_rec, static_cast<double*>(mdl.stage_cost.ptr), mdl.N, run_len,
+                                                           runs_per_traj, total_runs, mdl.bar, static_cast<unsigned int*>(mdl.sched.ptr));
+    if (slot >= 0) {
+        UB_CUDA(cudaEventRecord(g_ring.stop[slot], stream));
+        g_ring.head  = (g_ring.head + 1) % kRing;
+        g_ring.count = g_ring.count < kRing ? g_ring.count + 1 : kRing;
+    }
+    ++g_launches;
+    UB_CUDA(cudaGetLastError());
+    return UNGAR_B200_OK;
+}
+
 // Thread-per-node sweep (sweep_tpn.cuh) for the models without contact rows; one CTA per trajectory, persistent.
 template <class Mdl, class T>
 bool tpn_applicable(const ungar_b200_model& mdl) {
@@ -514,19 +558,27 @@ int launch_tpn(ungar_b200_model& mdl, const T* xp, int64_t batch, int64_t ld_xp,
 
 template <class Mdl, class T, int M>
 int launch_sweep_t(ungar_b200_model& mdl, const void* xp, int64_t batch, int64_t ld_xp, void* rec, int64_t ld_rec,
-                   int mode, void* summaries, cudaStream_t stream) {
+                   int mode, void* summaries, cudaStream_t stream, bool compact_out) {
     int entries = mdl.N + 1;  // partial entries per trajectory (generic sweep: one per node)
     if (int rc = mdl.stage_cost.reserve(size_t(batch) * (mdl.N + 1) * 4 * sizeof(T))) return rc;
     const T* x = static_cast<const T*>(xp);
     T* r       = static_cast<T*>(rec);
     int rc;
-    if (mode == MODE_JH) {
+    if (mode == MODE_JH && !compact_out) {
         rc = ub::launch_jh<Mdl, T>(x, batch, ld_xp, r, ld_rec, mdl.N, mdl.rl, stream);
         if (rc == 0) ++g_launches;
         else return fail(UNGAR_B200_ECUDA, "J_h kernel launch failed: %s", cudaGetErrorString(cudaError_t(rc)));
         return UNGAR_B200_OK;
     }
-    if constexpr (std::is_same<Mdl, ub::Quadruped>::value && std::is_same<T, double>::value) {
+    if (compact_out) {
+        if constexpr (std::is_same<Mdl, ub::Quadruped>::value && std::is_same<T, double>::value) {
+            if (mode == MODE_JH) return fail(UNGAR_B200_EINVAL, "internal: J_h is served from dense records");
+            entries = 2 * ((mdl.N + 9) / 10);
+            rc = mode == MODE_KKT ? launch_structured_compact<true>(mdl, x, batch, ld_xp, r, ld_rec, stream)
+                                  : launch_structured_compact<false>(mdl, x, batch, ld_xp, r, ld_rec, stream);
+        } else
+            return fail(UNGAR_B200_EUNSUPPORTED, "compact records exist for the quadruped in F64 only");
+    } else if constexpr (std::is_same<Mdl, ub::Quadruped>::value && std::is_same<T, double>::value) {
         if (structured_applicable(mdl, rec, ld_rec)) {
             entries = 2 * ((mdl.N + 9) / 10);  // structured sweep: one per (run, warp)
             rc = mode == MODE_KKT ? launch_structured<true>(mdl, x, batch, ld_xp, r, ld_rec, stream)
@@ -554,7 +606,8 @@ int launch_sweep_t(ungar_b200_model& mdl, const void* xp, int64_t batch, int64_t
     const ungar_b200_kkt_layout& L = mdl.layout;
     const int threads = 128;  // 4 trajectories per CTA
     ub::finalize_kernel<T><<<unsigned((batch * 32 + threads - 1) / threads), threads, 0, stream>>>(
-        static_cast<const T*>(mdl.stage_cost.ptr), entries, x, ld_xp, r, ld_rec, static_cast<T*>(summaries), mdl.rl.cost,
+        static_cast<const T*>(mdl.stage_cost.ptr), entries, x, ld_xp, r, ld_rec, static_cast<T*>(summaries),
+        compact_out ? int(ub::Compact::tail(mdl.N) + ub::Compact::tCost) : mdl.rl.cost,
         int(L.nx * (L.horizon + 1)), int(L.nu), int(L.nx), int(Mdl::xm_off(mdl.N)), batch);
     ++g_launches;
     UB_CUDA(cudaGetLastError());
@@ -562,18 +615,18 @@ int launch_sweep_t(ungar_b200_model& mdl, const void* xp, int64_t batch, int64_t
 }
 
 int launch_sweep(ungar_b200_model& mdl, const void* xp, int64_t batch, int64_t ld_xp, void* rec, int64_t ld_rec,
-                 int mode, void* summaries, cudaStream_t stream) {
+                 int mode, void* summaries, cudaStream_t stream, bool compact_out = false) {
     const bool f64 = mdl.desc.dtype == UNGAR_B200_F64;
     switch (mdl.desc.kind) {
         case UNGAR_B200_QUADROTOR:
-            return f64 ? launch_sweep_t<ub::Quadrotor, double, 15>(mdl, xp, batch, ld_xp, rec, ld_rec, mode, summaries, stream)
-                       : launch_sweep_t<ub::Quadrotor, float, 15>(mdl, xp, batch, ld_xp, rec, ld_rec, mode, summaries, stream);
+            return f64 ? launch_sweep_t<ub::Quadrotor, double, 15>(mdl, xp, batch, ld_xp, rec, ld_rec, mode, summaries, stream, compact_out)
+                       : launch_sweep_t<ub::Quadrotor, float, 15>(mdl, xp, batch, ld_xp, rec, ld_rec, mode, summaries, stream, compact_out);
         case UNGAR_B200_RC_CAR:
-            return f64 ? launch_sweep_t<ub::RcCar, double, 30>(mdl, xp, batch, ld_xp, rec, ld_rec, mode, summaries, stream)
-                       : launch_sweep_t<ub::RcCar, float, 30>(mdl, xp, batch, ld_xp, rec, ld_rec, mode, summaries, stream);
+            return f64 ? launch_sweep_t<ub::RcCar, double, 30>(mdl, xp, batch, ld_xp, rec, ld_rec, mode, summaries, stream, compact_out)
+                       : launch_sweep_t<ub::RcCar, float, 30>(mdl, xp, batch, ld_xp, rec, ld_rec, mode, summaries, stream, compact_out);
         case UNGAR_B200_QUADRUPED:
-            return f64 ? launch_sweep_t<ub::Quadruped, double, 4>(mdl, xp, batch, ld_xp, rec, ld_rec, mode, summaries, stream)
-                       : launch_sweep_t<ub::Quadruped, float, 4>(mdl, xp, batch, ld_xp, rec, ld_rec, mode, summaries, stream);
+            return f64 ? launch_sweep_t<ub::Quadruped, double, 4>(mdl, xp, batch, ld_xp, rec, ld_rec, mode, summaries, stream, compact_out)
+                       : launch_sweep_t<ub::Quadruped, float, 4>(mdl, xp, batch, ld_xp, rec, ld_rec, mode, summaries, stream, compact_out);
     }
     return fail(UNGAR_B200_EINVAL, "unknown model kind %d", mdl.desc.kind);
 }
@@ -763,12 +816,13 @@ int reference_call(ungar_b200_model* mdl, int32_t function, int want, const void
         rc = mdl->desc.dtype == UNGAR_B200_F64 ? launch_barrier_t<double>(*mdl, d_xp, d_ld_xp, d_out, d_ld_out, batch, want, stream)
                                                : launch_barrier_t<float>(*mdl, d_xp, d_ld_xp, d_out, d_ld_out, batch, want, stream);
     } else {
-        if ((rc = mdl->ws_records.reserve(size_t(batch) * mdl->layout.size * es))) return rc;
+        // the reference-format calls are served from a DENSE internal record whatever the handle's record format is
+        if ((rc = mdl->ws_dense.reserve(size_t(batch) * mdl->dense_size * es))) return rc;
         const int mode = (function == UNGAR_B200_INEQUALITIES && want == WANT_JAC) ? MODE_JH : MODE_PLAIN;
-        rc = launch_sweep(*mdl, d_xp, batch, d_ld_xp, mdl->ws_records.ptr, mdl->layout.size, mode, nullptr, stream);
+        rc = launch_sweep(*mdl, d_xp, batch, d_ld_xp, mdl->ws_dense.ptr, mdl->dense_size, mode, nullptr, stream, false);
         if (rc) return rc;
         const int32_t* src = want == WANT_Y ? F.d_y_src : want == WANT_JAC ? F.d_jac_src : F.d_hes_src;
-        rc = launch_gather(*mdl, mdl->ws_records.ptr, mdl->layout.size, src, n_out, d_out, d_ld_out, batch, stream);
+        rc = launch_gather(*mdl, mdl->ws_dense.ptr, mdl->dense_size, src, n_out, d_out, d_ld_out, batch, stream);
     }
     if (rc) return rc;
     if (mem == UNGAR_B200_MEM_HOST) {
@@ -938,12 +992,12 @@ static int blocks_call(ungar_b200_model* model, const void* xp, int64_t batch, i
     UB_CUDA(cudaSetDevice(model->desc.device));
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
     const size_t es = model->elem;
-    if (mem == UNGAR_B200_MEM_DEVICE) return launch_sweep(*model, xp, batch, ld_xp, records, ld_rec, mode, nullptr, stream);
+    if (mem == UNGAR_B200_MEM_DEVICE) return launch_sweep(*model, xp, batch, ld_xp, records, ld_rec, mode, nullptr, stream, model->compact);
 
     if (int rc = model->ws_xp.reserve(size_t(batch) * n_in * es)) return rc;
     if (int rc = model->ws_records.reserve(size_t(batch) * L.size * es)) return rc;
     UB_CUDA(cudaMemcpy2DAsync(model->ws_xp.ptr, n_in * es, xp, ld_xp * es, n_in * es, batch, cudaMemcpyHostToDevice, stream));
-    if (int rc = launch_sweep(*model, model->ws_xp.ptr, batch, n_in, model->ws_records.ptr, L.size, mode, nullptr, stream)) return rc;
+    if (int rc = launch_sweep(*model, model->ws_xp.ptr, batch, n_in, model->ws_records.ptr, L.size, mode, nullptr, stream, model->compact)) return rc;
     UB_CUDA(cudaMemcpy2DAsync(records, ld_rec * es, model->ws_records.ptr, L.size * es, L.size * es, batch,
                               cudaMemcpyDeviceToHost, stream));
     UB_CUDA(cudaStreamSynchronize(stream));
@@ -1022,7 +1076,10 @@ int ungar_b200_sqp_solve(ungar_b200_model* model, void* xp, int64_t batch, int64
     UB_CUDA(cudaSetDevice(model->desc.device));
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
     const size_t es = sizeof(double);
-    if (int rc = model->ws_records.reserve(size_t(batch) * L.size * es)) return rc;
+    // the records never leave the device here: the quadruped loop runs on the compact format whatever the handle's format is
+    const bool crec = model->desc.kind == UNGAR_B200_QUADRUPED;
+    const int64_t rsize = crec ? ub::Compact::size(model->N) : model->dense_size;
+    if (int rc = model->ws_records.reserve(size_t(batch) * rsize * es)) return rc;
     if (int rc = model->ws_steps.reserve(size_t(batch) * L.n_dec * es)) return rc;
     double* d_xp    = static_cast<double*>(xp);
     int64_t d_ld_xp = ld_xp;
@@ -1043,8 +1100,8 @@ int ungar_b200_sqp_solve(ungar_b200_model* model, void* xp, int64_t batch, int64
     if (d_info) UB_CUDA(cudaMemsetAsync(d_info, 0, size_t(batch) * UNGAR_B200_LINE_SEARCH_INFO_SIZE * es, stream));
     for (int it = 0; it < options->max_iterations; ++it) {
         // AssembleOSQPInstance -> Solve -> BacktrackingLineSearch::Do (soft_sqp.hpp:76-99), stream-ordered
-        if (int rc = launch_sweep(*model, d_xp, batch, d_ld_xp, model->ws_records.ptr, L.size, MODE_KKT, nullptr, stream)) return rc;
-        if (int rc = launch_qp(*model, model->ws_records.ptr, false, batch, L.size, model->ws_steps.ptr, L.n_dec, nullptr, 0, d_status, stream)) return rc;
+        if (int rc = launch_sweep(*model, d_xp, batch, d_ld_xp, model->ws_records.ptr, rsize, MODE_KKT, nullptr, stream, crec)) return rc;
+        if (int rc = launch_qp(*model, model->ws_records.ptr, crec, batch, rsize, model->ws_steps.ptr, L.n_dec, nullptr, 0, d_status, stream)) return rc;
         if (int rc = launch_line_search(*model, d_xp, batch, d_ld_xp, static_cast<const double*>(model->ws_steps.ptr), L.n_dec, *options,
                                         d_status, d_info, stream)) return rc;
     }
@@ -1125,13 +1182,13 @@ int ungar_b200_kkt_step(ungar_b200_model* model, const void* xp, int64_t batch, 
                 UB_CUDA(cudaStreamWaitEvent(stream, model->ev_chunk[c], 0));
             }
             if (int rc = launch_sweep(*model, w_xp + size_t(b0) * n_in * es, nb, n_in, static_cast<char*>(records_device) + size_t(b0) * ld_rec * es,
-                                      ld_rec, MODE_KKT, w_sum + size_t(b0) * UNGAR_B200_SUMMARY_SIZE * es, stream)) return rc;
+                                      ld_rec, MODE_KKT, w_sum + size_t(b0) * UNGAR_B200_SUMMARY_SIZE * es, stream, model->compact)) return rc;
         }
         UB_CUDA(cudaMemcpyAsync(summaries, w_sum, size_t(batch) * UNGAR_B200_SUMMARY_SIZE * es, cudaMemcpyDeviceToHost, stream));
         UB_CUDA(cudaStreamSynchronize(stream));
         return UNGAR_B200_OK;
     }
-    return launch_sweep(*model, xp, batch, ld_xp, records_device, ld_rec, MODE_KKT, summaries, stream);
+    return launch_sweep(*model, xp, batch, ld_xp, records_device, ld_rec, MODE_KKT, summaries, stream, model->compact);
 }
 
 int ungar_b200_summaries(ungar_b200_model* model, const void* xp, int64_t batch, int64_t ld_xp, const void* records,
@@ -1142,7 +1199,10 @@ int ungar_b200_summaries(ungar_b200_model* model, const void* xp, int64_t batch,
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
     const ungar_b200_kkt_layout& L = model->layout;
     const int u0 = int(L.nx * (L.horizon + 1));
-    if (model->desc.dtype == UNGAR_B200_F64)
+    if (model->compact)
+        ub::summary_compact_kernel<<<unsigned(batch), 32, 0, stream>>>(static_cast<const double*>(xp), ld_xp, static_cast<const double*>(records), ld_rec,
+                                                                        static_cast<double*>(summaries), model->N, u0);
+    else if (model->desc.dtype == UNGAR_B200_F64)
         ub::summary_kernel<double><<<unsigned(batch), 32, 0, stream>>>(static_cast<const double*>(xp), ld_xp,
             static_cast<const double*>(records), ld_rec, static_cast<double*>(summaries), model->rl, u0, int(L.nu), int(L.m_eq), int(L.m_ineq));
     else
