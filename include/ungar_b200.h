@@ -21,7 +21,9 @@
  *     device buffers (H2D, kernels, D2H on `stream`) and returns after the results have landed;
  *   - a model handle is immutable after creation except for its internal workspaces: calls on one handle
  *     must be issued from one thread at a time (the reference's Function is not re-entrant either:
- *     function.hpp:380-383).
+ *     function.hpp:380-383).  Calls on one handle are ordered even across streams: its workspaces and work-claim
+ *     counters are shared by every launch, so a call on another stream than the previous call's first waits (on the
+ *     device, cudaStreamWaitEvent) for that call's work.  Use one handle per stream for concurrent pipelines.
  *   - there is NO CPU fallback: every compute entry point fails with UNGAR_B200_ECUDA when no CUDA
  *     device is usable.
  */
@@ -181,6 +183,15 @@ int ungar_b200_summaries(ungar_b200_model* model, const void* xp, int64_t batch,
  * `mem`).  With UNGAR_B200_MEM_HOST the call returns after the summaries have landed. */
 int ungar_b200_kkt_step(ungar_b200_model* model, const void* xp, int64_t batch, int64_t ld_xp, void* records_device,
                         int64_t ld_rec, void* summaries, int32_t mem, void* stream);
+
+/* The MPC data flow splits the flat vector: the parameter block of xp (references, constants, measured state — Ungar's `parameters`,
+ * quadruped.example.cpp:94-139) changes once per control cycle, the decision variables [X | U] every outer iteration.
+ * ungar_b200_set_parameters copies parameters[b, 0:n_par] (host or device per `mem`) into a device-resident copy of xp owned by the
+ * handle; ungar_b200_kkt_step_x is ungar_b200_kkt_step taking only the decision variables x[b, 0:n_dec] (45 % fewer bytes over PCIe
+ * for the quadruped).  `batch` must equal the batch of the last ungar_b200_set_parameters. */
+int ungar_b200_set_parameters(ungar_b200_model* model, const void* parameters, int64_t batch, int64_t ld_par, int32_t mem, void* stream);
+int ungar_b200_kkt_step_x(ungar_b200_model* model, const void* x, int64_t batch, int64_t ld_x, void* records_device, int64_t ld_rec,
+                          void* summaries, int32_t mem, void* stream);
 
 /* Replaces the QP solve SoftSQPOptimizer delegates to OSQP (optimization/soft_sqp.hpp:193-233) for the equality-
  * constrained QP assembled by ungar_b200_kkt_blocks:  min 1/2 d^T P d + q^T d  s.t.  A d = -g.  Consumes the records in

@@ -29,7 +29,7 @@ def test_every_declared_symbol_is_exported():
     assert names == sorted(_lib.SYMBOLS)
     for name in names:
         assert getattr(lib, name) is not None
-    assert lib.ungar_b200_abi_version() == 1
+    assert lib.ungar_b200_abi_version() == _lib.EXPECTED_ABI == 2
 
 
 def test_argument_validation_needs_no_gpu():

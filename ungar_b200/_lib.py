@@ -30,7 +30,7 @@ SYMBOLS = [
     "ungar_b200_tape_create", "ungar_b200_tape_destroy", "ungar_b200_tape_info", "ungar_b200_tape_jacobian_pattern",
     "ungar_b200_tape_hessian_pattern", "ungar_b200_tape_set_jacobian_elements", "ungar_b200_tape_set_hessian_elements",
     "ungar_b200_tape_forward_zero", "ungar_b200_tape_sparse_jacobian", "ungar_b200_tape_sparse_hessian", "ungar_b200_kkt_solve_csc",
-    "ungar_b200_jacobian_blocks", "ungar_b200_kkt_compact_map",
+    "ungar_b200_jacobian_blocks", "ungar_b200_kkt_compact_map", "ungar_b200_set_parameters", "ungar_b200_kkt_step_x",
 ]
 
 
@@ -102,6 +102,8 @@ def load() -> ctypes.CDLL:
     L.ungar_b200_jacobian_blocks.argtypes = [c_vp, c_vp, c_i64, c_i64, c_vp, c_i64, c_i32, c_vp]
     L.ungar_b200_summaries.argtypes = [c_vp, c_vp, c_i64, c_i64, c_vp, c_i64, c_vp, c_vp]
     L.ungar_b200_kkt_step.argtypes = [c_vp, c_vp, c_i64, c_i64, c_vp, c_i64, c_vp, c_i32, c_vp]
+    L.ungar_b200_kkt_step_x.argtypes = [c_vp, c_vp, c_i64, c_i64, c_vp, c_i64, c_vp, c_i32, c_vp]
+    L.ungar_b200_set_parameters.argtypes = [c_vp, c_vp, c_i64, c_i64, c_i32, c_vp]
     L.ungar_b200_qp_solve.argtypes = [c_vp, c_vp, c_i64, c_i64, c_vp, c_i64, c_vp, c_i64, c_vp]
     L.ungar_b200_sqp_options_default.argtypes = [ctypes.POINTER(SqpOptions)]
     L.ungar_b200_line_search.argtypes = [c_vp, c_vp, c_i64, c_i64, c_vp, c_i64, ctypes.POINTER(SqpOptions), c_vp, c_vp, c_vp]

@@ -297,8 +297,13 @@ class TapeHandle:
             if not x.is_cuda or x.dtype != torch.float64:
                 raise ValueError("torch inputs must be float64 CUDA tensors")
             x2 = x.unsqueeze(0) if x.dim() == 1 else x
+            if x2.dim() != 2 or x2.shape[1] != self.n_independent:
+                raise ValueError(f"x has shape {tuple(x.shape)}, expected [B, {self.n_independent}]")
+            if x2.stride(-1) != 1:
+                raise ValueError("x rows must be contiguous")
             out = torch.empty((x2.shape[0], max(n_out, 1)), dtype=torch.float64, device=x.device)
-            check(getattr(self._lib, entry)(self._h, x2.data_ptr(), *extra, x2.shape[0], x2.stride(0), out.data_ptr(), out.stride(0),
+            ld_x = max(int(x2.stride(0)), self.n_independent)  # a size-1 leading dimension may report any stride
+            check(getattr(self._lib, entry)(self._h, x2.data_ptr(), *extra, x2.shape[0], ld_x, out.data_ptr(), out.stride(0),
                                             MEM_DEVICE, torch.cuda.current_stream().cuda_stream))
             out = out[:, :n_out]
             return out[0] if x.dim() == 1 else out

@@ -316,7 +316,8 @@ template <class Mdl, class T, bool BARRIER, int WARPS, bool JAC = false>
 __global__ void __launch_bounds__(WARPS * 32)
 small_team_kernel(const T* __restrict__ xp_all, long long ld_xp, T* __restrict__ rec_all, long long ld_rec,
                   T* __restrict__ partials, int N, int n_xp, long long batch, RecLayout L, BarrierCoef<T> bar,
-                  typename SmallShape<Mdl, T>::Offsets O, unsigned int* __restrict__ sched) {
+                  typename SmallShape<Mdl, T>::Offsets O, unsigned int* __restrict__ sched, const int* __restrict__ active = nullptr,
+                  const unsigned int* __restrict__ n_active = nullptr) {
     using Sh = SmallShape<Mdl, T>;
     using Pol = SmallPolicy<Mdl>;
     constexpr int NX = Sh::NX, NU = Sh::NU, NZ = Sh::NZ, TRI = Sh::TRI, G = Sh::G, NA = NX * NZ;
@@ -337,8 +338,11 @@ small_team_kernel(const T* __restrict__ xp_all, long long ld_xp, T* __restrict__
 
     // Trajectories are claimed from an atomic counter (sched[0]); the first one is the warp's index.  A warp that becomes resident
     // late then claims fewer trajectories instead of stretching the launch (same scheme as the quadruped sweep).
-    long long b = warp_id;
-    while (b < batch) {
+    // `active` / `n_active` (SQP loop): the work items are the trajectories still RUNNING, listed by build_active_kernel.
+    const long long limit = n_active ? (long long)*n_active : batch;
+    long long item = warp_id;
+    while (item < limit) {
+        const long long b = active ? (long long)active[item] : item;
         const T* __restrict__ x = xp_all + b * ld_xp;
         T* __restrict__ r       = rec_all + b * ld_rec;
         // ---- phase 0 ------------------------------------------------------------------------------------------------------
@@ -460,7 +464,7 @@ small_team_kernel(const T* __restrict__ xp_all, long long ld_xp, T* __restrict__
             pt[0] = cost; pt[1] = bsum; pt[2] = gmax; pt[3] = hmax;
             claimed = atomicAdd(&sched[0], 1u);
         }
-        b = n_warps + (long long)__shfl_sync(0xffffffffu, claimed, 0);
+        item = n_warps + (long long)__shfl_sync(0xffffffffu, claimed, 0);
     }
     if (lane == 0) {
         asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");

@@ -27,7 +27,8 @@ template <bool BARRIER>
 __global__ void __launch_bounds__(64, 6)
 quadruped_compact_kernel(const double* __restrict__ xp_all, long long ld_xp, double* __restrict__ rec_all, long long ld_rec,
                             double* __restrict__ partials, int N, int run_len, int runs_per_traj, long long total_runs,
-                            BarrierCoef<double> bar, unsigned int* __restrict__ sched) {
+                            BarrierCoef<double> bar, unsigned int* __restrict__ sched, const int* __restrict__ active = nullptr,
+                            const unsigned int* __restrict__ n_active = nullptr) {
     using Q = QuadrupedCompactSweep;
     using K = Compact;
     using Mdl = Quadruped;
@@ -63,10 +64,13 @@ quadruped_compact_kernel(const double* __restrict__ xp_all, long long ld_xp, dou
     // (sched[0]).  A CTA that becomes resident late — another kernel (the NCCL all-gather of the previous step, a neighbour's H2D
     // chunk sweep) holds part of an SM — then simply claims fewer runs instead of stretching the launch by a second wave.
     __shared__ long long s_next;
+    // `active` / `n_active` (SQP loop): only the trajectories still RUNNING are swept, listed by build_active_kernel
+    if (n_active) total_runs = (long long)*n_active * runs_per_traj;
     long long run = blockIdx.x;
     while (run < total_runs) {
-        const long long b = run / runs_per_traj;
-        const int run_in_traj = int(run - b * runs_per_traj);
+        const long long item = run / runs_per_traj;
+        const long long b = active ? (long long)active[item] : item;
+        const int run_in_traj = int(run - item * runs_per_traj);
         const int k0    = run_in_traj * run_len;
         const int nodes = min(N, k0 + run_len) - k0;
         const double* __restrict__ x = xp_all + b * ld_xp;
@@ -387,6 +391,12 @@ __global__ void summary_compact_kernel(const double* __restrict__ xp_all, long l
     else if (l == 26) v = gmax;
     else if (l == 27) v = hmax;
     out_all[b * 32 + l] = v;
+}
+
+// List of the trajectories whose SQP status is RUNNING (order irrelevant: trajectories are independent) and their count.
+__global__ void build_active_kernel(const int* __restrict__ status, long long batch, int* __restrict__ active, unsigned int* __restrict__ n_active) {
+    const long long b = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (b < batch && status[2 * b] == 0) active[atomicAdd(n_active, 1u)] = int(b);
 }
 
 }  // namespace ub

@@ -34,8 +34,25 @@ struct EventRing {
     bool enabled = false;
     cudaEvent_t start[kRing] = {}, stop[kRing] = {};
     bool created[kRing] = {};
+    int device[kRing] = {};  // events belong to the device they were created on
     int head = 0, count = 0;
 } g_ring;
+
+int fail(int code, const char* fmt, ...);
+// The timing events of a ring slot, (re)created on the device that is about to record them.
+int ring_slot_ready(int slot, int device) {
+    if (g_ring.created[slot] && g_ring.device[slot] == device) return 0;
+    if (g_ring.created[slot]) {
+        cudaEventDestroy(g_ring.start[slot]);
+        cudaEventDestroy(g_ring.stop[slot]);
+        g_ring.created[slot] = false;
+    }
+    if (cudaEventCreate(&g_ring.start[slot]) != cudaSuccess || cudaEventCreate(&g_ring.stop[slot]) != cudaSuccess)
+        return fail(UNGAR_B200_ECUDA, "cudaEventCreate failed for the profiling ring");
+    g_ring.created[slot] = true;
+    g_ring.device[slot]  = device;
+    return 0;
+}
 
 int fail(int code, const char* fmt, ...) {
     char buf[512];
@@ -108,7 +125,14 @@ struct ungar_b200_model {
     ub::RecLayout rl{};
     ub::BarrierCoef<double> bar{};
     FunctionTables fn[4];
-    DeviceBuffer stage_cost, ws_records, ws_xp, ws_out, ws_qp, ws_steps, ws_status, ws_info, sched, ws_compact, ws_dense;
+    DeviceBuffer stage_cost, ws_records, ws_xp, ws_out, ws_qp, ws_steps, ws_status, ws_info, sched, ws_compact, ws_dense, ws_xp_cached, ws_active;
+    const int* active = nullptr;              // SQP loop: list of RUNNING trajectories for the next sweep (device), or null
+    const unsigned int* n_active = nullptr;   // and its length (device)
+    // calls on one handle share its workspaces and scheduler counters: a call on a new stream first waits for the previous call's work
+    cudaEvent_t ev_last = nullptr;
+    cudaStream_t last_stream = nullptr;
+    bool has_last = false;
+    int64_t cached_batch = 0;  // trajectories whose parameter block sits in ws_xp_cached (ungar_b200_set_parameters)
     size_t elem = 8;
     // compact record (quadruped): compact slot -> dense offset (or -2: pad), host copy for the ABI and device copy for the gather
     bool compact = false;
@@ -122,6 +146,24 @@ struct ungar_b200_model {
 };
 
 namespace {
+
+// Orders the calls on one handle across streams: the handle's workspaces, partial-sum buffer and work-claim counters are
+// shared by every launch, so a call issued on a different stream than the previous one waits for that one's last recorded event.
+struct StreamScope {
+    ungar_b200_model& m;
+    cudaStream_t stream;
+    StreamScope(ungar_b200_model& model, cudaStream_t s) : m(model), stream(s) {
+        if (!m.ev_last) cudaEventCreateWithFlags(&m.ev_last, cudaEventDisableTiming);
+        if (m.has_last && m.last_stream != stream && m.ev_last) cudaStreamWaitEvent(stream, m.ev_last, 0);
+    }
+    ~StreamScope() {
+        if (m.ev_last) {
+            cudaEventRecord(m.ev_last, stream);
+            m.last_stream = stream;
+            m.has_last    = true;
+        }
+    }
+};
 
 using ub::Dep;
 
@@ -322,11 +364,7 @@ int launch_generic(ungar_b200_model& mdl, const T* xp, int64_t batch, int64_t ld
     int slot = -1;
     if (g_ring.enabled) {
         slot = g_ring.head;
-        if (!g_ring.created[slot]) {
-            UB_CUDA(cudaEventCreate(&g_ring.start[slot]));
-            UB_CUDA(cudaEventCreate(&g_ring.stop[slot]));
-            g_ring.created[slot] = true;
-        }
+        if (int rc = ring_slot_ready(slot, mdl.desc.device)) return rc;
         UB_CUDA(cudaEventRecord(g_ring.start[slot], stream));
     }
     kernel<<<(unsigned)grid, Sh::THREADS, smem, stream>>>(xp, ld_xp, rec, ld_rec, static_cast<T*>(mdl.stage_cost.ptr),
@@ -380,11 +418,7 @@ int launch_structured(ungar_b200_model& mdl, const double* xp, int64_t batch, in
     int slot = -1;
     if (g_ring.enabled) {
         slot = g_ring.head;
-        if (!g_ring.created[slot]) {
-            UB_CUDA(cudaEventCreate(&g_ring.start[slot]));
-            UB_CUDA(cudaEventCreate(&g_ring.stop[slot]));
-            g_ring.created[slot] = true;
-        }
+        if (int rc = ring_slot_ready(slot, mdl.desc.device)) return rc;
         UB_CUDA(cudaEventRecord(g_ring.start[slot], stream));
     }
     kernel<<<grid, Q::WARPS * 32, Q::SMEM_BYTES, stream>>>(xp, ld_xp, rec, ld_rec, static_cast<double*>(mdl.stage_cost.ptr),
@@ -423,15 +457,11 @@ int launch_structured_compact(ungar_b200_model& mdl, const double* xp, int64_t b
     int slot = -1;
     if (g_ring.enabled) {
         slot = g_ring.head;
-        if (!g_ring.created[slot]) {
-            UB_CUDA(cudaEventCreate(&g_ring.start[slot]));
-            UB_CUDA(cudaEventCreate(&g_ring.stop[slot]));
-            g_ring.created[slot] = true;
-        }
+        if (int rc = ring_slot_ready(slot, mdl.desc.device)) return rc;
         UB_CUDA(cudaEventRecord(g_ring.start[slot], stream));
     }
     kernel<<<grid, Q::WARPS * 32, Q::SMEM_BYTES, stream>>>(xp, ld_xp, rec, ld_rec, static_cast<double*>(mdl.stage_cost.ptr), mdl.N, run_len,
-                                                           runs_per_traj, total_runs, mdl.bar, static_cast<unsigned int*>(mdl.sched.ptr));
+                                                           runs_per_traj, total_runs, mdl.bar, static_cast<unsigned int*>(mdl.sched.ptr), mdl.active, mdl.n_active);
     if (slot >= 0) {
         UB_CUDA(cudaEventRecord(g_ring.stop[slot], stream));
         g_ring.head  = (g_ring.head + 1) % kRing;
@@ -475,11 +505,7 @@ int launch_tpn_s(ungar_b200_model& mdl, const T* xp, int64_t batch, int64_t ld_x
     int slot = -1;
     if (g_ring.enabled) {
         slot = g_ring.head;
-        if (!g_ring.created[slot]) {
-            UB_CUDA(cudaEventCreate(&g_ring.start[slot]));
-            UB_CUDA(cudaEventCreate(&g_ring.stop[slot]));
-            g_ring.created[slot] = true;
-        }
+        if (int rc = ring_slot_ready(slot, mdl.desc.device)) return rc;
         UB_CUDA(cudaEventRecord(g_ring.start[slot], stream));
     }
     kernel<<<grid, threads, smem, stream>>>(xp, ld_xp, rec, ld_rec, static_cast<T*>(mdl.stage_cost.ptr), mdl.N, n_xp, batch,
@@ -525,15 +551,11 @@ int launch_small(ungar_b200_model& mdl, const T* xp, int64_t batch, int64_t ld_x
     int slot = -1;
     if (g_ring.enabled) {
         slot = g_ring.head;
-        if (!g_ring.created[slot]) {
-            UB_CUDA(cudaEventCreate(&g_ring.start[slot]));
-            UB_CUDA(cudaEventCreate(&g_ring.stop[slot]));
-            g_ring.created[slot] = true;
-        }
+        if (int rc = ring_slot_ready(slot, mdl.desc.device)) return rc;
         UB_CUDA(cudaEventRecord(g_ring.start[slot], stream));
     }
     kernel<<<grid, WARPS * 32, smem, stream>>>(xp, ld_xp, rec, ld_rec, static_cast<T*>(mdl.stage_cost.ptr), mdl.N, n_xp, batch,
-                                               mdl.rl, cast_barrier<T>(mdl.bar), offs, static_cast<unsigned int*>(mdl.sched.ptr));
+                                               mdl.rl, cast_barrier<T>(mdl.bar), offs, static_cast<unsigned int*>(mdl.sched.ptr), mdl.active, mdl.n_active);
     if (slot >= 0) {
         UB_CUDA(cudaEventRecord(g_ring.stop[slot], stream));
         g_ring.head  = (g_ring.head + 1) % kRing;
@@ -797,6 +819,7 @@ int reference_call(ungar_b200_model* mdl, int32_t function, int want, const void
     if (ld_out < n_out) return fail(UNGAR_B200_EINVAL, "output stride %lld < %lld", (long long)ld_out, (long long)n_out);
     if (batch == 0) return UNGAR_B200_OK;
     UB_CUDA(cudaSetDevice(mdl->desc.device));
+    StreamScope scope_(*mdl, static_cast<cudaStream_t>(stream_));
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
     const size_t es = mdl->elem;
 
@@ -908,6 +931,7 @@ int ungar_b200_model_destroy(ungar_b200_model* model) {
         if (f.d_hes_src) cudaFree(f.d_hes_src);
     }
     if (model->d_c2d) cudaFree(model->d_c2d);
+    if (model->ev_last) cudaEventDestroy(model->ev_last);
     if (model->copy_stream) cudaStreamDestroy(model->copy_stream);
     if (model->ev_entry) cudaEventDestroy(model->ev_entry);
     for (auto& e : model->ev_chunk)
@@ -990,6 +1014,7 @@ static int blocks_call(ungar_b200_model* model, const void* xp, int64_t batch, i
     if (mem != UNGAR_B200_MEM_DEVICE && mem != UNGAR_B200_MEM_HOST) return fail(UNGAR_B200_EINVAL, "unknown mem %d", mem);
     if (batch == 0) return UNGAR_B200_OK;
     UB_CUDA(cudaSetDevice(model->desc.device));
+    StreamScope scope_(*model, static_cast<cudaStream_t>(stream_));
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
     const size_t es = model->elem;
     if (mem == UNGAR_B200_MEM_DEVICE) return launch_sweep(*model, xp, batch, ld_xp, records, ld_rec, mode, nullptr, stream, model->compact);
@@ -1025,6 +1050,7 @@ int ungar_b200_qp_solve(ungar_b200_model* model, const void* records_device, int
         return fail(UNGAR_B200_EINVAL, "stride smaller than the row it holds");
     if (batch == 0) return UNGAR_B200_OK;
     UB_CUDA(cudaSetDevice(model->desc.device));
+    StreamScope scope_(*model, static_cast<cudaStream_t>(stream_));
     return launch_qp(*model, records_device, model->compact, batch, ld_rec, steps, ld_steps, multipliers, ld_multipliers, nullptr,
                      static_cast<cudaStream_t>(stream_));
 }
@@ -1057,6 +1083,7 @@ int ungar_b200_line_search(ungar_b200_model* model, void* xp, int64_t batch, int
     if (int rc = check_options(*options)) return rc;
     if (batch == 0) return UNGAR_B200_OK;
     UB_CUDA(cudaSetDevice(model->desc.device));
+    StreamScope scope_(*model, static_cast<cudaStream_t>(stream_));
     return launch_line_search(*model, static_cast<double*>(xp), batch, ld_xp, static_cast<const double*>(steps), ld_steps, *options,
                               status, static_cast<double*>(info), static_cast<cudaStream_t>(stream_));
 }
@@ -1074,6 +1101,7 @@ int ungar_b200_sqp_solve(ungar_b200_model* model, void* xp, int64_t batch, int64
     if (int rc = check_options(*options)) return rc;
     if (batch == 0) return UNGAR_B200_OK;
     UB_CUDA(cudaSetDevice(model->desc.device));
+    StreamScope scope_(*model, static_cast<cudaStream_t>(stream_));
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
     const size_t es = sizeof(double);
     // the records never leave the device here: the quadruped loop runs on the compact format whatever the handle's format is
@@ -1098,8 +1126,22 @@ int ungar_b200_sqp_solve(ungar_b200_model* model, void* xp, int64_t batch, int64
     }
     UB_CUDA(cudaMemsetAsync(d_status, 0, size_t(batch) * 2 * sizeof(int32_t), stream));
     if (d_info) UB_CUDA(cudaMemsetAsync(d_info, 0, size_t(batch) * UNGAR_B200_LINE_SEARCH_INFO_SIZE * es, stream));
+    // Trajectories that stopped (soft_sqp.hpp:100-108 breaks out per problem) are skipped by every kernel: the QP solve and the line search
+    // read the status, the sweep takes the list of RUNNING trajectories rebuilt after each line search (no host round trip: the list and
+    // its length stay on the device).  Only the sweeps that take a work list use it (quadruped compact, small-team); others sweep all.
+    if (int rc = model->ws_active.reserve(size_t(batch) * sizeof(int) + 16)) return rc;
+    int* const d_active = static_cast<int*>(model->ws_active.ptr) + 4;
+    unsigned int* const d_nact = static_cast<unsigned int*>(model->ws_active.ptr);
+    struct ActiveReset { ungar_b200_model* m; ~ActiveReset() { m->active = nullptr; m->n_active = nullptr; } } active_reset{model};
     for (int it = 0; it < options->max_iterations; ++it) {
         // AssembleOSQPInstance -> Solve -> BacktrackingLineSearch::Do (soft_sqp.hpp:76-99), stream-ordered
+        if (it > 0) {
+            UB_CUDA(cudaMemsetAsync(d_nact, 0, sizeof(unsigned int), stream));
+            ub::build_active_kernel<<<unsigned((batch + 255) / 256), 256, 0, stream>>>(d_status, batch, d_active, d_nact);
+            ++g_launches;
+            model->active = d_active;
+            model->n_active = d_nact;
+        }
         if (int rc = launch_sweep(*model, d_xp, batch, d_ld_xp, model->ws_records.ptr, rsize, MODE_KKT, nullptr, stream, crec)) return rc;
         if (int rc = launch_qp(*model, model->ws_records.ptr, crec, batch, rsize, model->ws_steps.ptr, L.n_dec, nullptr, 0, d_status, stream)) return rc;
         if (int rc = launch_line_search(*model, d_xp, batch, d_ld_xp, static_cast<const double*>(model->ws_steps.ptr), L.n_dec, *options,
@@ -1133,62 +1175,116 @@ int ungar_b200_sweep_times(float* ms, int32_t cap, int32_t* count) {
     return UNGAR_B200_OK;
 }
 
-int ungar_b200_kkt_step(ungar_b200_model* model, const void* xp, int64_t batch, int64_t ld_xp, void* records_device,
-                        int64_t ld_rec, void* summaries, int32_t mem, void* stream_) {
-    if (!model) return fail(UNGAR_B200_EINVAL, "null model");
-    if (batch < 0 || (batch > 0 && (!xp || !summaries))) return fail(UNGAR_B200_EINVAL, "null buffer");
+// One outer-iteration step.  `width` leading scalars of every row of `src` are copied into columns [0, width) of the device workspace
+// `w_xp` (rows of n_in scalars) — the whole flat vector, or only the decision variables when the parameter block is cached —
+// then the sweep runs on the workspace.  Host sources: chunked H2D on a copy stream overlapped with the sweep of the previous chunk.
+static int step_impl(ungar_b200_model* model, const void* src, int64_t batch, int64_t ld_src, int64_t width, char* w_xp, void* records_device,
+                     int64_t ld_rec, void* summaries, int32_t mem, cudaStream_t stream) {
     const ungar_b200_kkt_layout& L = model->layout;
     const int64_t n_in = L.n_dec + L.n_par;
-    if (ld_xp < n_in) return fail(UNGAR_B200_EINVAL, "ld_xp %lld < %lld", (long long)ld_xp, (long long)n_in);
+    const size_t es = model->elem;
+    if (mem == UNGAR_B200_MEM_DEVICE) {
+        UB_CUDA(cudaMemcpy2DAsync(w_xp, n_in * es, src, ld_src * es, width * es, batch, cudaMemcpyDeviceToDevice, stream));
+        return launch_sweep(*model, w_xp, batch, n_in, records_device, ld_rec, MODE_KKT, summaries, stream, model->compact);
+    }
+    if (int rc = model->ws_out.reserve(size_t(batch) * UNGAR_B200_SUMMARY_SIZE * es)) return rc;
+    char* const w_sum = static_cast<char*>(model->ws_out.ptr);
+    // Chunked pipeline: the inputs are 4 % of the traffic of the sweep but PCIe is ~100x slower than HBM, so the transfer
+    // dominates; copying chunk c + 1 while chunk c is swept hides all but the last chunk's kernel time.
+    const int chunks = batch >= 64 * ungar_b200_model::kChunks ? ungar_b200_model::kChunks : 1;
+    if (chunks > 1 && !model->copy_stream) {
+        UB_CUDA(cudaStreamCreateWithFlags(&model->copy_stream, cudaStreamNonBlocking));
+        UB_CUDA(cudaEventCreateWithFlags(&model->ev_entry, cudaEventDisableTiming));
+        for (auto& e : model->ev_chunk) UB_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    }
+    if (chunks > 1) {  // the copies start after whatever the caller already queued on `stream`
+        UB_CUDA(cudaEventRecord(model->ev_entry, stream));
+        UB_CUDA(cudaStreamWaitEvent(model->copy_stream, model->ev_entry, 0));
+    }
+    const int64_t per = (batch + chunks - 1) / chunks;
+    for (int c = 0; c < chunks; ++c) {
+        const int64_t b0 = c * per, nb = std::min<int64_t>(per, batch - b0);
+        if (nb <= 0) break;
+        cudaStream_t cs = chunks > 1 ? model->copy_stream : stream;
+        const char* from = static_cast<const char*>(src) + size_t(b0) * ld_src * es;
+        if (ld_src == n_in && width == n_in) UB_CUDA(cudaMemcpyAsync(w_xp + size_t(b0) * n_in * es, from, size_t(nb) * n_in * es, cudaMemcpyHostToDevice, cs));
+        else UB_CUDA(cudaMemcpy2DAsync(w_xp + size_t(b0) * n_in * es, n_in * es, from, ld_src * es, width * es, nb, cudaMemcpyHostToDevice, cs));
+        if (chunks > 1) {
+            UB_CUDA(cudaEventRecord(model->ev_chunk[c], cs));
+            UB_CUDA(cudaStreamWaitEvent(stream, model->ev_chunk[c], 0));
+        }
+        if (int rc = launch_sweep(*model, w_xp + size_t(b0) * n_in * es, nb, n_in, static_cast<char*>(records_device) + size_t(b0) * ld_rec * es,
+                                  ld_rec, MODE_KKT, w_sum + size_t(b0) * UNGAR_B200_SUMMARY_SIZE * es, stream, model->compact)) return rc;
+    }
+    UB_CUDA(cudaMemcpyAsync(summaries, w_sum, size_t(batch) * UNGAR_B200_SUMMARY_SIZE * es, cudaMemcpyDeviceToHost, stream));
+    UB_CUDA(cudaStreamSynchronize(stream));
+    return UNGAR_B200_OK;
+}
+
+static int step_check(ungar_b200_model* model, const void* in, int64_t batch, int64_t ld_in, int64_t need, void*& records_device, int64_t& ld_rec,
+                      void* summaries, int32_t mem) {
+    if (!model) return fail(UNGAR_B200_EINVAL, "null model");
+    if (batch < 0 || (batch > 0 && (!in || !summaries))) return fail(UNGAR_B200_EINVAL, "null buffer");
+    if (ld_in < need) return fail(UNGAR_B200_EINVAL, "input stride %lld < %lld", (long long)ld_in, (long long)need);
     if (mem != UNGAR_B200_MEM_DEVICE && mem != UNGAR_B200_MEM_HOST) return fail(UNGAR_B200_EINVAL, "unknown mem %d", mem);
     if (batch == 0) return UNGAR_B200_OK;
     UB_CUDA(cudaSetDevice(model->desc.device));
-    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
-    const size_t es = model->elem;
+    const ungar_b200_kkt_layout& L = model->layout;
     if (!records_device) {
-        if (int rc = model->ws_records.reserve(size_t(batch) * L.size * es)) return rc;
+        if (int rc = model->ws_records.reserve(size_t(batch) * L.size * model->elem)) return rc;
         records_device = model->ws_records.ptr;
         ld_rec = L.size;
     } else if (ld_rec < L.size) {
         return fail(UNGAR_B200_EINVAL, "ld_rec %lld < record size %lld", (long long)ld_rec, (long long)L.size);
     }
-    if (mem == UNGAR_B200_MEM_HOST) {
-        if (int rc = model->ws_xp.reserve(size_t(batch) * n_in * es)) return rc;
-        if (int rc = model->ws_out.reserve(size_t(batch) * UNGAR_B200_SUMMARY_SIZE * es)) return rc;
-        char* const w_xp  = static_cast<char*>(model->ws_xp.ptr);
-        char* const w_sum = static_cast<char*>(model->ws_out.ptr);
-        // Chunked pipeline: the inputs are 4 % of the traffic of the sweep but PCIe is ~100x slower than HBM, so the transfer
-        // dominates; copying chunk c + 1 while chunk c is swept hides all but the last chunk's kernel time.
-        const int chunks = batch >= 64 * ungar_b200_model::kChunks ? ungar_b200_model::kChunks : 1;
-        if (chunks > 1 && !model->copy_stream) {
-            UB_CUDA(cudaStreamCreateWithFlags(&model->copy_stream, cudaStreamNonBlocking));
-            UB_CUDA(cudaEventCreateWithFlags(&model->ev_entry, cudaEventDisableTiming));
-            for (auto& e : model->ev_chunk) UB_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
-        }
-        if (chunks > 1) {  // the copies start after whatever the caller already queued on `stream`
-            UB_CUDA(cudaEventRecord(model->ev_entry, stream));
-            UB_CUDA(cudaStreamWaitEvent(model->copy_stream, model->ev_entry, 0));
-        }
-        const int64_t per = (batch + chunks - 1) / chunks;
-        for (int c = 0; c < chunks; ++c) {
-            const int64_t b0 = c * per, nb = std::min<int64_t>(per, batch - b0);
-            if (nb <= 0) break;
-            cudaStream_t cs = chunks > 1 ? model->copy_stream : stream;
-            const char* src = static_cast<const char*>(xp) + size_t(b0) * ld_xp * es;
-            if (ld_xp == n_in) UB_CUDA(cudaMemcpyAsync(w_xp + size_t(b0) * n_in * es, src, size_t(nb) * n_in * es, cudaMemcpyHostToDevice, cs));
-            else UB_CUDA(cudaMemcpy2DAsync(w_xp + size_t(b0) * n_in * es, n_in * es, src, ld_xp * es, n_in * es, nb, cudaMemcpyHostToDevice, cs));
-            if (chunks > 1) {
-                UB_CUDA(cudaEventRecord(model->ev_chunk[c], cs));
-                UB_CUDA(cudaStreamWaitEvent(stream, model->ev_chunk[c], 0));
-            }
-            if (int rc = launch_sweep(*model, w_xp + size_t(b0) * n_in * es, nb, n_in, static_cast<char*>(records_device) + size_t(b0) * ld_rec * es,
-                                      ld_rec, MODE_KKT, w_sum + size_t(b0) * UNGAR_B200_SUMMARY_SIZE * es, stream, model->compact)) return rc;
-        }
-        UB_CUDA(cudaMemcpyAsync(summaries, w_sum, size_t(batch) * UNGAR_B200_SUMMARY_SIZE * es, cudaMemcpyDeviceToHost, stream));
-        UB_CUDA(cudaStreamSynchronize(stream));
-        return UNGAR_B200_OK;
-    }
-    return launch_sweep(*model, xp, batch, ld_xp, records_device, ld_rec, MODE_KKT, summaries, stream, model->compact);
+    return UNGAR_B200_OK;
+}
+
+int ungar_b200_kkt_step(ungar_b200_model* model, const void* xp, int64_t batch, int64_t ld_xp, void* records_device,
+                        int64_t ld_rec, void* summaries, int32_t mem, void* stream_) {
+    const int64_t n_in = model ? model->layout.n_dec + model->layout.n_par : 0;
+    if (int rc = step_check(model, xp, batch, ld_xp, n_in, records_device, ld_rec, summaries, mem)) return rc;
+    if (batch == 0) return UNGAR_B200_OK;
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    StreamScope scope_(*model, stream);
+    if (mem == UNGAR_B200_MEM_DEVICE)  // device inputs are swept in place: no staging copy
+        return launch_sweep(*model, xp, batch, ld_xp, records_device, ld_rec, MODE_KKT, summaries, stream, model->compact);
+    if (int rc = model->ws_xp.reserve(size_t(batch) * n_in * model->elem)) return rc;
+    return step_impl(model, xp, batch, ld_xp, n_in, static_cast<char*>(model->ws_xp.ptr), records_device, ld_rec, summaries, mem, stream);
+}
+
+int ungar_b200_set_parameters(ungar_b200_model* model, const void* parameters, int64_t batch, int64_t ld_par, int32_t mem, void* stream_) {
+    if (!model) return fail(UNGAR_B200_EINVAL, "null model");
+    const ungar_b200_kkt_layout& L = model->layout;
+    if (batch < 0 || (batch > 0 && !parameters)) return fail(UNGAR_B200_EINVAL, "null buffer");
+    if (ld_par < L.n_par) return fail(UNGAR_B200_EINVAL, "ld_par %lld < %lld", (long long)ld_par, (long long)L.n_par);
+    if (mem != UNGAR_B200_MEM_DEVICE && mem != UNGAR_B200_MEM_HOST) return fail(UNGAR_B200_EINVAL, "unknown mem %d", mem);
+    UB_CUDA(cudaSetDevice(model->desc.device));
+    StreamScope scope_(*model, static_cast<cudaStream_t>(stream_));
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    const size_t es = model->elem;
+    const int64_t n_in = L.n_dec + L.n_par;
+    model->cached_batch = 0;
+    if (batch == 0) return UNGAR_B200_OK;
+    if (int rc = model->ws_xp_cached.reserve(size_t(batch) * n_in * es)) return rc;
+    UB_CUDA(cudaMemcpy2DAsync(static_cast<char*>(model->ws_xp_cached.ptr) + L.n_dec * es, n_in * es, parameters, ld_par * es, L.n_par * es, batch,
+                              mem == UNGAR_B200_MEM_HOST ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice, stream));
+    if (mem == UNGAR_B200_MEM_HOST) UB_CUDA(cudaStreamSynchronize(stream));
+    model->cached_batch = batch;
+    return UNGAR_B200_OK;
+}
+
+int ungar_b200_kkt_step_x(ungar_b200_model* model, const void* x, int64_t batch, int64_t ld_x, void* records_device, int64_t ld_rec,
+                          void* summaries, int32_t mem, void* stream_) {
+    const int64_t n_dec = model ? model->layout.n_dec : 0;
+    if (int rc = step_check(model, x, batch, ld_x, n_dec, records_device, ld_rec, summaries, mem)) return rc;
+    if (batch == 0) return UNGAR_B200_OK;
+    StreamScope scope_(*model, static_cast<cudaStream_t>(stream_));
+    if (batch != model->cached_batch)
+        return fail(UNGAR_B200_EINVAL, "ungar_b200_set_parameters holds the parameters of %lld trajectories, this call has %lld",
+                    (long long)model->cached_batch, (long long)batch);
+    return step_impl(model, x, batch, ld_x, n_dec, static_cast<char*>(model->ws_xp_cached.ptr), records_device, ld_rec, summaries, mem,
+                     static_cast<cudaStream_t>(stream_));
 }
 
 int ungar_b200_summaries(ungar_b200_model* model, const void* xp, int64_t batch, int64_t ld_xp, const void* records,
@@ -1196,6 +1292,7 @@ int ungar_b200_summaries(ungar_b200_model* model, const void* xp, int64_t batch,
     if (!model || (batch > 0 && (!xp || !records || !summaries))) return fail(UNGAR_B200_EINVAL, "null argument");
     if (batch <= 0) return batch == 0 ? UNGAR_B200_OK : fail(UNGAR_B200_EINVAL, "negative batch");
     UB_CUDA(cudaSetDevice(model->desc.device));
+    StreamScope scope_(*model, static_cast<cudaStream_t>(stream_));
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
     const ungar_b200_kkt_layout& L = model->layout;
     const int u0 = int(L.nx * (L.horizon + 1));

@@ -102,6 +102,26 @@ class Model:
             raise ValueError("output buffer must be a C-contiguous array of the model dtype")
         return xp2, out2, MEM_HOST, None, squeeze
 
+    def _dev(self, t, name: str, cols: int, int32: bool = False):
+        """Validates one torch argument of a device-pointer entry point (the C side can only compare strides with widths): CUDA tensor on
+        the model's device, the model's dtype (or int32), 2-D, contiguous rows, at least `cols` columns.  Returns (pointer, row stride)."""
+        import torch
+
+        if t is None:
+            return None, 0
+        if not _is_torch(t) or not t.is_cuda:
+            raise ValueError(f"{name} must be a CUDA tensor")
+        if t.device.index != self.device:
+            raise ValueError(f"{name} lives on cuda:{t.device.index}, the model on cuda:{self.device}")
+        want = torch.int32 if int32 else (torch.float32 if self.dtype == F32 else torch.float64)
+        if t.dtype != want:
+            raise ValueError(f"{name} has dtype {t.dtype}, expected {want}")
+        if t.dim() != 2 or t.shape[1] < cols:
+            raise ValueError(f"{name} has shape {tuple(t.shape)}, expected [B, >= {cols}]")
+        if t.stride(-1) != 1:
+            raise ValueError(f"{name} rows must be contiguous")
+        return t.data_ptr(), self._ld(t)
+
     @staticmethod
     def _ptr(a):
         return a.data_ptr() if _is_torch(a) else a.ctypes.data
@@ -131,17 +151,38 @@ class Model:
 
         if out is None:
             out = torch.empty((xp.shape[0], _lib.SUMMARY_SIZE), dtype=xp.dtype, device=xp.device)
-        check(self._lib.ungar_b200_summaries(self._handle, xp.data_ptr(), xp.shape[0], xp.stride(0), records.data_ptr(),
-                                             records.stride(0), out.data_ptr(), _torch_stream()))
+        (px, lx), (pr, lr), (po, _) = self._dev(xp, "xp", self.n_xp), self._dev(records, "records", self.layout["size"]), self._dev(out, "out", _lib.SUMMARY_SIZE)
+        if records.shape[0] != xp.shape[0] or out.shape[0] != xp.shape[0] or not out.is_contiguous():
+            raise ValueError("xp, records and out must have the same number of rows (out contiguous)")
+        check(self._lib.ungar_b200_summaries(self._handle, px, xp.shape[0], lx, pr, lr, po, _torch_stream()))
         return out
 
     def step(self, xp, records=None, summaries=None):
         """One outer-iteration step: KKT records stay in HBM (``records``: CUDA tensor or None for the handle's
         workspace), per-trajectory summaries ``[B, 32]`` come back where ``xp`` lives (numpy -> host)."""
         xp2, out2, mem, stream, _ = self._buffers(xp, summaries, _lib.SUMMARY_SIZE)
-        rec_ptr, rec_ld = (records.data_ptr(), records.stride(0)) if records is not None else (None, 0)
+        rec_ptr, rec_ld = self._dev(records, "records", self.layout["size"])
         check(self._lib.ungar_b200_kkt_step(self._handle, self._ptr(xp2), xp2.shape[0], self._ld(xp2), rec_ptr, rec_ld,
                                             self._ptr(out2), mem, stream))
+        return out2
+
+    def set_parameters(self, parameters) -> None:
+        """Cache the parameter block ``parameters[B, n_par]`` (numpy -> host, torch CUDA tensor -> device) in the handle; ``step_x`` then
+        takes only the decision variables (the MPC data flow: parameters change per control cycle, decision variables per iteration)."""
+        n_par = self.layout["n_par"]
+        if parameters.shape[-1] != n_par:
+            raise ValueError(f"parameters have {parameters.shape[-1]} columns, expected {n_par}")
+        p2, _, mem, stream, _ = self._buffers(parameters, parameters, n_par)
+        check(self._lib.ungar_b200_set_parameters(self._handle, self._ptr(p2), p2.shape[0], self._ld(p2), mem, stream))
+
+    def step_x(self, x, records=None, summaries=None):
+        """``step`` with the decision variables ``x[B, n_dec]`` only; the parameters come from ``set_parameters``."""
+        if x.shape[-1] < self.layout["n_dec"]:
+            raise ValueError(f"x has {x.shape[-1]} columns, expected at least {self.layout['n_dec']}")
+        x2, out2, mem, stream, _ = self._buffers(x, summaries, _lib.SUMMARY_SIZE)
+        rec_ptr, rec_ld = self._dev(records, "records", self.layout["size"])
+        check(self._lib.ungar_b200_kkt_step_x(self._handle, self._ptr(x2), x2.shape[0], self._ld(x2), rec_ptr, rec_ld,
+                                              self._ptr(out2), mem, stream))
         return out2
 
     def qp_solve(self, records, steps=None, multipliers=None, want_multipliers: bool = True):
@@ -154,9 +195,12 @@ class Model:
             steps = torch.empty((B, self.layout["n_dec"]), dtype=records.dtype, device=records.device)
         if multipliers is None and want_multipliers:
             multipliers = torch.empty((B, self.layout["m_eq"]), dtype=records.dtype, device=records.device)
-        mp, ml = (multipliers.data_ptr(), multipliers.stride(0)) if multipliers is not None else (None, 0)
-        check(self._lib.ungar_b200_qp_solve(self._handle, records.data_ptr(), B, records.stride(0), steps.data_ptr(),
-                                            steps.stride(0), mp, ml, _torch_stream()))
+        pr, lr = self._dev(records, "records", self.layout["size"])
+        ps, ls = self._dev(steps, "steps", self.layout["n_dec"])
+        mp, ml = self._dev(multipliers, "multipliers", self.layout["m_eq"])
+        if steps.shape[0] != B or (multipliers is not None and multipliers.shape[0] != B):
+            raise ValueError("records, steps and multipliers must have the same number of rows")
+        check(self._lib.ungar_b200_qp_solve(self._handle, pr, B, lr, ps, ls, mp, ml, _torch_stream()))
         return steps, multipliers
 
     def sqp_options(self, **overrides) -> "_lib.SqpOptions":
@@ -177,10 +221,13 @@ class Model:
         options = options or self.sqp_options()
         if info is None:
             info = torch.empty((xp.shape[0], _lib.LINE_SEARCH_INFO_SIZE), dtype=xp.dtype, device=xp.device)
-        check(self._lib.ungar_b200_line_search(self._handle, xp.data_ptr(), xp.shape[0], xp.stride(0), steps.data_ptr(),
-                                               steps.stride(0), ctypes.byref(options),
-                                               status.data_ptr() if status is not None else None, info.data_ptr(),
-                                               _torch_stream()))
+        (px, lx), (ps, ls) = self._dev(xp, "xp", self.n_xp), self._dev(steps, "steps", self.layout["n_dec"])
+        pst, _ = self._dev(status, "status", 2, int32=True)
+        pi, _ = self._dev(info, "info", _lib.LINE_SEARCH_INFO_SIZE)
+        if steps.shape[0] != xp.shape[0] or info.shape[0] != xp.shape[0] or not info.is_contiguous() or (
+                status is not None and (status.shape != (xp.shape[0], 2) or not status.is_contiguous())):
+            raise ValueError("steps / info / status must have one contiguous row per trajectory of xp")
+        check(self._lib.ungar_b200_line_search(self._handle, px, xp.shape[0], lx, ps, ls, ctypes.byref(options), pst, pi, _torch_stream()))
         return info
 
     def sqp_solve(self, xp, options=None, want_info: bool = True):
@@ -193,7 +240,8 @@ class Model:
             B = xp.shape[0]
             status = torch.empty((B, 2), dtype=torch.int32, device=xp.device)
             info = torch.empty((B, _lib.LINE_SEARCH_INFO_SIZE), dtype=xp.dtype, device=xp.device) if want_info else None
-            check(self._lib.ungar_b200_sqp_solve(self._handle, xp.data_ptr(), B, xp.stride(0), ctypes.byref(options),
+            px, lx = self._dev(xp, "xp", self.n_xp)
+            check(self._lib.ungar_b200_sqp_solve(self._handle, px, B, lx, ctypes.byref(options),
                                                  status.data_ptr(), info.data_ptr() if want_info else None, MEM_DEVICE,
                                                  _torch_stream()))
             return status, info
