@@ -25,7 +25,9 @@
 #include <cstdint>
 
 #include "compact.cuh"
+#ifndef QT_HOST_TEST  // tests/host/*.cpp compile the arithmetic below for the CPU and supply qp_ld2 / qp_st2 / the warp intrinsics themselves
 #include "qp_schur.cuh"  // qp_dmma, qp_ld2, qp_st2
+#endif
 
 namespace ub {
 
@@ -46,6 +48,7 @@ struct QpT {
 };
 static_assert(QpT::bc(28) + 28 < QpT::fRI, "factor image");
 
+#ifndef QT_HOST_TEST
 // ---------------------------------------------------------------------------------------------------------------------------------
 // mbarrier + bulk-copy helpers (one barrier per buffer per warp; lane 0 arms and issues, every lane waits on the phase)
 // ---------------------------------------------------------------------------------------------------------------------------------
@@ -103,6 +106,8 @@ struct QtCtx {
     __device__ __forceinline__ void load_factor(const double* wsg) const { issue(3, sm + QpT::oLO, wsg, QpT::WS_GROUP * 8); }
     __device__ __forceinline__ void swap() { cur ^= 1; }
 };
+
+#endif  // QT_HOST_TEST
 
 // ---------------------------------------------------------------------------------------------------------------------------------
 // Stage data.  `sm`: small part of a chunk (Cs, Cp, g, q -> t, Hd/Hb -> P^-1 in place); `ab`: AQ | AP of a chunk.
@@ -485,6 +490,7 @@ __device__ __forceinline__ double qt_v_dot(const double* __restrict__ ab, const 
     return acc;
 }
 
+#ifndef QT_HOST_TEST
 // S -= Lo Lo^T on the FP64 tensor cores.  The image (29 rows, stride LS) holds Lo; it is overwritten by the product, of which every
 // lane then subtracts its own row.  Ten lower 8x8 tiles x eight k-steps of mma.m8n8k4 (rows / k beyond 28 are masked).
 __device__ __forceinline__ void qt_syrk(double* __restrict__ img, double* s, int lane) {
@@ -521,6 +527,8 @@ __device__ __forceinline__ void qt_syrk(double* __restrict__ img, double* s, int
     s[G - 1] -= mine[G - 1];
     __syncwarp();
 }
+
+#endif  // QT_HOST_TEST
 
 // x[cc] += a * col[cc] for cc = FIRST .. 28, the column read from shared memory in batches of up to eight 16-byte loads that are
 // all issued before the first dependent FMA (left to itself the compiler reuses one load register and serialises load -> FMA pairs).
@@ -669,6 +677,7 @@ __device__ __forceinline__ double qt_outward_solve(const double* __restrict__ f,
     return lane < G ? u * (r_own * r_own) : 0.0;
 }
 
+#ifndef QT_HOST_TEST
 // =================================================================================================================================
 // One CTA of two warps per trajectory; the chains are separate (non-inlined) functions so that each gets its own register allocation.
 // =================================================================================================================================
@@ -987,5 +996,7 @@ qp_twisted_kernel(const double* __restrict__ rec_all, long long ld_rec, double* 
     if (wib == 0) qt_top_chain(lane, smem_raw);
     else qt_bottom_chain(lane, smem_raw);
 }
+
+#endif  // QT_HOST_TEST
 
 }  // namespace ub
