@@ -82,8 +82,49 @@ class Emitter:
         self.emit(f"v[{s}] = {expr};")
         return f"v[{s}]"
 
+    def reuse_slots(self) -> None:
+        """Temporaries that die inside the function that defines them become local `const double` scalars (registers); only values
+        that cross a function boundary keep a slot in the scratch array, and those slots are recycled by liveness — CppADCodeGen
+        reuses its temporaries the same way.  (One array slot per statement made the scratch ~14 MB per trajectory: memory-bound.)"""
+        import re
+
+        stmts = [st for body in self.funcs for st in body]
+        tok = re.compile(r"v\[(\d+)\]")
+        first, last = {}, {}
+        for idx, st in enumerate(stmts):
+            for mm in tok.finditer(st):
+                k = int(mm.group(1))
+                first.setdefault(k, idx)
+                last[k] = idx
+        local = {k for k in first if first[k] // CHUNK == last[k] // CHUNK}
+        expire = {}
+        for slot, idx in last.items():
+            if slot not in local:
+                expire.setdefault(idx, []).append(slot)
+        free, mapping, n_new = [], {}, 0
+        out = []
+        for idx, st in enumerate(stmts):
+            lhs = tok.match(st)
+            if lhs:
+                old = int(lhs.group(1))
+                if old in local:
+                    st = "const double t" + str(old) + st[lhs.end():]
+                elif old not in mapping:
+                    if free:
+                        mapping[old] = free.pop()
+                    else:
+                        mapping[old] = n_new
+                        n_new += 1
+            out.append(tok.sub(lambda mm: f"t{mm.group(1)}" if int(mm.group(1)) in local else f"v[{mapping[int(mm.group(1))]}]", st))
+            for old in expire.get(idx, ()):  # the slot's value is dead after this statement
+                if old in mapping:
+                    free.append(mapping[old])
+        self.n_slots = max(n_new, 1)
+        self.funcs = [out[i:i + CHUNK] for i in range(0, len(out), CHUNK)] or [[]]
+
     def source(self, signature_args: str) -> tuple[str, str]:
         """(C source of the chunk functions, body of the driver that calls them in order)."""
+        self.reuse_slots()
         parts, calls = [], []
         for i, body in enumerate(self.funcs):
             name = f"{self.prefix}_{i}"
@@ -301,9 +342,9 @@ def generate(model: str, N: int):
         oo["hes"] = oo["jac"] + bound
         ny, rows, cols, hes = gen_function(em, nodes, ni, dep_id, dep_const, n_dec, oo, order)
         assert rows.size <= bound
+        body, calls = em.source("const double* __restrict__ x, double* __restrict__ v, double* __restrict__ out")
         layout[fn] = {"y": oo["y"], "ny": ny, "jac": oo["jac"], "nnz": int(rows.size), "hes": oo["hes"], "nnz_hes": len(hes),
                       "rows": rows, "cols": cols, "hes_pattern": hes, "slots": em.n_slots}
-        body, calls = em.source("const double* __restrict__ x, double* __restrict__ v, double* __restrict__ out")
         src_parts.extend(body)
         drivers.append(calls)
         off = oo["hes"] + len(hes) + 8

@@ -258,6 +258,14 @@ class TapeHandle:
         except Exception:
             pass
 
+    def special_info(self) -> dict:
+        """State of the NVRTC-specialised kernels per order (0 values, 1 Jacobian, 2 Hessian): ``state`` 0 not tried / 1 specialised /
+        -1 interpreter, ``from_cache``, ``key`` = content hash the compiled kernel is cached under."""
+        buf = (ctypes.c_int64 * 12)()
+        check(self._lib.ungar_b200_tape_special_info(self._h, buf))
+        return {o: {"state": int(buf[4 * o]), "from_cache": bool(buf[4 * o + 1]), "key": (int(buf[4 * o + 3]) << 32) | int(buf[4 * o + 2])}
+                for o in range(3)}
+
     def info(self) -> dict:
         buf = (ctypes.c_int64 * 6)()
         check(self._lib.ungar_b200_tape_info(self._h, buf))

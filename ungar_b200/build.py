@@ -20,6 +20,8 @@ NVCC_FLAGS = [
     "-Xcompiler", "-fPIC", "-shared",
     # cuSOLVER's dense LU backs the generic QP fallback (csrc/kkt_dense.cu); everything else is hand-written
     "-lcusolver", "-Xlinker", "-rpath=/usr/local/cuda/lib64",
+    # the generic tape path specialises hot tapes with NVRTC and loads the cubin through the driver API (csrc/tape.cu)
+    "-lnvrtc", "-L/usr/local/cuda/lib64/stubs", "-lcuda", "-ldl",
 ]
 
 

@@ -2,6 +2,15 @@
 // launches of the register-machine kernels (tape_machine.cuh).  The only host arithmetic here is structural (liveness,
 // dependency sets, colouring); every value and derivative is computed on the device.
 #include <algorithm>
+#include <chrono>
+#include <cstdlib>
+#include <dlfcn.h>
+#include <unistd.h>
+#include <fstream>
+#include <sstream>
+#include <sys/stat.h>
+#include <cuda.h>
+#include <nvrtc.h>
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
@@ -111,6 +120,17 @@ struct ungar_b200_tape {
     std::vector<int> h_pi, h_pj;               // Hessian directions
     std::vector<int> h_di, h_dj, h_pr;         // per element: direction of e_i, of e_j, of e_i + e_j (-1 on the diagonal)
 
+    // NVRTC-specialised straight-line kernels, one per ORDER (0 values, 1 Jacobian, 2 Hessian jets): tried once each
+    struct Special {
+        int state = 0;  // 0: not tried, 1: ready, -1: unavailable (too large, NVRTC missing, compile error: the interpreter serves)
+        CUmodule module = nullptr;
+        CUfunction fn = nullptr;
+        uint64_t key = 0;
+        bool from_cache = false;
+        double compile_seconds = 0.0;
+    } special[3];
+    int64_t calls[3] = {0, 0, 0};
+
     // device state
     bool uploaded = false, j_uploaded = false, h_uploaded = false;
     DevBuf d_code, d_consts, d_color, d_jac_slot, d_pi, d_pj, d_di, d_dj, d_pr, d_w, scratch, ws_x, ws_out, ws_q;
@@ -211,6 +231,10 @@ void build_program(ungar_b200_tape& T) {
             in.a = slot[size_t(nd.a)];
             if (!is_unary(nd.op)) in.b = slot[size_t(nd.b)];
             if (is_cond(nd.op)) { in.c = slot[size_t(nd.c)]; in.d = slot[size_t(nd.d)]; }
+            if (nd.op == UNGAR_B200_OP_POW) {  // constant exponent: closed-form derivatives (finite for a <= 0), see jet_pow_const
+                in.c = -1;
+                if (T.nodes[size_t(nd.b)].op == UNGAR_B200_OP_CONST) { in.c = int(T.consts.size()); T.consts.push_back(T.nodes[size_t(nd.b)].k); }
+            }
         }
         // operands may be released before the destination is chosen: every instruction reads all operands before it writes
         for_operands(nd, [&](int32_t o) { release(o); });
@@ -363,6 +387,12 @@ int choose_hessian(ungar_b200_tape& T, const int64_t* rows, const int64_t* cols,
             if (!pattern.count({rows[e], cols[e]}))
                 return tfail(UNGAR_B200_EINVAL, "Hessian element (%lld, %lld) is structurally zero", (long long)rows[e], (long long)cols[e]);
         }
+        {
+            std::set<std::pair<int64_t, int64_t>> seen;
+            for (int64_t e = 0; e < nnz; ++e)
+                if (!seen.emplace(rows[e], cols[e]).second)
+                    return tfail(UNGAR_B200_EINVAL, "Hessian element (%lld, %lld) is listed twice", (long long)rows[e], (long long)cols[e]);
+        }
         sel_rows.assign(rows, rows + nnz);
         sel_cols.assign(cols, cols + nnz);
     } else {
@@ -457,16 +487,189 @@ int check_call(const ungar_b200_tape* T, const void* x, int64_t batch, int64_t l
     return UNGAR_B200_OK;
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// NVRTC specialisation.  The register machine pays ~0.3 us per tape instruction regardless of the batch
+// (fetch-decode of the instruction record, jets through HBM/L2).  For tapes up to kSpecializeMax instructions the same program
+// is emitted as ONE straight-line CUDA kernel — a named Jet<ORDER> variable per slot, the very op functions of tape_machine.cuh —
+// compiled with NVRTC for sm_100a and loaded with the driver API.  Where the reference runs gcc on generated C and caches the
+// library under its NAME only (function.hpp:420-451: a changed lambda under an old name silently reuses the stale library), the
+// compiled kernel is cached under a CONTENT hash: FNV-1a over the instruction stream, the constants, ORDER, the target arch and
+// the text of tape_machine.cuh.  UNGAR_B200_KERNEL_CACHE (default: $UNGAR_CODEGEN_FOLDER or /tmp/ungar_b200_kernels) holds
+// <hash>.cubin; UNGAR_B200_NO_NVRTC=1 disables the path.
+// ---------------------------------------------------------------------------------------------------------------------
+constexpr int kSpecializeMax = 12000;   // instructions; NVRTC + ptxas time grows superlinearly (8 k: seconds, 40 k: minutes)
+constexpr int64_t kSpecializeAfter = 1; // specialise on the second call of an ORDER: a function evaluated once never pays the compile
+
+uint64_t fnv1a(const void* data, size_t n, uint64_t h = 1469598103934665603ull) {
+    const unsigned char* p = static_cast<const unsigned char*>(data);
+    for (size_t i = 0; i < n; ++i) { h ^= p[i]; h *= 1099511628211ull; }
+    return h;
+}
+
+std::string machine_header_dir() {
+    Dl_info info;
+    if (dladdr(reinterpret_cast<void*>(&fnv1a), &info) && info.dli_fname) {
+        std::string lib = info.dli_fname;  // .../ungar_b200/libungar_b200.so -> .../ungar_b200/csrc
+        const size_t cut = lib.find_last_of('/');
+        return (cut == std::string::npos ? std::string(".") : lib.substr(0, cut)) + "/csrc";
+    }
+    return "csrc";
+}
+
+std::string cache_dir() {
+    if (const char* e = getenv("UNGAR_B200_KERNEL_CACHE")) return e;
+    if (const char* e = getenv("UNGAR_CODEGEN_FOLDER")) return std::string(e) + "/ungar_b200_kernels";
+    return "/tmp/ungar_b200_kernels";
+}
+
+std::string slurp(const std::string& path) {
+    std::ifstream f(path, std::ios::binary);
+    std::stringstream ss;
+    ss << f.rdbuf();
+    return ss.str();
+}
+
+// Straight-line kernel text of the program for one ORDER (same thread mapping and outputs as ub::tape::tape_kernel<ORDER>).
+std::string generate_kernel_source(const ungar_b200_tape& T, int order) {
+    using namespace ub::tape;
+    std::ostringstream o;
+    o.precision(17);
+    o << "#include \"tape_machine.cuh\"\nusing namespace ub::tape;\n"
+      << "extern \"C\" __global__ void __launch_bounds__(128) tape_special(Seeds S, const double* __restrict__ x_all, long long ld_x, long long batch, int ndir,\n"
+      << "    double* __restrict__ out_all, long long ld_out, const int* __restrict__ out_slot, const double* __restrict__ weights) {\n"
+      << "  constexpr int ORDER = " << order << ";\n"
+      << "  const long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x;\n  if (t >= batch * ndir) return;\n"
+      << "  const long long b = t / ndir;\n  const int dir = int(t - b * ndir);\n"
+      << "  const double* __restrict__ x = x_all + b * ld_x;\n  double* __restrict__ out = out_all + b * ld_out;\n"
+      << "  int s0 = -1, s1 = -1;\n  if (ORDER >= 1 && S.kind == 1) { s0 = S.pi[dir]; s1 = S.pj[dir]; }\n  double acc = 0.0;\n  (void)s0; (void)s1; (void)acc;\n";
+    for (int k = 0; k < T.n_slots; ++k) o << "  Jet<ORDER> r" << k << ";\n";
+    auto hexd = [&](double v) {  // exact round trip of a double constant
+        char buf[64];
+        snprintf(buf, sizeof(buf), "%a", v);
+        return std::string(buf);
+    };
+    for (const Instr& in : T.code) {
+        switch (in.op) {
+            case T_INDEP:
+                o << "  r" << in.dst << " = jet_const<ORDER>(x[" << in.a << "]);";
+                if (order >= 1) o << " r" << in.dst << ".d = (S.kind == 0 ? S.color[" << in.a << "] == dir : (" << in.a << " == s0 || " << in.a << " == s1)) ? 1.0 : 0.0;";
+                o << "\n";
+                break;
+            case T_CONST: o << "  r" << in.dst << " = jet_const<ORDER>(" << hexd(T.consts[size_t(in.a)]) << ");\n"; break;
+            case T_ADD: case T_SUB: case T_MUL: case T_DIV: case T_ATAN2:
+                o << "  r" << in.dst << " = jet_binary<ORDER>(" << in.op << ", r" << in.a << ", r" << in.b << ");\n";
+                break;
+            case T_POW:
+                if (in.c >= 0) o << "  r" << in.dst << " = jet_pow_const<ORDER>(r" << in.a << ", " << hexd(T.consts[size_t(in.c)]) << ");\n";
+                else o << "  r" << in.dst << " = jet_binary<ORDER>(" << int(T_POW) << ", r" << in.a << ", r" << in.b << ");\n";
+                break;
+            case T_CLT: case T_CLE: case T_CGT: case T_CGE: case T_CEQ:
+                o << "  r" << in.dst << " = jet_compare(" << in.op << ", r" << in.a << ".v, r" << in.b << ".v) ? r" << in.c << " : r" << in.d << ";\n";
+                break;
+            case T_OUTPUT: case T_OUTPUT_CONST: {
+                const std::string a = in.op == T_OUTPUT ? "r" + std::to_string(in.a) : "jet_const<ORDER>(" + hexd(T.consts[size_t(in.a)]) + ")";
+                if (order == 0) o << "  out[" << in.b << "] = " << a << ".v;\n";
+                if (order == 1) o << "  { const int e = out_slot[(long long)" << in.b << " * ndir + dir]; if (e >= 0) out[e] = " << a << ".d; }\n";
+                if (order == 2) o << "  acc += weights[" << in.b << "] * " << a << ".dd;\n";
+                break;
+            }
+            default:  // unary
+                o << "  r" << in.dst << " = jet_unary<ORDER>(" << in.op << ", r" << in.a << ");\n";
+        }
+    }
+    if (order == 2) o << "  out[dir] = acc;\n";
+    o << "}\n";
+    return o.str();
+}
+
+bool driver_ok(CUresult r) { return r == CUDA_SUCCESS; }
+
+// Compiles (or loads from the content-hashed cache) the specialised kernel of `order`.  Never fails the call: on any problem the
+// state becomes -1 and the interpreter keeps serving.
+void specialize(ungar_b200_tape& T, int order) {
+    ungar_b200_tape::Special& S = T.special[order];
+    S.state = -1;
+    const char* off = getenv("UNGAR_B200_NO_NVRTC");
+    if ((off && off[0] == '1') || int(T.code.size()) > kSpecializeMax || T.code.empty()) return;
+    const std::string dir = machine_header_dir();
+    const std::string header = slurp(dir + "/tape_machine.cuh");
+    if (header.empty()) return;
+    int major = 0, minor = 0;
+    cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, T.device);
+    cudaDeviceGetAttribute(&minor, cudaDevAttrComputeCapabilityMinor, T.device);
+    if (major != 10) return;  // sm_100a only
+    const std::string arch = "sm_100a";
+    uint64_t h = fnv1a(T.code.data(), T.code.size() * sizeof(Instr));
+    h = fnv1a(T.consts.data(), T.consts.size() * sizeof(double), h);
+    h = fnv1a(&order, sizeof(order), h);
+    const int dims[4] = {T.n_slots, int(T.n_indep), int(T.n_dep), 1 /* generator version */};
+    h = fnv1a(dims, sizeof(dims), h);
+    h = fnv1a(arch.data(), arch.size(), h);
+    h = fnv1a(header.data(), header.size(), h);
+    S.key = h;
+    char name[64];
+    snprintf(name, sizeof(name), "%016llx.cubin", (unsigned long long)h);
+    const std::string cdir = cache_dir(), path = cdir + "/" + name;
+    std::string cubin = slurp(path);
+    S.from_cache = !cubin.empty();
+    if (cubin.empty()) {
+        const std::string src = generate_kernel_source(T, order);
+        nvrtcProgram prog;
+        if (nvrtcCreateProgram(&prog, src.c_str(), "tape_special.cu", 0, nullptr, nullptr) != NVRTC_SUCCESS) return;
+        const std::string inc1 = "-I" + dir, inc2 = "-I/usr/local/cuda/include", a = "--gpu-architecture=" + arch;
+        const char* opts[] = {a.c_str(), inc1.c_str(), inc2.c_str(), "--std=c++17", "-default-device", "--fmad=true"};
+        const auto t0 = std::chrono::steady_clock::now();
+        const nvrtcResult rc = nvrtcCompileProgram(prog, 6, opts);
+        S.compile_seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+        if (rc != NVRTC_SUCCESS) {
+            size_t n = 0;
+            nvrtcGetProgramLogSize(prog, &n);
+            std::string log(n, '\0');
+            nvrtcGetProgramLog(prog, log.data());
+            if (getenv("UNGAR_B200_NVRTC_VERBOSE")) fprintf(stderr, "ungar_b200: NVRTC failed, the interpreter serves this tape:\n%s\n", log.c_str());
+            nvrtcDestroyProgram(&prog);
+            return;
+        }
+        size_t n = 0;
+        if (nvrtcGetCUBINSize(prog, &n) != NVRTC_SUCCESS || n == 0) { nvrtcDestroyProgram(&prog); return; }
+        cubin.resize(n);
+        nvrtcGetCUBIN(prog, cubin.data());
+        nvrtcDestroyProgram(&prog);
+        mkdir(cdir.c_str(), 0755);
+        const std::string tmp = path + ".tmp" + std::to_string(getpid());
+        std::ofstream f(tmp, std::ios::binary);
+        f.write(cubin.data(), std::streamsize(cubin.size()));
+        f.close();
+        if (f) rename(tmp.c_str(), path.c_str());
+    }
+    cudaFree(nullptr);  // make sure the runtime's primary context is current for the driver API
+    if (!driver_ok(cuModuleLoadData(&S.module, cubin.data()))) return;
+    if (!driver_ok(cuModuleGetFunction(&S.fn, S.module, "tape_special"))) return;
+    S.state = 1;
+}
+
 template <int ORDER>
 int launch(ungar_b200_tape& T, const ub::tape::Seeds& seeds, const double* d_x, int64_t ld_x, int64_t batch, int ndir, double* d_out,
            int64_t ld_out, const int* out_slot, const double* weights, cudaStream_t stream) {
     const long long threads = (long long)batch * ndir;
     const long long stride  = (threads + 31) & ~31LL;
+    const long long blocks = (threads + 127) / 128;
+    if (blocks > 2147483647LL) return tfail(UNGAR_B200_EINVAL, "batch x directions too large for one launch");
+    // the straight-line kernel from the second call of this ORDER on (a function evaluated once never pays the compile)
+    if (T.calls[ORDER]++ >= kSpecializeAfter && T.special[ORDER].state == 0) specialize(T, ORDER);
+    if (T.special[ORDER].state == 1) {
+        ub::tape::Seeds sd = seeds;
+        long long ldx = ld_x, b64 = batch, ldo = ld_out;
+        int nd = ndir;
+        void* args[] = {&sd, &d_x, &ldx, &b64, &nd, &d_out, &ldo, &out_slot, &weights};
+        const CUresult r = cuLaunchKernel(T.special[ORDER].fn, unsigned(blocks), 1, 1, 128, 1, 1, 0, reinterpret_cast<CUstream>(stream), args, nullptr);
+        if (r != CUDA_SUCCESS) return tfail(UNGAR_B200_ECUDA, "cuLaunchKernel of the specialised tape kernel failed (%d)", int(r));
+        ub_count_launch();
+        return UNGAR_B200_OK;
+    }
     if (int rc = T.scratch.reserve(size_t(T.n_slots) * (ORDER + 1) * size_t(stride) * sizeof(double))) return rc;
     const ub::tape::Program P{static_cast<const Instr*>(T.d_code.ptr), static_cast<const double*>(T.d_consts.ptr), int(T.code.size()),
                               T.n_slots, int(T.n_indep), int(T.n_dep)};
-    const long long blocks = (threads + 127) / 128;
-    if (blocks > 2147483647LL) return tfail(UNGAR_B200_EINVAL, "batch x directions too large for one launch");
     ub::tape::tape_kernel<ORDER><<<unsigned(blocks), 128, 0, stream>>>(P, seeds, d_x, ld_x, batch, ndir, static_cast<double*>(T.scratch.ptr),
                                                                          stride, d_out, ld_out, out_slot, weights);
     ub_count_launch();
@@ -504,7 +707,23 @@ int ungar_b200_tape_create(const ungar_b200_tape_node* nodes, int64_t n_nodes, i
     return UNGAR_B200_OK;
 }
 
+// info[4 * order + {0, 1, 2, 3}] for order 0..2: state (0 not tried, 1 specialised, -1 interpreter), served from the kernel cache (0 / 1),
+// low and high 32 bits of the content hash.  Test / diagnostics hook of the NVRTC path.
+int ungar_b200_tape_special_info(const ungar_b200_tape* tape, int64_t* info) {
+    if (!tape || !info) return tfail(UNGAR_B200_EINVAL, "null argument");
+    for (int o = 0; o < 3; ++o) {
+        info[4 * o + 0] = tape->special[o].state;
+        info[4 * o + 1] = tape->special[o].from_cache ? 1 : 0;
+        info[4 * o + 2] = int64_t(tape->special[o].key & 0xffffffffull);
+        info[4 * o + 3] = int64_t(tape->special[o].key >> 32);
+    }
+    return UNGAR_B200_OK;
+}
+
 int ungar_b200_tape_destroy(ungar_b200_tape* tape) {
+    if (tape)
+        for (auto& sp : tape->special)
+            if (sp.module) cuModuleUnload(sp.module);
     if (!tape) return UNGAR_B200_OK;
     int count = 0;
     if (cudaGetDeviceCount(&count) == cudaSuccess && tape->device < count) cudaSetDevice(tape->device);

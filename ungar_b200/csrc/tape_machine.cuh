@@ -101,6 +101,64 @@ __device__ __forceinline__ Jet<ORDER> jet_log(const Jet<ORDER>& a) {
     return jet_chain(a, log(a.v), inv, -inv * inv);
 }
 
+// ---- one function per tape operation: the interpreter below and the NVRTC-specialised kernels (tape.cu) share them, so both
+// evaluate a tape with the same arithmetic.
+template <int ORDER>
+__device__ __forceinline__ Jet<ORDER> jet_unary(int op, const Jet<ORDER>& a) {
+    switch (op) {
+        case T_NEG: return jet_neg(a);
+        case T_SQRT: return jet_sqrt(a);
+        case T_SIN: { double s, c; sincos(a.v, &s, &c); return jet_chain(a, s, c, -s); }
+        case T_COS: { double s, c; sincos(a.v, &s, &c); return jet_chain(a, c, -s, -c); }
+        case T_TAN: { const double y = tan(a.v), f1 = 1.0 + y * y; return jet_chain(a, y, f1, 2.0 * y * f1); }
+        case T_ATAN: { const double f1 = 1.0 / (1.0 + a.v * a.v); return jet_chain(a, atan(a.v), f1, -2.0 * a.v * f1 * f1); }
+        case T_ACOS: { const double s2 = 1.0 - a.v * a.v, f1 = -rsqrt(s2); return jet_chain(a, acos(a.v), f1, a.v * f1 / s2); }
+        case T_ASIN: { const double s2 = 1.0 - a.v * a.v, f1 = rsqrt(s2); return jet_chain(a, asin(a.v), f1, a.v * f1 / s2); }
+        case T_EXP: return jet_exp(a);
+        case T_LOG: return jet_log(a);
+        default: {  // T_ABS — CppAD: abs'(x) = sign(x), sign(0) = 0
+            const double sg = double((a.v > 0.0) - (a.v < 0.0));
+            return Jet<ORDER>{fabs(a.v), sg * a.d, sg * a.dd};
+        }
+    }
+}
+// pow(a, k) with a CONSTANT exponent k: closed-form derivatives k a^(k-1), k (k-1) a^(k-2) — finite for a <= 0 (the
+// general exp(k log a) form gives NaN derivatives there, e.g. pow(x, 2.0) at x < 0).
+template <int ORDER>
+__device__ __forceinline__ Jet<ORDER> jet_pow_const(const Jet<ORDER>& a, double k) {
+    const double y = pow(a.v, k);
+    const double f1 = ORDER >= 1 ? k * pow(a.v, k - 1.0) : 0.0;
+    const double f2 = ORDER >= 2 ? k * (k - 1.0) * pow(a.v, k - 2.0) : 0.0;
+    return jet_chain(a, y, f1, f2);
+}
+template <int ORDER>
+__device__ __forceinline__ Jet<ORDER> jet_binary(int op, const Jet<ORDER>& a, const Jet<ORDER>& b) {
+    switch (op) {
+        case T_ADD: return jet_add(a, b);
+        case T_SUB: return jet_sub(a, b);
+        case T_MUL: return jet_mul(a, b);
+        case T_DIV: return jet_div(a, b);
+        case T_POW: {  // general power: exp(b log a)
+            Jet<ORDER> r = jet_exp(jet_mul(b, jet_log(a)));
+            r.v = pow(a.v, b.v);
+            return r;
+        }
+        default: {  // T_ATAN2: atan2(y = a, x = b)
+            const double r2 = b.v * b.v + a.v * a.v, inv = 1.0 / r2;
+            Jet<ORDER> r = jet_const<ORDER>(atan2(a.v, b.v));
+            if (ORDER >= 1) {
+                const double num = b.v * a.d - a.v * b.d;
+                r.d = num * inv;
+                if (ORDER >= 2) r.dd = ((b.v * a.dd - a.v * b.dd) - r.d * 2.0 * (b.v * b.d + a.v * a.d)) * inv;
+            }
+            return r;
+        }
+    }
+}
+__device__ __forceinline__ bool jet_compare(int op, double l, double r) {
+    return op == T_CLT ? l < r : op == T_CLE ? l <= r : op == T_CGT ? l > r : op == T_CGE ? l >= r : l == r;
+}
+
 template <int ORDER>
 __device__ __forceinline__ Jet<ORDER> load_slot(const double* __restrict__ scratch, long long stride, long long t, int slot) {
     constexpr int NC = ORDER + 1;
@@ -145,78 +203,19 @@ tape_kernel(Program P, Seeds S, const double* __restrict__ x_all, long long ld_x
                 break;
             }
             case T_CONST: r = jet_const<ORDER>(P.consts[in.a]); break;
-            case T_ADD: r = jet_add(load_slot<ORDER>(scratch, stride, t, in.a), load_slot<ORDER>(scratch, stride, t, in.b)); break;
-            case T_SUB: r = jet_sub(load_slot<ORDER>(scratch, stride, t, in.a), load_slot<ORDER>(scratch, stride, t, in.b)); break;
-            case T_MUL: r = jet_mul(load_slot<ORDER>(scratch, stride, t, in.a), load_slot<ORDER>(scratch, stride, t, in.b)); break;
-            case T_DIV: r = jet_div(load_slot<ORDER>(scratch, stride, t, in.a), load_slot<ORDER>(scratch, stride, t, in.b)); break;
-            case T_NEG: r = jet_neg(load_slot<ORDER>(scratch, stride, t, in.a)); break;
-            case T_SQRT: r = jet_sqrt(load_slot<ORDER>(scratch, stride, t, in.a)); break;
-            case T_SIN: {
-                const Jet<ORDER> a = load_slot<ORDER>(scratch, stride, t, in.a);
-                double s, c;
-                sincos(a.v, &s, &c);
-                r = jet_chain(a, s, c, -s);
+            case T_ADD: case T_SUB: case T_MUL: case T_DIV: case T_ATAN2:
+                r = jet_binary(in.op, load_slot<ORDER>(scratch, stride, t, in.a), load_slot<ORDER>(scratch, stride, t, in.b));
                 break;
-            }
-            case T_COS: {
-                const Jet<ORDER> a = load_slot<ORDER>(scratch, stride, t, in.a);
-                double s, c;
-                sincos(a.v, &s, &c);
-                r = jet_chain(a, c, -s, -c);
+            case T_POW:  // in.c >= 0: the exponent is the constant consts[in.c] (closed-form derivatives)
+                r = in.c >= 0 ? jet_pow_const(load_slot<ORDER>(scratch, stride, t, in.a), P.consts[in.c])
+                              : jet_binary(T_POW, load_slot<ORDER>(scratch, stride, t, in.a), load_slot<ORDER>(scratch, stride, t, in.b));
                 break;
-            }
-            case T_TAN: {
-                const Jet<ORDER> a = load_slot<ORDER>(scratch, stride, t, in.a);
-                const double y = tan(a.v), f1 = 1.0 + y * y;
-                r = jet_chain(a, y, f1, 2.0 * y * f1);
+            case T_NEG: case T_SQRT: case T_SIN: case T_COS: case T_TAN: case T_ATAN: case T_ACOS: case T_ASIN: case T_EXP: case T_LOG: case T_ABS:
+                r = jet_unary(in.op, load_slot<ORDER>(scratch, stride, t, in.a));
                 break;
-            }
-            case T_ATAN: {
-                const Jet<ORDER> a = load_slot<ORDER>(scratch, stride, t, in.a);
-                const double f1 = 1.0 / (1.0 + a.v * a.v);
-                r = jet_chain(a, atan(a.v), f1, -2.0 * a.v * f1 * f1);
-                break;
-            }
-            case T_ACOS: {
-                const Jet<ORDER> a = load_slot<ORDER>(scratch, stride, t, in.a);
-                const double s2 = 1.0 - a.v * a.v, f1 = -rsqrt(s2);
-                r = jet_chain(a, acos(a.v), f1, a.v * f1 / s2);
-                break;
-            }
-            case T_ASIN: {
-                const Jet<ORDER> a = load_slot<ORDER>(scratch, stride, t, in.a);
-                const double s2 = 1.0 - a.v * a.v, f1 = rsqrt(s2);
-                r = jet_chain(a, asin(a.v), f1, a.v * f1 / s2);
-                break;
-            }
-            case T_EXP: r = jet_exp(load_slot<ORDER>(scratch, stride, t, in.a)); break;
-            case T_LOG: r = jet_log(load_slot<ORDER>(scratch, stride, t, in.a)); break;
-            case T_ABS: {  // CppAD: abs'(x) = sign(x), sign(0) = 0
-                const Jet<ORDER> a = load_slot<ORDER>(scratch, stride, t, in.a);
-                const double sg = double((a.v > 0.0) - (a.v < 0.0));
-                r = Jet<ORDER>{fabs(a.v), sg * a.d, sg * a.dd};
-                break;
-            }
-            case T_POW: {  // general power: exp(b log a)
-                const Jet<ORDER> a = load_slot<ORDER>(scratch, stride, t, in.a), e = load_slot<ORDER>(scratch, stride, t, in.b);
-                r = jet_exp(jet_mul(e, jet_log(a)));
-                r.v = pow(a.v, e.v);
-                break;
-            }
-            case T_ATAN2: {  // atan2(y = a, x = b)
-                const Jet<ORDER> y = load_slot<ORDER>(scratch, stride, t, in.a), xx = load_slot<ORDER>(scratch, stride, t, in.b);
-                const double r2 = xx.v * xx.v + y.v * y.v, inv = 1.0 / r2;
-                r = jet_const<ORDER>(atan2(y.v, xx.v));
-                if (ORDER >= 1) {
-                    const double num = xx.v * y.d - y.v * xx.d;
-                    r.d = num * inv;
-                    if (ORDER >= 2) r.dd = ((xx.v * y.dd - y.v * xx.dd) - r.d * 2.0 * (xx.v * xx.d + y.v * y.d)) * inv;
-                }
-                break;
-            }
             case T_CLT: case T_CLE: case T_CGT: case T_CGE: case T_CEQ: {
                 const double l = scratch[(long long)in.a * (ORDER + 1) * stride + t], rr = scratch[(long long)in.b * (ORDER + 1) * stride + t];
-                const bool take = in.op == T_CLT ? l < rr : in.op == T_CLE ? l <= rr : in.op == T_CGT ? l > rr : in.op == T_CGE ? l >= rr : l == rr;
+                const bool take = jet_compare(in.op, l, rr);
                 r = load_slot<ORDER>(scratch, stride, t, take ? in.c : in.d);
                 break;
             }
