@@ -82,6 +82,8 @@ class Emitter:
         self.emit(f"v[{s}] = {expr};")
         return f"v[{s}]"
 
+    LOCALS_MAX = 300000  # statements; beyond this gcc -O3 needs hours for the local-scalar form (quadruped N = 100: 1.7 M statements)
+
     def reuse_slots(self) -> None:
         """Temporaries that die inside the function that defines them become local `const double` scalars (registers); only values
         that cross a function boundary keep a slot in the scratch array, and those slots are recycled by liveness — CppADCodeGen
@@ -89,6 +91,8 @@ class Emitter:
         import re
 
         stmts = [st for body in self.funcs for st in body]
+        if len(stmts) > self.LOCALS_MAX:
+            return  # one array slot per statement: compiles in minutes, runs ~2x slower (measured on the quadrotor)
         tok = re.compile(r"v\[(\d+)\]")
         first, last = {}, {}
         for idx, st in enumerate(stmts):

@@ -15,8 +15,8 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 def baseline(name, N):
     from oracle import codegen_baseline as CG
 
-    if not os.path.exists(os.path.join(CG.OUT, f"{name}_N{N}.npz")) and not os.path.isdir(os.path.join(CG.TAPES, f"{name}_N{N}")):
-        pytest.skip("oracle/_ref tapes / codegen libraries not built (python oracle/build_ref.py; python oracle/codegen_baseline.py)")
+    if not os.path.exists(os.path.join(CG.OUT, f"{name}_N{N}.npz")):  # never built inside a test: the quadruped takes ~30 minutes of gcc
+        pytest.skip("oracle/_ref/codegen libraries not built (python oracle/build_ref.py; python oracle/codegen_baseline.py)")
     return CG.Baseline(name, N)
 
 

@@ -20,8 +20,9 @@ NVCC_FLAGS = [
     "-Xcompiler", "-fPIC", "-shared",
     # cuSOLVER's dense LU backs the generic QP fallback (csrc/kkt_dense.cu); everything else is hand-written
     "-lcusolver", "-Xlinker", "-rpath=/usr/local/cuda/lib64",
-    # the generic tape path specialises hot tapes with NVRTC and loads the cubin through the driver API (csrc/tape.cu)
-    "-lnvrtc", "-L/usr/local/cuda/lib64/stubs", "-lcuda", "-ldl",
+    # the generic tape path specialises hot tapes with NVRTC and loads the cubin through the driver API (csrc/tape.cu); both are
+    # bound with dlopen at run time so that the library still loads on hosts without a GPU driver
+    "-ldl",
 ]
 
 

@@ -9,6 +9,7 @@
 #include <fstream>
 #include <sstream>
 #include <sys/stat.h>
+#include <type_traits>
 #include <cuda.h>
 #include <nvrtc.h>
 #include <cstdarg>
@@ -500,6 +501,51 @@ int check_call(const ungar_b200_tape* T, const void* x, int64_t batch, int64_t l
 constexpr int kSpecializeMax = 12000;   // instructions; NVRTC + ptxas time grows superlinearly (8 k: seconds, 40 k: minutes)
 constexpr int64_t kSpecializeAfter = 1; // specialise on the second call of an ORDER: a function evaluated once never pays the compile
 
+// The driver API and NVRTC are bound at run time (dlopen), not at link time: the library must load — and export its ABI — on hosts
+// without a GPU driver (libcuda.so.1 is part of the driver, not of the toolkit), where only the host-side analysis is usable.
+struct LazyApi {
+    bool tried = false, ok = false;
+    CUresult (*moduleLoadData)(CUmodule*, const void*) = nullptr;
+    CUresult (*moduleGetFunction)(CUfunction*, CUmodule, const char*) = nullptr;
+    CUresult (*moduleUnload)(CUmodule) = nullptr;
+    CUresult (*launchKernel)(CUfunction, unsigned, unsigned, unsigned, unsigned, unsigned, unsigned, unsigned, CUstream, void**, void**) = nullptr;
+    nvrtcResult (*createProgram)(nvrtcProgram*, const char*, const char*, int, const char* const*, const char* const*) = nullptr;
+    nvrtcResult (*compileProgram)(nvrtcProgram, int, const char* const*) = nullptr;
+    nvrtcResult (*getProgramLogSize)(nvrtcProgram, size_t*) = nullptr;
+    nvrtcResult (*getProgramLog)(nvrtcProgram, char*) = nullptr;
+    nvrtcResult (*getCUBINSize)(nvrtcProgram, size_t*) = nullptr;
+    nvrtcResult (*getCUBIN)(nvrtcProgram, char*) = nullptr;
+    nvrtcResult (*destroyProgram)(nvrtcProgram*) = nullptr;
+};
+LazyApi& lazy_api() {
+    static LazyApi api;
+    if (api.tried) return api;
+    api.tried = true;
+    void* cu = dlopen("libcuda.so.1", RTLD_NOW | RTLD_GLOBAL);
+    void* rt = dlopen("libnvrtc.so.12", RTLD_NOW | RTLD_GLOBAL);
+    if (!rt) rt = dlopen("libnvrtc.so", RTLD_NOW | RTLD_GLOBAL);
+    if (!rt) rt = dlopen("/usr/local/cuda/lib64/libnvrtc.so", RTLD_NOW | RTLD_GLOBAL);
+    if (!cu || !rt) return api;
+    bool all = true;
+    auto bind = [&](auto& fn, void* lib, const char* name) {
+        fn = reinterpret_cast<std::remove_reference_t<decltype(fn)>>(dlsym(lib, name));
+        all = all && fn != nullptr;
+    };
+    bind(api.moduleLoadData, cu, "cuModuleLoadData");
+    bind(api.moduleGetFunction, cu, "cuModuleGetFunction");
+    bind(api.moduleUnload, cu, "cuModuleUnload");
+    bind(api.launchKernel, cu, "cuLaunchKernel");
+    bind(api.createProgram, rt, "nvrtcCreateProgram");
+    bind(api.compileProgram, rt, "nvrtcCompileProgram");
+    bind(api.getProgramLogSize, rt, "nvrtcGetProgramLogSize");
+    bind(api.getProgramLog, rt, "nvrtcGetProgramLog");
+    bind(api.getCUBINSize, rt, "nvrtcGetCUBINSize");
+    bind(api.getCUBIN, rt, "nvrtcGetCUBIN");
+    bind(api.destroyProgram, rt, "nvrtcDestroyProgram");
+    api.ok = all;
+    return api;
+}
+
 uint64_t fnv1a(const void* data, size_t n, uint64_t h = 1469598103934665603ull) {
     const unsigned char* p = static_cast<const unsigned char*>(data);
     for (size_t i = 0; i < n; ++i) { h ^= p[i]; h *= 1099511628211ull; }
@@ -591,6 +637,8 @@ void specialize(ungar_b200_tape& T, int order) {
     S.state = -1;
     const char* off = getenv("UNGAR_B200_NO_NVRTC");
     if ((off && off[0] == '1') || int(T.code.size()) > kSpecializeMax || T.code.empty()) return;
+    LazyApi& api = lazy_api();
+    if (!api.ok) return;
     const std::string dir = machine_header_dir();
     const std::string header = slurp(dir + "/tape_machine.cuh");
     if (header.empty()) return;
@@ -615,26 +663,26 @@ void specialize(ungar_b200_tape& T, int order) {
     if (cubin.empty()) {
         const std::string src = generate_kernel_source(T, order);
         nvrtcProgram prog;
-        if (nvrtcCreateProgram(&prog, src.c_str(), "tape_special.cu", 0, nullptr, nullptr) != NVRTC_SUCCESS) return;
+        if (api.createProgram(&prog, src.c_str(), "tape_special.cu", 0, nullptr, nullptr) != NVRTC_SUCCESS) return;
         const std::string inc1 = "-I" + dir, inc2 = "-I/usr/local/cuda/include", a = "--gpu-architecture=" + arch;
         const char* opts[] = {a.c_str(), inc1.c_str(), inc2.c_str(), "--std=c++17", "-default-device", "--fmad=true"};
         const auto t0 = std::chrono::steady_clock::now();
-        const nvrtcResult rc = nvrtcCompileProgram(prog, 6, opts);
+        const nvrtcResult rc = api.compileProgram(prog, 6, opts);
         S.compile_seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
         if (rc != NVRTC_SUCCESS) {
             size_t n = 0;
-            nvrtcGetProgramLogSize(prog, &n);
+            api.getProgramLogSize(prog, &n);
             std::string log(n, '\0');
-            nvrtcGetProgramLog(prog, log.data());
+            api.getProgramLog(prog, log.data());
             if (getenv("UNGAR_B200_NVRTC_VERBOSE")) fprintf(stderr, "ungar_b200: NVRTC failed, the interpreter serves this tape:\n%s\n", log.c_str());
-            nvrtcDestroyProgram(&prog);
+            api.destroyProgram(&prog);
             return;
         }
         size_t n = 0;
-        if (nvrtcGetCUBINSize(prog, &n) != NVRTC_SUCCESS || n == 0) { nvrtcDestroyProgram(&prog); return; }
+        if (api.getCUBINSize(prog, &n) != NVRTC_SUCCESS || n == 0) { api.destroyProgram(&prog); return; }
         cubin.resize(n);
-        nvrtcGetCUBIN(prog, cubin.data());
-        nvrtcDestroyProgram(&prog);
+        api.getCUBIN(prog, cubin.data());
+        api.destroyProgram(&prog);
         mkdir(cdir.c_str(), 0755);
         const std::string tmp = path + ".tmp" + std::to_string(getpid());
         std::ofstream f(tmp, std::ios::binary);
@@ -643,8 +691,8 @@ void specialize(ungar_b200_tape& T, int order) {
         if (f) rename(tmp.c_str(), path.c_str());
     }
     cudaFree(nullptr);  // make sure the runtime's primary context is current for the driver API
-    if (!driver_ok(cuModuleLoadData(&S.module, cubin.data()))) return;
-    if (!driver_ok(cuModuleGetFunction(&S.fn, S.module, "tape_special"))) return;
+    if (!driver_ok(api.moduleLoadData(&S.module, cubin.data()))) return;
+    if (!driver_ok(api.moduleGetFunction(&S.fn, S.module, "tape_special"))) return;
     S.state = 1;
 }
 
@@ -662,7 +710,7 @@ int launch(ungar_b200_tape& T, const ub::tape::Seeds& seeds, const double* d_x, 
         long long ldx = ld_x, b64 = batch, ldo = ld_out;
         int nd = ndir;
         void* args[] = {&sd, &d_x, &ldx, &b64, &nd, &d_out, &ldo, &out_slot, &weights};
-        const CUresult r = cuLaunchKernel(T.special[ORDER].fn, unsigned(blocks), 1, 1, 128, 1, 1, 0, reinterpret_cast<CUstream>(stream), args, nullptr);
+        const CUresult r = lazy_api().launchKernel(T.special[ORDER].fn, unsigned(blocks), 1, 1, 128, 1, 1, 0, reinterpret_cast<CUstream>(stream), args, nullptr);
         if (r != CUDA_SUCCESS) return tfail(UNGAR_B200_ECUDA, "cuLaunchKernel of the specialised tape kernel failed (%d)", int(r));
         ub_count_launch();
         return UNGAR_B200_OK;
@@ -723,7 +771,7 @@ int ungar_b200_tape_special_info(const ungar_b200_tape* tape, int64_t* info) {
 int ungar_b200_tape_destroy(ungar_b200_tape* tape) {
     if (tape)
         for (auto& sp : tape->special)
-            if (sp.module) cuModuleUnload(sp.module);
+            if (sp.module && lazy_api().ok) lazy_api().moduleUnload(sp.module);
     if (!tape) return UNGAR_B200_OK;
     int count = 0;
     if (cudaGetDeviceCount(&count) == cudaSuccess && tape->device < count) cudaSetDevice(tape->device);
