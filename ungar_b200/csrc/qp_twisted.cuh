@@ -37,12 +37,20 @@ struct QpT {
     // per-warp shared memory (doubles)
     static constexpr int oLO = 0, oSM0 = G * LS, oSM1 = oSM0 + K::SMALL, oAB = oSM1 + K::SMALL, oY = oAB + K::APART, oMISC = oY + 32,
                          oBAR = oMISC + 4, PER_WARP = oBAR + 4;
-    static constexpr int SMEM_BYTES = 2 * PER_WARP * 8 + 64;  // + the trajectory's pointers (QtArgs) behind the two warps' regions
+    static constexpr int SLOT_BYTES = 2 * PER_WARP * 8 + 64;  // one trajectory: two warps' regions + its pointers (QtArgs) behind them
+    // SLOTS trajectories share a CTA (one CTA per SM) so that their chains can run in LOCKSTEP: the unrolled column loops are ~0.5 MB of
+    // straight-line code, the SM's instruction cache holds 32 KB, and with every warp at its own program counter the kernel was bound by
+    // instruction fetch (ncu r02d: sm__icc hit rate 55 %, the GPC-level instruction cache at 74 % of its request peak, stall_no_instruction
+    // the largest stall).  The warps of one direction meet at a named barrier once per group, stay within a few hundred instructions of
+    // each other, and the line the first one fetches serves the other six.
+    static constexpr int SLOTS = 7;
+    static constexpr int SMEM_BYTES = SLOTS * SLOT_BYTES;
+    static constexpr int THREADS = 64 * SLOTS;
     // factor image (shared memory during a group, global workspace afterwards): unscaled columns, 1 / sqrt(pivot), y
     static constexpr int fRI = 450, fY = 480, WS_GROUP = 510;
     // scratch vectors of the outward pass live behind the factor image in the LO region
     static constexpr int oVA = 512, oVC = 552, oNU2 = 592;
-    static_assert((PER_WARP * 8) % 16 == 0 && (oSM0 * 8) % 16 == 0 && (oSM1 * 8) % 16 == 0 && (oAB * 8) % 16 == 0 && (WS_GROUP * 8) % 16 == 0, "TMA alignment");
+    static_assert(SLOT_BYTES % 16 == 0 && (PER_WARP * 8) % 16 == 0 && (oSM0 * 8) % 16 == 0 && (oSM1 * 8) % 16 == 0 && (oAB * 8) % 16 == 0 && (WS_GROUP * 8) % 16 == 0, "TMA alignment");
     // column c of the factor (rows c .. 28) sits at bc(c) + row: even bases, so that rows (2k, 2k+1) are one 16-byte load
     __host__ __device__ static constexpr int bc(int c) { return 28 * c - (c * (c - 1)) / 2 + c / 2; }
 };
@@ -78,8 +86,13 @@ struct QtArgs {
     double* step;
     double* mult;        // may be null
     int N;
+    int slot;          // which trajectory of the CTA: named barrier 1 + slot pairs its two warps
     double delta;
+    int lock_threads;  // 32 x (active trajectories of the CTA): arrival count of the two lockstep barriers
 };
+static_assert(sizeof(QtArgs) <= 64, "QtArgs lives in the 64 bytes behind the two warps' regions");
+// named barriers: 1 + slot = the two warps of a trajectory; 8 / 9 = all top / all bottom warps of the CTA (lockstep, see QpT::SLOTS)
+__device__ __forceinline__ void qt_named_sync(int id, int threads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory"); }
 struct QtCtx {
     double* sm;       // this warp's shared memory
     int lane;
@@ -721,6 +734,8 @@ __device__ __forceinline__ double qt_upu(const double* sma, int lane, double del
 #define QT_ARGS (*reinterpret_cast<const QtArgs*>(reinterpret_cast<const double*>(smem_raw) + 2 * QpT::PER_WARP))
 #define QT_CHUNK(j) (QT_ARGS.rec + (long long)(j) * QK::NODE)
 #define QT_WSG(j) (QT_ARGS.ws + (long long)(j) * QpT::WS_GROUP)
+#define QT_PAIR_SYNC() qt_named_sync(1 + QT_ARGS.slot, 64)
+#define QT_LOCKSTEP(dir) qt_named_sync(8 + (dir), QT_ARGS.lock_threads)
 
 __device__ __forceinline__ void qt_store_step(const unsigned char* smem_raw, const double* sma, const double* vC, int j, int lane) {
     const int N = QT_ARGS.N;
@@ -758,9 +773,11 @@ __device__ __noinline__ void qt_top_chain(int lane, unsigned char* smem_raw) {
     double gdef = st ? QT_ARGS.rec[QK::tail(QT_ARGS.N) + QK::tG0 + lane] : 0.0;  // x_0 - x_measured
     cx.wait_small(0);
     for (int j = 0; j < m; ++j) {  // a = small_j (landed), b = small_{j+1} and A_j (in flight)
+        QT_LOCKSTEP(0);
         qt_pinv_t(cx.small(0), lane, true);
         rpart += gdef + qt_upu<false>(cx.small(0), lane, QT_ARGS.delta, s);  // S_jj += U P^-1 U^T + delta I ;  rhs = g - U t + rpart
         if (j > 0) qt_syrk(img, s, lane);
+        QT_LOCKSTEP(0);
         const double yj = qt_cholesky(s, rpart, img, QT_WSG(j), cx.sm + Q::oMISC, lane);
         if (act) {
             sY[lane] = yj;
@@ -768,6 +785,7 @@ __device__ __noinline__ void qt_top_chain(int lane, unsigned char* smem_raw) {
         }
         cx.wait_small(1);
         cx.wait(2);
+        QT_LOCKSTEP(0);
         {   // coupling rows of group j+1: (V P^-1 U^T) row, solved against L_j, parked in the image
             double e[G];
             const QtLane LN(lane);
@@ -776,6 +794,7 @@ __device__ __noinline__ void qt_top_chain(int lane, unsigned char* smem_raw) {
             __syncwarp();
             rpart = qt_store_coupling(e, img, sY, lane) - carry;  // -Lo y_j - V t_j
         }
+        QT_LOCKSTEP(0);
         {
             const QtLane LN(lane);
             qt_vpv<true>(cx.ab(), cx.small(1), cx.small(0), LN, s);  // S_{j+1,j+1} part: V P^-1 V^T row
@@ -791,7 +810,7 @@ __device__ __noinline__ void qt_top_chain(int lane, unsigned char* smem_raw) {
     // ---- middle group m: top part S = V P^-1 V^T - Lo Lo^T, rhs = defect - V t - Lo y
     qt_syrk(img, s, lane);
     rpart += gdef;
-    __syncthreads();  // the bottom warp has parked its part of S_mm and of the right-hand side in its image
+    QT_PAIR_SYNC();  // the bottom warp has parked its part of S_mm and of the right-hand side in its image
     if (act) {
         const double* mine = cx.sm + Q::PER_WARP + Q::oLO + lane * LS;
 #pragma unroll
@@ -810,7 +829,7 @@ __device__ __noinline__ void qt_top_chain(int lane, unsigned char* smem_raw) {
         cx.sm[Q::PER_WARP + Q::oY + lane] = num;
         qt_store_mult(smem_raw, num, m, lane);
     }
-    __syncthreads();  // nu_m is visible to the bottom warp
+    QT_PAIR_SYNC();  // nu_m is visible to the bottom warp
 
     // ======================================================== outward: groups m-1 .. 0
     // the factor images in the workspace were written through the generic proxy and come back through the async proxy (TMA)
@@ -818,17 +837,26 @@ __device__ __noinline__ void qt_top_chain(int lane, unsigned char* smem_raw) {
     __syncwarp();
     double* const vA = img + Q::oVA;
     double* const vC = img + Q::oVC;
+    // every load is issued one group ahead, as soon as the last reader of its buffer is done (the first version issued and awaited them
+    // at the top of each group: a full HBM latency per group on a 50-group dependent chain)
     cx.load_small(1, QT_CHUNK(m));  // Cp_m
+    if (m > 0) {
+        cx.load_small(0, QT_CHUNK(m - 1));
+        cx.load_ab(QT_CHUNK(m - 1));
+        cx.load_factor(QT_WSG(m - 1));
+    }
     cx.wait_small(1);
-    for (int j = m - 1; j >= 0; --j) {
-        cx.load_small(0, QT_CHUNK(j));
-        cx.load_ab(QT_CHUNK(j));
-        cx.load_factor(QT_WSG(j));
+    for (int j = m - 1; j >= 0; --j) {  // a = small_j, A_j, factor_j (in flight or landed), b = small_{j+1}
+        QT_LOCKSTEP(0);
         cx.wait_small(0);
         cx.wait(2);
         qt_pinv_t(cx.small(0), lane, true);
         for (int k = lane; k < 37; k += 32) vA[k] = qt_vT_nu(cx.ab(), cx.small(1), sY, k);  // a = V_j^T nu_{j+1}
         __syncwarp();
+        if (j > 0) {  // A_j and Cp_{j+1} have been consumed: their buffers take the next group's data
+            cx.load_small(1, QT_CHUNK(j - 1));
+            cx.load_ab(QT_CHUNK(j - 1));
+        }
         qt_apply_pinv(cx.small(0), vA, vC, lane);
         double z;
         {
@@ -840,6 +868,7 @@ __device__ __noinline__ void qt_top_chain(int lane, unsigned char* smem_raw) {
         cx.wait(3);
         const double nu = qt_outward_solve(img, z, lane);
         __syncwarp();
+        if (j > 0) cx.load_factor(QT_WSG(j - 1));  // vA / vC live behind the factor image
         sY[lane] = nu;
         __syncwarp();
         for (int k = lane; k < 37; k += 32) vA[k] += qt_uT_nu(cx.small(0), sY, k);
@@ -848,7 +877,7 @@ __device__ __noinline__ void qt_top_chain(int lane, unsigned char* smem_raw) {
         qt_store_step(smem_raw, cx.small(0), vC, j, lane);
         qt_store_mult(smem_raw, nu, j, lane);
         __syncwarp();
-        cx.swap();  // b = small_j: group j-1 needs its Cp rows
+        cx.swap();  // a = small_{j-1} (in flight), b = small_j: group j-1 needs its Cp rows
     }
 }
 
@@ -876,21 +905,25 @@ __device__ __noinline__ void qt_bottom_chain(int lane, unsigned char* smem_raw) 
     cx.load_ab(QT_CHUNK(N - 1));
     qt_pinv_t(cx.small(0), lane, false);
     for (int j = N; j > m; --j) {
+        QT_LOCKSTEP(1);
         rpart += qt_upu<true>(cx.small(0), lane, QT_ARGS.delta, s);  // S_jj = U P^-1 U^T + delta I ;  rhs = contact values - U t + rpart
         if (j < N) qt_syrk(img, s, lane);
         cx.wait_small(1);
         cx.wait(2);
+        QT_LOCKSTEP(1);
         qt_pinv_t(cx.small(1), lane, true);
         rpart += st ? cx.small(1)[QK::oG + lane] : 0.0;  // defect of stage j-1
         {
             const QtLane LN(lane);
             rpart -= qt_vpv<false>(cx.ab(), cx.small(0), cx.small(1), LN, s);  // S_jj += V P^-1 V^T ;  rhs -= V t_{j-1}
         }
+        QT_LOCKSTEP(1);
         const double yj = qt_cholesky(s, rpart, img, QT_WSG(j), cx.sm + Q::oMISC, lane);
         if (act) {
             sY[lane] = yj;
             QT_WSG(j)[Q::fY + lane] = yj;
         }
+        QT_LOCKSTEP(1);
         {   // coupling rows of group j-1: (U_{j-1} P^-1 V^T) row, solved against M_j, parked in the image
             double e[G];
             const QtLane LN(lane);
@@ -916,8 +949,8 @@ __device__ __noinline__ void qt_bottom_chain(int lane, unsigned char* smem_raw) 
         for (int c = 0; c + 1 < G; c += 2) qp_st2(img + lane * LS + c, s[c], s[c + 1]);
         qp_st2(img + lane * LS + G - 1, s[G - 1], rpart);
     }
-    __syncthreads();  // parked
-    __syncthreads();  // nu_m has arrived in sY
+    QT_PAIR_SYNC();  // parked
+    QT_PAIR_SYNC();  // nu_m has arrived in sY
 
     // ======================================================== outward: groups m+1 .. N (and the steps d_m .. d_N)
     // invariant at group j: a = small_{j-1} (P^-1, t in place), A_{j-1} landed, sY = nu_{j-1}
@@ -927,20 +960,20 @@ __device__ __noinline__ void qt_bottom_chain(int lane, unsigned char* smem_raw) 
     double* const vC = img + Q::oVC;
     double* const nu2 = img + Q::oNU2;
     cx.load_ab(QT_CHUNK(m));
-    cx.wait(2);
-    for (int j = m + 1; j <= N; ++j) {
+    if (m + 1 <= N) cx.load_factor(QT_WSG(m + 1));
+    if (m + 1 < N) cx.load_small(1, QT_CHUNK(m + 1));
+    for (int j = m + 1; j <= N; ++j) {  // loads are issued one group ahead (see the top chain)
+        QT_LOCKSTEP(1);
         const bool last = j == N;
-        cx.load_factor(QT_WSG(j));
-        if (!last) {
-            cx.load_small(1, QT_CHUNK(j));
-            cx.wait_small(1);
-        } else {
+        if (!last) cx.wait_small(1);
+        else {
             for (int k = lane; k < 96; k += 32) cx.small(1)[QK::oCp + k] = 0.0;  // group N has no contact rows
             __syncwarp();
         }
         for (int k = lane; k < 37; k += 32) vA[k] = qt_uT_nu(cx.small(0), sY, k);  // b = U_{j-1}^T nu_{j-1}
         __syncwarp();
         qt_apply_pinv(cx.small(0), vA, vC, lane);
+        cx.wait(2);  // A_{j-1}
         double z;
         {
             const QtLane LN(lane);
@@ -949,20 +982,21 @@ __device__ __noinline__ void qt_bottom_chain(int lane, unsigned char* smem_raw) 
         cx.wait(3);
         const double nu = qt_outward_solve(img, z, lane);
         __syncwarp();
+        if (!last) cx.load_factor(QT_WSG(j + 1));  // vA / vC / nu2 live behind the factor image
         nu2[lane] = nu;
         __syncwarp();
         for (int k = lane; k < 37; k += 32) vA[k] += qt_vT_nu(cx.ab(), cx.small(1), nu2, k);
         __syncwarp();
+        if (!last) cx.load_ab(QT_CHUNK(j));  // A_{j-1} has been consumed
         qt_apply_pinv(cx.small(0), vA, vC, lane);
         qt_store_step(smem_raw, cx.small(0), vC, j - 1, lane);  // d_{j-1}
         qt_store_mult(smem_raw, nu, j, lane);
         sY[lane] = nu;
         __syncwarp();
         if (!last) {
-            cx.swap();  // a = small_j
+            cx.swap();  // a = small_j, b = the buffer small_{j-1} leaves
+            if (j + 1 < N) cx.load_small(1, QT_CHUNK(j + 1));
             qt_pinv_t(cx.small(0), lane, true);
-            cx.load_ab(QT_CHUNK(j));
-            cx.wait(2);
         }
     }
     // d_N = -P_N^-1 (q_N + nu_N)
@@ -971,28 +1005,33 @@ __device__ __noinline__ void qt_bottom_chain(int lane, unsigned char* smem_raw) 
         QT_ARGS.step[13 * N + lane] = -(tail[QK::tQN + lane] + sY[lane]) / tail[QK::tHN + lane];
     }
 }
+#undef QT_PAIR_SYNC
+#undef QT_LOCKSTEP
 #undef QT_ARGS
 #undef QT_CHUNK
 #undef QT_WSG
 
-__global__ void __launch_bounds__(64, 7)
+__global__ void __launch_bounds__(QpT::THREADS, 1)
 qp_twisted_kernel(const double* __restrict__ rec_all, long long ld_rec, double* __restrict__ ws_all, double* __restrict__ step_all, long long ld_step,
                   double* __restrict__ mult_all, long long ld_mult, int N, long long batch, double delta, const int* __restrict__ skip_status) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-    const long long b = blockIdx.x;
-    if (b >= batch) return;
-    if (skip_status && skip_status[2 * b] != 0) return;  // SQP loop: this trajectory has stopped (CTA-uniform)
-    {
+    extern __shared__ __align__(16) unsigned char smem_cta[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, slot = warp >> 1, wib = warp & 1;
+    unsigned char* const smem_raw = smem_cta + slot * QpT::SLOT_BYTES;  // this trajectory's two regions + QtArgs
+    const long long b = (long long)blockIdx.x * QpT::SLOTS + slot;
+    // SQP loop: a trajectory that has stopped is skipped (uniform over its two warps)
+    const bool active = b < batch && !(skip_status && skip_status[2 * b] != 0);
+    if (active) {
         uint64_t* const bars = reinterpret_cast<uint64_t*>(reinterpret_cast<double*>(smem_raw) + wib * QpT::PER_WARP + QpT::oBAR);
         if (lane < 4) qt_bar_init(bars + lane);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-        if (threadIdx.x == 0)
-            *reinterpret_cast<QtArgs*>(reinterpret_cast<double*>(smem_raw) + 2 * QpT::PER_WARP) =
-                QtArgs{rec_all + b * ld_rec, ws_all + b * (long long)(N + 1) * QpT::WS_GROUP, step_all + b * ld_step,
-                       mult_all ? mult_all + b * ld_mult : nullptr, N, delta};
     }
-    __syncthreads();
+    const int n_active = __syncthreads_count(active && lane == 0 && wib == 0);
+    if (!active) return;  // from here on only named barriers with explicit arrival counts
+    if (wib == 0 && lane == 0)
+        *reinterpret_cast<QtArgs*>(reinterpret_cast<double*>(smem_raw) + 2 * QpT::PER_WARP) =
+            QtArgs{rec_all + b * ld_rec, ws_all + b * (long long)(N + 1) * QpT::WS_GROUP, step_all + b * ld_step,
+                   mult_all ? mult_all + b * ld_mult : nullptr, N, slot, delta, 32 * n_active};
+    qt_named_sync(1 + slot, 64);
     if (wib == 0) qt_top_chain(lane, smem_raw);
     else qt_bottom_chain(lane, smem_raw);
 }

@@ -719,12 +719,12 @@ int launch_qp_twisted(ungar_b200_model& mdl, const void* rec, bool rec_is_compac
     static PerDevice configured;
     if (!configured[mdl.desc.device]) {
         UB_CUDA(cudaFuncSetAttribute(ub::qp_twisted_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, Q::SMEM_BYTES));
-        // 7 CTAs x 31.5 KB need the largest shared-memory carveout (the driver's default pick was 196 KB: 6 CTAs, a second wave)
+        // one CTA of 7 trajectories x 29.4 KB per SM needs the largest shared-memory carveout
         UB_CUDA(cudaFuncSetAttribute(ub::qp_twisted_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
         configured[mdl.desc.device] = 1;
     }
     if (batch > 2147483647LL) return fail(UNGAR_B200_EINVAL, "batch too large for one launch");
-    ub::qp_twisted_kernel<<<unsigned(batch), 64, Q::SMEM_BYTES, stream>>>(
+    ub::qp_twisted_kernel<<<unsigned((batch + Q::SLOTS - 1) / Q::SLOTS), Q::THREADS, Q::SMEM_BYTES, stream>>>(
         static_cast<const double*>(rec), ld_rec, static_cast<double*>(mdl.ws_qp.ptr), static_cast<double*>(steps), ld_steps,
         static_cast<double*>(mult), ld_mult, mdl.N, batch, 1e-9, skip_status);
     ++g_launches;
