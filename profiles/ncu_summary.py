@@ -32,6 +32,8 @@ KEYS = [
     "smsp__average_warps_issue_stalled_branch_resolving_per_issue_active.ratio",
     "smsp__average_warps_issue_stalled_selected_per_issue_active.ratio",
     "smsp__average_warps_issue_stalled_not_selected_per_issue_active.ratio",
+    "smsp__average_warp_latency_per_inst_issued.ratio",
+    "sm__icc_request_hit_rate.pct", "gcc__cache_requests_type_instruction.sum.pct_of_peak_sustained_elapsed",  # instruction fetch
 ]
 
 

@@ -8,7 +8,7 @@ for m in quadruped quadrotor rc_car; do python profiles/sqp_timing.py $m; done >
 cat gpurun_out/sqp_timing_${TAG}.log
 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/sqp_launches_${TAG}.csv \
     python profiles/sqp_timing.py quadruped > gpurun_out/ncu_sqp_launches_${TAG}.log 2>&1
-ncu --set full --clock-control none --import-source on -k regex:"qp_schur" -s 2 -c 1 -f -o gpurun_out/sqp_${TAG} \
+ncu --set full --clock-control none --import-source on -k regex:"qp_twisted|qp_schur" -s 2 -c 1 -f -o gpurun_out/sqp_${TAG} \
     python profiles/sqp_timing.py quadruped > gpurun_out/ncu_sqp_full_${TAG}.log 2>&1
 ncu --set full --clock-control none --import-source on -k regex:"line_search" -s 2 -c 1 -f -o gpurun_out/ls_${TAG} \
     python profiles/sqp_timing.py quadruped > gpurun_out/ncu_ls_full_${TAG}.log 2>&1

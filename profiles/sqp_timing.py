@@ -13,7 +13,8 @@ from ungar_b200 import workloads as W
 name = sys.argv[1] if len(sys.argv) > 1 else "quadruped"
 N, B = {"quadruped": (100, 1024), "quadrotor": (30, 4096), "rc_car": (60, 8192)}[name]
 mid = W.MODEL_IDS[name]
-m = ungar_b200.Model(name, N, dtype="f64", barrier=ungar_b200.EXAMPLE_BARRIER[mid])
+# the quadruped's consumers work on the compact record (csrc/compact.cuh), which is what ungar_b200_sqp_solve uses internally
+m = ungar_b200.Model(name, N, dtype="f64", barrier=ungar_b200.EXAMPLE_BARRIER[mid], record_format="compact" if name == "quadruped" else "dense")
 xp0 = torch.from_numpy(W.synthetic_batch(mid, N, B)).cuda()
 xp = xp0.clone()
 rec = m.kkt_blocks(xp)

@@ -363,13 +363,17 @@ class Blueprint:
 class TapeFunction:
     """Mirror of Ungar::Autodiff::Function (function.hpp:77-361) for an arbitrary taped lambda."""
 
-    def __init__(self, blueprint: Blueprint, device: int = 0):
+    def __init__(self, blueprint: Blueprint, device: int = 0, _recorded=None):
         bp = blueprint
         self._nx, self._np = bp.independentVariableSize, bp.parameterSize
-        nodes, deps, consts = record(bp.functionImpl, bp.tapingPoint)
+        # `_recorded`: a tape saved by save() — the counterpart of the reference loading an existing model library instead of taping
+        # the lambda again (function.hpp:420-451), except that what is stored is the tape itself, so nothing can go stale
+        nodes, deps, consts = _recorded if _recorded is not None else record(bp.functionImpl, bp.tapingPoint)
+        self._recorded = (nodes, deps, consts)
         self._tape = TapeHandle(nodes, self._nx + self._np, deps, consts, device)
         self._ny = deps.size
         self.name = bp.name
+        self._enabled = int(bp.enabledDerivatives)
         self._jac = bool(bp.enabledDerivatives & JACOBIAN)
         self._hes = bool(bp.enabledDerivatives & HESSIAN) and self._ny == 1  # scalar functions only (function.hpp:136-137)
         self._jr = self._jc = self._hr = self._hc = np.zeros(0, np.int64)
@@ -383,6 +387,21 @@ class TapeFunction:
             keep = (r < self._nx) & (c < self._nx) & (c >= r)
             self._hr, self._hc = r[keep], c[keep]
             self._tape.set_hessian_elements(self._hr, self._hc)
+
+    def save(self, path: str) -> None:
+        """Writes the recorded tape (nodes, dependents, sizes) to a compressed .npz; load() rebuilds the function without the lambda."""
+        nodes, deps, consts = self._recorded
+        np.savez_compressed(path, nodes=nodes, dependents=deps, dependent_constants=consts, sizes=np.array([self._nx, self._np, self._enabled]),
+                            name=np.array(self.name))
+
+    @classmethod
+    def load(cls, path: str, device: int = 0) -> "TapeFunction":
+        z = np.load(path)
+        nx, npar, enabled = (int(v) for v in z["sizes"])
+        bp = Blueprint.__new__(Blueprint)
+        bp.functionImpl, bp.independentVariableSize, bp.parameterSize = None, nx, npar
+        bp.name, bp.enabledDerivatives, bp.tapingPoint = str(z["name"]), enabled, None
+        return cls(bp, device, _recorded=(z["nodes"].astype(NODE_DTYPE), z["dependents"], z["dependent_constants"]))
 
     def IndependentVariableSize(self): return self._nx  # noqa: E704
     def ParameterSize(self): return self._np  # noqa: E704
