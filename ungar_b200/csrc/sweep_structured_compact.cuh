@@ -18,13 +18,16 @@ struct QuadrupedCompactSweep {
     static_assert((PER_WARP * 8) % 16 == 0 && (RUN + 1) * CORE <= 848, "shared memory layout");
     static constexpr int WARPS = 2;
     static constexpr int SMEM_BYTES = PER_WARP * 8;
+    // resident teams per SM: the compact image is 5 KB per warp (23 KB per team), so registers set the limit — 128 per thread
+    // (no spills) leave room for 8 teams = 16 warps; the dense sweep's 24 KB pair image caps it at 6
+    static constexpr int TEAMS_PER_SM = 8;
     static constexpr int cR = 0, cQ = 9, cE = 21, cXN = 25, cSGN = 38, cM = 39;
 };
 
 // One CTA = one TEAM of two warps sharing the run's inputs; warp w owns node 2 p + w of every node pair and its OWN staging image: one
 // compact chunk (compact.cuh), handed to the TMA engine with ONE bulk store per node (5008 B).
 template <bool BARRIER>
-__global__ void __launch_bounds__(64, 6)
+__global__ void __launch_bounds__(64, QuadrupedCompactSweep::TEAMS_PER_SM)
 quadruped_compact_kernel(const double* __restrict__ xp_all, long long ld_xp, double* __restrict__ rec_all, long long ld_rec,
                             double* __restrict__ partials, int N, int run_len, int runs_per_traj, long long total_runs,
                             BarrierCoef<double> bar, unsigned int* __restrict__ sched, const int* __restrict__ active = nullptr,

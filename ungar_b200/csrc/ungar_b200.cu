@@ -452,7 +452,7 @@ int launch_structured_compact(ungar_b200_model& mdl, const double* xp, int64_t b
     const int runs_per_traj = (mdl.N + 9) / 10;
     const int run_len       = 2 * ((mdl.N + 2 * runs_per_traj - 1) / (2 * runs_per_traj));
     const long long total_runs = (long long)batch * runs_per_traj;
-    const unsigned grid = unsigned(std::min<long long>(total_runs, (long long)sm_count * 6));  // persistent: 6 teams / SM
+    const unsigned grid = unsigned(std::min<long long>(total_runs, (long long)sm_count * Q::TEAMS_PER_SM));  // persistent
     if (int rc = ensure_sched(mdl, stream)) return rc;
     int slot = -1;
     if (g_ring.enabled) {
