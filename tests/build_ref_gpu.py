@@ -60,6 +60,8 @@ def main(force: bool = False) -> bool:
     targets = [("function_tests_gpu", os.path.join(ROOT, "oracle/ref_drivers/function_tests.cpp"), []),
                ("function_example_gpu", os.path.join(REF, "example/autodiff/function.example.cpp"), []),
                ("soft_sqp_tests_gpu", os.path.join(HERE, "ref_drivers/soft_sqp_tests.cpp"), [])]
+    for tag, coeff in (("a", "2.0"), ("b", "3.0")):  # same function name, same folder, different lambda (tests/test_tape_host.py)
+        targets.append((f"stale_tape_{tag}", os.path.join(HERE, "ref_drivers/stale_tape_driver.cpp"), [f"-DCOEFF={coeff}"]))
     for example in ("quadrotor", "rc_car", "quadruped"):
         targets.append((f"example_{example}_gpu", driver, [f'-DUNGAR_EXAMPLE_SOURCE="{REF}/example/mpc/{example}.example.cpp"']))
     for name, src, extra in targets:

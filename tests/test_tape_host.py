@@ -190,3 +190,39 @@ def test_product_header_records_the_same_tapes_as_the_oracle_shim(example, funct
         assert a[1] == b[1] and np.array_equal(a[2], b[2]) and a[0].size == b[0].size
         for field in ("op", "a", "b", "c", "d", "k"):
             assert np.array_equal(a[0][field], b[0][field]), (fn, field)
+
+
+def test_a_changed_lambda_under_the_same_name_is_taped_again():
+    """SURVEY.md §5 / function.hpp:420-451: the reference keys its generated library by NAME, so a changed lambda under an unchanged
+    name silently runs the old code.  Two builds of one driver (tests/ref_drivers/stale_tape_driver.cpp: y = COEFF x0 x1, COEFF = 2 / 3)
+    share the function name and the codegen folder and call the reference's unchanged MakeFunction with recompileLibraries = false.
+    The product's tapes carry the identity of the executable that recorded them: the same build finds its tape again ("Loading"), the
+    other build finds it stale, deletes it before the reference looks for it and tapes its own lambda ("Compiling")."""
+    import os
+    import shutil
+    import subprocess
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = {t: os.path.join(root, "tests", "_ref_gpu", f"stale_tape_{t}") for t in "ab"}
+    if not all(os.path.exists(e) for e in exe.values()):
+        pytest.skip("tests/_ref_gpu was not built (needs /root/reference at build time)")
+    for d in ("stale_probe", "stale_probe_internal"):
+        shutil.rmtree(os.path.join(root, "tests", "_ref_gpu", "tapes", d), ignore_errors=True)
+    tape = os.path.join(root, "tests", "_ref_gpu", "tapes", "stale_probe", "cppad_cg", "stale_probe_lib.so")
+
+    def run(tag):
+        proc = subprocess.run([exe[tag]], capture_output=True, text=True, cwd=os.path.dirname(exe[tag]))
+        assert proc.returncode == 0, proc.stderr
+        raw = open(tape, "rb").read()
+        nn = int(np.frombuffer(raw, dtype=np.int64, count=5)[1])
+        consts = np.frombuffer(raw, dtype=A.NODE_DTYPE, count=nn, offset=40)["k"]
+        return ("Loading shared library" in proc.stdout, "Compiling shared library" in proc.stdout, set(consts.tolist()))
+
+    loaded, compiled, k = run("a")
+    assert compiled and not loaded and 2.0 in k and 3.0 not in k
+    loaded, compiled, k = run("a")          # same build: the tape is found again by name, exactly like the reference's library
+    assert loaded and not compiled and 2.0 in k
+    loaded, compiled, k = run("b")          # other lambda, same name: NOT served from a's tape
+    assert compiled and not loaded and 3.0 in k and 2.0 not in k
+    loaded, compiled, k = run("a")
+    assert compiled and not loaded and 2.0 in k and 3.0 not in k

@@ -20,6 +20,7 @@
 
 #include <cmath>
 #include <cstdint>
+#include <cstdlib>
 #include <cstring>
 #include <filesystem>
 #include <fstream>
@@ -114,6 +115,16 @@ inline void read_sets(std::istream& f, SparsitySets& s) {
     }
 }
 
+// Identity of the running executable: a tape is only trusted by the build that recorded it.
+inline std::string taped_by() {
+    std::error_code ec;
+    const std::filesystem::path exe = std::filesystem::read_symlink("/proc/self/exe", ec);
+    if (ec) return "unknown";
+    const auto size = std::filesystem::file_size(exe, ec);
+    const auto when = std::filesystem::last_write_time(exe, ec).time_since_epoch().count();
+    return exe.string() + "|" + std::to_string(static_cast<unsigned long long>(size)) + "|" + std::to_string(static_cast<long long>(when));
+}
+
 inline void save(const LibraryImage& img, const std::string& path) {
     const Tape& t = *img.tape;
     std::ofstream f(path, std::ios::binary);
@@ -129,8 +140,64 @@ inline void save(const LibraryImage& img, const std::string& path) {
     f.write(reinterpret_cast<const char*>(t.dep_const.data()), nd * sizeof(double));
     write_sets(f, img.customJac);
     write_sets(f, img.customHes);
+    const std::string who = taped_by();
+    const std::uint64_t nw = who.size();
+    f.write(reinterpret_cast<const char*>(&nw), 8);
+    f.write(who.data(), static_cast<std::streamsize>(nw));
     if (!f) throw std::runtime_error("ungar_b200: cannot write tape " + path);
 }
+
+// Who taped the file at `path` ("" if it is not one of ours or predates the fingerprint).
+inline std::string tape_owner(const std::string& path) {
+    std::ifstream f(path, std::ios::binary);
+    std::uint64_t magic = 0, nn = 0, nd = 0;
+    std::int64_t ni = 0, flags = 0;
+    f.read(reinterpret_cast<char*>(&magic), 8);
+    f.read(reinterpret_cast<char*>(&nn), 8);
+    f.read(reinterpret_cast<char*>(&nd), 8);
+    f.read(reinterpret_cast<char*>(&ni), 8);
+    f.read(reinterpret_cast<char*>(&flags), 8);
+    if (!f || magic != 0x3130505430303242ull) return {};
+    f.seekg(static_cast<std::streamoff>(nn * sizeof(Node) + nd * (sizeof(std::int32_t) + sizeof(double))), std::ios::cur);
+    SparsitySets skip;
+    read_sets(f, skip);
+    read_sets(f, skip);
+    std::uint64_t nw = 0;
+    f.read(reinterpret_cast<char*>(&nw), 8);
+    if (!f || nw > 4096) return {};
+    std::string who(nw, '\0');
+    f.read(who.data(), static_cast<std::streamsize>(nw));
+    return f ? who : std::string{};
+}
+inline bool is_tape_file(const std::string& path) {
+    std::ifstream f(path, std::ios::binary);
+    std::uint64_t magic = 0;
+    f.read(reinterpret_cast<char*>(&magic), 8);
+    return f && magic == 0x3130505430303242ull;
+}
+
+// Deletes the tapes below `folder` that another build of a program recorded (see LinuxDynamicLib).  Runs once per process, before
+// the reference's IsLibraryAvailable() looks for them.
+inline int sweep_stale_tapes(const std::filesystem::path& folder) {
+    int removed = 0;
+    std::error_code ec;
+    if (!std::filesystem::is_directory(folder, ec)) return 0;
+    const std::string me = taped_by();
+    std::vector<std::filesystem::path> stale;
+    for (std::filesystem::recursive_directory_iterator it(folder, std::filesystem::directory_options::skip_permission_denied, ec), end; !ec && it != end;
+         it.increment(ec)) {
+        if (!it->is_regular_file(ec)) continue;
+        const std::string p = it->path().string();
+        if (it->path().extension() != ".so" || !is_tape_file(p)) continue;
+        if (tape_owner(p) != me) stale.push_back(it->path());
+    }
+    for (const auto& p : stale)
+        if (std::filesystem::remove(p, ec)) ++removed;
+    return removed;
+}
+#ifdef UNGAR_CODEGEN_FOLDER
+inline const int g_stale_tapes_removed = sweep_stale_tapes(UNGAR_CODEGEN_FOLDER);
+#endif
 
 inline LibraryImage load(const std::string& path) {
     std::ifstream f(path, std::ios::binary);
@@ -157,6 +224,17 @@ inline LibraryImage load(const std::string& path) {
     read_sets(f, img.customJac);
     read_sets(f, img.customHes);
     if (!f) throw std::runtime_error("ungar_b200: truncated tape file: " + path);
+    std::uint64_t nw = 0;
+    std::string who;
+    f.read(reinterpret_cast<char*>(&nw), 8);
+    if (f && nw <= 4096) {
+        who.assign(nw, '\0');
+        f.read(who.data(), static_cast<std::streamsize>(nw));
+    }
+    const char* trust = std::getenv("UNGAR_B200_TRUST_TAPES");  // tools that read tapes recorded by another program (tape_tool, tests)
+    if (!(trust && trust[0] == '1') && (!f || who != taped_by()))
+        throw std::runtime_error("ungar_b200: stale tape " + path + ": it was recorded by another build (" + (who.empty() ? "unknown" : who) +
+                                 "), so the lambda may have changed; delete the file or pass recompileLibraries = true");
     return img;
 }
 
@@ -545,8 +623,14 @@ class DynamicLib {
     SparsitySets customJac, customHes;
 };
 
-// The "shared library" is one file: the tape plus the options of its model (the reference finds it again by name on the next
-// run, function.hpp:420-451).
+// The "shared library" is one file: the tape plus the options of its model.  The reference finds a library again BY NAME on the next
+// run and then skips the lambda (function.hpp:420-451) — a changed lambda under an unchanged name silently runs the old code
+// (SURVEY.md §5).  That decision is taken inside the reference's unchanged function.hpp, before this header sees the lambda, so the
+// defence sits in the file: every tape records WHICH EXECUTABLE taped it (path, size, modification time of /proc/self/exe).  A
+// rebuilt program — the only way a C++ lambda changes — no longer matches: at start-up the stale tapes under UNGAR_CODEGEN_FOLDER
+// are deleted (IsLibraryAvailable() turns false, the lambda is taped again: milliseconds to a second), and a stale tape anywhere
+// else fails LOUDLY on load instead of being evaluated.  What is expensive — the NVRTC-compiled kernel of a tape — is cached under
+// a hash of the tape's CONTENT (csrc/tape.cu), so an unchanged lambda in a rebuilt program still starts warm.
 template <class Base>
 class LinuxDynamicLib : public DynamicLib<Base> {
   public:
