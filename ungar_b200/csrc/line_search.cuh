@@ -105,8 +105,13 @@ __device__ __forceinline__ void ls_node_values(const T* x, int N, int k, const B
     }
 }
 
+// Residency: the trial vector takes (n_dec + n_par) * 8 bytes of shared memory per CTA (quadruped N = 100: 53.5 KB -> 4 CTAs per SM);
+// left alone ptxas takes 205 registers for the quadruped functors, which caps the SM at 2 CTAs = 8 warps of a latency-bound kernel.
+template <class Mdl>
+struct LsResidency { static constexpr int MIN_CTAS = Mdl::LEGS > 0 ? 4 : 1; };
+
 template <class Mdl, class T>
-__global__ void __launch_bounds__(LS_THREADS)
+__global__ void __launch_bounds__(LS_THREADS, LsResidency<Mdl>::MIN_CTAS)
 line_search_kernel(T* __restrict__ xp_all, long long ld_xp, const T* __restrict__ dw_all, long long ld_dw, int N,
                    BarrierCoef<T> bar, LineSearchParams P, int* __restrict__ status_all, T* __restrict__ info_all) {
     constexpr int NX = Mdl::NX, NU = Mdl::NU, NZ = Mdl::NZ;
