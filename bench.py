@@ -52,6 +52,8 @@ def parse_args():
     ap.add_argument("--dtype", default="f64", choices=["f32", "f64"])
     ap.add_argument("--cpu-seconds", type=float, default=15.0, help="CPU work budget of the cpu_baseline leg")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-other-configs", action="store_true",
+                    help="skip the short legs on BASELINE configs 2 and 3 (quadrotor / RC car, fp32) that the default line carries as other_configs")
     ap.add_argument("--mode", default="kkt", choices=["kkt", "jacobian"],
                     help="kkt: full KKT block set (default, BASELINE configs[2..4]); jacobian: g + A only (configs[1], ungar_b200_jacobian_blocks)")
     return ap.parse_args()
@@ -592,10 +594,48 @@ def ours(args, rank: int, local_rank: int, world: int):
         "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu, "parity": parity, "sqp_loop": sqp,
         "collective": collective,
     }
+    if default_headline(args) and world == 1:
+        line["other_configs"] = other_configs(args)
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
+
+
+def default_headline(args) -> bool:
+    return (args.model == "quadruped" and args.horizon == 100 and args.dtype == "f64" and args.mode == "kkt" and not args.global_batch
+            and not args.no_other_configs and not args.no_cpu_baseline)
+
+
+def other_configs(args) -> dict:
+    """BASELINE.json configs 2 and 3 (the fp32 small-model sweeps north_star's roofline clause is about) measured by this same script
+    in short sub-runs, so that their numbers are in the driver's bench line and not only in builder-run records: device-resident
+    value, kernel time, roofline fraction on the config's own byte count, strict parity against the oracle, end-to-end value.
+    Each sub-run is `python bench.py --model ... --no-other-configs` (its own process: a model handle per process keeps the timing clean)."""
+    out = {}
+    runs = {
+        "configs[1] quadrotor N=30 B=4096 f32, Jacobian sweep (g + A)": ["--model", "quadrotor", "--horizon", "30", "--batch", "4096", "--dtype", "f32", "--mode", "jacobian"],
+        "configs[1] quadrotor N=30 B=4096 f32, full KKT block set": ["--model", "quadrotor", "--horizon", "30", "--batch", "4096", "--dtype", "f32"],
+        "configs[2] rc_car N=60 B=8192 f32, full KKT block set": ["--model", "rc_car", "--horizon", "60", "--batch", "8192", "--dtype", "f32"],
+    }
+    for name, extra in runs.items():
+        cmd = [sys.executable, os.path.abspath(__file__), "--steps", "200", "--warmup", "10", "--cpu-seconds", "2", "--no-other-configs"] + extra
+        try:
+            proc = subprocess.run(cmd, capture_output=True, text=True, timeout=300)
+            d = json.loads([ln for ln in proc.stdout.splitlines() if ln.startswith("{")][-1])
+            if "error" in d:
+                out[name] = d
+                continue
+            par = d.get("parity") or {}
+            out[name] = {"value": d["value"], "unit": d["unit"], "ms_per_step": d["ms_per_step"], "dtype": d["dtype"],
+                         "roofline": {k: d["roofline"].get(k) for k in ("achieved", "peak", "unit", "frac", "kernel_ms", "algorithmic_bytes_per_launch")},
+                         "e2e": d["e2e"]["value"], "cpu_baseline": (d.get("cpu_baseline") or {}).get("value"),
+                         "parity": {k: par.get(k) for k in ("ok", "tolerance", "max_rel_err", "strict_failures", "cancellation_entries",
+                                                            "cancellation_worst_ulps", "checked_trajectories")},
+                         "command": "python bench.py " + " ".join(extra)}
+        except Exception as exc:  # an auxiliary figure must not fail the headline line
+            out[name] = {"error": f"{type(exc).__name__}: {exc}"}
+    return out
 
 
 def cpu_codegen_baseline(args, pool):

@@ -199,8 +199,9 @@ int ungar_b200_kkt_step_x(ungar_b200_model* model, const void* x, int64_t batch,
  * if `multipliers` is not NULL, the equality multipliers `multipliers[b, 0:m_eq]` in the reference's row order.
  * Exact stage-wise factorisations, not ADMM: quadrotor and RC car by a Riccati recursion (the input-rate coupling of
  * the objective is carried by augmenting the state with the previous input), quadruped by a block-tridiagonal Schur
- * complement on the multipliers (its contact rows are extra equalities).  F64 models only (UNGAR_B200_EUNSUPPORTED
- * otherwise). */
+ * complement on the multipliers (its contact rows are extra equalities).  The factorisation is always fp64 (the
+ * reference computes in double, data_types.hpp:89): an F32 model hands its fp32 record to it through a twin F64 handle
+ * (record widened, step and multipliers narrowed, on the device). */
 int ungar_b200_qp_solve(ungar_b200_model* model, const void* records_device, int64_t batch, int64_t ld_rec, void* steps,
                         int64_t ld_steps, void* multipliers, int64_t ld_multipliers, void* stream);
 
@@ -234,8 +235,9 @@ enum ungar_b200_sqp_status {
  * theta = multiplier * |g|_2, both evaluated on the device at every trial point w + alpha dw.  All DEVICE pointers.
  * On acceptance xp[b, 0:n_dec] += alpha * steps[b, :] in place.  `status` (int32 [batch][2], may be NULL) skips the
  * trajectories whose status is not RUNNING and receives the bookkeeping of soft_sqp.hpp:100-108; `info`
- * ([batch][8], may be NULL) receives the report above.  F64 models only: the acceptance tests compare relative
- * changes of 1e-6 (EUNSUPPORTED for F32). */
+ * ([batch][8], may be NULL) receives the report above.  The search always evaluates in fp64 (its acceptance tests compare
+ * relative changes of 1e-6): an F32 model widens `xp` and `steps` on the device, searches on a twin F64 handle and narrows the
+ * accepted iterate and the report. */
 int ungar_b200_line_search(ungar_b200_model* model, void* xp, int64_t batch, int64_t ld_xp, const void* steps,
                            int64_t ld_steps, const ungar_b200_sqp_options* options, int32_t* status, void* info,
                            void* stream);
@@ -244,7 +246,8 @@ int ungar_b200_line_search(ungar_b200_model* model, void* xp, int64_t batch, int
  * max_iterations times { KKT sweep -> QP solve -> line search }, entirely on the device, no host round trip inside
  * the loop.  `xp` is updated in place (the reference returns _cache.xp.head(n_dec)); `status` (int32 [batch][2])
  * and `info` ([batch][8], may be NULL; report of the last line search) are host or device buffers per `mem`.
- * Trajectories that stop early are frozen exactly where the reference's loop breaks.  F64 models only. */
+ * Trajectories that stop early are frozen exactly where the reference's loop breaks.  The loop computes in
+ * fp64; an F32 model (BASELINE configs 2 and 3) widens the iterate on the device, runs it on a twin F64 handle and narrows the result. */
 int ungar_b200_sqp_solve(ungar_b200_model* model, void* xp, int64_t batch, int64_t ld_xp,
                          const ungar_b200_sqp_options* options, int32_t* status, void* info, int32_t mem, void* stream);
 

@@ -97,12 +97,27 @@ def test_riccati_qp_matches_monolithic_kkt_solve(oracle, name, N):
         assert np.max(np.abs(P @ steps[b] + q + A.T @ mult[b])) <= 1e-7 * max(1.0, np.max(np.abs(q)))
 
 
-def test_qp_rejects_f32():
+@pytest.mark.parametrize("name,N", [("quadrotor", 30), ("rc_car", 60), ("quadruped", 10)])
+def test_qp_on_an_f32_handle_factorises_in_fp64(name, N):
+    """BASELINE configs 2 and 3 are fp32.  An F32 handle sweeps in fp32 and hands its fp32 record to the same fp64 factorisation
+    (widened on the device, on a twin F64 handle): the step equals the F64 handle's solve of the widened record up to the fp32
+    rounding of the output, and it solves the QP the fp32 record states."""
     import torch
 
     import ungar_b200
-    from ungar_b200 import _lib
+    from ungar_b200 import EXAMPLE_BARRIER
+    from ungar_b200 import workloads as W
 
-    m = ungar_b200.Model("quadrotor", 30, dtype="f32")
-    with pytest.raises(_lib.UngarB200Error):
-        m.qp_solve(torch.zeros((1, m.layout["size"]), dtype=torch.float32, device="cuda"))
+    mid = W.MODEL_IDS[name]
+    m32 = ungar_b200.Model(name, N, dtype="f32", barrier=EXAMPLE_BARRIER[mid])
+    m64 = ungar_b200.Model(name, N, dtype="f64", barrier=EXAMPLE_BARRIER[mid])
+    xp = torch.from_numpy(W.synthetic_batch(mid, N, 6, seed=3)).cuda()
+    rec32 = m32.kkt_blocks(xp.float())
+    assert rec32.dtype == torch.float32
+    steps32, mult32 = m32.qp_solve(rec32)
+    steps64, mult64 = m64.qp_solve(rec32.double())
+    assert steps32.dtype == torch.float32 and torch.isfinite(steps32).all()
+    scale = steps64.abs().amax(dim=1, keepdim=True).clamp_min(1e-30)
+    assert float(((steps32.double() - steps64).abs() / scale).max()) <= 2e-7        # one fp32 rounding of the output
+    mscale = mult64.abs().amax(dim=1, keepdim=True).clamp_min(1e-30)
+    assert float(((mult32.double() - mult64).abs() / mscale).max()) <= 2e-7

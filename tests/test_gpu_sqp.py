@@ -80,9 +80,15 @@ def test_line_search_skips_stopped_trajectories_and_rejects_f32():
     st = status.cpu().numpy()
     assert np.array_equal(st[1], [1, 3]) and np.array_equal(st[2], [2, 5]) and st[0, 1] == 1 and st[3, 1] == 2
     assert torch.equal(xp[1], before[1]) and torch.equal(xp[2], before[2])
+    # an F32 handle searches in fp64 (twin handle, arguments widened on the device): same decisions as the F64 handle on the widened
+    # arguments, iterate and report narrowed back
     m32 = ungar_b200.Model("rc_car", N, dtype="f32", barrier=EXAMPLE_BARRIER[W.RC_CAR])
-    with pytest.raises(_lib.UngarB200Error):
-        m32.line_search(xp.float(), dw.float())
+    x32, d32 = before.float().clone(), dw.float()
+    x64 = x32.double()
+    info64 = m.line_search(x64, d32.double())
+    info32 = m32.line_search(x32, d32)
+    assert info32.dtype == torch.float32 and torch.equal(info32[:, 0].double(), info64[:, 0])            # same step sizes
+    assert torch.allclose(info32.double(), info64, rtol=1e-6, atol=1e-30) and torch.equal(x32, x64.float())
 
 
 @pytest.mark.parametrize("name,N,iters,perturb", [("quadruped", 10, 5, False), ("quadruped", 30, 4, True), ("quadrotor", 30, 6, False),
@@ -173,11 +179,34 @@ def test_sqp_solve_full_batch_properties():
     d2 = torch.from_numpy(xp0.copy()).cuda()
     s2, _ = m.sqp_solve(d2, opts)
     assert torch.equal(d2, d_xp) and torch.equal(s2, status)
-    # F32 models fail loudly
-    from ungar_b200 import _lib
-    q = ungar_b200.Model("quadrotor", 30, dtype="f32")
-    with pytest.raises(_lib.UngarB200Error):
-        q.sqp_solve(torch.zeros((1, q.n_xp), dtype=torch.float32, device="cuda"))
+
+
+@pytest.mark.parametrize("name,N", [("quadrotor", 30), ("rc_car", 60)])
+def test_sqp_solve_on_an_f32_handle_runs_the_fp64_loop(name, N):
+    """BASELINE configs 2 and 3 (fp32): ungar_b200_sqp_solve on an F32 handle widens the iterate on the device, runs the F64 loop on
+    a twin handle and narrows the result — statuses, iteration counts and step sizes equal the F64 handle's on the widened input,
+    the iterate equals its fp32 rounding; device and host buffers."""
+    import torch
+
+    import ungar_b200
+    from ungar_b200 import EXAMPLE_BARRIER
+    from ungar_b200 import workloads as W
+
+    mid = W.MODEL_IDS[name]
+    m32 = ungar_b200.Model(name, N, dtype="f32", barrier=EXAMPLE_BARRIER[mid])
+    m64 = ungar_b200.Model(name, N, dtype="f64", barrier=EXAMPLE_BARRIER[mid])
+    opts = m64.sqp_options(max_iterations=4, constraint_violation_multiplier=1.0 if name == "quadrotor" else 1.0 / N)
+    xp32 = torch.from_numpy(W.synthetic_batch(mid, N, 16, seed=9)).float().cuda()
+    x64 = xp32.double()
+    st64, info64 = m64.sqp_solve(x64, opts)
+    x32 = xp32.clone()
+    st32, info32 = m32.sqp_solve(x32, opts)
+    assert torch.equal(st32, st64) and info32.dtype == torch.float32
+    assert torch.equal(info32[:, 0].double(), info64[:, 0]) and torch.equal(x32, x64.float())
+    assert not torch.equal(x32, xp32)                                                   # the iterate moved
+    host = xp32.cpu().numpy().copy()
+    sth, _ = m32.sqp_solve(host, opts)                                                  # host buffers
+    assert np.array_equal(sth, st64.cpu().numpy()) and np.array_equal(host[:, :m32.layout["n_dec"]], x32.cpu().numpy()[:, :m32.layout["n_dec"]])
 
 
 @pytest.mark.parametrize("name,N", [("quadruped", 10), ("quadrotor", 30), ("rc_car", 30)])

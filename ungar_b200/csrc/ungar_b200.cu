@@ -133,6 +133,10 @@ struct ungar_b200_model {
     cudaStream_t last_stream = nullptr;
     bool has_last = false;
     int64_t cached_batch = 0;  // trajectories whose parameter block sits in ws_xp_cached (ungar_b200_set_parameters)
+    // F32 handles: the consumers of the records (QP solve, line search, SQP loop) compute in fp64 on a TWIN handle of the same problem
+    // (widen on the device -> F64 kernels -> narrow); see f32_consumers below
+    ungar_b200_model* twin = nullptr;
+    DeviceBuffer wide_a, wide_b, wide_c, wide_d;
     size_t elem = 8;
     // compact record (quadruped): compact slot -> dense offset (or -2: pad), host copy for the ABI and device copy for the gather
     bool compact = false;
@@ -858,6 +862,41 @@ int reference_call(ungar_b200_model* mdl, int32_t function, int want, const void
 
 }  // namespace
 
+// ---- F32 handles and the consumers of the records ---------------------------------------------------------------------------------
+// BASELINE configs 2 and 3 are fp32.  Their sweeps run in fp32; the QP factorisation and the line search do not: the reference computes
+// them in double (data_types.hpp:89), the Schur / Riccati pivots span 1e16 (weights of 1e-8 against a 1e-9 regularisation) and the
+// acceptance tests of the line search compare relative changes of 1e-6.  An F32 handle therefore keeps a TWIN F64 handle of the same
+// problem: arguments are widened on the device, the F64 kernels run, results are narrowed back.  qp_solve consumes the fp32 record as
+// it is (fp32 sweep, fp64 factorisation); line_search and sqp_solve evaluate the model in fp64 at the widened iterate.
+namespace {
+
+template <class A, class B>
+__global__ void convert_kernel(const A* __restrict__ src, long long ld_src, B* __restrict__ dst, long long ld_dst, long long n, long long batch) {
+    const long long b = blockIdx.y;
+    for (long long b0 = b; b0 < batch; b0 += gridDim.y)
+        for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+            dst[b0 * ld_dst + i] = static_cast<B>(src[b0 * ld_src + i]);
+}
+
+template <class A, class B>
+int convert(const A* src, int64_t ld_src, B* dst, int64_t ld_dst, int64_t n, int64_t batch, cudaStream_t stream) {
+    if (n <= 0 || batch <= 0) return UNGAR_B200_OK;
+    const dim3 grid(unsigned(std::min<int64_t>((n + 255) / 256, 1024)), unsigned(std::min<int64_t>(batch, 65535)));
+    convert_kernel<A, B><<<grid, 256, 0, stream>>>(src, ld_src, dst, ld_dst, n, batch);
+    ++g_launches;
+    UB_CUDA(cudaGetLastError());
+    return UNGAR_B200_OK;
+}
+
+int ensure_twin(ungar_b200_model& m) {
+    if (m.twin) return UNGAR_B200_OK;
+    ungar_b200_model_desc d = m.desc;
+    d.dtype = UNGAR_B200_F64;
+    return ungar_b200_model_create(&d, &m.twin);
+}
+
+}  // namespace
+
 // =============================================================================================
 extern "C" {
 
@@ -931,6 +970,7 @@ int ungar_b200_model_destroy(ungar_b200_model* model) {
         if (f.d_hes_src) cudaFree(f.d_hes_src);
     }
     if (model->d_c2d) cudaFree(model->d_c2d);
+    if (model->twin) ungar_b200_model_destroy(model->twin);
     if (model->ev_last) cudaEventDestroy(model->ev_last);
     if (model->copy_stream) cudaStreamDestroy(model->copy_stream);
     if (model->ev_entry) cudaEventDestroy(model->ev_entry);
@@ -1042,8 +1082,28 @@ int ungar_b200_jacobian_blocks(ungar_b200_model* model, const void* xp, int64_t 
 int ungar_b200_qp_solve(ungar_b200_model* model, const void* records_device, int64_t batch, int64_t ld_rec, void* steps,
                         int64_t ld_steps, void* multipliers, int64_t ld_multipliers, void* stream_) {
     if (!model) return fail(UNGAR_B200_EINVAL, "null model");
-    if (model->desc.dtype != UNGAR_B200_F64)
-        return fail(UNGAR_B200_EUNSUPPORTED, "qp_solve factorises in fp64: F64 models only (the reference computes in double, data_types.hpp:89)");
+    if (model->desc.dtype != UNGAR_B200_F64) {  // fp32 record in, fp64 factorisation, fp32 step out
+        if (batch < 0 || (batch > 0 && (!records_device || !steps))) return fail(UNGAR_B200_EINVAL, "null buffer");
+        const ungar_b200_kkt_layout& L = model->layout;
+        if (ld_rec < L.size || ld_steps < L.n_dec || (multipliers && ld_multipliers < L.m_eq))
+            return fail(UNGAR_B200_EINVAL, "stride smaller than the row it holds");
+        if (batch == 0) return UNGAR_B200_OK;
+        UB_CUDA(cudaSetDevice(model->desc.device));
+        if (int rc = ensure_twin(*model)) return rc;
+        cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+        StreamScope scope_(*model, stream);
+        if (int rc = model->wide_a.reserve(size_t(batch) * L.size * 8)) return rc;
+        if (int rc = model->wide_b.reserve(size_t(batch) * L.n_dec * 8)) return rc;
+        if (multipliers) { if (int rc = model->wide_c.reserve(size_t(batch) * L.m_eq * 8)) return rc; }
+        double* wrec = static_cast<double*>(model->wide_a.ptr);
+        double* wstep = static_cast<double*>(model->wide_b.ptr);
+        double* wmult = multipliers ? static_cast<double*>(model->wide_c.ptr) : nullptr;
+        if (int rc = convert(static_cast<const float*>(records_device), ld_rec, wrec, L.size, L.size, batch, stream)) return rc;
+        if (int rc = ungar_b200_qp_solve(model->twin, wrec, batch, L.size, wstep, L.n_dec, wmult, L.m_eq, stream_)) return rc;
+        if (int rc = convert(wstep, L.n_dec, static_cast<float*>(steps), ld_steps, L.n_dec, batch, stream)) return rc;
+        if (multipliers) return convert(wmult, L.m_eq, static_cast<float*>(multipliers), ld_multipliers, L.m_eq, batch, stream);
+        return UNGAR_B200_OK;
+    }
     if (batch < 0 || (batch > 0 && (!records_device || !steps))) return fail(UNGAR_B200_EINVAL, "null buffer");
     const ungar_b200_kkt_layout& L = model->layout;
     if (ld_rec < L.size || ld_steps < L.n_dec || (multipliers && ld_multipliers < L.m_eq))
@@ -1075,14 +1135,31 @@ int ungar_b200_sqp_options_default(ungar_b200_sqp_options* out) {
 int ungar_b200_line_search(ungar_b200_model* model, void* xp, int64_t batch, int64_t ld_xp, const void* steps, int64_t ld_steps,
                            const ungar_b200_sqp_options* options, int32_t* status, void* info, void* stream_) {
     if (!model || !options) return fail(UNGAR_B200_EINVAL, "null argument");
-    if (model->desc.dtype != UNGAR_B200_F64)
-        return fail(UNGAR_B200_EUNSUPPORTED, "the line search compares relative changes of 1e-6: F64 models only");
     if (batch < 0 || (batch > 0 && (!xp || !steps))) return fail(UNGAR_B200_EINVAL, "null buffer");
     const ungar_b200_kkt_layout& L = model->layout;
     if (ld_xp < L.n_dec + L.n_par || ld_steps < L.n_dec) return fail(UNGAR_B200_EINVAL, "stride smaller than the row it holds");
     if (int rc = check_options(*options)) return rc;
     if (batch == 0) return UNGAR_B200_OK;
     UB_CUDA(cudaSetDevice(model->desc.device));
+    if (model->desc.dtype != UNGAR_B200_F64) {  // widen xp and the step, search in fp64, narrow the accepted iterate and the record
+        if (int rc = ensure_twin(*model)) return rc;
+        cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+        StreamScope scope_(*model, stream);
+        const int64_t n_in = L.n_dec + L.n_par;
+        if (int rc = model->wide_a.reserve(size_t(batch) * n_in * 8)) return rc;
+        if (int rc = model->wide_b.reserve(size_t(batch) * L.n_dec * 8)) return rc;
+        if (info) { if (int rc = model->wide_d.reserve(size_t(batch) * UNGAR_B200_LINE_SEARCH_INFO_SIZE * 8)) return rc; }
+        double* wxp = static_cast<double*>(model->wide_a.ptr);
+        double* wdw = static_cast<double*>(model->wide_b.ptr);
+        double* winfo = info ? static_cast<double*>(model->wide_d.ptr) : nullptr;
+        if (int rc = convert(static_cast<const float*>(xp), ld_xp, wxp, n_in, n_in, batch, stream)) return rc;
+        if (int rc = convert(static_cast<const float*>(steps), ld_steps, wdw, L.n_dec, L.n_dec, batch, stream)) return rc;
+        if (int rc = ungar_b200_line_search(model->twin, wxp, batch, n_in, wdw, L.n_dec, options, status, winfo, stream_)) return rc;
+        if (int rc = convert(wxp, n_in, static_cast<float*>(xp), ld_xp, L.n_dec, batch, stream)) return rc;
+        if (info) return convert(winfo, UNGAR_B200_LINE_SEARCH_INFO_SIZE, static_cast<float*>(info), UNGAR_B200_LINE_SEARCH_INFO_SIZE,
+                                 UNGAR_B200_LINE_SEARCH_INFO_SIZE, batch, stream);
+        return UNGAR_B200_OK;
+    }
     StreamScope scope_(*model, static_cast<cudaStream_t>(stream_));
     return launch_line_search(*model, static_cast<double*>(xp), batch, ld_xp, static_cast<const double*>(steps), ld_steps, *options,
                               status, static_cast<double*>(info), static_cast<cudaStream_t>(stream_));
@@ -1091,8 +1168,6 @@ int ungar_b200_line_search(ungar_b200_model* model, void* xp, int64_t batch, int
 int ungar_b200_sqp_solve(ungar_b200_model* model, void* xp, int64_t batch, int64_t ld_xp, const ungar_b200_sqp_options* options,
                          int32_t* status, void* info, int32_t mem, void* stream_) {
     if (!model || !options) return fail(UNGAR_B200_EINVAL, "null argument");
-    if (model->desc.dtype != UNGAR_B200_F64)
-        return fail(UNGAR_B200_EUNSUPPORTED, "sqp_solve needs qp_solve and the line search: F64 models only");
     if (batch < 0 || (batch > 0 && (!xp || !status))) return fail(UNGAR_B200_EINVAL, "null buffer");
     if (mem != UNGAR_B200_MEM_DEVICE && mem != UNGAR_B200_MEM_HOST) return fail(UNGAR_B200_EINVAL, "unknown mem %d", mem);
     const ungar_b200_kkt_layout& L = model->layout;
@@ -1101,6 +1176,43 @@ int ungar_b200_sqp_solve(ungar_b200_model* model, void* xp, int64_t batch, int64
     if (int rc = check_options(*options)) return rc;
     if (batch == 0) return UNGAR_B200_OK;
     UB_CUDA(cudaSetDevice(model->desc.device));
+    if (model->desc.dtype != UNGAR_B200_F64) {  // the whole loop in fp64 on the twin, the iterate widened / narrowed on the device
+        if (int rc = ensure_twin(*model)) return rc;
+        cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+        StreamScope scope_(*model, stream);
+        if (int rc = model->wide_a.reserve(size_t(batch) * n_in * 8)) return rc;
+        if (info) { if (int rc = model->wide_d.reserve(size_t(batch) * UNGAR_B200_LINE_SEARCH_INFO_SIZE * 8)) return rc; }
+        double* wxp = static_cast<double*>(model->wide_a.ptr);
+        double* winfo = info ? static_cast<double*>(model->wide_d.ptr) : nullptr;
+        float* d_xp32 = static_cast<float*>(xp);
+        int64_t d_ld = ld_xp;
+        int32_t* d_status = status;
+        if (mem == UNGAR_B200_MEM_HOST) {
+            if (int rc = model->ws_xp.reserve(size_t(batch) * n_in * 4)) return rc;
+            if (int rc = model->ws_status.reserve(size_t(batch) * 2 * sizeof(int32_t))) return rc;
+            UB_CUDA(cudaMemcpy2DAsync(model->ws_xp.ptr, n_in * 4, xp, ld_xp * 4, n_in * 4, batch, cudaMemcpyHostToDevice, stream));
+            d_xp32 = static_cast<float*>(model->ws_xp.ptr); d_ld = n_in;
+            d_status = static_cast<int32_t*>(model->ws_status.ptr);
+        }
+        if (int rc = convert(d_xp32, d_ld, wxp, n_in, n_in, batch, stream)) return rc;
+        if (int rc = ungar_b200_sqp_solve(model->twin, wxp, batch, n_in, options, d_status, winfo, UNGAR_B200_MEM_DEVICE, stream_)) return rc;
+        if (int rc = convert(wxp, n_in, d_xp32, d_ld, L.n_dec, batch, stream)) return rc;
+        if (mem == UNGAR_B200_MEM_HOST) {
+            if (info) {
+                if (int rc = model->ws_info.reserve(size_t(batch) * UNGAR_B200_LINE_SEARCH_INFO_SIZE * 4)) return rc;
+                if (int rc = convert(winfo, UNGAR_B200_LINE_SEARCH_INFO_SIZE, static_cast<float*>(model->ws_info.ptr), UNGAR_B200_LINE_SEARCH_INFO_SIZE,
+                                     UNGAR_B200_LINE_SEARCH_INFO_SIZE, batch, stream)) return rc;
+                UB_CUDA(cudaMemcpyAsync(info, model->ws_info.ptr, size_t(batch) * UNGAR_B200_LINE_SEARCH_INFO_SIZE * 4, cudaMemcpyDeviceToHost, stream));
+            }
+            UB_CUDA(cudaMemcpy2DAsync(xp, ld_xp * 4, d_xp32, n_in * 4, L.n_dec * 4, batch, cudaMemcpyDeviceToHost, stream));
+            UB_CUDA(cudaMemcpyAsync(status, d_status, size_t(batch) * 2 * sizeof(int32_t), cudaMemcpyDeviceToHost, stream));
+            UB_CUDA(cudaStreamSynchronize(stream));
+            return UNGAR_B200_OK;
+        }
+        if (info) return convert(winfo, UNGAR_B200_LINE_SEARCH_INFO_SIZE, static_cast<float*>(info), UNGAR_B200_LINE_SEARCH_INFO_SIZE,
+                                 UNGAR_B200_LINE_SEARCH_INFO_SIZE, batch, stream);
+        return UNGAR_B200_OK;
+    }
     StreamScope scope_(*model, static_cast<cudaStream_t>(stream_));
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
     const size_t es = sizeof(double);

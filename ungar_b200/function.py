@@ -187,7 +187,8 @@ class Model:
 
     def qp_solve(self, records, steps=None, multipliers=None, want_multipliers: bool = True):
         """Batched solve of the equality-constrained QP of the records (CUDA tensors): ``(steps[B, n_dec], multipliers[B, m_eq])``.
-        Replaces the OSQP call of SoftSQPOptimizer::SolveLocalQPProblem (soft_sqp.hpp:193-233); quadruped fp64 only."""
+        Replaces the OSQP call of SoftSQPOptimizer::SolveLocalQPProblem (soft_sqp.hpp:193-233).  The factorisation is fp64; an f32
+        model's fp32 records are widened on the device."""
         import torch
 
         B = records.shape[0]
