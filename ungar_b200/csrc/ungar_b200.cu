@@ -137,6 +137,7 @@ struct ungar_b200_model {
     // (widen on the device -> F64 kernels -> narrow); see f32_consumers below
     ungar_b200_model* twin = nullptr;
     DeviceBuffer wide_a, wide_b, wide_c, wide_d;
+    DeviceBuffer ws_stage;  // contiguous landing zone of narrow host rows (ungar_b200_kkt_step_x), see step_impl
     size_t elem = 8;
     // compact record (quadruped): compact slot -> dense offset (or -2: pad), host copy for the ABI and device copy for the gather
     bool compact = false;
@@ -144,7 +145,7 @@ struct ungar_b200_model {
     int32_t* d_c2d = nullptr;
     int64_t dense_size = 0, rec_size = 0;  // rec_size: length of a record in the handle's format
     // host-buffer pipeline of ungar_b200_kkt_step: H2D of chunk c + 1 on `copy_stream` overlaps the sweep of chunk c
-    static constexpr int kChunks = 4;
+    static constexpr int kChunks = 8;
     cudaStream_t copy_stream = nullptr;
     cudaEvent_t ev_entry = nullptr, ev_chunk[kChunks] = {};
 };
@@ -1314,13 +1315,32 @@ static int step_impl(ungar_b200_model* model, const void* src, int64_t batch, in
         UB_CUDA(cudaStreamWaitEvent(model->copy_stream, model->ev_entry, 0));
     }
     const int64_t per = (batch + chunks - 1) / chunks;
+    char* stage = nullptr;
+    {
+        const char* flat = getenv("UNGAR_B200_H2D_PITCHED");  // measurement switch: the former pitched H2D copy
+        // rows of 16 KB and more (quadruped: 29.9 KB of decision variables) already move at the linear rate when pitched — measured
+        // 150 M nodes/s pitched against 135 M staged; rows of 1-2 KB (quadrotor, RC car) do not: 0.18 -> 0.40 and 0.37 -> 1.05 G nodes/s
+        if (width < n_in && ld_src == width && size_t(width) * es < 16384 && !(flat && flat[0] == '1')) {
+            if (int rc = model->ws_stage.reserve(size_t(batch) * width * es)) return rc;
+            stage = static_cast<char*>(model->ws_stage.ptr);
+        }
+    }
     for (int c = 0; c < chunks; ++c) {
         const int64_t b0 = c * per, nb = std::min<int64_t>(per, batch - b0);
         if (nb <= 0) break;
         cudaStream_t cs = chunks > 1 ? model->copy_stream : stream;
         const char* from = static_cast<const char*>(src) + size_t(b0) * ld_src * es;
-        if (ld_src == n_in && width == n_in) UB_CUDA(cudaMemcpyAsync(w_xp + size_t(b0) * n_in * es, from, size_t(nb) * n_in * es, cudaMemcpyHostToDevice, cs));
-        else UB_CUDA(cudaMemcpy2DAsync(w_xp + size_t(b0) * n_in * es, n_in * es, from, ld_src * es, width * es, nb, cudaMemcpyHostToDevice, cs));
+        if (ld_src == n_in && width == n_in) {
+            UB_CUDA(cudaMemcpyAsync(w_xp + size_t(b0) * n_in * es, from, size_t(nb) * n_in * es, cudaMemcpyHostToDevice, cs));
+        } else if (ld_src == width && stage) {
+            // contiguous host rows narrower than the device rows (decision variables only): ONE linear transfer over PCIe into a
+            // landing zone, then a strided device-to-device copy at HBM speed — a pitched H2D copy pays a DMA descriptor per row
+            UB_CUDA(cudaMemcpyAsync(stage + size_t(b0) * width * es, from, size_t(nb) * width * es, cudaMemcpyHostToDevice, cs));
+            UB_CUDA(cudaMemcpy2DAsync(w_xp + size_t(b0) * n_in * es, n_in * es, stage + size_t(b0) * width * es, width * es, width * es, nb,
+                                      cudaMemcpyDeviceToDevice, cs));
+        } else {
+            UB_CUDA(cudaMemcpy2DAsync(w_xp + size_t(b0) * n_in * es, n_in * es, from, ld_src * es, width * es, nb, cudaMemcpyHostToDevice, cs));
+        }
         if (chunks > 1) {
             UB_CUDA(cudaEventRecord(model->ev_chunk[c], cs));
             UB_CUDA(cudaStreamWaitEvent(stream, model->ev_chunk[c], 0));
