@@ -43,6 +43,7 @@ print("qp_solve    %d x N=%d: %.3f ms" % (B, N, timed(lambda: m.qp_solve(rec, st
 info = m.line_search(xp, steps, opts)
 print("line_search %d x N=%d: %.3f ms (mean trials %.2f)" % (B, N, timed(lambda: m.line_search(xp, steps, opts), setup=lambda: xp.copy_(xp0)),
                                                           float((-torch.log2(info[:, 0].clamp_min(2.0 ** -14))).mean()) + 1))
+m.sqp_solve(xp.copy_(xp0), opts)  # warm-up: the first call allocates the loop's workspaces (0.5 GB of compact records) and loads its kernels
 t = timed(lambda: m.sqp_solve(xp, opts), setup=lambda: xp.copy_(xp0))
 st, _ = m.sqp_solve(xp.copy_(xp0), opts)
 print("sqp_solve   %d x N=%d, 4 iterations: %.3f ms  (status counts %s)" % (B, N, t, torch.bincount(st[:, 0], minlength=3).tolist()))

@@ -1062,10 +1062,38 @@ static int blocks_call(ungar_b200_model* model, const void* xp, int64_t batch, i
 
     if (int rc = model->ws_xp.reserve(size_t(batch) * n_in * es)) return rc;
     if (int rc = model->ws_records.reserve(size_t(batch) * L.size * es)) return rc;
-    UB_CUDA(cudaMemcpy2DAsync(model->ws_xp.ptr, n_in * es, xp, ld_xp * es, n_in * es, batch, cudaMemcpyHostToDevice, stream));
-    if (int rc = launch_sweep(*model, model->ws_xp.ptr, batch, n_in, model->ws_records.ptr, L.size, mode, nullptr, stream, model->compact)) return rc;
-    UB_CUDA(cudaMemcpy2DAsync(records, ld_rec * es, model->ws_records.ptr, L.size * es, L.size * es, batch,
-                              cudaMemcpyDeviceToHost, stream));
+    // Chunked pipeline: the record is 10-25x the input, so the D2H transfer dominates; PCIe is full duplex, so the upload and the sweep
+    // of chunk c + 1 run while chunk c's record goes back on the copy stream — all but the first chunk's upload and sweep are hidden.
+    const int chunks = batch >= 64 * ungar_b200_model::kChunks ? ungar_b200_model::kChunks : 1;
+    if (chunks > 1 && !model->copy_stream) {
+        UB_CUDA(cudaStreamCreateWithFlags(&model->copy_stream, cudaStreamNonBlocking));
+        UB_CUDA(cudaEventCreateWithFlags(&model->ev_entry, cudaEventDisableTiming));
+        for (auto& e : model->ev_chunk) UB_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    }
+    char* const w_xp  = static_cast<char*>(model->ws_xp.ptr);
+    char* const w_rec = static_cast<char*>(model->ws_records.ptr);
+    const int64_t per = (batch + chunks - 1) / chunks;
+    for (int c = 0; c < chunks; ++c) {
+        const int64_t b0 = c * per, nb = std::min<int64_t>(per, batch - b0);
+        if (nb <= 0) break;
+        const char* from = static_cast<const char*>(xp) + size_t(b0) * ld_xp * es;
+        char* to         = static_cast<char*>(records) + size_t(b0) * ld_rec * es;
+        UB_CUDA(cudaMemcpy2DAsync(w_xp + size_t(b0) * n_in * es, n_in * es, from, ld_xp * es, n_in * es, nb, cudaMemcpyHostToDevice, stream));
+        if (int rc = launch_sweep(*model, w_xp + size_t(b0) * n_in * es, nb, n_in, w_rec + size_t(b0) * L.size * es, L.size, mode, nullptr, stream,
+                                  model->compact)) return rc;
+        cudaStream_t ds = stream;
+        if (chunks > 1) {
+            UB_CUDA(cudaEventRecord(model->ev_chunk[c], stream));
+            UB_CUDA(cudaStreamWaitEvent(model->copy_stream, model->ev_chunk[c], 0));
+            ds = model->copy_stream;
+        }
+        if (ld_rec == L.size) UB_CUDA(cudaMemcpyAsync(to, w_rec + size_t(b0) * L.size * es, size_t(nb) * L.size * es, cudaMemcpyDeviceToHost, ds));
+        else UB_CUDA(cudaMemcpy2DAsync(to, ld_rec * es, w_rec + size_t(b0) * L.size * es, L.size * es, L.size * es, nb, cudaMemcpyDeviceToHost, ds));
+    }
+    if (chunks > 1) {
+        UB_CUDA(cudaEventRecord(model->ev_entry, model->copy_stream));
+        UB_CUDA(cudaStreamWaitEvent(stream, model->ev_entry, 0));
+    }
     UB_CUDA(cudaStreamSynchronize(stream));
     return UNGAR_B200_OK;
 }
