@@ -143,6 +143,7 @@ struct ungar_b200_model {
     bool compact = false;
     std::vector<int32_t> c2d;
     int32_t* d_c2d = nullptr;
+    int32_t* d_d2c = nullptr;  // the inverse: dense offset -> compact slot (or -2: a structural zero of the dense record)
     int64_t dense_size = 0, rec_size = 0;  // rec_size: length of a record in the handle's format
     // host-buffer pipeline of ungar_b200_kkt_step: H2D of chunk c + 1 on `copy_stream` overlaps the sweep of chunk c
     static constexpr int kChunks = 8;
@@ -641,9 +642,33 @@ int launch_sweep_t(ungar_b200_model& mdl, const void* xp, int64_t batch, int64_t
     return UNGAR_B200_OK;
 }
 
+template <class T>
+int launch_gather_t(const void* rec, int64_t ld_rec, const int32_t* src, int64_t count, void* out, int64_t ld_out, int64_t batch, cudaStream_t stream);
+int ensure_d2c(ungar_b200_model& mdl);
+
 int launch_sweep(ungar_b200_model& mdl, const void* xp, int64_t batch, int64_t ld_xp, void* rec, int64_t ld_rec,
                  int mode, void* summaries, cudaStream_t stream, bool compact_out = false) {
     const bool f64 = mdl.desc.dtype == UNGAR_B200_F64;
+    // Quadruped fp64 into a DENSE record the structured kernel cannot take (odd horizon: its TMA stores pair the nodes; records that are
+    // not 16-byte aligned): the compact sweep — one chunk per node, any horizon — into a workspace, then one expansion pass that writes
+    // every dense slot once (value or structural zero).  ~0.5 ms per 1024 x N=100 instead of the generic kernel's 2.4 ms.
+    static const bool forced_generic = [] {
+        const char* e = getenv("UNGAR_B200_FORCE_GENERIC");
+        return e && e[0] == '1';
+    }();
+    if (mdl.desc.kind == UNGAR_B200_QUADRUPED && f64 && !compact_out && !forced_generic && (mode == MODE_KKT || mode == MODE_PLAIN) &&
+        !structured_applicable(mdl, rec, ld_rec)) {
+        const int64_t csize = ub::Compact::size(mdl.N);
+        if (int rc = ensure_d2c(mdl)) return rc;
+        if (int rc = mdl.ws_compact.reserve(size_t(batch) * csize * sizeof(double))) return rc;
+        if (int rc = launch_sweep_t<ub::Quadruped, double, 4>(mdl, xp, batch, ld_xp, mdl.ws_compact.ptr, csize, mode, summaries, stream, true)) return rc;
+        for (int64_t b0 = 0; b0 < batch; b0 += 65535) {
+            const int64_t nb = std::min<int64_t>(65535, batch - b0);
+            if (int rc = launch_gather_t<double>(static_cast<const double*>(mdl.ws_compact.ptr) + b0 * csize, csize, mdl.d_d2c, mdl.dense_size,
+                                                 static_cast<double*>(rec) + b0 * ld_rec, ld_rec, nb, stream)) return rc;
+        }
+        return UNGAR_B200_OK;
+    }
     switch (mdl.desc.kind) {
         case UNGAR_B200_QUADROTOR:
             return f64 ? launch_sweep_t<ub::Quadrotor, double, 15>(mdl, xp, batch, ld_xp, rec, ld_rec, mode, summaries, stream, compact_out)
@@ -700,6 +725,20 @@ int ensure_c2d(ungar_b200_model& mdl) {
     }
     UB_CUDA(cudaMalloc(reinterpret_cast<void**>(&mdl.d_c2d), mdl.c2d.size() * sizeof(int32_t)));
     UB_CUDA(cudaMemcpy(mdl.d_c2d, mdl.c2d.data(), mdl.c2d.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
+    return UNGAR_B200_OK;
+}
+
+int ensure_d2c(ungar_b200_model& mdl) {
+    if (mdl.d_d2c) return UNGAR_B200_OK;
+    if (mdl.c2d.empty()) {
+        const ungar_b200_kkt_layout& L = mdl.layout;
+        mdl.c2d = ub::compact_to_dense_map(mdl.N, ub::DenseOffsets{L.g, L.A, L.C, L.h, L.cost, L.grad, L.H, L.HN});
+    }
+    std::vector<int32_t> d2c(size_t(mdl.dense_size), -2);
+    for (size_t i = 0; i < mdl.c2d.size(); ++i)
+        if (mdl.c2d[i] >= 0) d2c[size_t(mdl.c2d[i])] = int32_t(i);
+    UB_CUDA(cudaMalloc(reinterpret_cast<void**>(&mdl.d_d2c), d2c.size() * sizeof(int32_t)));
+    UB_CUDA(cudaMemcpy(mdl.d_d2c, d2c.data(), d2c.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
     return UNGAR_B200_OK;
 }
 
@@ -971,6 +1010,7 @@ int ungar_b200_model_destroy(ungar_b200_model* model) {
         if (f.d_hes_src) cudaFree(f.d_hes_src);
     }
     if (model->d_c2d) cudaFree(model->d_c2d);
+    if (model->d_d2c) cudaFree(model->d_d2c);
     if (model->twin) ungar_b200_model_destroy(model->twin);
     if (model->ev_last) cudaEventDestroy(model->ev_last);
     if (model->copy_stream) cudaStreamDestroy(model->copy_stream);
