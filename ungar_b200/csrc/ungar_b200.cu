@@ -1386,9 +1386,10 @@ static int step_impl(ungar_b200_model* model, const void* src, int64_t batch, in
     char* stage = nullptr;
     {
         const char* flat = getenv("UNGAR_B200_H2D_PITCHED");  // measurement switch: the former pitched H2D copy
-        // rows of 16 KB and more (quadruped: 29.9 KB of decision variables) already move at the linear rate when pitched — measured
-        // 150 M nodes/s pitched against 135 M staged; rows of 1-2 KB (quadrotor, RC car) do not: 0.18 -> 0.40 and 0.37 -> 1.05 G nodes/s
-        if (width < n_in && ld_src == width && size_t(width) * es < 16384 && !(flat && flat[0] == '1')) {
+        // A pitched H2D copy pays a DMA descriptor per row: rows of 1-2 KB (quadrotor, RC car) crawl (0.18 / 0.37 G nodes/s against
+        // 0.40 / 1.05 staged), and even the quadruped's 29.9 KB rows swing between 26 and 44 GB/s from box to box and run to run while a
+        // linear transfer of the same bytes holds 42-49 GB/s in the same process.
+        if (width < n_in && ld_src == width && !(flat && flat[0] == '1')) {
             if (int rc = model->ws_stage.reserve(size_t(batch) * width * es)) return rc;
             stage = static_cast<char*>(model->ws_stage.ptr);
         }
@@ -1402,16 +1403,22 @@ static int step_impl(ungar_b200_model* model, const void* src, int64_t batch, in
             UB_CUDA(cudaMemcpyAsync(w_xp + size_t(b0) * n_in * es, from, size_t(nb) * n_in * es, cudaMemcpyHostToDevice, cs));
         } else if (ld_src == width && stage) {
             // contiguous host rows narrower than the device rows (decision variables only): ONE linear transfer over PCIe into a
-            // landing zone, then a strided device-to-device copy at HBM speed — a pitched H2D copy pays a DMA descriptor per row
+            // landing zone on the copy stream; the rows are scattered into place on the COMPUTE stream (below, at HBM speed), so the
+            // copy stream goes straight on to the next chunk
             UB_CUDA(cudaMemcpyAsync(stage + size_t(b0) * width * es, from, size_t(nb) * width * es, cudaMemcpyHostToDevice, cs));
-            UB_CUDA(cudaMemcpy2DAsync(w_xp + size_t(b0) * n_in * es, n_in * es, stage + size_t(b0) * width * es, width * es, width * es, nb,
-                                      cudaMemcpyDeviceToDevice, cs));
         } else {
             UB_CUDA(cudaMemcpy2DAsync(w_xp + size_t(b0) * n_in * es, n_in * es, from, ld_src * es, width * es, nb, cudaMemcpyHostToDevice, cs));
         }
         if (chunks > 1) {
             UB_CUDA(cudaEventRecord(model->ev_chunk[c], cs));
             UB_CUDA(cudaStreamWaitEvent(stream, model->ev_chunk[c], 0));
+        }
+        if (ld_src == width && stage && !(ld_src == n_in && width == n_in)) {
+            const int rc = es == 8 ? convert(reinterpret_cast<const double*>(stage + size_t(b0) * width * es), width,
+                                             reinterpret_cast<double*>(w_xp + size_t(b0) * n_in * es), n_in, width, nb, stream)
+                                   : convert(reinterpret_cast<const float*>(stage + size_t(b0) * width * es), width,
+                                             reinterpret_cast<float*>(w_xp + size_t(b0) * n_in * es), n_in, width, nb, stream);
+            if (rc) return rc;
         }
         if (int rc = launch_sweep(*model, w_xp + size_t(b0) * n_in * es, nb, n_in, static_cast<char*>(records_device) + size_t(b0) * ld_rec * es,
                                   ld_rec, MODE_KKT, w_sum + size_t(b0) * UNGAR_B200_SUMMARY_SIZE * es, stream, model->compact)) return rc;
