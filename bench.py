@@ -592,7 +592,7 @@ def ours(args, rank: int, local_rank: int, world: int):
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": B * (model.n_xp if jac else L["n_dec"]) * elem,
                 "d2h_bytes_per_step": B * (L["size"] if jac else 32) * elem, "steps": e2e_steps,
                 "path": "ungar_b200_jacobian_blocks(MEM_HOST): pinned host xp -> H2D -> Jacobian sweep -> record -> D2H" if jac else
-                        "ungar_b200_kkt_step_x(MEM_HOST): pinned host decision variables [X | U] -> H2D in 4 chunks overlapped with the sweep of the previous "
+                        "ungar_b200_kkt_step_x(MEM_HOST): pinned host decision variables [X | U] -> H2D in 8 linear chunks (landing zone, scattered on the device) overlapped with the sweep of the previous "
                         "chunk (parameter block cached on the device by ungar_b200_set_parameters once per control cycle; records stay in HBM) -> summaries -> D2H"},
         "e2e_full_xp": e2e_full_xp, "e2e_full_record_d2h": full_value, "compact": compact,
         "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu, "parity": parity, "sqp_loop": sqp,

@@ -1300,7 +1300,8 @@ int ungar_b200_sqp_solve(ungar_b200_model* model, void* xp, int64_t batch, int64
         if (info) {
             if (int rc = model->ws_info.reserve(size_t(batch) * UNGAR_B200_LINE_SEARCH_INFO_SIZE * es)) return rc;
         }
-        UB_CUDA(cudaMemcpy2DAsync(model->ws_xp.ptr, n_in * es, xp, ld_xp * es, n_in * es, batch, cudaMemcpyHostToDevice, stream));
+        if (ld_xp == n_in) UB_CUDA(cudaMemcpyAsync(model->ws_xp.ptr, xp, size_t(batch) * n_in * es, cudaMemcpyHostToDevice, stream));  // one linear transfer
+        else UB_CUDA(cudaMemcpy2DAsync(model->ws_xp.ptr, n_in * es, xp, ld_xp * es, n_in * es, batch, cudaMemcpyHostToDevice, stream));
         d_xp = static_cast<double*>(model->ws_xp.ptr); d_ld_xp = n_in;
         d_status = static_cast<int32_t*>(model->ws_status.ptr);
         d_info   = info ? static_cast<double*>(model->ws_info.ptr) : nullptr;
