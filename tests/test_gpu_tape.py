@@ -374,3 +374,37 @@ def test_specialised_quadrotor_jacobian_meets_the_latency_target(tmp_path, monke
     print(f"\n[tape] quadrotor N=30 equality Jacobian, batch 1024: interpreter {ms_interp:.3f} ms, NVRTC-specialised {ms_special:.3f} ms")
     assert torch.allclose(J_special, J_interp, rtol=1e-12, atol=1e-14)
     assert ms_special < 0.2
+
+
+def test_long_tapes_run_as_segmented_specialised_kernels(tmp_path, monkeypatch):
+    """A tape beyond the single-kernel limit (12 k instructions) is cut into kernels of 6 k instructions; values that cross a cut travel
+    through the scratch array (liveness over the cuts).  A chained recurrence with long-lived values, CondExp and a late use of the first
+    independents — so that every kind of value crosses several cuts — against the interpreter (first call) for values and Jacobian."""
+    monkeypatch.setenv("UNGAR_B200_KERNEL_CACHE", str(tmp_path / "kernels"))
+    n = 6
+
+    def chain(v):
+        a, b, c = v[0], v[1], v[2]
+        keep = [v[3] * v[4], A.sin(v[5])]                 # live from the first to the last segment
+        acc = 0.0
+        for k in range(2600):                             # ~7 instructions per round
+            a, b, c = b * 0.999 + 0.001 * A.sin(c), c - 0.002 * a * b, A.CondExpGt(a, b, a, b) * 0.5 + 0.5 * c
+            if k % 400 == 0:
+                acc = acc + a * keep[0] + b * keep[1]
+        return [a + acc, b * keep[0], c + v[0] * keep[1]]
+
+    f = A.MakeFunction(A.Blueprint(chain, n, 0, "long_chain", A.JACOBIAN))
+    assert f.tape_info()["live_nodes"] > 13000
+    rng = np.random.default_rng(8)
+    X = 0.5 + 0.2 * rng.standard_normal((96, n))
+    y0, J0 = f._tape.forward_zero(X), f._tape.sparse_jacobian(X)          # interpreter
+    y1, J1 = f._tape.forward_zero(X), f._tape.sparse_jacobian(X)          # segmented specialised kernels
+    info = f._tape.special_info()
+    assert info[0]["state"] == 1 and info[1]["state"] == 1, info
+    assert np.isfinite(y1).all() and np.isfinite(J1).all()
+    assert np.allclose(y1, y0, rtol=1e-12, atol=1e-14) and np.allclose(J1, J0, rtol=1e-11, atol=1e-13)
+    monkeypatch.setenv("UNGAR_B200_NO_SEGMENTS", "1")                     # the switch keeps long tapes on the interpreter
+    g = A.MakeFunction(A.Blueprint(chain, n, 0, "long_chain", A.JACOBIAN))
+    g._tape.forward_zero(X)
+    g._tape.forward_zero(X)
+    assert g._tape.special_info()[0]["state"] == -1

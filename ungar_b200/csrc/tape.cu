@@ -126,6 +126,7 @@ struct ungar_b200_tape {
         int state = 0;  // 0: not tried, 1: ready, -1: unavailable (too large, NVRTC missing, compile error: the interpreter serves)
         CUmodule module = nullptr;
         CUfunction fn = nullptr;
+        std::vector<CUfunction> parts;  // segmented kernels of a tape beyond kSpecializeMax (run back to back, values cross through the scratch)
         uint64_t key = 0;
         bool from_cache = false;
         double compile_seconds = 0.0;
@@ -498,7 +499,9 @@ int check_call(const ungar_b200_tape* T, const void* x, int64_t batch, int64_t l
 // the text of tape_machine.cuh.  UNGAR_B200_KERNEL_CACHE (default: $UNGAR_CODEGEN_FOLDER or /tmp/ungar_b200_kernels) holds
 // <hash>.cubin; UNGAR_B200_NO_NVRTC=1 disables the path.
 // ---------------------------------------------------------------------------------------------------------------------
-constexpr int kSpecializeMax = 12000;   // instructions; NVRTC + ptxas time grows superlinearly (8 k: seconds, 40 k: minutes)
+constexpr int kSpecializeMax = 12000;   // instructions per KERNEL; NVRTC + ptxas time grows superlinearly (8 k: seconds, 40 k: minutes)
+constexpr int kSegment       = 6000;    // longer tapes are cut into kernels of this many instructions (compile time stays linear)
+constexpr int kSegmentedMax  = 100000;  // beyond this even the segmented module takes minutes to compile: the interpreter keeps serving
 constexpr int64_t kSpecializeAfter = 1; // specialise on the second call of an ORDER: a function evaluated once never pays the compile
 
 // The driver API and NVRTC are bound at run time (dlopen), not at link time: the library must load — and export its ABI — on hosts
@@ -576,55 +579,150 @@ std::string slurp(const std::string& path) {
 }
 
 // Straight-line kernel text of the program for one ORDER (same thread mapping and outputs as ub::tape::tape_kernel<ORDER>).
-std::string generate_kernel_source(const ungar_b200_tape& T, int order) {
+std::string hexd(double v) {  // exact round trip of a double constant
+    char buf[64];
+    snprintf(buf, sizeof(buf), "%a", v);
+    return std::string(buf);
+}
+
+// One statement per instruction; slots are the local variables r<slot>.
+void emit_instruction(std::ostringstream& o, const ungar_b200_tape& T, const ub::tape::Instr& in, int order) {
     using namespace ub::tape;
+    switch (in.op) {
+        case T_INDEP:
+            o << "  r" << in.dst << " = jet_const<ORDER>(x[" << in.a << "]);";
+            if (order >= 1) o << " r" << in.dst << ".d = (S.kind == 0 ? S.color[" << in.a << "] == dir : (" << in.a << " == s0 || " << in.a << " == s1)) ? 1.0 : 0.0;";
+            o << "\n";
+            break;
+        case T_CONST: o << "  r" << in.dst << " = jet_const<ORDER>(" << hexd(T.consts[size_t(in.a)]) << ");\n"; break;
+        case T_ADD: case T_SUB: case T_MUL: case T_DIV: case T_ATAN2:
+            o << "  r" << in.dst << " = jet_binary<ORDER>(" << in.op << ", r" << in.a << ", r" << in.b << ");\n";
+            break;
+        case T_POW:
+            if (in.c >= 0) o << "  r" << in.dst << " = jet_pow_const<ORDER>(r" << in.a << ", " << hexd(T.consts[size_t(in.c)]) << ");\n";
+            else o << "  r" << in.dst << " = jet_binary<ORDER>(" << int(T_POW) << ", r" << in.a << ", r" << in.b << ");\n";
+            break;
+        case T_CLT: case T_CLE: case T_CGT: case T_CGE: case T_CEQ:
+            o << "  r" << in.dst << " = jet_compare(" << in.op << ", r" << in.a << ".v, r" << in.b << ".v) ? r" << in.c << " : r" << in.d << ";\n";
+            break;
+        case T_OUTPUT: case T_OUTPUT_CONST: {
+            const std::string a = in.op == T_OUTPUT ? "r" + std::to_string(in.a) : "jet_const<ORDER>(" + hexd(T.consts[size_t(in.a)]) + ")";
+            if (order == 0) o << "  out[" << in.b << "] = " << a << ".v;\n";
+            if (order == 1) o << "  { const int e = out_slot[(long long)" << in.b << " * ndir + dir]; if (e >= 0) out[e] = " << a << ".d; }\n";
+            if (order == 2) o << "  acc += weights[" << in.b << "] * " << a << ".dd;\n";
+            break;
+        }
+        default:  // unary
+            o << "  r" << in.dst << " = jet_unary<ORDER>(" << in.op << ", r" << in.a << ");\n";
+    }
+}
+
+const char* kKernelProlog =
+    "  const long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x;\n  if (t >= batch * ndir) return;\n"
+    "  const long long b = t / ndir;\n  const int dir = int(t - b * ndir);\n"
+    "  const double* __restrict__ x = x_all + b * ld_x;\n  double* __restrict__ out = out_all + b * ld_out;\n"
+    "  int s0 = -1, s1 = -1;\n  if (ORDER >= 1 && S.kind == 1) { s0 = S.pi[dir]; s1 = S.pj[dir]; }\n  double acc = 0.0;\n  (void)s0; (void)s1; (void)acc; (void)x; (void)out;\n";
+
+std::string generate_kernel_source(const ungar_b200_tape& T, int order) {
     std::ostringstream o;
     o.precision(17);
     o << "#include \"tape_machine.cuh\"\nusing namespace ub::tape;\n"
       << "extern \"C\" __global__ void __launch_bounds__(128) tape_special(Seeds S, const double* __restrict__ x_all, long long ld_x, long long batch, int ndir,\n"
       << "    double* __restrict__ out_all, long long ld_out, const int* __restrict__ out_slot, const double* __restrict__ weights) {\n"
       << "  constexpr int ORDER = " << order << ";\n"
-      << "  const long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x;\n  if (t >= batch * ndir) return;\n"
-      << "  const long long b = t / ndir;\n  const int dir = int(t - b * ndir);\n"
-      << "  const double* __restrict__ x = x_all + b * ld_x;\n  double* __restrict__ out = out_all + b * ld_out;\n"
-      << "  int s0 = -1, s1 = -1;\n  if (ORDER >= 1 && S.kind == 1) { s0 = S.pi[dir]; s1 = S.pj[dir]; }\n  double acc = 0.0;\n  (void)s0; (void)s1; (void)acc;\n";
+      << kKernelProlog;
     for (int k = 0; k < T.n_slots; ++k) o << "  Jet<ORDER> r" << k << ";\n";
-    auto hexd = [&](double v) {  // exact round trip of a double constant
-        char buf[64];
-        snprintf(buf, sizeof(buf), "%a", v);
-        return std::string(buf);
-    };
-    for (const Instr& in : T.code) {
-        switch (in.op) {
-            case T_INDEP:
-                o << "  r" << in.dst << " = jet_const<ORDER>(x[" << in.a << "]);";
-                if (order >= 1) o << " r" << in.dst << ".d = (S.kind == 0 ? S.color[" << in.a << "] == dir : (" << in.a << " == s0 || " << in.a << " == s1)) ? 1.0 : 0.0;";
-                o << "\n";
-                break;
-            case T_CONST: o << "  r" << in.dst << " = jet_const<ORDER>(" << hexd(T.consts[size_t(in.a)]) << ");\n"; break;
-            case T_ADD: case T_SUB: case T_MUL: case T_DIV: case T_ATAN2:
-                o << "  r" << in.dst << " = jet_binary<ORDER>(" << in.op << ", r" << in.a << ", r" << in.b << ");\n";
-                break;
-            case T_POW:
-                if (in.c >= 0) o << "  r" << in.dst << " = jet_pow_const<ORDER>(r" << in.a << ", " << hexd(T.consts[size_t(in.c)]) << ");\n";
-                else o << "  r" << in.dst << " = jet_binary<ORDER>(" << int(T_POW) << ", r" << in.a << ", r" << in.b << ");\n";
-                break;
-            case T_CLT: case T_CLE: case T_CGT: case T_CGE: case T_CEQ:
-                o << "  r" << in.dst << " = jet_compare(" << in.op << ", r" << in.a << ".v, r" << in.b << ".v) ? r" << in.c << " : r" << in.d << ";\n";
-                break;
-            case T_OUTPUT: case T_OUTPUT_CONST: {
-                const std::string a = in.op == T_OUTPUT ? "r" + std::to_string(in.a) : "jet_const<ORDER>(" + hexd(T.consts[size_t(in.a)]) + ")";
-                if (order == 0) o << "  out[" << in.b << "] = " << a << ".v;\n";
-                if (order == 1) o << "  { const int e = out_slot[(long long)" << in.b << " * ndir + dir]; if (e >= 0) out[e] = " << a << ".d; }\n";
-                if (order == 2) o << "  acc += weights[" << in.b << "] * " << a << ".dd;\n";
-                break;
-            }
-            default:  // unary
-                o << "  r" << in.dst << " = jet_unary<ORDER>(" << in.op << ", r" << in.a << ");\n";
-        }
-    }
+    for (const ub::tape::Instr& in : T.code) emit_instruction(o, T, in, order);
     if (order == 2) o << "  out[dir] = acc;\n";
     o << "}\n";
+    return o.str();
+}
+
+// Which slots an instruction reads / writes (-1: none).
+void instr_uses(const ub::tape::Instr& in, int reads[4], int& write) {
+    using namespace ub::tape;
+    reads[0] = reads[1] = reads[2] = reads[3] = -1;
+    write = -1;
+    switch (in.op) {
+        case T_INDEP: case T_CONST: write = in.dst; break;
+        case T_ADD: case T_SUB: case T_MUL: case T_DIV: case T_ATAN2: reads[0] = in.a; reads[1] = in.b; write = in.dst; break;
+        case T_POW: reads[0] = in.a; if (in.c < 0) reads[1] = in.b; write = in.dst; break;
+        case T_CLT: case T_CLE: case T_CGT: case T_CGE: case T_CEQ: reads[0] = in.a; reads[1] = in.b; reads[2] = in.c; reads[3] = in.d; write = in.dst; break;
+        case T_OUTPUT: reads[0] = in.a; break;
+        case T_OUTPUT_CONST: break;
+        default: reads[0] = in.a; write = in.dst;  // unary
+    }
+}
+
+// A tape beyond kSpecializeMax as a sequence of kernels of kSegment instructions each.  Inside a kernel the slots are registers, as in
+// the single-kernel form; a value that crosses a cut travels through the scratch array of the interpreter ([slot][component][thread],
+// coalesced): kernel k loads the slots it reads before writing them and stores the slots it wrote that a later kernel still reads
+// (backward liveness over the cuts).  Orders 0 and 1 (the Hessian accumulator would have to cross the cuts too).
+std::string generate_segmented_source(const ungar_b200_tape& T, int order, int& n_parts) {
+    const int n = int(T.code.size());
+    n_parts = (n + kSegment - 1) / kSegment;
+    const size_t np = size_t(n_parts), ns = size_t(T.n_slots);
+    std::vector<std::vector<int>> loads(np), stores(np), touched(np);
+    std::vector<char> live(ns, 0);  // live at the END of the segment being processed (backward)
+    for (int k = n_parts - 1; k >= 0; --k) {
+        const int i0 = k * kSegment, i1 = std::min(n, i0 + kSegment);
+        std::vector<char> written(ns, 0), exposed(ns, 0), seen(ns, 0);
+        for (int i = i0; i < i1; ++i) {
+            int rd[4], wr;
+            instr_uses(T.code[size_t(i)], rd, wr);
+            for (int r : rd)
+                if (r >= 0) {
+                    if (!written[size_t(r)]) exposed[size_t(r)] = 1;  // read before any write of this segment: comes from an earlier one
+                    seen[size_t(r)] = 1;
+                }
+            if (wr >= 0) { written[size_t(wr)] = 1; seen[size_t(wr)] = 1; }
+        }
+        for (int sl = 0; sl < T.n_slots; ++sl) {
+            if (seen[size_t(sl)]) touched[size_t(k)].push_back(sl);
+            if (exposed[size_t(sl)]) loads[size_t(k)].push_back(sl);
+            if (written[size_t(sl)] && live[size_t(sl)]) stores[size_t(k)].push_back(sl);
+        }
+        for (int sl = 0; sl < T.n_slots; ++sl) live[size_t(sl)] = exposed[size_t(sl)] || (live[size_t(sl)] && !written[size_t(sl)]);
+    }
+    std::ostringstream o;
+    o.precision(17);
+    o << "#include \"tape_machine.cuh\"\nusing namespace ub::tape;\n";
+    for (int k = 0; k < n_parts; ++k) {
+        const int i0 = k * kSegment, i1 = std::min(n, i0 + kSegment);
+        o << "extern \"C\" __global__ void __launch_bounds__(128) tape_part_" << k
+          << "(Seeds S, const double* __restrict__ x_all, long long ld_x, long long batch, int ndir,\n"
+          << "    double* __restrict__ out_all, long long ld_out, const int* __restrict__ out_slot, const double* __restrict__ weights,\n"
+          << "    double* __restrict__ scratch, long long stride) {\n"
+          << "  constexpr int ORDER = " << order << ";\n"
+          << kKernelProlog;
+        // a value that comes from an earlier kernel is loaded right before its first use, a value a later kernel needs is stored right
+        // after its last write: live ranges stay as short as in the tape itself (loading every live-in at the top made hundreds of jets
+        // live at once: kilobytes of spills per thread, and a stack size that slowed every later launch of the process)
+        std::vector<char> need_load(ns, 0), need_store(ns, 0);
+        for (int sl : loads[size_t(k)]) need_load[size_t(sl)] = 1;
+        for (int sl : stores[size_t(k)]) need_store[size_t(sl)] = 1;
+        std::vector<int> last_write(ns, -1);
+        for (int i = i0; i < i1; ++i) {
+            int rd[4], wr;
+            instr_uses(T.code[size_t(i)], rd, wr);
+            if (wr >= 0) last_write[size_t(wr)] = i;
+        }
+        for (int sl : touched[size_t(k)]) o << "  Jet<ORDER> r" << sl << ";\n";
+        for (int i = i0; i < i1; ++i) {
+            int rd[4], wr;
+            instr_uses(T.code[size_t(i)], rd, wr);
+            for (int r : rd)
+                if (r >= 0 && need_load[size_t(r)]) {
+                    o << "  r" << r << " = load_slot<ORDER>(scratch, stride, t, " << r << ");\n";
+                    need_load[size_t(r)] = 0;
+                }
+            if (wr >= 0) need_load[size_t(wr)] = 0;  // (an exposed read always precedes the first write, so this never drops a load)
+            emit_instruction(o, T, T.code[size_t(i)], order);
+            if (wr >= 0 && need_store[size_t(wr)] && last_write[size_t(wr)] == i)
+                o << "  store_slot<ORDER>(scratch, stride, t, " << wr << ", r" << wr << ");\n";
+        }
+        o << "}\n";
+    }
     return o.str();
 }
 
@@ -636,7 +734,13 @@ void specialize(ungar_b200_tape& T, int order) {
     ungar_b200_tape::Special& S = T.special[order];
     S.state = -1;
     const char* off = getenv("UNGAR_B200_NO_NVRTC");
-    if ((off && off[0] == '1') || int(T.code.size()) > kSpecializeMax || T.code.empty()) return;
+    if ((off && off[0] == '1') || T.code.empty()) return;
+    const bool segmented = int(T.code.size()) > kSpecializeMax;
+    if (segmented && (order == 2 || int(T.code.size()) > kSegmentedMax)) return;
+    if (segmented) {
+        const char* seg_off = getenv("UNGAR_B200_NO_SEGMENTS");  // measurement switch: long tapes stay on the interpreter
+        if (seg_off && seg_off[0] == '1') return;
+    }
     LazyApi& api = lazy_api();
     if (!api.ok) return;
     const std::string dir = machine_header_dir();
@@ -650,7 +754,7 @@ void specialize(ungar_b200_tape& T, int order) {
     uint64_t h = fnv1a(T.code.data(), T.code.size() * sizeof(Instr));
     h = fnv1a(T.consts.data(), T.consts.size() * sizeof(double), h);
     h = fnv1a(&order, sizeof(order), h);
-    const int dims[4] = {T.n_slots, int(T.n_indep), int(T.n_dep), 1 /* generator version */};
+    const int dims[6] = {T.n_slots, int(T.n_indep), int(T.n_dep), 3 /* generator version */, segmented ? kSegment : 0, segmented ? 1 : 0};
     h = fnv1a(dims, sizeof(dims), h);
     h = fnv1a(arch.data(), arch.size(), h);
     h = fnv1a(header.data(), header.size(), h);
@@ -661,7 +765,8 @@ void specialize(ungar_b200_tape& T, int order) {
     std::string cubin = slurp(path);
     S.from_cache = !cubin.empty();
     if (cubin.empty()) {
-        const std::string src = generate_kernel_source(T, order);
+        int n_parts_gen = 0;
+        const std::string src = segmented ? generate_segmented_source(T, order, n_parts_gen) : generate_kernel_source(T, order);
         nvrtcProgram prog;
         if (api.createProgram(&prog, src.c_str(), "tape_special.cu", 0, nullptr, nullptr) != NVRTC_SUCCESS) return;
         const std::string inc1 = "-I" + dir, inc2 = "-I/usr/local/cuda/include", a = "--gpu-architecture=" + arch;
@@ -692,7 +797,16 @@ void specialize(ungar_b200_tape& T, int order) {
     }
     cudaFree(nullptr);  // make sure the runtime's primary context is current for the driver API
     if (!driver_ok(api.moduleLoadData(&S.module, cubin.data()))) return;
-    if (!driver_ok(api.moduleGetFunction(&S.fn, S.module, "tape_special"))) return;
+    if (segmented) {
+        const int n_parts = (int(T.code.size()) + kSegment - 1) / kSegment;
+        S.parts.assign(size_t(n_parts), nullptr);
+        for (int k = 0; k < n_parts; ++k) {
+            const std::string fname = "tape_part_" + std::to_string(k);
+            if (!driver_ok(api.moduleGetFunction(&S.parts[size_t(k)], S.module, fname.c_str()))) { S.parts.clear(); return; }
+        }
+    } else if (!driver_ok(api.moduleGetFunction(&S.fn, S.module, "tape_special"))) {
+        return;
+    }
     S.state = 1;
 }
 
@@ -705,6 +819,20 @@ int launch(ungar_b200_tape& T, const ub::tape::Seeds& seeds, const double* d_x, 
     if (blocks > 2147483647LL) return tfail(UNGAR_B200_EINVAL, "batch x directions too large for one launch");
     // the straight-line kernel from the second call of this ORDER on (a function evaluated once never pays the compile)
     if (T.calls[ORDER]++ >= kSpecializeAfter && T.special[ORDER].state == 0) specialize(T, ORDER);
+    if (T.special[ORDER].state == 1 && !T.special[ORDER].parts.empty()) {  // a long tape: its kernels back to back, values cross through the scratch
+        if (int rc = T.scratch.reserve(size_t(T.n_slots) * (ORDER + 1) * size_t(stride) * sizeof(double))) return rc;
+        ub::tape::Seeds sd = seeds;
+        long long ldx = ld_x, b64 = batch, ldo = ld_out, st = stride;
+        int nd = ndir;
+        double* scr = static_cast<double*>(T.scratch.ptr);
+        void* args[] = {&sd, &d_x, &ldx, &b64, &nd, &d_out, &ldo, &out_slot, &weights, &scr, &st};
+        for (CUfunction fn : T.special[ORDER].parts) {
+            const CUresult r = lazy_api().launchKernel(fn, unsigned(blocks), 1, 1, 128, 1, 1, 0, reinterpret_cast<CUstream>(stream), args, nullptr);
+            if (r != CUDA_SUCCESS) return tfail(UNGAR_B200_ECUDA, "cuLaunchKernel of a segment of the specialised tape kernel failed (%d)", int(r));
+            ub_count_launch();
+        }
+        return UNGAR_B200_OK;
+    }
     if (T.special[ORDER].state == 1) {
         ub::tape::Seeds sd = seeds;
         long long ldx = ld_x, b64 = batch, ldo = ld_out;
