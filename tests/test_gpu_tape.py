@@ -403,6 +403,12 @@ def test_long_tapes_run_as_segmented_specialised_kernels(tmp_path, monkeypatch):
     assert info[0]["state"] == 1 and info[1]["state"] == 1, info
     assert np.isfinite(y1).all() and np.isfinite(J1).all()
     assert np.allclose(y1, y0, rtol=1e-12, atol=1e-14) and np.allclose(J1, J0, rtol=1e-11, atol=1e-13)
+    # second-order jets (Hessian of w . y): the accumulator crosses the cuts too
+    w = np.array([0.7, -1.3, 0.4])
+    H0 = f._tape.sparse_hessian(X[:8], w)
+    H1 = f._tape.sparse_hessian(X[:8], w)
+    assert f._tape.special_info()[2]["state"] == 1 and H1.shape[1] > 0
+    assert np.allclose(H1, H0, rtol=1e-10, atol=1e-12)
     monkeypatch.setenv("UNGAR_B200_NO_SEGMENTS", "1")                     # the switch keeps long tapes on the interpreter
     g = A.MakeFunction(A.Blueprint(chain, n, 0, "long_chain", A.JACOBIAN))
     g._tape.forward_zero(X)

@@ -657,7 +657,7 @@ void instr_uses(const ub::tape::Instr& in, int reads[4], int& write) {
 // A tape beyond kSpecializeMax as a sequence of kernels of kSegment instructions each.  Inside a kernel the slots are registers, as in
 // the single-kernel form; a value that crosses a cut travels through the scratch array of the interpreter ([slot][component][thread],
 // coalesced): kernel k loads the slots it reads before writing them and stores the slots it wrote that a later kernel still reads
-// (backward liveness over the cuts).  Orders 0 and 1 (the Hessian accumulator would have to cross the cuts too).
+// (backward liveness over the cuts).  The Hessian order's accumulator crosses the cuts in one extra scratch row.
 std::string generate_segmented_source(const ungar_b200_tape& T, int order, int& n_parts) {
     const int n = int(T.code.size());
     n_parts = (n + kSegment - 1) / kSegment;
@@ -708,6 +708,8 @@ std::string generate_segmented_source(const ungar_b200_tape& T, int order, int& 
             if (wr >= 0) last_write[size_t(wr)] = i;
         }
         for (int sl : touched[size_t(k)]) o << "  Jet<ORDER> r" << sl << ";\n";
+        // the Hessian order accumulates sum_i w_i y_i'' over the outputs: the partial sum crosses the cuts in one extra scratch row
+        if (order == 2 && k > 0) o << "  acc = scratch[(long long)" << T.n_slots << " * (ORDER + 1) * stride + t];\n";
         for (int i = i0; i < i1; ++i) {
             int rd[4], wr;
             instr_uses(T.code[size_t(i)], rd, wr);
@@ -720,6 +722,10 @@ std::string generate_segmented_source(const ungar_b200_tape& T, int order, int& 
             emit_instruction(o, T, T.code[size_t(i)], order);
             if (wr >= 0 && need_store[size_t(wr)] && last_write[size_t(wr)] == i)
                 o << "  store_slot<ORDER>(scratch, stride, t, " << wr << ", r" << wr << ");\n";
+        }
+        if (order == 2) {
+            if (k + 1 < n_parts) o << "  scratch[(long long)" << T.n_slots << " * (ORDER + 1) * stride + t] = acc;\n";
+            else o << "  out[dir] = acc;\n";
         }
         o << "}\n";
     }
@@ -736,7 +742,7 @@ void specialize(ungar_b200_tape& T, int order) {
     const char* off = getenv("UNGAR_B200_NO_NVRTC");
     if ((off && off[0] == '1') || T.code.empty()) return;
     const bool segmented = int(T.code.size()) > kSpecializeMax;
-    if (segmented && (order == 2 || int(T.code.size()) > kSegmentedMax)) return;
+    if (segmented && int(T.code.size()) > kSegmentedMax) return;
     if (segmented) {
         const char* seg_off = getenv("UNGAR_B200_NO_SEGMENTS");  // measurement switch: long tapes stay on the interpreter
         if (seg_off && seg_off[0] == '1') return;
@@ -754,7 +760,7 @@ void specialize(ungar_b200_tape& T, int order) {
     uint64_t h = fnv1a(T.code.data(), T.code.size() * sizeof(Instr));
     h = fnv1a(T.consts.data(), T.consts.size() * sizeof(double), h);
     h = fnv1a(&order, sizeof(order), h);
-    const int dims[6] = {T.n_slots, int(T.n_indep), int(T.n_dep), 3 /* generator version */, segmented ? kSegment : 0, segmented ? 1 : 0};
+    const int dims[6] = {T.n_slots, int(T.n_indep), int(T.n_dep), 4 /* generator version */, segmented ? kSegment : 0, segmented ? 1 : 0};
     h = fnv1a(dims, sizeof(dims), h);
     h = fnv1a(arch.data(), arch.size(), h);
     h = fnv1a(header.data(), header.size(), h);
@@ -820,7 +826,7 @@ int launch(ungar_b200_tape& T, const ub::tape::Seeds& seeds, const double* d_x, 
     // the straight-line kernel from the second call of this ORDER on (a function evaluated once never pays the compile)
     if (T.calls[ORDER]++ >= kSpecializeAfter && T.special[ORDER].state == 0) specialize(T, ORDER);
     if (T.special[ORDER].state == 1 && !T.special[ORDER].parts.empty()) {  // a long tape: its kernels back to back, values cross through the scratch
-        if (int rc = T.scratch.reserve(size_t(T.n_slots) * (ORDER + 1) * size_t(stride) * sizeof(double))) return rc;
+        if (int rc = T.scratch.reserve(size_t(T.n_slots + 1) * (ORDER + 1) * size_t(stride) * sizeof(double))) return rc;  // + the Hessian accumulator's row
         ub::tape::Seeds sd = seeds;
         long long ldx = ld_x, b64 = batch, ldo = ld_out, st = stride;
         int nd = ndir;
