@@ -290,12 +290,19 @@ int ungar_b200_tape_create(const ungar_b200_tape_node* nodes, int64_t n_nodes, i
                            int32_t device, ungar_b200_tape** out);
 int ungar_b200_tape_destroy(ungar_b200_tape* tape);
 /* Diagnostics of the NVRTC-specialised kernels (csrc/tape.cu): from the second evaluation of an order on, a tape of up to 12 000
- * instructions runs as ONE straight-line sm_100a kernel compiled with NVRTC and cached on disk under a CONTENT hash (instruction
+ * instructions runs as ONE straight-line sm_100a kernel (a longer one, up to 100 000, as a sequence of kernels of 6 000 instructions)
+ * compiled with NVRTC and cached on disk under a CONTENT hash (instruction
  * stream, constants, order, arch, the text of csrc/tape_machine.cuh) — the reference caches its generated library by NAME only
  * (function.hpp:420-451).  info[4 * order + {0, 1, 2, 3}], order 0..2 = {state: 0 not tried / 1 specialised / -1 interpreter,
  * served from the cache, low 32 bits of the hash, high 32 bits}.  UNGAR_B200_KERNEL_CACHE names the cache directory,
  * UNGAR_B200_NO_NVRTC=1 keeps the interpreter. */
 int ungar_b200_tape_special_info(const ungar_b200_tape* tape, int64_t* info);
+/* The CUDA source the NVRTC path generates for `order` (0 values, 1 Jacobian, 2 Hessian jets): ONE kernel `tape_special` for tapes of
+ * up to 12 000 instructions, otherwise kernels `tape_part_<k>` of 6 000 instructions each whose cross-kernel values travel through the
+ * scratch array.  Host-only (no device, no compile): `buffer` receives at most `capacity` bytes including the terminating 0,
+ * `*required` the size of the whole text, `*n_kernels` the number of kernels.  Diagnostics / tests. */
+int ungar_b200_tape_kernel_source(const ungar_b200_tape* tape, int32_t order, char* buffer, int64_t capacity, int64_t* required,
+                                  int32_t* n_kernels);
 /* info[6] = independents, dependents, nodes kept after dead-node elimination, scratch slots, Jacobian colours,
  * Hessian directions (the last two are 0 until the element sets below are chosen). */
 int ungar_b200_tape_info(const ungar_b200_tape* tape, int64_t* info);

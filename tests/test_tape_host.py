@@ -226,3 +226,86 @@ def test_a_changed_lambda_under_the_same_name_is_taped_again():
     assert compiled and not loaded and 3.0 in k and 2.0 not in k
     loaded, compiled, k = run("a")
     assert compiled and not loaded and 2.0 in k and 3.0 not in k
+
+
+def _long_chain(v):
+    a, b, c = v[0], v[1], v[2]
+    keep = [v[3] * v[4], A.sin(v[5])]
+    acc = 0.0
+    for k in range(2600):
+        a, b, c = b * 0.999 + 0.001 * A.sin(c), c - 0.002 * a * b, A.CondExpGt(a, b, a, b) * 0.5 + 0.5 * c
+        if k % 400 == 0:
+            acc = acc + a * keep[0] + b * keep[1]
+    return [a + acc, b * keep[0], c + v[0] * keep[1]]
+
+
+def test_segmented_kernel_source_never_reads_an_undefined_register():
+    """Tapes beyond the single-kernel limit are cut into kernels of 6 k instructions (csrc/tape.cu::generate_segmented_source).  Host-only
+    check of the liveness logic on the generated text: inside every kernel a register is loaded from the scratch array or assigned before
+    it is read; everything a kernel loads was stored by an earlier kernel after its last write there; the last kernel stores nothing."""
+    import re
+
+    f = A.MakeFunction(A.Blueprint(_long_chain, 6, 0, "long_chain_host", A.JACOBIAN))
+    for order in (0, 1, 2):
+        src, parts = f._tape.kernel_source(order)
+        assert parts >= 3 and src.count("extern \"C\" __global__") == parts
+        kernels = re.split(r'extern "C" __global__', src)[1:]
+        stored = set()                                   # slots whose current value sits in the scratch array
+        for k, body in enumerate(kernels):
+            defined, loaded_here, stored_here = set(), set(), set()
+            for line in body.splitlines():
+                line = line.strip()
+                m = re.match(r"r(\d+) = load_slot<ORDER>\(scratch, stride, t, (\d+)\);", line)
+                if m:
+                    assert m.group(1) == m.group(2) and int(m.group(1)) in stored, (order, k, line)
+                    defined.add(int(m.group(1))); loaded_here.add(int(m.group(1)))
+                    continue
+                m = re.match(r"store_slot<ORDER>\(scratch, stride, t, (\d+), r(\d+)\);", line)
+                if m:
+                    assert m.group(1) == m.group(2) and int(m.group(1)) in defined, (order, k, line)
+                    stored_here.add(int(m.group(1)))
+                    continue
+                m = re.match(r"r(\d+) = ([^;]*);", line)  # (an independent's line goes on to seed its own .d: not a read)
+                if m:
+                    reads = {int(x) for x in re.findall(r"\br(\d+)\b", m.group(2))}
+                    assert reads <= defined, (order, k, line, sorted(reads - defined))
+                    defined.add(int(m.group(1)))
+                    continue
+                if line.startswith("out[") or line.startswith("{ const int e") or line.startswith("acc +="):
+                    reads = {int(x) for x in re.findall(r"\br(\d+)\b", line)}
+                    assert reads <= defined, (order, k, line)
+            stored |= stored_here
+            if k == parts - 1:
+                assert not stored_here
+        assert stored                                     # values did cross the cuts
+
+
+def test_generated_kernels_compile_for_sm_100a_without_a_gpu():
+    """NVRTC needs no device: the generated single-kernel and segmented sources compile to sm_100a cubins on a CPU host (the driver's
+    "does it build" check extended to the generated code)."""
+    try:
+        from cuda.bindings import nvrtc
+    except Exception:
+        try:
+            from cuda import nvrtc
+        except Exception:
+            pytest.skip("cuda-python (NVRTC bindings) not importable")
+    import os
+
+    hdr = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "ungar_b200", "csrc")
+    small = A.MakeFunction(A.Blueprint(lambda v: [v[4] * sum(x * A.sin(x) for x in v[:4]) + A.pow(v[1], 3)], 4, 1, "small_host", A.JACOBIAN))
+    long_ = A.MakeFunction(A.Blueprint(_long_chain, 6, 0, "long_chain_host", A.JACOBIAN))
+    for f, order in ((small, 1), (small, 2), (long_, 0)):  # (order 1 of the long tape compiles for a minute: the GPU tests do that)
+        src, parts = f._tape.kernel_source(order)
+        err, prog = nvrtc.nvrtcCreateProgram(src.encode(), b"tape_special.cu", 0, [], [])
+        assert err == nvrtc.nvrtcResult.NVRTC_SUCCESS
+        opts = [b"--gpu-architecture=sm_100a", f"-I{hdr}".encode(), b"-I/usr/local/cuda/include", b"--std=c++17", b"-default-device", b"--fmad=true"]
+        (err,) = nvrtc.nvrtcCompileProgram(prog, len(opts), opts)
+        if err != nvrtc.nvrtcResult.NVRTC_SUCCESS:
+            _, n = nvrtc.nvrtcGetProgramLogSize(prog)
+            log = b" " * n
+            nvrtc.nvrtcGetProgramLog(prog, log)
+            raise AssertionError(log.decode(errors="replace")[-2000:])
+        err, n = nvrtc.nvrtcGetCUBINSize(prog)
+        assert err == nvrtc.nvrtcResult.NVRTC_SUCCESS and n > 1000
+        nvrtc.nvrtcDestroyProgram(prog)

@@ -266,6 +266,14 @@ class TapeHandle:
         return {o: {"state": int(buf[4 * o]), "from_cache": bool(buf[4 * o + 1]), "key": (int(buf[4 * o + 3]) << 32) | int(buf[4 * o + 2])}
                 for o in range(3)}
 
+    def kernel_source(self, order: int = 0):
+        """(CUDA source the NVRTC path generates for ``order``, number of kernels) — host-only, nothing is compiled."""
+        need, parts = ctypes.c_int64(), ctypes.c_int32()
+        check(self._lib.ungar_b200_tape_kernel_source(self._h, int(order), None, 0, ctypes.byref(need), ctypes.byref(parts)))
+        buf = ctypes.create_string_buffer(int(need.value))
+        check(self._lib.ungar_b200_tape_kernel_source(self._h, int(order), buf, int(need.value), None, None))
+        return buf.value.decode(), int(parts.value)
+
     def info(self) -> dict:
         buf = (ctypes.c_int64 * 6)()
         check(self._lib.ungar_b200_tape_info(self._h, buf))

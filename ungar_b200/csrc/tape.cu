@@ -889,6 +889,20 @@ int ungar_b200_tape_create(const ungar_b200_tape_node* nodes, int64_t n_nodes, i
     return UNGAR_B200_OK;
 }
 
+int ungar_b200_tape_kernel_source(const ungar_b200_tape* tape, int32_t order, char* buffer, int64_t capacity, int64_t* required, int32_t* n_kernels) {
+    if (!tape || order < 0 || order > 2 || capacity < 0 || (capacity > 0 && !buffer)) return tfail(UNGAR_B200_EINVAL, "bad argument");
+    int parts = 1;
+    const std::string src = int(tape->code.size()) > kSpecializeMax ? generate_segmented_source(*tape, order, parts) : generate_kernel_source(*tape, order);
+    if (required) *required = int64_t(src.size()) + 1;
+    if (n_kernels) *n_kernels = parts;
+    if (capacity > 0) {
+        const size_t n = std::min<size_t>(src.size(), size_t(capacity) - 1);
+        memcpy(buffer, src.data(), n);
+        buffer[n] = 0;
+    }
+    return UNGAR_B200_OK;
+}
+
 // info[4 * order + {0, 1, 2, 3}] for order 0..2: state (0 not tried, 1 specialised, -1 interpreter), served from the kernel cache (0 / 1),
 // low and high 32 bits of the content hash.  Test / diagnostics hook of the NVRTC path.
 int ungar_b200_tape_special_info(const ungar_b200_tape* tape, int64_t* info) {
