@@ -194,6 +194,12 @@ def test_reference_lambda_tapes_on_the_register_machine(oracle, name, N, batch):
         for b in (0, batch - 1):
             ref_J = oracle.jacobian(mid, fn, N, xp[b])[2]
             assert np.max(np.abs(J[b] - ref_J)) <= 1e-11 * max(1.0, np.max(np.abs(ref_J))), (suffix, b)
+        if name == "quadruped" and N == 30 and fn == 1:
+            # second calls: this 20 k-instruction tape (713 slots) now runs as four segmented NVRTC kernels whose cross-kernel values
+            # travel through the scratch array — same values, same Jacobian
+            y2, J2 = t.forward_zero(xp), t.sparse_jacobian(xp)
+            assert t.special_info()[0]["state"] == 1 and t.special_info()[1]["state"] == 1
+            assert np.max(np.abs(y2 - y)) <= 1e-13 * max(scale, np.max(np.abs(y))) and np.max(np.abs(J2 - J)) <= 1e-12 * max(1.0, np.max(np.abs(J)))
         # ... and the hand-written kernels agree with the register machine (same reference-format arrays)
         Jk = hand[fn].JacobianValues(xp[:2])
         hr, hc = hand[fn].JacobianSparsity()
@@ -387,14 +393,14 @@ def test_long_tapes_run_as_segmented_specialised_kernels(tmp_path, monkeypatch):
         a, b, c = v[0], v[1], v[2]
         keep = [v[3] * v[4], A.sin(v[5])]                 # live from the first to the last segment
         acc = 0.0
-        for k in range(2600):                             # ~7 instructions per round
+        for k in range(850):                             # ~7 instructions per round
             a, b, c = b * 0.999 + 0.001 * A.sin(c), c - 0.002 * a * b, A.CondExpGt(a, b, a, b) * 0.5 + 0.5 * c
-            if k % 400 == 0:
+            if k % 200 == 0:
                 acc = acc + a * keep[0] + b * keep[1]
         return [a + acc, b * keep[0], c + v[0] * keep[1]]
 
     f = A.MakeFunction(A.Blueprint(chain, n, 0, "long_chain", A.JACOBIAN))
-    assert f.tape_info()["live_nodes"] > 13000
+    assert f.tape_info()["live_nodes"] > 12500
     rng = np.random.default_rng(8)
     X = 0.5 + 0.2 * rng.standard_normal((96, n))
     y0, J0 = f._tape.forward_zero(X), f._tape.sparse_jacobian(X)          # interpreter

@@ -232,9 +232,9 @@ def _long_chain(v):
     a, b, c = v[0], v[1], v[2]
     keep = [v[3] * v[4], A.sin(v[5])]
     acc = 0.0
-    for k in range(2600):
+    for k in range(850):
         a, b, c = b * 0.999 + 0.001 * A.sin(c), c - 0.002 * a * b, A.CondExpGt(a, b, a, b) * 0.5 + 0.5 * c
-        if k % 400 == 0:
+        if k % 200 == 0:
             acc = acc + a * keep[0] + b * keep[1]
     return [a + acc, b * keep[0], c + v[0] * keep[1]]
 
