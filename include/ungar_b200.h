@@ -297,6 +297,10 @@ int ungar_b200_tape_destroy(ungar_b200_tape* tape);
  * served from the cache, low 32 bits of the hash, high 32 bits}.  UNGAR_B200_KERNEL_CACHE names the cache directory,
  * UNGAR_B200_NO_NVRTC=1 keeps the interpreter. */
 int ungar_b200_tape_special_info(const ungar_b200_tape* tape, int64_t* info);
+/* The kernels of a tape beyond 12 000 instructions take tens of seconds to compile: a worker thread does it (state 2 in
+ * ungar_b200_tape_special_info) while the interpreter keeps serving the calls.  This call blocks until no compile is in flight.
+ * UNGAR_B200_NVRTC_SYNC=1 compiles in the calling thread instead. */
+int ungar_b200_tape_special_wait(ungar_b200_tape* tape);
 /* The CUDA source the NVRTC path generates for `order` (0 values, 1 Jacobian, 2 Hessian jets): ONE kernel `tape_special` for tapes of
  * up to 12 000 instructions, otherwise kernels `tape_part_<k>` of 6 000 instructions each whose cross-kernel values travel through the
  * scratch array.  Host-only (no device, no compile): `buffer` receives at most `capacity` bytes including the terminating 0,

@@ -48,9 +48,11 @@ for name, N in (("quadrotor", 30), ("rc_car", 60), ("quadruped", 30), ("quadrupe
     ti.set_jacobian_elements(r[keep], c[keep])
     x1 = torch.from_numpy(W.synthetic_batch(mid, N, 1, seed=3)).cuda()
     ti.sparse_jacobian(x1); ti.sparse_jacobian(x1)
+    ti.wait_specialised()  # (a long tape's worker thread reads the switch when it starts compiling)
     del os.environ["UNGAR_B200_NO_NVRTC"]
     t0 = time.perf_counter()
     t.sparse_jacobian(x1); t.sparse_jacobian(x1)  # the second call of an order compiles (or loads from the cache) the specialised kernel(s)
+    t.wait_specialised()                          # (long tapes compile on a worker thread while the interpreter serves)
     torch.cuda.synchronize()
     print(f"   NVRTC specialisation: state {t.special_info()[1]['state']}, {time.perf_counter() - t0:.1f} s including the compile"
           f" ({'from the cache' if t.special_info()[1]['from_cache'] else 'compiled'})")

@@ -197,8 +197,10 @@ def test_reference_lambda_tapes_on_the_register_machine(oracle, name, N, batch):
         if name == "quadruped" and N == 30 and fn == 1:
             # second calls: this 20 k-instruction tape (713 slots) now runs as four segmented NVRTC kernels whose cross-kernel values
             # travel through the scratch array — same values, same Jacobian
+            t.forward_zero(xp), t.sparse_jacobian(xp)   # start the background compiles (these calls are still served by the interpreter)
+            info2 = t.wait_specialised()
+            assert info2[0]["state"] == 1 and info2[1]["state"] == 1, info2
             y2, J2 = t.forward_zero(xp), t.sparse_jacobian(xp)
-            assert t.special_info()[0]["state"] == 1 and t.special_info()[1]["state"] == 1
             assert np.max(np.abs(y2 - y)) <= 1e-13 * max(scale, np.max(np.abs(y))) and np.max(np.abs(J2 - J)) <= 1e-12 * max(1.0, np.max(np.abs(J)))
         # ... and the hand-written kernels agree with the register machine (same reference-format arrays)
         Jk = hand[fn].JacobianValues(xp[:2])
@@ -373,9 +375,20 @@ def test_specialised_quadrotor_jacobian_meets_the_latency_target(tmp_path, monke
         torch.cuda.synchronize()
         return e0.elapsed_time(e1) / reps, out
 
+    def busy(seconds):  # the tests before this one may have left the GPU idle for tens of seconds (CPU oracle, NVRTC): wake its clocks up
+        a = torch.randn(4096, 4096, device="cuda")
+        t0 = time.perf_counter()
+        while time.perf_counter() - t0 < seconds:
+            (a @ a).sum().item()
+
+    import time
+
+    busy(0.5)
     ms_interp, J_interp = timed(1)
     _, J_special = timed(1)  # compiles
     assert t.special_info()[1]["state"] == 1
+    busy(0.5)
+    timed(50)
     ms_special, J_special = timed(20)
     print(f"\n[tape] quadrotor N=30 equality Jacobian, batch 1024: interpreter {ms_interp:.3f} ms, NVRTC-specialised {ms_special:.3f} ms")
     assert torch.allclose(J_special, J_interp, rtol=1e-12, atol=1e-14)
@@ -404,19 +417,24 @@ def test_long_tapes_run_as_segmented_specialised_kernels(tmp_path, monkeypatch):
     rng = np.random.default_rng(8)
     X = 0.5 + 0.2 * rng.standard_normal((96, n))
     y0, J0 = f._tape.forward_zero(X), f._tape.sparse_jacobian(X)          # interpreter
-    y1, J1 = f._tape.forward_zero(X), f._tape.sparse_jacobian(X)          # segmented specialised kernels
-    info = f._tape.special_info()
+    yb, Jb = f._tape.forward_zero(X), f._tape.sparse_jacobian(X)          # second calls: a worker thread starts compiling, the interpreter serves
+    assert np.array_equal(yb, y0) and np.array_equal(Jb, J0)
+    assert all(v["state"] in (1, 2) for o, v in f._tape.special_info().items() if o < 2)
+    info = f._tape.wait_specialised()
     assert info[0]["state"] == 1 and info[1]["state"] == 1, info
+    y1, J1 = f._tape.forward_zero(X), f._tape.sparse_jacobian(X)          # segmented specialised kernels
     assert np.isfinite(y1).all() and np.isfinite(J1).all()
     assert np.allclose(y1, y0, rtol=1e-12, atol=1e-14) and np.allclose(J1, J0, rtol=1e-11, atol=1e-13)
     # second-order jets (Hessian of w . y): the accumulator crosses the cuts too
     w = np.array([0.7, -1.3, 0.4])
     H0 = f._tape.sparse_hessian(X[:8], w)
+    f._tape.sparse_hessian(X[:8], w)
+    assert f._tape.wait_specialised()[2]["state"] == 1
     H1 = f._tape.sparse_hessian(X[:8], w)
-    assert f._tape.special_info()[2]["state"] == 1 and H1.shape[1] > 0
+    assert H1.shape[1] > 0
     assert np.allclose(H1, H0, rtol=1e-10, atol=1e-12)
     monkeypatch.setenv("UNGAR_B200_NO_SEGMENTS", "1")                     # the switch keeps long tapes on the interpreter
     g = A.MakeFunction(A.Blueprint(chain, n, 0, "long_chain", A.JACOBIAN))
     g._tape.forward_zero(X)
     g._tape.forward_zero(X)
-    assert g._tape.special_info()[0]["state"] == -1
+    assert g._tape.wait_specialised()[0]["state"] == -1

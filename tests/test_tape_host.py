@@ -242,42 +242,55 @@ def _long_chain(v):
 def test_segmented_kernel_source_never_reads_an_undefined_register():
     """Tapes beyond the single-kernel limit are cut into kernels of 6 k instructions (csrc/tape.cu::generate_segmented_source).  Host-only
     check of the liveness logic on the generated text: inside every kernel a register is loaded from the scratch array or assigned before
-    it is read; everything a kernel loads was stored by an earlier kernel after its last write there; the last kernel stores nothing."""
+    it is read, and whatever is loaded — across a cut, or after being parked because its next use was far away — is the CURRENT value of
+    its slot (stored after the slot's last assignment)."""
     import re
 
-    f = A.MakeFunction(A.Blueprint(_long_chain, 6, 0, "long_chain_host", A.JACOBIAN))
-    for order in (0, 1, 2):
-        src, parts = f._tape.kernel_source(order)
+    import glob
+    import os
+
+    handles = [A.MakeFunction(A.Blueprint(_long_chain, 6, 0, "long_chain_host", A.JACOBIAN))._tape]
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    hits = glob.glob(os.path.join(root, "oracle", "_ref", "tapes", "quadruped_N30", "quadruped_mpc_eqs", "cppad_cg", "*_lib.so"))
+    if hits:  # the reference's own quadruped equality lambda: 20 k instructions, 713 slots alive at once
+        raw = open(hits[0], "rb").read()
+        magic, nn, nd, ni, _ = np.frombuffer(raw, dtype=np.int64, count=5)
+        nodes = np.frombuffer(raw, dtype=A.NODE_DTYPE, count=int(nn), offset=40)
+        deps = np.frombuffer(raw, dtype=np.int32, count=int(nd), offset=40 + int(nn) * 32)
+        consts = np.frombuffer(raw, dtype=np.float64, count=int(nd), offset=40 + int(nn) * 32 + int(nd) * 4)
+        handles.append(A.TapeHandle(nodes, int(ni), deps, consts))
+    for tape, order in [(h, o) for h in handles for o in (0, 1, 2)]:
+        src, parts = tape.kernel_source(order)
         assert parts >= 3 and src.count("extern \"C\" __global__") == parts
         kernels = re.split(r'extern "C" __global__', src)[1:]
-        stored = set()                                   # slots whose current value sits in the scratch array
+        scratch_valid = set()                            # slots whose CURRENT value sits in the scratch array
+        crossed = 0
         for k, body in enumerate(kernels):
-            defined, loaded_here, stored_here = set(), set(), set()
+            defined = set()                              # registers holding the current value of their slot (they do not survive a kernel)
             for line in body.splitlines():
                 line = line.strip()
                 m = re.match(r"r(\d+) = load_slot<ORDER>\(scratch, stride, t, (\d+)\);", line)
                 if m:
-                    assert m.group(1) == m.group(2) and int(m.group(1)) in stored, (order, k, line)
-                    defined.add(int(m.group(1))); loaded_here.add(int(m.group(1)))
+                    assert m.group(1) == m.group(2) and int(m.group(1)) in scratch_valid, (order, k, line)
+                    crossed += int(m.group(1)) not in defined
+                    defined.add(int(m.group(1)))
                     continue
                 m = re.match(r"store_slot<ORDER>\(scratch, stride, t, (\d+), r(\d+)\);", line)
                 if m:
                     assert m.group(1) == m.group(2) and int(m.group(1)) in defined, (order, k, line)
-                    stored_here.add(int(m.group(1)))
+                    scratch_valid.add(int(m.group(1)))
                     continue
                 m = re.match(r"r(\d+) = ([^;]*);", line)  # (an independent's line goes on to seed its own .d: not a read)
                 if m:
                     reads = {int(x) for x in re.findall(r"\br(\d+)\b", m.group(2))}
                     assert reads <= defined, (order, k, line, sorted(reads - defined))
                     defined.add(int(m.group(1)))
+                    scratch_valid.discard(int(m.group(1)))  # a new value: whatever the scratch array holds for this slot is stale now
                     continue
                 if line.startswith("out[") or line.startswith("{ const int e") or line.startswith("acc +="):
                     reads = {int(x) for x in re.findall(r"\br(\d+)\b", line)}
                     assert reads <= defined, (order, k, line)
-            stored |= stored_here
-            if k == parts - 1:
-                assert not stored_here
-        assert stored                                     # values did cross the cuts
+        assert crossed > 0                                # values did cross the cuts
 
 
 def test_generated_kernels_compile_for_sm_100a_without_a_gpu():

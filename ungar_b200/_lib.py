@@ -30,7 +30,7 @@ SYMBOLS = [
     "ungar_b200_tape_create", "ungar_b200_tape_destroy", "ungar_b200_tape_info", "ungar_b200_tape_jacobian_pattern",
     "ungar_b200_tape_hessian_pattern", "ungar_b200_tape_set_jacobian_elements", "ungar_b200_tape_set_hessian_elements",
     "ungar_b200_tape_forward_zero", "ungar_b200_tape_sparse_jacobian", "ungar_b200_tape_sparse_hessian", "ungar_b200_kkt_solve_csc",
-    "ungar_b200_jacobian_blocks", "ungar_b200_kkt_compact_map", "ungar_b200_set_parameters", "ungar_b200_kkt_step_x", "ungar_b200_tape_special_info", "ungar_b200_tape_kernel_source",
+    "ungar_b200_jacobian_blocks", "ungar_b200_kkt_compact_map", "ungar_b200_set_parameters", "ungar_b200_kkt_step_x", "ungar_b200_tape_special_info", "ungar_b200_tape_kernel_source", "ungar_b200_tape_special_wait",
 ]
 
 
@@ -112,6 +112,7 @@ def load() -> ctypes.CDLL:
     L.ungar_b200_tape_destroy.argtypes = [c_vp]
     L.ungar_b200_tape_info.argtypes = [c_vp, c_i64_p]
     L.ungar_b200_tape_special_info.argtypes = [c_vp, c_i64_p]
+    L.ungar_b200_tape_special_wait.argtypes = [c_vp]
     L.ungar_b200_tape_kernel_source.argtypes = [c_vp, c_i32, ctypes.c_char_p, c_i64, c_i64_p, ctypes.POINTER(c_i32)]
     for name in ("ungar_b200_tape_jacobian_pattern", "ungar_b200_tape_hessian_pattern"):
         getattr(L, name).argtypes = [c_vp, ctypes.POINTER(c_i64_p), ctypes.POINTER(c_i64_p), c_i64_p]

@@ -260,11 +260,17 @@ class TapeHandle:
 
     def special_info(self) -> dict:
         """State of the NVRTC-specialised kernels per order (0 values, 1 Jacobian, 2 Hessian): ``state`` 0 not tried / 1 specialised /
-        -1 interpreter, ``from_cache``, ``key`` = content hash the compiled kernel is cached under."""
+        -1 interpreter / 2 compiling in the background, ``from_cache``, ``key`` = content hash the compiled kernel is cached under."""
         buf = (ctypes.c_int64 * 12)()
         check(self._lib.ungar_b200_tape_special_info(self._h, buf))
         return {o: {"state": int(buf[4 * o]), "from_cache": bool(buf[4 * o + 1]), "key": (int(buf[4 * o + 3]) << 32) | int(buf[4 * o + 2])}
                 for o in range(3)}
+
+    def wait_specialised(self) -> dict:
+        """Blocks until no background compile of this tape's kernels is in flight (long tapes compile on a worker thread while the
+        interpreter serves); returns special_info()."""
+        check(self._lib.ungar_b200_tape_special_wait(self._h))
+        return self.special_info()
 
     def kernel_source(self, order: int = 0):
         """(CUDA source the NVRTC path generates for ``order``, number of kernels) — host-only, nothing is compiled."""

@@ -9,6 +9,8 @@
 #include <fstream>
 #include <sstream>
 #include <sys/stat.h>
+#include <atomic>
+#include <thread>
 #include <type_traits>
 #include <cuda.h>
 #include <nvrtc.h>
@@ -123,7 +125,10 @@ struct ungar_b200_tape {
 
     // NVRTC-specialised straight-line kernels, one per ORDER (0 values, 1 Jacobian, 2 Hessian jets): tried once each
     struct Special {
-        int state = 0;  // 0: not tried, 1: ready, -1: unavailable (too large, NVRTC missing, compile error: the interpreter serves)
+        // 0: not tried, 1: ready, -1: unavailable (too large, NVRTC missing, compile error: the interpreter serves), 2: a worker thread is
+        // compiling the segmented kernels of a long tape (tens of seconds) while the interpreter keeps serving the calls
+        std::atomic<int> state{0};
+        std::thread worker;
         CUmodule module = nullptr;
         CUfunction fn = nullptr;
         std::vector<CUfunction> parts;  // segmented kernels of a tape beyond kSpecializeMax (run back to back, values cross through the scratch)
@@ -501,7 +506,8 @@ int check_call(const ungar_b200_tape* T, const void* x, int64_t batch, int64_t l
 // ---------------------------------------------------------------------------------------------------------------------
 constexpr int kSpecializeMax = 12000;   // instructions per KERNEL; NVRTC + ptxas time grows superlinearly (8 k: seconds, 40 k: minutes)
 constexpr int kSegment       = 6000;    // longer tapes are cut into kernels of this many instructions (compile time stays linear)
-constexpr int kSegmentedMax  = 100000;  // beyond this even the segmented module takes minutes to compile: the interpreter keeps serving
+constexpr int kSegmentedMax  = 100000;
+constexpr int kLiveWindow    = 64;      // instructions a value may wait in a register for its next use inside a segmented kernel  // beyond this even the segmented module takes minutes to compile: the interpreter keeps serving
 constexpr int64_t kSpecializeAfter = 1; // specialise on the second call of an ORDER: a function evaluated once never pays the compile
 
 // The driver API and NVRTC are bound at run time (dlopen), not at link time: the library must load — and export its ABI — on hosts
@@ -707,6 +713,29 @@ std::string generate_segmented_source(const ungar_b200_tape& T, int order, int& 
             instr_uses(T.code[size_t(i)], rd, wr);
             if (wr >= 0) last_write[size_t(wr)] = i;
         }
+        // ... and inside a kernel a value whose next use lies more than kLiveWindow instructions ahead is parked in the scratch array
+        // and re-loaded there: the quadruped tapes keep 700-2300 values alive at once, which ptxas would spill to thread-local memory
+        // (a stack frame of kilobytes, and launches of every other kernel of the process slowed down by the local-memory pool it forces)
+        std::set<std::pair<int, int>> park_after, reload_before;  // (instruction, slot)
+        {
+            std::vector<int> last_pos(ns, -1);     // last access of the slot's CURRENT value in this kernel
+            std::vector<char> in_scratch(ns, 0);   // the current value is in the scratch array
+            for (int sl : loads[size_t(k)]) in_scratch[size_t(sl)] = 1;
+            for (int i = i0; i < i1; ++i) {
+                int rd[4], wr;
+                instr_uses(T.code[size_t(i)], rd, wr);
+                for (int r : rd) {
+                    if (r < 0) continue;
+                    const int lp = last_pos[size_t(r)];
+                    if (lp >= 0 && lp != i && i - lp > kLiveWindow) {
+                        if (!in_scratch[size_t(r)]) { park_after.insert({lp, r}); in_scratch[size_t(r)] = 1; }
+                        reload_before.insert({i, r});
+                    }
+                    last_pos[size_t(r)] = i;
+                }
+                if (wr >= 0) { last_pos[size_t(wr)] = i; in_scratch[size_t(wr)] = 0; }
+            }
+        }
         for (int sl : touched[size_t(k)]) o << "  Jet<ORDER> r" << sl << ";\n";
         // the Hessian order accumulates sum_i w_i y_i'' over the outputs: the partial sum crosses the cuts in one extra scratch row
         if (order == 2 && k > 0) o << "  acc = scratch[(long long)" << T.n_slots << " * (ORDER + 1) * stride + t];\n";
@@ -714,14 +743,25 @@ std::string generate_segmented_source(const ungar_b200_tape& T, int order, int& 
             int rd[4], wr;
             instr_uses(T.code[size_t(i)], rd, wr);
             for (int r : rd)
-                if (r >= 0 && need_load[size_t(r)]) {
+                if (r >= 0 && (need_load[size_t(r)] || reload_before.count({i, r}))) {
                     o << "  r" << r << " = load_slot<ORDER>(scratch, stride, t, " << r << ");\n";
                     need_load[size_t(r)] = 0;
+                    reload_before.erase({i, r});
                 }
             if (wr >= 0) need_load[size_t(wr)] = 0;  // (an exposed read always precedes the first write, so this never drops a load)
             emit_instruction(o, T, T.code[size_t(i)], order);
-            if (wr >= 0 && need_store[size_t(wr)] && last_write[size_t(wr)] == i)
+            bool stored = false;
+            if (wr >= 0 && need_store[size_t(wr)] && last_write[size_t(wr)] == i) {
                 o << "  store_slot<ORDER>(scratch, stride, t, " << wr << ", r" << wr << ");\n";
+                stored = true;
+            }
+            // park values whose next use is far away (the definition itself, or an operand last touched here)
+            if (wr >= 0 && !stored && park_after.count({i, wr})) o << "  store_slot<ORDER>(scratch, stride, t, " << wr << ", r" << wr << ");\n";
+            for (int r : rd)
+                if (r >= 0 && r != wr && park_after.count({i, r})) {
+                    o << "  store_slot<ORDER>(scratch, stride, t, " << r << ", r" << r << ");\n";
+                    park_after.erase({i, r});
+                }
         }
         if (order == 2) {
             if (k + 1 < n_parts) o << "  scratch[(long long)" << T.n_slots << " * (ORDER + 1) * stride + t] = acc;\n";
@@ -736,31 +776,30 @@ bool driver_ok(CUresult r) { return r == CUDA_SUCCESS; }
 
 // Compiles (or loads from the content-hashed cache) the specialised kernel of `order`.  Never fails the call: on any problem the
 // state becomes -1 and the interpreter keeps serving.
-void specialize(ungar_b200_tape& T, int order) {
+int specialize_impl(ungar_b200_tape& T, int order) {
     ungar_b200_tape::Special& S = T.special[order];
-    S.state = -1;
     const char* off = getenv("UNGAR_B200_NO_NVRTC");
-    if ((off && off[0] == '1') || T.code.empty()) return;
+    if ((off && off[0] == '1') || T.code.empty()) return -1;
     const bool segmented = int(T.code.size()) > kSpecializeMax;
-    if (segmented && int(T.code.size()) > kSegmentedMax) return;
+    if (segmented && int(T.code.size()) > kSegmentedMax) return -1;
     if (segmented) {
         const char* seg_off = getenv("UNGAR_B200_NO_SEGMENTS");  // measurement switch: long tapes stay on the interpreter
-        if (seg_off && seg_off[0] == '1') return;
+        if (seg_off && seg_off[0] == '1') return -1;
     }
     LazyApi& api = lazy_api();
-    if (!api.ok) return;
+    if (!api.ok) return -1;
     const std::string dir = machine_header_dir();
     const std::string header = slurp(dir + "/tape_machine.cuh");
-    if (header.empty()) return;
+    if (header.empty()) return -1;
     int major = 0, minor = 0;
     cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, T.device);
     cudaDeviceGetAttribute(&minor, cudaDevAttrComputeCapabilityMinor, T.device);
-    if (major != 10) return;  // sm_100a only
+    if (major != 10) return -1;  // sm_100a only
     const std::string arch = "sm_100a";
     uint64_t h = fnv1a(T.code.data(), T.code.size() * sizeof(Instr));
     h = fnv1a(T.consts.data(), T.consts.size() * sizeof(double), h);
     h = fnv1a(&order, sizeof(order), h);
-    const int dims[6] = {T.n_slots, int(T.n_indep), int(T.n_dep), 4 /* generator version */, segmented ? kSegment : 0, segmented ? 1 : 0};
+    const int dims[6] = {T.n_slots, int(T.n_indep), int(T.n_dep), 5 /* generator version */, segmented ? kSegment : 0, segmented ? 1 : 0};
     h = fnv1a(dims, sizeof(dims), h);
     h = fnv1a(arch.data(), arch.size(), h);
     h = fnv1a(header.data(), header.size(), h);
@@ -774,7 +813,7 @@ void specialize(ungar_b200_tape& T, int order) {
         int n_parts_gen = 0;
         const std::string src = segmented ? generate_segmented_source(T, order, n_parts_gen) : generate_kernel_source(T, order);
         nvrtcProgram prog;
-        if (api.createProgram(&prog, src.c_str(), "tape_special.cu", 0, nullptr, nullptr) != NVRTC_SUCCESS) return;
+        if (api.createProgram(&prog, src.c_str(), "tape_special.cu", 0, nullptr, nullptr) != NVRTC_SUCCESS) return -1;
         const std::string inc1 = "-I" + dir, inc2 = "-I/usr/local/cuda/include", a = "--gpu-architecture=" + arch;
         const char* opts[] = {a.c_str(), inc1.c_str(), inc2.c_str(), "--std=c++17", "-default-device", "--fmad=true"};
         const auto t0 = std::chrono::steady_clock::now();
@@ -787,10 +826,10 @@ void specialize(ungar_b200_tape& T, int order) {
             api.getProgramLog(prog, log.data());
             if (getenv("UNGAR_B200_NVRTC_VERBOSE")) fprintf(stderr, "ungar_b200: NVRTC failed, the interpreter serves this tape:\n%s\n", log.c_str());
             api.destroyProgram(&prog);
-            return;
+            return -1;
         }
         size_t n = 0;
-        if (api.getCUBINSize(prog, &n) != NVRTC_SUCCESS || n == 0) { api.destroyProgram(&prog); return; }
+        if (api.getCUBINSize(prog, &n) != NVRTC_SUCCESS || n == 0) { api.destroyProgram(&prog); return -1; }
         cubin.resize(n);
         api.getCUBIN(prog, cubin.data());
         api.destroyProgram(&prog);
@@ -802,18 +841,38 @@ void specialize(ungar_b200_tape& T, int order) {
         if (f) rename(tmp.c_str(), path.c_str());
     }
     cudaFree(nullptr);  // make sure the runtime's primary context is current for the driver API
-    if (!driver_ok(api.moduleLoadData(&S.module, cubin.data()))) return;
+    if (!driver_ok(api.moduleLoadData(&S.module, cubin.data()))) return -1;
     if (segmented) {
         const int n_parts = (int(T.code.size()) + kSegment - 1) / kSegment;
         S.parts.assign(size_t(n_parts), nullptr);
         for (int k = 0; k < n_parts; ++k) {
             const std::string fname = "tape_part_" + std::to_string(k);
-            if (!driver_ok(api.moduleGetFunction(&S.parts[size_t(k)], S.module, fname.c_str()))) { S.parts.clear(); return; }
+            if (!driver_ok(api.moduleGetFunction(&S.parts[size_t(k)], S.module, fname.c_str()))) { S.parts.clear(); return -1; }
         }
     } else if (!driver_ok(api.moduleGetFunction(&S.fn, S.module, "tape_special"))) {
-        return;
+        return -1;
     }
-    S.state = 1;
+    return 1;
+}
+
+
+// Short tapes compile in seconds, in the calling thread.  The segmented kernels of a long tape take tens of seconds: a worker thread
+// compiles them while the interpreter keeps serving the calls; the specialised kernels take over from the first call after the
+// compile has finished (ungar_b200_tape_special_wait blocks until then).  UNGAR_B200_NVRTC_SYNC=1 compiles everything in the caller.
+void specialize(ungar_b200_tape& T, int order) {
+    ungar_b200_tape::Special& S = T.special[order];
+    const char* sync = getenv("UNGAR_B200_NVRTC_SYNC");
+    lazy_api();  // bind NVRTC / the driver API in this thread (the first use is not thread-safe)
+    if (int(T.code.size()) > kSpecializeMax && !(sync && sync[0] == '1')) {
+        S.state.store(2, std::memory_order_release);
+        ungar_b200_tape* tp = &T;
+        S.worker = std::thread([tp, order] {
+            cudaSetDevice(tp->device);
+            tp->special[order].state.store(specialize_impl(*tp, order), std::memory_order_release);
+        });
+    } else {
+        S.state.store(specialize_impl(T, order), std::memory_order_release);
+    }
 }
 
 template <int ORDER>
@@ -824,8 +883,9 @@ int launch(ungar_b200_tape& T, const ub::tape::Seeds& seeds, const double* d_x, 
     const long long blocks = (threads + 127) / 128;
     if (blocks > 2147483647LL) return tfail(UNGAR_B200_EINVAL, "batch x directions too large for one launch");
     // the straight-line kernel from the second call of this ORDER on (a function evaluated once never pays the compile)
-    if (T.calls[ORDER]++ >= kSpecializeAfter && T.special[ORDER].state == 0) specialize(T, ORDER);
-    if (T.special[ORDER].state == 1 && !T.special[ORDER].parts.empty()) {  // a long tape: its kernels back to back, values cross through the scratch
+    if (T.calls[ORDER]++ >= kSpecializeAfter && T.special[ORDER].state.load(std::memory_order_acquire) == 0) specialize(T, ORDER);
+    const int special_state = T.special[ORDER].state.load(std::memory_order_acquire);
+    if (special_state == 1 && !T.special[ORDER].parts.empty()) {  // a long tape: its kernels back to back, values cross through the scratch
         if (int rc = T.scratch.reserve(size_t(T.n_slots + 1) * (ORDER + 1) * size_t(stride) * sizeof(double))) return rc;  // + the Hessian accumulator's row
         ub::tape::Seeds sd = seeds;
         long long ldx = ld_x, b64 = batch, ldo = ld_out, st = stride;
@@ -839,7 +899,7 @@ int launch(ungar_b200_tape& T, const ub::tape::Seeds& seeds, const double* d_x, 
         }
         return UNGAR_B200_OK;
     }
-    if (T.special[ORDER].state == 1) {
+    if (special_state == 1) {
         ub::tape::Seeds sd = seeds;
         long long ldx = ld_x, b64 = batch, ldo = ld_out;
         int nd = ndir;
@@ -908,18 +968,28 @@ int ungar_b200_tape_kernel_source(const ungar_b200_tape* tape, int32_t order, ch
 int ungar_b200_tape_special_info(const ungar_b200_tape* tape, int64_t* info) {
     if (!tape || !info) return tfail(UNGAR_B200_EINVAL, "null argument");
     for (int o = 0; o < 3; ++o) {
-        info[4 * o + 0] = tape->special[o].state;
-        info[4 * o + 1] = tape->special[o].from_cache ? 1 : 0;
-        info[4 * o + 2] = int64_t(tape->special[o].key & 0xffffffffull);
-        info[4 * o + 3] = int64_t(tape->special[o].key >> 32);
+        const int st = tape->special[o].state.load(std::memory_order_acquire);
+        info[4 * o + 0] = st;
+        info[4 * o + 1] = st != 2 && tape->special[o].from_cache ? 1 : 0;  // (a worker may still be writing these)
+        info[4 * o + 2] = st != 2 ? int64_t(tape->special[o].key & 0xffffffffull) : 0;
+        info[4 * o + 3] = st != 2 ? int64_t(tape->special[o].key >> 32) : 0;
     }
+    return UNGAR_B200_OK;
+}
+
+int ungar_b200_tape_special_wait(ungar_b200_tape* tape) {
+    if (!tape) return tfail(UNGAR_B200_EINVAL, "null argument");
+    for (auto& sp : tape->special)
+        if (sp.worker.joinable()) sp.worker.join();
     return UNGAR_B200_OK;
 }
 
 int ungar_b200_tape_destroy(ungar_b200_tape* tape) {
     if (tape)
-        for (auto& sp : tape->special)
+        for (auto& sp : tape->special) {
+            if (sp.worker.joinable()) sp.worker.join();
             if (sp.module && lazy_api().ok) lazy_api().moduleUnload(sp.module);
+        }
     if (!tape) return UNGAR_B200_OK;
     int count = 0;
     if (cudaGetDeviceCount(&count) == cudaSuccess && tape->device < count) cudaSetDevice(tape->device);
