@@ -293,15 +293,18 @@ int ungar_b200_tape_destroy(ungar_b200_tape* tape);
  * instructions runs as ONE straight-line sm_100a kernel (a longer one, up to 100 000, as a sequence of kernels of 6 000 instructions)
  * compiled with NVRTC and cached on disk under a CONTENT hash (instruction
  * stream, constants, order, arch, the text of csrc/tape_machine.cuh) — the reference caches its generated library by NAME only
- * (function.hpp:420-451).  info[4 * order + {0, 1, 2, 3}], order 0..2 = {state: 0 not tried / 1 specialised / -1 interpreter,
+ * (function.hpp:420-451).  info[4 * order + {0, 1, 2, 3}] (16 entries), order 0..2 and 3 = the reverse sweep that serves the gradient
+ * of a SCALAR function with 8 or more colours in one pass per vector = {state: 0 not tried / 1 specialised / -1 interpreter / 2 compiling,
  * served from the cache, low 32 bits of the hash, high 32 bits}.  UNGAR_B200_KERNEL_CACHE names the cache directory,
- * UNGAR_B200_NO_NVRTC=1 keeps the interpreter. */
+ * UNGAR_B200_NO_NVRTC=1 keeps the interpreter.  The reverse sweep is opt-in (UNGAR_B200_REVERSE=1): validated on the CPU by replaying its
+ * generated text, not yet run on a GPU. */
 int ungar_b200_tape_special_info(const ungar_b200_tape* tape, int64_t* info);
 /* The kernels of a tape beyond 12 000 instructions take tens of seconds to compile: a worker thread does it (state 2 in
  * ungar_b200_tape_special_info) while the interpreter keeps serving the calls.  This call blocks until no compile is in flight.
  * UNGAR_B200_NVRTC_SYNC=1 compiles in the calling thread instead. */
 int ungar_b200_tape_special_wait(ungar_b200_tape* tape);
-/* The CUDA source the NVRTC path generates for `order` (0 values, 1 Jacobian, 2 Hessian jets): ONE kernel `tape_special` for tapes of
+/* The CUDA source the NVRTC path generates for `order` (0 values, 1 Jacobian, 2 Hessian jets, 3 the reverse sweep of a scalar
+ * function, kernel `tape_reverse`): ONE kernel `tape_special` for tapes of
  * up to 12 000 instructions, otherwise kernels `tape_part_<k>` of 6 000 instructions each whose cross-kernel values travel through the
  * scratch array.  Host-only (no device, no compile): `buffer` receives at most `capacity` bytes including the terminating 0,
  * `*required` the size of the whole text, `*n_kernels` the number of kernels.  Diagnostics / tests. */

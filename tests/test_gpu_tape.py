@@ -438,3 +438,36 @@ def test_long_tapes_run_as_segmented_specialised_kernels(tmp_path, monkeypatch):
     g._tape.forward_zero(X)
     g._tape.forward_zero(X)
     assert g._tape.wait_specialised()[0]["state"] == -1
+
+
+@pytest.mark.skipif(os.environ.get("UNGAR_B200_RUN_UNVALIDATED") != "1",
+                    reason="the reverse sweep is opt-in and has not run on a GPU yet (GPU budget of the round was spent): its generator is validated "
+                           "on the CPU by tests/test_tape_host.py::test_reverse_sweep_source_is_consistent_and_compiles")
+def test_reverse_sweep_serves_the_gradient_of_scalar_functions(monkeypatch, tmp_path):
+    """A scalar function has one dense Jacobian row: forward mode needs one direction per independent.  With UNGAR_B200_REVERSE=1 the
+    gradient comes, from the second call on, from ONE generated reverse sweep per vector (csrc/tape.cu::generate_reverse_source,
+    special_info()[3]); it must equal the forward-mode Jacobian of the first call."""
+    from test_tape_host import _scalar_objective
+
+    monkeypatch.setenv("UNGAR_B200_REVERSE", "1")
+    monkeypatch.setenv("UNGAR_B200_KERNEL_CACHE", str(tmp_path / "kernels"))
+    n = 24
+    f = A.MakeFunction(A.Blueprint(_scalar_objective, n, 0, "scalar_objective", A.JACOBIAN))
+    assert f.tape_info()["jacobian_colors"] == n
+    rng = np.random.default_rng(4)
+    X = 0.3 + 0.4 * rng.random((257, n))
+    J0 = f._tape.sparse_jacobian(X)                       # forward mode, n directions per vector (interpreter)
+    J1 = f._tape.sparse_jacobian(X)                       # reverse sweep, one thread per vector
+    info = f._tape.special_info()
+    assert info[3]["state"] == 1 and info[1]["state"] == 0, info
+    assert np.isfinite(J1).all() and np.allclose(J1, J0, rtol=1e-12, atol=1e-14)
+    import torch
+
+    J2 = f._tape.sparse_jacobian(torch.from_numpy(X).cuda()).cpu().numpy()
+    assert np.array_equal(J2, J1)
+    monkeypatch.delenv("UNGAR_B200_REVERSE")              # without the switch: the forward path (which then specialises as before)
+    g = A.MakeFunction(A.Blueprint(_scalar_objective, n, 0, "scalar_objective", A.JACOBIAN))
+    g._tape.sparse_jacobian(X)
+    Jg = g._tape.sparse_jacobian(X)
+    gi = g._tape.special_info()
+    assert gi[3]["state"] == 0 and gi[1]["state"] == 1 and np.allclose(Jg, J0, rtol=1e-12, atol=1e-14)

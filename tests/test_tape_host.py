@@ -322,3 +322,143 @@ def test_generated_kernels_compile_for_sm_100a_without_a_gpu():
         err, n = nvrtc.nvrtcGetCUBINSize(prog)
         assert err == nvrtc.nvrtcResult.NVRTC_SUCCESS and n > 1000
         nvrtc.nvrtcDestroyProgram(prog)
+
+
+def _scalar_objective(v):
+    """A scalar function touching every tape operation the reference's objectives use, with slot reuse and a CondExp."""
+    n = len(v)
+    acc = 0.0
+    for i in range(n - 1):
+        d = v[i] - 0.5 * v[i + 1]
+        acc = acc + d * d + 0.1 * A.sin(v[i]) * A.cos(v[i + 1]) + A.sqrt(1.0 + v[i] * v[i]) / (2.0 + A.exp(-v[i + 1]))
+        acc = acc + A.CondExpGt(v[i], v[i + 1], v[i] * v[i + 1], A.pow(v[i], 2)) + A.atan2(v[i], 1.5 + v[i + 1] * v[i + 1]) - A.log(2.0 + A.abs_(d))
+    return [acc]
+
+
+def test_reverse_sweep_source_is_consistent_and_compiles():
+    """Reverse sweep of a scalar function (csrc/tape.cu::generate_reverse_source): host-only replay of the generated text with plain
+    floats — forward statements through a tiny interpreter of the op functions, backward statements as written — against central
+    differences, and an NVRTC compile for sm_100a."""
+    import math
+    import re
+
+    n = 24
+    f = A.MakeFunction(A.Blueprint(_scalar_objective, n, 0, "scalar_objective_host", A.JACOBIAN))
+    src, parts = f._tape.kernel_source(3)
+    assert parts == 1 and "tape_reverse" in src
+    rng = np.random.default_rng(2)
+    x = 0.3 + 0.4 * rng.random(n)
+    rows, cols = f.JacobianSparsity()
+    elem = -np.ones(n, dtype=int)
+    elem[cols] = np.arange(cols.size)
+
+    # --- replay: translate the generated statements into Python (values only; the op functions restated here)
+    OPS = {2: lambda a, b: a + b, 3: lambda a, b: a - b, 4: lambda a, b: a * b, 5: lambda a, b: a / b, 18: lambda a, b: math.atan2(a, b),
+           17: lambda a, b: a ** b}
+    UN = {6: lambda a: -a, 7: math.sqrt, 8: math.sin, 9: math.cos, 10: math.tan, 11: math.atan, 12: math.acos, 13: math.asin, 14: math.exp,
+          15: math.log, 16: abs}
+    CMP = {19: lambda a, b: a < b, 20: lambda a, b: a <= b, 21: lambda a, b: a > b, 22: lambda a, b: a >= b, 23: lambda a, b: a == b}
+    r, a, V, out = {}, {}, {}, np.zeros(cols.size)
+    body = src[src.index("tape_reverse"):]
+    for line in body.splitlines():
+        line = line.strip()
+        m = re.match(r"Jet<ORDER> r(\d+); double a(\d+) = 0.0;", line)
+        if m:
+            a[int(m.group(2))] = 0.0
+            continue
+        m = re.match(r"V\((\d+)\) = r(\d+)\.v;", line)
+        if m:
+            V[int(m.group(1))] = r[int(m.group(2))]
+            continue
+        m = re.match(r"r(\d+) = jet_const<ORDER>\(x\[(\d+)\]\);", line)
+        if m:
+            r[int(m.group(1))] = float(x[int(m.group(2))])
+            continue
+        m = re.match(r"r(\d+) = jet_const<ORDER>\((\S+)\);", line)
+        if m:
+            r[int(m.group(1))] = float.fromhex(m.group(2))
+            continue
+        m = re.match(r"r(\d+) = jet_binary<ORDER>\((\d+), r(\d+), r(\d+)\);", line)
+        if m:
+            r[int(m.group(1))] = OPS[int(m.group(2))](r[int(m.group(3))], r[int(m.group(4))])
+            continue
+        m = re.match(r"r(\d+) = jet_pow_const<ORDER>\(r(\d+), (\S+)\);", line)
+        if m:
+            r[int(m.group(1))] = r[int(m.group(2))] ** float.fromhex(m.group(3))
+            continue
+        m = re.match(r"r(\d+) = jet_unary<ORDER>\((\d+), r(\d+)\);", line)
+        if m:
+            r[int(m.group(1))] = UN[int(m.group(2))](r[int(m.group(3))])
+            continue
+        m = re.match(r"r(\d+) = jet_compare\((\d+), r(\d+)\.v, r(\d+)\.v\) \? r(\d+) : r(\d+);", line)
+        if m:
+            r[int(m.group(1))] = r[int(m.group(5))] if CMP[int(m.group(2))](r[int(m.group(3))], r[int(m.group(4))]) else r[int(m.group(6))]
+            continue
+        # ---- backward statements: C expressions over a<k>, V(i), g and a few locals — evaluated as written
+        if line.startswith("{ const int e = elem["):
+            m = re.match(r"\{ const int e = elem\[(\d+)\]; if \(e >= 0\) out\[e\] \+= a(\d+); a(\d+) = 0.0; \}", line)
+            j, s_ = int(m.group(1)), int(m.group(2))
+            if elem[j] >= 0:
+                out[elem[j]] += a[s_]
+            a[s_] = 0.0
+            continue
+        m = re.match(r"a(\d+) \+= 1\.0;", line)
+        if m:
+            a[int(m.group(1))] += 1.0
+            continue
+        m = re.match(r"a(\d+) = 0\.0;", line)
+        if m:
+            a[int(m.group(1))] = 0.0
+            continue
+        if line.startswith("{ const double g = a"):
+            env = {"pow": math.pow, "log": math.log, "sin": math.sin, "cos": math.cos, "rsqrt": lambda z: 1.0 / math.sqrt(z),
+                   "double": float, "jet_compare": lambda op, p, q: CMP[op](p, q)}
+            stmts = [t.strip() for t in line.strip("{} ").split(";") if t.strip()]
+            for st in stmts:
+                st = re.sub(r"V\((-?\d+)\)", lambda mm: repr(V[int(mm.group(1))]), st)
+                st = re.sub(r"\ba(\d+)\b", r"A[\1]", st)
+                st = re.sub(r"0x[0-9a-fA-F.]+p[+-]?\d+", lambda mm: repr(float.fromhex(mm.group(0))), st)
+                if st.startswith("const double "):
+                    for piece in st[len("const double "):].split(", "):
+                        name, expr = piece.split(" = ", 1)
+                        env[name.strip()] = eval(expr, {"A": a}, env)
+                elif st.startswith("if ("):
+                    mm = re.match(r"if \((.*)\) (A\[\d+\]) \+= g$", st)
+                    cond = eval(mm.group(1), {"A": a}, env)
+                    pending_else = (mm.group(2), cond)
+                    if cond:
+                        exec(f"{mm.group(2)} += g", {"A": a}, env)
+                elif st.startswith("else "):
+                    if not pending_else[1]:
+                        exec(st[5:], {"A": a}, env)
+                else:
+                    exec(st, {"A": a}, env)
+            continue
+    ref = np.zeros(cols.size)
+    fx = lambda z: float(_scalar_objective(list(z))[0])  # noqa: E731
+    for e, j in enumerate(cols):
+        h = 1e-6
+        xp_, xm_ = x.copy(), x.copy()
+        xp_[j] += h
+        xm_[j] -= h
+        ref[e] = (fx(xp_) - fx(xm_)) / (2 * h)
+    assert np.allclose(out, ref, rtol=2e-6, atol=1e-8), np.max(np.abs(out - ref))
+
+    try:
+        from cuda.bindings import nvrtc
+    except Exception:
+        try:
+            from cuda import nvrtc
+        except Exception:
+            return
+    import os
+
+    hdr = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "ungar_b200", "csrc")
+    err, prog = nvrtc.nvrtcCreateProgram(src.encode(), b"tape_reverse.cu", 0, [], [])
+    opts = [b"--gpu-architecture=sm_100a", f"-I{hdr}".encode(), b"-I/usr/local/cuda/include", b"--std=c++17", b"-default-device", b"--fmad=true"]
+    (err,) = nvrtc.nvrtcCompileProgram(prog, len(opts), opts)
+    if err != nvrtc.nvrtcResult.NVRTC_SUCCESS:
+        _, nlog = nvrtc.nvrtcGetProgramLogSize(prog)
+        log = b" " * nlog
+        nvrtc.nvrtcGetProgramLog(prog, log)
+        raise AssertionError(log.decode(errors="replace")[-2000:])

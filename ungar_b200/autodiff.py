@@ -259,12 +259,12 @@ class TapeHandle:
             pass
 
     def special_info(self) -> dict:
-        """State of the NVRTC-specialised kernels per order (0 values, 1 Jacobian, 2 Hessian): ``state`` 0 not tried / 1 specialised /
+        """State of the NVRTC-specialised kernels per order (0 values, 1 Jacobian, 2 Hessian, 3 reverse sweep of a scalar function): ``state`` 0 not tried / 1 specialised /
         -1 interpreter / 2 compiling in the background, ``from_cache``, ``key`` = content hash the compiled kernel is cached under."""
-        buf = (ctypes.c_int64 * 12)()
+        buf = (ctypes.c_int64 * 16)()
         check(self._lib.ungar_b200_tape_special_info(self._h, buf))
         return {o: {"state": int(buf[4 * o]), "from_cache": bool(buf[4 * o + 1]), "key": (int(buf[4 * o + 3]) << 32) | int(buf[4 * o + 2])}
-                for o in range(3)}
+                for o in range(4)}  # 3: the reverse sweep of a scalar function
 
     def wait_specialised(self) -> dict:
         """Blocks until no background compile of this tape's kernels is in flight (long tapes compile on a worker thread while the

@@ -9,6 +9,7 @@
 #include <fstream>
 #include <sstream>
 #include <sys/stat.h>
+#include <array>
 #include <atomic>
 #include <thread>
 #include <type_traits>
@@ -135,12 +136,14 @@ struct ungar_b200_tape {
         uint64_t key = 0;
         bool from_cache = false;
         double compile_seconds = 0.0;
-    } special[3];
-    int64_t calls[3] = {0, 0, 0};
+    } special[4];  // orders 0, 1, 2 and [3]: the reverse sweep of a scalar function (gradient in one pass)
+    int64_t calls[4] = {0, 0, 0, 0};
+    std::vector<int> elem_of_indep;  // scalar functions: selected Jacobian element of independent i, or -1
+    bool elem_uploaded = false;
 
     // device state
     bool uploaded = false, j_uploaded = false, h_uploaded = false;
-    DevBuf d_code, d_consts, d_color, d_jac_slot, d_pi, d_pj, d_di, d_dj, d_pr, d_w, scratch, ws_x, ws_out, ws_q;
+    DevBuf d_elem, d_code, d_consts, d_color, d_jac_slot, d_pi, d_pj, d_di, d_dj, d_pr, d_w, scratch, ws_x, ws_out, ws_q;
 };
 
 namespace {
@@ -379,6 +382,13 @@ int choose_jacobian(ungar_b200_tape& T, const int64_t* rows, const int64_t* cols
     T.j_cols.swap(sel_cols);
     T.j_set = true;
     T.j_uploaded = false;
+    // scalar functions: where the reverse sweep puts d y / d x_i
+    T.elem_of_indep.clear();
+    T.elem_uploaded = false;
+    if (T.n_dep == 1) {
+        T.elem_of_indep.assign(size_t(T.n_indep), -1);
+        for (size_t e = 0; e < T.j_cols.size(); ++e) T.elem_of_indep[size_t(T.j_cols[e])] = int(e);
+    }
     return UNGAR_B200_OK;
 }
 
@@ -644,6 +654,84 @@ std::string generate_kernel_source(const ungar_b200_tape& T, int order) {
     return o.str();
 }
 
+// Reverse sweep of a SCALAR function: one thread per xp vector computes the whole gradient in two passes over the tape instead of one
+// forward pass per colour (an objective has one dense row: as many colours as independents it depends on).  Forward: the value
+// program as in the single-kernel form, every instruction's value also written to the scratch array V[instruction][thread].
+// Backward: adjoints live in registers named after the SLOT of the value they belong to — the adjoint of a value is live exactly where
+// the value was (from its last use back to its definition), so the liveness-based slot assignment of the forward program is a valid
+// register assignment for the adjoints too; an instruction takes the adjoint of its result, clears it (the slot's previous occupant
+// starts from zero) and adds its partial derivatives, read from V, to the adjoints of its operands' slots.
+void instr_uses(const ub::tape::Instr& in, int reads[4], int& write);
+
+std::string generate_reverse_source(const ungar_b200_tape& T) {
+    using namespace ub::tape;
+    const int n = int(T.code.size());
+    std::vector<int> prod(size_t(T.n_slots), -1);               // instruction that produced the slot's current value
+    std::vector<std::array<int, 4>> from(size_t(n), std::array<int, 4>{-1, -1, -1, -1});
+    for (int i = 0; i < n; ++i) {
+        int rd[4], wr;
+        instr_uses(T.code[size_t(i)], rd, wr);
+        for (int q = 0; q < 4; ++q)
+            if (rd[q] >= 0) from[size_t(i)][size_t(q)] = prod[size_t(rd[q])];
+        if (wr >= 0) prod[size_t(wr)] = i;
+    }
+    std::ostringstream o;
+    o.precision(17);
+    o << "#include \"tape_machine.cuh\"\nusing namespace ub::tape;\n#define V(i) scratch[(long long)(i) * stride + t]\n"
+      << "extern \"C\" __global__ void __launch_bounds__(128) tape_reverse(const double* __restrict__ x_all, long long ld_x, long long batch,\n"
+      << "    double* __restrict__ out_all, long long ld_out, const int* __restrict__ elem, int nnz, double* __restrict__ scratch, long long stride) {\n"
+      << "  constexpr int ORDER = 0;\n"
+      << "  const long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x;\n  if (t >= batch) return;\n"
+      << "  const double* __restrict__ x = x_all + t * ld_x;\n  double* __restrict__ out = out_all + t * ld_out;\n"
+      << "  for (int e = 0; e < nnz; ++e) out[e] = 0.0;\n";
+    for (int k = 0; k < T.n_slots; ++k) o << "  Jet<ORDER> r" << k << "; double a" << k << " = 0.0;\n";
+    for (int i = 0; i < n; ++i) {
+        const Instr& in = T.code[size_t(i)];
+        if (in.op == T_OUTPUT || in.op == T_OUTPUT_CONST) continue;
+        emit_instruction(o, T, in, 0);
+        o << "  V(" << i << ") = r" << in.dst << ".v;\n";
+    }
+    auto A = [](int slot) { return "a" + std::to_string(slot); };
+    for (int i = n - 1; i >= 0; --i) {
+        const Instr& in = T.code[size_t(i)];
+        const std::array<int, 4>& pr = from[size_t(i)];
+        const std::string va = "V(" + std::to_string(pr[0]) + ")", vb = "V(" + std::to_string(pr[1]) + ")", vi = "V(" + std::to_string(i) + ")";
+        if (in.op == T_OUTPUT) { o << "  " << A(in.a) << " += 1.0;\n"; continue; }
+        if (in.op == T_OUTPUT_CONST) continue;
+        if (in.op == T_INDEP) { o << "  { const int e = elem[" << in.a << "]; if (e >= 0) out[e] += " << A(in.dst) << "; " << A(in.dst) << " = 0.0; }\n"; continue; }
+        if (in.op == T_CONST) { o << "  " << A(in.dst) << " = 0.0;\n"; continue; }
+        o << "  { const double g = " << A(in.dst) << "; " << A(in.dst) << " = 0.0; ";
+        switch (in.op) {
+            case T_ADD: o << A(in.a) << " += g; " << A(in.b) << " += g;"; break;
+            case T_SUB: o << A(in.a) << " += g; " << A(in.b) << " -= g;"; break;
+            case T_MUL: o << "const double pa = " << va << ", pb = " << vb << "; " << A(in.a) << " += g * pb; " << A(in.b) << " += g * pa;"; break;
+            case T_DIV: o << "const double ib = 1.0 / " << vb << "; " << A(in.a) << " += g * ib; " << A(in.b) << " -= g * " << vi << " * ib;"; break;
+            case T_ATAN2: o << "const double pa = " << va << ", pb = " << vb << ", inv = g / (pa * pa + pb * pb); " << A(in.a) << " += pb * inv; " << A(in.b) << " -= pa * inv;"; break;
+            case T_POW:
+                if (in.c >= 0) o << "const double k = " << hexd(T.consts[size_t(in.c)]) << "; " << A(in.a) << " += g * k * pow(" << va << ", k - 1.0);";
+                else o << "const double pa = " << va << ", pb = " << vb << "; " << A(in.a) << " += g * pb * pow(pa, pb - 1.0); " << A(in.b) << " += g * " << vi << " * log(pa);";
+                break;
+            case T_CLT: case T_CLE: case T_CGT: case T_CGE: case T_CEQ:
+                o << "if (jet_compare(" << in.op << ", " << va << ", " << vb << ")) " << A(in.c) << " += g; else " << A(in.d) << " += g;";
+                break;
+            case T_NEG: o << A(in.a) << " -= g;"; break;
+            case T_SQRT: o << A(in.a) << " += g * 0.5 / " << vi << ";"; break;
+            case T_SIN: o << A(in.a) << " += g * cos(" << va << ");"; break;
+            case T_COS: o << A(in.a) << " -= g * sin(" << va << ");"; break;
+            case T_TAN: o << "const double y = " << vi << "; " << A(in.a) << " += g * (1.0 + y * y);"; break;
+            case T_ATAN: o << "const double pa = " << va << "; " << A(in.a) << " += g / (1.0 + pa * pa);"; break;
+            case T_ACOS: o << "const double pa = " << va << "; " << A(in.a) << " -= g * rsqrt(1.0 - pa * pa);"; break;
+            case T_ASIN: o << "const double pa = " << va << "; " << A(in.a) << " += g * rsqrt(1.0 - pa * pa);"; break;
+            case T_EXP: o << A(in.a) << " += g * " << vi << ";"; break;
+            case T_LOG: o << A(in.a) << " += g / " << va << ";"; break;
+            default: o << "const double pa = " << va << "; " << A(in.a) << " += g * double((pa > 0.0) - (pa < 0.0));";  // T_ABS
+        }
+        o << " }\n";
+    }
+    o << "}\n";
+    return o.str();
+}
+
 // Which slots an instruction reads / writes (-1: none).
 void instr_uses(const ub::tape::Instr& in, int reads[4], int& write) {
     using namespace ub::tape;
@@ -780,7 +868,8 @@ int specialize_impl(ungar_b200_tape& T, int order) {
     ungar_b200_tape::Special& S = T.special[order];
     const char* off = getenv("UNGAR_B200_NO_NVRTC");
     if ((off && off[0] == '1') || T.code.empty()) return -1;
-    const bool segmented = int(T.code.size()) > kSpecializeMax;
+    if (order == 3 && (int(T.code.size()) > kSpecializeMax || T.n_dep != 1)) return -1;  // the reverse sweep: one kernel, scalar functions
+    const bool segmented = order < 3 && int(T.code.size()) > kSpecializeMax;
     if (segmented && int(T.code.size()) > kSegmentedMax) return -1;
     if (segmented) {
         const char* seg_off = getenv("UNGAR_B200_NO_SEGMENTS");  // measurement switch: long tapes stay on the interpreter
@@ -811,7 +900,7 @@ int specialize_impl(ungar_b200_tape& T, int order) {
     S.from_cache = !cubin.empty();
     if (cubin.empty()) {
         int n_parts_gen = 0;
-        const std::string src = segmented ? generate_segmented_source(T, order, n_parts_gen) : generate_kernel_source(T, order);
+        const std::string src = order == 3 ? generate_reverse_source(T) : segmented ? generate_segmented_source(T, order, n_parts_gen) : generate_kernel_source(T, order);
         nvrtcProgram prog;
         if (api.createProgram(&prog, src.c_str(), "tape_special.cu", 0, nullptr, nullptr) != NVRTC_SUCCESS) return -1;
         const std::string inc1 = "-I" + dir, inc2 = "-I/usr/local/cuda/include", a = "--gpu-architecture=" + arch;
@@ -849,7 +938,7 @@ int specialize_impl(ungar_b200_tape& T, int order) {
             const std::string fname = "tape_part_" + std::to_string(k);
             if (!driver_ok(api.moduleGetFunction(&S.parts[size_t(k)], S.module, fname.c_str()))) { S.parts.clear(); return -1; }
         }
-    } else if (!driver_ok(api.moduleGetFunction(&S.fn, S.module, "tape_special"))) {
+    } else if (!driver_ok(api.moduleGetFunction(&S.fn, S.module, order == 3 ? "tape_reverse" : "tape_special"))) {
         return -1;
     }
     return 1;
@@ -863,7 +952,7 @@ void specialize(ungar_b200_tape& T, int order) {
     ungar_b200_tape::Special& S = T.special[order];
     const char* sync = getenv("UNGAR_B200_NVRTC_SYNC");
     lazy_api();  // bind NVRTC / the driver API in this thread (the first use is not thread-safe)
-    if (int(T.code.size()) > kSpecializeMax && !(sync && sync[0] == '1')) {
+    if (order < 3 && int(T.code.size()) > kSpecializeMax && !(sync && sync[0] == '1')) {
         S.state.store(2, std::memory_order_release);
         ungar_b200_tape* tp = &T;
         S.worker = std::thread([tp, order] {
@@ -919,6 +1008,39 @@ int launch(ungar_b200_tape& T, const ub::tape::Seeds& seeds, const double* d_x, 
     return UNGAR_B200_OK;
 }
 
+// Gradient of a scalar function by the generated reverse sweep (generate_reverse_source): one thread per xp vector.  Returns 1 when the
+// call was served, 0 when the caller should use the forward path (not a scalar function, too few colours to pay, kernel unavailable).
+constexpr int kReverseMinColors = 8;
+int launch_reverse(ungar_b200_tape& T, const double* d_x, int64_t ld_x, int64_t batch, double* d_out, int64_t ld_out, int nnz, cudaStream_t stream, int& served) {
+    served = 0;
+    // OPT-IN (UNGAR_B200_REVERSE=1): the generator is validated on the CPU (tests/test_tape_host.py replays the generated text against
+    // differences and compiles it with NVRTC) but has not run on a GPU yet, and its compile time grows to minutes for tapes of
+    // several thousand instructions — too long for a synchronous first use.
+    const char* on = getenv("UNGAR_B200_REVERSE");
+    if (!(on && on[0] == '1')) return UNGAR_B200_OK;
+    if (T.n_dep != 1 || T.n_colors < kReverseMinColors || int(T.code.size()) > kSpecializeMax) return UNGAR_B200_OK;
+    if (T.calls[3]++ >= kSpecializeAfter && T.special[3].state.load(std::memory_order_acquire) == 0) specialize(T, 3);
+    if (T.special[3].state.load(std::memory_order_acquire) != 1) return UNGAR_B200_OK;
+    if (T.elem_of_indep.empty()) return UNGAR_B200_OK;
+    if (!T.elem_uploaded) {
+        if (int rc = T.d_elem.upload(T.elem_of_indep)) return rc;
+        T.elem_uploaded = true;
+    }
+    const long long stride = (batch + 31) & ~31LL;
+    const long long blocks = (batch + 127) / 128;
+    if (int rc = T.scratch.reserve(size_t(T.code.size()) * size_t(stride) * sizeof(double))) return rc;
+    long long ldx = ld_x, b64 = batch, ldo = ld_out, st = stride;
+    int nz = nnz;
+    const int* elem = static_cast<const int*>(T.d_elem.ptr);
+    double* scr = static_cast<double*>(T.scratch.ptr);
+    void* args[] = {&d_x, &ldx, &b64, &d_out, &ldo, &elem, &nz, &scr, &st};
+    const CUresult r = lazy_api().launchKernel(T.special[3].fn, unsigned(blocks), 1, 1, 128, 1, 1, 0, reinterpret_cast<CUstream>(stream), args, nullptr);
+    if (r != CUDA_SUCCESS) return tfail(UNGAR_B200_ECUDA, "cuLaunchKernel of the reverse-sweep kernel failed (%d)", int(r));
+    ub_count_launch();
+    served = 1;
+    return UNGAR_B200_OK;
+}
+
 }  // namespace
 
 // =====================================================================================================================
@@ -950,9 +1072,12 @@ int ungar_b200_tape_create(const ungar_b200_tape_node* nodes, int64_t n_nodes, i
 }
 
 int ungar_b200_tape_kernel_source(const ungar_b200_tape* tape, int32_t order, char* buffer, int64_t capacity, int64_t* required, int32_t* n_kernels) {
-    if (!tape || order < 0 || order > 2 || capacity < 0 || (capacity > 0 && !buffer)) return tfail(UNGAR_B200_EINVAL, "bad argument");
+    if (!tape || order < 0 || order > 3 || capacity < 0 || (capacity > 0 && !buffer)) return tfail(UNGAR_B200_EINVAL, "bad argument");
+    if (order == 3 && (tape->n_dep != 1 || int(tape->code.size()) > kSpecializeMax))
+        return tfail(UNGAR_B200_EUNSUPPORTED, "the reverse sweep serves scalar functions of up to %d instructions", kSpecializeMax);
     int parts = 1;
-    const std::string src = int(tape->code.size()) > kSpecializeMax ? generate_segmented_source(*tape, order, parts) : generate_kernel_source(*tape, order);
+    const std::string src = order == 3 ? generate_reverse_source(*tape)
+                            : int(tape->code.size()) > kSpecializeMax ? generate_segmented_source(*tape, order, parts) : generate_kernel_source(*tape, order);
     if (required) *required = int64_t(src.size()) + 1;
     if (n_kernels) *n_kernels = parts;
     if (capacity > 0) {
@@ -967,7 +1092,7 @@ int ungar_b200_tape_kernel_source(const ungar_b200_tape* tape, int32_t order, ch
 // low and high 32 bits of the content hash.  Test / diagnostics hook of the NVRTC path.
 int ungar_b200_tape_special_info(const ungar_b200_tape* tape, int64_t* info) {
     if (!tape || !info) return tfail(UNGAR_B200_EINVAL, "null argument");
-    for (int o = 0; o < 3; ++o) {
+    for (int o = 0; o < 4; ++o) {
         const int st = tape->special[o].state.load(std::memory_order_acquire);
         info[4 * o + 0] = st;
         info[4 * o + 1] = st != 2 && tape->special[o].from_cache ? 1 : 0;  // (a worker may still be writing these)
@@ -1059,10 +1184,14 @@ int ungar_b200_tape_sparse_jacobian(ungar_b200_tape* tape, const double* x, int6
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
     Staged s;
     if (int rc = stage_in(*tape, x, batch, ld_x, vals, ld_vals, nnz, mem, stream, s)) return rc;
-    const ub::tape::Seeds seeds{0, static_cast<const int*>(tape->d_color.ptr), nullptr, nullptr};
-    if (int rc = launch<1>(*tape, seeds, s.d_x, s.ld_x, batch, tape->n_colors, s.d_out, s.ld_out, static_cast<const int*>(tape->d_jac_slot.ptr),
-                           nullptr, stream))
-        return rc;
+    int served = 0;  // a scalar function with many colours: the whole gradient in one reverse sweep per vector (from the second call on)
+    if (int rc = launch_reverse(*tape, s.d_x, s.ld_x, batch, s.d_out, s.ld_out, int(nnz), stream, served)) return rc;
+    if (!served) {
+        const ub::tape::Seeds seeds{0, static_cast<const int*>(tape->d_color.ptr), nullptr, nullptr};
+        if (int rc = launch<1>(*tape, seeds, s.d_x, s.ld_x, batch, tape->n_colors, s.d_out, s.ld_out, static_cast<const int*>(tape->d_jac_slot.ptr),
+                               nullptr, stream))
+            return rc;
+    }
     return stage_out(s, vals, ld_vals, nnz, batch, mem, stream);
 }
 
